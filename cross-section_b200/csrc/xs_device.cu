@@ -1,0 +1,799 @@
+// xs_device.cu — sm_100a kernels + the C ABI of libxs3d_b200.so (include/xs3d_b200.h).
+//
+// Kernels
+//   ingest_f16_kernel / ingest_generic_kernel : uint8 volume -> 2x2x2 occupancy bytes ("cubes"),
+//        the only HBM-streaming kernel of the area path (reads V bytes, writes V/8).  Replaces the
+//        host-side np.asfortranarray + per-query compute_cube() loads (xs3d.hpp:26-48).
+//   area_warp_kernel  (T0): persistent, one WARP per query, whole working set in shared memory.
+//   area_block_kernel (T1/T2): persistent, one CTA per query; lattice bitmap + DFS stack ring in
+//        shared memory, everything else in a per-CTA slab in HBM.  Takes the queries T0 could not
+//        fit (and single-query calls).  T2 is the same kernel with one CTA and a worst-case slab.
+//   section_block_kernel : path B (xs3d.cross_section) for one query, sparse output.
+// No CPU implementation exists behind the ABI: without a device every call fails loudly.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <mutex>
+
+#include "xs_query.cuh"
+#include "xs_device.h"
+#include "../../include/xs3d_b200.h"
+
+using namespace xs;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                     \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess) {                                                                        \
+      char b__[512];                                                                                 \
+      snprintf(b__, sizeof(b__), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return fail(XS3D_ERR_CUDA, b__);                                                               \
+    }                                                                                                \
+  } while (0)
+#define RET(call)                   \
+  do {                              \
+    int r__ = (call);               \
+    if (r__ != XS3D_OK) return r__; \
+  } while (0)
+
+extern "C" const char* xs3d_last_error(void) { return g_err.c_str(); }
+extern "C" int xs3d_version(void) { return 100; }
+extern "C" int xs3d_device_count(int* count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) { *count = 0; return fail(XS3D_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+  *count = n;
+  return XS3D_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ingest: uint8 voxels -> one occupancy byte per 2x2x2 block
+// ------------------------------------------------------------------------------------------------
+// Fast path: Fortran order, sx % 16 == 0, 16-byte aligned base.  Each thread turns 16 voxels x 4 rows
+// (four 16-byte streaming loads) into 8 output bytes (one 8-byte store): fully coalesced both ways.
+__device__ __forceinline__ uint32_t pair_bits(uint32_t w) {
+  // bytes (v0,v1,v2,v3) -> byte0 = [v0!=0] | [v1!=0]<<1, byte2 = [v2!=0] | [v3!=0]<<1
+  const uint32_t m = __vcmpne4(w, 0u) & 0x01010101u;
+  return (m | (m >> 7)) & 0x00030003u;
+}
+
+__global__ void __launch_bounds__(256) ingest_f16_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ cubes,
+                                                         int sx, int sy, int sz, int hx, int hy, int hz) {
+  const int gx = hx >> 3;   // groups of 8 blocks along x
+  const size_t total = (size_t)gx * hy * hz;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int xg = (int)(idx % gx);
+    const size_t t = idx / gx;
+    const int by = (int)(t % hy), bz = (int)(t / hy);
+    const int y0 = 2 * by, z0 = 2 * bz;
+    const bool y1ok = (y0 + 1) < sy, z1ok = (z0 + 1) < sz;
+    const size_t row = (size_t)sx;
+    const uint8_t* p00 = img + (size_t)16 * xg + row * ((size_t)y0 + (size_t)sy * z0);
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    const uint4 a = __ldcs(reinterpret_cast<const uint4*>(p00));
+    const uint4 b = y1ok ? __ldcs(reinterpret_cast<const uint4*>(p00 + row)) : zero;
+    const uint4 c = z1ok ? __ldcs(reinterpret_cast<const uint4*>(p00 + row * sy)) : zero;
+    const uint4 d = (y1ok && z1ok) ? __ldcs(reinterpret_cast<const uint4*>(p00 + row * sy + row)) : zero;
+    uint32_t o[4];
+    const uint32_t aw[4] = { a.x, a.y, a.z, a.w }, bw[4] = { b.x, b.y, b.z, b.w };
+    const uint32_t cw[4] = { c.x, c.y, c.z, c.w }, dw[4] = { d.x, d.y, d.z, d.w };
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint32_t q = pair_bits(aw[i]) | (pair_bits(bw[i]) << 2) | (pair_bits(cw[i]) << 4) | (pair_bits(dw[i]) << 6);
+      o[i] = (q & 0xffu) | ((q >> 8) & 0xff00u);   // two cube bytes
+    }
+    uint2 out;
+    out.x = o[0] | (o[1] << 16);
+    out.y = o[2] | (o[3] << 16);
+    *reinterpret_cast<uint2*>(cubes + (size_t)8 * xg + (size_t)hx * ((size_t)by + (size_t)hy * bz)) = out;
+  }
+}
+
+// Generic path: any size / alignment / memory order, one thread per output byte.
+// ZFAST selects the thread->block mapping that keeps reads contiguous for C-ordered input.
+template <bool ZFAST>
+__global__ void __launch_bounds__(256) ingest_generic_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ cubes,
+                                                             int sx, int sy, int sz, int hx, int hy, int hz,
+                                                             long long stx, long long sty, long long stz) {
+  const size_t total = (size_t)hx * hy * hz;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    int bx, by, bz;
+    if (ZFAST) { bz = (int)(idx % hz); const size_t t = idx / hz; by = (int)(t % hy); bx = (int)(t / hy); }
+    else { bx = (int)(idx % hx); const size_t t = idx / hx; by = (int)(t % hy); bz = (int)(t / hy); }
+    uint32_t m = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const int x = 2 * bx + (b & 1), y = 2 * by + ((b >> 1) & 1), z = 2 * bz + (b >> 2);
+      if (x < sx && y < sy && z < sz && __ldg(img + (long long)x * stx + (long long)y * sty + (long long)z * stz)) m |= 1u << b;
+    }
+    cubes[(size_t)bx + (size_t)hx * ((size_t)by + (size_t)hy * bz)] = (uint8_t)m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// T0: one warp per query, shared-memory arena
+// ------------------------------------------------------------------------------------------------
+template <int TILES, int MAXN, int HCAP, int MAXM>
+struct WarpLayout {
+  static constexpr int W = TILES * 32;
+  static constexpr int STRIDE = TILES + 1;
+  static constexpr int O_BITS = 0;
+  static constexpr int O_TESTED = O_BITS + W * STRIDE;
+  static constexpr int O_ORDER = O_TESTED + 4;
+  static constexpr int O_STACK = O_ORDER + MAXN;
+  static constexpr int O_HTAG = O_STACK + MAXN;
+  static constexpr int O_HKEY = O_HTAG + HCAP;
+  static constexpr int O_ITEMS = O_HKEY + HCAP;
+  static constexpr int O_CTL = O_ITEMS + MAXM;
+  static constexpr int WORDS = O_CTL + 32;
+  static_assert(TILES * TILES <= 128, "tested bitmask");
+  static_assert(MAXM <= 2 * HCAP, "vals alias the hash");
+  static_assert(sizeof(Ctl) <= 30 * 4, "ctl slot");
+};
+
+struct BatchArgs {
+  VolView vol;
+  const float* pos;
+  const float* nrm;
+  float wx, wy, wz;
+  uint32_t nq;
+  float* area;
+  uint8_t* contact;
+  uint32_t* counters;        // see CNT_* below
+  unsigned long long* stats; // [0] samples [1] items [2] tiles, [4..9] warp-tier phase cycles, [10..15] CTA-tier phase cycles
+  uint32_t* list_in;         // queries to process (null: 0..nq-1)
+  uint32_t* list_out;        // queries this tier could not fit
+};
+enum { CNT_NEXT0 = 0, CNT_OVER0 = 1, CNT_NEXT1 = 2, CNT_OVER1 = 3, CNT_NEXT2 = 4, CNT_OVER2 = 5, CNT_WORDS = 8 };
+
+template <int WARPS, int TILES, int MAXN, int HCAP, int MAXM>
+__global__ void __launch_bounds__(WARPS * 32, 1) area_warp_kernel(BatchArgs a) {
+  using L = WarpLayout<TILES, MAXN, HCAP, MAXM>;
+  extern __shared__ __align__(16) uint32_t smem[];
+  uint32_t* base = smem + (threadIdx.x >> 5) * L::WORDS;
+  Arena A;
+  A.tx = A.ty = TILES; A.stride = L::STRIDE; A.halo = 0;
+  A.bits = base + L::O_BITS; A.tested = base + L::O_TESTED;
+  A.order = base + L::O_ORDER; A.max_n = MAXN;
+  A.stack = base + L::O_STACK; A.stack_cap = MAXN; A.spill = nullptr; A.mask = A.stack;
+  A.htag = base + L::O_HTAG; A.hkey = base + L::O_HKEY; A.hcap = HCAP; A.hcap_max = HCAP; A.hash_factor = 0; A.max_probe = 64;
+  int lg = 0;
+  while ((1 << lg) < HCAP) lg++;
+  A.hshift = 32 - lg;
+  A.items = base + L::O_ITEMS; A.vals = reinterpret_cast<float*>(A.htag); A.max_m = MAXM;
+  A.stage = nullptr; A.stage_cap = 0;
+  Ctl& ctl = *reinterpret_cast<Ctl*>(base + L::O_CTL);
+  float* scratch = reinterpret_cast<float*>(base + L::O_CTL + 30);
+  WarpGroup g;
+  const V3 w = mk(a.wx, a.wy, a.wz);
+  for (;;) {
+    uint32_t q = 0;
+    if (g.lane() == 0) q = atomicAdd(&a.counters[CNT_NEXT0], 1u);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= a.nq) break;
+    PlaneCtx c;
+    const V3 p = mk(__ldg(a.pos + 3 * q), __ldg(a.pos + 3 * q + 1), __ldg(a.pos + 3 * q + 2));
+    const V3 n = mk(__ldg(a.nrm + 3 * q), __ldg(a.nrm + 3 * q + 1), __ldg(a.nrm + 3 * q + 2));
+    if (!plane_init(c, a.vol, p, n, w)) {
+      if (g.lane() == 0) { a.area[q] = 0.0f; a.contact[q] = 0; }
+      continue;
+    }
+    A.ox = A.oy = c.c - 16 - 32 * (TILES / 2);
+    const int st = run_area(g, c, a.vol, A, ctl, scratch, &a.area[q], &a.contact[q]);
+    if (g.lane() == 0) {
+      if (st != Q_OK) {
+        a.list_out[atomicAdd(&a.counters[CNT_OVER0], 1u)] = q;
+      } else {
+        atomicAdd(&a.stats[0], (unsigned long long)ctl.n);
+        atomicAdd(&a.stats[1], (unsigned long long)ctl.m);
+        atomicAdd(&a.stats[2], (unsigned long long)ctl.tiles);
+        for (int i = 0; i < 6; i++) atomicAdd(&a.stats[4 + i], (unsigned long long)ctl.t[i]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// T1 / T2: one CTA per query
+// ------------------------------------------------------------------------------------------------
+struct SlabCfg {
+  char* base;            // slab of CTA b starts at base + b * stride
+  size_t stride;
+  int max_n;             // order / mask / spill capacity (words each)
+  uint32_t hcap_max;     // htag / hkey capacity
+  int max_m;             // items / vals capacity
+  size_t bits_words;     // global fallback for the lattice bitmap
+  size_t tested_words;   // global fallback for the tile-tested mask
+  int hash_factor;
+  int max_probe;
+};
+
+__host__ __device__ inline size_t slab_bytes(const SlabCfg& s) {
+  size_t words = (size_t)s.max_n * 3 + (size_t)s.hcap_max * 2 + (size_t)s.max_m * 2 + s.bits_words + s.tested_words;
+  return ((words * 4 + 255) / 256) * 256;
+}
+
+constexpr int BLK_THREADS = 512;
+constexpr int BLK_RING = 16384;          // DFS stack ring (words)
+constexpr int BLK_TESTED = 1024;         // tile mask words held in shared memory
+constexpr int BLK_CTL_WORDS = 40;            // Ctl + a few scalars
+constexpr int BLK_FIXED_WORDS = 64 + BLK_CTL_WORDS + BLK_RING + BLK_TESTED;
+
+__device__ __forceinline__ void block_arena(Arena& A, const SlabCfg& s, uint32_t* smem, int smem_bits_words, const PlaneCtx& c, const VolView& vol) {
+  char* slab = s.base + (size_t)blockIdx.x * s.stride;
+  uint32_t* p = reinterpret_cast<uint32_t*>(slab);
+  A.order = p; p += s.max_n;
+  A.mask = p; p += s.max_n;
+  A.spill = p; p += s.max_n;
+  A.htag = p; p += s.hcap_max;
+  A.hkey = p; p += s.hcap_max;
+  A.items = p; p += s.max_m;
+  A.vals = reinterpret_cast<float*>(p); p += s.max_m;
+  uint32_t* g_bits = p; p += s.bits_words;
+  uint32_t* g_tested = p;
+  A.max_n = s.max_n; A.max_m = s.max_m;
+  A.hcap = s.hcap_max; A.hcap_max = s.hcap_max; A.hash_factor = s.hash_factor; A.max_probe = s.max_probe;
+  int lg = 0;
+  while ((1u << lg) < s.hcap_max) lg++;
+  A.hshift = 32 - lg;
+  A.stack = smem + 64 + BLK_CTL_WORDS; A.stack_cap = BLK_RING;
+  A.stage = A.stack; A.stage_cap = BLK_RING;       // the ring is idle by the time the ordered sum runs
+  bbox_window(c, vol, &A.ox, &A.oy, &A.tx, &A.ty);
+  A.stride = A.tx + 1;
+  A.halo = 1;
+  const size_t words = (size_t)A.ty * 32 * A.stride;
+  A.bits = (words <= (size_t)smem_bits_words) ? (smem + BLK_FIXED_WORDS) : g_bits;
+  A.tested = ((A.tx * A.ty + 31) / 32 <= BLK_TESTED) ? (smem + 64 + BLK_CTL_WORDS + BLK_RING) : g_tested;
+}
+
+__global__ void __launch_bounds__(BLK_THREADS, 1) area_block_kernel(BatchArgs a, SlabCfg s, int smem_bits_words, int cnt_next, int cnt_over, const uint32_t* count_ptr) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  BlockGroup g(reinterpret_cast<int*>(smem));
+  Ctl& ctl = *reinterpret_cast<Ctl*>(smem + 64);
+  static_assert(sizeof(Ctl) <= 36 * 4, "ctl slot");
+  float* scratch = reinterpret_cast<float*>(smem + 64 + 36);
+  int* next = reinterpret_cast<int*>(smem + 64 + 37);
+  const V3 w = mk(a.wx, a.wy, a.wz);
+  const uint32_t count = count_ptr ? *count_ptr : a.nq;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) *next = (int)atomicAdd(&a.counters[cnt_next], 1u);
+    __syncthreads();
+    const uint32_t i = (uint32_t)*next;
+    if (i >= count) break;
+    const uint32_t q = a.list_in ? a.list_in[i] : i;
+    PlaneCtx c;
+    const V3 p = mk(__ldg(a.pos + 3 * q), __ldg(a.pos + 3 * q + 1), __ldg(a.pos + 3 * q + 2));
+    const V3 n = mk(__ldg(a.nrm + 3 * q), __ldg(a.nrm + 3 * q + 1), __ldg(a.nrm + 3 * q + 2));
+    if (!plane_init(c, a.vol, p, n, w)) {
+      if (threadIdx.x == 0) { a.area[q] = 0.0f; a.contact[q] = 0; }
+      continue;
+    }
+    Arena A;
+    block_arena(A, s, smem, smem_bits_words, c, a.vol);
+    const size_t need_words = (size_t)A.ty * 32 * A.stride;
+    int st;
+    if (A.bits != smem + BLK_FIXED_WORDS && need_words > s.bits_words) st = Q_OVERFLOW;   // window larger than any buffer we own
+    else if (A.tested != smem + 64 + BLK_CTL_WORDS + BLK_RING && (size_t)((A.tx * A.ty + 31) / 32) > s.tested_words) st = Q_OVERFLOW;
+    else st = run_area(g, c, a.vol, A, ctl, scratch, &a.area[q], &a.contact[q]);
+    if (threadIdx.x == 0) {
+      if (st != Q_OK) {
+        a.list_out[atomicAdd(&a.counters[cnt_over], 1u)] = q;
+      } else {
+        atomicAdd(&a.stats[0], (unsigned long long)ctl.n);
+        atomicAdd(&a.stats[1], (unsigned long long)ctl.m);
+        atomicAdd(&a.stats[2], (unsigned long long)ctl.tiles);
+        for (int i = 0; i < 6; i++) atomicAdd(&a.stats[10 + i], (unsigned long long)ctl.t[i]);
+      }
+    }
+  }
+}
+
+// Path B for one query.  result[0] = status, result[1] = nnz, result[2] = contact
+__global__ void __launch_bounds__(BLK_THREADS, 1) section_block_kernel(VolView vol, V3 p, V3 n, V3 w, SlabCfg s, int smem_bits_words,
+                                                                        uint64_t* out_idx, float* out_val, uint32_t out_cap, uint32_t* result) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  BlockGroup g(reinterpret_cast<int*>(smem));
+  Ctl& ctl = *reinterpret_cast<Ctl*>(smem + 64);
+  uint8_t* ct = reinterpret_cast<uint8_t*>(smem + 64 + 36);
+  PlaneCtx c;
+  if (threadIdx.x == 0) { result[0] = Q_OK; result[1] = 0; result[2] = 0; }
+  if (!plane_init(c, vol, p, n, w)) return;
+  Arena A;
+  block_arena(A, s, smem, smem_bits_words, c, vol);
+  const size_t need_words = (size_t)A.ty * 32 * A.stride;
+  int st;
+  if (A.bits != smem + BLK_FIXED_WORDS && need_words > s.bits_words) st = Q_OVERFLOW;
+  else if (A.tested != smem + 64 + BLK_CTL_WORDS + BLK_RING && (size_t)((A.tx * A.ty + 31) / 32) > s.tested_words) st = Q_OVERFLOW;
+  else st = run_section(g, c, vol, A, ctl, out_idx, out_val, out_cap, ct);
+  __syncthreads();
+  if (threadIdx.x == 0) { result[0] = (uint32_t)st; result[1] = ctl.counter; result[2] = (st == Q_OK) ? *ct : 0u; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return XS3D_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { p = nullptr; return fail(XS3D_ERR_CUDA, std::string("cudaMalloc(") + std::to_string(want) + "): " + cudaGetErrorString(e)); }
+    cap = want;
+    return XS3D_OK;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// warp tier configuration (shared memory per warp = WarpLayout::WORDS * 4 bytes)
+constexpr int T0_WARPS = 14, T0_TILES = 3, T0_MAXN = 384, T0_HCAP = 1024, T0_MAXM = 768;
+using T0Layout = WarpLayout<T0_TILES, T0_MAXN, T0_HCAP, T0_MAXM>;
+
+struct xs3d_volume {
+  int device = 0;
+  int sx = 0, sy = 0, sz = 0, hx = 0, hy = 0, hz = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf cubes, raw;
+  bool loaded = false;
+  // labels (slice)
+  DevBuf labels;
+  int itemsize = 0, labels_c_order = 0;
+  bool labels_loaded = false;
+  // batch workspace
+  DevBuf q_pos, q_nrm, q_area, q_contact, lists, counters, slab1, slab2, sec_idx, sec_val, misc;
+  SlabCfg cfg1{}, cfg2{};
+  uint32_t* h_counters = nullptr;   // pinned: CNT_WORDS counters + 8 u64 stats
+  uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int sm_count = 0, smem_optin = 0;
+  bool kernels_configured = false;
+};
+
+static VolView view_of(const xs3d_volume* v) {
+  VolView r;
+  r.cubes = (const uint8_t*)v->cubes.p;
+  r.sx = v->sx; r.sy = v->sy; r.sz = v->sz; r.hx = v->hx; r.hy = v->hy; r.hz = v->hz;
+  return r;
+}
+
+static int block_smem_bytes(const xs3d_volume* v) { return v->smem_optin; }
+static int block_smem_bits_words(const xs3d_volume* v) { return v->smem_optin / 4 - BLK_FIXED_WORDS; }
+
+static int configure_kernels(xs3d_volume* v) {
+  if (v->kernels_configured) return XS3D_OK;
+  const int t0_bytes = T0_WARPS * T0Layout::WORDS * 4;
+  if (t0_bytes > v->smem_optin) return fail(XS3D_ERR_UNSUPPORTED, "device shared memory too small for the warp tier");
+  CK(cudaFuncSetAttribute(area_warp_kernel<T0_WARPS, T0_TILES, T0_MAXN, T0_HCAP, T0_MAXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, t0_bytes));
+  CK(cudaFuncSetAttribute(area_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
+  CK(cudaFuncSetAttribute(section_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
+  v->kernels_configured = true;
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_volume_create(int device, uint64_t sx, uint64_t sy, uint64_t sz, xs3d_volume** out) {
+  *out = nullptr;
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(XS3D_ERR_ARG, "no such CUDA device");
+  if (sx > 60000 || sy > 60000 || sz > 60000) return fail(XS3D_ERR_UNSUPPORTED, "volume side > 60000");
+  const uint64_t hx = (sx + 1) >> 1, hy = (sy + 1) >> 1, hz = (sz + 1) >> 1;
+  if (hx * hy * hz >= 0xffffffffull) return fail(XS3D_ERR_UNSUPPORTED, "volume has >= 2^32 2x2x2 blocks");
+  CK(cudaSetDevice(device));
+  xs3d_volume* v = new xs3d_volume();
+  v->device = device;
+  v->sx = (int)sx; v->sy = (int)sy; v->sz = (int)sz; v->hx = (int)hx; v->hy = (int)hy; v->hz = (int)hz;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  v->sm_count = prop.multiProcessorCount;
+  v->smem_optin = (int)prop.sharedMemPerBlockOptin;
+  CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
+  RET(v->cubes.ensure(hx * hy * hz + 64));
+  CK(cudaHostAlloc((void**)&v->h_counters, 256, cudaHostAllocDefault));
+  *out = v;
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
+  if (!v) return XS3D_OK;
+  cudaSetDevice(v->device);
+  if (v->stream) { cudaStreamSynchronize(v->stream); cudaStreamDestroy(v->stream); }
+  DevBuf* bufs[] = { &v->cubes, &v->raw, &v->labels, &v->q_pos, &v->q_nrm, &v->q_area, &v->q_contact, &v->lists,
+                     &v->counters, &v->slab1, &v->slab2, &v->sec_idx, &v->sec_val, &v->misc };
+  for (DevBuf* b : bufs) b->release();
+  if (v->h_counters) cudaFreeHost(v->h_counters);
+  delete v;
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_volume_shape(xs3d_volume* v, uint64_t shape[3]) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  shape[0] = v->sx; shape[1] = v->sy; shape[2] = v->sz;
+  return XS3D_OK;
+}
+
+static int launch_ingest(xs3d_volume* v, const uint8_t* d_img, int c_order) {
+  const size_t nblocks = (size_t)v->hx * v->hy * v->hz;
+  if (nblocks == 0) return XS3D_OK;
+  const bool fast = !c_order && (v->sx % 16 == 0) && ((uintptr_t)d_img % 16 == 0);
+  if (fast) {
+    const size_t total = nblocks / 8;
+    int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
+    ingest_f16_kernel<<<grid, 256, 0, v->stream>>>(d_img, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+  } else {
+    int grid = (int)std::min<size_t>((nblocks + 255) / 256, (size_t)v->sm_count * 32);
+    if (c_order)
+      ingest_generic_kernel<true><<<grid, 256, 0, v->stream>>>(d_img, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz,
+                                                                (long long)v->sy * v->sz, (long long)v->sz, 1ll);
+    else
+      ingest_generic_kernel<false><<<grid, 256, 0, v->stream>>>(d_img, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz,
+                                                                 1ll, (long long)v->sx, (long long)v->sx * v->sy);
+  }
+  CK(cudaGetLastError());
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_volume_load(xs3d_volume* v, const uint8_t* binimg, int mem, int c_order) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  CK(cudaSetDevice(v->device));
+  const size_t voxels = (size_t)v->sx * v->sy * v->sz;
+  if (voxels == 0) { v->loaded = true; return XS3D_OK; }
+  if (!binimg) return fail(XS3D_ERR_ARG, "null image");
+  const uint8_t* d_img = binimg;
+  if (mem == XS3D_HOST) {
+    RET(v->raw.ensure(voxels + 64));
+    CK(cudaMemcpyAsync(v->raw.p, binimg, voxels, cudaMemcpyHostToDevice, v->stream));
+    d_img = (const uint8_t*)v->raw.p;
+  }
+  RET(launch_ingest(v, d_img, c_order));
+  CK(cudaStreamSynchronize(v->stream));
+  v->loaded = true;
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_volume_cubes(xs3d_volume* v, void** device_ptr, uint64_t* bytes) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  *device_ptr = v->cubes.p;
+  *bytes = (uint64_t)v->hx * v->hy * v->hz;
+  return XS3D_OK;
+}
+extern "C" int xs3d_volume_mark_loaded(xs3d_volume* v) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  v->loaded = true;
+  return XS3D_OK;
+}
+
+// Slab sizing.  T1: moderate per-CTA slabs (one per SM).  T2: a single worst-case slab.
+static SlabCfg make_cfg(const xs3d_volume* v, bool worst_case) {
+  SlabCfg s{};
+  const long long m = std::max(v->sx, std::max(v->sy, v->sz));
+  const long long psx = 2 * 97 * m / 56 + 1;
+  const size_t win = (size_t)(psx + 2 + 64);
+  s.bits_words = ((win + 31) / 32 + 1) * (win + 32);
+  s.tested_words = (((win + 31) / 32) * ((win + 31) / 32) + 31) / 32 + 1;
+  const unsigned long long nblocks = (unsigned long long)v->hx * v->hy * v->hz;
+  if (!worst_case) {
+    s.max_n = 1 << 16;
+    s.hcap_max = 1u << 19;
+    s.max_m = 1 << 17;
+    s.hash_factor = 8;
+    s.max_probe = 256;
+  } else {
+    // the largest planar section of a box is < 1.5 * m^2 lattice cells (plus rim)
+    unsigned long long mn = (unsigned long long)(1.5 * (double)m * (double)m) + 16ull * m + 4096ull;
+    if (mn > 0x7fffffffull / 32) mn = 0x7fffffffull / 32;
+    s.max_n = (int)mn;
+    // the same table serves path A (keys = blocks) and path B (keys = voxels): never more than 27 per sample
+    const unsigned long long nvoxels = (unsigned long long)v->sx * v->sy * v->sz;
+    const unsigned long long keys = std::min<unsigned long long>(27ull * mn, nvoxels + 1);
+    const unsigned long long blocks = std::min<unsigned long long>(27ull * mn, nblocks + 1);
+    unsigned long long cap = 1024;
+    while (cap < 2 * keys) cap <<= 1;
+    s.hcap_max = (uint32_t)std::min<unsigned long long>(cap, 1ull << 31);
+    s.max_m = (int)std::min<unsigned long long>(blocks, 0x7fffffffull);
+    s.hash_factor = 64;
+    s.max_probe = 1 << 30;     // the table can never fill; the bound only turns a logic error into a loud failure
+  }
+  return s;
+}
+
+static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
+  RET(configure_kernels(v));
+  RET(v->q_pos.ensure(n * 12 + 64));
+  RET(v->q_nrm.ensure(n * 12 + 64));
+  RET(v->q_area.ensure(n * 4 + 64));
+  RET(v->q_contact.ensure(n + 64));
+  RET(v->lists.ensure(n * 4 * 3 + 64));
+  RET(v->counters.ensure(256));
+  if (!v->slab1.p) {
+    v->cfg1 = make_cfg(v, false);
+    v->cfg1.stride = slab_bytes(v->cfg1);
+    RET(v->slab1.ensure(v->cfg1.stride * (size_t)v->sm_count));
+    v->cfg1.base = (char*)v->slab1.p;
+  }
+  return XS3D_OK;
+}
+
+static int ensure_worst_case_slab(xs3d_volume* v) {
+  if (v->slab2.p) return XS3D_OK;
+  v->cfg2 = make_cfg(v, true);
+  v->cfg2.stride = slab_bytes(v->cfg2);
+  RET(v->slab2.ensure(v->cfg2.stride));
+  v->cfg2.base = (char*)v->slab2.p;
+  return XS3D_OK;
+}
+
+// Core of the batched area path; all pointers are device pointers.  skip_warp_tier: single queries go
+// straight to the CTA tier.
+static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, const float* d_nrm, const float w[3],
+                             float* d_area, uint8_t* d_contact, bool skip_warp_tier) {
+  uint32_t* d_cnt = (uint32_t*)v->counters.p;
+  unsigned long long* d_stats = (unsigned long long*)(d_cnt + CNT_WORDS);
+  uint32_t* list0 = (uint32_t*)v->lists.p;
+  uint32_t* list1 = list0 + n;
+  uint32_t* list2 = list1 + n;
+  CK(cudaMemsetAsync(d_cnt, 0, 256, v->stream));
+  BatchArgs a;
+  a.vol = view_of(v);
+  a.pos = d_pos; a.nrm = d_nrm; a.wx = w[0]; a.wy = w[1]; a.wz = w[2];
+  a.nq = (uint32_t)n; a.area = d_area; a.contact = d_contact; a.counters = d_cnt; a.stats = d_stats;
+  int launches = 0;
+  if (!skip_warp_tier) {
+    a.list_in = nullptr; a.list_out = list0;
+    const int grid = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count);
+    area_warp_kernel<T0_WARPS, T0_TILES, T0_MAXN, T0_HCAP, T0_MAXM>
+        <<<grid, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, v->stream>>>(a);
+    CK(cudaGetLastError());
+    launches++;
+    a.list_in = list0; a.list_out = list1;
+    area_block_kernel<<<v->sm_count, BLK_THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT1, CNT_OVER1, d_cnt + CNT_OVER0);
+    CK(cudaGetLastError());
+    launches++;
+  } else {
+    a.list_in = nullptr; a.list_out = list1;
+    const int grid = (int)std::min<uint64_t>(n, (uint64_t)v->sm_count);
+    area_block_kernel<<<grid, BLK_THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT1, CNT_OVER1, nullptr);
+    CK(cudaGetLastError());
+    launches++;
+  }
+  CK(cudaMemcpyAsync(v->h_counters, d_cnt, 256, cudaMemcpyDeviceToHost, v->stream));
+  CK(cudaStreamSynchronize(v->stream));
+  uint32_t over0 = v->h_counters[CNT_OVER0], over1 = v->h_counters[CNT_OVER1];
+  uint32_t over2 = 0;
+  if (over1 > 0) {
+    RET(ensure_worst_case_slab(v));
+    a.list_in = list1; a.list_out = list2;
+    area_block_kernel<<<1, BLK_THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg2, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVER1);
+    CK(cudaGetLastError());
+    launches++;
+    CK(cudaMemcpyAsync(v->h_counters, d_cnt, 256, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaStreamSynchronize(v->stream));
+    over2 = v->h_counters[CNT_OVER2];
+  }
+  const unsigned long long* hs = (const unsigned long long*)(v->h_counters + CNT_WORDS);
+  v->stats[0] = hs[0]; v->stats[1] = hs[1]; v->stats[2] = hs[2] * 1024ull;
+  v->stats[3] = over0; v->stats[4] = over1; v->stats[5] = (uint64_t)launches; v->stats[6] = over2; v->stats[7] = 0;
+  for (int i = 0; i < 12; i++) v->prof[i] = hs[4 + i];
+  if (over2 > 0) return fail(XS3D_ERR_CAPACITY, "a query exceeded the worst-case working set");
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_area_batch(xs3d_volume* v, uint64_t n, const float* pos, const float* normal, const float anisotropy[3],
+                               int mem, float* area, uint8_t* contact) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (!v->loaded) return fail(XS3D_ERR_ARG, "volume has no image loaded");
+  if (n == 0) return XS3D_OK;
+  if (n >= 0x7fffffffull) return fail(XS3D_ERR_ARG, "too many queries in one batch");
+  if (!pos || !normal || !anisotropy || !area || !contact) return fail(XS3D_ERR_ARG, "null argument");
+  CK(cudaSetDevice(v->device));
+  if ((size_t)v->sx * v->sy * v->sz == 0) {
+    if (mem == XS3D_HOST) { memset(area, 0, n * 4); memset(contact, 0, n); }
+    else { CK(cudaMemsetAsync(area, 0, n * 4, v->stream)); CK(cudaMemsetAsync(contact, 0, n, v->stream)); CK(cudaStreamSynchronize(v->stream)); }
+    return XS3D_OK;
+  }
+  RET(ensure_batch_workspace(v, n));
+  const float* d_pos = pos; const float* d_nrm = normal;
+  float* d_area = area; uint8_t* d_contact = contact;
+  if (mem == XS3D_HOST) {
+    CK(cudaMemcpyAsync(v->q_pos.p, pos, n * 12, cudaMemcpyHostToDevice, v->stream));
+    CK(cudaMemcpyAsync(v->q_nrm.p, normal, n * 12, cudaMemcpyHostToDevice, v->stream));
+    d_pos = (const float*)v->q_pos.p; d_nrm = (const float*)v->q_nrm.p;
+    d_area = (float*)v->q_area.p; d_contact = (uint8_t*)v->q_contact.p;
+  }
+  RET(area_batch_device(v, n, d_pos, d_nrm, anisotropy, d_area, d_contact, n < 4));
+  if (mem == XS3D_HOST) {
+    CK(cudaMemcpyAsync(area, d_area, n * 4, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaMemcpyAsync(contact, d_contact, n, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaStreamSynchronize(v->stream));
+  }
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_volume_stats(xs3d_volume* v, uint64_t stats[8]) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  for (int i = 0; i < 8; i++) stats[i] = v->stats[i];
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_volume_profile(xs3d_volume* v, uint64_t prof[12]) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  for (int i = 0; i < 12; i++) prof[i] = v->prof[i];
+  return XS3D_OK;
+}
+
+// ---- path B ----------------------------------------------------------------------------------------
+static int section_fast_sparse(xs3d_volume* v, const float p[3], const float n[3], const float w[3],
+                               uint64_t** d_idx, float** d_val, uint64_t* nnz, uint8_t* contact) {
+  RET(configure_kernels(v));
+  RET(ensure_worst_case_slab(v));
+  RET(v->counters.ensure(256));
+  // output capacity: every sample can introduce at most 27 voxels, bounded by the volume
+  const unsigned long long voxels = (unsigned long long)v->sx * v->sy * v->sz;
+  unsigned long long cap = std::min<unsigned long long>(27ull * (unsigned long long)v->cfg2.max_n, voxels);
+  cap = std::min<unsigned long long>(cap, 0x7fffffffull);
+  if (voxels >= 0xffffffffull) return fail(XS3D_ERR_UNSUPPORTED, "cross_section on volumes with >= 2^32 voxels");
+  RET(v->sec_idx.ensure(cap * 8 + 64));
+  RET(v->sec_val.ensure(cap * 4 + 64));
+  SlabCfg s = v->cfg2;
+  s.hash_factor = 32;   // >= 27 voxels per sample: the dedupe set can never fill
+  // the voxel set may need more slots than the block table: clamp to what the slab holds (htag+hkey are contiguous)
+  s.hcap_max = v->cfg2.hcap_max;
+  uint32_t* d_res = (uint32_t*)v->counters.p + 44;
+  section_block_kernel<<<1, BLK_THREADS, block_smem_bytes(v), v->stream>>>(view_of(v), mk(p[0], p[1], p[2]), mk(n[0], n[1], n[2]), mk(w[0], w[1], w[2]),
+                                                                            s, block_smem_bits_words(v), (uint64_t*)v->sec_idx.p, (float*)v->sec_val.p,
+                                                                            (uint32_t)cap, d_res);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(v->h_counters, d_res, 16, cudaMemcpyDeviceToHost, v->stream));
+  CK(cudaStreamSynchronize(v->stream));
+  if (v->h_counters[0] != Q_OK) return fail(XS3D_ERR_CAPACITY, "cross_section exceeded the worst-case working set");
+  *nnz = v->h_counters[1];
+  *contact = (uint8_t)v->h_counters[2];
+  *d_idx = (uint64_t*)v->sec_idx.p;
+  *d_val = (float*)v->sec_val.p;
+  return XS3D_OK;
+}
+
+int xs_section_slow_sparse(xs3d_volume* v, const float p[3], const float n[3], const float w[3], int method,
+                           uint64_t** d_idx, float** d_val, uint64_t* nnz, uint8_t* contact);   // xs_slow.cu
+int xs_area_slow(xs3d_volume* v, const float p[3], const float n[3], const float w[3], float* area, uint8_t* contact);   // xs_slow.cu
+
+extern "C" int xs3d_section_sparse(xs3d_volume* v, const float pos[3], const float normal[3], const float anisotropy[3],
+                                   int method, uint64_t* idx, float* val, uint64_t cap, uint64_t* nnz, uint8_t* contact) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (!v->loaded) return fail(XS3D_ERR_ARG, "volume has no image loaded");
+  CK(cudaSetDevice(v->device));
+  *nnz = 0; *contact = 0;
+  if ((size_t)v->sx * v->sy * v->sz == 0) return XS3D_OK;
+  uint64_t* d_idx = nullptr; float* d_val = nullptr;
+  if (method == 0) RET(section_fast_sparse(v, pos, normal, anisotropy, &d_idx, &d_val, nnz, contact));
+  else RET(xs_section_slow_sparse(v, pos, normal, anisotropy, method, &d_idx, &d_val, nnz, contact));
+  if (*nnz > cap) return fail(XS3D_ERR_ARG, "sparse output buffers too small (nnz returned)");
+  if (*nnz) {
+    CK(cudaMemcpyAsync(idx, d_idx, *nnz * 8, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaMemcpyAsync(val, d_val, *nnz * 4, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaStreamSynchronize(v->stream));
+  }
+  return XS3D_OK;
+}
+
+// ---- process-wide default volume backing the drop-in single-call entry points ------------------------
+static std::mutex g_mu;
+static xs3d_volume* g_default = nullptr;   // last image seen by a single-call entry point
+static bool g_persistent_image = false;    // set by xs3d_set_shape_image
+
+static int default_volume(uint64_t sx, uint64_t sy, uint64_t sz, xs3d_volume** out) {
+  if (g_default && ((uint64_t)g_default->sx != sx || (uint64_t)g_default->sy != sy || (uint64_t)g_default->sz != sz)) {
+    xs3d_volume_destroy(g_default);
+    g_default = nullptr;
+    g_persistent_image = false;
+  }
+  if (!g_default) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    RET(xs3d_volume_create(dev, sx, sy, sz, &g_default));
+  }
+  *out = g_default;
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_set_shape(uint64_t, uint64_t, uint64_t) { return XS3D_OK; }
+extern "C" int xs3d_set_shape_image(const uint8_t* binimg, uint64_t sx, uint64_t sy, uint64_t sz, int c_order) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  xs3d_volume* v;
+  RET(default_volume(sx, sy, sz, &v));
+  RET(xs3d_volume_load(v, binimg, XS3D_HOST, c_order));
+  g_persistent_image = true;
+  return XS3D_OK;
+}
+extern "C" int xs3d_clear_shape(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_default) xs3d_volume_destroy(g_default);
+  g_default = nullptr;
+  g_persistent_image = false;
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_area(const uint8_t* binimg, uint64_t sx, uint64_t sy, uint64_t sz, const float pos[3], const float normal[3],
+                         const float anisotropy[3], int slow_method, int use_persistent_data, float* area, uint8_t* contact) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  *area = 0.0f; *contact = 0;
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) return fail(XS3D_ERR_CUDA, "no CUDA device");
+  if (sx * sy * sz == 0) return XS3D_OK;
+  xs3d_volume* v;
+  RET(default_volume(sx, sy, sz, &v));
+  if (!(use_persistent_data && g_persistent_image && v->loaded)) {
+    RET(xs3d_volume_load(v, binimg, XS3D_HOST, 0));
+    g_persistent_image = false;
+  }
+  if (slow_method) return xs_area_slow(v, pos, normal, anisotropy, area, contact);
+  return xs3d_area_batch(v, 1, pos, normal, anisotropy, XS3D_HOST, area, contact);
+}
+
+extern "C" int xs3d_section(const uint8_t* binimg, uint64_t sx, uint64_t sy, uint64_t sz, const float pos[3], const float normal[3],
+                            const float anisotropy[3], int method, float* out, uint8_t* contact) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  *contact = 0;
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) return fail(XS3D_ERR_CUDA, "no CUDA device");
+  if (sx * sy * sz == 0) return XS3D_OK;
+  xs3d_volume* v;
+  RET(default_volume(sx, sy, sz, &v));
+  RET(xs3d_volume_load(v, binimg, XS3D_HOST, 0));
+  g_persistent_image = false;
+  uint64_t* d_idx = nullptr; float* d_val = nullptr; uint64_t nnz = 0;
+  if (method == 0) RET(section_fast_sparse(v, pos, normal, anisotropy, &d_idx, &d_val, &nnz, contact));
+  else RET(xs_section_slow_sparse(v, pos, normal, anisotropy, method, &d_idx, &d_val, &nnz, contact));
+  if (nnz) {
+    std::vector<uint64_t> idx(nnz);
+    std::vector<float> val(nnz);
+    CK(cudaMemcpyAsync(idx.data(), d_idx, nnz * 8, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaMemcpyAsync(val.data(), d_val, nnz * 4, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaStreamSynchronize(v->stream));
+    for (uint64_t i = 0; i < nnz; i++) out[idx[i]] = val[i];   // scatter into the caller's zero-filled image
+  }
+  return XS3D_OK;
+}
+
+// accessors for the other translation units
+xs::VolView xs_view(const xs3d_volume* v) { return view_of(v); }
+cudaStream_t xs_stream(const xs3d_volume* v) { return v->stream; }
+int xs_sm_count(const xs3d_volume* v) { return v->sm_count; }
+int xs_fail(int code, const char* msg) { return fail(code, msg); }
+int xs_buf(xs3d_volume* v, int which, size_t bytes, void** p) {
+  DevBuf* b = which == 0 ? &v->sec_idx : (which == 1 ? &v->sec_val : (which == 2 ? &v->misc : &v->counters));
+  int r = b->ensure(bytes);
+  *p = b->p;
+  return r;
+}
+uint32_t* xs_pinned(xs3d_volume* v) { return v->h_counters; }
+int xs_default_volume(uint64_t sx, uint64_t sy, uint64_t sz, xs3d_volume** out) {
+  return default_volume(sx, sy, sz, out);
+}
+std::mutex& xs_mutex() { return g_mu; }
+void xs_labels(xs3d_volume* v, void** p, int* itemsize, int* c_order, bool* loaded) {
+  *p = v->labels.p; *itemsize = v->itemsize; *c_order = v->labels_c_order; *loaded = v->labels_loaded;
+}
+int xs_labels_set(xs3d_volume* v, const void* labels, int itemsize, int mem, int c_order) {
+  const size_t bytes = (size_t)v->sx * v->sy * v->sz * (size_t)itemsize;
+  v->itemsize = itemsize; v->labels_c_order = c_order;
+  if (bytes == 0) { v->labels_loaded = true; return XS3D_OK; }
+  RET(v->labels.ensure(bytes + 64));
+  CK(cudaMemcpyAsync(v->labels.p, labels, bytes, mem == XS3D_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, v->stream));
+  CK(cudaStreamSynchronize(v->stream));
+  v->labels_loaded = true;
+  return XS3D_OK;
+}

@@ -1,0 +1,213 @@
+// xs_geom.cuh — plane ∩ cube polygon, polygon area, 2x2x2 block value and block adjacency.
+//
+// Behavioural spec: SURVEY.md Appendix A.  Reference functions replaced (file:line in /root/reference/src):
+//   plane_cube_points<1>  <- check_intersections_1x1x1   xs3d.hpp:238-359
+//   plane_cube_points<2>  <- check_intersections_2x2x2   xs3d.hpp:102-236
+//   polygon_area          <- xs3d::area::points_to_area   area.hpp:211-228 (+ :14-24, :37-52, :68-143, :147-207)
+//   block_value           <- calc_area_at_point_2x2x2     xs3d.hpp:361-440
+//   blocks_adjacent       <- is_26_connected              xs3d.hpp:537-646
+#pragma once
+#include "xs_math.cuh"
+
+namespace xs {
+
+// float32 constants after the reference's C++ promotion rules
+#define XS_EPS 1.99999994947575032711029052734375e-05f      /* 0x37a7c5ac : constexpr float epsilon = 2e-5 */
+#define XS_FAR1 0.866045415401458740234375f                  /* 0x3f5db527 : float(1.7320508076/2 + eps)   */
+#define XS_FAR2 1.73207080364227294921875f                   /* 0x3fddb47f : float(1.7320508076 + eps)     */
+#define XS_BOUND1 0.500020027160644531250f                   /* 0x3f000150 : float(0.5 + eps)              */
+#define XS_BOUND2 1.00002002716064453125f                    /* 0x3f8000a8 : 1.0f + eps                    */
+#define XS_TMAX2 2.0000200271606445312500f                   /* 0x40000054 : 2.0f + eps                    */
+
+struct PlaneGeom {
+  V3 pos;      // plane point (unrounded query vertex)
+  V3 n;        // unit normal (float32-normalised once)
+  V3 w;        // anisotropy
+  float inv[3];  // 1/n[a], 0 where n[a]==0   (xs3d.hpp:859-864)
+  int max_pts;   // 4 if the normal has a zero component else 6 (xs3d.hpp:299-301)
+};
+
+XS_HD void geom_init(PlaneGeom& g, V3 pos, V3 unit_n, V3 w) {
+  g.pos = pos; g.n = unit_n; g.w = w;
+  g.inv[0] = (unit_n.x == 0.0f) ? 0.0f : fdiv(1.0f, unit_n.x);   // 1.0/p in double then narrowed == 1.0f/p
+  g.inv[1] = (unit_n.y == 0.0f) ? 0.0f : fdiv(1.0f, unit_n.y);
+  g.inv[2] = (unit_n.z == 0.0f) ? 0.0f : fdiv(1.0f, unit_n.z);
+  g.max_pts = ((unit_n.x == 0.0f) + (unit_n.y == 0.0f) + (unit_n.z == 0.0f)) >= 1 ? 4 : 6;
+}
+
+// Intersect the plane with the 12 edges of the cube of side S whose low voxel is (x,y,z)
+// (S=1: the voxel itself, spanning [x-.5,x+.5]; S=2: the block spanning [x-.5,x+1.5]).
+template <int S>
+XS_HD int plane_cube_points(float x, float y, float z, const PlaneGeom& g, V3* pts) {
+  const float fS = (float)S;
+  const V3 low = mk(x, y, z);
+  const V3 centre = (S == 1) ? low : vadd(low, mk(0.5f, 0.5f, 0.5f));
+  const float dist = fabsf(vdot(vsub(centre, g.pos), g.n));
+  if (dist > (S == 1 ? XS_FAR1 : XS_FAR2)) return 0;
+
+  const V3 minpt = vadd(low, mk(-0.5f, -0.5f, -0.5f));
+  const V3 rel = vsub(g.pos, minpt);
+  // the four alternating corners (0,0,0) (0,S,S) (S,0,S) (S,S,0): each edge touches exactly one
+  float cproj[4];
+  cproj[0] = vdot(rel, g.n);   // rel - (0,0,0) is exact
+  cproj[1] = vdot(vsub(rel, mk(0.0f, fS, fS)), g.n);
+  cproj[2] = vdot(vsub(rel, mk(fS, 0.0f, fS)), g.n);
+  cproj[3] = vdot(vsub(rel, mk(fS, fS, 0.0f)), g.n);
+
+  const float bound = (S == 1) ? XS_BOUND1 : XS_BOUND2;
+  const float tmax = (S == 1) ? XS_BOUND2 : XS_TMAX2;   // 1+eps / 2+eps
+  int np = 0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    const int k = i & 3, a = i >> 2;
+    const float proj = cproj[k];
+    V3 c = mk((k >= 2) ? fS : 0.0f, (k == 1 || k == 3) ? fS : 0.0f, (k == 1 || k == 2) ? fS : 0.0f);
+    c = vadd(c, minpt);
+    if (proj == 0.0f) {
+      if (i < 4) {
+        bool dup = false;
+        for (int j = 0; j < np; j++) dup = dup || vclose(pts[j], c);
+        if (!dup) pts[np++] = c;
+      }
+      continue;
+    }
+    const float na = (a == 0) ? g.n.x : (a == 1 ? g.n.y : g.n.z);
+    if (na == 0.0f) continue;
+    const float t = fmul(proj, g.inv[a]);
+    const float at = fabsf(t);
+    if (at > tmax) continue;
+    V3 hit = c;
+    if (a == 0) hit.x = fadd(c.x, t);
+    else if (a == 1) hit.y = fadd(c.y, t);
+    else hit.z = fadd(c.z, t);
+    if (fabsf(fsub(hit.x, centre.x)) >= bound) continue;
+    if (fabsf(fsub(hit.y, centre.y)) >= bound) continue;
+    if (fabsf(fsub(hit.z, centre.z)) >= bound) continue;
+    const bool oncorner = (at < XS_EPS) || (fabsf(fsub(at, fS)) < XS_EPS);
+    bool dup = false;
+    if (oncorner) {
+      for (int j = 0; j < np; j++) dup = dup || vclose(pts[j], hit);
+    }
+    if (!dup) {
+      pts[np++] = hit;
+      if (np >= g.max_pts) break;
+    }
+  }
+  return np;
+}
+
+XS_HD void cswap(float* key, V3* v, int a, int b) {
+  if (key[a] > key[b]) {
+    float tk = key[a]; key[a] = key[b]; key[b] = tk;
+    V3 tv = v[a]; v[a] = v[b]; v[b] = tv;
+  }
+}
+
+// Anisotropy-scaled area of the convex polygon with vertices pts[0..np) lying in the plane.
+XS_HD float polygon_area(const V3* pts, int np, const PlaneGeom& g) {
+  if (np < 3) return 0.0f;
+  if (np == 3) {
+    V3 a = vmul(vsub(pts[1], pts[0]), g.w), b = vmul(vsub(pts[2], pts[0]), g.w);
+    return fmul(vnorm(vcross(a, b)), 0.5f);
+  }
+  V3 cen = mk(0.0f, 0.0f, 0.0f);
+  for (int i = 0; i < np; i++) cen = vadd(cen, pts[i]);
+  cen = vdivs(cen, (float)np);
+  V3 sp[6];
+  float key[6];
+  for (int i = 0; i < 6; i++) {
+    if (i < np) sp[i] = vsub(pts[i], cen);
+  }
+  const V3 prime = vdivs(sp[0], vnorm(sp[0]));
+  V3 basis = vcross(prime, g.n);
+  basis = vdivs(basis, vnorm(basis));
+  for (int i = 0; i < 6; i++) {
+    if (i < np) {
+      float c = fdiv(vdot(sp[i], prime), vnorm(sp[i]));
+      key[i] = (vdot(sp[i], basis) < 0.0f) ? fsub(c, 1.0f) : fsub(1.0f, c);
+    }
+  }
+  // fixed comparator networks of area.hpp:68-143 (strict >, so ties keep their order)
+  if (np == 4) {
+    cswap(key, sp, 0, 2); cswap(key, sp, 1, 3); cswap(key, sp, 0, 1); cswap(key, sp, 2, 3); cswap(key, sp, 1, 2);
+  } else if (np == 5) {
+    cswap(key, sp, 0, 3); cswap(key, sp, 1, 4); cswap(key, sp, 0, 2); cswap(key, sp, 1, 3); cswap(key, sp, 0, 1);
+    cswap(key, sp, 2, 4); cswap(key, sp, 1, 2); cswap(key, sp, 3, 4); cswap(key, sp, 2, 3);
+  } else {
+    cswap(key, sp, 0, 5); cswap(key, sp, 1, 3); cswap(key, sp, 2, 4); cswap(key, sp, 1, 2); cswap(key, sp, 3, 4);
+    cswap(key, sp, 0, 3); cswap(key, sp, 2, 5); cswap(key, sp, 0, 1); cswap(key, sp, 2, 3); cswap(key, sp, 4, 5);
+    cswap(key, sp, 1, 2); cswap(key, sp, 3, 4);
+  }
+  for (int i = 0; i < 6; i++) {
+    if (i < np) sp[i] = vmul(sp[i], g.w);
+  }
+  float area = 0.0f;
+  for (int i = 0; i < 5; i++) {
+    if (i + 1 < np) area = fadd(area, vnorm(vcross(sp[i], sp[i + 1])));
+  }
+  area = fadd(area, vnorm(vcross(sp[0], sp[np - 1])));
+  return fmul(area, 0.5f);
+}
+
+XS_HD float voxel_area(float x, float y, float z, const PlaneGeom& g) {
+  V3 pts[7];
+  int np = plane_cube_points<1>(x, y, z, g, pts);
+  return polygon_area(pts, np, g);
+}
+
+// Value of the 2x2x2 block with low (even) voxel (bx,by,bz) and occupancy mask `cube`
+// (bit = dx + 2dy + 4dz): block polygon minus absent voxels when >=5 voxels are set,
+// else the sum of the present voxels, always in ascending bit order.
+XS_HD float block_value(uint32_t cube, float bx, float by, float bz, const PlaneGeom& g) {
+  const V3 centre = vadd(mk(bx, by, bz), mk(0.5f, 0.5f, 0.5f));
+  if (fabsf(vdot(vsub(centre, g.pos), g.n)) > XS_FAR2) return 0.0f;
+  float area = 0.0f;
+#ifdef __CUDA_ARCH__
+  const int pop = __popc(cube & 0xffu);
+#else
+  const int pop = __builtin_popcount(cube & 0xffu);
+#endif
+  if (pop >= 5) {
+    V3 pts[7];
+    int np = plane_cube_points<2>(bx, by, bz, g, pts);
+    area = polygon_area(pts, np, g);
+    if (area == 0.0f) return area;
+    for (int b = 0; b < 8; b++) {
+      if (!((cube >> b) & 1u))
+        area = fsub(area, voxel_area(fadd(bx, (float)(b & 1)), fadd(by, (float)((b >> 1) & 1)), fadd(bz, (float)(b >> 2)), g));
+    }
+  } else {
+    for (int b = 0; b < 8; b++) {
+      if ((cube >> b) & 1u)
+        area = fadd(area, voxel_area(fadd(bx, (float)(b & 1)), fadd(by, (float)((b >> 1) & 1)), fadd(bz, (float)(b >> 2)), g));
+    }
+  }
+  return area;
+}
+
+// Face masks of a block: voxels with coordinate a == v, as bits dx + 2dy + 4dz.
+XS_HD uint32_t face_mask(int ox, int oy, int oz, bool candidate_side) {
+  // centre side: o<0 -> coordinate 0, o>0 -> coordinate 1; candidate side is the opposite face
+  uint32_t m = 0xffu;
+  const uint32_t X0 = 0x55u, X1 = 0xaau, Y0 = 0x33u, Y1 = 0xccu, Z0 = 0x0fu, Z1 = 0xf0u;
+  if (ox < 0) m &= candidate_side ? X1 : X0;
+  if (ox > 0) m &= candidate_side ? X0 : X1;
+  if (oy < 0) m &= candidate_side ? Y1 : Y0;
+  if (oy > 0) m &= candidate_side ? Y0 : Y1;
+  if (oz < 0) m &= candidate_side ? Z1 : Z0;
+  if (oz > 0) m &= candidate_side ? Z0 : Z1;
+  return m;
+}
+
+// Two neighbouring blocks count as connected when each has a set voxel on the side facing the
+// other.  One entry of the reference's table deviates from that rule and is reproduced:
+// o = (-,+,0) uses the centre mask 0b01000010 (xs3d.hpp:569).
+XS_HD bool blocks_adjacent(uint32_t centre, uint32_t cand, int ox, int oy, int oz) {
+  if ((ox | oy | oz) == 0) return true;
+  uint32_t cm = face_mask(ox, oy, oz, false);
+  const uint32_t km = face_mask(ox, oy, oz, true);
+  if (ox < 0 && oy > 0 && oz == 0) cm = 0x42u;
+  return ((cand & km) != 0u) && ((centre & cm) != 0u);
+}
+
+}  // namespace xs

@@ -1,0 +1,767 @@
+// xs_query.cuh — one cross-section query, cooperatively executed by a thread group.
+//
+// Replaces (file:line in /root/reference/src): cross_sectional_area xs3d.hpp:1305-1365,
+// cross_sectional_area_helper_2x2x2 :809-961, robust_calc_area_at_point_2x2x2 :648-726,
+// cross_section :1367-1426, cross_sectional_area_helper :1118-1268, calc_area_at_point :442-535.
+//
+// The reference fuses everything into one sequential flood fill.  Here the query is decomposed
+//  so that only a bitmap walk is sequential:
+//   1. lattice tiles   : the plane lattice (basis b1,b2, unit spacing, centred on the vertex) is
+//                        sampled in 32x32-cell tiles ON DEMAND into a foreground bitmap (one ballot
+//                        per lattice row) — work scales with the section, not with the volume;
+//   2. component + rank: thread 0 walks the bitmap depth-first from the centre cell with the
+//                        reference's neighbour priority; the walk both delimits the 8-connected
+//                        component and yields its DFS preorder (`order[]`);
+//   3. claims          : every sample claims the <=27 neighbouring 2x2x2 blocks whose probe voxel
+//                        is set, atomicMin of (rank,k) into a hash table keyed by block id —
+//                        "first touch wins" without the sequential visit;
+//   4. ownership/items : owners are compacted, in (rank,k) order, into an item list;
+//   5. evaluate        : one item per thread: adjacency test + plane∩block polygon value;
+//   6. ordered sum     : float32 sum per sample in k order, then over samples in rank order.
+// Path B (cross_section) shares 1-2 and replaces 3-6 by a per-voxel dedupe + polygon pass.
+//
+// Volume layout ("cubes"): one byte per 2x2x2 block = the reference's compute_cube() mask
+// (xs3d.hpp:26-48), bit = dx + 2dy + 4dz, out-of-volume voxels 0; x fastest.  A voxel test and a
+// block-mask fetch are both ONE byte load, and a 512^3 volume is 16 MiB — L2 resident.
+#pragma once
+#include "xs_geom.cuh"
+
+namespace xs {
+
+struct VolView {
+  const uint8_t* cubes;
+  int sx, sy, sz;   // voxels
+  int hx, hy, hz;   // blocks = ceil(s/2)
+};
+
+XS_HD uint32_t cube_at(const VolView& v, int bx, int by, int bz) {
+#ifdef __CUDA_ARCH__
+  return __ldg(v.cubes + ((size_t)bx + (size_t)v.hx * ((size_t)by + (size_t)v.hy * (size_t)bz)));
+#else
+  return v.cubes[(size_t)bx + (size_t)v.hx * ((size_t)by + (size_t)v.hy * (size_t)bz)];
+#endif
+}
+XS_HD bool vox_fg(const VolView& v, int x, int y, int z) {
+  const uint32_t c = cube_at(v, x >> 1, y >> 1, z >> 1);
+  return (c >> ((x & 1) | ((y & 1) << 1) | ((z & 1) << 2))) & 1u;
+}
+
+struct PlaneCtx {
+  PlaneGeom g;
+  V3 b1, b2;        // lattice basis (xs3d.hpp:831-838)
+  float lim[3];     // float(s) - 0.5           (xs3d.hpp:866-868)
+  float hi[3];      // s - 1.5 (exact in float) (xs3d.hpp:910,912,914)
+  int psx, c;       // lattice side, centre index (xs3d.hpp:823,840)
+  int axis_aligned;
+};
+
+// Seed validation + per-query constants.  Returns false when the reference returns (0, 0)
+// (xs3d.hpp:1315-1345): vertex outside the volume or on background.
+XS_HD bool plane_init(PlaneCtx& c, const VolView& v, V3 pos, V3 nraw, V3 w) {
+  if (v.sx <= 0 || v.sy <= 0 || v.sz <= 0) return false;
+  if (!(pos.x >= 0.0f) || pos.x >= (float)v.sx) return false;
+  if (!(pos.y >= 0.0f) || pos.y >= (float)v.sy) return false;
+  if (!(pos.z >= 0.0f) || pos.z >= (float)v.sz) return false;
+  const V3 r = vround(pos);
+  if (r.x >= (float)v.sx || r.y >= (float)v.sy || r.z >= (float)v.sz) return false;
+  if (!vox_fg(v, (int)r.x, (int)r.y, (int)r.z)) return false;
+  const V3 n = vdivs(nraw, vnorm(nraw));
+  geom_init(c.g, pos, n, w);
+  int m = v.sx > v.sy ? v.sx : v.sy;
+  if (v.sz > m) m = v.sz;
+  c.psx = (int)((2ll * 97ll * (long long)m) / 56ll + 1ll);
+  c.c = c.psx / 2;
+  V3 b1 = vcross(n, mk(1.0f, 0.0f, 0.0f));
+  if (vnull(b1)) b1 = vcross(n, mk(0.0f, 1.0f, 0.0f));
+  b1 = vdivs(b1, vnorm(b1));
+  V3 b2 = vcross(n, b1);
+  b2 = vdivs(b2, vnorm(b2));
+  c.b1 = b1; c.b2 = b2;
+  c.lim[0] = fsub((float)v.sx, 0.5f); c.lim[1] = fsub((float)v.sy, 0.5f); c.lim[2] = fsub((float)v.sz, 0.5f);
+  c.hi[0] = (float)v.sx - 1.5f; c.hi[1] = (float)v.sy - 1.5f; c.hi[2] = (float)v.sz - 1.5f;
+  c.axis_aligned = (((n.x != 0.0f) + (n.y != 0.0f) + (n.z != 0.0f)) == 1) ? 1 : 0;
+  return true;
+}
+
+// Sample point of lattice cell (i,j): (pos + b1*dx) + b2*dy with dx = float(i) - float(c) (xs3d.hpp:883-886)
+XS_HD V3 cell_point(const PlaneCtx& c, int i, int j) {
+  const float dx = fsub((float)i, (float)c.c), dy = fsub((float)j, (float)c.c);
+  return vadd(vadd(c.g.pos, vscale(c.b1, dx)), vscale(c.b2, dy));
+}
+
+// Cell is inside the volume (xs3d.hpp:888-893) and its rounded voxel is foreground (:895-907).
+// A coordinate of exactly -0.5 passes the reference's test and then rounds to -1 (UB cast);
+// such samples are treated as outside (documented divergence).
+XS_HD bool cell_fg(const PlaneCtx& c, const VolView& v, int i, int j) {
+  if (i < 0 || j < 0 || i >= c.psx || j >= c.psx) return false;
+  const V3 p = cell_point(c, i, j);
+  if (p.x < -0.5f || p.y < -0.5f || p.z < -0.5f) return false;
+  if (p.x >= c.lim[0] || p.y >= c.lim[1] || p.z >= c.lim[2]) return false;
+  if (!(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z)) return false;
+  const V3 r = vround(p);
+  if (r.x < 0.0f || r.y < 0.0f || r.z < 0.0f) return false;
+  return vox_fg(v, (int)r.x, (int)r.y, (int)r.z);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Thread-group policies.  WarpGroup: one warp per query (T0).  BlockGroup: one CTA per query (T1).
+// HostGroup: a single host thread, test builds only.
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+struct WarpGroup {
+  int lane_;
+  __device__ WarpGroup() : lane_(threadIdx.x & 31) {}
+  __device__ int tid() const { return lane_; }
+  __device__ int size() const { return 32; }
+  __device__ int lane() const { return lane_; }
+  __device__ int warp() const { return 0; }
+  __device__ int nwarps() const { return 1; }
+  __device__ void sync() const { __syncwarp(); }
+  __device__ uint32_t ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+  __device__ int exscan(int v, int& total) const {
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane_ >= d) inc += t;
+    }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+  }
+  __device__ uint32_t or_reduce(uint32_t v) const { return __reduce_or_sync(0xffffffffu, v); }
+};
+
+struct BlockGroup {
+  int* scratch;   // >= 36 ints of shared memory
+  __device__ explicit BlockGroup(int* s) : scratch(s) {}
+  __device__ int tid() const { return threadIdx.x; }
+  __device__ int size() const { return blockDim.x; }
+  __device__ int lane() const { return threadIdx.x & 31; }
+  __device__ int warp() const { return threadIdx.x >> 5; }
+  __device__ int nwarps() const { return blockDim.x >> 5; }
+  __device__ void sync() const { __syncthreads(); }
+  __device__ uint32_t ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+  __device__ int exscan(int v, int& total) const {
+    const int l = lane(), w = warp(), nw = nwarps();
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (l >= d) inc += t;
+    }
+    if (l == 31) scratch[w] = inc;
+    __syncthreads();
+    int base = 0, tot = 0;
+    for (int i = 0; i < nw; i++) {
+      int s = scratch[i];
+      if (i < w) base += s;
+      tot += s;
+    }
+    __syncthreads();
+    total = tot;
+    return base + inc - v;
+  }
+  __device__ uint32_t or_reduce(uint32_t v) const {
+    v = __reduce_or_sync(0xffffffffu, v);
+    if (threadIdx.x == 0) scratch[34] = 0;
+    __syncthreads();
+    if (lane() == 0 && v) atomicOr((unsigned int*)&scratch[34], v);
+    __syncthreads();
+    uint32_t r = (uint32_t)scratch[34];
+    __syncthreads();
+    return r;
+  }
+};
+#endif
+
+struct HostGroup {
+  int tid() const { return 0; }
+  int size() const { return 1; }
+  int lane() const { return 0; }
+  int warp() const { return 0; }
+  int nwarps() const { return 1; }
+  void sync() const {}
+  int exscan(int v, int& total) const { total = v; return 0; }
+  uint32_t or_reduce(uint32_t v) const { return v; }
+};
+
+XS_HD uint32_t atomic_cas_u32(uint32_t* p, uint32_t cmp, uint32_t val) {
+#ifdef __CUDA_ARCH__
+  return atomicCAS(p, cmp, val);
+#else
+  uint32_t old = *p;
+  if (old == cmp) *p = val;
+  return old;
+#endif
+}
+XS_HD void atomic_min_u32(uint32_t* p, uint32_t val) {
+#ifdef __CUDA_ARCH__
+  atomicMin(p, val);
+#else
+  if (val < *p) *p = val;
+#endif
+}
+XS_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t val) {
+#ifdef __CUDA_ARCH__
+  return atomicAdd(p, val);
+#else
+  uint32_t old = *p; *p = old + val; return old;
+#endif
+}
+XS_HD void atomic_or_u32(uint32_t* p, uint32_t val) {
+#ifdef __CUDA_ARCH__
+  atomicOr(p, val);
+#else
+  *p |= val;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-query working set.  Pointers may address shared memory (T0, and T1's bitmap/stack ring) or a
+// per-CTA slab in global memory (T1).
+// ------------------------------------------------------------------------------------------------
+struct Arena {
+  // lattice window: local cell (u,v) <-> lattice cell (ox+u, oy+v); tx x ty tiles of 32x32 cells
+  int ox, oy, tx, ty, stride;   // stride = tx + 1 words per row (one zero pad word)
+  uint32_t* bits;               // foreground-and-unvisited bitmap, (32*ty) rows x stride words
+  uint32_t* tested;             // one bit per tile, ceil(tx*ty/32) words
+  int halo;                     // tiles tested around a requested tile (0: just that tile)
+  // samples
+  uint32_t* order;              // rank -> u | v<<16
+  int max_n;
+  uint32_t* stack;              // DFS stack ring (depth % stack_cap) of u | v<<16
+  int stack_cap;                // power of two when `spill` is set, else >= max_n
+  uint32_t* spill;              // global backing store for the ring, or null when stack_cap >= max_n
+  uint32_t* mask;               // per-sample 27-bit candidate / ownership masks (may alias `stack`)
+  // block ownership hash (open addressing, linear probing)
+  uint32_t* htag;
+  uint32_t* hkey;
+  uint32_t hcap;                // power of two (capacity in use)
+  int hshift;                   // 32 - log2(hcap)
+  uint32_t hcap_max;            // allocated capacity; with hash_factor > 0 the capacity in use is
+  int hash_factor;              //   re-chosen per query as pow2 >= hash_factor * samples (<= hcap_max)
+  int max_probe;                // give up (-> Q_OVERFLOW) after this many probes; 0 = never
+  // items
+  uint32_t* items;              // rank<<5 | k, in (rank,k) order
+  float* vals;                  // may alias htag (dead by then)
+  int max_m;
+  // optional staging buffer for the ordered sum (shared memory), or null to read vals directly
+  uint32_t* stage;
+  int stage_cap;
+};
+
+struct Ctl {          // lives in shared memory (one per group)
+  int status;
+  int req_tx, req_ty;
+  int n;              // samples visited so far
+  int depth;          // DFS stack depth
+  int lo;             // lowest stack depth resident in the ring
+  int u, v;           // current cell
+  int m;              // items
+  int overflow;
+  uint32_t contact;
+  uint32_t counter;   // generic atomic counter (path B output length)
+  int tiles;          // lattice tiles sampled (1024 cells each)
+  long long tmark;    // phase profiling (thread 0): last timestamp and per-phase cycle counts
+  uint32_t t[6];      //   0 flood (tiles + walk)  1 claims  2 items  3 evaluate  4 ordered sum  5 walk only
+};
+
+XS_HD long long xs_clock() {
+#ifdef __CUDA_ARCH__
+  return clock64();
+#else
+  return 0;
+#endif
+}
+// thread 0 only
+XS_HD void prof_mark(Ctl& ctl, int phase) {
+  const long long now = xs_clock();
+  ctl.t[phase] += (uint32_t)(now - ctl.tmark);
+  ctl.tmark = now;
+}
+
+enum { ST_DONE = 0, ST_NEED_TILE = 1, ST_OVERFLOW = 2 };
+enum { Q_OK = 0, Q_OVERFLOW = 1 };
+
+#define XS_HEMPTY 0xffffffffu
+
+XS_HD bool tile_tested(const Arena& A, int tx, int ty) {
+  const int t = ty * A.tx + tx;
+  return (A.tested[t >> 5] >> (t & 31)) & 1u;
+}
+
+// Sample the lattice rows of every untested tile in the tile rectangle [tx0,tx1]x[ty0,ty1] (clipped).
+template <class G>
+XS_D void test_tiles(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A, Ctl& ctl, int tx0, int ty0, int tx1, int ty1) {
+  tx0 = tx0 < 0 ? 0 : tx0; ty0 = ty0 < 0 ? 0 : ty0;
+  tx1 = tx1 >= A.tx ? A.tx - 1 : tx1; ty1 = ty1 >= A.ty ? A.ty - 1 : ty1;
+  const int nx = tx1 - tx0 + 1, ny = ty1 - ty0 + 1;
+  const int units = nx * ny * 32;
+  for (int unit = g.warp(); unit < units; unit += g.nwarps()) {
+    const int row = unit & 31, t = unit >> 5;
+    const int tx = tx0 + t % nx, ty = ty0 + t / nx;
+    if (tile_tested(A, tx, ty)) continue;   // warp-uniform
+    const int v = ty * 32 + row, u0 = tx * 32;
+    uint32_t word;
+#ifdef __CUDA_ARCH__
+    word = __ballot_sync(0xffffffffu, cell_fg(c, vol, A.ox + u0 + g.lane(), A.oy + v));
+    if (g.lane() == 0) A.bits[(size_t)v * A.stride + tx] = word;
+#else
+    word = 0;
+    for (int l = 0; l < 32; l++) word |= (uint32_t)cell_fg(c, vol, A.ox + u0 + l, A.oy + v) << l;
+    A.bits[(size_t)v * A.stride + tx] = word;
+#endif
+  }
+  g.sync();
+  if (g.tid() == 0) {
+    for (int ty = ty0; ty <= ty1; ty++)
+      for (int tx = tx0; tx <= tx1; tx++) {
+        const int t = ty * A.tx + tx;
+        if (!((A.tested[t >> 5] >> (t & 31)) & 1u)) ctl.tiles++;
+        A.tested[t >> 5] |= 1u << (t & 31);
+      }
+  }
+  g.sync();
+}
+
+XS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {
+#ifdef __CUDA_ARCH__
+  return __funnelshift_r(lo, hi, sh);
+#else
+  return sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+#endif
+}
+
+// Depth-first walk over the bitmap, run by ONE thread.  Neighbour priority is the reverse of the
+// reference's push order (xs3d.hpp:926-950): (+1,+1) (-1,+1) (+1,-1) (-1,-1) (0,+1) (0,-1) (+1,0) (-1,0).
+// A visited cell has its bit cleared, so "set" means foreground-and-unvisited, which only ever
+// decreases: re-examining a cell after a child returns picks exactly the neighbour the reference's
+// explicit stack would pop next.  Returns ST_DONE / ST_NEED_TILE (ctl.req_*) / ST_OVERFLOW.
+XS_HD int dfs_run(const Arena& A, Ctl& ctl) {
+  int n = ctl.n, depth = ctl.depth, lo = ctl.lo, u = ctl.u, v = ctl.v;
+  const int W = A.tx * 32, H = A.ty * 32;
+  const int smask = A.spill ? (A.stack_cap - 1) : 0x7fffffff;   // no ring wrap when the whole stack is resident
+  int status;
+  for (;;) {
+    // all four tiles under the 3x3 neighbourhood must have been sampled
+    const int ua = (u - 1) >> 5, ub = (u + 1) >> 5, va = (v - 1) >> 5, vb = (v + 1) >> 5;
+    if (ua != ub || va != vb) {
+      int need_x = -1, need_y = 0;
+      if (!tile_tested(A, ua, va)) { need_x = ua; need_y = va; }
+      else if (!tile_tested(A, ub, va)) { need_x = ub; need_y = va; }
+      else if (!tile_tested(A, ua, vb)) { need_x = ua; need_y = vb; }
+      else if (!tile_tested(A, ub, vb)) { need_x = ub; need_y = vb; }
+      if (need_x >= 0) { ctl.req_tx = need_x; ctl.req_ty = need_y; status = ST_NEED_TILE; break; }
+    }
+    const int sh = (u - 1) & 31;
+    const uint32_t* rp = A.bits + (size_t)(v - 1) * A.stride + ((u - 1) >> 5);
+    const uint32_t rm = funnel_r(rp[0], rp[1], sh) & 7u;
+    const uint32_t r0 = funnel_r(rp[A.stride], rp[A.stride + 1], sh) & 7u;
+    const uint32_t rq = funnel_r(rp[2 * A.stride], rp[2 * A.stride + 1], sh) & 7u;   // rows v-1, v, v+1
+    // bit d of m <=> neighbour with priority d is available
+    const uint32_t m = ((rq >> 2) & 1u) | ((rq & 1u) << 1) | (((rm >> 2) & 1u) << 2) | ((rm & 1u) << 3) |
+                       (((rq >> 1) & 1u) << 4) | (((rm >> 1) & 1u) << 5) | (((r0 >> 2) & 1u) << 6) | ((r0 & 1u) << 7);
+    if (m == 0u) {
+      // backtrack
+      depth--;
+      if (depth == 0) { status = ST_DONE; break; }
+      if (depth - 1 < lo) {
+        // refill the lower half of the ring from the global spill area
+        int nlo = lo - A.stack_cap / 2;
+        if (nlo < 0) nlo = 0;
+        for (int d = nlo; d < lo; d++) A.stack[d & smask] = A.spill[d];
+        lo = nlo;
+      }
+      const uint32_t p = A.stack[(depth - 1) & smask];
+      u = (int)(p & 0xffffu); v = (int)(p >> 16);
+      continue;
+    }
+#ifdef __CUDA_ARCH__
+    const int d = __ffs(m) - 1;
+#else
+    const int d = __builtin_ffs(m) - 1;
+#endif
+    // du+1 / dv+1 packed two bits per direction
+    const int du = (int)((0x2522u >> (2 * d)) & 3u) - 1;   // d:0..7 -> +1,-1,+1,-1,0,0,+1,-1
+    const int dv = (int)((0x520au >> (2 * d)) & 3u) - 1;   // d:0..7 -> +1,+1,-1,-1,+1,-1,0,0
+    u += du; v += dv;
+    A.bits[(size_t)v * A.stride + (u >> 5)] &= ~(1u << (u & 31));
+    if (u == 0 || v == 0 || u == W - 1 || v == H - 1 || n >= A.max_n) { status = ST_OVERFLOW; break; }
+    const uint32_t p = (uint32_t)u | ((uint32_t)v << 16);
+    A.order[n++] = p;
+    if (depth - lo == A.stack_cap) {
+      // ring full: spill the lower half
+      const int nlo = lo + A.stack_cap / 2;
+      for (int dd = lo; dd < nlo; dd++) A.spill[dd] = A.stack[dd & smask];
+      lo = nlo;
+    }
+    A.stack[depth & smask] = p;
+    depth++;
+  }
+  ctl.n = n; ctl.depth = depth; ctl.lo = lo; ctl.u = u; ctl.v = v;
+  return status;
+}
+
+// Steps 1-2: sample tiles on demand and walk the component.  On return ctl.n samples are in
+// A.order (rank order).  Returns Q_OK or Q_OVERFLOW; *empty is set when the centre cell itself is
+// not foreground on the lattice (the reference then returns zeros).
+template <class G>
+XS_D int flood_component(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A, Ctl& ctl, bool* empty) {
+  const int words = A.ty * 32 * A.stride;
+  for (int i = g.tid(); i < words; i += g.size()) A.bits[i] = 0u;
+  const int tw = (A.tx * A.ty + 31) >> 5;
+  for (int i = g.tid(); i < tw; i += g.size()) A.tested[i] = 0u;
+  const int cu = c.c - A.ox, cv = c.c - A.oy;
+  if (g.tid() == 0) {
+    ctl.status = ST_NEED_TILE; ctl.req_tx = cu >> 5; ctl.req_ty = cv >> 5;
+    ctl.n = 0; ctl.depth = 0; ctl.lo = 0; ctl.u = cu; ctl.v = cv; ctl.m = 0; ctl.overflow = 0; ctl.contact = 0u; ctl.counter = 0u; ctl.tiles = 0;
+    for (int i = 0; i < 6; i++) ctl.t[i] = 0u;
+    ctl.tmark = xs_clock();
+  }
+  g.sync();
+  *empty = false;
+  bool first = true;
+  for (;;) {
+    const int rtx = ctl.req_tx, rty = ctl.req_ty;
+    g.sync();
+    test_tiles(g, c, vol, A, ctl, rtx - A.halo, rty - A.halo, rtx + A.halo, rty + A.halo);
+    if (g.tid() == 0) {
+      int st;
+      if (first) {
+        uint32_t* w = &A.bits[(size_t)cv * A.stride + (cu >> 5)];
+        if (!((*w >> (cu & 31)) & 1u)) {
+          st = ST_DONE; ctl.n = 0;
+        } else {
+          *w &= ~(1u << (cu & 31));
+          const uint32_t p = (uint32_t)cu | ((uint32_t)cv << 16);
+          A.order[0] = p; A.stack[0] = p;
+          ctl.n = 1; ctl.depth = 1;
+          const long long w0 = xs_clock();
+          st = dfs_run(A, ctl);
+          ctl.t[5] += (uint32_t)(xs_clock() - w0);
+        }
+      } else {
+        const long long w0 = xs_clock();
+        st = dfs_run(A, ctl);
+        ctl.t[5] += (uint32_t)(xs_clock() - w0);
+      }
+      ctl.status = st;
+    }
+    first = false;
+    g.sync();
+    const int st = ctl.status;
+    if (st == ST_NEED_TILE) continue;
+    if (st == ST_OVERFLOW) return Q_OVERFLOW;
+    break;
+  }
+  *empty = (ctl.n == 0);
+  return Q_OK;
+}
+
+struct Sample {
+  int rx, ry, rz;   // rounded voxel of the lattice sample
+};
+XS_HD Sample sample_at(const PlaneCtx& c, const Arena& A, int r, V3* rounded) {
+  const uint32_t p = A.order[r];
+  const V3 cur = vround(cell_point(c, A.ox + (int)(p & 0xffffu), A.oy + (int)(p >> 16)));
+  Sample s;
+  s.rx = (int)cur.x; s.ry = (int)cur.y; s.rz = (int)cur.z;
+  if (rounded) *rounded = cur;
+  return s;
+}
+
+XS_HD uint32_t block_id(const VolView& v, int bx, int by, int bz) {
+  return (uint32_t)bx + (uint32_t)v.hx * ((uint32_t)by + (uint32_t)v.hy * (uint32_t)bz);
+}
+XS_HD uint32_t hash_u32(uint32_t k, int shift) { return (k * 2654435761u) >> shift; }
+
+// Pick the hash capacity for a query with n samples (tiers with a big allocated table clear and use
+// only what the query needs).
+XS_HD Arena size_hash(const Arena& A, int n) {
+  Arena B = A;
+  if (A.hash_factor > 0) {
+    uint32_t cap = 1024u;
+    const uint64_t want = (uint64_t)A.hash_factor * (uint64_t)n;
+    while ((uint64_t)cap < want && cap < A.hcap_max) cap <<= 1;
+    int lg = 0;
+    while ((1u << lg) < cap) lg++;
+    B.hcap = cap; B.hshift = 32 - lg;
+  }
+  return B;
+}
+
+// Step 3: contact bits (xs3d.hpp:909-914) and first-touch claims (xs3d.hpp:689-708).
+template <class G>
+XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A, Ctl& ctl) {
+  const int n = ctl.n;
+  for (uint32_t i = g.tid(); i < A.hcap; i += g.size()) { A.htag[i] = XS_HEMPTY; A.hkey[i] = XS_HEMPTY; }
+  g.sync();
+  uint32_t ct = 0u;
+  bool ovf = false;
+  for (int r = g.tid(); r < n; r += g.size()) {
+    V3 cur;
+    const Sample s = sample_at(c, A, r, &cur);
+    ct |= (uint32_t)(cur.x < 1.0f) | ((uint32_t)(cur.x >= c.hi[0]) << 1) | ((uint32_t)(cur.y < 1.0f) << 2) |
+          ((uint32_t)(cur.y >= c.hi[1]) << 3) | ((uint32_t)(cur.z < 1.0f) << 4) | ((uint32_t)(cur.z >= c.hi[2]) << 5);
+    const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
+    const int pb = (s.rx & 1) | ((s.ry & 1) << 1) | ((s.rz & 1) << 2);
+    uint32_t cmask = 0u;
+    for (int k = 0; k < 27; k++) {
+      if (c.axis_aligned && k != 13) continue;                       // xs3d.hpp:677-685
+      const int ox = k % 3 - 1, oy = (k / 3) % 3 - 1, oz = k / 9 - 1;
+      const int x = s.rx + 2 * ox, y = s.ry + 2 * oy, z = s.rz + 2 * oz;
+      if (x < 0 || y < 0 || z < 0 || x >= vol.sx || y >= vol.sy || z >= vol.sz) continue;   // :665-671
+      const uint32_t cb = cube_at(vol, bx + ox, by + oy, bz + oz);
+      if (!((cb >> pb) & 1u)) continue;                              // :704 probe voxel is background
+      cmask |= 1u << k;
+      const uint32_t id = block_id(vol, bx + ox, by + oy, bz + oz);
+      const uint32_t key = ((uint32_t)r << 5) | (uint32_t)k;
+      uint32_t h = hash_u32(id, A.hshift);
+      int probes = 0;
+      for (;;) {
+        const uint32_t t = atomic_cas_u32(&A.htag[h], XS_HEMPTY, id);
+        if (t == XS_HEMPTY || t == id) { atomic_min_u32(&A.hkey[h], key); break; }
+        h = (h + 1u) & (A.hcap - 1u);
+        if (++probes == A.max_probe) { ovf = true; break; }
+      }
+    }
+    A.mask[r] = cmask;
+  }
+  ct = g.or_reduce(ct);
+  if (g.tid() == 0) ctl.contact = ct;
+  if (ovf) ctl.overflow = 1;
+  g.sync();
+}
+
+// Step 4: which candidates did each sample win?  Then compact owners into (rank,k)-ordered items.
+template <class G>
+XS_D void build_items(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A, Ctl& ctl) {
+  const int n = ctl.n;
+  for (int r = g.tid(); r < n; r += g.size()) {
+    uint32_t cm = A.mask[r], own = 0u;
+    if (cm) {
+      const Sample s = sample_at(c, A, r, nullptr);
+      const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
+      while (cm) {
+#ifdef __CUDA_ARCH__
+        const int k = __ffs(cm) - 1;
+#else
+        const int k = __builtin_ffs(cm) - 1;
+#endif
+        cm &= cm - 1u;
+        const int ox = k % 3 - 1, oy = (k / 3) % 3 - 1, oz = k / 9 - 1;
+        const uint32_t id = block_id(vol, bx + ox, by + oy, bz + oz);
+        uint32_t h = hash_u32(id, A.hshift);
+        while (A.htag[h] != id) h = (h + 1u) & (A.hcap - 1u);
+        if (A.hkey[h] == (((uint32_t)r << 5) | (uint32_t)k)) own |= 1u << k;
+      }
+    }
+    A.mask[r] = own;
+  }
+  g.sync();
+  int base = 0;
+  bool ovf = false;
+  const int gs = g.size();
+  for (int r0 = 0; r0 < n; r0 += gs) {
+    const int r = r0 + g.tid();
+    uint32_t own = (r < n) ? A.mask[r] : 0u;
+#ifdef __CUDA_ARCH__
+    const int cnt = __popc(own);
+#else
+    const int cnt = __builtin_popcount(own);
+#endif
+    int total;
+    int off = base + g.exscan(cnt, total);
+    if (base + total > A.max_m) { ovf = true; break; }   // uniform across the group
+    while (own) {
+#ifdef __CUDA_ARCH__
+      const int k = __ffs(own) - 1;
+#else
+      const int k = __builtin_ffs(own) - 1;
+#endif
+      own &= own - 1u;
+      A.items[off++] = ((uint32_t)r << 5) | (uint32_t)k;
+    }
+    base += total;
+  }
+  if (g.tid() == 0) { ctl.m = base; if (ovf) ctl.overflow = 1; }
+  g.sync();
+}
+
+// Step 5: adjacency test (xs3d.hpp:710-712) and block value (:713-719) of every owned block.
+template <class G>
+XS_D void eval_items(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A, Ctl& ctl) {
+  const int m = ctl.m;
+  for (int it = g.tid(); it < m; it += g.size()) {
+    const uint32_t e = A.items[it];
+    const int r = (int)(e >> 5), k = (int)(e & 31u);
+    const Sample s = sample_at(c, A, r, nullptr);
+    const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
+    const int ox = k % 3 - 1, oy = (k / 3) % 3 - 1, oz = k / 9 - 1;
+    const uint32_t centre = cube_at(vol, bx, by, bz);
+    const uint32_t cand = cube_at(vol, bx + ox, by + oy, bz + oz);
+    float val = 0.0f;
+    if (blocks_adjacent(centre, cand, ox, oy, oz))
+      val = block_value(cand, (float)(2 * (bx + ox)), (float)(2 * (by + oy)), (float)(2 * (bz + oz)), c.g);
+    A.vals[it] = val;
+  }
+  g.sync();
+}
+
+// Step 6: two-level float32 sum in the reference's order (xs3d.hpp:663,713 then :848,952).
+template <class G>
+XS_D float ordered_sum(const G& g, const Arena& A, Ctl& ctl, float* shared_result) {
+  const int m = ctl.m;
+  float total = 0.0f, sub = 0.0f;
+  uint32_t cur_r = 0xffffffffu;
+  if (A.stage == nullptr) {
+    if (g.tid() == 0) {
+      for (int it = 0; it < m; it++) {
+        const uint32_t r = A.items[it] >> 5;
+        if (r != cur_r) { total = fadd(total, sub); sub = 0.0f; cur_r = r; }
+        sub = fadd(sub, A.vals[it]);
+      }
+      total = fadd(total, sub);
+      *shared_result = total;
+    }
+  } else {
+    const int chunk = A.stage_cap / 2;
+    uint32_t* s_items = A.stage;
+    float* s_vals = (float*)(A.stage + chunk);
+    for (int b = 0; b < m; b += chunk) {
+      const int len = (m - b) < chunk ? (m - b) : chunk;
+      for (int i = g.tid(); i < len; i += g.size()) { s_items[i] = A.items[b + i]; s_vals[i] = A.vals[b + i]; }
+      g.sync();
+      if (g.tid() == 0) {
+        for (int i = 0; i < len; i++) {
+          const uint32_t r = s_items[i] >> 5;
+          if (r != cur_r) { total = fadd(total, sub); sub = 0.0f; cur_r = r; }
+          sub = fadd(sub, s_vals[i]);
+        }
+      }
+      g.sync();
+    }
+    if (g.tid() == 0) { total = fadd(total, sub); *shared_result = total; }
+  }
+  g.sync();
+  return *shared_result;
+}
+
+// Path A: xs3d.cross_sectional_area for one query.  Every thread of the group returns the same
+// status; on Q_OK thread 0 has written *area / *contact.
+template <class G>
+XS_D int run_area(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A, Ctl& ctl, float* scratch_f,
+                  float* area, uint8_t* contact) {
+  bool empty;
+  if (flood_component(g, c, vol, A, ctl, &empty) != Q_OK) return Q_OVERFLOW;
+  if (empty) {
+    if (g.tid() == 0) { *area = 0.0f; *contact = 0; }
+    return Q_OK;
+  }
+  if (g.tid() == 0) prof_mark(ctl, 0);
+  const Arena B = size_hash(A, ctl.n);
+  claim_blocks(g, c, vol, B, ctl);
+  if (ctl.overflow) return Q_OVERFLOW;
+  if (g.tid() == 0) prof_mark(ctl, 1);
+  build_items(g, c, vol, B, ctl);
+  if (ctl.overflow) return Q_OVERFLOW;
+  if (g.tid() == 0) prof_mark(ctl, 2);
+  eval_items(g, c, vol, B, ctl);
+  if (g.tid() == 0) prof_mark(ctl, 3);
+  const float total = ordered_sum(g, B, ctl, scratch_f);
+  if (g.tid() == 0) { prof_mark(ctl, 4); *area = total; *contact = (uint8_t)ctl.contact; }
+  return Q_OK;
+}
+
+// Path B: xs3d.cross_section for one query.  Emits the sparse image {voxel index -> area > 0}
+// (unordered) into out_idx/out_val (capacity out_cap); count in ctl.counter.  The voxel-dedupe set
+// reuses the claim hash (htag only).  Neighbourhood and contact follow the UNROUNDED sample
+// (xs3d.hpp:458-478, :1215-1220).
+template <class G>
+XS_D int run_section(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A_in, Ctl& ctl,
+                     uint64_t* out_idx, float* out_val, uint32_t out_cap, uint8_t* contact) {
+  bool empty;
+  if (flood_component(g, c, vol, A_in, ctl, &empty) != Q_OK) return Q_OVERFLOW;
+  if (empty) {
+    if (g.tid() == 0) *contact = 0;
+    return Q_OK;
+  }
+  const int n = ctl.n;
+  const Arena A = size_hash(A_in, n);
+  for (uint32_t i = g.tid(); i < A.hcap; i += g.size()) A.htag[i] = XS_HEMPTY;
+  g.sync();
+  uint32_t ct = 0u;
+  bool ovf = false;
+  const float fsx = (float)vol.sx, fsy = (float)vol.sy, fsz = (float)vol.sz;
+  for (int r = g.tid(); r < n; r += g.size()) {
+    const uint32_t p = A.order[r];
+    const V3 cur = cell_point(c, A.ox + (int)(p & 0xffffu), A.oy + (int)(p >> 16));
+    ct |= (uint32_t)(cur.x < 0.5f) | ((uint32_t)(cur.x >= c.hi[0]) << 1) | ((uint32_t)(cur.y < 0.5f) << 2) |
+          ((uint32_t)(cur.y >= c.hi[1]) << 3) | ((uint32_t)(cur.z < 0.5f) << 4) | ((uint32_t)(cur.z >= c.hi[2]) << 5);
+    int lo[3], hi[3];
+    lo[0] = (fsub(cur.x, 1.0f) >= 0.0f) ? -1 : 0; lo[1] = (fsub(cur.y, 1.0f) >= 0.0f) ? -1 : 0; lo[2] = (fsub(cur.z, 1.0f) >= 0.0f) ? -1 : 0;
+    hi[0] = (fadd(cur.x, 1.0f) < fsx) ? 1 : 0; hi[1] = (fadd(cur.y, 1.0f) < fsy) ? 1 : 0; hi[2] = (fadd(cur.z, 1.0f) < fsz) ? 1 : 0;
+    if (c.axis_aligned) { lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0; }
+    for (int dz = lo[2]; dz <= hi[2]; dz++)
+      for (int dy = lo[1]; dy <= hi[1]; dy++)
+        for (int dx = lo[0]; dx <= hi[0]; dx++) {
+          const V3 q = vround(vadd(mk((float)dx, (float)dy, (float)dz), cur));
+          if (q.x < 0.0f || q.x >= fsx || q.y < 0.0f || q.y >= fsy || q.z < 0.0f || q.z >= fsz) continue;
+          const int x = (int)q.x, y = (int)q.y, z = (int)q.z;
+          if (!vox_fg(vol, x, y, z)) continue;
+          const uint32_t id = (uint32_t)x + (uint32_t)vol.sx * ((uint32_t)y + (uint32_t)vol.sy * (uint32_t)z);
+          uint32_t h = hash_u32(id, A.hshift);
+          int probes = 0;
+          bool fresh = false;
+          for (;;) {
+            const uint32_t t = atomic_cas_u32(&A.htag[h], XS_HEMPTY, id);
+            if (t == XS_HEMPTY) { fresh = true; break; }
+            if (t == id) break;
+            h = (h + 1u) & (A.hcap - 1u);
+            if (++probes == A.max_probe) { ovf = true; break; }
+          }
+          if (!fresh) continue;                  // first touch only (xs3d.hpp:511-512)
+          const float a = voxel_area((float)x, (float)y, (float)z, c.g);
+          if (a > 0.0f) {                        // xs3d.hpp:526-528
+            const uint32_t slot = atomic_add_u32(&ctl.counter, 1u);
+            if (slot < out_cap) { out_idx[slot] = (uint64_t)id; out_val[slot] = a; }
+            else ovf = true;
+          }
+        }
+  }
+  ct = g.or_reduce(ct);
+  if (ovf) ctl.overflow = 1;
+  g.sync();
+  if (ctl.overflow) return Q_OVERFLOW;
+  if (g.tid() == 0) *contact = (uint8_t)ct;
+  return Q_OK;
+}
+
+// Lattice window that provably contains every in-volume lattice cell of the plane: the projection
+// of the volume box onto (b1,b2), padded, clipped to the lattice plus one ring of outside cells.
+XS_HD void bbox_window(const PlaneCtx& c, const VolView& v, int* ox, int* oy, int* tx, int* ty) {
+  float mn[2] = { 0.0f, 0.0f }, mx[2] = { 0.0f, 0.0f };
+  for (int k = 0; k < 8; k++) {
+    const float qx = ((k & 1) ? (float)v.sx - 0.5f : -0.5f) - c.g.pos.x;
+    const float qy = ((k & 2) ? (float)v.sy - 0.5f : -0.5f) - c.g.pos.y;
+    const float qz = ((k & 4) ? (float)v.sz - 0.5f : -0.5f) - c.g.pos.z;
+    const float a = qx * c.b1.x + qy * c.b1.y + qz * c.b1.z;
+    const float b = qx * c.b2.x + qy * c.b2.y + qz * c.b2.z;
+    mn[0] = a < mn[0] ? a : mn[0]; mx[0] = a > mx[0] ? a : mx[0];
+    mn[1] = b < mn[1] ? b : mn[1]; mx[1] = b > mx[1] ? b : mx[1];
+  }
+  // b1,b2 are unit to ~1e-7, so |true - projected| << 1 cell; pad by 3 cells + 0.1%
+  int lo[2], hi[2];
+  for (int a = 0; a < 2; a++) {
+    const float pad = 3.0f + 0.001f * (mx[a] - mn[a]);
+    lo[a] = c.c + (int)floorf(mn[a] - pad);
+    hi[a] = c.c + (int)ceilf(mx[a] + pad);
+    if (lo[a] < -1) lo[a] = -1;
+    if (hi[a] > c.psx) hi[a] = c.psx;
+  }
+  *ox = lo[0]; *oy = lo[1];
+  *tx = (hi[0] - lo[0] + 1 + 31) / 32;
+  *ty = (hi[1] - lo[1] + 1 + 31) / 32;
+}
+
+}  // namespace xs

@@ -1,0 +1,106 @@
+/* xs3d_b200.h — C ABI of libxs3d_b200.so, the B200-native replacement for the reference's pybind11
+ * extension `fastxs3d` (/root/reference/src/fastxs3d.cpp:218-226).
+ *
+ * Plain C: pointers, sizes, status codes.  No torch / numpy / C++ types cross this boundary.
+ * Every entry point returns XS3D_OK (0) or an error code; xs3d_last_error() returns the message of
+ * the last failure on the calling thread.  There is NO CPU implementation behind these symbols:
+ * without a CUDA device every compute entry point fails with XS3D_ERR_CUDA.
+ *
+ * Array conventions (same as the reference, xs3d/__init__.py:77-83, fastxs3d.cpp:20-26):
+ *   binimg : uint8 (bool viewed as uint8), 3-D, Fortran order  -> index x + sx*(y + sy*z); nonzero = foreground
+ *   pos / normal / anisotropy : float32[3] per query (batched: float32[n][3], row-major)
+ *   area   : float32 (the reference's float32 result, bit-identical)
+ *   contact: uint8 bitfield  bit0 -x, bit1 +x, bit2 -y, bit3 +y, bit4 -z, bit5 +z
+ * `mem` arguments say where the caller's buffers live: XS3D_HOST (0) or XS3D_DEVICE (1, same device
+ * as the volume; stream-ordered on the volume's stream and synchronised before returning).
+ */
+#ifndef XS3D_B200_H_
+#define XS3D_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XS3D_OK 0
+#define XS3D_ERR_CUDA 1        /* CUDA runtime failure / no device */
+#define XS3D_ERR_ARG 2         /* invalid argument */
+#define XS3D_ERR_UNSUPPORTED 3 /* e.g. volume with >= 2^32 voxel blocks */
+#define XS3D_ERR_CAPACITY 4    /* internal working set exceeded even on the last-resort path */
+
+#define XS3D_HOST 0
+#define XS3D_DEVICE 1
+
+typedef struct xs3d_volume xs3d_volume;   /* a volume resident on one GPU + its workspaces */
+
+const char* xs3d_last_error(void);
+int xs3d_version(void);
+int xs3d_device_count(int* count);
+
+/* ---- resident volumes (the GPU meaning of the reference's set_shape/clear_shape, xs3d.hpp:1295-1303,
+ *      and the handle the batched entry points work on) ------------------------------------------------ */
+int xs3d_volume_create(int device, uint64_t sx, uint64_t sy, uint64_t sz, xs3d_volume** out);
+int xs3d_volume_destroy(xs3d_volume* vol);
+/* Upload (if mem == XS3D_HOST) and ingest a binary image into the 2x2x2 occupancy layout.
+ * c_order != 0: the buffer is C-contiguous [sx][sy][sz] (index z + sz*(y + sy*x)); this replaces the
+ * host-side np.asfortranarray copy of xs3d/__init__.py:77. */
+int xs3d_volume_load(xs3d_volume* vol, const uint8_t* binimg, int mem, int c_order);
+/* Attach a label volume for xs3d_projection_v (any 1/2/4/8-byte dtype, C or F order; fastxs3d.cpp:135,199-215). */
+int xs3d_volume_load_labels(xs3d_volume* vol, const void* labels, int itemsize, int mem, int c_order);
+/* Device pointer + size of the ingested occupancy bytes (for an NCCL broadcast by the host layer),
+ * and the call that marks them valid after such a broadcast wrote them. */
+int xs3d_volume_cubes(xs3d_volume* vol, void** device_ptr, uint64_t* bytes);
+int xs3d_volume_mark_loaded(xs3d_volume* vol);
+int xs3d_volume_shape(xs3d_volume* vol, uint64_t shape[3]);
+
+/* ---- batched entry point (new): many (vertex, normal) queries against one resident volume.
+ *      Same per-query semantics as fastxs3d.area(..., slow_method=False)  (xs3d.hpp:1305-1365). */
+int xs3d_area_batch(xs3d_volume* vol, uint64_t n, const float* pos, const float* normal,
+                    const float anisotropy[3], int mem, float* area, uint8_t* contact);
+/* Counters of the last xs3d_area_batch on this volume:
+ * stats[0] lattice samples, [1] owned blocks, [2] lattice cells tested, [3] queries escalated warp->CTA tier,
+ * [4] queries escalated to the last-resort slab, [5] kernel launches of the call. */
+int xs3d_volume_stats(xs3d_volume* vol, uint64_t stats[8]);
+/* SM-clock cycles thread 0 of each query group spent per phase in the last xs3d_area_batch, summed over
+ * queries: prof[0..5] warp tier, prof[6..11] CTA tier; phases: lattice flood (tiles + walk), claims,
+ * ownership/items, evaluate, ordered sum, walk only. */
+int xs3d_volume_profile(xs3d_volume* vol, uint64_t prof[12]);
+
+/* ---- drop-in single-call entry points: one per fastxs3d export ------------------------------------- */
+/* fastxs3d.area (fastxs3d.cpp:82-117).  use_persistent_data != 0 reuses the volume uploaded by the
+ * last xs3d_set_shape_image() instead of re-uploading binimg (the caller promises it is the same image,
+ * the reference's own contract: xs3d/__init__.py:239-241). */
+int xs3d_area(const uint8_t* binimg, uint64_t sx, uint64_t sy, uint64_t sz,
+              const float pos[3], const float normal[3], const float anisotropy[3],
+              int slow_method, int use_persistent_data, float* area, uint8_t* contact);
+/* fastxs3d.section (fastxs3d.cpp:13-80).  `out` is a HOST float32 F-order buffer of
+ * sx*sy*sz elements (method 0/1) or ceil(sx/2)*ceil(sy/2)*ceil(sz/2) (method 2) that the caller has
+ * zero-filled (the reference's std::fill, fastxs3d.cpp:42-44); non-zero contributions are scattered into it. */
+int xs3d_section(const uint8_t* binimg, uint64_t sx, uint64_t sy, uint64_t sz,
+                 const float pos[3], const float normal[3], const float anisotropy[3],
+                 int method, float* out, uint8_t* contact);
+/* Sparse form of the same result on a resident volume: up to `cap` (linear index, value) pairs, HOST buffers. */
+int xs3d_section_sparse(xs3d_volume* vol, const float pos[3], const float normal[3], const float anisotropy[3],
+                        int method, uint64_t* idx, float* val, uint64_t cap, uint64_t* nnz, uint8_t* contact);
+/* fastxs3d.projection (fastxs3d.cpp:119-216).  Two-call protocol: the first call (out == NULL) returns the
+ * cut-out shape; the second fills `out` (HOST, F-order [shape0][shape1], itemsize bytes per element). */
+int xs3d_projection(const void* labels, uint64_t sx, uint64_t sy, uint64_t sz, int itemsize, int c_order,
+                    const float pos[3], const float normal[3], const float anisotropy[3],
+                    int standardize_basis, float crop_distance, void* out, int64_t shape[2]);
+/* Batched slices on a resident label volume: n planes, fixed-pitch output.  Plane i's cut-out
+ * (shapes[2i] x shapes[2i+1], F-order) is written at out + i*pitch_elems*itemsize; planes whose cut-out
+ * exceeds pitch_elems are reported with shapes but not written (status XS3D_OK, flag in overflow[i]). */
+int xs3d_projection_batch(xs3d_volume* vol, uint64_t n, const float* pos, const float* normal,
+                          const float anisotropy[3], int standardize_basis, float crop_distance,
+                          void* out, uint64_t pitch_elems, int64_t* shapes, uint8_t* overflow, int mem);
+/* fastxs3d.set_shape / clear_shape (fastxs3d.cpp:224-225).  set_shape only records the shape (as the
+ * reference does); xs3d_set_shape_image additionally makes the image resident for use_persistent_data. */
+int xs3d_set_shape(uint64_t sx, uint64_t sy, uint64_t sz);
+int xs3d_set_shape_image(const uint8_t* binimg, uint64_t sx, uint64_t sy, uint64_t sz, int c_order);
+int xs3d_clear_shape(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XS3D_B200_H_ */

@@ -1,0 +1,205 @@
+// tests/hostsim/hostsim.cpp — TEST INFRASTRUCTURE: compiles the kernel headers (csrc/xs_*.cuh) as plain
+// C++ with a one-thread "group", so the exact query logic that runs on the GPU can be checked against
+// the oracle on a machine without a GPU (pytest -m "not gpu").  Never linked into libxs3d_b200.so and
+// never used by the product path.
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "xs_query.cuh"
+#include "xs_slice.cuh"
+
+using namespace xs;
+
+static void host_ingest(const uint8_t* img, int sx, int sy, int sz, std::vector<uint8_t>& cubes) {
+  const int hx = (sx + 1) >> 1, hy = (sy + 1) >> 1, hz = (sz + 1) >> 1;
+  cubes.assign((size_t)hx * hy * hz, 0);
+  for (int z = 0; z < sz; z++)
+    for (int y = 0; y < sy; y++)
+      for (int x = 0; x < sx; x++)
+        if (img[(size_t)x + (size_t)sx * ((size_t)y + (size_t)sy * z)])
+          cubes[(size_t)(x >> 1) + (size_t)hx * ((size_t)(y >> 1) + (size_t)hy * (z >> 1))] |=
+              (uint8_t)(1u << ((x & 1) | ((y & 1) << 1) | ((z & 1) << 2)));
+}
+
+struct HostArena {
+  std::vector<uint32_t> bits, tested, order, stack, spill, mask, htag, hkey, items, stage;
+  std::vector<float> vals;
+  Arena A;
+  // small == true mimics the warp tier's fixed shared-memory arena (so overflow paths get exercised)
+  void setup(const PlaneCtx& c, const VolView& v, bool small, int tiles, int max_n, uint32_t hcap, int max_m, int stack_cap) {
+    memset(&A, 0, sizeof(A));
+    if (small) {
+      A.tx = A.ty = tiles;
+      A.ox = c.c - 16 - 32 * (tiles / 2);
+      A.oy = A.ox;
+      A.halo = 0;
+    } else {
+      bbox_window(c, v, &A.ox, &A.oy, &A.tx, &A.ty);
+      A.halo = 1;
+    }
+    A.stride = A.tx + 1;
+    bits.assign((size_t)A.ty * 32 * A.stride, 0xdeadbeefu);   // kernel must clear it itself
+    tested.assign((A.tx * A.ty + 31) / 32, 0xdeadbeefu);
+    order.assign(max_n, 0); mask.assign(max_n, 0);
+    A.max_n = max_n;
+    if (stack_cap > 0) { stack.assign(stack_cap, 0); spill.assign(max_n, 0); A.stack_cap = stack_cap; A.spill = spill.data(); }
+    else { stack.assign(max_n, 0); A.stack_cap = max_n; A.spill = nullptr; }
+    htag.assign(hcap, 0); hkey.assign(hcap, 0);
+    A.hcap = hcap; A.hshift = 32 - __builtin_ctz(hcap); A.hcap_max = hcap; A.hash_factor = small ? 0 : 16; A.max_probe = small ? 128 : 0;
+    items.assign(max_m, 0); vals.assign(max_m, 0.f);
+    A.max_m = max_m;
+    A.bits = bits.data(); A.tested = tested.data(); A.order = order.data(); A.stack = stack.data();
+    A.mask = mask.data(); A.htag = htag.data(); A.hkey = hkey.data(); A.items = items.data(); A.vals = vals.data();
+    A.stage = nullptr; A.stage_cap = 0;
+  }
+};
+
+static uint32_t pow2_at_least(uint64_t x) { uint32_t p = 64; while (p < x) p <<= 1; return p; }
+
+extern "C" {
+
+// mode 0: big arena only.  mode 1: small (warp-tier-like) arena first, big arena on overflow.
+// mode 2: like 0 but with a tiny DFS stack ring (exercises spill/refill) and staged ordered sum.
+// stats[0] = queries that overflowed the small arena, stats[1] = total samples, stats[2] = total items
+void hostsim_area_batch(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t sz, uint64_t nq, const float* pos,
+                        const float* nrm, const float* w, float* area, uint8_t* contact, int mode, int64_t* stats) {
+  std::vector<uint8_t> cubes;
+  host_ingest(img, (int)sx, (int)sy, (int)sz, cubes);
+  VolView v = { cubes.data(), (int)sx, (int)sy, (int)sz, ((int)sx + 1) >> 1, ((int)sy + 1) >> 1, ((int)sz + 1) >> 1 };
+  HostGroup g;
+  HostArena small, big;
+  int64_t n_over = 0, n_samples = 0, n_items = 0;
+  for (uint64_t q = 0; q < nq; q++) {
+    PlaneCtx c;
+    area[q] = 0.f; contact[q] = 0;
+    if (!plane_init(c, v, mk(pos[3*q], pos[3*q+1], pos[3*q+2]), mk(nrm[3*q], nrm[3*q+1], nrm[3*q+2]), mk(w[0], w[1], w[2]))) continue;
+    Ctl ctl; float scratch;
+    int st = Q_OVERFLOW;
+    if (mode == 1) {
+      small.setup(c, v, true, 3, 384, 1024, 768, 0);
+      st = run_area(g, c, v, small.A, ctl, &scratch, &area[q], &contact[q]);
+      if (st != Q_OK) n_over++;
+    }
+    if (st != Q_OK) {
+      int otx, oty, ox, oy;
+      bbox_window(c, v, &ox, &oy, &otx, &oty);
+      const int max_n = otx * oty * 1024;
+      big.setup(c, v, false, 0, max_n, pow2_at_least((uint64_t)max_n * 8), max_n * 4, mode == 2 ? 16 : 0);
+      std::vector<uint32_t> stage;
+      if (mode == 2) { stage.assign(64, 0); big.A.stage = stage.data(); big.A.stage_cap = 64; }
+      st = run_area(g, c, v, big.A, ctl, &scratch, &area[q], &contact[q]);
+      if (st != Q_OK) { area[q] = -1.f; contact[q] = 0xff; }
+    }
+    n_samples += ctl.n; n_items += ctl.m;
+  }
+  if (stats) { stats[0] = n_over; stats[1] = n_samples; stats[2] = n_items; }
+}
+
+// Dense float32 F-order image (zeroed by the caller), like fastxs3d.section method 0.
+int hostsim_section(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t sz, const float* p, const float* n,
+                    const float* w, float* out, uint8_t* contact) {
+  std::vector<uint8_t> cubes;
+  host_ingest(img, (int)sx, (int)sy, (int)sz, cubes);
+  VolView v = { cubes.data(), (int)sx, (int)sy, (int)sz, ((int)sx + 1) >> 1, ((int)sy + 1) >> 1, ((int)sz + 1) >> 1 };
+  HostGroup g;
+  PlaneCtx c;
+  *contact = 0;
+  if (!plane_init(c, v, mk(p[0], p[1], p[2]), mk(n[0], n[1], n[2]), mk(w[0], w[1], w[2]))) return 0;
+  HostArena big;
+  int otx, oty, ox, oy;
+  bbox_window(c, v, &ox, &oy, &otx, &oty);
+  const int max_n = otx * oty * 1024;
+  big.setup(c, v, false, 0, max_n, pow2_at_least((uint64_t)max_n * 64), 16, 0);
+  std::vector<uint64_t> idx((size_t)max_n * 27);
+  std::vector<float> val((size_t)max_n * 27);
+  Ctl ctl;
+  int st = run_section(g, c, v, big.A, ctl, idx.data(), val.data(), (uint32_t)idx.size(), contact);
+  if (st != Q_OK) return -1;
+  for (uint32_t i = 0; i < ctl.counter; i++) out[idx[i]] = val[i];
+  return (int)ctl.counter;
+}
+
+float hostsim_voxel_area(uint64_t x, uint64_t y, uint64_t z, const float* p, const float* n, const float* w) {
+  PlaneGeom g;
+  geom_init(g, mk(p[0], p[1], p[2]), mk(n[0], n[1], n[2]), mk(w[0], w[1], w[2]));
+  return voxel_area((float)x, (float)y, (float)z, g);
+}
+
+float hostsim_block_area(uint8_t cube, const float* cur, const float* p, const float* n, const float* w) {
+  PlaneGeom g;
+  geom_init(g, mk(p[0], p[1], p[2]), mk(n[0], n[1], n[2]), mk(w[0], w[1], w[2]));
+  return block_value(cube, (float)((uint64_t)cur[0] & ~1ull), (float)((uint64_t)cur[1] & ~1ull), (float)((uint64_t)cur[2] & ~1ull), g);
+}
+
+int hostsim_is_26_connected(uint8_t centre, uint8_t cand, int x, int y, int z) { return blocks_adjacent(centre, cand, x, y, z) ? 1 : 0; }
+
+float hostsim_round(float x) { return fround(x); }
+
+// slice with the reference's raw layout: `out` holds psx*psx labels (zeroed by the caller), bbox as
+// cross_section_projection returns it.  mode 1 forces the iterative fallback fill.
+int hostsim_projection(const void* labels, uint64_t sx, uint64_t sy, uint64_t sz, int itemsize, int c_order,
+                       const float* p, const float* n, const float* w, int positive_basis, float crop,
+                       void* out, int64_t* bbox, int mode) {
+  SliceCtx s;
+  slice_init(s, (int)sx, (int)sy, (int)sz, mk(p[0], p[1], p[2]), mk(n[0], n[1], n[2]), mk(w[0], w[1], w[2]), positive_basis != 0, crop);
+  bbox[0] = bbox[1] = bbox[2] = bbox[3] = 0;
+  if (!s.pos_inside) return 0;
+  bbox[0] = bbox[1] = bbox[2] = bbox[3] = s.c;
+  if (!s.active) return 0;
+  const int words = (s.ww + 31) / 32;
+  std::vector<uint32_t> V((size_t)words * s.wh, 0), R;
+  for (int y = 0; y < s.wh; y++)
+    for (int x = 0; x < s.ww; x++)
+      if (slice_cell(s, s.wx0 + x, s.wy0 + y, false, nullptr)) V[(size_t)y * words + (x >> 5)] |= 1u << (x & 31);
+  std::vector<RowRuns> rows(s.wh);
+  for (int y = 0; y < s.wh; y++) rows[y] = row_runs(&V[(size_t)y * words], words);
+  const int cx = (int)(s.c - s.wx0), cy = (int)(s.c - s.wy0);
+  SliceResult r = scan_rows(rows.data(), s.wh, cx, cy);
+  const uint32_t* mask = V.data();
+  int used_fallback = 0;
+  if (r.fallback || (mode == 1 && r.y0 <= r.y1)) {
+    used_fallback = 1;
+    R.assign(V.size(), 0);
+    R[(size_t)cy * words + (cx >> 5)] = V[(size_t)cy * words + (cx >> 5)] & (1u << (cx & 31));
+    bool changed = true;
+    while (changed) {
+      changed = false;
+      for (int y = 0; y < s.wh; y++)
+        for (int x = 0; x < s.ww; x++) {
+          const size_t wi = (size_t)y * words + (x >> 5);
+          const uint32_t bit = 1u << (x & 31);
+          if (!(V[wi] & bit) || (R[wi] & bit)) continue;
+          auto get = [&](int xx, int yy) { return xx >= 0 && yy >= 0 && xx < s.ww && yy < s.wh && ((R[(size_t)yy * words + (xx >> 5)] >> (xx & 31)) & 1u); };
+          if (get(x - 1, y) || get(x + 1, y) || get(x, y - 1) || get(x, y + 1)) { R[wi] |= bit; changed = true; }
+        }
+    }
+    for (int y = 0; y < s.wh; y++) rows[y] = row_runs(&R[(size_t)y * words], words);
+    r.y0 = 0x7fffffff; r.y1 = -1; r.x0 = 0x7fffffff; r.x1 = -1;
+    for (int y = 0; y < s.wh; y++) {
+      if (rows[y].runs == 0) continue;
+      if (y < r.y0) r.y0 = y;
+      r.y1 = y;
+      if (rows[y].a < r.x0) r.x0 = rows[y].a;
+      if (rows[y].b > r.x1) r.x1 = rows[y].b;
+    }
+    mask = R.data();
+  }
+  if (r.y0 > r.y1) return used_fallback;
+  bbox[0] = s.wx0 + r.x0; bbox[1] = s.wx0 + r.x1; bbox[2] = s.wy0 + r.y0; bbox[3] = s.wy0 + r.y1;
+  for (int y = r.y0; y <= r.y1; y++)
+    for (int x = r.x0; x <= r.x1; x++) {
+      if (!((mask[(size_t)y * words + (x >> 5)] >> (x & 31)) & 1u)) continue;
+      size_t loc;
+      slice_cell(s, s.wx0 + x, s.wy0 + y, c_order != 0, &loc);
+      memcpy((char*)out + ((size_t)(s.wx0 + x) + (size_t)s.psx * (size_t)(s.wy0 + y)) * itemsize, (const char*)labels + loc * itemsize, itemsize);
+    }
+  return used_fallback;
+}
+
+long long hostsim_plane_size(uint64_t sx, uint64_t sy, uint64_t sz, const float* w, float crop) {
+  return slice_plane_size((int)sx, (int)sy, (int)sz, mk(w[0], w[1], w[2]), crop);
+}
+
+}  // extern "C"

@@ -1,0 +1,87 @@
+"""CPU: the C-ABI library loads, exports every symbol the header declares, the Python host layer mirrors
+the reference's argument validation, and compute calls fail loudly (no CPU fallback) without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+  src = open(os.path.join(ROOT, "include", "xs3d_b200.h")).read()
+  src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+  return sorted(set(re.findall(r"\b(xs3d_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol():
+  from xs3d import _abi
+  lib = C.CDLL(_abi.LIB_PATH)
+  syms = header_symbols()
+  assert len(syms) >= 20
+  for s in syms:
+    assert hasattr(lib, s), f"{s} declared in include/xs3d_b200.h but not exported"
+  assert sorted(_abi.SYMBOLS) == syms
+  assert lib.xs3d_version() >= 100
+
+
+def test_no_cpu_fallback_without_gpu():
+  import torch
+  if torch.cuda.is_available():
+    pytest.skip("a GPU is present")
+  import xs3d
+  vol = np.ones((4, 4, 4), dtype=bool, order="F")
+  with pytest.raises(xs3d.XS3DError):
+    xs3d.cross_sectional_area(vol, [1, 1, 1], [0, 0, 1])
+  with pytest.raises(xs3d.XS3DError):
+    xs3d.Volume(vol)
+  with pytest.raises(xs3d.XS3DError):
+    xs3d.cross_section(vol, [1, 1, 1], [0, 0, 1])
+  with pytest.raises(xs3d.XS3DError):
+    xs3d.slice(vol.astype(np.uint8), [1, 1, 1], [0, 0, 1])
+
+
+def test_input_validation_matches_reference():
+  """automated_test.py:344-390 and :332-342 (the ValueErrors are raised before the device is touched)."""
+  import xs3d
+  labels = np.arange(9, dtype=np.uint8).reshape([3, 3, 1], order="F")
+  for fn in (xs3d.cross_sectional_area, xs3d.cross_section):
+    with pytest.raises(ValueError):
+      fn(labels, [0, 0, 0], [0, 0, 1])
+    ok = np.ones([3, 3, 1], dtype=bool, order="F")
+    with pytest.raises(ValueError):
+      fn(ok, [0, 0, 0], [0, 0, 0])
+    for bad in ([-1, 1, 1], [1, -1, 1], [1, 1, -1], [-1, -1, -1], [0, 1, 1]):
+      with pytest.raises(ValueError):
+        fn(ok, [0, 0, 0], [0, 0, 1], bad)
+    with pytest.raises(ValueError):
+      fn(np.ones([3, 3, 3, 3], dtype=bool, order="F"), [0, 0, 0], [0, 0, 1], [1, 1, 1])
+  with pytest.raises(ValueError):
+    xs3d.slice(labels, [0, 0, 0], [0, 0, 0])
+  with pytest.raises(ValueError):
+    xs3d.slice(np.ones([3, 3, 3, 3], dtype=bool, order="F"), [0, 0, 0], [0, 0, 1])
+  with pytest.raises(AssertionError):
+    xs3d.slice(labels, [0, 0, 0], [0, 0, 1], crop=-1.0)
+
+
+def test_signatures_match_reference():
+  import inspect
+  import xs3d
+  assert list(inspect.signature(xs3d.cross_sectional_area).parameters) == ["binimg", "pos", "normal", "anisotropy", "return_contact", "slow_method", "use_persistent_data"]
+  assert list(inspect.signature(xs3d.cross_section).parameters) == ["binimg", "pos", "normal", "anisotropy", "return_contact", "method"]
+  assert list(inspect.signature(xs3d.slice).parameters) == ["labels", "pos", "normal", "anisotropy", "standardize_basis", "crop"]
+  assert list(inspect.signature(xs3d.set_shape).parameters) == ["image"]
+  assert list(inspect.signature(xs3d.clear_shape).parameters) == []
+
+
+def test_shard_bounds():
+  from xs3d.dist import shard_bounds
+  for n in (0, 1, 7, 10000, 10001):
+    for world in (1, 2, 3, 8):
+      chunks = [shard_bounds(n, world, r) for r in range(world)]
+      assert chunks[0][0] == 0 and chunks[-1][1] == n
+      assert all(chunks[i][1] == chunks[i + 1][0] for i in range(world - 1))
+      sizes = [hi - lo for lo, hi in chunks]
+      assert max(sizes) - min(sizes) <= 1

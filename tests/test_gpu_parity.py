@@ -1,0 +1,233 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (ctypes, xs3d/_abi.py), against the oracle on the
+same seeded inputs, against the committed golden vectors produced by the unmodified reference, against
+the compiled reference when oracle/_ref travelled with the repo, and through size-independent
+properties at BASELINE.json's full sizes.  Integer / mask / contact results must be bit-exact; areas and
+voxel contributions are compared as float32 BIT PATTERNS (stricter than north_star's 1e-5 relative)."""
+import numpy as np
+import pytest
+
+import cases
+import golden_util as gu
+from conftest import bits
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def xs(xs3d_gpu):
+  assert xs3d_gpu._abi.device_count() >= 1
+  return xs3d_gpu
+
+
+@pytest.fixture(scope="module")
+def neurite512():
+  from xs3d import synthetic
+  vol, verts, tans = synthetic.make_neurite(512, seed=0)
+  assert vol.sum() == 377673 and len(verts) == 2724
+  return vol, verts, tans
+
+
+def test_ingest_matches_numpy(xs):
+  """The occupancy-byte volume equals compute_cube() of every block, for aligned/unaligned sizes and both memory orders."""
+  import torch
+  rng = np.random.default_rng(0)
+  for shape in [(64, 48, 32), (33, 17, 9), (1, 1, 1), (16, 1, 5), (128, 64, 2), (50, 50, 50)]:
+    vol = rng.random(shape) < 0.4
+    for order in ("F", "C"):
+      v = np.asfortranarray(vol) if order == "F" else np.ascontiguousarray(vol)
+      with xs.Volume(v) as V:
+        ptr, nbytes = V.cubes()
+        holder = type("H", (), {})()
+        holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        got = torch.as_tensor(holder, device="cuda").cpu().numpy()
+      h = [(s + 1) // 2 for s in shape]
+      pad = np.zeros([2 * x for x in h], bool)
+      pad[: shape[0], : shape[1], : shape[2]] = vol
+      exp = np.zeros(h, np.uint8)
+      for b in range(8):
+        exp |= (pad[(b & 1)::2, ((b >> 1) & 1)::2, (b >> 2)::2].astype(np.uint8) << b)
+      assert np.array_equal(got, exp.ravel(order="F")), (shape, order)
+
+
+def test_golden_small_area_and_sections(xs, golden):
+  for i, vol, p, n, w in gu.small_cases(golden):
+    a, c = xs.cross_sectional_area(vol, p, n, w, return_contact=True)
+    assert bits(a) == bits(golden["small_area"][i]) and c == golden["small_contact"][i], i
+    if i % 2 == 0:
+      a, c = xs.cross_sectional_area(vol, p, n, w, return_contact=True, slow_method=True)
+      assert bits(a) == bits(golden["small_slow_area"][i]) and c == golden["small_slow_contact"][i], i
+      for m in (0, 1, 2):
+        img, c = xs.cross_section(vol, p, n, w, return_contact=True, method=m)
+        exp, ec = gu.section_golden(golden, m, i, vol.shape)
+        assert img.dtype == np.float32 and img.flags.f_contiguous
+        assert gu.same_bits(img, np.asfortranarray(exp)) and c == ec, (i, m)
+
+
+def test_golden_slices(xs, golden):
+  for i, lab, p, n, w, sb, crop, exp, ub in gu.slice_cases(golden):
+    got = xs.slice(lab, p, n, w, sb, crop)
+    assert got.shape == exp.shape and got.dtype == exp.dtype, i
+    if not ub:
+      assert gu.same_bits(got, exp), i
+
+
+def test_random_vs_oracle(xs, oracle):
+  rng = np.random.default_rng(31337)
+  for it in range(300):
+    vol, p, n, w = cases.rand_case(rng, max_side=24)
+    a, c = oracle.area(vol, p, n, w)
+    ga, gc = xs.cross_sectional_area(vol, p, n, w, return_contact=True)
+    assert bits(a) == bits(ga) and c == gc, (it, vol.shape, p, n, w)
+    if it % 6 == 0:
+      s, c = oracle.section(vol, p, n, w, method=0)
+      gs, gc = xs.cross_section(vol, p, n, w, return_contact=True)
+      assert gu.same_bits(s, gs) and c == gc, it
+    if it % 10 == 0:
+      cv = np.ascontiguousarray(vol)   # C-order input: ingested on the device without a host transpose
+      ga2 = xs.cross_sectional_area(cv, p, n, w)
+      assert bits(ga2) == bits(a), it
+
+
+def test_random_slices_vs_oracle(xs, oracle):
+  rng = np.random.default_rng(99)
+  for it in range(200):
+    lab, p, n, w, sb, crop = cases.rand_labels_case(rng, max_side=40)
+    o = oracle.projection(lab, p, n, w, sb, crop)
+    g = xs.slice(lab, p, n, w, sb, crop)
+    assert gu.same_bits(o, g), (it, lab.shape, lab.dtype, p, n, w, sb, crop)
+
+
+def test_reference_known_answers(xs):
+  """automated_test.py:101-160, 252-286, 288-292, 433-465 through the drop-in API."""
+  img = np.zeros([10, 10, 10], dtype=bool, order="F")
+  img[:3, :3, :3] = True
+  img[6:, 6:, :3] = True
+  a, c = xs.cross_sectional_area(img, [1, 1, 1], [0, 0, 1], return_contact=True)
+  assert a == 9 and c > 0
+  assert xs.cross_sectional_area(img, [7, 7, 1], [0, 0, 1]) == 16
+  assert xs.cross_sectional_area(img, [7, 7, 5], [0, 0, 1]) == 0
+  img[:4, :4, :4] = True
+  img[1, 1, 1] = False
+  assert xs.cross_sectional_area(img, [0, 1, 1], [0, 0, 1]) == 15
+  assert xs.cross_sectional_area(np.ones([5, 5, 1], dtype=bool), [0, 0, 0], [0, 0, 1]) == 25
+  labels = np.ones((5, 5, 5), dtype=bool, order="F")
+  for nrm in ([1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]):
+    assert xs.cross_sectional_area(labels, [2, 2, 2], nrm) == 25
+  for nrm in ([1, 1, 0], [1, 0, 1], [0, 1, 1], [-1, 1, 0], [0, -1, 1]):
+    assert np.isclose(xs.cross_sectional_area(labels, [2, 2, 2], nrm), 25 * np.sqrt(2))
+  assert xs.cross_sectional_area(np.zeros([0, 0, 0], dtype=bool), [0, 0, 0], [1, 1, 1]) == 0
+  labels = np.ones([11, 11, 11], dtype=bool)
+  for nrm, exp in (([0, 0, 1], 0b001111), ([0, 1, 0], 0b110011), ([1, 0, 0], 0b111100), ([1, 1, 1], 0b111111)):
+    assert xs.cross_sectional_area(labels, [5, 5, 5], nrm, return_contact=True)[1] == exp
+  assert xs.cross_sectional_area(labels, [100, 5, 2], [1, 1, 1], return_contact=True) == (0.0, 0)
+  lab = np.arange(9, dtype=np.uint8).reshape([3, 3, 1], order="F")
+  assert np.all(xs.slice(lab, [0, 0, 0], [0, 0, 1], standardize_basis=True) == lab[:, :, 0])
+
+
+def test_cross_section_sums_to_area(xs):   # automated_test.py:317-330
+  labels = np.ones((5, 5, 5), dtype=bool, order="F")
+  for theta in range(0, 25, 3):
+    nrm = [0, np.cos(theta / 25 * 2 * np.pi), np.sin(theta / 25 * 2 * np.pi)]
+    a = xs.cross_sectional_area(labels, (2, 2, 2), nrm)
+    for method in (0, 1):
+      img = xs.cross_section(labels, (2, 2, 2), nrm, method=method)
+      assert img.dtype == np.float32 and np.isclose(img.sum(), a)
+
+
+def test_neurite_batch_golden_and_tiers(xs, golden):
+  """1000 skeleton queries on the 256^3 neurite: float32-bit-identical to the reference's outputs."""
+  from xs3d import synthetic
+  vol, verts, tans = synthetic.make_neurite(256, seed=0)
+  qp, qn = synthetic.draw_queries(verts, tans, 1000, seed=1)
+  with xs.Volume(vol) as V:
+    a, c = V.cross_sectional_area_batch(qp, qn, [32, 32, 40], return_contact=True)
+    st = V.stats()
+  assert np.array_equal(bits(a), bits(golden["neurite256_area"]))
+  assert np.array_equal(c, golden["neurite256_contact"])
+  assert st["samples"] > 0 and st["launches"] >= 2
+
+
+def test_neurite512_sweep_parity_and_properties(xs, oracle, neurite512):
+  """BASELINE config 3: the 10k-vertex sweep.  Oracle parity on a 1500-query sample, then
+  size-independent properties on all 10k: determinism, order independence (permuting the batch
+  permutes the result), batch == single-call, C-order ingest == F-order ingest."""
+  from xs3d import synthetic
+  vol, verts, tans = neurite512
+  qp, qn = synthetic.draw_queries(verts, tans, 10000, seed=1)
+  w = [32, 32, 40]
+  with xs.Volume(vol) as V:
+    a, c = V.cross_sectional_area_batch(qp, qn, w, return_contact=True)
+    st = V.stats()
+    a2, c2 = V.cross_sectional_area_batch(qp, qn, w, return_contact=True)
+    perm = np.random.default_rng(0).permutation(len(qp))
+    a3, c3 = V.cross_sectional_area_batch(qp[perm], qn[perm], w, return_contact=True)
+    singles = [V.cross_sectional_area(qp[i], qn[i], w, return_contact=True) for i in range(0, 10000, 500)]
+  oa, oc = oracle.area_batch(vol, qp[:1500], qn[:1500], w)
+  assert np.array_equal(bits(a[:1500]), bits(oa)) and np.array_equal(c[:1500], oc)
+  assert np.array_equal(bits(a), bits(a2)) and np.array_equal(c, c2)
+  assert np.array_equal(bits(a[perm]), bits(a3)) and np.array_equal(c[perm], c3)
+  for k, i in enumerate(range(0, 10000, 500)):
+    assert bits(singles[k][0]) == bits(a[i]) and singles[k][1] == c[i]
+  assert (a > 0).all() and st["escalated_cta"] > 0
+  with xs.Volume(np.ascontiguousarray(vol)) as VC:
+    a4 = VC.cross_sectional_area_batch(qp[:2000], qn[:2000], w)
+  assert np.array_equal(bits(a4), bits(a[:2000]))
+
+
+def test_neurite512_vs_compiled_reference(xs, ref, neurite512):
+  """When oracle/_ref (the unmodified reference, compiled in the dev container) travelled with the repo:
+  all 10k queries of the sweep, bit for bit."""
+  from xs3d import synthetic
+  vol, verts, tans = neurite512
+  qp, qn = synthetic.draw_queries(verts, tans, 10000, seed=1)
+  with xs.Volume(vol) as V:
+    a, c = V.cross_sectional_area_batch(qp, qn, [32, 32, 40], return_contact=True)
+  ra, rc = ref.area_batch(vol, qp, qn, [32, 32, 40])
+  assert np.array_equal(bits(a), bits(ra)) and np.array_equal(c, rc)
+
+
+def test_config0_sphere_and_config1_cylinder(xs, golden):
+  """BASELINE configs 0/1 at full size against the reference's stored outputs (large single sections:
+  CTA tier with the bitmap in shared memory, ring-spilled walk, global hash)."""
+  from xs3d import synthetic
+  sph = synthetic.make_sphere()
+  a, c = xs.cross_sectional_area(sph, [250, 250, 250], [0.01, 0.033, 0.9], [32, 32, 40], return_contact=True)
+  assert bits(a) == bits(golden["sphere_area"]) and c == golden["sphere_contact"]
+  img = xs.cross_section(sph, [250, 250, 250], [0.01, 0.033, 0.9], [32, 32, 40])
+  assert np.count_nonzero(img) == golden["sphere_section_nnz"]
+  assert img.sum(dtype=np.float64) == golden["sphere_section_sum"]
+  xs.set_shape(sph)
+  a2 = xs.cross_sectional_area(sph, [250, 250, 250], [0.01, 0.033, 0.9], [32, 32, 40], use_persistent_data=True)
+  xs.clear_shape()
+  assert bits(a2) == bits(a)
+  del img, sph
+  cyl, axis = synthetic.make_cylinder()
+  with xs.Volume(cyl) as V:
+    for k in range(3):
+      a, c = V.cross_sectional_area(golden["cyl_verts"][k], axis, [32, 32, 40], return_contact=True)
+      assert bits(a) == bits(golden["cyl_area"][k]) and c == golden["cyl_contact"][k], k
+    idx, val, ct = V.cross_section_sparse(golden["cyl_verts"][0], axis, [32, 32, 40])
+  assert len(idx) == golden["cyl_section_nnz"] and len(np.unique(idx)) == len(idx)
+  order = np.argsort(idx)
+  assert val[order].sum(dtype=np.float64) == golden["cyl_section_sum"]
+
+
+def test_slice_batch_matches_single(xs, oracle, neurite512):
+  """BASELINE config 4 proxy at 512^3 / uint64: batched cropped slices equal single-call slices and the oracle."""
+  from xs3d import synthetic
+  vol, verts, tans = neurite512
+  lab = synthetic.make_labels(vol, np.uint64, hashed=True)
+  qp, qn = synthetic.draw_queries(verts, tans, 300, seed=2)
+  w = [32, 32, 40]
+  with xs.Volume(labels=lab) as V:
+    res = V.slice_batch(qp, qn, w, crop=100)
+    res_big = V.slice_batch(qp[:20], qn[:20], w, crop=1000)
+  for i in range(0, 300, 7):
+    o = oracle.projection(lab, qp[i], qn[i], w, True, 100.0)
+    assert gu.same_bits(np.asfortranarray(res[i]), o), i
+  for i in range(0, 20, 4):
+    o = oracle.projection(lab, qp[i], qn[i], w, True, 1000.0)
+    assert gu.same_bits(np.asfortranarray(res_big[i]), o), i
+  o = oracle.projection(lab, qp[0], qn[0], w, True, float("inf"))
+  g = xs.slice(lab, qp[0], qn[0], w)
+  assert gu.same_bits(g, o)

@@ -1,0 +1,75 @@
+"""CPU: the CUDA kernel headers compiled as plain C++ (tests/hostsim) against the oracle.  This covers the
+query logic that runs on the GPU — lattice tiles, bitmap walk, first-touch hash, ownership compaction,
+ordered sums, slice row-scan — on a machine without a GPU.  Device-only concerns (float contraction,
+intrinsics, atomics under real concurrency) are covered by the -m gpu tests."""
+import numpy as np
+import pytest
+
+import cases
+import golden_util as gu
+from conftest import bits
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_area_random(hostsim, oracle, mode):
+  rng = np.random.default_rng(1234 + mode)
+  for it in range(250):
+    vol, p, n, w = cases.rand_case(rng, max_side=18)
+    a, c = oracle.area(vol, p, n, w)
+    a2, c2, _ = hostsim.area_batch(vol, p, n, w, mode)
+    assert bits(a) == bits(a2[0]) and c == c2[0], (it, vol.shape, p, n, w)
+
+
+def test_area_golden(hostsim, golden):
+  for i, vol, p, n, w in gu.small_cases(golden):
+    a2, c2, _ = hostsim.area_batch(vol, p, n, w, 1)
+    assert bits(a2[0]) == bits(golden["small_area"][i]) and c2[0] == golden["small_contact"][i], i
+
+
+def test_area_neurite_tiers(hostsim, oracle):
+  """Warp-tier-sized arena with overflow to the big arena (mode 1) and ring-spill walk (mode 2)."""
+  from xs3d import synthetic
+  vol, verts, tans = synthetic.make_neurite(256, seed=0)
+  qp, qn = synthetic.draw_queries(verts, tans, 400, seed=3)
+  a, c = oracle.area_batch(vol, qp, qn, [32, 32, 40])
+  a1, c1, st = hostsim.area_batch(vol, qp, qn, [32, 32, 40], 1)
+  assert np.array_equal(bits(a), bits(a1)) and np.array_equal(c, c1)
+  assert st[0] > 0, "expected some queries to overflow the small arena"
+  a2, c2, _ = hostsim.area_batch(vol, qp[:60], qn[:60], [32, 32, 40], 2)
+  assert np.array_equal(bits(a[:60]), bits(a2)) and np.array_equal(c[:60], c2)
+
+
+def test_section_random(hostsim, oracle):
+  rng = np.random.default_rng(4321)
+  for it in range(150):
+    vol, p, n, w = cases.rand_case(rng, max_side=14)
+    s, c = oracle.section(vol, p, n, w, method=0)
+    s2, c2 = hostsim.section(vol, p, n, w)
+    assert gu.same_bits(s, s2) and c == c2, it
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_slice_golden(hostsim, golden, mode):
+  for i, lab, p, n, w, sb, crop, exp, ub in gu.slice_cases(golden):
+    got = hostsim.projection(lab, p, n, w, sb, crop, mode)
+    assert got.shape == exp.shape and got.dtype == exp.dtype, i
+    if not ub:
+      assert gu.same_bits(got, exp), i
+
+
+def test_slice_random_vs_oracle(hostsim, oracle):
+  rng = np.random.default_rng(8)
+  for it in range(300):
+    lab, p, n, w, sb, crop = cases.rand_labels_case(rng)
+    o = oracle.projection(lab, p, n, w, sb, crop)
+    for mode in (0, 1):
+      h = hostsim.projection(lab, p, n, w, sb, crop, mode)
+      assert gu.same_bits(o, h), (it, mode)
+
+
+def test_round_half_away(hostsim):
+  xs = np.concatenate([np.array([0.5, -0.5, 1.5, -1.5, 2.5, 0.49999997, -0.49999997, 8388607.5, -8388607.5, 1e9, -0.0, 0.0], np.float32),
+                       np.random.default_rng(0).normal(scale=100, size=2000).astype(np.float32)])
+  for x in xs:
+    exp = np.float32(np.sign(x) * np.floor(np.abs(np.float64(x)) + 0.5))
+    assert hostsim.lib.hostsim_round(float(x)) == exp, x
