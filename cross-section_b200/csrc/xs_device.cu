@@ -119,24 +119,23 @@ __global__ void __launch_bounds__(256) ingest_generic_kernel(const uint8_t* __re
 }
 
 // ------------------------------------------------------------------------------------------------
-// T0: one warp per query, shared-memory arena
+// T0: one warp per query, shared-memory arena (7.3 KB per warp -> 30 warps per SM)
 // ------------------------------------------------------------------------------------------------
-template <int TILES, int MAXN, int HCAP, int MAXM>
+template <int TILES, int MAXN, int HCAP>
 struct WarpLayout {
   static constexpr int W = TILES * 32;
   static constexpr int STRIDE = TILES + 1;
-  static constexpr int O_BITS = 0;
+  static constexpr int O_BITS = 0;                       // lattice bitmap; after the walk: per-sample masks
   static constexpr int O_TESTED = O_BITS + W * STRIDE;
-  static constexpr int O_ORDER = O_TESTED + 4;
-  static constexpr int O_STACK = O_ORDER + MAXN;
-  static constexpr int O_HTAG = O_STACK + MAXN;
-  static constexpr int O_HKEY = O_HTAG + HCAP;
-  static constexpr int O_ITEMS = O_HKEY + HCAP;
-  static constexpr int O_CTL = O_ITEMS + MAXM;
-  static constexpr int WORDS = O_CTL + 32;
+  static constexpr int O_ORDER = O_TESTED + 4;           // uint16 cells
+  static constexpr int O_STACK = O_ORDER + MAXN / 2;
+  static constexpr int O_HASH = O_STACK + MAXN / 2;
+  static constexpr int O_CTL = O_HASH + HCAP;
+  static constexpr int WORDS = O_CTL + 40;
   static_assert(TILES * TILES <= 128, "tested bitmask");
-  static_assert(MAXM <= 2 * HCAP, "vals alias the hash");
-  static_assert(sizeof(Ctl) <= 30 * 4, "ctl slot");
+  static_assert(MAXN <= W * STRIDE, "masks alias the bitmap");
+  static_assert(MAXN <= 512 && W <= 256, "packed hash rank / uint16 cell range");
+  static_assert(sizeof(Ctl) <= 40 * 4, "ctl slot");
 };
 
 struct BatchArgs {
@@ -145,8 +144,7 @@ struct BatchArgs {
   const float* nrm;
   float wx, wy, wz;
   uint32_t nq;
-  float* area;
-  uint8_t* contact;
+  EmitOut out;
   uint32_t* counters;        // see CNT_* below
   unsigned long long* stats; // [0] samples [1] items [2] tiles, [4..9] warp-tier phase cycles, [10..15] CTA-tier phase cycles
   uint32_t* list_in;         // queries to process (null: 0..nq-1)
@@ -154,24 +152,41 @@ struct BatchArgs {
 };
 enum { CNT_NEXT0 = 0, CNT_OVER0 = 1, CNT_NEXT1 = 2, CNT_OVER1 = 3, CNT_NEXT2 = 4, CNT_OVER2 = 5, CNT_WORDS = 8 };
 
-template <int WARPS, int TILES, int MAXN, int HCAP, int MAXM>
-__global__ void __launch_bounds__(WARPS * 32, 1) area_warp_kernel(BatchArgs a) {
-  using L = WarpLayout<TILES, MAXN, HCAP, MAXM>;
+__device__ __forceinline__ void finish_query(const BatchArgs& a, const Ctl& ctl, uint32_t q, int st, int cnt_over, int stats_base) {
+  // thread 0 of the group
+  if (st == Q_OK) {
+    atomicAdd(&a.stats[0], (unsigned long long)ctl.n);
+    atomicAdd(&a.stats[1], (unsigned long long)ctl.m);
+    atomicAdd(&a.stats[2], (unsigned long long)ctl.tiles);
+    for (int i = 0; i < 6; i++) atomicAdd(&a.stats[stats_base + i], (unsigned long long)ctl.t[i]);
+  } else {
+    QInfo qi; qi.item_off = 0; qi.n_items = 0; qi.contact = 0; qi.status = QS_PENDING;
+    a.out.qinfo[q] = qi;
+    if (st == Q_OVERFLOW) a.list_out[atomicAdd(&a.counters[cnt_over], 1u)] = q;   // Q_CAPACITY: the host re-runs the batch
+  }
+}
+__device__ __forceinline__ void zero_query(const BatchArgs& a, uint32_t q) {
+  QInfo qi; qi.item_off = 0; qi.n_items = 0; qi.contact = 0; qi.status = QS_READY;
+  a.out.qinfo[q] = qi;
+}
+
+template <int WARPS, int TILES, int MAXN, int HCAP>
+__global__ void __launch_bounds__(WARPS * 32, 2) area_warp_kernel(BatchArgs a) {
+  using L = WarpLayout<TILES, MAXN, HCAP>;
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t* base = smem + (threadIdx.x >> 5) * L::WORDS;
-  Arena A;
+  Arena<uint16_t> A;
   A.tx = A.ty = TILES; A.stride = L::STRIDE; A.halo = 0;
   A.bits = base + L::O_BITS; A.tested = base + L::O_TESTED;
-  A.order = base + L::O_ORDER; A.max_n = MAXN;
-  A.stack = base + L::O_STACK; A.stack_cap = MAXN; A.spill = nullptr; A.mask = A.stack;
-  A.htag = base + L::O_HTAG; A.hkey = base + L::O_HKEY; A.hcap = HCAP; A.hcap_max = HCAP; A.hash_factor = 0; A.max_probe = 64;
+  A.order = reinterpret_cast<uint16_t*>(base + L::O_ORDER); A.max_n = MAXN;
+  A.stack = reinterpret_cast<uint16_t*>(base + L::O_STACK); A.stack_cap = MAXN; A.spill = nullptr;
+  A.mask = A.bits;
+  PackedHash H;
+  H.slot = base + L::O_HASH; H.cap = HCAP; H.max_probe = 48;
   int lg = 0;
   while ((1 << lg) < HCAP) lg++;
-  A.hshift = 32 - lg;
-  A.items = base + L::O_ITEMS; A.vals = reinterpret_cast<float*>(A.htag); A.max_m = MAXM;
-  A.stage = nullptr; A.stage_cap = 0;
+  H.shift = 32 - lg;
   Ctl& ctl = *reinterpret_cast<Ctl*>(base + L::O_CTL);
-  float* scratch = reinterpret_cast<float*>(base + L::O_CTL + 30);
   WarpGroup g;
   const V3 w = mk(a.wx, a.wy, a.wz);
   for (;;) {
@@ -183,21 +198,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) area_warp_kernel(BatchArgs a) {
     const V3 p = mk(__ldg(a.pos + 3 * q), __ldg(a.pos + 3 * q + 1), __ldg(a.pos + 3 * q + 2));
     const V3 n = mk(__ldg(a.nrm + 3 * q), __ldg(a.nrm + 3 * q + 1), __ldg(a.nrm + 3 * q + 2));
     if (!plane_init(c, a.vol, p, n, w)) {
-      if (g.lane() == 0) { a.area[q] = 0.0f; a.contact[q] = 0; }
+      if (g.lane() == 0) zero_query(a, q);
       continue;
     }
     A.ox = A.oy = c.c - 16 - 32 * (TILES / 2);
-    const int st = run_area(g, c, a.vol, A, ctl, scratch, &a.area[q], &a.contact[q]);
-    if (g.lane() == 0) {
-      if (st != Q_OK) {
-        a.list_out[atomicAdd(&a.counters[CNT_OVER0], 1u)] = q;
-      } else {
-        atomicAdd(&a.stats[0], (unsigned long long)ctl.n);
-        atomicAdd(&a.stats[1], (unsigned long long)ctl.m);
-        atomicAdd(&a.stats[2], (unsigned long long)ctl.tiles);
-        for (int i = 0; i < 6; i++) atomicAdd(&a.stats[4 + i], (unsigned long long)ctl.t[i]);
-      }
-    }
+    const V3 rp = vround(p);
+    H.cbx = (int)rp.x >> 1; H.cby = (int)rp.y >> 1; H.cbz = (int)rp.z >> 1;
+    const int st = run_area_emit(g, c, a.vol, A, H, ctl, q, a.out);
+    if (g.lane() == 0) finish_query(a, ctl, q, st, CNT_OVER0, 4);
     __syncwarp();
   }
 }
@@ -210,7 +218,6 @@ struct SlabCfg {
   size_t stride;
   int max_n;             // order / mask / spill capacity (words each)
   uint32_t hcap_max;     // htag / hkey capacity
-  int max_m;             // items / vals capacity
   size_t bits_words;     // global fallback for the lattice bitmap
   size_t tested_words;   // global fallback for the tile-tested mask
   int hash_factor;
@@ -218,50 +225,55 @@ struct SlabCfg {
 };
 
 __host__ __device__ inline size_t slab_bytes(const SlabCfg& s) {
-  size_t words = (size_t)s.max_n * 3 + (size_t)s.hcap_max * 2 + (size_t)s.max_m * 2 + s.bits_words + s.tested_words;
+  size_t words = (size_t)s.max_n * 3 + (size_t)s.hcap_max * 2 + s.bits_words + s.tested_words;
   return ((words * 4 + 255) / 256) * 256;
 }
 
 constexpr int BLK_THREADS = 512;
 constexpr int BLK_RING = 16384;          // DFS stack ring (words)
 constexpr int BLK_TESTED = 1024;         // tile mask words held in shared memory
-constexpr int BLK_CTL_WORDS = 40;            // Ctl + a few scalars
+constexpr int BLK_CTL_WORDS = 48;        // Ctl + a few scalars
 constexpr int BLK_FIXED_WORDS = 64 + BLK_CTL_WORDS + BLK_RING + BLK_TESTED;
+static_assert(sizeof(Ctl) <= 40 * 4, "ctl slot");
 
-__device__ __forceinline__ void block_arena(Arena& A, const SlabCfg& s, uint32_t* smem, int smem_bits_words, const PlaneCtx& c, const VolView& vol) {
+// returns false when the window does not fit any buffer this CTA owns
+__device__ __forceinline__ bool block_arena(Arena<uint32_t>& A, WideHash& H, const SlabCfg& s, uint32_t* smem, int smem_bits_words,
+                                            const PlaneCtx& c, const VolView& vol) {
   char* slab = s.base + (size_t)blockIdx.x * s.stride;
   uint32_t* p = reinterpret_cast<uint32_t*>(slab);
   A.order = p; p += s.max_n;
   A.mask = p; p += s.max_n;
   A.spill = p; p += s.max_n;
-  A.htag = p; p += s.hcap_max;
-  A.hkey = p; p += s.hcap_max;
-  A.items = p; p += s.max_m;
-  A.vals = reinterpret_cast<float*>(p); p += s.max_m;
+  H.htag = p; p += s.hcap_max;
+  H.hkey = p; p += s.hcap_max;
   uint32_t* g_bits = p; p += s.bits_words;
   uint32_t* g_tested = p;
-  A.max_n = s.max_n; A.max_m = s.max_m;
-  A.hcap = s.hcap_max; A.hcap_max = s.hcap_max; A.hash_factor = s.hash_factor; A.max_probe = s.max_probe;
+  A.max_n = s.max_n;
+  H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
+  H.hx = vol.hx; H.hy = vol.hy;
   int lg = 0;
   while ((1u << lg) < s.hcap_max) lg++;
-  A.hshift = 32 - lg;
+  H.shift = 32 - lg;
   A.stack = smem + 64 + BLK_CTL_WORDS; A.stack_cap = BLK_RING;
-  A.stage = A.stack; A.stage_cap = BLK_RING;       // the ring is idle by the time the ordered sum runs
   bbox_window(c, vol, &A.ox, &A.oy, &A.tx, &A.ty);
   A.stride = A.tx + 1;
   A.halo = 1;
   const size_t words = (size_t)A.ty * 32 * A.stride;
-  A.bits = (words <= (size_t)smem_bits_words) ? (smem + BLK_FIXED_WORDS) : g_bits;
-  A.tested = ((A.tx * A.ty + 31) / 32 <= BLK_TESTED) ? (smem + 64 + BLK_CTL_WORDS + BLK_RING) : g_tested;
+  const size_t twords = (size_t)((A.tx * A.ty + 31) / 32);
+  const bool bits_in_smem = words <= (size_t)smem_bits_words;
+  const bool tested_in_smem = twords <= (size_t)BLK_TESTED;
+  A.bits = bits_in_smem ? (smem + BLK_FIXED_WORDS) : g_bits;
+  A.tested = tested_in_smem ? (smem + 64 + BLK_CTL_WORDS + BLK_RING) : g_tested;
+  if (!bits_in_smem && words > s.bits_words) return false;
+  if (!tested_in_smem && twords > s.tested_words) return false;
+  return true;
 }
 
 __global__ void __launch_bounds__(BLK_THREADS, 1) area_block_kernel(BatchArgs a, SlabCfg s, int smem_bits_words, int cnt_next, int cnt_over, const uint32_t* count_ptr) {
   extern __shared__ __align__(16) uint32_t smem[];
   BlockGroup g(reinterpret_cast<int*>(smem));
   Ctl& ctl = *reinterpret_cast<Ctl*>(smem + 64);
-  static_assert(sizeof(Ctl) <= 36 * 4, "ctl slot");
-  float* scratch = reinterpret_cast<float*>(smem + 64 + 36);
-  int* next = reinterpret_cast<int*>(smem + 64 + 37);
+  int* next = reinterpret_cast<int*>(smem + 64 + 42);
   const V3 w = mk(a.wx, a.wy, a.wz);
   const uint32_t count = count_ptr ? *count_ptr : a.nq;
   for (;;) {
@@ -275,48 +287,90 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) area_block_kernel(BatchArgs a,
     const V3 p = mk(__ldg(a.pos + 3 * q), __ldg(a.pos + 3 * q + 1), __ldg(a.pos + 3 * q + 2));
     const V3 n = mk(__ldg(a.nrm + 3 * q), __ldg(a.nrm + 3 * q + 1), __ldg(a.nrm + 3 * q + 2));
     if (!plane_init(c, a.vol, p, n, w)) {
-      if (threadIdx.x == 0) { a.area[q] = 0.0f; a.contact[q] = 0; }
+      if (threadIdx.x == 0) zero_query(a, q);
       continue;
     }
-    Arena A;
-    block_arena(A, s, smem, smem_bits_words, c, a.vol);
-    const size_t need_words = (size_t)A.ty * 32 * A.stride;
-    int st;
-    if (A.bits != smem + BLK_FIXED_WORDS && need_words > s.bits_words) st = Q_OVERFLOW;   // window larger than any buffer we own
-    else if (A.tested != smem + 64 + BLK_CTL_WORDS + BLK_RING && (size_t)((A.tx * A.ty + 31) / 32) > s.tested_words) st = Q_OVERFLOW;
-    else st = run_area(g, c, a.vol, A, ctl, scratch, &a.area[q], &a.contact[q]);
-    if (threadIdx.x == 0) {
-      if (st != Q_OK) {
-        a.list_out[atomicAdd(&a.counters[cnt_over], 1u)] = q;
-      } else {
-        atomicAdd(&a.stats[0], (unsigned long long)ctl.n);
-        atomicAdd(&a.stats[1], (unsigned long long)ctl.m);
-        atomicAdd(&a.stats[2], (unsigned long long)ctl.tiles);
-        for (int i = 0; i < 6; i++) atomicAdd(&a.stats[10 + i], (unsigned long long)ctl.t[i]);
-      }
-    }
+    Arena<uint32_t> A;
+    WideHash H;
+    int st = Q_OVERFLOW;
+    if (block_arena(A, H, s, smem, smem_bits_words, c, a.vol)) st = run_area_emit(g, c, a.vol, A, H, ctl, q, a.out);
+    if (threadIdx.x == 0) finish_query(a, ctl, q, st, cnt_over, 10);
   }
 }
 
-// Path B for one query.  result[0] = status, result[1] = nnz, result[2] = contact
+// Path B for one query.  result[0] = status, result[1] = records, result[2] = contact; geom[0] = the plane.
 __global__ void __launch_bounds__(BLK_THREADS, 1) section_block_kernel(VolView vol, V3 p, V3 n, V3 w, SlabCfg s, int smem_bits_words,
-                                                                        uint64_t* out_idx, float* out_val, uint32_t out_cap, uint32_t* result) {
+                                                                        PolyRec* out_rec, uint64_t* out_idx, uint32_t out_cap,
+                                                                        PlaneGeom* geom, uint32_t* result) {
   extern __shared__ __align__(16) uint32_t smem[];
   BlockGroup g(reinterpret_cast<int*>(smem));
   Ctl& ctl = *reinterpret_cast<Ctl*>(smem + 64);
-  uint8_t* ct = reinterpret_cast<uint8_t*>(smem + 64 + 36);
+  uint8_t* ct = reinterpret_cast<uint8_t*>(smem + 64 + 42);
   PlaneCtx c;
   if (threadIdx.x == 0) { result[0] = Q_OK; result[1] = 0; result[2] = 0; }
   if (!plane_init(c, vol, p, n, w)) return;
-  Arena A;
-  block_arena(A, s, smem, smem_bits_words, c, vol);
-  const size_t need_words = (size_t)A.ty * 32 * A.stride;
-  int st;
-  if (A.bits != smem + BLK_FIXED_WORDS && need_words > s.bits_words) st = Q_OVERFLOW;
-  else if (A.tested != smem + 64 + BLK_CTL_WORDS + BLK_RING && (size_t)((A.tx * A.ty + 31) / 32) > s.tested_words) st = Q_OVERFLOW;
-  else st = run_section(g, c, vol, A, ctl, out_idx, out_val, out_cap, ct);
+  Arena<uint32_t> A;
+  WideHash H;
+  int st = Q_OVERFLOW;
+  if (threadIdx.x == 0) ctl.counter = 0u;
   __syncthreads();
-  if (threadIdx.x == 0) { result[0] = (uint32_t)st; result[1] = ctl.counter; result[2] = (st == Q_OK) ? *ct : 0u; }
+  if (block_arena(A, H, s, smem, smem_bits_words, c, vol)) st = run_section_emit(g, c, vol, A, H, ctl, out_rec, out_idx, out_cap, ct);
+  __syncthreads();
+  if (threadIdx.x == 0) { geom[0] = c.g; result[0] = (uint32_t)st; result[1] = ctl.counter; result[2] = (st == Q_OK) ? *ct : 0u; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// polygon kernel: one thread per polygon record, no shared memory, full occupancy
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) poly_eval_kernel(const PolyRec* __restrict__ polys, const PlaneGeom* __restrict__ geom,
+                                                        float* __restrict__ vals, const uint32_t* __restrict__ count_ptr,
+                                                        uint32_t start, uint32_t cap) {
+  uint32_t n = *count_ptr;
+  if (n > cap) n = cap;
+  for (uint32_t i = start + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const PolyRec r = polys[i];
+    const PlaneGeom g = geom[r.q];
+    vals[i] = poly_eval(r, g);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// combine kernel: one CTA per query; item values in parallel, then the reference's ordered sums
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) combine_kernel(const ItemRec* __restrict__ items, float* __restrict__ vals, const QInfo* __restrict__ qinfo,
+                                                      const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count, uint32_t nq,
+                                                      float* __restrict__ area, uint8_t* __restrict__ contact) {
+  const uint32_t count = list ? *list_count : nq;
+  for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
+    const uint32_t q = list ? list[i] : i;
+    const QInfo qi = qinfo[q];
+    if (qi.status != QS_READY) continue;
+    const ItemRec* it = items + qi.item_off;
+    const uint32_t n = qi.n_items;
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+      const ItemRec e = it[k];
+      vals[e.poly] = item_value(e, vals);       // an item's polygons are its own: safe to overwrite its first slot
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      OrderedSum s;
+      s.init();
+      for (uint32_t b = 0; b < n; b += 32) {
+        const uint32_t k = b + threadIdx.x;
+        float v = 0.0f;
+        int first = 0;
+        if (k < n) { const ItemRec e = it[k]; v = vals[e.poly]; first = (e.meta >> 5) & 1; }
+        const int len = (n - b) < 32u ? (int)(n - b) : 32;
+        for (int j = 0; j < len; j++) {
+          const float vj = __shfl_sync(0xffffffffu, v, j);
+          const int fj = __shfl_sync(0xffffffffu, first, j);
+          s.add(vj, fj != 0);
+        }
+      }
+      if (threadIdx.x == 0) { area[q] = s.finish(); contact[q] = (uint8_t)qi.contact; }
+    }
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -338,8 +392,9 @@ struct DevBuf {
 };
 
 // warp tier configuration (shared memory per warp = WarpLayout::WORDS * 4 bytes)
-constexpr int T0_WARPS = 14, T0_TILES = 3, T0_MAXN = 384, T0_HCAP = 1024, T0_MAXM = 768;
-using T0Layout = WarpLayout<T0_TILES, T0_MAXN, T0_HCAP, T0_MAXM>;
+constexpr int T0_WARPS = 15, T0_TILES = 3, T0_MAXN = 384, T0_HCAP = 1024;   // 2 CTAs per SM -> 30 warps per SM
+using T0Layout = WarpLayout<T0_TILES, T0_MAXN, T0_HCAP>;
+#define T0_KERNEL area_warp_kernel<T0_WARPS, T0_TILES, T0_MAXN, T0_HCAP>
 
 struct xs3d_volume {
   int device = 0;
@@ -353,12 +408,17 @@ struct xs3d_volume {
   bool labels_loaded = false;
   // batch workspace
   DevBuf q_pos, q_nrm, q_area, q_contact, lists, counters, slab1, slab2, sec_idx, sec_val, misc;
+  DevBuf polys, items, vals, geom, qinfo;
+  uint64_t poly_cap = 0, item_cap = 0;
   SlabCfg cfg1{}, cfg2{};
   uint32_t* h_counters = nullptr;   // pinned: CNT_WORDS counters + 8 u64 stats
   uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   int sm_count = 0, smem_optin = 0;
   bool kernels_configured = false;
+  bool own_stream = true;
+  cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  float timing[6] = {0, 0, 0, 0, 0, 0};   // ms of the last call: warp-tier, CTA-tier, worst-case query kernels, ingest, polygon, combine
 };
 
 static VolView view_of(const xs3d_volume* v) {
@@ -375,7 +435,7 @@ static int configure_kernels(xs3d_volume* v) {
   if (v->kernels_configured) return XS3D_OK;
   const int t0_bytes = T0_WARPS * T0Layout::WORDS * 4;
   if (t0_bytes > v->smem_optin) return fail(XS3D_ERR_UNSUPPORTED, "device shared memory too small for the warp tier");
-  CK(cudaFuncSetAttribute(area_warp_kernel<T0_WARPS, T0_TILES, T0_MAXN, T0_HCAP, T0_MAXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, t0_bytes));
+  CK(cudaFuncSetAttribute(T0_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, t0_bytes));
   CK(cudaFuncSetAttribute(area_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
   CK(cudaFuncSetAttribute(section_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
   v->kernels_configured = true;
@@ -399,8 +459,9 @@ extern "C" int xs3d_volume_create(int device, uint64_t sx, uint64_t sy, uint64_t
   v->sm_count = prop.multiProcessorCount;
   v->smem_optin = (int)prop.sharedMemPerBlockOptin;
   CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 8; i++) CK(cudaEventCreate(&v->ev[i]));
   RET(v->cubes.ensure(hx * hy * hz + 64));
-  CK(cudaHostAlloc((void**)&v->h_counters, 256, cudaHostAllocDefault));
+  CK(cudaHostAlloc((void**)&v->h_counters, 512, cudaHostAllocDefault));
   *out = v;
   return XS3D_OK;
 }
@@ -408,9 +469,11 @@ extern "C" int xs3d_volume_create(int device, uint64_t sx, uint64_t sy, uint64_t
 extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
   if (!v) return XS3D_OK;
   cudaSetDevice(v->device);
-  if (v->stream) { cudaStreamSynchronize(v->stream); cudaStreamDestroy(v->stream); }
+  if (v->stream) { cudaStreamSynchronize(v->stream); if (v->own_stream) cudaStreamDestroy(v->stream); }
+  for (int i = 0; i < 8; i++) if (v->ev[i]) cudaEventDestroy(v->ev[i]);
   DevBuf* bufs[] = { &v->cubes, &v->raw, &v->labels, &v->q_pos, &v->q_nrm, &v->q_area, &v->q_contact, &v->lists,
-                     &v->counters, &v->slab1, &v->slab2, &v->sec_idx, &v->sec_val, &v->misc };
+                     &v->counters, &v->slab1, &v->slab2, &v->sec_idx, &v->sec_val, &v->misc,
+                     &v->polys, &v->items, &v->vals, &v->geom, &v->qinfo };
   for (DevBuf* b : bufs) b->release();
   if (v->h_counters) cudaFreeHost(v->h_counters);
   delete v;
@@ -456,8 +519,11 @@ extern "C" int xs3d_volume_load(xs3d_volume* v, const uint8_t* binimg, int mem, 
     CK(cudaMemcpyAsync(v->raw.p, binimg, voxels, cudaMemcpyHostToDevice, v->stream));
     d_img = (const uint8_t*)v->raw.p;
   }
+  CK(cudaEventRecord(v->ev[6], v->stream));
   RET(launch_ingest(v, d_img, c_order));
+  CK(cudaEventRecord(v->ev[7], v->stream));
   CK(cudaStreamSynchronize(v->stream));
+  CK(cudaEventElapsedTime(&v->timing[3], v->ev[6], v->ev[7]));
   v->loaded = true;
   return XS3D_OK;
 }
@@ -482,11 +548,9 @@ static SlabCfg make_cfg(const xs3d_volume* v, bool worst_case) {
   const size_t win = (size_t)(psx + 2 + 64);
   s.bits_words = ((win + 31) / 32 + 1) * (win + 32);
   s.tested_words = (((win + 31) / 32) * ((win + 31) / 32) + 31) / 32 + 1;
-  const unsigned long long nblocks = (unsigned long long)v->hx * v->hy * v->hz;
   if (!worst_case) {
     s.max_n = 1 << 16;
     s.hcap_max = 1u << 19;
-    s.max_m = 1 << 17;
     s.hash_factor = 8;
     s.max_probe = 256;
   } else {
@@ -497,11 +561,9 @@ static SlabCfg make_cfg(const xs3d_volume* v, bool worst_case) {
     // the same table serves path A (keys = blocks) and path B (keys = voxels): never more than 27 per sample
     const unsigned long long nvoxels = (unsigned long long)v->sx * v->sy * v->sz;
     const unsigned long long keys = std::min<unsigned long long>(27ull * mn, nvoxels + 1);
-    const unsigned long long blocks = std::min<unsigned long long>(27ull * mn, nblocks + 1);
     unsigned long long cap = 1024;
     while (cap < 2 * keys) cap <<= 1;
     s.hcap_max = (uint32_t)std::min<unsigned long long>(cap, 1ull << 31);
-    s.max_m = (int)std::min<unsigned long long>(blocks, 0x7fffffffull);
     s.hash_factor = 64;
     s.max_probe = 1 << 30;     // the table can never fill; the bound only turns a logic error into a loud failure
   }
@@ -515,7 +577,17 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
   RET(v->q_area.ensure(n * 4 + 64));
   RET(v->q_contact.ensure(n + 64));
   RET(v->lists.ensure(n * 4 * 3 + 64));
-  RET(v->counters.ensure(256));
+  RET(v->counters.ensure(512));
+  RET(v->geom.ensure(n * sizeof(PlaneGeom) + 64));
+  RET(v->qinfo.ensure(n * sizeof(QInfo) + 64));
+  if (v->poly_cap == 0) {
+    // first guess: ~1k polygons per query (a neurite-scale section needs 200-600); grown on demand
+    v->poly_cap = std::max<uint64_t>(1ull << 20, n * 1024ull);
+    v->item_cap = v->poly_cap / 2;
+  }
+  RET(v->polys.ensure(v->poly_cap * sizeof(PolyRec) + 64));
+  RET(v->vals.ensure(v->poly_cap * 4 + 64));
+  RET(v->items.ensure(v->item_cap * sizeof(ItemRec) + 64));
   if (!v->slab1.p) {
     v->cfg1 = make_cfg(v, false);
     v->cfg1.stride = slab_bytes(v->cfg1);
@@ -534,59 +606,106 @@ static int ensure_worst_case_slab(xs3d_volume* v) {
   return XS3D_OK;
 }
 
-// Core of the batched area path; all pointers are device pointers.  skip_warp_tier: single queries go
-// straight to the CTA tier.
+// Core of the batched area path; all pointers are device pointers.  skip_warp_tier: tiny batches go
+// straight to the CTA tier.  Launch sequence (no host synchronisation in between):
+//   warp-tier query kernel -> CTA-tier query kernel (what the warp tier could not fit) -> polygon kernel
+//   -> combine kernel;  then one sync to read the counters.  Rare paths after that sync: queries that
+//   overflowed the CTA tier's slab re-run with the worst-case slab; a full record buffer grows and the
+//   batch re-runs.
 static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, const float* d_nrm, const float w[3],
                              float* d_area, uint8_t* d_contact, bool skip_warp_tier) {
   uint32_t* d_cnt = (uint32_t*)v->counters.p;
   unsigned long long* d_stats = (unsigned long long*)(d_cnt + CNT_WORDS);
+  uint32_t* d_emit = d_cnt + 64;     // [0] polygons [1] items [2] capacity flag
   uint32_t* list0 = (uint32_t*)v->lists.p;
   uint32_t* list1 = list0 + n;
   uint32_t* list2 = list1 + n;
-  CK(cudaMemsetAsync(d_cnt, 0, 256, v->stream));
-  BatchArgs a;
-  a.vol = view_of(v);
-  a.pos = d_pos; a.nrm = d_nrm; a.wx = w[0]; a.wy = w[1]; a.wz = w[2];
-  a.nq = (uint32_t)n; a.area = d_area; a.contact = d_contact; a.counters = d_cnt; a.stats = d_stats;
   int launches = 0;
-  if (!skip_warp_tier) {
-    a.list_in = nullptr; a.list_out = list0;
-    const int grid = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count);
-    area_warp_kernel<T0_WARPS, T0_TILES, T0_MAXN, T0_HCAP, T0_MAXM>
-        <<<grid, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, v->stream>>>(a);
+  for (int attempt = 0; attempt < 8; attempt++) {
+    CK(cudaMemsetAsync(d_cnt, 0, 512, v->stream));
+    BatchArgs a;
+    a.vol = view_of(v);
+    a.pos = d_pos; a.nrm = d_nrm; a.wx = w[0]; a.wy = w[1]; a.wz = w[2];
+    a.nq = (uint32_t)n; a.counters = d_cnt; a.stats = d_stats;
+    a.out.polys = (PolyRec*)v->polys.p; a.out.items = (ItemRec*)v->items.p; a.out.geom = (PlaneGeom*)v->geom.p;
+    a.out.qinfo = (QInfo*)v->qinfo.p; a.out.counters = d_emit;
+    a.out.poly_cap = (uint32_t)std::min<uint64_t>(v->poly_cap, 0xffffffffull); a.out.item_cap = (uint32_t)std::min<uint64_t>(v->item_cap, 0xffffffffull);
+    CK(cudaEventRecord(v->ev[0], v->stream));
+    if (!skip_warp_tier) {
+      a.list_in = nullptr; a.list_out = list0;
+      const int grid = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * 2);
+      T0_KERNEL<<<grid, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, v->stream>>>(a);
+      CK(cudaGetLastError());
+      launches++;
+    }
+    CK(cudaEventRecord(v->ev[1], v->stream));
+    if (!skip_warp_tier) {
+      a.list_in = list0; a.list_out = list1;
+      area_block_kernel<<<v->sm_count, BLK_THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT1, CNT_OVER1, d_cnt + CNT_OVER0);
+    } else {
+      a.list_in = nullptr; a.list_out = list1;
+      const int grid = (int)std::min<uint64_t>(n, (uint64_t)v->sm_count);
+      area_block_kernel<<<grid, BLK_THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT1, CNT_OVER1, nullptr);
+    }
     CK(cudaGetLastError());
     launches++;
-    a.list_in = list0; a.list_out = list1;
-    area_block_kernel<<<v->sm_count, BLK_THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT1, CNT_OVER1, d_cnt + CNT_OVER0);
+    CK(cudaEventRecord(v->ev[2], v->stream));
+    poly_eval_kernel<<<v->sm_count * 8, 256, 0, v->stream>>>(a.out.polys, a.out.geom, (float*)v->vals.p, d_emit, 0u, a.out.poly_cap);
     CK(cudaGetLastError());
     launches++;
-  } else {
-    a.list_in = nullptr; a.list_out = list1;
-    const int grid = (int)std::min<uint64_t>(n, (uint64_t)v->sm_count);
-    area_block_kernel<<<grid, BLK_THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT1, CNT_OVER1, nullptr);
+    CK(cudaEventRecord(v->ev[3], v->stream));
+    combine_kernel<<<(unsigned)std::min<uint64_t>(n, 65535ull * 16), 128, 0, v->stream>>>(a.out.items, (float*)v->vals.p, a.out.qinfo, nullptr, nullptr, (uint32_t)n, d_area, d_contact);
     CK(cudaGetLastError());
     launches++;
-  }
-  CK(cudaMemcpyAsync(v->h_counters, d_cnt, 256, cudaMemcpyDeviceToHost, v->stream));
-  CK(cudaStreamSynchronize(v->stream));
-  uint32_t over0 = v->h_counters[CNT_OVER0], over1 = v->h_counters[CNT_OVER1];
-  uint32_t over2 = 0;
-  if (over1 > 0) {
-    RET(ensure_worst_case_slab(v));
-    a.list_in = list1; a.list_out = list2;
-    area_block_kernel<<<1, BLK_THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg2, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVER1);
-    CK(cudaGetLastError());
-    launches++;
-    CK(cudaMemcpyAsync(v->h_counters, d_cnt, 256, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaEventRecord(v->ev[4], v->stream));
+    CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, v->stream));
     CK(cudaStreamSynchronize(v->stream));
-    over2 = v->h_counters[CNT_OVER2];
+    CK(cudaEventElapsedTime(&v->timing[0], v->ev[0], v->ev[1]));
+    CK(cudaEventElapsedTime(&v->timing[1], v->ev[1], v->ev[2]));
+    CK(cudaEventElapsedTime(&v->timing[4], v->ev[2], v->ev[3]));
+    CK(cudaEventElapsedTime(&v->timing[5], v->ev[3], v->ev[4]));
+    v->timing[2] = 0.0f;
+    const uint32_t over0 = v->h_counters[CNT_OVER0], over1 = v->h_counters[CNT_OVER1];
+    const uint32_t* he = v->h_counters + 64;
+    uint32_t over2 = 0;
+    bool capacity = he[2] != 0;
+    uint32_t polys_used = he[0];
+    if (!capacity && over1 > 0) {
+      // worst-case slab, one CTA, only for the queries the CTA tier could not fit
+      RET(ensure_worst_case_slab(v));
+      a.list_in = list1; a.list_out = list2;
+      CK(cudaEventRecord(v->ev[0], v->stream));
+      area_block_kernel<<<1, BLK_THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg2, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVER1);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(v->ev[1], v->stream));
+      poly_eval_kernel<<<v->sm_count * 8, 256, 0, v->stream>>>(a.out.polys, a.out.geom, (float*)v->vals.p, d_emit, polys_used, a.out.poly_cap);
+      combine_kernel<<<1024, 128, 0, v->stream>>>(a.out.items, (float*)v->vals.p, a.out.qinfo, list1, d_cnt + CNT_OVER1, (uint32_t)n, d_area, d_contact);
+      CK(cudaGetLastError());
+      launches += 3;
+      CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, v->stream));
+      CK(cudaStreamSynchronize(v->stream));
+      CK(cudaEventElapsedTime(&v->timing[2], v->ev[0], v->ev[1]));
+      over2 = v->h_counters[CNT_OVER2];
+      capacity = he[2] != 0;
+      polys_used = he[0];
+    }
+    const unsigned long long* hs = (const unsigned long long*)(v->h_counters + CNT_WORDS);
+    v->stats[0] = hs[0]; v->stats[1] = hs[1]; v->stats[2] = hs[2] * 1024ull;
+    v->stats[3] = over0; v->stats[4] = over1; v->stats[5] = (uint64_t)launches; v->stats[6] = over2; v->stats[7] = polys_used;
+    for (int i = 0; i < 12; i++) v->prof[i] = hs[4 + i];
+    if (capacity) {
+      // a record buffer filled up: double it and run the batch again
+      v->poly_cap *= 2; v->item_cap *= 2;
+      if (v->poly_cap > (1ull << 31)) return fail(XS3D_ERR_CAPACITY, "polygon record buffer would exceed 2^31 entries; split the batch");
+      RET(v->polys.ensure(v->poly_cap * sizeof(PolyRec) + 64));
+      RET(v->vals.ensure(v->poly_cap * 4 + 64));
+      RET(v->items.ensure(v->item_cap * sizeof(ItemRec) + 64));
+      continue;
+    }
+    if (over2 > 0) return fail(XS3D_ERR_CAPACITY, "a query exceeded the worst-case working set");
+    return XS3D_OK;
   }
-  const unsigned long long* hs = (const unsigned long long*)(v->h_counters + CNT_WORDS);
-  v->stats[0] = hs[0]; v->stats[1] = hs[1]; v->stats[2] = hs[2] * 1024ull;
-  v->stats[3] = over0; v->stats[4] = over1; v->stats[5] = (uint64_t)launches; v->stats[6] = over2; v->stats[7] = 0;
-  for (int i = 0; i < 12; i++) v->prof[i] = hs[4 + i];
-  if (over2 > 0) return fail(XS3D_ERR_CAPACITY, "a query exceeded the worst-case working set");
-  return XS3D_OK;
+  return fail(XS3D_ERR_CAPACITY, "record buffers kept overflowing");
 }
 
 extern "C" int xs3d_area_batch(xs3d_volume* v, uint64_t n, const float* pos, const float* normal, const float anisotropy[3],
@@ -626,6 +745,22 @@ extern "C" int xs3d_volume_stats(xs3d_volume* v, uint64_t stats[8]) {
   return XS3D_OK;
 }
 
+extern "C" int xs3d_volume_timing(xs3d_volume* v, float ms[6]) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  for (int i = 0; i < 6; i++) ms[i] = v->timing[i];
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_volume_set_stream(xs3d_volume* v, void* cuda_stream) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  CK(cudaSetDevice(v->device));
+  CK(cudaStreamSynchronize(v->stream));
+  if (v->own_stream) CK(cudaStreamDestroy(v->stream));
+  v->stream = (cudaStream_t)cuda_stream;
+  v->own_stream = false;
+  return XS3D_OK;
+}
+
 extern "C" int xs3d_volume_profile(xs3d_volume* v, uint64_t prof[12]) {
   if (!v) return fail(XS3D_ERR_ARG, "null volume");
   for (int i = 0; i < 12; i++) prof[i] = v->prof[i];
@@ -633,31 +768,36 @@ extern "C" int xs3d_volume_profile(xs3d_volume* v, uint64_t prof[12]) {
 }
 
 // ---- path B ----------------------------------------------------------------------------------------
+// One CTA floods the section and emits one record per distinct foreground voxel it touches; the polygon
+// kernel values them; entries with value > 0 are the reference's non-zero voxels (xs3d.hpp:526-528).
 static int section_fast_sparse(xs3d_volume* v, const float p[3], const float n[3], const float w[3],
                                uint64_t** d_idx, float** d_val, uint64_t* nnz, uint8_t* contact) {
   RET(configure_kernels(v));
   RET(ensure_worst_case_slab(v));
-  RET(v->counters.ensure(256));
-  // output capacity: every sample can introduce at most 27 voxels, bounded by the volume
+  RET(v->counters.ensure(512));
   const unsigned long long voxels = (unsigned long long)v->sx * v->sy * v->sz;
+  if (voxels >= 0xffffffffull) return fail(XS3D_ERR_UNSUPPORTED, "cross_section on volumes with >= 2^32 voxels");
+  // every sample can introduce at most 27 voxels, bounded by the volume
   unsigned long long cap = std::min<unsigned long long>(27ull * (unsigned long long)v->cfg2.max_n, voxels);
   cap = std::min<unsigned long long>(cap, 0x7fffffffull);
-  if (voxels >= 0xffffffffull) return fail(XS3D_ERR_UNSUPPORTED, "cross_section on volumes with >= 2^32 voxels");
   RET(v->sec_idx.ensure(cap * 8 + 64));
   RET(v->sec_val.ensure(cap * 4 + 64));
+  RET(v->misc.ensure(cap * sizeof(PolyRec) + 1024));
   SlabCfg s = v->cfg2;
   s.hash_factor = 32;   // >= 27 voxels per sample: the dedupe set can never fill
-  // the voxel set may need more slots than the block table: clamp to what the slab holds (htag+hkey are contiguous)
-  s.hcap_max = v->cfg2.hcap_max;
-  uint32_t* d_res = (uint32_t*)v->counters.p + 44;
+  uint32_t* d_res = (uint32_t*)v->counters.p + 96;
+  PlaneGeom* d_geom = (PlaneGeom*)((char*)v->misc.p + ((cap * sizeof(PolyRec) + 255) / 256) * 256);
+  PolyRec* d_rec = (PolyRec*)v->misc.p;
   section_block_kernel<<<1, BLK_THREADS, block_smem_bytes(v), v->stream>>>(view_of(v), mk(p[0], p[1], p[2]), mk(n[0], n[1], n[2]), mk(w[0], w[1], w[2]),
-                                                                            s, block_smem_bits_words(v), (uint64_t*)v->sec_idx.p, (float*)v->sec_val.p,
-                                                                            (uint32_t)cap, d_res);
+                                                                            s, block_smem_bits_words(v), d_rec, (uint64_t*)v->sec_idx.p,
+                                                                            (uint32_t)cap, d_geom, d_res);
+  CK(cudaGetLastError());
+  poly_eval_kernel<<<v->sm_count * 8, 256, 0, v->stream>>>(d_rec, d_geom, (float*)v->sec_val.p, d_res + 1, 0u, (uint32_t)cap);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(v->h_counters, d_res, 16, cudaMemcpyDeviceToHost, v->stream));
   CK(cudaStreamSynchronize(v->stream));
   if (v->h_counters[0] != Q_OK) return fail(XS3D_ERR_CAPACITY, "cross_section exceeded the worst-case working set");
-  *nnz = v->h_counters[1];
+  *nnz = v->h_counters[1];        // touched voxels; callers keep those with value > 0
   *contact = (uint8_t)v->h_counters[2];
   *d_idx = (uint64_t*)v->sec_idx.p;
   *d_val = (float*)v->sec_val.p;
@@ -678,11 +818,23 @@ extern "C" int xs3d_section_sparse(xs3d_volume* v, const float pos[3], const flo
   uint64_t* d_idx = nullptr; float* d_val = nullptr;
   if (method == 0) RET(section_fast_sparse(v, pos, normal, anisotropy, &d_idx, &d_val, nnz, contact));
   else RET(xs_section_slow_sparse(v, pos, normal, anisotropy, method, &d_idx, &d_val, nnz, contact));
-  if (*nnz > cap) return fail(XS3D_ERR_ARG, "sparse output buffers too small (nnz returned)");
-  if (*nnz) {
-    CK(cudaMemcpyAsync(idx, d_idx, *nnz * 8, cudaMemcpyDeviceToHost, v->stream));
-    CK(cudaMemcpyAsync(val, d_val, *nnz * 4, cudaMemcpyDeviceToHost, v->stream));
+  // bring the touched entries back and keep the non-zero ones (method 0 emits every touched voxel)
+  const uint64_t touched = *nnz;
+  std::vector<uint64_t> hi(touched);
+  std::vector<float> hv(touched);
+  if (touched) {
+    CK(cudaMemcpyAsync(hi.data(), d_idx, touched * 8, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaMemcpyAsync(hv.data(), d_val, touched * 4, cudaMemcpyDeviceToHost, v->stream));
     CK(cudaStreamSynchronize(v->stream));
+  }
+  uint64_t k = 0;
+  for (uint64_t i = 0; i < touched; i++) k += (method == 0) ? (hv[i] > 0.0f) : 1;
+  *nnz = k;
+  if (k > cap) return fail(XS3D_ERR_ARG, "sparse output buffers too small (nnz returned)");
+  k = 0;
+  for (uint64_t i = 0; i < touched; i++) {
+    if (method == 0 && !(hv[i] > 0.0f)) continue;
+    idx[k] = hi[i]; val[k] = hv[i]; k++;
   }
   return XS3D_OK;
 }
@@ -763,7 +915,8 @@ extern "C" int xs3d_section(const uint8_t* binimg, uint64_t sx, uint64_t sy, uin
     CK(cudaMemcpyAsync(idx.data(), d_idx, nnz * 8, cudaMemcpyDeviceToHost, v->stream));
     CK(cudaMemcpyAsync(val.data(), d_val, nnz * 4, cudaMemcpyDeviceToHost, v->stream));
     CK(cudaStreamSynchronize(v->stream));
-    for (uint64_t i = 0; i < nnz; i++) out[idx[i]] = val[i];   // scatter into the caller's zero-filled image
+    for (uint64_t i = 0; i < nnz; i++)
+      if (method != 0 || val[i] > 0.0f) out[idx[i]] = val[i];   // scatter into the caller's zero-filled image (xs3d.hpp:526-528)
   }
   return XS3D_OK;
 }

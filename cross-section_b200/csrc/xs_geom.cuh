@@ -35,15 +35,40 @@ XS_HD void geom_init(PlaneGeom& g, V3 pos, V3 unit_n, V3 w) {
   g.max_pts = ((unit_n.x == 0.0f) + (unit_n.y == 0.0f) + (unit_n.z == 0.0f)) >= 1 ? 4 : 6;
 }
 
+// A polygon of up to 6 vertices held in named slots so that, after full unrolling, every access has a
+// compile-time index and the whole thing lives in registers (no local-memory stack).
+struct Poly {
+  V3 p[6];
+  int n;
+};
+
+XS_HD void poly_push(Poly& q, V3 v) {
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    if (j == q.n) q.p[j] = v;
+  }
+  q.n++;
+}
+XS_HD bool poly_has(const Poly& q, V3 v) {
+  bool dup = false;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    if (j < q.n) dup = dup || vclose(q.p[j], v);
+  }
+  return dup;
+}
+
 // Intersect the plane with the 12 edges of the cube of side S whose low voxel is (x,y,z)
 // (S=1: the voxel itself, spanning [x-.5,x+.5]; S=2: the block spanning [x-.5,x+1.5]).
+// Edge order, corner de-duplication and the 4/6 vertex cap follow xs3d.hpp:183-233 / 307-358.
 template <int S>
-XS_HD int plane_cube_points(float x, float y, float z, const PlaneGeom& g, V3* pts) {
+XS_HD void plane_cube_points(float x, float y, float z, const PlaneGeom& g, Poly& q) {
+  q.n = 0;
   const float fS = (float)S;
   const V3 low = mk(x, y, z);
   const V3 centre = (S == 1) ? low : vadd(low, mk(0.5f, 0.5f, 0.5f));
   const float dist = fabsf(vdot(vsub(centre, g.pos), g.n));
-  if (dist > (S == 1 ? XS_FAR1 : XS_FAR2)) return 0;
+  if (dist > (S == 1 ? XS_FAR1 : XS_FAR2)) return;
 
   const V3 minpt = vadd(low, mk(-0.5f, -0.5f, -0.5f));
   const V3 rel = vsub(g.pos, minpt);
@@ -53,21 +78,24 @@ XS_HD int plane_cube_points(float x, float y, float z, const PlaneGeom& g, V3* p
   cproj[1] = vdot(vsub(rel, mk(0.0f, fS, fS)), g.n);
   cproj[2] = vdot(vsub(rel, mk(fS, 0.0f, fS)), g.n);
   cproj[3] = vdot(vsub(rel, mk(fS, fS, 0.0f)), g.n);
+  V3 corner[4];
+  corner[0] = minpt;                                   // (0,0,0) + minpt is exact
+  corner[1] = vadd(mk(0.0f, fS, fS), minpt);
+  corner[2] = vadd(mk(fS, 0.0f, fS), minpt);
+  corner[3] = vadd(mk(fS, fS, 0.0f), minpt);
 
   const float bound = (S == 1) ? XS_BOUND1 : XS_BOUND2;
   const float tmax = (S == 1) ? XS_BOUND2 : XS_TMAX2;   // 1+eps / 2+eps
-  int np = 0;
+  bool done = false;
 #pragma unroll
   for (int i = 0; i < 12; i++) {
     const int k = i & 3, a = i >> 2;
     const float proj = cproj[k];
-    V3 c = mk((k >= 2) ? fS : 0.0f, (k == 1 || k == 3) ? fS : 0.0f, (k == 1 || k == 2) ? fS : 0.0f);
-    c = vadd(c, minpt);
+    const V3 c = corner[k];
+    if (done) continue;
     if (proj == 0.0f) {
       if (i < 4) {
-        bool dup = false;
-        for (int j = 0; j < np; j++) dup = dup || vclose(pts[j], c);
-        if (!dup) pts[np++] = c;
+        if (!poly_has(q, c)) poly_push(q, c);
       }
       continue;
     }
@@ -85,15 +113,12 @@ XS_HD int plane_cube_points(float x, float y, float z, const PlaneGeom& g, V3* p
     if (fabsf(fsub(hit.z, centre.z)) >= bound) continue;
     const bool oncorner = (at < XS_EPS) || (fabsf(fsub(at, fS)) < XS_EPS);
     bool dup = false;
-    if (oncorner) {
-      for (int j = 0; j < np; j++) dup = dup || vclose(pts[j], hit);
-    }
+    if (oncorner) dup = poly_has(q, hit);
     if (!dup) {
-      pts[np++] = hit;
-      if (np >= g.max_pts) break;
+      poly_push(q, hit);
+      if (q.n >= g.max_pts) done = true;
     }
   }
-  return np;
 }
 
 XS_HD void cswap(float* key, V3* v, int a, int b) {
@@ -103,29 +128,31 @@ XS_HD void cswap(float* key, V3* v, int a, int b) {
   }
 }
 
-// Anisotropy-scaled area of the convex polygon with vertices pts[0..np) lying in the plane.
-XS_HD float polygon_area(const V3* pts, int np, const PlaneGeom& g) {
+// Anisotropy-scaled area of the convex polygon q lying in the plane (area.hpp:211-228).
+XS_HD float polygon_area(const Poly& q, const PlaneGeom& g) {
+  const int np = q.n;
   if (np < 3) return 0.0f;
   if (np == 3) {
-    V3 a = vmul(vsub(pts[1], pts[0]), g.w), b = vmul(vsub(pts[2], pts[0]), g.w);
+    V3 a = vmul(vsub(q.p[1], q.p[0]), g.w), b = vmul(vsub(q.p[2], q.p[0]), g.w);
     return fmul(vnorm(vcross(a, b)), 0.5f);
   }
   V3 cen = mk(0.0f, 0.0f, 0.0f);
-  for (int i = 0; i < np; i++) cen = vadd(cen, pts[i]);
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    if (i < np) cen = vadd(cen, q.p[i]);
+  }
   cen = vdivs(cen, (float)np);
   V3 sp[6];
   float key[6];
-  for (int i = 0; i < 6; i++) {
-    if (i < np) sp[i] = vsub(pts[i], cen);
-  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) sp[i] = vsub(q.p[i < np ? i : 0], cen);
   const V3 prime = vdivs(sp[0], vnorm(sp[0]));
   V3 basis = vcross(prime, g.n);
   basis = vdivs(basis, vnorm(basis));
+#pragma unroll
   for (int i = 0; i < 6; i++) {
-    if (i < np) {
-      float c = fdiv(vdot(sp[i], prime), vnorm(sp[i]));
-      key[i] = (vdot(sp[i], basis) < 0.0f) ? fsub(c, 1.0f) : fsub(1.0f, c);
-    }
+    const float c = fdiv(vdot(sp[i], prime), vnorm(sp[i]));
+    key[i] = (vdot(sp[i], basis) < 0.0f) ? fsub(c, 1.0f) : fsub(1.0f, c);
   }
   // fixed comparator networks of area.hpp:68-143 (strict >, so ties keep their order)
   if (np == 4) {
@@ -138,21 +165,27 @@ XS_HD float polygon_area(const V3* pts, int np, const PlaneGeom& g) {
     cswap(key, sp, 0, 3); cswap(key, sp, 2, 5); cswap(key, sp, 0, 1); cswap(key, sp, 2, 3); cswap(key, sp, 4, 5);
     cswap(key, sp, 1, 2); cswap(key, sp, 3, 4);
   }
-  for (int i = 0; i < 6; i++) {
-    if (i < np) sp[i] = vmul(sp[i], g.w);
-  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) sp[i] = vmul(sp[i], g.w);
   float area = 0.0f;
+#pragma unroll
   for (int i = 0; i < 5; i++) {
     if (i + 1 < np) area = fadd(area, vnorm(vcross(sp[i], sp[i + 1])));
   }
-  area = fadd(area, vnorm(vcross(sp[0], sp[np - 1])));
+  const V3 last = (np == 4) ? sp[3] : (np == 5 ? sp[4] : sp[5]);
+  area = fadd(area, vnorm(vcross(sp[0], last)));
   return fmul(area, 0.5f);
 }
 
 XS_HD float voxel_area(float x, float y, float z, const PlaneGeom& g) {
-  V3 pts[7];
-  int np = plane_cube_points<1>(x, y, z, g, pts);
-  return polygon_area(pts, np, g);
+  Poly q;
+  plane_cube_points<1>(x, y, z, g, q);
+  return polygon_area(q, g);
+}
+XS_HD float block_polygon_area(float bx, float by, float bz, const PlaneGeom& g) {
+  Poly q;
+  plane_cube_points<2>(bx, by, bz, g, q);
+  return polygon_area(q, g);
 }
 
 // Value of the 2x2x2 block with low (even) voxel (bx,by,bz) and occupancy mask `cube`
@@ -168,9 +201,7 @@ XS_HD float block_value(uint32_t cube, float bx, float by, float bz, const Plane
   const int pop = __builtin_popcount(cube & 0xffu);
 #endif
   if (pop >= 5) {
-    V3 pts[7];
-    int np = plane_cube_points<2>(bx, by, bz, g, pts);
-    area = polygon_area(pts, np, g);
+    area = block_polygon_area(bx, by, bz, g);
     if (area == 0.0f) return area;
     for (int b = 0; b < 8; b++) {
       if (!((cube >> b) & 1u))

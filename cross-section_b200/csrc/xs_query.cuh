@@ -5,7 +5,9 @@
 // cross_section :1367-1426, cross_sectional_area_helper :1118-1268, calc_area_at_point :442-535.
 //
 // The reference fuses everything into one sequential flood fill.  Here the query is decomposed
-//  so that only a bitmap walk is sequential:
+//  so that only a bitmap walk is sequential, and the floating-point work is split off
+// into a separate, perfectly regular kernel:
+//   QUERY KERNELS (one warp or one CTA per query; this file, run_area_emit / run_section_emit)
 //   1. lattice tiles   : the plane lattice (basis b1,b2, unit spacing, centred on the vertex) is
 //                        sampled in 32x32-cell tiles ON DEMAND into a foreground bitmap (one ballot
 //                        per lattice row) — work scales with the section, not with the volume;
@@ -13,12 +15,18 @@
 //                        reference's neighbour priority; the walk both delimits the 8-connected
 //                        component and yields its DFS preorder (`order[]`);
 //   3. claims          : every sample claims the <=27 neighbouring 2x2x2 blocks whose probe voxel
-//                        is set, atomicMin of (rank,k) into a hash table keyed by block id —
+//                        is set: atomicMin of its rank into a hash table keyed by block —
 //                        "first touch wins" without the sequential visit;
-//   4. ownership/items : owners are compacted, in (rank,k) order, into an item list;
-//   5. evaluate        : one item per thread: adjacency test + plane∩block polygon value;
-//   6. ordered sum     : float32 sum per sample in k order, then over samples in rank order.
-// Path B (cross_section) shares 1-2 and replaces 3-6 by a per-voxel dedupe + polygon pass.
+//   4. emit            : owners that pass the adjacency and plane-distance tests become ITEMS, in
+//                        (rank,k) order; each item lists the plane∩cube POLYGONS it needs (the block
+//                        polygon and/or unit-voxel polygons) as 12-byte records in HBM.
+//   POLYGON KERNEL (one thread per polygon record, full occupancy; poly_eval)
+//   5. evaluate        : intersect the 12 cube edges with the plane, order the vertices, area.
+//   COMBINE KERNEL (one CTA per query; combine_query)
+//   6. ordered sum     : block value from its polygons, float32 sum per sample in k order, then
+//                        over samples in rank order — the reference's exact summation order.
+// Path B (cross_section) shares 1-2, replaces 3-4 by a per-voxel dedupe that emits voxel polygons,
+// and needs no combine.
 //
 // Volume layout ("cubes"): one byte per 2x2x2 block = the reference's compute_cube() mask
 // (xs3d.hpp:26-48), bit = dx + 2dy + 4dz, out-of-volume voxels 0; x fastest.  A voxel test and a
@@ -217,9 +225,133 @@ XS_HD void atomic_or_u32(uint32_t* p, uint32_t val) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-query working set.  Pointers may address shared memory (T0, and T1's bitmap/stack ring) or a
-// per-CTA slab in global memory (T1).
+// Records exchanged between the query kernels, the polygon kernel and the combine kernel (HBM).
 // ------------------------------------------------------------------------------------------------
+struct PolyRec {            // 12 bytes: one plane∩cube polygon to evaluate
+  uint32_t q;               // query index (-> GeomRec)
+  uint16_t x, y, z;         // low voxel of the cube
+  uint16_t kind;            // 1: unit voxel, 2: 2x2x2 block
+};
+struct ItemRec {            // 8 bytes: one owned block that contributes to the area
+  uint32_t poly;            // absolute index of its first polygon record / value
+  uint32_t meta;            // bits 0-3 polygon count, bit 4 subtract mode (>=5 voxels set), bit 5 first item of its sample
+};
+struct QInfo {              // 16 bytes per query
+  uint32_t item_off, n_items;
+  uint32_t contact;
+  uint32_t status;          // QS_*
+};
+enum { QS_PENDING = 0, QS_READY = 1 };
+struct EmitOut {
+  PolyRec* polys;
+  ItemRec* items;
+  PlaneGeom* geom;          // per query
+  QInfo* qinfo;             // per query
+  uint32_t* counters;       // [0] polygons used, [1] items used, [2] capacity overflow flag
+  uint32_t poly_cap, item_cap;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Per-query working set.  Pointers may address shared memory (warp tier, and the CTA tier's bitmap /
+// stack ring) or a per-CTA slab in global memory (CTA tier).  CellT packs a window cell (u,v):
+// uint16_t (u | v<<8) for the warp tier's 96x96 window, uint32_t (u | v<<16) otherwise.
+// ------------------------------------------------------------------------------------------------
+template <class CellT> struct CellPack;
+template <> struct CellPack<uint16_t> {
+  static XS_HD uint16_t pack(int u, int v) { return (uint16_t)(u | (v << 8)); }
+  static XS_HD int u(uint16_t p) { return p & 0xff; }
+  static XS_HD int v(uint16_t p) { return p >> 8; }
+};
+template <> struct CellPack<uint32_t> {
+  static XS_HD uint32_t pack(int u, int v) { return (uint32_t)u | ((uint32_t)v << 16); }
+  static XS_HD int u(uint32_t p) { return (int)(p & 0xffffu); }
+  static XS_HD int v(uint32_t p) { return (int)(p >> 16); }
+};
+
+#define XS_HEMPTY 0xffffffffu
+
+// First-touch table, packed form (warp tier): one 32-bit word per slot = tag<<9 | rank, where tag is the
+// block position relative to the query's centre block (7 bits per axis) and rank < 512.  Because all
+// claims on a slot that already holds the same tag share the upper bits, atomicMin on the whole word is
+// atomicMin on the rank.
+struct PackedHash {
+  XS_HD void fit(int) {}
+  uint32_t* slot;
+  uint32_t cap;        // power of two
+  int shift;           // 32 - log2(cap)
+  int cbx, cby, cbz;   // centre block of the query
+  int max_probe;
+  XS_HD uint32_t tag(int bx, int by, int bz) const {
+    return (uint32_t)(bx - cbx + 64) | ((uint32_t)(by - cby + 64) << 7) | ((uint32_t)(bz - cbz + 64) << 14);
+  }
+  template <class G> XS_D void clear(const G& g) const {
+    for (uint32_t i = g.tid(); i < cap; i += g.size()) slot[i] = XS_HEMPTY;
+  }
+  XS_HD bool claim(int bx, int by, int bz, uint32_t rank) const {
+    const uint32_t t = tag(bx, by, bz), word = (t << 9) | rank;
+    uint32_t h = (t * 2654435761u) >> shift;
+    for (int probes = 0; probes < max_probe; probes++) {
+      uint32_t old = slot[h];
+      if (old == XS_HEMPTY) old = atomic_cas_u32(&slot[h], XS_HEMPTY, word);
+      if (old == XS_HEMPTY) return true;
+      if ((old >> 9) == t) { atomic_min_u32(&slot[h], word); return true; }
+      h = (h + 1u) & (cap - 1u);
+    }
+    return false;
+  }
+  XS_HD uint32_t owner(int bx, int by, int bz) const {
+    const uint32_t t = tag(bx, by, bz);
+    uint32_t h = (t * 2654435761u) >> shift;
+    for (;;) {
+      const uint32_t e = slot[h];
+      if ((e >> 9) == t) return e & 0x1ffu;
+      h = (h + 1u) & (cap - 1u);
+    }
+  }
+};
+
+// First-touch table, wide form (CTA tier): separate tag (linear block id) and rank arrays in HBM.
+struct WideHash {
+  uint32_t* htag;
+  uint32_t* hkey;
+  uint32_t cap;        // capacity in use (power of two)
+  int shift;           // 32 - log2(cap)
+  int hx, hy;
+  int max_probe;
+  uint32_t cap_max;    // allocated capacity; with factor > 0 the capacity in use is re-chosen per query
+  int factor;          //   as the power of two >= factor * samples (<= cap_max), so small queries clear little
+  XS_HD void fit(int n) {
+    if (factor <= 0) return;
+    uint32_t c2 = 1024u;
+    const uint64_t want = (uint64_t)factor * (uint64_t)n;
+    while ((uint64_t)c2 < want && c2 < cap_max) c2 <<= 1;
+    int lg = 0;
+    while ((1u << lg) < c2) lg++;
+    cap = c2; shift = 32 - lg;
+  }
+  XS_HD uint32_t id(int bx, int by, int bz) const { return (uint32_t)bx + (uint32_t)hx * ((uint32_t)by + (uint32_t)hy * (uint32_t)bz); }
+  template <class G> XS_D void clear(const G& g) const {
+    for (uint32_t i = g.tid(); i < cap; i += g.size()) { htag[i] = XS_HEMPTY; hkey[i] = XS_HEMPTY; }
+  }
+  XS_HD bool claim(int bx, int by, int bz, uint32_t rank) const {
+    const uint32_t t = id(bx, by, bz);
+    uint32_t h = (t * 2654435761u) >> shift;
+    for (int probes = 0; probes < max_probe; probes++) {
+      const uint32_t old = atomic_cas_u32(&htag[h], XS_HEMPTY, t);
+      if (old == XS_HEMPTY || old == t) { atomic_min_u32(&hkey[h], rank); return true; }
+      h = (h + 1u) & (cap - 1u);
+    }
+    return false;
+  }
+  XS_HD uint32_t owner(int bx, int by, int bz) const {
+    const uint32_t t = id(bx, by, bz);
+    uint32_t h = (t * 2654435761u) >> shift;
+    while (htag[h] != t) h = (h + 1u) & (cap - 1u);
+    return hkey[h];
+  }
+};
+
+template <class CellT>
 struct Arena {
   // lattice window: local cell (u,v) <-> lattice cell (ox+u, oy+v); tx x ty tiles of 32x32 cells
   int ox, oy, tx, ty, stride;   // stride = tx + 1 words per row (one zero pad word)
@@ -227,27 +359,12 @@ struct Arena {
   uint32_t* tested;             // one bit per tile, ceil(tx*ty/32) words
   int halo;                     // tiles tested around a requested tile (0: just that tile)
   // samples
-  uint32_t* order;              // rank -> u | v<<16
+  CellT* order;                 // rank -> packed (u,v)
   int max_n;
-  uint32_t* stack;              // DFS stack ring (depth % stack_cap) of u | v<<16
+  CellT* stack;                 // DFS stack ring (depth % stack_cap)
   int stack_cap;                // power of two when `spill` is set, else >= max_n
-  uint32_t* spill;              // global backing store for the ring, or null when stack_cap >= max_n
-  uint32_t* mask;               // per-sample 27-bit candidate / ownership masks (may alias `stack`)
-  // block ownership hash (open addressing, linear probing)
-  uint32_t* htag;
-  uint32_t* hkey;
-  uint32_t hcap;                // power of two (capacity in use)
-  int hshift;                   // 32 - log2(hcap)
-  uint32_t hcap_max;            // allocated capacity; with hash_factor > 0 the capacity in use is
-  int hash_factor;              //   re-chosen per query as pow2 >= hash_factor * samples (<= hcap_max)
-  int max_probe;                // give up (-> Q_OVERFLOW) after this many probes; 0 = never
-  // items
-  uint32_t* items;              // rank<<5 | k, in (rank,k) order
-  float* vals;                  // may alias htag (dead by then)
-  int max_m;
-  // optional staging buffer for the ordered sum (shared memory), or null to read vals directly
-  uint32_t* stage;
-  int stage_cap;
+  CellT* spill;                 // global backing store for the ring, or null when stack_cap >= max_n
+  uint32_t* mask;               // per-sample 27-bit candidate / kept-item masks (warp tier: aliases `bits`)
 };
 
 struct Ctl {          // lives in shared memory (one per group)
@@ -257,13 +374,15 @@ struct Ctl {          // lives in shared memory (one per group)
   int depth;          // DFS stack depth
   int lo;             // lowest stack depth resident in the ring
   int u, v;           // current cell
-  int m;              // items
+  int m;              // items emitted
+  int npoly;          // polygons emitted
   int overflow;
   uint32_t contact;
   uint32_t counter;   // generic atomic counter (path B output length)
+  uint32_t item_off, poly_off;
   int tiles;          // lattice tiles sampled (1024 cells each)
   long long tmark;    // phase profiling (thread 0): last timestamp and per-phase cycle counts
-  uint32_t t[6];      //   0 flood (tiles + walk)  1 claims  2 items  3 evaluate  4 ordered sum  5 walk only
+  uint32_t t[6];      //   0 flood (tiles + walk)  1 claims  2 emit  3 -  4 -  5 walk only
 };
 
 XS_HD long long xs_clock() {
@@ -281,18 +400,17 @@ XS_HD void prof_mark(Ctl& ctl, int phase) {
 }
 
 enum { ST_DONE = 0, ST_NEED_TILE = 1, ST_OVERFLOW = 2 };
-enum { Q_OK = 0, Q_OVERFLOW = 1 };
+enum { Q_OK = 0, Q_OVERFLOW = 1, Q_CAPACITY = 2 };
 
-#define XS_HEMPTY 0xffffffffu
-
-XS_HD bool tile_tested(const Arena& A, int tx, int ty) {
+template <class CellT>
+XS_HD bool tile_tested(const Arena<CellT>& A, int tx, int ty) {
   const int t = ty * A.tx + tx;
   return (A.tested[t >> 5] >> (t & 31)) & 1u;
 }
 
 // Sample the lattice rows of every untested tile in the tile rectangle [tx0,tx1]x[ty0,ty1] (clipped).
-template <class G>
-XS_D void test_tiles(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A, Ctl& ctl, int tx0, int ty0, int tx1, int ty1) {
+template <class G, class CellT>
+XS_D void test_tiles(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, Ctl& ctl, int tx0, int ty0, int tx1, int ty1) {
   tx0 = tx0 < 0 ? 0 : tx0; ty0 = ty0 < 0 ? 0 : ty0;
   tx1 = tx1 >= A.tx ? A.tx - 1 : tx1; ty1 = ty1 >= A.ty ? A.ty - 1 : ty1;
   const int nx = tx1 - tx0 + 1, ny = ty1 - ty0 + 1;
@@ -337,7 +455,9 @@ XS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {
 // A visited cell has its bit cleared, so "set" means foreground-and-unvisited, which only ever
 // decreases: re-examining a cell after a child returns picks exactly the neighbour the reference's
 // explicit stack would pop next.  Returns ST_DONE / ST_NEED_TILE (ctl.req_*) / ST_OVERFLOW.
-XS_HD int dfs_run(const Arena& A, Ctl& ctl) {
+template <class CellT>
+XS_HD int dfs_run(const Arena<CellT>& A, Ctl& ctl) {
+  typedef CellPack<CellT> P;
   int n = ctl.n, depth = ctl.depth, lo = ctl.lo, u = ctl.u, v = ctl.v;
   const int W = A.tx * 32, H = A.ty * 32;
   const int smask = A.spill ? (A.stack_cap - 1) : 0x7fffffff;   // no ring wrap when the whole stack is resident
@@ -372,8 +492,8 @@ XS_HD int dfs_run(const Arena& A, Ctl& ctl) {
         for (int d = nlo; d < lo; d++) A.stack[d & smask] = A.spill[d];
         lo = nlo;
       }
-      const uint32_t p = A.stack[(depth - 1) & smask];
-      u = (int)(p & 0xffffu); v = (int)(p >> 16);
+      const CellT p = A.stack[(depth - 1) & smask];
+      u = P::u(p); v = P::v(p);
       continue;
     }
 #ifdef __CUDA_ARCH__
@@ -387,7 +507,7 @@ XS_HD int dfs_run(const Arena& A, Ctl& ctl) {
     u += du; v += dv;
     A.bits[(size_t)v * A.stride + (u >> 5)] &= ~(1u << (u & 31));
     if (u == 0 || v == 0 || u == W - 1 || v == H - 1 || n >= A.max_n) { status = ST_OVERFLOW; break; }
-    const uint32_t p = (uint32_t)u | ((uint32_t)v << 16);
+    const CellT p = P::pack(u, v);
     A.order[n++] = p;
     if (depth - lo == A.stack_cap) {
       // ring full: spill the lower half
@@ -405,8 +525,9 @@ XS_HD int dfs_run(const Arena& A, Ctl& ctl) {
 // Steps 1-2: sample tiles on demand and walk the component.  On return ctl.n samples are in
 // A.order (rank order).  Returns Q_OK or Q_OVERFLOW; *empty is set when the centre cell itself is
 // not foreground on the lattice (the reference then returns zeros).
-template <class G>
-XS_D int flood_component(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A, Ctl& ctl, bool* empty) {
+template <class G, class CellT>
+XS_D int flood_component(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, Ctl& ctl, bool* empty) {
+  typedef CellPack<CellT> P;
   const int words = A.ty * 32 * A.stride;
   for (int i = g.tid(); i < words; i += g.size()) A.bits[i] = 0u;
   const int tw = (A.tx * A.ty + 31) >> 5;
@@ -414,7 +535,8 @@ XS_D int flood_component(const G& g, const PlaneCtx& c, const VolView& vol, cons
   const int cu = c.c - A.ox, cv = c.c - A.oy;
   if (g.tid() == 0) {
     ctl.status = ST_NEED_TILE; ctl.req_tx = cu >> 5; ctl.req_ty = cv >> 5;
-    ctl.n = 0; ctl.depth = 0; ctl.lo = 0; ctl.u = cu; ctl.v = cv; ctl.m = 0; ctl.overflow = 0; ctl.contact = 0u; ctl.counter = 0u; ctl.tiles = 0;
+    ctl.n = 0; ctl.depth = 0; ctl.lo = 0; ctl.u = cu; ctl.v = cv; ctl.m = 0; ctl.npoly = 0; ctl.overflow = 0; ctl.contact = 0u; ctl.counter = 0u; ctl.tiles = 0;
+    ctl.item_off = 0u; ctl.poly_off = 0u;
     for (int i = 0; i < 6; i++) ctl.t[i] = 0u;
     ctl.tmark = xs_clock();
   }
@@ -427,24 +549,22 @@ XS_D int flood_component(const G& g, const PlaneCtx& c, const VolView& vol, cons
     test_tiles(g, c, vol, A, ctl, rtx - A.halo, rty - A.halo, rtx + A.halo, rty + A.halo);
     if (g.tid() == 0) {
       int st;
+      const long long w0 = xs_clock();
       if (first) {
         uint32_t* w = &A.bits[(size_t)cv * A.stride + (cu >> 5)];
         if (!((*w >> (cu & 31)) & 1u)) {
           st = ST_DONE; ctl.n = 0;
         } else {
           *w &= ~(1u << (cu & 31));
-          const uint32_t p = (uint32_t)cu | ((uint32_t)cv << 16);
+          const CellT p = P::pack(cu, cv);
           A.order[0] = p; A.stack[0] = p;
           ctl.n = 1; ctl.depth = 1;
-          const long long w0 = xs_clock();
           st = dfs_run(A, ctl);
-          ctl.t[5] += (uint32_t)(xs_clock() - w0);
         }
       } else {
-        const long long w0 = xs_clock();
         st = dfs_run(A, ctl);
-        ctl.t[5] += (uint32_t)(xs_clock() - w0);
       }
+      ctl.t[5] += (uint32_t)(xs_clock() - w0);
       ctl.status = st;
     }
     first = false;
@@ -461,40 +581,24 @@ XS_D int flood_component(const G& g, const PlaneCtx& c, const VolView& vol, cons
 struct Sample {
   int rx, ry, rz;   // rounded voxel of the lattice sample
 };
-XS_HD Sample sample_at(const PlaneCtx& c, const Arena& A, int r, V3* rounded) {
-  const uint32_t p = A.order[r];
-  const V3 cur = vround(cell_point(c, A.ox + (int)(p & 0xffffu), A.oy + (int)(p >> 16)));
+template <class CellT>
+XS_HD Sample sample_at(const PlaneCtx& c, const Arena<CellT>& A, int r, V3* rounded) {
+  typedef CellPack<CellT> P;
+  const CellT p = A.order[r];
+  const V3 cur = vround(cell_point(c, A.ox + P::u(p), A.oy + P::v(p)));
   Sample s;
   s.rx = (int)cur.x; s.ry = (int)cur.y; s.rz = (int)cur.z;
   if (rounded) *rounded = cur;
   return s;
 }
 
-XS_HD uint32_t block_id(const VolView& v, int bx, int by, int bz) {
-  return (uint32_t)bx + (uint32_t)v.hx * ((uint32_t)by + (uint32_t)v.hy * (uint32_t)bz);
-}
-XS_HD uint32_t hash_u32(uint32_t k, int shift) { return (k * 2654435761u) >> shift; }
-
-// Pick the hash capacity for a query with n samples (tiers with a big allocated table clear and use
-// only what the query needs).
-XS_HD Arena size_hash(const Arena& A, int n) {
-  Arena B = A;
-  if (A.hash_factor > 0) {
-    uint32_t cap = 1024u;
-    const uint64_t want = (uint64_t)A.hash_factor * (uint64_t)n;
-    while ((uint64_t)cap < want && cap < A.hcap_max) cap <<= 1;
-    int lg = 0;
-    while ((1u << lg) < cap) lg++;
-    B.hcap = cap; B.hshift = 32 - lg;
-  }
-  return B;
-}
-
 // Step 3: contact bits (xs3d.hpp:909-914) and first-touch claims (xs3d.hpp:689-708).
-template <class G>
-XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A, Ctl& ctl) {
+// The owner of a block is the claimer with the smallest DFS rank; since a sample probes each block at
+// most once, the rank alone identifies the (rank,k) pair the reference would have visited first.
+template <class G, class CellT, class H>
+XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, const H& hash, Ctl& ctl) {
   const int n = ctl.n;
-  for (uint32_t i = g.tid(); i < A.hcap; i += g.size()) { A.htag[i] = XS_HEMPTY; A.hkey[i] = XS_HEMPTY; }
+  hash.clear(g);
   g.sync();
   uint32_t ct = 0u;
   bool ovf = false;
@@ -514,16 +618,7 @@ XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const 
       const uint32_t cb = cube_at(vol, bx + ox, by + oy, bz + oz);
       if (!((cb >> pb) & 1u)) continue;                              // :704 probe voxel is background
       cmask |= 1u << k;
-      const uint32_t id = block_id(vol, bx + ox, by + oy, bz + oz);
-      const uint32_t key = ((uint32_t)r << 5) | (uint32_t)k;
-      uint32_t h = hash_u32(id, A.hshift);
-      int probes = 0;
-      for (;;) {
-        const uint32_t t = atomic_cas_u32(&A.htag[h], XS_HEMPTY, id);
-        if (t == XS_HEMPTY || t == id) { atomic_min_u32(&A.hkey[h], key); break; }
-        h = (h + 1u) & (A.hcap - 1u);
-        if (++probes == A.max_probe) { ovf = true; break; }
-      }
+      if (!hash.claim(bx + ox, by + oy, bz + oz, (uint32_t)r)) ovf = true;
     }
     A.mask[r] = cmask;
   }
@@ -533,169 +628,215 @@ XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const 
   g.sync();
 }
 
-// Step 4: which candidates did each sample win?  Then compact owners into (rank,k)-ordered items.
-template <class G>
-XS_D void build_items(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A, Ctl& ctl) {
-  const int n = ctl.n;
-  for (int r = g.tid(); r < n; r += g.size()) {
-    uint32_t cm = A.mask[r], own = 0u;
-    if (cm) {
-      const Sample s = sample_at(c, A, r, nullptr);
-      const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
-      while (cm) {
+XS_HD int popc8(uint32_t x) {
 #ifdef __CUDA_ARCH__
-        const int k = __ffs(cm) - 1;
+  return __popc(x & 0xffu);
 #else
-        const int k = __builtin_ffs(cm) - 1;
+  return __builtin_popcount(x & 0xffu);
 #endif
+}
+XS_HD int ffs32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return __ffs(x);
+#else
+  return __builtin_ffs(x);
+#endif
+}
+// polygons an item needs (xs3d.hpp:420-437): >=5 voxels set: the block polygon + one per ABSENT voxel; else one per present voxel
+XS_HD int item_polys(uint32_t cube) {
+  const int pop = popc8(cube);
+  return pop >= 5 ? 1 + (8 - pop) : pop;
+}
+
+// Step 4: ownership -> adjacency test (xs3d.hpp:710-712) -> plane-distance test (:384-389) -> item and polygon
+// records, written in (rank,k) order into ranges reserved with one atomicAdd per query.
+template <class G, class CellT, class H>
+XS_D int emit_items(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, const H& hash, Ctl& ctl,
+                    uint32_t q, const EmitOut& out) {
+  const int n = ctl.n;
+  // pass 1: which candidates become items; totals
+  int my_items = 0, my_polys = 0;
+  for (int r = g.tid(); r < n; r += g.size()) {
+    uint32_t cm = A.mask[r], keep = 0u;
+    if (cm) {
+      const Sample s = sample_at(c, A, r, (V3*)nullptr);
+      const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
+      const uint32_t centre = cube_at(vol, bx, by, bz);
+      while (cm) {
+        const int k = ffs32(cm) - 1;
         cm &= cm - 1u;
         const int ox = k % 3 - 1, oy = (k / 3) % 3 - 1, oz = k / 9 - 1;
-        const uint32_t id = block_id(vol, bx + ox, by + oy, bz + oz);
-        uint32_t h = hash_u32(id, A.hshift);
-        while (A.htag[h] != id) h = (h + 1u) & (A.hcap - 1u);
-        if (A.hkey[h] == (((uint32_t)r << 5) | (uint32_t)k)) own |= 1u << k;
+        if (hash.owner(bx + ox, by + oy, bz + oz) != (uint32_t)r) continue;         // someone with a smaller rank touched it first
+        const uint32_t cand = cube_at(vol, bx + ox, by + oy, bz + oz);
+        if (!blocks_adjacent(centre, cand, ox, oy, oz)) continue;                    // visited, but contributes nothing
+        const V3 ctr = vadd(mk((float)(2 * (bx + ox)), (float)(2 * (by + oy)), (float)(2 * (bz + oz))), mk(0.5f, 0.5f, 0.5f));
+        if (fabsf(vdot(vsub(ctr, c.g.pos), c.g.n)) > XS_FAR2) continue;             // block value is exactly 0
+        keep |= 1u << k;
+        my_items++;
+        my_polys += item_polys(cand);
       }
     }
-    A.mask[r] = own;
+    A.mask[r] = keep;
   }
   g.sync();
-  int base = 0;
-  bool ovf = false;
+  // reserve the output ranges
+  int m, npoly;
+  {
+    int t1, t2;
+    g.exscan(my_items, t1);
+    g.exscan(my_polys, t2);
+    m = t1; npoly = t2;
+  }
+  if (g.tid() == 0) {
+    ctl.m = m; ctl.npoly = npoly;
+    ctl.item_off = m ? atomic_add_u32(&out.counters[1], (uint32_t)m) : 0u;
+    ctl.poly_off = npoly ? atomic_add_u32(&out.counters[0], (uint32_t)npoly) : 0u;
+    if ((uint64_t)ctl.item_off + (uint64_t)m > out.item_cap || (uint64_t)ctl.poly_off + (uint64_t)npoly > out.poly_cap) {
+      ctl.overflow = 2;
+      out.counters[2] = 1u;
+    }
+  }
+  g.sync();
+  if (ctl.overflow) return Q_CAPACITY;
+  const uint32_t item_off = ctl.item_off, poly_off = ctl.poly_off;
+  // pass 2: write, one chunk of g.size() consecutive ranks at a time
+  int ibase = 0, pbase = 0;
   const int gs = g.size();
   for (int r0 = 0; r0 < n; r0 += gs) {
     const int r = r0 + g.tid();
-    uint32_t own = (r < n) ? A.mask[r] : 0u;
-#ifdef __CUDA_ARCH__
-    const int cnt = __popc(own);
-#else
-    const int cnt = __builtin_popcount(own);
-#endif
-    int total;
-    int off = base + g.exscan(cnt, total);
-    if (base + total > A.max_m) { ovf = true; break; }   // uniform across the group
-    while (own) {
-#ifdef __CUDA_ARCH__
-      const int k = __ffs(own) - 1;
-#else
-      const int k = __builtin_ffs(own) - 1;
-#endif
-      own &= own - 1u;
-      A.items[off++] = ((uint32_t)r << 5) | (uint32_t)k;
-    }
-    base += total;
-  }
-  if (g.tid() == 0) { ctl.m = base; if (ovf) ctl.overflow = 1; }
-  g.sync();
-}
-
-// Step 5: adjacency test (xs3d.hpp:710-712) and block value (:713-719) of every owned block.
-template <class G>
-XS_D void eval_items(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A, Ctl& ctl) {
-  const int m = ctl.m;
-  for (int it = g.tid(); it < m; it += g.size()) {
-    const uint32_t e = A.items[it];
-    const int r = (int)(e >> 5), k = (int)(e & 31u);
-    const Sample s = sample_at(c, A, r, nullptr);
-    const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
-    const int ox = k % 3 - 1, oy = (k / 3) % 3 - 1, oz = k / 9 - 1;
-    const uint32_t centre = cube_at(vol, bx, by, bz);
-    const uint32_t cand = cube_at(vol, bx + ox, by + oy, bz + oz);
-    float val = 0.0f;
-    if (blocks_adjacent(centre, cand, ox, oy, oz))
-      val = block_value(cand, (float)(2 * (bx + ox)), (float)(2 * (by + oy)), (float)(2 * (bz + oz)), c.g);
-    A.vals[it] = val;
-  }
-  g.sync();
-}
-
-// Step 6: two-level float32 sum in the reference's order (xs3d.hpp:663,713 then :848,952).
-template <class G>
-XS_D float ordered_sum(const G& g, const Arena& A, Ctl& ctl, float* shared_result) {
-  const int m = ctl.m;
-  float total = 0.0f, sub = 0.0f;
-  uint32_t cur_r = 0xffffffffu;
-  if (A.stage == nullptr) {
-    if (g.tid() == 0) {
-      for (int it = 0; it < m; it++) {
-        const uint32_t r = A.items[it] >> 5;
-        if (r != cur_r) { total = fadd(total, sub); sub = 0.0f; cur_r = r; }
-        sub = fadd(sub, A.vals[it]);
+    const uint32_t keep = (r < n) ? A.mask[r] : 0u;
+    int bx = 0, by = 0, bz = 0, ni = 0, np = 0;
+    if (keep) {
+      const Sample s = sample_at(c, A, r, (V3*)nullptr);
+      bx = s.rx >> 1; by = s.ry >> 1; bz = s.rz >> 1;
+      uint32_t km = keep;
+      while (km) {
+        const int k = ffs32(km) - 1;
+        km &= km - 1u;
+        ni++;
+        np += item_polys(cube_at(vol, bx + k % 3 - 1, by + (k / 3) % 3 - 1, bz + k / 9 - 1));
       }
-      total = fadd(total, sub);
-      *shared_result = total;
     }
-  } else {
-    const int chunk = A.stage_cap / 2;
-    uint32_t* s_items = A.stage;
-    float* s_vals = (float*)(A.stage + chunk);
-    for (int b = 0; b < m; b += chunk) {
-      const int len = (m - b) < chunk ? (m - b) : chunk;
-      for (int i = g.tid(); i < len; i += g.size()) { s_items[i] = A.items[b + i]; s_vals[i] = A.vals[b + i]; }
-      g.sync();
-      if (g.tid() == 0) {
-        for (int i = 0; i < len; i++) {
-          const uint32_t r = s_items[i] >> 5;
-          if (r != cur_r) { total = fadd(total, sub); sub = 0.0f; cur_r = r; }
-          sub = fadd(sub, s_vals[i]);
-        }
+    int ti, tp;
+    uint32_t io = item_off + (uint32_t)(ibase + g.exscan(ni, ti));
+    uint32_t po = poly_off + (uint32_t)(pbase + g.exscan(np, tp));
+    uint32_t km = keep;
+    bool first = true;
+    while (km) {
+      const int k = ffs32(km) - 1;
+      km &= km - 1u;
+      const int cx = bx + k % 3 - 1, cy = by + (k / 3) % 3 - 1, cz = bz + k / 9 - 1;
+      const uint32_t cand = cube_at(vol, cx, cy, cz);
+      const int pop = popc8(cand);
+      const int cnt = item_polys(cand);
+      ItemRec it;
+      it.poly = po;
+      it.meta = (uint32_t)cnt | (pop >= 5 ? 16u : 0u) | (first ? 32u : 0u);
+      out.items[io++] = it;
+      first = false;
+      PolyRec pr;
+      pr.q = q;
+      if (pop >= 5) {
+        pr.x = (uint16_t)(2 * cx); pr.y = (uint16_t)(2 * cy); pr.z = (uint16_t)(2 * cz); pr.kind = 2;
+        out.polys[po++] = pr;
       }
-      g.sync();
+      const uint32_t want = (pop >= 5) ? (~cand & 0xffu) : cand;   // absent voxels are subtracted, present ones added
+      for (int b = 0; b < 8; b++) {
+        if (!((want >> b) & 1u)) continue;
+        pr.x = (uint16_t)(2 * cx + (b & 1)); pr.y = (uint16_t)(2 * cy + ((b >> 1) & 1)); pr.z = (uint16_t)(2 * cz + (b >> 2)); pr.kind = 1;
+        out.polys[po++] = pr;
+      }
     }
-    if (g.tid() == 0) { total = fadd(total, sub); *shared_result = total; }
+    ibase += ti; pbase += tp;
   }
-  g.sync();
-  return *shared_result;
-}
-
-// Path A: xs3d.cross_sectional_area for one query.  Every thread of the group returns the same
-// status; on Q_OK thread 0 has written *area / *contact.
-template <class G>
-XS_D int run_area(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A, Ctl& ctl, float* scratch_f,
-                  float* area, uint8_t* contact) {
-  bool empty;
-  if (flood_component(g, c, vol, A, ctl, &empty) != Q_OK) return Q_OVERFLOW;
-  if (empty) {
-    if (g.tid() == 0) { *area = 0.0f; *contact = 0; }
-    return Q_OK;
-  }
-  if (g.tid() == 0) prof_mark(ctl, 0);
-  const Arena B = size_hash(A, ctl.n);
-  claim_blocks(g, c, vol, B, ctl);
-  if (ctl.overflow) return Q_OVERFLOW;
-  if (g.tid() == 0) prof_mark(ctl, 1);
-  build_items(g, c, vol, B, ctl);
-  if (ctl.overflow) return Q_OVERFLOW;
-  if (g.tid() == 0) prof_mark(ctl, 2);
-  eval_items(g, c, vol, B, ctl);
-  if (g.tid() == 0) prof_mark(ctl, 3);
-  const float total = ordered_sum(g, B, ctl, scratch_f);
-  if (g.tid() == 0) { prof_mark(ctl, 4); *area = total; *contact = (uint8_t)ctl.contact; }
   return Q_OK;
 }
 
-// Path B: xs3d.cross_section for one query.  Emits the sparse image {voxel index -> area > 0}
-// (unordered) into out_idx/out_val (capacity out_cap); count in ctl.counter.  The voxel-dedupe set
-// reuses the claim hash (htag only).  Neighbourhood and contact follow the UNROUNDED sample
-// (xs3d.hpp:458-478, :1215-1220).
-template <class G>
-XS_D int run_section(const G& g, const PlaneCtx& c, const VolView& vol, const Arena& A_in, Ctl& ctl,
-                     uint64_t* out_idx, float* out_val, uint32_t out_cap, uint8_t* contact) {
+// Path A, query side: everything up to the polygon records.  Every thread returns the same status.
+// On Q_OK thread 0 has filled qinfo[q] (QS_READY) and geom[q].
+template <class G, class CellT, class H>
+XS_D int run_area_emit(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, H& hash, Ctl& ctl,
+                       uint32_t q, const EmitOut& out) {
   bool empty;
-  if (flood_component(g, c, vol, A_in, ctl, &empty) != Q_OK) return Q_OVERFLOW;
+  if (flood_component(g, c, vol, A, ctl, &empty) != Q_OK) return Q_OVERFLOW;
+  if (g.tid() == 0) prof_mark(ctl, 0);
+  if (empty) {
+    if (g.tid() == 0) {
+      QInfo qi; qi.item_off = 0; qi.n_items = 0; qi.contact = 0; qi.status = QS_READY;
+      out.qinfo[q] = qi;
+    }
+    return Q_OK;
+  }
+  hash.fit(ctl.n);
+  claim_blocks(g, c, vol, A, hash, ctl);
+  if (ctl.overflow) return Q_OVERFLOW;
+  if (g.tid() == 0) prof_mark(ctl, 1);
+  const int st = emit_items(g, c, vol, A, hash, ctl, q, out);
+  if (st != Q_OK) return st;
+  if (g.tid() == 0) {
+    prof_mark(ctl, 2);
+    out.geom[q] = c.g;
+    QInfo qi; qi.item_off = ctl.item_off; qi.n_items = (uint32_t)ctl.m; qi.contact = ctl.contact; qi.status = QS_READY;
+    out.qinfo[q] = qi;
+  }
+  return Q_OK;
+}
+
+// Step 5: one polygon record -> its anisotropy-scaled area.
+XS_HD float poly_eval(const PolyRec& r, const PlaneGeom& g) {
+  if (r.kind == 2) return block_polygon_area((float)r.x, (float)r.y, (float)r.z, g);
+  return voxel_area((float)r.x, (float)r.y, (float)r.z, g);
+}
+
+// Step 6a: value of one item from the values of its polygons (xs3d.hpp:420-437), in record order.
+XS_HD float item_value(const ItemRec& it, const float* vals) {
+  const int cnt = (int)(it.meta & 15u);
+  float a = 0.0f;
+  if (it.meta & 16u) {
+    a = vals[it.poly];
+    if (a == 0.0f) return a;
+    for (int j = 1; j < cnt; j++) a = fsub(a, vals[it.poly + j]);
+  } else {
+    for (int j = 0; j < cnt; j++) a = fadd(a, vals[it.poly + j]);
+  }
+  return a;
+}
+
+// Step 6b: two-level float32 sum in the reference's order (xs3d.hpp:663,713 then :848,952) over item
+// values `iv[0..n)` whose `first` flag marks the first item of each lattice sample.
+struct OrderedSum {
+  float total, sub;
+  XS_HD void init() { total = 0.0f; sub = 0.0f; }
+  XS_HD void add(float v, bool first) {
+    if (first) { total = fadd(total, sub); sub = 0.0f; }
+    sub = fadd(sub, v);
+  }
+  XS_HD float finish() { return fadd(total, sub); }
+};
+
+// Path B, query side: xs3d.cross_section for one query.  Emits one record per distinct foreground voxel
+// the fill touches (kind 1) plus its linear index; the polygon kernel then gives each its value.
+// Neighbourhood and contact follow the UNROUNDED sample (xs3d.hpp:458-478, :1215-1220).
+template <class G, class CellT, class H>
+XS_D int run_section_emit(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, H& hash, Ctl& ctl,
+                          PolyRec* out_rec, uint64_t* out_idx, uint32_t out_cap, uint8_t* contact) {
+  typedef CellPack<CellT> P;
+  bool empty;
+  if (flood_component(g, c, vol, A, ctl, &empty) != Q_OK) return Q_OVERFLOW;
   if (empty) {
     if (g.tid() == 0) *contact = 0;
     return Q_OK;
   }
   const int n = ctl.n;
-  const Arena A = size_hash(A_in, n);
-  for (uint32_t i = g.tid(); i < A.hcap; i += g.size()) A.htag[i] = XS_HEMPTY;
+  hash.fit(n);
+  hash.clear(g);
   g.sync();
   uint32_t ct = 0u;
   bool ovf = false;
   const float fsx = (float)vol.sx, fsy = (float)vol.sy, fsz = (float)vol.sz;
   for (int r = g.tid(); r < n; r += g.size()) {
-    const uint32_t p = A.order[r];
-    const V3 cur = cell_point(c, A.ox + (int)(p & 0xffffu), A.oy + (int)(p >> 16));
+    const CellT p = A.order[r];
+    const V3 cur = cell_point(c, A.ox + P::u(p), A.oy + P::v(p));
     ct |= (uint32_t)(cur.x < 0.5f) | ((uint32_t)(cur.x >= c.hi[0]) << 1) | ((uint32_t)(cur.y < 0.5f) << 2) |
           ((uint32_t)(cur.y >= c.hi[1]) << 3) | ((uint32_t)(cur.z < 0.5f) << 4) | ((uint32_t)(cur.z >= c.hi[2]) << 5);
     int lo[3], hi[3];
@@ -705,27 +846,30 @@ XS_D int run_section(const G& g, const PlaneCtx& c, const VolView& vol, const Ar
     for (int dz = lo[2]; dz <= hi[2]; dz++)
       for (int dy = lo[1]; dy <= hi[1]; dy++)
         for (int dx = lo[0]; dx <= hi[0]; dx++) {
-          const V3 q = vround(vadd(mk((float)dx, (float)dy, (float)dz), cur));
-          if (q.x < 0.0f || q.x >= fsx || q.y < 0.0f || q.y >= fsy || q.z < 0.0f || q.z >= fsz) continue;
-          const int x = (int)q.x, y = (int)q.y, z = (int)q.z;
+          const V3 qv = vround(vadd(mk((float)dx, (float)dy, (float)dz), cur));
+          if (qv.x < 0.0f || qv.x >= fsx || qv.y < 0.0f || qv.y >= fsy || qv.z < 0.0f || qv.z >= fsz) continue;
+          const int x = (int)qv.x, y = (int)qv.y, z = (int)qv.z;
           if (!vox_fg(vol, x, y, z)) continue;
+          // dedupe on the voxel: the wide table keyed by (x,y,z) as if they were block coordinates of a
+          // volume with hx=sx, hy=sy; rank 0 everywhere, "fresh" = we created the entry
           const uint32_t id = (uint32_t)x + (uint32_t)vol.sx * ((uint32_t)y + (uint32_t)vol.sy * (uint32_t)z);
-          uint32_t h = hash_u32(id, A.hshift);
-          int probes = 0;
+          uint32_t h = (id * 2654435761u) >> hash.shift;
           bool fresh = false;
-          for (;;) {
-            const uint32_t t = atomic_cas_u32(&A.htag[h], XS_HEMPTY, id);
+          for (int probes = 0;; probes++) {
+            const uint32_t t = atomic_cas_u32(&hash.htag[h], XS_HEMPTY, id);
             if (t == XS_HEMPTY) { fresh = true; break; }
             if (t == id) break;
-            h = (h + 1u) & (A.hcap - 1u);
-            if (++probes == A.max_probe) { ovf = true; break; }
+            h = (h + 1u) & (hash.cap - 1u);
+            if (probes == hash.max_probe) { ovf = true; break; }
           }
           if (!fresh) continue;                  // first touch only (xs3d.hpp:511-512)
-          const float a = voxel_area((float)x, (float)y, (float)z, c.g);
-          if (a > 0.0f) {                        // xs3d.hpp:526-528
-            const uint32_t slot = atomic_add_u32(&ctl.counter, 1u);
-            if (slot < out_cap) { out_idx[slot] = (uint64_t)id; out_val[slot] = a; }
-            else ovf = true;
+          const uint32_t slot = atomic_add_u32(&ctl.counter, 1u);
+          if (slot < out_cap) {
+            PolyRec pr; pr.q = 0; pr.x = (uint16_t)x; pr.y = (uint16_t)y; pr.z = (uint16_t)z; pr.kind = 1;
+            out_rec[slot] = pr;
+            out_idx[slot] = (uint64_t)id;
+          } else {
+            ovf = true;
           }
         }
   }

@@ -63,9 +63,7 @@ __global__ void __launch_bounds__(256) slow_scan_kernel(SlowArgs a) {
       }
     } else {
       if (!(cube & 1u) || d > 1.8f) continue;   // auxiliary.hpp:72: only blocks whose origin voxel is set
-      V3 pts[7];
-      const int np = plane_cube_points<2>((float)(2 * bx), (float)(2 * by), (float)(2 * bz), a.g, pts);
-      const float area = polygon_area(pts, np, a.g);
+      const float area = block_polygon_area((float)(2 * bx), (float)(2 * by), (float)(2 * bz), a.g);
       if (!(area == 0.0f)) {
         const uint32_t slot = atomicAdd(&a.counters[0], 1u);
         if (slot < a.cap) { a.idx[slot] = (uint64_t)i; a.val[slot] = area; }

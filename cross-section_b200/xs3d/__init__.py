@@ -165,13 +165,24 @@ class Volume:
     s = (C.c_uint64 * 8)()
     _abi.check(self._lib.xs3d_volume_stats(self._h, s))
     return {"samples": s[0], "blocks": s[1], "cells_tested": s[2], "escalated_cta": s[3],
-            "escalated_worst_case": s[4], "launches": s[5]}
+            "escalated_worst_case": s[4], "launches": s[5], "failed": s[6], "polygons": s[7]}
+
+  def timing(self):
+    """CUDA-event kernel durations (ms) of the last call: warp tier, CTA tier, worst-case tier, ingest."""
+    t = (C.c_float * 6)()
+    _abi.check(self._lib.xs3d_volume_timing(self._h, t))
+    return {"warp_tier_ms": t[0], "cta_tier_ms": t[1], "worst_case_ms": t[2], "ingest_ms": t[3],
+            "polygon_ms": t[4], "combine_ms": t[5]}
+
+  def set_stream(self, cuda_stream):
+    """Launch on the given cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
+    _abi.check(self._lib.xs3d_volume_set_stream(self._h, C.c_void_p(int(cuda_stream))))
 
   def profile(self):
     """Per-phase SM cycles of the last batch (thread 0 of each query group, summed over queries)."""
     p = (C.c_uint64 * 12)()
     _abi.check(self._lib.xs3d_volume_profile(self._h, p))
-    names = ["flood", "claims", "items", "evaluate", "sum", "walk_only"]
+    names = ["flood", "claims", "emit", "unused3", "unused4", "walk_only"]
     return {"warp_tier": dict(zip(names, p[0:6])), "cta_tier": dict(zip(names, p[6:12]))}
 
   # -- queries

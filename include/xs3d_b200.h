@@ -59,13 +59,21 @@ int xs3d_volume_shape(xs3d_volume* vol, uint64_t shape[3]);
 int xs3d_area_batch(xs3d_volume* vol, uint64_t n, const float* pos, const float* normal,
                     const float anisotropy[3], int mem, float* area, uint8_t* contact);
 /* Counters of the last xs3d_area_batch on this volume:
- * stats[0] lattice samples, [1] owned blocks, [2] lattice cells tested, [3] queries escalated warp->CTA tier,
- * [4] queries escalated to the last-resort slab, [5] kernel launches of the call. */
+ * stats[0] lattice samples, [1] contributing blocks (items), [2] lattice cells tested, [3] queries escalated
+ * warp->CTA tier, [4] queries escalated to the worst-case slab, [5] kernel launches of the call,
+ * [6] queries that failed even there, [7] polygon records evaluated. */
 int xs3d_volume_stats(xs3d_volume* vol, uint64_t stats[8]);
 /* SM-clock cycles thread 0 of each query group spent per phase in the last xs3d_area_batch, summed over
- * queries: prof[0..5] warp tier, prof[6..11] CTA tier; phases: lattice flood (tiles + walk), claims,
- * ownership/items, evaluate, ordered sum, walk only. */
+ * queries: prof[0..5] warp tier, prof[6..11] CTA tier; phases: [0] lattice flood (tiles + walk), [1] claims,
+ * [2] ownership + record emission, [3] [4] unused, [5] walk only. */
 int xs3d_volume_profile(xs3d_volume* vol, uint64_t prof[12]);
+/* CUDA-event durations (ms, measured on the launching stream) of the kernels of the last call on this volume:
+ * ms[0] warp-tier query kernel, ms[1] CTA-tier query kernel, ms[2] worst-case query kernel,
+ * ms[3] ingest kernel (last xs3d_volume_load), ms[4] polygon kernel, ms[5] combine kernel. */
+int xs3d_volume_timing(xs3d_volume* vol, float ms[6]);
+/* Launch on the caller's stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) instead of the
+ * volume's own, so the caller's CUDA events bracket the work.  The stream must outlive the volume. */
+int xs3d_volume_set_stream(xs3d_volume* vol, void* cuda_stream);
 
 /* ---- drop-in single-call entry points: one per fastxs3d export ------------------------------------- */
 /* fastxs3d.area (fastxs3d.cpp:82-117).  use_persistent_data != 0 reuses the volume uploaded by the

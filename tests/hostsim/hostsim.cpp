@@ -23,78 +23,118 @@ static void host_ingest(const uint8_t* img, int sx, int sy, int sz, std::vector<
               (uint8_t)(1u << ((x & 1) | ((y & 1) << 1) | ((z & 1) << 2)));
 }
 
-struct HostArena {
-  std::vector<uint32_t> bits, tested, order, stack, spill, mask, htag, hkey, items, stage;
-  std::vector<float> vals;
-  Arena A;
-  // small == true mimics the warp tier's fixed shared-memory arena (so overflow paths get exercised)
-  void setup(const PlaneCtx& c, const VolView& v, bool small, int tiles, int max_n, uint32_t hcap, int max_m, int stack_cap) {
-    memset(&A, 0, sizeof(A));
-    if (small) {
-      A.tx = A.ty = tiles;
-      A.ox = c.c - 16 - 32 * (tiles / 2);
-      A.oy = A.ox;
-      A.halo = 0;
-    } else {
-      bbox_window(c, v, &A.ox, &A.oy, &A.tx, &A.ty);
-      A.halo = 1;
-    }
-    A.stride = A.tx + 1;
-    bits.assign((size_t)A.ty * 32 * A.stride, 0xdeadbeefu);   // kernel must clear it itself
-    tested.assign((A.tx * A.ty + 31) / 32, 0xdeadbeefu);
+static uint32_t pow2_at_least(uint64_t x) { uint32_t p = 64; while (p < x) p <<= 1; return p; }
+
+// Output buffers of the query kernels (what lives in HBM on the device)
+struct HostOut {
+  std::vector<PolyRec> polys;
+  std::vector<ItemRec> items;
+  std::vector<PlaneGeom> geom;
+  std::vector<QInfo> qinfo;
+  uint32_t counters[4];
+  EmitOut out;
+  void setup(size_t nq, size_t poly_cap, size_t item_cap) {
+    polys.assign(poly_cap, PolyRec()); items.assign(item_cap, ItemRec()); geom.assign(nq, PlaneGeom()); qinfo.assign(nq, QInfo());
+    counters[0] = counters[1] = counters[2] = counters[3] = 0;
+    out.polys = polys.data(); out.items = items.data(); out.geom = geom.data(); out.qinfo = qinfo.data();
+    out.counters = counters; out.poly_cap = (uint32_t)poly_cap; out.item_cap = (uint32_t)item_cap;
+  }
+};
+
+// warp-tier-like arena: 96x96 window, uint16 cells, packed hash, fixed capacities
+struct SmallArena {
+  std::vector<uint32_t> bits, tested, slots;
+  std::vector<uint16_t> order, stack;
+  Arena<uint16_t> A;
+  PackedHash H;
+  void setup(const PlaneCtx& c, const Sample& centre) {
+    const int tiles = 3, max_n = 384, hcap = 1024;
+    A.tx = A.ty = tiles; A.ox = A.oy = c.c - 16 - 32 * (tiles / 2); A.halo = 0; A.stride = tiles + 1;
+    bits.assign((size_t)tiles * 32 * A.stride, 0xdeadbeefu); tested.assign(4, 0xdeadbeefu);
+    order.assign(max_n, 0); stack.assign(max_n, 0); slots.assign(hcap, 0);
+    A.bits = bits.data(); A.tested = tested.data(); A.order = order.data(); A.stack = stack.data();
+    A.max_n = max_n; A.stack_cap = max_n; A.spill = nullptr; A.mask = A.bits;   // masks alias the (dead) bitmap
+    H.slot = slots.data(); H.cap = hcap; H.shift = 32 - __builtin_ctz(hcap); H.max_probe = 64;
+    H.cbx = centre.rx >> 1; H.cby = centre.ry >> 1; H.cbz = centre.rz >> 1;
+  }
+};
+
+// CTA-tier-like arena: bbox window, uint32 cells, wide hash, optional tiny stack ring
+struct BigArena {
+  std::vector<uint32_t> bits, tested, order, stack, spill, mask, htag, hkey;
+  Arena<uint32_t> A;
+  WideHash H;
+  void setup(const PlaneCtx& c, const VolView& v, int stack_cap, int factor) {
+    bbox_window(c, v, &A.ox, &A.oy, &A.tx, &A.ty);
+    A.halo = 1; A.stride = A.tx + 1;
+    const int max_n = A.tx * A.ty * 1024;
+    bits.assign((size_t)A.ty * 32 * A.stride, 0xdeadbeefu); tested.assign((A.tx * A.ty + 31) / 32, 0xdeadbeefu);
     order.assign(max_n, 0); mask.assign(max_n, 0);
     A.max_n = max_n;
     if (stack_cap > 0) { stack.assign(stack_cap, 0); spill.assign(max_n, 0); A.stack_cap = stack_cap; A.spill = spill.data(); }
     else { stack.assign(max_n, 0); A.stack_cap = max_n; A.spill = nullptr; }
+    const uint32_t hcap = pow2_at_least((uint64_t)max_n * (uint64_t)factor + 64);
     htag.assign(hcap, 0); hkey.assign(hcap, 0);
-    A.hcap = hcap; A.hshift = 32 - __builtin_ctz(hcap); A.hcap_max = hcap; A.hash_factor = small ? 0 : 16; A.max_probe = small ? 128 : 0;
-    items.assign(max_m, 0); vals.assign(max_m, 0.f);
-    A.max_m = max_m;
-    A.bits = bits.data(); A.tested = tested.data(); A.order = order.data(); A.stack = stack.data();
-    A.mask = mask.data(); A.htag = htag.data(); A.hkey = hkey.data(); A.items = items.data(); A.vals = vals.data();
-    A.stage = nullptr; A.stage_cap = 0;
+    A.bits = bits.data(); A.tested = tested.data(); A.order = order.data(); A.stack = stack.data(); A.mask = mask.data();
+    H.htag = htag.data(); H.hkey = hkey.data(); H.cap = hcap; H.cap_max = hcap; H.shift = 32 - __builtin_ctz(hcap);
+    H.hx = v.hx; H.hy = v.hy; H.max_probe = 1 << 30; H.factor = factor;
   }
 };
-
-static uint32_t pow2_at_least(uint64_t x) { uint32_t p = 64; while (p < x) p <<= 1; return p; }
 
 extern "C" {
 
 // mode 0: big arena only.  mode 1: small (warp-tier-like) arena first, big arena on overflow.
-// mode 2: like 0 but with a tiny DFS stack ring (exercises spill/refill) and staged ordered sum.
-// stats[0] = queries that overflowed the small arena, stats[1] = total samples, stats[2] = total items
+// mode 2: like 0 but with a tiny DFS stack ring (exercises spill/refill).
+// stats[0] = queries that overflowed the small arena, stats[1] = total samples, stats[2] = total items, stats[3] = polygons
 void hostsim_area_batch(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t sz, uint64_t nq, const float* pos,
                         const float* nrm, const float* w, float* area, uint8_t* contact, int mode, int64_t* stats) {
   std::vector<uint8_t> cubes;
   host_ingest(img, (int)sx, (int)sy, (int)sz, cubes);
   VolView v = { cubes.data(), (int)sx, (int)sy, (int)sz, ((int)sx + 1) >> 1, ((int)sy + 1) >> 1, ((int)sz + 1) >> 1 };
   HostGroup g;
-  HostArena small, big;
-  int64_t n_over = 0, n_samples = 0, n_items = 0;
+  int64_t n_over = 0, n_samples = 0;
+  HostOut O;
+  O.setup(nq, 1 << 22, 1 << 21);
+  // ---- query kernels
   for (uint64_t q = 0; q < nq; q++) {
     PlaneCtx c;
-    area[q] = 0.f; contact[q] = 0;
+    QInfo qi; qi.item_off = 0; qi.n_items = 0; qi.contact = 0; qi.status = QS_READY;
+    O.qinfo[q] = qi;
     if (!plane_init(c, v, mk(pos[3*q], pos[3*q+1], pos[3*q+2]), mk(nrm[3*q], nrm[3*q+1], nrm[3*q+2]), mk(w[0], w[1], w[2]))) continue;
-    Ctl ctl; float scratch;
+    O.qinfo[q].status = QS_PENDING;
+    Ctl ctl;
     int st = Q_OVERFLOW;
     if (mode == 1) {
-      small.setup(c, v, true, 3, 384, 1024, 768, 0);
-      st = run_area(g, c, v, small.A, ctl, &scratch, &area[q], &contact[q]);
+      SmallArena sa;
+      const V3 rp = vround(c.g.pos);
+      Sample ctr; ctr.rx = (int)rp.x; ctr.ry = (int)rp.y; ctr.rz = (int)rp.z;
+      sa.setup(c, ctr);
+      st = run_area_emit(g, c, v, sa.A, sa.H, ctl, (uint32_t)q, O.out);
       if (st != Q_OK) n_over++;
     }
     if (st != Q_OK) {
-      int otx, oty, ox, oy;
-      bbox_window(c, v, &ox, &oy, &otx, &oty);
-      const int max_n = otx * oty * 1024;
-      big.setup(c, v, false, 0, max_n, pow2_at_least((uint64_t)max_n * 8), max_n * 4, mode == 2 ? 16 : 0);
-      std::vector<uint32_t> stage;
-      if (mode == 2) { stage.assign(64, 0); big.A.stage = stage.data(); big.A.stage_cap = 64; }
-      st = run_area(g, c, v, big.A, ctl, &scratch, &area[q], &contact[q]);
-      if (st != Q_OK) { area[q] = -1.f; contact[q] = 0xff; }
+      BigArena ba;
+      ba.setup(c, v, mode == 2 ? 16 : 0, 16);
+      st = run_area_emit(g, c, v, ba.A, ba.H, ctl, (uint32_t)q, O.out);
     }
-    n_samples += ctl.n; n_items += ctl.m;
+    n_samples += ctl.n;
   }
-  if (stats) { stats[0] = n_over; stats[1] = n_samples; stats[2] = n_items; }
+  // ---- polygon kernel
+  const uint32_t np = O.counters[0];
+  std::vector<float> vals(np);
+  for (uint32_t i = 0; i < np; i++) vals[i] = poly_eval(O.polys[i], O.geom[O.polys[i].q]);
+  // ---- combine kernel
+  for (uint64_t q = 0; q < nq; q++) {
+    const QInfo qi = O.qinfo[q];
+    if (qi.status != QS_READY) { area[q] = -1.f; contact[q] = 0xff; continue; }
+    OrderedSum s; s.init();
+    for (uint32_t i = 0; i < qi.n_items; i++) {
+      const ItemRec it = O.items[qi.item_off + i];
+      s.add(item_value(it, vals.data()), (it.meta & 32u) != 0);
+    }
+    area[q] = s.finish(); contact[q] = (uint8_t)qi.contact;
+  }
+  if (stats) { stats[0] = n_over; stats[1] = n_samples; stats[2] = O.counters[1]; }
 }
 
 // Dense float32 F-order image (zeroed by the caller), like fastxs3d.section method 0.
@@ -107,17 +147,18 @@ int hostsim_section(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t sz, c
   PlaneCtx c;
   *contact = 0;
   if (!plane_init(c, v, mk(p[0], p[1], p[2]), mk(n[0], n[1], n[2]), mk(w[0], w[1], w[2]))) return 0;
-  HostArena big;
-  int otx, oty, ox, oy;
-  bbox_window(c, v, &ox, &oy, &otx, &oty);
-  const int max_n = otx * oty * 1024;
-  big.setup(c, v, false, 0, max_n, pow2_at_least((uint64_t)max_n * 64), 16, 0);
-  std::vector<uint64_t> idx((size_t)max_n * 27);
-  std::vector<float> val((size_t)max_n * 27);
+  BigArena ba;
+  ba.setup(c, v, 0, 64);
+  const size_t cap = (size_t)ba.A.max_n * 27;
+  std::vector<uint64_t> idx(cap);
+  std::vector<PolyRec> rec(cap);
   Ctl ctl;
-  int st = run_section(g, c, v, big.A, ctl, idx.data(), val.data(), (uint32_t)idx.size(), contact);
+  int st = run_section_emit(g, c, v, ba.A, ba.H, ctl, rec.data(), idx.data(), (uint32_t)cap, contact);
   if (st != Q_OK) return -1;
-  for (uint32_t i = 0; i < ctl.counter; i++) out[idx[i]] = val[i];
+  for (uint32_t i = 0; i < ctl.counter; i++) {
+    const float a = poly_eval(rec[i], c.g);
+    if (a > 0.0f) out[idx[i]] = a;          // xs3d.hpp:526-528
+  }
   return (int)ctl.counter;
 }
 
