@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — cross-sections/sec for a batched skeleton sweep on a 512^3 synthetic neurite (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Own arm (default).  One step = one pass of the hot path over one batch: QUERIES (10 000) (vertex, normal)
+queries of the skeleton sweep against the 512^3 neurite volume.
+  value : whole-job throughput with inputs resident in HBM (volume ingested, queries and results on the
+          device), timed with CUDA events on the launching stream, L2 flushed between steps, max over ranks.
+  e2e   : the same sweep through the C ABI with HOST buffers: every step uploads the 128 MiB volume and the
+          queries from pinned host memory, ingests, runs, and reads areas + contact bits back.
+  roofline     : the dominant kernel (warp-tier query kernel), algorithmic bytes / CUDA-event duration vs the
+                 measured HBM peak (MEASURED_PEAKS.json).
+  cpu_baseline : the compiled reference (oracle/_ref, else the C port) fanned out over all host cores.
+N > 1: one process per GPU (torchrun), queries partitioned with no data-path collective (weak scaling:
+each rank sweeps its own 10 000-query draw); the volume's occupancy bytes are NCCL-broadcast once at setup.
+
+Reference arm (--impl reference): the reference's own CPU implementation of the path (oracle/_ref when it
+was compiled, else the port) on all host cores, same workload/metric; rank 0 only.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "cross-section_b200"))
+
+QUERIES = 10000
+VOLUME_N = 512
+ANISOTROPY = (32.0, 32.0, 40.0)
+METRIC = "cross-sections/sec (batched skeleton vertices, 512^3 vol)"
+WORKLOAD = "neurite512_sweep10k"
+
+
+def make_workload(rank=0):
+  from xs3d import synthetic
+  vol, verts, tans = synthetic.make_neurite(VOLUME_N, seed=0)
+  pos, nrm = synthetic.draw_queries(verts, tans, QUERIES, seed=1 + rank)
+  return vol, pos, nrm
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+_G = {}
+
+
+def _cpu_chunk(args):
+  lo, hi = args
+  return _G["chk"].area_batch(_G["vol"], _G["pos"][lo:hi], _G["nrm"][lo:hi], ANISOTROPY, nthreads=1)
+
+
+def cpu_sweep_rate(vol, pos, nrm, passes, warm=1):
+  """The single-query reference fanned out over all host cores with fork()ed workers (the volume is
+  inherited copy-on-write), one contiguous chunk per worker.  Returns
+  (xs/s, cores, kind, seconds per pass list)."""
+  sys.path.insert(0, os.path.join(ROOT, "oracle"))
+  import refapi
+  if refapi.have_ref():
+    chk, kind = refapi.Ref(), "reference"
+  else:
+    if not refapi.have_oracle():
+      subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+    chk, kind = refapi.Oracle(), "port"
+  cores = os.cpu_count() or 1
+  _G.update(chk=chk, vol=vol, pos=pos, nrm=nrm)
+  n = len(pos)
+  chunks = [(i * n // cores, (i + 1) * n // cores) for i in range(cores)]
+  times = []
+  with mp.get_context("fork").Pool(cores) as pool:
+    for _ in range(warm):
+      pool.map(_cpu_chunk, chunks)
+    for _ in range(passes):
+      t = time.perf_counter()
+      pool.map(_cpu_chunk, chunks)
+      times.append(time.perf_counter() - t)
+  return n / (sum(times) / len(times)), cores, kind, times
+
+
+def run_reference_arm(args):
+  rank = int(os.environ.get("RANK", "0"))
+  if rank != 0:
+    return
+  vol, pos, nrm = make_workload(0)
+  rate, cores, kind, times = cpu_sweep_rate(vol, pos, nrm, passes=max(1, args.steps), warm=max(1, args.warmup))
+  ms = 1000.0 * sum(times) / len(times)
+  line = {
+    "impl": "reference", "metric": METRIC, "value": rate, "unit": "cross-sections/s", "n_gpus": args.gpus,
+    "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+    "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+    "config": {"workload": WORKLOAD, "volume": [VOLUME_N] * 3, "queries_per_step": QUERIES, "anisotropy": list(ANISOTROPY)},
+    "cpu_baseline": {"value": rate, "unit": "cross-sections/s", "cores": cores, "kind": kind,
+                     "sample": f"{len(times)} passes of the full {QUERIES}-query sweep, fork()ed workers, one chunk per core"},
+    "e2e": {"value": rate, "unit": "cross-sections/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    "gpu_launches": 0,
+  }
+  print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+  """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+  Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+  def __init__(self, index):
+    self.index, self.rows, self.proc = index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      threading.Thread(target=self._read, daemon=True).start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([x.strip() for x in line.split(",")])
+
+  def stop(self):
+    if self.proc:
+      self.proc.terminate()
+    sm, mx, reasons = [], 0, set()
+    for r in self.rows:
+      try:
+        sm.append(float(r[1])); mx = max(mx, float(r[2]))
+        for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+          if val.lower().startswith("active"):
+            reasons.add(name)
+      except Exception:
+        pass
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_own_arm(args):
+  import torch
+  import torch.distributed as dist
+  import xs3d
+  from xs3d import dist as xdist
+
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local = int(os.environ.get("LOCAL_RANK", "0"))
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+  torch.cuda.set_device(local)
+  dev = torch.device("cuda", local)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+  vol, pos, nrm = make_workload(rank)
+  w = np.asarray(ANISOTROPY, np.float32)
+  V = xs3d.Volume(shape=vol.shape, device=local)
+  V.set_stream(torch.cuda.current_stream().cuda_stream)
+  if world > 1:
+    xdist.broadcast_volume(V, vol if rank == 0 else None, src=0)   # one NCCL broadcast of the 16 MiB occupancy bytes
+  else:
+    V.load(vol)
+  dpos = torch.from_numpy(pos).to(dev)
+  dnrm = torch.from_numpy(nrm).to(dev)
+  flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      dist.barrier()
+      torch.cuda.synchronize()
+
+  # ---- resident-in-HBM timing (`value`)
+  def step_resident():
+    return V.cross_sectional_area_batch(dpos, dnrm, w, return_contact=True)
+
+  for _ in range(max(3, args.warmup)):
+    step_resident()
+  sampler = ClockSampler(local)
+  if rank == 0:
+    sampler.start()
+  barrier()
+  starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+  ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+  kern = {"warp_tier_ms": 0.0, "mid_tier_ms": 0.0, "big_tier_ms": 0.0, "polygon_ms": 0.0, "combine_ms": 0.0, "worst_case_ms": 0.0}
+  launches = 0
+  stats = None
+  for i in range(args.steps):
+    flush.fill_(i & 255)                 # evict L2 between timed iterations (untimed)
+    starts[i].record()
+    step_resident()
+    ends[i].record()
+    torch.cuda.synchronize()
+    t = V.timing()
+    for k in kern:
+      kern[k] += t[k]
+    stats = V.stats()
+    launches += stats["launches"]
+  barrier()
+  ms_total = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+  if world > 1:
+    tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+  value = world * QUERIES * args.steps / (ms_total / 1000.0)
+
+  # ---- end to end through the C ABI with host buffers (`e2e`): volume + queries up, results down, every step
+  import ctypes as C
+  from xs3d import _abi
+  hvol = torch.from_numpy(np.ascontiguousarray(vol.view(np.uint8).ravel(order="F"))).pin_memory()
+  hpos = torch.from_numpy(pos.copy()).pin_memory()
+  hnrm = torch.from_numpy(nrm.copy()).pin_memory()
+  harea = torch.empty(QUERIES, dtype=torch.float32).pin_memory()
+  hct = torch.empty(QUERIES, dtype=torch.uint8).pin_memory()
+  L = _abi.lib()
+
+  def step_e2e():
+    _abi.check(L.xs3d_volume_load(V._h, hvol.data_ptr(), _abi.HOST, 0))
+    _abi.check(L.xs3d_area_batch(V._h, QUERIES, hpos.data_ptr(), hnrm.data_ptr(), _abi.fptr(w), _abi.HOST, harea.data_ptr(), hct.data_ptr()))
+
+  def step_e2e_resident():
+    _abi.check(L.xs3d_area_batch(V._h, QUERIES, hpos.data_ptr(), hnrm.data_ptr(), _abi.fptr(w), _abi.HOST, harea.data_ptr(), hct.data_ptr()))
+
+  def time_steps(fn):
+    for _ in range(max(3, args.warmup)):
+      fn()
+    barrier()
+    tot = 0.0
+    for i in range(args.steps):
+      flush.fill_(i & 255)
+      s = torch.cuda.Event(enable_timing=True); e = torch.cuda.Event(enable_timing=True)
+      s.record(); fn(); e.record()
+      torch.cuda.synchronize()
+      tot += s.elapsed_time(e)
+    barrier()
+    if world > 1:
+      tt = torch.tensor([tot], dtype=torch.float64, device=dev)
+      dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+      tot = float(tt.item())
+    return tot
+
+  ms_e2e = time_steps(step_e2e)
+  ingest_ms = V.timing()["ingest_ms"]
+  ms_e2e_res = time_steps(step_e2e_resident)
+  e2e_value = world * QUERIES * args.steps / (ms_e2e / 1000.0)
+  e2e_res_value = world * QUERIES * args.steps / (ms_e2e_res / 1000.0)
+  clocks = sampler.stop() if rank == 0 else None
+
+  # parity spot check inside the bench (results of the e2e path vs the resident path)
+  da, dc = step_resident()
+  assert np.array_equal(da.cpu().numpy().view(np.uint32), harea.numpy().view(np.uint32)) and np.array_equal(dc.cpu().numpy(), hct.numpy())
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
+  # ---- roofline of the dominant kernel
+  peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(peaks_path):
+    peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+  else:
+    peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+  dom = max(("warp_tier_ms", "mid_tier_ms", "big_tier_ms", "polygon_ms"), key=lambda k: kern[k])
+  dom_ms = kern[dom] / args.steps
+  # algorithmic bytes of one sweep (SURVEY.md §8d formula for the uint8 volume): one byte per
+  # lattice sample, 8 bytes per 2x2x2 block touched, 24 B query in, 5 B result out
+  alg_bytes = stats["samples"] * 1 + 8 * stats["blocks"] + 29 * QUERIES
+  achieved = alg_bytes / (dom_ms / 1000.0) / 1e9
+  roofline = {"bound": "hbm", "kernel": {"warp_tier_ms": "area_warp_kernel", "mid_tier_ms": "area_block_kernel<MidTier>", "big_tier_ms": "area_block_kernel<BigTier>", "polygon_ms": "poly_eval_kernel"}[dom],
+              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms,
+              "note": "latency/issue-bound graph walk: ~1.8 KB of algorithmic traffic per query, L2-resident 16 MiB occupancy volume (see profiles/)",
+              "ingest_kernel": {"ms": ingest_ms, "achieved": (vol.size * 1.125) / (ingest_ms / 1000.0) / 1e9 if ingest_ms > 0 else None,
+                                "unit": "GB/s", "algorithmic_bytes": int(vol.size * 1.125)}}
+
+  # ---- CPU baseline on this box's host cores (bounded: a few passes of the same sweep)
+  rate, cores, kind, times = cpu_sweep_rate(vol, pos, nrm, passes=3, warm=1)
+  line = {
+    "metric": METRIC, "value": value, "unit": "cross-sections/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+    "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    "dtype": "f32", "data": "synthetic",
+    "config": {"workload": WORKLOAD, "volume": [VOLUME_N] * 3, "queries_per_step": QUERIES, "queries_per_rank": QUERIES,
+               "anisotropy": list(ANISOTROPY), "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"query-sharded x{world}"},
+    "e2e": {"value": e2e_value, "unit": "cross-sections/s", "h2d_bytes_per_step": int(vol.size + 2 * pos.nbytes),
+            "d2h_bytes_per_step": int(QUERIES * 5), "ms_per_step": ms_e2e / args.steps,
+            "includes": "volume upload (128 MiB) + ingest + queries up + results down, every step",
+            "volume_resident": {"value": e2e_res_value, "ms_per_step": ms_e2e_res / args.steps, "h2d_bytes_per_step": int(2 * pos.nbytes)}},
+    "gpu_launches": int(launches),
+    "kernels_ms_per_step": {k: v / args.steps for k, v in kern.items()},
+    "work_per_step": {k: int(stats[k]) for k in ("samples", "blocks", "polygons", "cells_tested", "escalated_mid", "escalated_big", "escalated_worst_case")},
+    "roofline": roofline,
+    "cpu_baseline": {"value": rate, "unit": "cross-sections/s", "cores": cores, "kind": kind,
+                     "sample": f"{len(times)} passes of the full {QUERIES}-query sweep, fork()ed workers, one chunk per core"},
+    "clocks": clocks,
+  }
+  print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=3)
+  ap.add_argument("--impl", default="own", choices=["own", "reference"])
+  args = ap.parse_args()
+  if args.impl == "reference":
+    run_reference_arm(args)
+  else:
+    run_own_arm(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -150,7 +150,7 @@ struct BatchArgs {
   uint32_t* list_in;         // queries to process (null: 0..nq-1)
   uint32_t* list_out;        // queries this tier could not fit
 };
-enum { CNT_NEXT0 = 0, CNT_OVER0 = 1, CNT_NEXT1 = 2, CNT_OVER1 = 3, CNT_NEXT2 = 4, CNT_OVER2 = 5, CNT_WORDS = 8 };
+enum { CNT_NEXT0 = 0, CNT_OVER0 = 1, CNT_NEXT1 = 2, CNT_OVER1 = 3, CNT_NEXT2 = 4, CNT_OVER2 = 5, CNT_NEXT3 = 6, CNT_OVER3 = 7, CNT_WORDS = 8 };
 
 __device__ __forceinline__ void finish_query(const BatchArgs& a, const Ctl& ctl, uint32_t q, int st, int cnt_over, int stats_base) {
   // thread 0 of the group
@@ -229,14 +229,30 @@ __host__ __device__ inline size_t slab_bytes(const SlabCfg& s) {
   return ((words * 4 + 255) / 256) * 256;
 }
 
-constexpr int BLK_THREADS = 512;
-constexpr int BLK_RING = 16384;          // DFS stack ring (words)
-constexpr int BLK_TESTED = 1024;         // tile mask words held in shared memory
-constexpr int BLK_CTL_WORDS = 48;        // Ctl + a few scalars
-constexpr int BLK_FIXED_WORDS = 64 + BLK_CTL_WORDS + BLK_RING + BLK_TESTED;
+// CTA-tier shapes.  MID: many small CTAs with a centred window (the few-percent of sweep queries that do not
+// fit a warp).  BIG: one full-SM CTA with the whole-plane window in shared memory (large single sections).
+template <int THREADS_, int RING_, int WIN_TILES_, int TESTED_, int MIN_BLOCKS_>
+struct BlockTier {
+  static constexpr int THREADS = THREADS_;
+  static constexpr int RING = RING_;               // DFS stack ring (words) in shared memory
+  static constexpr int WIN_TILES = WIN_TILES_;     // > 0: centred window of WIN_TILES^2 tiles; 0: whole-plane (bbox) window
+  static constexpr int TESTED = TESTED_;           // tile-mask words in shared memory
+  static constexpr int MIN_BLOCKS = MIN_BLOCKS_;
+  static constexpr int CTL_WORDS = 48;
+  static constexpr int O_CTL = 64;
+  static constexpr int O_RING = O_CTL + CTL_WORDS;
+  static constexpr int O_TESTED = O_RING + RING;
+  static constexpr int O_BITS = O_TESTED + TESTED;
+  static constexpr int WIN_WORDS = WIN_TILES * 32 * (WIN_TILES + 1);
+  static constexpr int FIXED_WORDS = O_BITS;       // + bitmap words
+};
+using MidTier = BlockTier<128, 2048, 17, 16, 4>;   // 544 x 544 cells, ~47 KB -> 4 CTAs per SM
+using BigTier = BlockTier<512, 16384, 0, 1024, 1>;
+constexpr int BLK_THREADS = BigTier::THREADS;
 static_assert(sizeof(Ctl) <= 40 * 4, "ctl slot");
 
 // returns false when the window does not fit any buffer this CTA owns
+template <class T>
 __device__ __forceinline__ bool block_arena(Arena<uint32_t>& A, WideHash& H, const SlabCfg& s, uint32_t* smem, int smem_bits_words,
                                             const PlaneCtx& c, const VolView& vol) {
   char* slab = s.base + (size_t)blockIdx.x * s.stride;
@@ -254,26 +270,37 @@ __device__ __forceinline__ bool block_arena(Arena<uint32_t>& A, WideHash& H, con
   int lg = 0;
   while ((1u << lg) < s.hcap_max) lg++;
   H.shift = 32 - lg;
-  A.stack = smem + 64 + BLK_CTL_WORDS; A.stack_cap = BLK_RING;
+  A.stack = smem + T::O_RING; A.stack_cap = T::RING;
+  if (T::WIN_TILES > 0) {
+    A.tx = A.ty = T::WIN_TILES;
+    A.ox = A.oy = c.c - 16 - 32 * (T::WIN_TILES / 2);
+    A.stride = A.tx + 1;
+    A.halo = 0;
+    A.bits = smem + T::O_BITS;
+    A.tested = smem + T::O_TESTED;
+    return true;
+  }
   bbox_window(c, vol, &A.ox, &A.oy, &A.tx, &A.ty);
   A.stride = A.tx + 1;
   A.halo = 1;
   const size_t words = (size_t)A.ty * 32 * A.stride;
   const size_t twords = (size_t)((A.tx * A.ty + 31) / 32);
   const bool bits_in_smem = words <= (size_t)smem_bits_words;
-  const bool tested_in_smem = twords <= (size_t)BLK_TESTED;
-  A.bits = bits_in_smem ? (smem + BLK_FIXED_WORDS) : g_bits;
-  A.tested = tested_in_smem ? (smem + 64 + BLK_CTL_WORDS + BLK_RING) : g_tested;
+  const bool tested_in_smem = twords <= (size_t)T::TESTED;
+  A.bits = bits_in_smem ? (smem + T::O_BITS) : g_bits;
+  A.tested = tested_in_smem ? (smem + T::O_TESTED) : g_tested;
   if (!bits_in_smem && words > s.bits_words) return false;
   if (!tested_in_smem && twords > s.tested_words) return false;
   return true;
 }
 
-__global__ void __launch_bounds__(BLK_THREADS, 1) area_block_kernel(BatchArgs a, SlabCfg s, int smem_bits_words, int cnt_next, int cnt_over, const uint32_t* count_ptr) {
+template <class T>
+__global__ void __launch_bounds__(T::THREADS, T::MIN_BLOCKS) area_block_kernel(BatchArgs a, SlabCfg s, int smem_bits_words, int cnt_next, int cnt_over,
+                                                                                 const uint32_t* count_ptr, int stats_base) {
   extern __shared__ __align__(16) uint32_t smem[];
   BlockGroup g(reinterpret_cast<int*>(smem));
-  Ctl& ctl = *reinterpret_cast<Ctl*>(smem + 64);
-  int* next = reinterpret_cast<int*>(smem + 64 + 42);
+  Ctl& ctl = *reinterpret_cast<Ctl*>(smem + T::O_CTL);
+  int* next = reinterpret_cast<int*>(smem + T::O_CTL + 42);
   const V3 w = mk(a.wx, a.wy, a.wz);
   const uint32_t count = count_ptr ? *count_ptr : a.nq;
   for (;;) {
@@ -293,8 +320,8 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) area_block_kernel(BatchArgs a,
     Arena<uint32_t> A;
     WideHash H;
     int st = Q_OVERFLOW;
-    if (block_arena(A, H, s, smem, smem_bits_words, c, a.vol)) st = run_area_emit(g, c, a.vol, A, H, ctl, q, a.out);
-    if (threadIdx.x == 0) finish_query(a, ctl, q, st, cnt_over, 10);
+    if (block_arena<T>(A, H, s, smem, smem_bits_words, c, a.vol)) st = run_area_emit(g, c, a.vol, A, H, ctl, q, a.out);
+    if (threadIdx.x == 0) finish_query(a, ctl, q, st, cnt_over, stats_base);
   }
 }
 
@@ -304,8 +331,8 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) section_block_kernel(VolView v
                                                                         PlaneGeom* geom, uint32_t* result) {
   extern __shared__ __align__(16) uint32_t smem[];
   BlockGroup g(reinterpret_cast<int*>(smem));
-  Ctl& ctl = *reinterpret_cast<Ctl*>(smem + 64);
-  uint8_t* ct = reinterpret_cast<uint8_t*>(smem + 64 + 42);
+  Ctl& ctl = *reinterpret_cast<Ctl*>(smem + BigTier::O_CTL);
+  uint8_t* ct = reinterpret_cast<uint8_t*>(smem + BigTier::O_CTL + 42);
   PlaneCtx c;
   if (threadIdx.x == 0) { result[0] = Q_OK; result[1] = 0; result[2] = 0; }
   if (!plane_init(c, vol, p, n, w)) return;
@@ -314,7 +341,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) section_block_kernel(VolView v
   int st = Q_OVERFLOW;
   if (threadIdx.x == 0) ctl.counter = 0u;
   __syncthreads();
-  if (block_arena(A, H, s, smem, smem_bits_words, c, vol)) st = run_section_emit(g, c, vol, A, H, ctl, out_rec, out_idx, out_cap, ct);
+  if (block_arena<BigTier>(A, H, s, smem, smem_bits_words, c, vol)) st = run_section_emit(g, c, vol, A, H, ctl, out_rec, out_idx, out_cap, ct);
   __syncthreads();
   if (threadIdx.x == 0) { geom[0] = c.g; result[0] = (uint32_t)st; result[1] = ctl.counter; result[2] = (st == Q_OK) ? *ct : 0u; }
 }
@@ -408,17 +435,19 @@ struct xs3d_volume {
   bool labels_loaded = false;
   // batch workspace
   DevBuf q_pos, q_nrm, q_area, q_contact, lists, counters, slab1, slab2, sec_idx, sec_val, misc;
-  DevBuf polys, items, vals, geom, qinfo;
+  DevBuf polys, items, vals, geom, qinfo, slab_mid;
+  SlabCfg cfg_mid{};
+  int mid_ctas = 0;
   uint64_t poly_cap = 0, item_cap = 0;
   SlabCfg cfg1{}, cfg2{};
   uint32_t* h_counters = nullptr;   // pinned: CNT_WORDS counters + 8 u64 stats
-  uint64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   int sm_count = 0, smem_optin = 0;
   bool kernels_configured = false;
   bool own_stream = true;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  float timing[6] = {0, 0, 0, 0, 0, 0};   // ms of the last call: warp-tier, CTA-tier, worst-case query kernels, ingest, polygon, combine
+  float timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // ms: warp / mid / big / worst-case query kernels, ingest, polygon, combine, spare
 };
 
 static VolView view_of(const xs3d_volume* v) {
@@ -429,14 +458,16 @@ static VolView view_of(const xs3d_volume* v) {
 }
 
 static int block_smem_bytes(const xs3d_volume* v) { return v->smem_optin; }
-static int block_smem_bits_words(const xs3d_volume* v) { return v->smem_optin / 4 - BLK_FIXED_WORDS; }
+static int block_smem_bits_words(const xs3d_volume* v) { return v->smem_optin / 4 - BigTier::FIXED_WORDS; }
+constexpr int MID_SMEM_BYTES = (MidTier::FIXED_WORDS + MidTier::WIN_WORDS) * 4;
 
 static int configure_kernels(xs3d_volume* v) {
   if (v->kernels_configured) return XS3D_OK;
   const int t0_bytes = T0_WARPS * T0Layout::WORDS * 4;
   if (t0_bytes > v->smem_optin) return fail(XS3D_ERR_UNSUPPORTED, "device shared memory too small for the warp tier");
   CK(cudaFuncSetAttribute(T0_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, t0_bytes));
-  CK(cudaFuncSetAttribute(area_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
+  CK(cudaFuncSetAttribute(area_block_kernel<BigTier>, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
+  CK(cudaFuncSetAttribute(area_block_kernel<MidTier>, cudaFuncAttributeMaxDynamicSharedMemorySize, MID_SMEM_BYTES));
   CK(cudaFuncSetAttribute(section_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
   v->kernels_configured = true;
   return XS3D_OK;
@@ -473,7 +504,7 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
   for (int i = 0; i < 8; i++) if (v->ev[i]) cudaEventDestroy(v->ev[i]);
   DevBuf* bufs[] = { &v->cubes, &v->raw, &v->labels, &v->q_pos, &v->q_nrm, &v->q_area, &v->q_contact, &v->lists,
                      &v->counters, &v->slab1, &v->slab2, &v->sec_idx, &v->sec_val, &v->misc,
-                     &v->polys, &v->items, &v->vals, &v->geom, &v->qinfo };
+                     &v->polys, &v->items, &v->vals, &v->geom, &v->qinfo, &v->slab_mid };
   for (DevBuf* b : bufs) b->release();
   if (v->h_counters) cudaFreeHost(v->h_counters);
   delete v;
@@ -523,7 +554,7 @@ extern "C" int xs3d_volume_load(xs3d_volume* v, const uint8_t* binimg, int mem, 
   RET(launch_ingest(v, d_img, c_order));
   CK(cudaEventRecord(v->ev[7], v->stream));
   CK(cudaStreamSynchronize(v->stream));
-  CK(cudaEventElapsedTime(&v->timing[3], v->ev[6], v->ev[7]));
+  CK(cudaEventElapsedTime(&v->timing[4], v->ev[6], v->ev[7]));
   v->loaded = true;
   return XS3D_OK;
 }
@@ -576,8 +607,17 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
   RET(v->q_nrm.ensure(n * 12 + 64));
   RET(v->q_area.ensure(n * 4 + 64));
   RET(v->q_contact.ensure(n + 64));
-  RET(v->lists.ensure(n * 4 * 3 + 64));
+  RET(v->lists.ensure(n * 4 * 4 + 64));
   RET(v->counters.ensure(512));
+  if (!v->slab_mid.p) {
+    SlabCfg m{};
+    m.max_n = 1 << 14; m.hcap_max = 1u << 17; m.bits_words = 0; m.tested_words = 0; m.hash_factor = 8; m.max_probe = 256;
+    m.stride = slab_bytes(m);
+    v->mid_ctas = v->sm_count * MidTier::MIN_BLOCKS;
+    RET(v->slab_mid.ensure(m.stride * (size_t)v->mid_ctas));
+    m.base = (char*)v->slab_mid.p;
+    v->cfg_mid = m;
+  }
   RET(v->geom.ensure(n * sizeof(PlaneGeom) + 64));
   RET(v->qinfo.ensure(n * sizeof(QInfo) + 64));
   if (v->poly_cap == 0) {
@@ -606,20 +646,20 @@ static int ensure_worst_case_slab(xs3d_volume* v) {
   return XS3D_OK;
 }
 
-// Core of the batched area path; all pointers are device pointers.  skip_warp_tier: tiny batches go
-// straight to the CTA tier.  Launch sequence (no host synchronisation in between):
-//   warp-tier query kernel -> CTA-tier query kernel (what the warp tier could not fit) -> polygon kernel
-//   -> combine kernel;  then one sync to read the counters.  Rare paths after that sync: queries that
-//   overflowed the CTA tier's slab re-run with the worst-case slab; a full record buffer grows and the
-//   batch re-runs.
+// Core of the batched area path; all pointers are device pointers.  Launch sequence (no host synchronisation
+// in between): warp-tier query kernel -> mid-tier -> big-tier (each consumes what the previous tier could not
+// fit) -> polygon kernel -> combine kernel; then one sync to read the counters.  Rare paths after that sync:
+// queries that overflowed the big tier's slab re-run with the worst-case slab; a full record buffer grows and
+// the batch re-runs.  tiny batches skip the warp and mid tiers.
 static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, const float* d_nrm, const float w[3],
-                             float* d_area, uint8_t* d_contact, bool skip_warp_tier) {
+                             float* d_area, uint8_t* d_contact, bool single) {
   uint32_t* d_cnt = (uint32_t*)v->counters.p;
   unsigned long long* d_stats = (unsigned long long*)(d_cnt + CNT_WORDS);
   uint32_t* d_emit = d_cnt + 64;     // [0] polygons [1] items [2] capacity flag
   uint32_t* list0 = (uint32_t*)v->lists.p;
   uint32_t* list1 = list0 + n;
   uint32_t* list2 = list1 + n;
+  uint32_t* list3 = list2 + n;
   int launches = 0;
   for (int attempt = 0; attempt < 8; attempt++) {
     CK(cudaMemsetAsync(d_cnt, 0, 512, v->stream));
@@ -631,7 +671,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     a.out.qinfo = (QInfo*)v->qinfo.p; a.out.counters = d_emit;
     a.out.poly_cap = (uint32_t)std::min<uint64_t>(v->poly_cap, 0xffffffffull); a.out.item_cap = (uint32_t)std::min<uint64_t>(v->item_cap, 0xffffffffull);
     CK(cudaEventRecord(v->ev[0], v->stream));
-    if (!skip_warp_tier) {
+    if (!single) {
       a.list_in = nullptr; a.list_out = list0;
       const int grid = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * 2);
       T0_KERNEL<<<grid, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, v->stream>>>(a);
@@ -639,59 +679,68 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       launches++;
     }
     CK(cudaEventRecord(v->ev[1], v->stream));
-    if (!skip_warp_tier) {
+    if (!single) {
       a.list_in = list0; a.list_out = list1;
-      area_block_kernel<<<v->sm_count, BLK_THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT1, CNT_OVER1, d_cnt + CNT_OVER0);
+      area_block_kernel<MidTier><<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, v->stream>>>(a, v->cfg_mid, 0, CNT_NEXT1, CNT_OVER1, d_cnt + CNT_OVER0, 10);
+      CK(cudaGetLastError());
+      launches++;
+    }
+    CK(cudaEventRecord(v->ev[2], v->stream));
+    if (!single) {
+      a.list_in = list1; a.list_out = list2;
+      area_block_kernel<BigTier><<<v->sm_count, BigTier::THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVER1, 10);
     } else {
-      a.list_in = nullptr; a.list_out = list1;
+      a.list_in = nullptr; a.list_out = list2;
       const int grid = (int)std::min<uint64_t>(n, (uint64_t)v->sm_count);
-      area_block_kernel<<<grid, BLK_THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT1, CNT_OVER1, nullptr);
+      area_block_kernel<BigTier><<<grid, BigTier::THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, nullptr, 10);
     }
     CK(cudaGetLastError());
     launches++;
-    CK(cudaEventRecord(v->ev[2], v->stream));
+    CK(cudaEventRecord(v->ev[3], v->stream));
     poly_eval_kernel<<<v->sm_count * 8, 256, 0, v->stream>>>(a.out.polys, a.out.geom, (float*)v->vals.p, d_emit, 0u, a.out.poly_cap);
     CK(cudaGetLastError());
     launches++;
-    CK(cudaEventRecord(v->ev[3], v->stream));
+    CK(cudaEventRecord(v->ev[4], v->stream));
     combine_kernel<<<(unsigned)std::min<uint64_t>(n, 65535ull * 16), 128, 0, v->stream>>>(a.out.items, (float*)v->vals.p, a.out.qinfo, nullptr, nullptr, (uint32_t)n, d_area, d_contact);
     CK(cudaGetLastError());
     launches++;
-    CK(cudaEventRecord(v->ev[4], v->stream));
+    CK(cudaEventRecord(v->ev[5], v->stream));
     CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, v->stream));
     CK(cudaStreamSynchronize(v->stream));
     CK(cudaEventElapsedTime(&v->timing[0], v->ev[0], v->ev[1]));
     CK(cudaEventElapsedTime(&v->timing[1], v->ev[1], v->ev[2]));
-    CK(cudaEventElapsedTime(&v->timing[4], v->ev[2], v->ev[3]));
+    CK(cudaEventElapsedTime(&v->timing[2], v->ev[2], v->ev[3]));
     CK(cudaEventElapsedTime(&v->timing[5], v->ev[3], v->ev[4]));
-    v->timing[2] = 0.0f;
-    const uint32_t over0 = v->h_counters[CNT_OVER0], over1 = v->h_counters[CNT_OVER1];
+    CK(cudaEventElapsedTime(&v->timing[6], v->ev[4], v->ev[5]));
+    v->timing[3] = 0.0f;
+    const uint32_t over0 = v->h_counters[CNT_OVER0], over1 = v->h_counters[CNT_OVER1], over2 = v->h_counters[CNT_OVER2];
     const uint32_t* he = v->h_counters + 64;
-    uint32_t over2 = 0;
+    uint32_t over3 = 0;
     bool capacity = he[2] != 0;
     uint32_t polys_used = he[0];
-    if (!capacity && over1 > 0) {
-      // worst-case slab, one CTA, only for the queries the CTA tier could not fit
+    if (!capacity && over2 > 0) {
+      // worst-case slab, one CTA, only for the queries the big tier could not fit
       RET(ensure_worst_case_slab(v));
-      a.list_in = list1; a.list_out = list2;
+      a.list_in = list2; a.list_out = list3;
       CK(cudaEventRecord(v->ev[0], v->stream));
-      area_block_kernel<<<1, BLK_THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg2, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVER1);
+      area_block_kernel<BigTier><<<1, BigTier::THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg2, block_smem_bits_words(v), CNT_NEXT3, CNT_OVER3, d_cnt + CNT_OVER2, 10);
       CK(cudaGetLastError());
       CK(cudaEventRecord(v->ev[1], v->stream));
       poly_eval_kernel<<<v->sm_count * 8, 256, 0, v->stream>>>(a.out.polys, a.out.geom, (float*)v->vals.p, d_emit, polys_used, a.out.poly_cap);
-      combine_kernel<<<1024, 128, 0, v->stream>>>(a.out.items, (float*)v->vals.p, a.out.qinfo, list1, d_cnt + CNT_OVER1, (uint32_t)n, d_area, d_contact);
+      combine_kernel<<<1024, 128, 0, v->stream>>>(a.out.items, (float*)v->vals.p, a.out.qinfo, list2, d_cnt + CNT_OVER2, (uint32_t)n, d_area, d_contact);
       CK(cudaGetLastError());
       launches += 3;
       CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, v->stream));
       CK(cudaStreamSynchronize(v->stream));
-      CK(cudaEventElapsedTime(&v->timing[2], v->ev[0], v->ev[1]));
-      over2 = v->h_counters[CNT_OVER2];
+      CK(cudaEventElapsedTime(&v->timing[3], v->ev[0], v->ev[1]));
+      over3 = v->h_counters[CNT_OVER3];
       capacity = he[2] != 0;
       polys_used = he[0];
     }
     const unsigned long long* hs = (const unsigned long long*)(v->h_counters + CNT_WORDS);
     v->stats[0] = hs[0]; v->stats[1] = hs[1]; v->stats[2] = hs[2] * 1024ull;
     v->stats[3] = over0; v->stats[4] = over1; v->stats[5] = (uint64_t)launches; v->stats[6] = over2; v->stats[7] = polys_used;
+    v->stats[8] = over3;
     for (int i = 0; i < 12; i++) v->prof[i] = hs[4 + i];
     if (capacity) {
       // a record buffer filled up: double it and run the batch again
@@ -702,7 +751,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       RET(v->items.ensure(v->item_cap * sizeof(ItemRec) + 64));
       continue;
     }
-    if (over2 > 0) return fail(XS3D_ERR_CAPACITY, "a query exceeded the worst-case working set");
+    if (over3 > 0) return fail(XS3D_ERR_CAPACITY, "a query exceeded the worst-case working set");
     return XS3D_OK;
   }
   return fail(XS3D_ERR_CAPACITY, "record buffers kept overflowing");
@@ -739,15 +788,15 @@ extern "C" int xs3d_area_batch(xs3d_volume* v, uint64_t n, const float* pos, con
   return XS3D_OK;
 }
 
-extern "C" int xs3d_volume_stats(xs3d_volume* v, uint64_t stats[8]) {
+extern "C" int xs3d_volume_stats(xs3d_volume* v, uint64_t stats[10]) {
   if (!v) return fail(XS3D_ERR_ARG, "null volume");
-  for (int i = 0; i < 8; i++) stats[i] = v->stats[i];
+  for (int i = 0; i < 10; i++) stats[i] = v->stats[i];
   return XS3D_OK;
 }
 
-extern "C" int xs3d_volume_timing(xs3d_volume* v, float ms[6]) {
+extern "C" int xs3d_volume_timing(xs3d_volume* v, float ms[8]) {
   if (!v) return fail(XS3D_ERR_ARG, "null volume");
-  for (int i = 0; i < 6; i++) ms[i] = v->timing[i];
+  for (int i = 0; i < 8; i++) ms[i] = v->timing[i];
   return XS3D_OK;
 }
 

@@ -42,12 +42,24 @@ struct VolView {
   int hx, hy, hz;   // blocks = ceil(s/2)
 };
 
-XS_HD uint32_t cube_at(const VolView& v, int bx, int by, int bz) {
+// block index arithmetic is 32-bit: volumes are limited to < 2^32 blocks (checked at xs3d_volume_create)
+XS_HD uint32_t cube_index(const VolView& v, int bx, int by, int bz) {
+  return (uint32_t)bx + (uint32_t)v.hx * ((uint32_t)by + (uint32_t)v.hy * (uint32_t)bz);
+}
+XS_HD uint32_t cube_load(const VolView& v, uint32_t idx) {
 #ifdef __CUDA_ARCH__
-  return __ldg(v.cubes + ((size_t)bx + (size_t)v.hx * ((size_t)by + (size_t)v.hy * (size_t)bz)));
+  return __ldg(v.cubes + idx);
 #else
-  return v.cubes[(size_t)bx + (size_t)v.hx * ((size_t)by + (size_t)v.hy * (size_t)bz)];
+  return v.cubes[idx];
 #endif
+}
+XS_HD uint32_t cube_at(const VolView& v, int bx, int by, int bz) { return cube_load(v, cube_index(v, bx, by, bz)); }
+// k = (ox+1) + 3(oy+1) + 9(oz+1)  ->  offsets, without integer division
+XS_HD void decode_k(int k, int& ox, int& oy, int& oz) {
+  const int z = (k * 57) >> 9;          // k / 9 for k < 27
+  const int rem = k - 9 * z;
+  const int y = (rem * 11) >> 5;        // rem / 3 for rem < 9
+  ox = rem - 3 * y - 1; oy = y - 1; oz = z - 1;
 }
 XS_HD bool vox_fg(const VolView& v, int x, int y, int z) {
   const uint32_t c = cube_at(v, x >> 1, y >> 1, z >> 1);
@@ -125,6 +137,7 @@ struct WarpGroup {
   __device__ int warp() const { return 0; }
   __device__ int nwarps() const { return 1; }
   __device__ void sync() const { __syncwarp(); }
+  __device__ void converge() const { __syncwarp(); }
   __device__ uint32_t ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
   __device__ int exscan(int v, int& total) const {
     int inc = v;
@@ -148,6 +161,7 @@ struct BlockGroup {
   __device__ int warp() const { return threadIdx.x >> 5; }
   __device__ int nwarps() const { return blockDim.x >> 5; }
   __device__ void sync() const { __syncthreads(); }
+  __device__ void converge() const { __syncwarp(); }   // re-join the lanes of each warp after divergent per-lane loops
   __device__ uint32_t ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
   __device__ int exscan(int v, int& total) const {
     const int l = lane(), w = warp(), nw = nwarps();
@@ -189,6 +203,7 @@ struct HostGroup {
   int warp() const { return 0; }
   int nwarps() const { return 1; }
   void sync() const {}
+  void converge() const {}
   int exscan(int v, int& total) const { total = v; return 0; }
   uint32_t or_reduce(uint32_t v) const { return v; }
 };
@@ -294,7 +309,7 @@ struct PackedHash {
       uint32_t old = slot[h];
       if (old == XS_HEMPTY) old = atomic_cas_u32(&slot[h], XS_HEMPTY, word);
       if (old == XS_HEMPTY) return true;
-      if ((old >> 9) == t) { atomic_min_u32(&slot[h], word); return true; }
+      if ((old >> 9) == t) { if (old > word) atomic_min_u32(&slot[h], word); return true; }
       h = (h + 1u) & (cap - 1u);
     }
     return false;
@@ -450,22 +465,68 @@ XS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {
 #endif
 }
 
-// Depth-first walk over the bitmap, run by ONE thread.  Neighbour priority is the reverse of the
-// reference's push order (xs3d.hpp:926-950): (+1,+1) (-1,+1) (+1,-1) (-1,-1) (0,+1) (0,-1) (+1,0) (-1,0).
-// A visited cell has its bit cleared, so "set" means foreground-and-unvisited, which only ever
-// decreases: re-examining a cell after a child returns picks exactly the neighbour the reference's
-// explicit stack would pop next.  Returns ST_DONE / ST_NEED_TILE (ctl.req_*) / ST_OVERFLOW.
+// Walk direction table: index = the 3x3 availability neighbourhood (rows v-1, v, v+1, three bits each: u-1,u,u+1);
+// entry = 0xff when no neighbour is available, else (du+1) | (dv+1)<<2 of the FIRST available neighbour in
+// the reference's priority order — the reverse of its push order (xs3d.hpp:926-950):
+// (+1,+1) (-1,+1) (+1,-1) (-1,-1) (0,+1) (0,-1) (+1,0) (-1,0).
+struct DirLut { uint8_t e[512]; };
+constexpr DirLut make_dir_lut() {
+  DirLut t{};
+  const int du[8] = { 1, -1, 1, -1, 0, 0, 1, -1 };
+  const int dv[8] = { 1, 1, -1, -1, 1, -1, 0, 0 };
+  for (int idx = 0; idx < 512; idx++) {
+    int found = 0xff;
+    for (int d = 7; d >= 0; d--) {
+      const int row = dv[d] + 1, col = du[d] + 1;       // row 0 = v-1, row 2 = v+1
+      if ((idx >> (3 * row + col)) & 1) found = (du[d] + 1) | ((dv[d] + 1) << 2);
+    }
+    t.e[idx] = (uint8_t)found;
+  }
+  return t;
+}
+#ifdef __CUDACC__
+__constant__ DirLut g_dir_lut = make_dir_lut();
+#endif
+static const DirLut h_dir_lut = make_dir_lut();
+XS_HD uint32_t dir_lut(uint32_t idx) {
+#ifdef __CUDA_ARCH__
+  return g_dir_lut.e[idx];
+#else
+  return h_dir_lut.e[idx];
+#endif
+}
+
+// Depth-first walk over the bitmap, run by ONE thread.  A visited cell has its bit cleared, so "set" means
+// foreground-and-unvisited, which only ever decreases: re-examining a cell after a child returns picks
+// exactly the neighbour the reference's explicit stack would pop next.  The loop is latency critical (one
+// thread, one dependent chain per step): 32-bit index arithmetic, one table lookup for the direction, the
+// visited bit cleared with a fire-and-forget atomic, spill code out of line.
+// Returns ST_DONE / ST_NEED_TILE (ctl.req_*) / ST_OVERFLOW.
+XS_HD void clear_bit(uint32_t* w, uint32_t bit) {
+#ifdef __CUDA_ARCH__
+  atomicAnd(w, ~bit);
+#else
+  *w &= ~bit;
+#endif
+}
+
 template <class CellT>
 XS_HD int dfs_run(const Arena<CellT>& A, Ctl& ctl) {
   typedef CellPack<CellT> P;
   int n = ctl.n, depth = ctl.depth, lo = ctl.lo, u = ctl.u, v = ctl.v;
-  const int W = A.tx * 32, H = A.ty * 32;
-  const int smask = A.spill ? (A.stack_cap - 1) : 0x7fffffff;   // no ring wrap when the whole stack is resident
+  const unsigned Wm2 = (unsigned)(A.tx * 32 - 2), Hm2 = (unsigned)(A.ty * 32 - 2);
+  const int stride = A.stride, max_n = A.max_n;
+  uint32_t* const bits = A.bits;
+  CellT* const stack = A.stack;
+  CellT* const order = A.order;
+  const bool ring = A.spill != nullptr;
+  const int smask = ring ? (A.stack_cap - 1) : 0x7fffffff;   // no ring wrap when the whole stack is resident
+  const int cap = ring ? A.stack_cap : 0x7fffffff;
   int status;
   for (;;) {
-    // all four tiles under the 3x3 neighbourhood must have been sampled
-    const int ua = (u - 1) >> 5, ub = (u + 1) >> 5, va = (v - 1) >> 5, vb = (v + 1) >> 5;
-    if (ua != ub || va != vb) {
+    // all four tiles under the 3x3 neighbourhood must have been sampled (only cells on a tile border can miss)
+    if ((((u + 1) & 31) < 2) | (((v + 1) & 31) < 2)) {
+      const int ua = (u - 1) >> 5, ub = (u + 1) >> 5, va = (v - 1) >> 5, vb = (v + 1) >> 5;
       int need_x = -1, need_y = 0;
       if (!tile_tested(A, ua, va)) { need_x = ua; need_y = va; }
       else if (!tile_tested(A, ub, va)) { need_x = ub; need_y = va; }
@@ -473,49 +534,41 @@ XS_HD int dfs_run(const Arena<CellT>& A, Ctl& ctl) {
       else if (!tile_tested(A, ub, vb)) { need_x = ub; need_y = vb; }
       if (need_x >= 0) { ctl.req_tx = need_x; ctl.req_ty = need_y; status = ST_NEED_TILE; break; }
     }
-    const int sh = (u - 1) & 31;
-    const uint32_t* rp = A.bits + (size_t)(v - 1) * A.stride + ((u - 1) >> 5);
-    const uint32_t rm = funnel_r(rp[0], rp[1], sh) & 7u;
-    const uint32_t r0 = funnel_r(rp[A.stride], rp[A.stride + 1], sh) & 7u;
-    const uint32_t rq = funnel_r(rp[2 * A.stride], rp[2 * A.stride + 1], sh) & 7u;   // rows v-1, v, v+1
-    // bit d of m <=> neighbour with priority d is available
-    const uint32_t m = ((rq >> 2) & 1u) | ((rq & 1u) << 1) | (((rm >> 2) & 1u) << 2) | ((rm & 1u) << 3) |
-                       (((rq >> 1) & 1u) << 4) | (((rm >> 1) & 1u) << 5) | (((r0 >> 2) & 1u) << 6) | ((r0 & 1u) << 7);
-    if (m == 0u) {
+    const int um1 = u - 1;
+    const int sh = um1 & 31;
+    const uint32_t* rp = bits + ((v - 1) * stride + (um1 >> 5));
+    const uint32_t a0 = rp[0], a1 = rp[1], b0 = rp[stride], b1 = rp[stride + 1], c0 = rp[2 * stride], c1 = rp[2 * stride + 1];
+    const uint32_t idx = (funnel_r(a0, a1, sh) & 7u) | ((funnel_r(b0, b1, sh) & 7u) << 3) | ((funnel_r(c0, c1, sh) & 7u) << 6);
+    const uint32_t e = dir_lut(idx);
+    if (e == 0xffu) {
       // backtrack
       depth--;
       if (depth == 0) { status = ST_DONE; break; }
       if (depth - 1 < lo) {
-        // refill the lower half of the ring from the global spill area
+        // (ring only) refill the lower half of the ring from the global spill area
         int nlo = lo - A.stack_cap / 2;
         if (nlo < 0) nlo = 0;
-        for (int d = nlo; d < lo; d++) A.stack[d & smask] = A.spill[d];
+#pragma unroll 1
+        for (int d = nlo; d < lo; d++) stack[d & smask] = A.spill[d];
         lo = nlo;
       }
-      const CellT p = A.stack[(depth - 1) & smask];
+      const CellT p = stack[(depth - 1) & smask];
       u = P::u(p); v = P::v(p);
       continue;
     }
-#ifdef __CUDA_ARCH__
-    const int d = __ffs(m) - 1;
-#else
-    const int d = __builtin_ffs(m) - 1;
-#endif
-    // du+1 / dv+1 packed two bits per direction
-    const int du = (int)((0x2522u >> (2 * d)) & 3u) - 1;   // d:0..7 -> +1,-1,+1,-1,0,0,+1,-1
-    const int dv = (int)((0x520au >> (2 * d)) & 3u) - 1;   // d:0..7 -> +1,+1,-1,-1,+1,-1,0,0
-    u += du; v += dv;
-    A.bits[(size_t)v * A.stride + (u >> 5)] &= ~(1u << (u & 31));
-    if (u == 0 || v == 0 || u == W - 1 || v == H - 1 || n >= A.max_n) { status = ST_OVERFLOW; break; }
+    u += (int)(e & 3u) - 1; v += (int)(e >> 2) - 1;
+    bits[v * stride + (u >> 5)] &= ~(1u << (u & 31));
+    if (((unsigned)(u - 1) >= Wm2) | ((unsigned)(v - 1) >= Hm2) | (n >= max_n)) { status = ST_OVERFLOW; break; }
     const CellT p = P::pack(u, v);
-    A.order[n++] = p;
-    if (depth - lo == A.stack_cap) {
-      // ring full: spill the lower half
+    order[n++] = p;
+    if (depth - lo == cap) {
+      // (ring only) ring full: spill the lower half
       const int nlo = lo + A.stack_cap / 2;
-      for (int dd = lo; dd < nlo; dd++) A.spill[dd] = A.stack[dd & smask];
+#pragma unroll 1
+      for (int dd = lo; dd < nlo; dd++) A.spill[dd] = stack[dd & smask];
       lo = nlo;
     }
-    A.stack[depth & smask] = p;
+    stack[depth & smask] = p;
     depth++;
   }
   ctl.n = n; ctl.depth = depth; ctl.lo = lo; ctl.u = u; ctl.v = v;
@@ -592,42 +645,6 @@ XS_HD Sample sample_at(const PlaneCtx& c, const Arena<CellT>& A, int r, V3* roun
   return s;
 }
 
-// Step 3: contact bits (xs3d.hpp:909-914) and first-touch claims (xs3d.hpp:689-708).
-// The owner of a block is the claimer with the smallest DFS rank; since a sample probes each block at
-// most once, the rank alone identifies the (rank,k) pair the reference would have visited first.
-template <class G, class CellT, class H>
-XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, const H& hash, Ctl& ctl) {
-  const int n = ctl.n;
-  hash.clear(g);
-  g.sync();
-  uint32_t ct = 0u;
-  bool ovf = false;
-  for (int r = g.tid(); r < n; r += g.size()) {
-    V3 cur;
-    const Sample s = sample_at(c, A, r, &cur);
-    ct |= (uint32_t)(cur.x < 1.0f) | ((uint32_t)(cur.x >= c.hi[0]) << 1) | ((uint32_t)(cur.y < 1.0f) << 2) |
-          ((uint32_t)(cur.y >= c.hi[1]) << 3) | ((uint32_t)(cur.z < 1.0f) << 4) | ((uint32_t)(cur.z >= c.hi[2]) << 5);
-    const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
-    const int pb = (s.rx & 1) | ((s.ry & 1) << 1) | ((s.rz & 1) << 2);
-    uint32_t cmask = 0u;
-    for (int k = 0; k < 27; k++) {
-      if (c.axis_aligned && k != 13) continue;                       // xs3d.hpp:677-685
-      const int ox = k % 3 - 1, oy = (k / 3) % 3 - 1, oz = k / 9 - 1;
-      const int x = s.rx + 2 * ox, y = s.ry + 2 * oy, z = s.rz + 2 * oz;
-      if (x < 0 || y < 0 || z < 0 || x >= vol.sx || y >= vol.sy || z >= vol.sz) continue;   // :665-671
-      const uint32_t cb = cube_at(vol, bx + ox, by + oy, bz + oz);
-      if (!((cb >> pb) & 1u)) continue;                              // :704 probe voxel is background
-      cmask |= 1u << k;
-      if (!hash.claim(bx + ox, by + oy, bz + oz, (uint32_t)r)) ovf = true;
-    }
-    A.mask[r] = cmask;
-  }
-  ct = g.or_reduce(ct);
-  if (g.tid() == 0) ctl.contact = ct;
-  if (ovf) ctl.overflow = 1;
-  g.sync();
-}
-
 XS_HD int popc8(uint32_t x) {
 #ifdef __CUDA_ARCH__
   return __popc(x & 0xffu);
@@ -642,6 +659,69 @@ XS_HD int ffs32(uint32_t x) {
   return __builtin_ffs(x);
 #endif
 }
+// Step 3: contact bits (xs3d.hpp:909-914) and first-touch claims (xs3d.hpp:689-708).
+// The owner of a block is the claimer with the smallest DFS rank; since a sample probes each block at
+// most once, the rank alone identifies the (rank,k) pair the reference would have visited first.
+template <class G, class CellT, class H>
+XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, const H& hash, Ctl& ctl) {
+  const int n = ctl.n;
+  hash.clear(g);
+  g.sync();
+  uint32_t ct = 0u;
+  bool ovf = false;
+  const int hx = vol.hx, hxy = vol.hx * vol.hy;
+  // uniform trip count + an explicit reconvergence point per chunk: the per-lane claim loop below has a
+  // data-dependent length, and without the re-join the lanes of a warp drift apart for the rest of the phase
+  for (int r0 = 0; r0 < n; r0 += g.size()) {
+    const int r = r0 + g.tid();
+    if (r < n) {
+      V3 cur;
+      const Sample s = sample_at(c, A, r, &cur);
+      ct |= (uint32_t)(cur.x < 1.0f) | ((uint32_t)(cur.x >= c.hi[0]) << 1) | ((uint32_t)(cur.y < 1.0f) << 2) |
+            ((uint32_t)(cur.y >= c.hi[1]) << 3) | ((uint32_t)(cur.z < 1.0f) << 4) | ((uint32_t)(cur.z >= c.hi[2]) << 5);
+      const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
+      const int pb = (s.rx & 1) | ((s.ry & 1) << 1) | ((s.rz & 1) << 2);
+      const uint32_t base = cube_index(vol, bx, by, bz);
+      uint32_t cmask = 0u;
+      if (c.axis_aligned) {                                              // xs3d.hpp:677-685: only the sample's own block
+        cmask = ((cube_load(vol, base) >> pb) & 1u) << 13;
+      } else {
+        // probe voxel r + 2o must be inside the volume (xs3d.hpp:665-671) and set (:704).  Branch-free: an
+        // out-of-volume probe reads the sample's own block instead and is masked off.
+        const uint32_t okx = (s.rx - 2 >= 0 ? 1u : 0u) | 2u | (s.rx + 2 < vol.sx ? 4u : 0u);
+        const uint32_t oky = (s.ry - 2 >= 0 ? 1u : 0u) | 2u | (s.ry + 2 < vol.sy ? 4u : 0u);
+        const uint32_t okz = (s.rz - 2 >= 0 ? 1u : 0u) | 2u | (s.rz + 2 < vol.sz ? 4u : 0u);
+#pragma unroll
+        for (int oz = 0; oz < 3; oz++) {
+#pragma unroll
+          for (int oy = 0; oy < 3; oy++) {
+#pragma unroll
+            for (int ox = 0; ox < 3; ox++) {
+              const uint32_t ok = (okx >> ox) & (oky >> oy) & (okz >> oz) & 1u;
+              const uint32_t off = (uint32_t)((ox - 1) + (oy - 1) * hx + (oz - 1) * hxy);
+              const uint32_t cb = cube_load(vol, base + (ok ? off : 0u));
+              cmask |= ((cb >> pb) & ok) << (ox + 3 * oy + 9 * oz);
+            }
+          }
+        }
+      }
+      A.mask[r] = cmask;
+      while (cmask) {
+        const int k = ffs32(cmask) - 1;
+        cmask &= cmask - 1u;
+        int ox, oy, oz;
+        decode_k(k, ox, oy, oz);
+        if (!hash.claim(bx + ox, by + oy, bz + oz, (uint32_t)r)) ovf = true;
+      }
+    }
+    g.converge();
+  }
+  ct = g.or_reduce(ct);
+  if (g.tid() == 0) ctl.contact = ct;
+  if (ovf) ctl.overflow = 1;
+  g.sync();
+}
+
 // polygons an item needs (xs3d.hpp:420-437): >=5 voxels set: the block polygon + one per ABSENT voxel; else one per present voxel
 XS_HD int item_polys(uint32_t cube) {
   const int pop = popc8(cube);
@@ -656,27 +736,32 @@ XS_D int emit_items(const G& g, const PlaneCtx& c, const VolView& vol, const Are
   const int n = ctl.n;
   // pass 1: which candidates become items; totals
   int my_items = 0, my_polys = 0;
-  for (int r = g.tid(); r < n; r += g.size()) {
-    uint32_t cm = A.mask[r], keep = 0u;
-    if (cm) {
-      const Sample s = sample_at(c, A, r, (V3*)nullptr);
-      const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
-      const uint32_t centre = cube_at(vol, bx, by, bz);
-      while (cm) {
-        const int k = ffs32(cm) - 1;
-        cm &= cm - 1u;
-        const int ox = k % 3 - 1, oy = (k / 3) % 3 - 1, oz = k / 9 - 1;
-        if (hash.owner(bx + ox, by + oy, bz + oz) != (uint32_t)r) continue;         // someone with a smaller rank touched it first
-        const uint32_t cand = cube_at(vol, bx + ox, by + oy, bz + oz);
-        if (!blocks_adjacent(centre, cand, ox, oy, oz)) continue;                    // visited, but contributes nothing
-        const V3 ctr = vadd(mk((float)(2 * (bx + ox)), (float)(2 * (by + oy)), (float)(2 * (bz + oz))), mk(0.5f, 0.5f, 0.5f));
-        if (fabsf(vdot(vsub(ctr, c.g.pos), c.g.n)) > XS_FAR2) continue;             // block value is exactly 0
-        keep |= 1u << k;
-        my_items++;
-        my_polys += item_polys(cand);
+  for (int r0 = 0; r0 < n; r0 += g.size()) {
+    const int r = r0 + g.tid();
+    if (r < n) {
+      uint32_t cm = A.mask[r], keep = 0u;
+      if (cm) {
+        const Sample s = sample_at(c, A, r, (V3*)nullptr);
+        const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
+        const uint32_t centre = cube_at(vol, bx, by, bz);
+        while (cm) {
+          const int k = ffs32(cm) - 1;
+          cm &= cm - 1u;
+          int ox, oy, oz;
+          decode_k(k, ox, oy, oz);
+          if (hash.owner(bx + ox, by + oy, bz + oz) != (uint32_t)r) continue;         // someone with a smaller rank touched it first
+          const uint32_t cand = cube_at(vol, bx + ox, by + oy, bz + oz);
+          if (!blocks_adjacent(centre, cand, ox, oy, oz)) continue;                    // visited, but contributes nothing
+          const V3 ctr = vadd(mk((float)(2 * (bx + ox)), (float)(2 * (by + oy)), (float)(2 * (bz + oz))), mk(0.5f, 0.5f, 0.5f));
+          if (fabsf(vdot(vsub(ctr, c.g.pos), c.g.n)) > XS_FAR2) continue;             // block value is exactly 0
+          keep |= 1u << k;
+          my_items++;
+          my_polys += item_polys(cand);
+        }
       }
+      A.mask[r] = keep;
     }
-    A.mask[r] = keep;
+    g.converge();
   }
   g.sync();
   // reserve the output ranges
@@ -714,7 +799,9 @@ XS_D int emit_items(const G& g, const PlaneCtx& c, const VolView& vol, const Are
         const int k = ffs32(km) - 1;
         km &= km - 1u;
         ni++;
-        np += item_polys(cube_at(vol, bx + k % 3 - 1, by + (k / 3) % 3 - 1, bz + k / 9 - 1));
+        int ox, oy, oz;
+        decode_k(k, ox, oy, oz);
+        np += item_polys(cube_at(vol, bx + ox, by + oy, bz + oz));
       }
     }
     int ti, tp;
@@ -725,7 +812,9 @@ XS_D int emit_items(const G& g, const PlaneCtx& c, const VolView& vol, const Are
     while (km) {
       const int k = ffs32(km) - 1;
       km &= km - 1u;
-      const int cx = bx + k % 3 - 1, cy = by + (k / 3) % 3 - 1, cz = bz + k / 9 - 1;
+      int ox, oy, oz;
+      decode_k(k, ox, oy, oz);
+      const int cx = bx + ox, cy = by + oy, cz = bz + oz;
       const uint32_t cand = cube_at(vol, cx, cy, cz);
       const int pop = popc8(cand);
       const int cnt = item_polys(cand);
@@ -748,6 +837,7 @@ XS_D int emit_items(const G& g, const PlaneCtx& c, const VolView& vol, const Are
       }
     }
     ibase += ti; pbase += tp;
+    g.converge();
   }
   return Q_OK;
 }

@@ -162,17 +162,17 @@ class Volume:
     _abi.check(self._lib.xs3d_volume_mark_loaded(self._h))
 
   def stats(self):
-    s = (C.c_uint64 * 8)()
+    s = (C.c_uint64 * 10)()
     _abi.check(self._lib.xs3d_volume_stats(self._h, s))
-    return {"samples": s[0], "blocks": s[1], "cells_tested": s[2], "escalated_cta": s[3],
-            "escalated_worst_case": s[4], "launches": s[5], "failed": s[6], "polygons": s[7]}
+    return {"samples": s[0], "blocks": s[1], "cells_tested": s[2], "escalated_mid": s[3], "escalated_big": s[4],
+            "launches": s[5], "escalated_worst_case": s[6], "polygons": s[7], "failed": s[8]}
 
   def timing(self):
     """CUDA-event kernel durations (ms) of the last call: warp tier, CTA tier, worst-case tier, ingest."""
-    t = (C.c_float * 6)()
+    t = (C.c_float * 8)()
     _abi.check(self._lib.xs3d_volume_timing(self._h, t))
-    return {"warp_tier_ms": t[0], "cta_tier_ms": t[1], "worst_case_ms": t[2], "ingest_ms": t[3],
-            "polygon_ms": t[4], "combine_ms": t[5]}
+    return {"warp_tier_ms": t[0], "mid_tier_ms": t[1], "big_tier_ms": t[2], "worst_case_ms": t[3], "ingest_ms": t[4],
+            "polygon_ms": t[5], "combine_ms": t[6]}
 
   def set_stream(self, cuda_stream):
     """Launch on the given cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""

@@ -60,17 +60,17 @@ int xs3d_area_batch(xs3d_volume* vol, uint64_t n, const float* pos, const float*
                     const float anisotropy[3], int mem, float* area, uint8_t* contact);
 /* Counters of the last xs3d_area_batch on this volume:
  * stats[0] lattice samples, [1] contributing blocks (items), [2] lattice cells tested, [3] queries escalated
- * warp->CTA tier, [4] queries escalated to the worst-case slab, [5] kernel launches of the call,
- * [6] queries that failed even there, [7] polygon records evaluated. */
-int xs3d_volume_stats(xs3d_volume* vol, uint64_t stats[8]);
+ * warp->mid tier, [4] mid->big tier, [5] kernel launches of the call, [6] big->worst-case slab,
+ * [7] polygon records evaluated, [8] queries that failed even with the worst-case slab, [9] reserved. */
+int xs3d_volume_stats(xs3d_volume* vol, uint64_t stats[10]);
 /* SM-clock cycles thread 0 of each query group spent per phase in the last xs3d_area_batch, summed over
- * queries: prof[0..5] warp tier, prof[6..11] CTA tier; phases: [0] lattice flood (tiles + walk), [1] claims,
+ * queries: prof[0..5] warp tier, prof[6..11] CTA tiers (mid + big); phases: [0] lattice flood (tiles + walk), [1] claims,
  * [2] ownership + record emission, [3] [4] unused, [5] walk only. */
 int xs3d_volume_profile(xs3d_volume* vol, uint64_t prof[12]);
 /* CUDA-event durations (ms, measured on the launching stream) of the kernels of the last call on this volume:
- * ms[0] warp-tier query kernel, ms[1] CTA-tier query kernel, ms[2] worst-case query kernel,
- * ms[3] ingest kernel (last xs3d_volume_load), ms[4] polygon kernel, ms[5] combine kernel. */
-int xs3d_volume_timing(xs3d_volume* vol, float ms[6]);
+ * ms[0] warp-tier, ms[1] mid-tier, ms[2] big-tier, ms[3] worst-case query kernels, ms[4] ingest kernel (last
+ * xs3d_volume_load), ms[5] polygon kernel, ms[6] combine kernel, ms[7] reserved. */
+int xs3d_volume_timing(xs3d_volume* vol, float ms[8]);
 /* Launch on the caller's stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) instead of the
  * volume's own, so the caller's CUDA events bracket the work.  The stream must outlive the volume. */
 int xs3d_volume_set_stream(xs3d_volume* vol, void* cuda_stream);

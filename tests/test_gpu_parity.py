@@ -168,7 +168,7 @@ def test_neurite512_sweep_parity_and_properties(xs, oracle, neurite512):
   assert np.array_equal(bits(a[perm]), bits(a3)) and np.array_equal(c[perm], c3)
   for k, i in enumerate(range(0, 10000, 500)):
     assert bits(singles[k][0]) == bits(a[i]) and singles[k][1] == c[i]
-  assert (a > 0).all() and st["escalated_cta"] > 0
+  assert (a > 0).all() and st["escalated_mid"] > 0
   with xs.Volume(np.ascontiguousarray(vol)) as VC:
     a4 = VC.cross_sectional_area_batch(qp[:2000], qn[:2000], w)
   assert np.array_equal(bits(a4), bits(a[:2000]))

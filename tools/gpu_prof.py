@@ -20,8 +20,8 @@ for tier in p:
   tot = sum(p[tier][k] for k in ("flood", "claims", "emit"))
   print(tier, {k: "%.1f%%" % (100.0 * v / max(tot, 1)) for k, v in p[tier].items()}, "total Mcycles %.1f" % (tot / 1e6))
 st = V.stats()
-nq0 = NQ - st["escalated_cta"]
-print("warp tier: mean cycles/query %.0f ; cta tier: mean cycles/query %.0f" % (sum(list(p["warp_tier"].values())[:3]) / max(nq0, 1), sum(list(p["cta_tier"].values())[:3]) / max(st["escalated_cta"], 1)))
+nq0 = NQ - st["escalated_mid"]
+print("warp tier: mean cycles/query %.0f ; cta tier: mean cycles/query %.0f" % (sum(list(p["warp_tier"].values())[:3]) / max(nq0, 1), sum(list(p["cta_tier"].values())[:3]) / max(st["escalated_mid"], 1)))
 print(V.timing())
 t = time.time(); V.load(vol); print("upload+ingest %.4fs" % (time.time() - t))
 dv = torch.from_numpy(vol.view(np.uint8).ravel(order="K")).cuda()
