@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) area_warp_kernel(BatchArgs a) {
   A.order = reinterpret_cast<uint16_t*>(base + L::O_ORDER); A.max_n = MAXN;
   A.stack = reinterpret_cast<uint16_t*>(base + L::O_STACK); A.stack_cap = MAXN; A.spill = nullptr;
   A.mask = A.bits;
+  A.cells = nullptr; A.wlog = 0;
   PackedHash H;
   H.slot = base + L::O_HASH; H.cap = HCAP; H.max_probe = 48;
   int lg = 0;
@@ -246,7 +247,6 @@ struct BlockTier {
   static constexpr int WIN_WORDS = WIN_TILES * 32 * (WIN_TILES + 1);
   static constexpr int FIXED_WORDS = O_BITS;       // + bitmap words
 };
-using MidTier = BlockTier<128, 2048, 17, 16, 4>;   // 544 x 544 cells, ~47 KB -> 4 CTAs per SM
 using BigTier = BlockTier<512, 16384, 0, 1024, 1>;
 constexpr int BLK_THREADS = BigTier::THREADS;
 static_assert(sizeof(Ctl) <= 40 * 4, "ctl slot");
@@ -265,6 +265,7 @@ __device__ __forceinline__ bool block_arena(Arena<uint32_t>& A, WideHash& H, con
   uint32_t* g_bits = p; p += s.bits_words;
   uint32_t* g_tested = p;
   A.max_n = s.max_n;
+  A.cells = nullptr; A.wlog = 0;
   H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
   H.hx = vol.hx; H.hy = vol.hy;
   int lg = 0;
@@ -321,6 +322,71 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_BLOCKS) area_block_kernel(B
     WideHash H;
     int st = Q_OVERFLOW;
     if (block_arena<T>(A, H, s, smem, smem_bits_words, c, a.vol)) st = run_area_emit(g, c, a.vol, A, H, ctl, q, a.out);
+    if (threadIdx.x == 0) finish_query(a, ctl, q, st, cnt_over, stats_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// MID tier: one 256-thread CTA per query, byte-per-cell 256x256 window in shared memory (64 KB) so the
+// single-thread walk has a short dependent chain per step.  Takes the few per cent of sweep queries that
+// do not fit a warp; two CTAs per SM so they all run in one wave.
+// ------------------------------------------------------------------------------------------------
+struct MidTier {
+  static constexpr int THREADS = 256;
+  static constexpr int WLOG = 8;                   // 256 x 256 cells; uint16 cell index u | v<<8
+  static constexpr int RING = 4096;                // DFS stack ring entries (uint16) in shared memory
+  static constexpr int O_CTL = 64;
+  static constexpr int O_RING = O_CTL + 48;
+  static constexpr int O_CELLS = O_RING + RING / 2;
+  static constexpr int WORDS = O_CELLS + ((1 << (2 * WLOG)) >> 2);
+};
+
+__host__ __device__ inline size_t mid_slab_bytes(const SlabCfg& s) {
+  size_t bytes = (size_t)s.max_n * (2 + 4 + 2) + (size_t)s.hcap_max * 8;
+  return ((bytes + 255) / 256) * 256;
+}
+
+__global__ void __launch_bounds__(MidTier::THREADS, 2) area_mid_kernel(BatchArgs a, SlabCfg s, int cnt_next, int cnt_over, const uint32_t* count_ptr, int stats_base) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  BlockGroup g(reinterpret_cast<int*>(smem));
+  Ctl& ctl = *reinterpret_cast<Ctl*>(smem + MidTier::O_CTL);
+  int* next = reinterpret_cast<int*>(smem + MidTier::O_CTL + 42);
+  const V3 w = mk(a.wx, a.wy, a.wz);
+  const uint32_t count = count_ptr ? *count_ptr : a.nq;
+  // per-CTA slab in HBM: order (u16), kept masks (u32), stack spill (u16), first-touch table
+  char* slab = s.base + (size_t)blockIdx.x * s.stride;
+  Arena<uint16_t> A;
+  A.mask = reinterpret_cast<uint32_t*>(slab);
+  A.order = reinterpret_cast<uint16_t*>(slab + (size_t)s.max_n * 4);
+  A.spill = reinterpret_cast<uint16_t*>(slab + (size_t)s.max_n * 6);
+  WideHash H;
+  H.htag = reinterpret_cast<uint32_t*>(slab + (size_t)s.max_n * 8);
+  H.hkey = H.htag + s.hcap_max;
+  A.max_n = s.max_n;
+  A.stack = reinterpret_cast<uint16_t*>(smem + MidTier::O_RING); A.stack_cap = MidTier::RING;
+  A.cells = reinterpret_cast<uint8_t*>(smem + MidTier::O_CELLS); A.wlog = MidTier::WLOG;
+  A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = (1 << MidTier::WLOG) / 32; A.stride = 0; A.halo = 1;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) *next = (int)atomicAdd(&a.counters[cnt_next], 1u);
+    __syncthreads();
+    const uint32_t i = (uint32_t)*next;
+    if (i >= count) break;
+    const uint32_t q = a.list_in ? a.list_in[i] : i;
+    PlaneCtx c;
+    const V3 p = mk(__ldg(a.pos + 3 * q), __ldg(a.pos + 3 * q + 1), __ldg(a.pos + 3 * q + 2));
+    const V3 n = mk(__ldg(a.nrm + 3 * q), __ldg(a.nrm + 3 * q + 1), __ldg(a.nrm + 3 * q + 2));
+    if (!plane_init(c, a.vol, p, n, w)) {
+      if (threadIdx.x == 0) zero_query(a, q);
+      continue;
+    }
+    A.ox = A.oy = c.c - (1 << (MidTier::WLOG - 1));
+    H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
+    H.hx = a.vol.hx; H.hy = a.vol.hy;
+    int lg = 0;
+    while ((1u << lg) < s.hcap_max) lg++;
+    H.shift = 32 - lg;
+    const int st = run_area_emit(g, c, a.vol, A, H, ctl, q, a.out);
     if (threadIdx.x == 0) finish_query(a, ctl, q, st, cnt_over, stats_base);
   }
 }
@@ -459,7 +525,7 @@ static VolView view_of(const xs3d_volume* v) {
 
 static int block_smem_bytes(const xs3d_volume* v) { return v->smem_optin; }
 static int block_smem_bits_words(const xs3d_volume* v) { return v->smem_optin / 4 - BigTier::FIXED_WORDS; }
-constexpr int MID_SMEM_BYTES = (MidTier::FIXED_WORDS + MidTier::WIN_WORDS) * 4;
+constexpr int MID_SMEM_BYTES = MidTier::WORDS * 4;
 
 static int configure_kernels(xs3d_volume* v) {
   if (v->kernels_configured) return XS3D_OK;
@@ -467,7 +533,7 @@ static int configure_kernels(xs3d_volume* v) {
   if (t0_bytes > v->smem_optin) return fail(XS3D_ERR_UNSUPPORTED, "device shared memory too small for the warp tier");
   CK(cudaFuncSetAttribute(T0_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, t0_bytes));
   CK(cudaFuncSetAttribute(area_block_kernel<BigTier>, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
-  CK(cudaFuncSetAttribute(area_block_kernel<MidTier>, cudaFuncAttributeMaxDynamicSharedMemorySize, MID_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(area_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MID_SMEM_BYTES));
   CK(cudaFuncSetAttribute(section_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
   v->kernels_configured = true;
   return XS3D_OK;
@@ -612,8 +678,8 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
   if (!v->slab_mid.p) {
     SlabCfg m{};
     m.max_n = 1 << 14; m.hcap_max = 1u << 17; m.bits_words = 0; m.tested_words = 0; m.hash_factor = 8; m.max_probe = 256;
-    m.stride = slab_bytes(m);
-    v->mid_ctas = v->sm_count * MidTier::MIN_BLOCKS;
+    m.stride = mid_slab_bytes(m);
+    v->mid_ctas = v->sm_count * 2;
     RET(v->slab_mid.ensure(m.stride * (size_t)v->mid_ctas));
     m.base = (char*)v->slab_mid.p;
     v->cfg_mid = m;
@@ -681,7 +747,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     CK(cudaEventRecord(v->ev[1], v->stream));
     if (!single) {
       a.list_in = list0; a.list_out = list1;
-      area_block_kernel<MidTier><<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, v->stream>>>(a, v->cfg_mid, 0, CNT_NEXT1, CNT_OVER1, d_cnt + CNT_OVER0, 10);
+      area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, v->stream>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, d_cnt + CNT_OVER0, 10);
       CK(cudaGetLastError());
       launches++;
     }

@@ -380,6 +380,10 @@ struct Arena {
   int stack_cap;                // power of two when `spill` is set, else >= max_n
   CellT* spill;                 // global backing store for the ring, or null when stack_cap >= max_n
   uint32_t* mask;               // per-sample 27-bit candidate / kept-item masks (warp tier: aliases `bits`)
+  // byte-per-cell variant of the window (mid tier): (1<<wlog)^2 cells, local cell index u | v<<wlog.
+  // States: 0 background or visited, 1 foreground-unvisited, 2 not sampled yet, 3 foreground on the guard ring.
+  uint8_t* cells;               // null: use the bitmap
+  int wlog;
 };
 
 struct Ctl {          // lives in shared memory (one per group)
@@ -465,6 +469,20 @@ XS_HD uint32_t funnel_r(uint32_t lo, uint32_t hi, int sh) {
 #endif
 }
 
+XS_HD int popc8(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return __popc(x & 0xffu);
+#else
+  return __builtin_popcount(x & 0xffu);
+#endif
+}
+XS_HD int ffs32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return __ffs(x);
+#else
+  return __builtin_ffs(x);
+#endif
+}
 // Walk direction table: index = the 3x3 availability neighbourhood (rows v-1, v, v+1, three bits each: u-1,u,u+1);
 // entry = 0xff when no neighbour is available, else (du+1) | (dv+1)<<2 of the FIRST available neighbour in
 // the reference's priority order — the reverse of its push order (xs3d.hpp:926-950):
@@ -631,6 +649,178 @@ XS_D int flood_component(const G& g, const PlaneCtx& c, const VolView& vol, cons
   return Q_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Byte-per-cell flood (mid tier).  Same semantics as the bitmap flood above; the representation trades
+// 8x the shared memory for a much shorter dependent chain per walk step: one address add, eight
+// independent byte loads, a find-first, one byte store — and the "not sampled yet" and "guard ring"
+// conditions ride along in the cell state instead of needing coordinate checks.
+// ------------------------------------------------------------------------------------------------
+template <class G, class CellT>
+XS_D void test_tile_bytes(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, int tx, int ty) {
+  // one 32x32 tile: a warp per row, a lane per cell
+  const int W = 1 << A.wlog;
+  for (int row = g.warp(); row < 32; row += g.nwarps()) {
+    const int v = ty * 32 + row;
+#ifdef __CUDA_ARCH__
+    {
+      const int u = tx * 32 + g.lane();
+      const bool f = cell_fg(c, vol, A.ox + u, A.oy + v);
+      const bool ring = (u == 0) | (v == 0) | (u == W - 1) | (v == W - 1);
+      A.cells[(v << A.wlog) + u] = (uint8_t)(f ? (ring ? 3 : 1) : 0);
+    }
+#else
+    for (int l = 0; l < 32; l++) {
+      const int u = tx * 32 + l;
+      const bool f = cell_fg(c, vol, A.ox + u, A.oy + v);
+      const bool ring = (u == 0) | (v == 0) | (u == W - 1) | (v == W - 1);
+      A.cells[(v << A.wlog) + u] = (uint8_t)(f ? (ring ? 3 : 1) : 0);
+    }
+#endif
+  }
+}
+
+// Returns ST_DONE / ST_NEED_TILE (ctl.req_*) / ST_OVERFLOW.  ctl.u holds the current cell index.
+template <class CellT>
+XS_HD int dfs_run_bytes(const Arena<CellT>& A, Ctl& ctl) {
+  int n = ctl.n, depth = ctl.depth, lo = ctl.lo, ci = ctl.u;
+  const int P = 1 << A.wlog;
+  const int max_n = A.max_n;
+  uint8_t* const cells = A.cells;
+  CellT* const stack = A.stack;
+  CellT* const order = A.order;
+  const bool ring = A.spill != nullptr;
+  const int smask = ring ? (A.stack_cap - 1) : 0x7fffffff;
+  const int cap = ring ? A.stack_cap : 0x7fffffff;
+  int status;
+  for (;;) {
+    const uint8_t* q = cells + ci;
+    // neighbours in the reference's priority order: (+1,+1) (-1,+1) (+1,-1) (-1,-1) (0,+1) (0,-1) (+1,0) (-1,0)
+    const uint32_t b0 = q[P + 1], b1 = q[P - 1], b2 = q[1 - P], b3 = q[-P - 1], b4 = q[P], b5 = q[-P], b6 = q[1], b7 = q[-1];
+    const uint32_t any = b0 | b1 | b2 | b3 | b4 | b5 | b6 | b7;
+    if (any & 2u) {
+      // a neighbour is either not sampled yet (2) or foreground on the guard ring (3)
+      const int off[8] = { P + 1, P - 1, 1 - P, -P - 1, P, -P, 1, -1 };
+      const uint32_t bb[8] = { b0, b1, b2, b3, b4, b5, b6, b7 };
+      int need = -1;
+      bool over = false;
+      for (int d = 0; d < 8; d++) {
+        if (bb[d] == 3u) over = true;
+        else if (bb[d] == 2u && need < 0) need = ci + off[d];
+      }
+      if (over) { status = ST_OVERFLOW; break; }
+      ctl.req_tx = (need & (P - 1)) >> 5; ctl.req_ty = (need >> A.wlog) >> 5;
+      status = ST_NEED_TILE;
+      break;
+    }
+    const uint32_t m = b0 | (b1 << 1) | (b2 << 2) | (b3 << 3) | (b4 << 4) | (b5 << 5) | (b6 << 6) | (b7 << 7);
+    if (m == 0u) {
+      depth--;
+      if (depth == 0) { status = ST_DONE; break; }
+      if (depth - 1 < lo) {
+        int nlo = lo - A.stack_cap / 2;
+        if (nlo < 0) nlo = 0;
+#pragma unroll 1
+        for (int d = nlo; d < lo; d++) stack[d & smask] = A.spill[d];
+        lo = nlo;
+      }
+      ci = (int)stack[(depth - 1) & smask];
+      continue;
+    }
+    const int d = ffs32(m) - 1;
+    const int du = (int)((0x2522u >> (2 * d)) & 3u) - 1;   // d:0..7 -> +1,-1,+1,-1,0,0,+1,-1
+    const int dv = (int)((0x520au >> (2 * d)) & 3u) - 1;   // d:0..7 -> +1,+1,-1,-1,+1,-1,0,0
+    ci += du + (dv << A.wlog);
+    cells[ci] = 0;
+    if (n >= max_n) { status = ST_OVERFLOW; break; }
+    order[n++] = (CellT)ci;
+    if (depth - lo == cap) {
+      const int nlo = lo + A.stack_cap / 2;
+#pragma unroll 1
+      for (int dd = lo; dd < nlo; dd++) A.spill[dd] = stack[dd & smask];
+      lo = nlo;
+    }
+    stack[depth & smask] = (CellT)ci;
+    depth++;
+  }
+  ctl.n = n; ctl.depth = depth; ctl.lo = lo; ctl.u = ci;
+  return status;
+}
+
+template <class G, class CellT>
+XS_D int flood_component_bytes(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, Ctl& ctl, bool* empty) {
+  const int W = 1 << A.wlog;
+  {
+    uint32_t* w32 = reinterpret_cast<uint32_t*>(A.cells);
+    const int words = (W * W) >> 2;
+    for (int i = g.tid(); i < words; i += g.size()) w32[i] = 0x02020202u;
+  }
+  const int cu = c.c - A.ox, cv = c.c - A.oy;
+  if (g.tid() == 0) {
+    ctl.status = ST_NEED_TILE; ctl.req_tx = cu >> 5; ctl.req_ty = cv >> 5;
+    ctl.n = 0; ctl.depth = 0; ctl.lo = 0; ctl.u = cu + (cv << A.wlog); ctl.v = 0; ctl.m = 0; ctl.npoly = 0; ctl.overflow = 0; ctl.contact = 0u; ctl.counter = 0u; ctl.tiles = 0;
+    ctl.item_off = 0u; ctl.poly_off = 0u;
+    for (int i = 0; i < 6; i++) ctl.t[i] = 0u;
+    ctl.tmark = xs_clock();
+  }
+  g.sync();
+  *empty = false;
+  bool first = true;
+  const int nt = W >> 5;
+  for (;;) {
+    const int rtx = ctl.req_tx, rty = ctl.req_ty;
+    g.sync();
+    // sample the requested tile and (halo) its unsampled neighbours.  Every thread takes the same decisions
+    // from the same snapshot (no cell is written between the sync above and the one below).
+    uint32_t todo = 0u;
+    {
+      int idx = 0;
+      for (int ty = rty - A.halo; ty <= rty + A.halo; ty++)
+        for (int tx = rtx - A.halo; tx <= rtx + A.halo; tx++, idx++) {
+          if (tx < 0 || ty < 0 || tx >= nt || ty >= nt) continue;
+          if (A.cells[((ty * 32) << A.wlog) + tx * 32 + 1] == 2) todo |= 1u << idx;   // tiles are sampled whole
+        }
+    }
+    g.sync();
+    {
+      int idx = 0;
+      for (int ty = rty - A.halo; ty <= rty + A.halo; ty++)
+        for (int tx = rtx - A.halo; tx <= rtx + A.halo; tx++, idx++) {
+          if (!((todo >> idx) & 1u)) continue;
+          test_tile_bytes(g, c, vol, A, tx, ty);
+          if (g.tid() == 0) ctl.tiles++;
+        }
+    }
+    g.sync();
+    if (g.tid() == 0) {
+      int st;
+      const long long w0 = xs_clock();
+      if (first) {
+        uint8_t* cc = A.cells + ctl.u;
+        if (*cc != 1) {
+          st = ST_DONE; ctl.n = 0;
+        } else {
+          *cc = 0;
+          A.order[0] = (CellT)ctl.u; A.stack[0] = (CellT)ctl.u;
+          ctl.n = 1; ctl.depth = 1;
+          st = dfs_run_bytes(A, ctl);
+        }
+      } else {
+        st = dfs_run_bytes(A, ctl);
+      }
+      ctl.t[5] += (uint32_t)(xs_clock() - w0);
+      ctl.status = st;
+    }
+    first = false;
+    g.sync();
+    const int st = ctl.status;
+    if (st == ST_NEED_TILE) continue;
+    if (st == ST_OVERFLOW) return Q_OVERFLOW;
+    break;
+  }
+  *empty = (ctl.n == 0);
+  return Q_OK;
+}
+
 struct Sample {
   int rx, ry, rz;   // rounded voxel of the lattice sample
 };
@@ -645,20 +835,6 @@ XS_HD Sample sample_at(const PlaneCtx& c, const Arena<CellT>& A, int r, V3* roun
   return s;
 }
 
-XS_HD int popc8(uint32_t x) {
-#ifdef __CUDA_ARCH__
-  return __popc(x & 0xffu);
-#else
-  return __builtin_popcount(x & 0xffu);
-#endif
-}
-XS_HD int ffs32(uint32_t x) {
-#ifdef __CUDA_ARCH__
-  return __ffs(x);
-#else
-  return __builtin_ffs(x);
-#endif
-}
 // Step 3: contact bits (xs3d.hpp:909-914) and first-touch claims (xs3d.hpp:689-708).
 // The owner of a block is the claimer with the smallest DFS rank; since a sample probes each block at
 // most once, the rank alone identifies the (rank,k) pair the reference would have visited first.
@@ -848,7 +1024,8 @@ template <class G, class CellT, class H>
 XS_D int run_area_emit(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, H& hash, Ctl& ctl,
                        uint32_t q, const EmitOut& out) {
   bool empty;
-  if (flood_component(g, c, vol, A, ctl, &empty) != Q_OK) return Q_OVERFLOW;
+  const int fst = A.cells ? flood_component_bytes(g, c, vol, A, ctl, &empty) : flood_component(g, c, vol, A, ctl, &empty);
+  if (fst != Q_OK) return Q_OVERFLOW;
   if (g.tid() == 0) prof_mark(ctl, 0);
   if (empty) {
     if (g.tid() == 0) {

@@ -54,6 +54,7 @@ struct SmallArena {
     order.assign(max_n, 0); stack.assign(max_n, 0); slots.assign(hcap, 0);
     A.bits = bits.data(); A.tested = tested.data(); A.order = order.data(); A.stack = stack.data();
     A.max_n = max_n; A.stack_cap = max_n; A.spill = nullptr; A.mask = A.bits;   // masks alias the (dead) bitmap
+    A.cells = nullptr; A.wlog = 0;
     H.slot = slots.data(); H.cap = hcap; H.shift = 32 - __builtin_ctz(hcap); H.max_probe = 64;
     H.cbx = centre.rx >> 1; H.cby = centre.ry >> 1; H.cbz = centre.rz >> 1;
   }
@@ -76,8 +77,28 @@ struct BigArena {
     const uint32_t hcap = pow2_at_least((uint64_t)max_n * (uint64_t)factor + 64);
     htag.assign(hcap, 0); hkey.assign(hcap, 0);
     A.bits = bits.data(); A.tested = tested.data(); A.order = order.data(); A.stack = stack.data(); A.mask = mask.data();
+    A.cells = nullptr; A.wlog = 0;
     H.htag = htag.data(); H.hkey = hkey.data(); H.cap = hcap; H.cap_max = hcap; H.shift = 32 - __builtin_ctz(hcap);
     H.hx = v.hx; H.hy = v.hy; H.max_probe = 1 << 30; H.factor = factor;
+  }
+};
+
+// mid-tier-like arena: byte-per-cell 256x256 window, uint16 cells, wide hash, small stack ring
+struct ByteArena {
+  std::vector<uint8_t> cells;
+  std::vector<uint16_t> order, stack, spill;
+  std::vector<uint32_t> mask, htag, hkey;
+  Arena<uint16_t> A;
+  WideHash H;
+  void setup(const PlaneCtx& c, const VolView& v, int max_n, int ring) {
+    cells.assign(65536, 0xee); order.assign(max_n, 0); stack.assign(ring, 0); spill.assign(max_n, 0); mask.assign(max_n, 0);
+    const uint32_t hcap = pow2_at_least((uint64_t)max_n * 16 + 64);
+    htag.assign(hcap, 0); hkey.assign(hcap, 0);
+    A.cells = cells.data(); A.wlog = 8; A.ox = A.oy = c.c - 128; A.halo = 1;
+    A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = 8; A.stride = 0;
+    A.order = order.data(); A.max_n = max_n; A.stack = stack.data(); A.stack_cap = ring; A.spill = spill.data(); A.mask = mask.data();
+    H.htag = htag.data(); H.hkey = hkey.data(); H.cap = hcap; H.cap_max = hcap; H.shift = 32 - __builtin_ctz(hcap);
+    H.hx = v.hx; H.hy = v.hy; H.max_probe = 1 << 30; H.factor = 16;
   }
 };
 
@@ -85,6 +106,7 @@ extern "C" {
 
 // mode 0: big arena only.  mode 1: small (warp-tier-like) arena first, big arena on overflow.
 // mode 2: like 0 but with a tiny DFS stack ring (exercises spill/refill).
+// mode 3: byte-per-cell (mid-tier-like) arena with a 64-entry ring first, big arena on overflow.
 // stats[0] = queries that overflowed the small arena, stats[1] = total samples, stats[2] = total items, stats[3] = polygons
 void hostsim_area_batch(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t sz, uint64_t nq, const float* pos,
                         const float* nrm, const float* w, float* area, uint8_t* contact, int mode, int64_t* stats) {
@@ -110,6 +132,12 @@ void hostsim_area_batch(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t s
       Sample ctr; ctr.rx = (int)rp.x; ctr.ry = (int)rp.y; ctr.rz = (int)rp.z;
       sa.setup(c, ctr);
       st = run_area_emit(g, c, v, sa.A, sa.H, ctl, (uint32_t)q, O.out);
+      if (st != Q_OK) n_over++;
+    }
+    if (mode == 3) {
+      ByteArena ya;
+      ya.setup(c, v, 4096, 64);
+      st = run_area_emit(g, c, v, ya.A, ya.H, ctl, (uint32_t)q, O.out);
       if (st != Q_OK) n_over++;
     }
     if (st != Q_OK) {

@@ -10,7 +10,7 @@ import golden_util as gu
 from conftest import bits
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_area_random(hostsim, oracle, mode):
   rng = np.random.default_rng(1234 + mode)
   for it in range(250):
@@ -37,6 +37,8 @@ def test_area_neurite_tiers(hostsim, oracle):
   assert st[0] > 0, "expected some queries to overflow the small arena"
   a2, c2, _ = hostsim.area_batch(vol, qp[:60], qn[:60], [32, 32, 40], 2)
   assert np.array_equal(bits(a[:60]), bits(a2)) and np.array_equal(c[:60], c2)
+  a3, c3, st3 = hostsim.area_batch(vol, qp[:200], qn[:200], [32, 32, 40], 3)   # byte-per-cell (mid tier) flood
+  assert np.array_equal(bits(a[:200]), bits(a3)) and np.array_equal(c[:200], c3)
 
 
 def test_section_random(hostsim, oracle):
