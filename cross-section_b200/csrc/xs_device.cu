@@ -268,6 +268,7 @@ __device__ __forceinline__ bool block_arena(Arena<uint32_t>& A, WideHash& H, con
   A.cells = nullptr; A.wlog = 0;
   H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
   H.hx = vol.hx; H.hy = vol.hy;
+  H.alt_tag = nullptr; H.alt_key = nullptr; H.alt_cap = 0;
   int lg = 0;
   while ((1u << lg) < s.hcap_max) lg++;
   H.shift = 32 - lg;
@@ -360,8 +361,8 @@ __global__ void __launch_bounds__(MidTier::THREADS, 2) area_mid_kernel(BatchArgs
   A.order = reinterpret_cast<uint16_t*>(slab + (size_t)s.max_n * 4);
   A.spill = reinterpret_cast<uint16_t*>(slab + (size_t)s.max_n * 6);
   WideHash H;
-  H.htag = reinterpret_cast<uint32_t*>(slab + (size_t)s.max_n * 8);
-  H.hkey = H.htag + s.hcap_max;
+  uint32_t* const g_tag = reinterpret_cast<uint32_t*>(slab + (size_t)s.max_n * 8);
+  uint32_t* const g_key = g_tag + s.hcap_max;
   A.max_n = s.max_n;
   A.stack = reinterpret_cast<uint16_t*>(smem + MidTier::O_RING); A.stack_cap = MidTier::RING;
   A.cells = reinterpret_cast<uint8_t*>(smem + MidTier::O_CELLS); A.wlog = MidTier::WLOG;
@@ -381,8 +382,11 @@ __global__ void __launch_bounds__(MidTier::THREADS, 2) area_mid_kernel(BatchArgs
       continue;
     }
     A.ox = A.oy = c.c - (1 << (MidTier::WLOG - 1));
+    H.htag = g_tag; H.hkey = g_key;
     H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
     H.hx = a.vol.hx; H.hy = a.vol.hy;
+    // the 64 KB cell window is dead once the walk is done: 8192-entry first-touch table in shared memory
+    H.alt_tag = smem + MidTier::O_CELLS; H.alt_key = H.alt_tag + 8192; H.alt_cap = 8192;
     int lg = 0;
     while ((1u << lg) < s.hcap_max) lg++;
     H.shift = 32 - lg;
@@ -463,6 +467,26 @@ __global__ void __launch_bounds__(128) combine_kernel(const ItemRec* __restrict_
       if (threadIdx.x == 0) { area[q] = s.finish(); contact[q] = (uint8_t)qi.contact; }
     }
     __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// classification pre-pass: foreground count of the 32x32 lattice tile around each query's centre cell.
+// Large sections fill that tile; routing them to the mid tier up front lets both tiers start at t = 0.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) classify_kernel(VolView vol, const float* __restrict__ pos, const float* __restrict__ nrm,
+                                                       float wx, float wy, float wz, uint32_t nq, uint16_t* __restrict__ popc) {
+  const int lane = threadIdx.x & 31;
+  for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += (gridDim.x * blockDim.x) >> 5) {
+    PlaneCtx c;
+    const V3 p = mk(__ldg(pos + 3 * q), __ldg(pos + 3 * q + 1), __ldg(pos + 3 * q + 2));
+    const V3 n = mk(__ldg(nrm + 3 * q), __ldg(nrm + 3 * q + 1), __ldg(nrm + 3 * q + 2));
+    int cnt = 0;
+    if (plane_init(c, vol, p, n, mk(wx, wy, wz))) {
+      for (int row = 0; row < 32; row++) cnt += cell_fg(c, vol, c.c - 16 + lane, c.c - 16 + row) ? 1 : 0;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) popc[q] = (uint16_t)cnt;
   }
 }
 
@@ -851,6 +875,22 @@ extern "C" int xs3d_area_batch(xs3d_volume* v, uint64_t n, const float* pos, con
     CK(cudaMemcpyAsync(contact, d_contact, n, cudaMemcpyDeviceToHost, v->stream));
     CK(cudaStreamSynchronize(v->stream));
   }
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_debug_classify(xs3d_volume* v, uint64_t n, const float* pos, const float* normal, const float anisotropy[3], uint16_t* popc_host) {
+  if (!v || !v->loaded) return fail(XS3D_ERR_ARG, "volume not loaded");
+  CK(cudaSetDevice(v->device));
+  RET(ensure_batch_workspace(v, n));
+  RET(v->misc.ensure(n * 2 + 64));
+  CK(cudaMemcpyAsync(v->q_pos.p, pos, n * 12, cudaMemcpyHostToDevice, v->stream));
+  CK(cudaMemcpyAsync(v->q_nrm.p, normal, n * 12, cudaMemcpyHostToDevice, v->stream));
+  CK(cudaEventRecord(v->ev[0], v->stream));
+  classify_kernel<<<v->sm_count * 4, 256, 0, v->stream>>>(view_of(v), (const float*)v->q_pos.p, (const float*)v->q_nrm.p, anisotropy[0], anisotropy[1], anisotropy[2], (uint32_t)n, (uint16_t*)v->misc.p);
+  CK(cudaEventRecord(v->ev[1], v->stream));
+  CK(cudaMemcpyAsync(popc_host, v->misc.p, n * 2, cudaMemcpyDeviceToHost, v->stream));
+  CK(cudaStreamSynchronize(v->stream));
+  CK(cudaEventElapsedTime(&v->timing[7], v->ev[0], v->ev[1]));
   return XS3D_OK;
 }
 

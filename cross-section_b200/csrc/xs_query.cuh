@@ -335,7 +335,20 @@ struct WideHash {
   int max_probe;
   uint32_t cap_max;    // allocated capacity; with factor > 0 the capacity in use is re-chosen per query
   int factor;          //   as the power of two >= factor * samples (<= cap_max), so small queries clear little
+  uint32_t* alt_tag;   // optional small table in SHARED memory (the mid tier's cell window, dead after the walk):
+  uint32_t* alt_key;   //   used instead of the HBM table whenever 3 * samples fit in it
+  uint32_t alt_cap;
   XS_HD void fit(int n) {
+    if (alt_tag != nullptr && 3ull * (uint64_t)n <= (uint64_t)alt_cap) {
+      uint32_t c2 = 1024u;
+      while (c2 < 3u * (uint32_t)n) c2 <<= 1;
+      if (c2 > alt_cap) c2 = alt_cap;
+      int lg = 0;
+      while ((1u << lg) < c2) lg++;
+      htag = alt_tag; hkey = alt_key; cap = c2; shift = 32 - lg;
+      if (max_probe > 256) max_probe = 256;
+      return;
+    }
     if (factor <= 0) return;
     uint32_t c2 = 1024u;
     const uint64_t want = (uint64_t)factor * (uint64_t)n;

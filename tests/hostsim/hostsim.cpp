@@ -80,6 +80,7 @@ struct BigArena {
     A.cells = nullptr; A.wlog = 0;
     H.htag = htag.data(); H.hkey = hkey.data(); H.cap = hcap; H.cap_max = hcap; H.shift = 32 - __builtin_ctz(hcap);
     H.hx = v.hx; H.hy = v.hy; H.max_probe = 1 << 30; H.factor = factor;
+    H.alt_tag = nullptr; H.alt_key = nullptr; H.alt_cap = 0;
   }
 };
 
@@ -99,6 +100,8 @@ struct ByteArena {
     A.order = order.data(); A.max_n = max_n; A.stack = stack.data(); A.stack_cap = ring; A.spill = spill.data(); A.mask = mask.data();
     H.htag = htag.data(); H.hkey = hkey.data(); H.cap = hcap; H.cap_max = hcap; H.shift = 32 - __builtin_ctz(hcap);
     H.hx = v.hx; H.hy = v.hy; H.max_probe = 1 << 30; H.factor = 16;
+    // like the device: a small table aliased onto the (dead) cell window
+    H.alt_tag = reinterpret_cast<uint32_t*>(cells.data()); H.alt_key = H.alt_tag + 8192; H.alt_cap = 8192;
   }
 };
 
