@@ -159,6 +159,10 @@ __device__ __forceinline__ void finish_query(const BatchArgs& a, const Ctl& ctl,
     atomicAdd(&a.stats[1], (unsigned long long)ctl.m);
     atomicAdd(&a.stats[2], (unsigned long long)ctl.tiles);
     for (int i = 0; i < 6; i++) atomicAdd(&a.stats[stats_base + i], (unsigned long long)ctl.t[i]);
+    if (stats_base != 4) {   // CTA tiers: their own share of the work counters (the warp tier's is the remainder)
+      atomicAdd(&a.stats[16], (unsigned long long)ctl.n);
+      atomicAdd(&a.stats[17], (unsigned long long)ctl.m);
+    }
   } else {
     QInfo qi; qi.item_off = 0; qi.n_items = 0; qi.contact = 0; qi.status = QS_PENDING;
     a.out.qinfo[q] = qi;
@@ -532,6 +536,7 @@ struct xs3d_volume {
   SlabCfg cfg1{}, cfg2{};
   uint32_t* h_counters = nullptr;   // pinned: CNT_WORDS counters + 8 u64 stats
   uint64_t stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t tier_stats[2] = {0, 0};   // samples / items handled by the CTA tiers
   uint64_t prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   int sm_count = 0, smem_optin = 0;
   bool kernels_configured = false;
@@ -830,7 +835,8 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     const unsigned long long* hs = (const unsigned long long*)(v->h_counters + CNT_WORDS);
     v->stats[0] = hs[0]; v->stats[1] = hs[1]; v->stats[2] = hs[2] * 1024ull;
     v->stats[3] = over0; v->stats[4] = over1; v->stats[5] = (uint64_t)launches; v->stats[6] = over2; v->stats[7] = polys_used;
-    v->stats[8] = over3;
+    v->stats[8] = over3; v->stats[9] = 0;
+    v->tier_stats[0] = hs[16]; v->tier_stats[1] = hs[17];
     for (int i = 0; i < 12; i++) v->prof[i] = hs[4 + i];
     if (capacity) {
       // a record buffer filled up: double it and run the batch again
@@ -894,9 +900,42 @@ extern "C" int xs3d_debug_classify(xs3d_volume* v, uint64_t n, const float* pos,
   return XS3D_OK;
 }
 
+// One sweep with everything on the host: queries are enqueued BEFORE the (much larger) image so that, when several
+// sweeps are in flight on different volumes/streams, a sweep's query upload never queues behind another sweep's
+// 128 MiB image in the copy engine; then ingest, the query kernels and the read-back — one call, one final sync.
+extern "C" int xs3d_area_sweep_host(xs3d_volume* v, const uint8_t* binimg, int c_order, uint64_t n, const float* pos, const float* normal,
+                                    const float anisotropy[3], float* area, uint8_t* contact) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (!binimg || !pos || !normal || !anisotropy || !area || !contact) return fail(XS3D_ERR_ARG, "null argument");
+  if (n >= 0x7fffffffull) return fail(XS3D_ERR_ARG, "too many queries in one batch");
+  CK(cudaSetDevice(v->device));
+  const size_t voxels = (size_t)v->sx * v->sy * v->sz;
+  if (voxels == 0 || n == 0) {
+    memset(area, 0, n * 4); memset(contact, 0, n);
+    v->loaded = true;
+    return XS3D_OK;
+  }
+  RET(ensure_batch_workspace(v, n));
+  RET(v->raw.ensure(voxels + 64));
+  CK(cudaMemcpyAsync(v->q_pos.p, pos, n * 12, cudaMemcpyHostToDevice, v->stream));
+  CK(cudaMemcpyAsync(v->q_nrm.p, normal, n * 12, cudaMemcpyHostToDevice, v->stream));
+  CK(cudaMemcpyAsync(v->raw.p, binimg, voxels, cudaMemcpyHostToDevice, v->stream));
+  CK(cudaEventRecord(v->ev[6], v->stream));
+  RET(launch_ingest(v, (const uint8_t*)v->raw.p, c_order));
+  CK(cudaEventRecord(v->ev[7], v->stream));
+  v->loaded = true;
+  RET(area_batch_device(v, n, (const float*)v->q_pos.p, (const float*)v->q_nrm.p, anisotropy, (float*)v->q_area.p, (uint8_t*)v->q_contact.p, n < 4));
+  CK(cudaEventElapsedTime(&v->timing[4], v->ev[6], v->ev[7]));
+  CK(cudaMemcpyAsync(area, v->q_area.p, n * 4, cudaMemcpyDeviceToHost, v->stream));
+  CK(cudaMemcpyAsync(contact, v->q_contact.p, n, cudaMemcpyDeviceToHost, v->stream));
+  CK(cudaStreamSynchronize(v->stream));
+  return XS3D_OK;
+}
+
 extern "C" int xs3d_volume_stats(xs3d_volume* v, uint64_t stats[10]) {
   if (!v) return fail(XS3D_ERR_ARG, "null volume");
   for (int i = 0; i < 10; i++) stats[i] = v->stats[i];
+  stats[9] = v->tier_stats[0];   // samples handled by the CTA tiers (of stats[0])
   return XS3D_OK;
 }
 

@@ -165,7 +165,7 @@ class Volume:
     s = (C.c_uint64 * 10)()
     _abi.check(self._lib.xs3d_volume_stats(self._h, s))
     return {"samples": s[0], "blocks": s[1], "cells_tested": s[2], "escalated_mid": s[3], "escalated_big": s[4],
-            "launches": s[5], "escalated_worst_case": s[6], "polygons": s[7], "failed": s[8]}
+            "launches": s[5], "escalated_worst_case": s[6], "polygons": s[7], "failed": s[8], "samples_cta_tiers": s[9]}
 
   def timing(self):
     """CUDA-event kernel durations (ms) of the last call: warp tier, CTA tier, worst-case tier, ingest."""
@@ -224,6 +224,30 @@ class Volume:
       contact = np.empty(n, dtype=np.uint8)
     _abi.check(self._lib.xs3d_area_batch(self._h, n, pos.ctypes.data, nrm.ctypes.data, _abi.fptr(w), HOST,
                                          area.ctypes.data, contact.ctypes.data))
+    return (area, contact) if return_contact else area
+
+  def sweep(self, binimg, positions, normals, anisotropy=None, return_contact=False, out=None):
+    """(Re)load `binimg` into this volume and run all queries, in ONE call from host buffers: the natural unit
+    when sweeping many objects (one volume + its skeleton vertices per call).  Several Volumes driven from
+    different host threads overlap their uploads with each other's kernels."""
+    if binimg.dtype != bool and binimg.dtype != np.uint8:
+      raise ValueError(f"A boolean image is required. Got: {binimg.dtype}")
+    if tuple(int(s) for s in binimg.shape) != self.shape:
+      raise ValueError("image shape does not match the volume")
+    if anisotropy is None:
+      anisotropy = (1.0, 1.0, 1.0)
+    w = _abi.f3(anisotropy)
+    if np.any(w <= 0):
+      raise ValueError(f"anisotropy values must be > 0. Got: {w}")
+    a, ptr, c_order = _image_pointer(binimg)
+    pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+    nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+    if np.any(np.all(nrm == 0, axis=1)):
+      raise ValueError("normal vector must not be a null vector (all zeros).")
+    n = pos.shape[0]
+    area, contact = out if out is not None else (np.empty(n, dtype=np.float32), np.empty(n, dtype=np.uint8))
+    _abi.check(self._lib.xs3d_area_sweep_host(self._h, ptr, c_order, n, pos.ctypes.data, nrm.ctypes.data, _abi.fptr(w),
+                                              area.ctypes.data, contact.ctypes.data))
     return (area, contact) if return_contact else area
 
   def cross_sectional_area(self, pos, normal, anisotropy=None, return_contact=False):
@@ -292,8 +316,11 @@ def cross_sectional_area_batch(binimg, positions, normals, anisotropy=None, retu
     raise ValueError(f"A boolean image is required. Got: {binimg.dtype}")
   if binimg.ndim != 3:
     raise ValueError("dimensions not supported")
-  with Volume(binimg, device=device) as vol:
-    return vol.cross_sectional_area_batch(positions, normals, anisotropy, return_contact)
+  if _is_torch_tensor(binimg) or _is_torch_tensor(positions):
+    with Volume(binimg, device=device) as vol:
+      return vol.cross_sectional_area_batch(positions, normals, anisotropy, return_contact)
+  with Volume(shape=binimg.shape, device=device) as vol:
+    return vol.sweep(binimg, positions, normals, anisotropy, return_contact)
 
 
 def cross_sectional_area(

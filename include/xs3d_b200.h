@@ -58,10 +58,17 @@ int xs3d_volume_shape(xs3d_volume* vol, uint64_t shape[3]);
  *      Same per-query semantics as fastxs3d.area(..., slow_method=False)  (xs3d.hpp:1305-1365). */
 int xs3d_area_batch(xs3d_volume* vol, uint64_t n, const float* pos, const float* normal,
                     const float anisotropy[3], int mem, float* area, uint8_t* contact);
+/* One whole sweep from host buffers in a single call: upload the queries, upload + ingest `binimg` into `vol`
+ * (which must have the image's shape), run the batch, read areas + contacts back.  Equivalent to
+ * xs3d_volume_load(HOST) followed by xs3d_area_batch(HOST), but with the copies ordered so that several sweeps in
+ * flight on different volumes overlap their uploads with each other's kernels. */
+int xs3d_area_sweep_host(xs3d_volume* vol, const uint8_t* binimg, int c_order, uint64_t n, const float* pos,
+                         const float* normal, const float anisotropy[3], float* area, uint8_t* contact);
 /* Counters of the last xs3d_area_batch on this volume:
  * stats[0] lattice samples, [1] contributing blocks (items), [2] lattice cells tested, [3] queries escalated
  * warp->mid tier, [4] mid->big tier, [5] kernel launches of the call, [6] big->worst-case slab,
- * [7] polygon records evaluated, [8] queries that failed even with the worst-case slab, [9] reserved. */
+ * [7] polygon records evaluated, [8] queries that failed even with the worst-case slab, [9] lattice samples handled by the CTA tiers
+ * (the warp tier handled stats[0] - stats[9]). */
 int xs3d_volume_stats(xs3d_volume* vol, uint64_t stats[10]);
 /* SM-clock cycles thread 0 of each query group spent per phase in the last xs3d_area_batch, summed over
  * queries: prof[0..5] warp tier, prof[6..11] CTA tiers (mid + big); phases: [0] lattice flood (tiles + walk), [1] claims,

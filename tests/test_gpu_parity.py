@@ -147,6 +147,31 @@ def test_neurite_batch_golden_and_tiers(xs, golden):
   assert st["samples"] > 0 and st["launches"] >= 2
 
 
+def test_host_sweep_entry_point_and_threads(xs, golden):
+  """xs3d_area_sweep_host (image + queries from host in one call) equals load + batch, also when two volumes
+  are swept concurrently from two host threads (the pipelined end-to-end mode of bench.py)."""
+  import threading
+  from xs3d import synthetic
+  vol, verts, tans = synthetic.make_neurite(256, seed=0)
+  qp, qn = synthetic.draw_queries(verts, tans, 1000, seed=1)
+  w = [32, 32, 40]
+  a, c = xs.cross_sectional_area_batch(vol, qp, qn, w, return_contact=True)
+  assert np.array_equal(bits(a), bits(golden["neurite256_area"])) and np.array_equal(c, golden["neurite256_contact"])
+  cvol = np.ascontiguousarray(vol)
+  res = {}
+
+  def worker(k, image):
+    with xs.Volume(shape=vol.shape) as V:
+      for _ in range(3):
+        res[k] = V.sweep(image, qp, qn, w, return_contact=True)
+
+  ts = [threading.Thread(target=worker, args=(0, vol)), threading.Thread(target=worker, args=(1, cvol))]
+  [t.start() for t in ts]
+  [t.join() for t in ts]
+  for k in (0, 1):
+    assert np.array_equal(bits(res[k][0]), bits(a)) and np.array_equal(res[k][1], c)
+
+
 def test_neurite512_sweep_parity_and_properties(xs, oracle, neurite512):
   """BASELINE config 3: the 10k-vertex sweep.  Oracle parity on a 1500-query sample, then
   size-independent properties on all 10k: determinism, order independence (permuting the batch
