@@ -675,10 +675,17 @@ static SlabCfg make_cfg(const xs3d_volume* v, bool worst_case) {
   s.bits_words = ((win + 31) / 32 + 1) * (win + 32);
   s.tested_words = (((win + 31) / 32) * ((win + 31) / 32) + 31) / 32 + 1;
   if (!worst_case) {
-    s.max_n = 1 << 16;
-    s.hcap_max = 1u << 19;
-    s.hash_factor = 8;
-    s.max_probe = 256;
+    // big tier, one slab per SM: large enough for the biggest planar section of volumes up to ~600^3 (so the
+    // reference's perf.cpp-style sweeps through solid volumes run 148 planes at a time), capped at 2^19 samples
+    unsigned long long mn = (unsigned long long)(1.5 * (double)m * (double)m) + 16ull * m + 4096ull;
+    if (mn > (1ull << 19)) mn = 1ull << 19;
+    if (mn < (1ull << 16)) mn = 1ull << 16;
+    s.max_n = (int)mn;
+    unsigned long long cap = 1024;
+    while (cap < 4 * mn) cap <<= 1;
+    s.hcap_max = (uint32_t)cap;
+    s.hash_factor = 4;
+    s.max_probe = 1024;
   } else {
     // the largest planar section of a box is < 1.5 * m^2 lattice cells (plus rim)
     unsigned long long mn = (unsigned long long)(1.5 * (double)m * (double)m) + 16ull * m + 4096ull;

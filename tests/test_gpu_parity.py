@@ -256,3 +256,41 @@ def test_slice_batch_matches_single(xs, oracle, neurite512):
   o = oracle.projection(lab, qp[0], qn[0], w, True, float("inf"))
   g = xs.slice(lab, qp[0], qn[0], w)
   assert gu.same_bits(g, o)
+
+
+def test_config3_neurite1024_sweep(xs, oracle):
+  """BASELINE config 3: 10k skeleton queries on the 1024^3 neurite (1 GiB image, 128 MiB occupancy bytes).
+  Oracle parity on a 300-query sample, size-independent properties on all 10k."""
+  from xs3d import synthetic
+  vol, verts, tans = synthetic.make_neurite(1024, seed=0)
+  assert vol.sum() > 500000 and len(verts) > 3000
+  qp, qn = synthetic.draw_queries(verts, tans, 10000, seed=1)
+  w = [32, 32, 40]
+  with xs.Volume(vol) as V:
+    a, c = V.cross_sectional_area_batch(qp, qn, w, return_contact=True)
+    perm = np.random.default_rng(1).permutation(len(qp))
+    a2, c2 = V.cross_sectional_area_batch(qp[perm], qn[perm], w, return_contact=True)
+  oa, oc = oracle.area_batch(vol, qp[:300], qn[:300], w)
+  assert np.array_equal(bits(a[:300]), bits(oa)) and np.array_equal(c[:300], oc)
+  assert np.array_equal(bits(a[perm]), bits(a2)) and np.array_equal(c[perm], c2)
+  assert (a > 0).all()
+
+
+def test_config4_slice_1024_uint64(xs, oracle):
+  """BASELINE config 4: cropped slices of a 1024^3 uint64 label volume (8 GiB), 10k planes in one batch.
+  Skipped when the host cannot hold the label volume."""
+  import psutil
+  if psutil.virtual_memory().available < 40 * 2 ** 30:
+    pytest.skip("needs ~20 GiB of free host memory")
+  from xs3d import synthetic
+  vol, verts, tans = synthetic.make_neurite(1024, seed=0)
+  lab = synthetic.make_labels(vol, np.uint64, hashed=True)
+  del vol
+  qp, qn = synthetic.draw_queries(verts, tans, 10000, seed=2)
+  w = [32, 32, 40]
+  with xs.Volume(labels=lab) as V:
+    res = V.slice_batch(qp, qn, w, crop=100)
+  assert len(res) == 10000
+  for i in range(0, 10000, 997):
+    o = oracle.projection(lab, qp[i], qn[i], w, True, 100.0)
+    assert gu.same_bits(np.asfortranarray(res[i]), o), i
