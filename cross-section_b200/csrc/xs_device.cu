@@ -118,6 +118,28 @@ __global__ void __launch_bounds__(256) ingest_generic_kernel(const uint8_t* __re
   }
 }
 
+// Label volume -> occupancy bytes of ONE label: one resident segmentation serves every object in
+// it without materialising (or uploading) a boolean image per object.  One thread per output byte, any item size,
+// either memory order.  HBM-bound: reads V * itemsize bytes, writes V/8.
+template <typename T>
+__global__ void __launch_bounds__(256) ingest_label_kernel(const T* __restrict__ labels, T want, uint8_t* __restrict__ cubes,
+                                                           int sx, int sy, int sz, int hx, int hy, int hz,
+                                                           long long stx, long long sty, long long stz) {
+  const size_t total = (size_t)hx * hy * hz;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int bx = (int)(idx % hx);
+    const size_t t = idx / hx;
+    const int by = (int)(t % hy), bz = (int)(t / hy);
+    uint32_t m = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const int x = 2 * bx + (b & 1), y = 2 * by + ((b >> 1) & 1), z = 2 * bz + (b >> 2);
+      if (x < sx && y < sy && z < sz && __ldg(labels + (long long)x * stx + (long long)y * sty + (long long)z * stz) == want) m |= 1u << b;
+    }
+    cubes[idx] = (uint8_t)m;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // T0: one warp per query, shared-memory arena (7.3 KB per warp -> 30 warps per SM)
 // ------------------------------------------------------------------------------------------------
@@ -647,6 +669,32 @@ extern "C" int xs3d_volume_load(xs3d_volume* v, const uint8_t* binimg, int mem, 
   }
   CK(cudaEventRecord(v->ev[6], v->stream));
   RET(launch_ingest(v, d_img, c_order));
+  CK(cudaEventRecord(v->ev[7], v->stream));
+  CK(cudaStreamSynchronize(v->stream));
+  CK(cudaEventElapsedTime(&v->timing[4], v->ev[6], v->ev[7]));
+  v->loaded = true;
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_volume_select_label(xs3d_volume* v, uint64_t label) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (!v->labels_loaded) return fail(XS3D_ERR_ARG, "volume has no labels loaded");
+  CK(cudaSetDevice(v->device));
+  const size_t nblocks = (size_t)v->hx * v->hy * v->hz;
+  if (nblocks == 0) { v->loaded = true; return XS3D_OK; }
+  const long long stx = v->labels_c_order ? (long long)v->sy * v->sz : 1ll;
+  const long long sty = v->labels_c_order ? (long long)v->sz : (long long)v->sx;
+  const long long stz = v->labels_c_order ? 1ll : (long long)v->sx * v->sy;
+  const int grid = (int)std::min<size_t>((nblocks + 255) / 256, (size_t)v->sm_count * 32);
+  uint8_t* cubes = (uint8_t*)v->cubes.p;
+  CK(cudaEventRecord(v->ev[6], v->stream));
+  switch (v->itemsize) {
+    case 1: ingest_label_kernel<uint8_t><<<grid, 256, 0, v->stream>>>((const uint8_t*)v->labels.p, (uint8_t)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz, stx, sty, stz); break;
+    case 2: ingest_label_kernel<uint16_t><<<grid, 256, 0, v->stream>>>((const uint16_t*)v->labels.p, (uint16_t)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz, stx, sty, stz); break;
+    case 4: ingest_label_kernel<uint32_t><<<grid, 256, 0, v->stream>>>((const uint32_t*)v->labels.p, (uint32_t)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz, stx, sty, stz); break;
+    default: ingest_label_kernel<unsigned long long><<<grid, 256, 0, v->stream>>>((const unsigned long long*)v->labels.p, (unsigned long long)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz, stx, sty, stz); break;
+  }
+  CK(cudaGetLastError());
   CK(cudaEventRecord(v->ev[7], v->stream));
   CK(cudaStreamSynchronize(v->stream));
   CK(cudaEventElapsedTime(&v->timing[4], v->ev[6], v->ev[7]));

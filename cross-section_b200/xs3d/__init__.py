@@ -26,7 +26,7 @@ VECTOR_T = Union[tuple, npt.NDArray[np.float32]]
 
 __all__ = [
   "cross_sectional_area", "cross_section", "slice", "set_shape", "clear_shape",
-  "Volume", "cross_sectional_area_batch", "XS3DError",
+  "Volume", "cross_sectional_area_batch", "skeleton_tangents", "sweep_skeleton", "XS3DError",
 ]
 
 
@@ -150,6 +150,11 @@ class Volume:
       raise ValueError("labels must have a 1, 2, 4 or 8 byte dtype")
     self._label_dtype = labels.dtype
     _abi.check(self._lib.xs3d_volume_load_labels(self._h, labels.ctypes.data, labels.dtype.itemsize, HOST, c_order))
+
+  def select_label(self, label):
+    """Make the resident binary image `labels == label` (labels loaded with load_labels / Volume(labels=...)):
+    rebuilt on the device, nothing is uploaded.  One resident segmentation then serves every object in it."""
+    _abi.check(self._lib.xs3d_volume_select_label(self._h, C.c_uint64(int(label) & 0xFFFFFFFFFFFFFFFF)))
 
   def cubes(self):
     """(device pointer, nbytes) of the ingested 2x2x2 occupancy bytes (used by xs3d.dist.broadcast)."""
@@ -321,6 +326,45 @@ def cross_sectional_area_batch(binimg, positions, normals, anisotropy=None, retu
       return vol.cross_sectional_area_batch(positions, normals, anisotropy, return_contact)
   with Volume(shape=binimg.shape, device=device) as vol:
     return vol.sweep(binimg, positions, normals, anisotropy, return_contact)
+
+
+def skeleton_tangents(vertices, edges):
+  """Unit tangent per skeleton vertex, in the coordinates of `vertices` (pass voxel coordinates: the reference
+  takes plane normals in voxel space, README.md:20-24).  The tangent of a vertex is the normalised sum of its
+  incident edge directions, each flipped to agree with the vertex's first edge (so the two edges of a path vertex
+  reinforce instead of cancelling).  Vertices without edges get (0, 0, 1)."""
+  v = np.asarray(vertices, dtype=np.float64).reshape(-1, 3)
+  e = np.asarray(edges, dtype=np.int64).reshape(-1, 2)
+  m = len(v)
+  src = np.concatenate([e[:, 0], e[:, 1]])
+  dst = np.concatenate([e[:, 1], e[:, 0]])
+  d = v[dst] - v[src]
+  nrm = np.linalg.norm(d, axis=1)
+  ok = nrm > 0
+  src, d = src[ok], d[ok] / nrm[ok, None]
+  first = np.full(m, -1, dtype=np.int64)
+  order = np.arange(len(src))[::-1]
+  first[src[order]] = order                     # first incident half-edge of every vertex
+  ref = np.zeros((m, 3))
+  has = first >= 0
+  ref[has] = d[first[has]]
+  sign = np.where(np.einsum("ij,ij->i", d, ref[src]) < 0, -1.0, 1.0)
+  t = np.zeros((m, 3))
+  np.add.at(t, src, d * sign[:, None])
+  n = np.linalg.norm(t, axis=1)
+  out = np.tile(np.array([0.0, 0.0, 1.0]), (m, 1))
+  good = n > 0
+  out[good] = t[good] / n[good, None]
+  return out.astype(np.float32)
+
+
+def sweep_skeleton(binimg, vertices, edges, anisotropy=None, return_contact=False, device=0):
+  """Cross-sectional area at every vertex of a skeleton (vertices [M,3] in voxel coordinates, edges [E,2]),
+  section planes normal to the skeleton tangent — the use the reference is written for (README.md:59-71),
+  as one batched call.  `binimg` may be a bool ndarray or a resident Volume."""
+  normals = skeleton_tangents(vertices, edges)
+  pos = np.asarray(vertices, dtype=np.float32).reshape(-1, 3)
+  return cross_sectional_area_batch(binimg, pos, normals, anisotropy, return_contact, device=device)
 
 
 def cross_sectional_area(

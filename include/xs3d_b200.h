@@ -48,6 +48,9 @@ int xs3d_volume_destroy(xs3d_volume* vol);
 int xs3d_volume_load(xs3d_volume* vol, const uint8_t* binimg, int mem, int c_order);
 /* Attach a label volume for xs3d_projection_v (any 1/2/4/8-byte dtype, C or F order; fastxs3d.cpp:135,199-215). */
 int xs3d_volume_load_labels(xs3d_volume* vol, const void* labels, int itemsize, int mem, int c_order);
+/* Make the resident image "labels == label" (labels attached with xs3d_volume_load_labels): the occupancy bytes
+ * are rebuilt on the device from the label volume, so one uploaded segmentation serves every object in it. */
+int xs3d_volume_select_label(xs3d_volume* vol, uint64_t label);
 /* Device pointer + size of the ingested occupancy bytes (for an NCCL broadcast by the host layer),
  * and the call that marks them valid after such a broadcast wrote them. */
 int xs3d_volume_cubes(xs3d_volume* vol, void** device_ptr, uint64_t* bytes);

@@ -85,3 +85,15 @@ def test_shard_bounds():
       assert all(chunks[i][1] == chunks[i + 1][0] for i in range(world - 1))
       sizes = [hi - lo for lo, hi in chunks]
       assert max(sizes) - min(sizes) <= 1
+
+
+def test_skeleton_tangents():
+  import xs3d
+  verts = np.array([[0, 0, 0], [1, 0, 0], [2, 0, 0], [2, 1, 0], [9, 9, 9]], float)
+  edges = np.array([[0, 1], [1, 2], [2, 3]])
+  t = xs3d.skeleton_tangents(verts, edges)
+  assert t.dtype == np.float32 and t.shape == (5, 3)
+  assert np.allclose(np.abs(t[0]), [1, 0, 0]) and np.allclose(np.abs(t[1]), [1, 0, 0])
+  assert np.allclose(np.abs(t[2]), np.array([1, 1, 0]) / np.sqrt(2), atol=1e-6)
+  assert np.allclose(np.abs(t[3]), [0, 1, 0]) and np.allclose(t[4], [0, 0, 1])
+  assert np.allclose(np.linalg.norm(t, axis=1), 1, atol=1e-6)

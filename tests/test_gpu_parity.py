@@ -294,3 +294,30 @@ def test_config4_slice_1024_uint64(xs, oracle):
   for i in range(0, 10000, 997):
     o = oracle.projection(lab, qp[i], qn[i], w, True, 100.0)
     assert gu.same_bits(np.asfortranarray(res[i]), o), i
+
+
+def test_select_label_and_skeleton_sweep(xs, oracle):
+  """a resident label volume serves each object through xs3d_volume_select_label (mask built on the
+  device), and sweep_skeleton runs a whole skeleton in one call.  Both equal the per-object reference path."""
+  from xs3d import synthetic
+  vol, verts, tans = synthetic.make_neurite(192, seed=3, n_branches=5)
+  rng = np.random.default_rng(0)
+  other = np.asfortranarray(rng.random(vol.shape) < 0.02) & ~vol
+  for dt in (np.uint8, np.uint32, np.uint64):
+    lab = np.zeros(vol.shape, dtype=dt, order="F")
+    lab[vol] = 7
+    lab[other] = 9
+    for arr in (lab, np.ascontiguousarray(lab)):
+      with xs.Volume(labels=arr) as V:
+        for label, mask in ((7, vol), (9, other)):
+          V.select_label(label)
+          idx = np.argwhere(mask)[:: max(1, int(mask.sum()) // 40)][:40].astype(np.float32)
+          nr = np.tile(np.array([0.3, -0.2, 0.9], np.float32), (len(idx), 1))
+          a, c = V.cross_sectional_area_batch(idx, nr, [32, 32, 40], return_contact=True)
+          oa, oc = oracle.area_batch(mask, idx, nr, [32, 32, 40])
+          assert np.array_equal(bits(a), bits(oa)) and np.array_equal(c, oc), (dt, label)
+  edges = np.stack([np.arange(len(verts) - 1), np.arange(1, len(verts))], 1)
+  a, c = xs.sweep_skeleton(vol, verts, edges, [32, 32, 40], return_contact=True)
+  nrm = xs.skeleton_tangents(verts, edges)
+  oa, oc = oracle.area_batch(vol, verts.astype(np.float32), nrm, [32, 32, 40])
+  assert np.array_equal(bits(a), bits(oa)) and np.array_equal(c, oc)
