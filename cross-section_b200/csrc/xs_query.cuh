@@ -497,8 +497,8 @@ XS_HD int ffs32(uint32_t x) {
 #endif
 }
 // Walk direction table: index = the 3x3 availability neighbourhood (rows v-1, v, v+1, three bits each: u-1,u,u+1);
-// entry = 0xff when no neighbour is available, else (du+1) | (dv+1)<<2 of the FIRST available neighbour in
-// the reference's priority order — the reverse of its push order (xs3d.hpp:926-950):
+// entry = 0xff when no neighbour is available, else (du+1) | (dv+1)<<2 | more<<4 for the FIRST available neighbour
+// in the reference's priority order (more = at least one other neighbour is available too) — the reverse of its push order (xs3d.hpp:926-950):
 // (+1,+1) (-1,+1) (+1,-1) (-1,-1) (0,+1) (0,-1) (+1,0) (-1,0).
 struct DirLut { uint8_t e[512]; };
 constexpr DirLut make_dir_lut() {
@@ -506,11 +506,12 @@ constexpr DirLut make_dir_lut() {
   const int du[8] = { 1, -1, 1, -1, 0, 0, 1, -1 };
   const int dv[8] = { 1, 1, -1, -1, 1, -1, 0, 0 };
   for (int idx = 0; idx < 512; idx++) {
-    int found = 0xff;
+    int found = 0xff, count = 0;
     for (int d = 7; d >= 0; d--) {
       const int row = dv[d] + 1, col = du[d] + 1;       // row 0 = v-1, row 2 = v+1
-      if ((idx >> (3 * row + col)) & 1) found = (du[d] + 1) | ((dv[d] + 1) << 2);
+      if ((idx >> (3 * row + col)) & 1) { found = (du[d] + 1) | ((dv[d] + 1) << 2); count++; }
     }
+    if (count >= 2) found |= 16;                        // bit 4: other neighbours remain after taking this one
     t.e[idx] = (uint8_t)found;
   }
   return t;
@@ -587,11 +588,14 @@ XS_HD int dfs_run(const Arena<CellT>& A, Ctl& ctl) {
       u = P::u(p); v = P::v(p);
       continue;
     }
-    u += (int)(e & 3u) - 1; v += (int)(e >> 2) - 1;
+    u += (int)(e & 3u) - 1; v += (int)((e >> 2) & 3u) - 1;
     bits[v * stride + (u >> 5)] &= ~(1u << (u & 31));
     if (((unsigned)(u - 1) >= Wm2) | ((unsigned)(v - 1) >= Hm2) | (n >= max_n)) { status = ST_OVERFLOW; break; }
     const CellT p = P::pack(u, v);
     order[n++] = p;
+    // Tail call: if the cell we are leaving has no other available neighbour NOW it never will (availability only
+    // decreases), so coming back to it would find nothing — reuse its frame instead of stacking on top of it.
+    if (!(e & 16u)) depth--;
     if (depth - lo == cap) {
       // (ring only) ring full: spill the lower half
       const int nlo = lo + A.stack_cap / 2;
@@ -746,6 +750,7 @@ XS_HD int dfs_run_bytes(const Arena<CellT>& A, Ctl& ctl) {
     cells[ci] = 0;
     if (n >= max_n) { status = ST_OVERFLOW; break; }
     order[n++] = (CellT)ci;
+    if ((m & (m - 1u)) == 0u) depth--;     // tail call: the cell we leave has nothing left, reuse its frame
     if (depth - lo == cap) {
       const int nlo = lo + A.stack_cap / 2;
 #pragma unroll 1
