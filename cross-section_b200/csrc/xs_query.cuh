@@ -217,11 +217,13 @@ XS_HD uint32_t atomic_cas_u32(uint32_t* p, uint32_t cmp, uint32_t val) {
   return old;
 #endif
 }
-XS_HD void atomic_min_u32(uint32_t* p, uint32_t val) {
+XS_HD uint32_t atomic_min_u32(uint32_t* p, uint32_t val) {   // returns the previous value
 #ifdef __CUDA_ARCH__
-  atomicMin(p, val);
+  return atomicMin(p, val);
 #else
-  if (val < *p) *p = val;
+  const uint32_t old = *p;
+  if (val < old) *p = val;
+  return old;
 #endif
 }
 XS_HD uint32_t atomic_add_u32(uint32_t* p, uint32_t val) {
@@ -302,17 +304,22 @@ struct PackedHash {
   template <class G> XS_D void clear(const G& g) const {
     for (uint32_t i = g.tid(); i < cap; i += g.size()) slot[i] = XS_HEMPTY;
   }
-  XS_HD bool claim(int bx, int by, int bz, uint32_t rank) const {
+  // returns 0: table full (probe limit), 1: claimed but a smaller rank holds the block, 2: this rank holds it NOW
+  // (it may still lose it to a smaller rank claiming later — "tentative owner")
+  XS_HD int claim(int bx, int by, int bz, uint32_t rank) const {
     const uint32_t t = tag(bx, by, bz), word = (t << 9) | rank;
     uint32_t h = (t * 2654435761u) >> shift;
     for (int probes = 0; probes < max_probe; probes++) {
       uint32_t old = slot[h];
       if (old == XS_HEMPTY) old = atomic_cas_u32(&slot[h], XS_HEMPTY, word);
-      if (old == XS_HEMPTY) return true;
-      if ((old >> 9) == t) { if (old > word) atomic_min_u32(&slot[h], word); return true; }
+      if (old == XS_HEMPTY) return 2;
+      if ((old >> 9) == t) {
+        if (old > word) old = atomic_min_u32(&slot[h], word);
+        return old > word ? 2 : 1;
+      }
       h = (h + 1u) & (cap - 1u);
     }
-    return false;
+    return 0;
   }
   XS_HD uint32_t owner(int bx, int by, int bz) const {
     const uint32_t t = tag(bx, by, bz);
@@ -361,15 +368,15 @@ struct WideHash {
   template <class G> XS_D void clear(const G& g) const {
     for (uint32_t i = g.tid(); i < cap; i += g.size()) { htag[i] = XS_HEMPTY; hkey[i] = XS_HEMPTY; }
   }
-  XS_HD bool claim(int bx, int by, int bz, uint32_t rank) const {
+  XS_HD int claim(int bx, int by, int bz, uint32_t rank) const {   // 0 full / 1 not owner / 2 tentative owner
     const uint32_t t = id(bx, by, bz);
     uint32_t h = (t * 2654435761u) >> shift;
     for (int probes = 0; probes < max_probe; probes++) {
       const uint32_t old = atomic_cas_u32(&htag[h], XS_HEMPTY, t);
-      if (old == XS_HEMPTY || old == t) { atomic_min_u32(&hkey[h], rank); return true; }
+      if (old == XS_HEMPTY || old == t) return atomic_min_u32(&hkey[h], rank) > rank ? 2 : 1;
       h = (h + 1u) & (cap - 1u);
     }
-    return false;
+    return 0;
   }
   XS_HD uint32_t owner(int bx, int by, int bz) const {
     const uint32_t t = id(bx, by, bz);
@@ -899,14 +906,19 @@ XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const 
           }
         }
       }
-      A.mask[r] = cmask;
+      // claim every probed block; remember only the claims that WON at claim time: a sample can end up owning a
+      // block only if it held it at some point, so the ownership pass re-checks those few instead of all ~20
+      uint32_t tentative = 0u;
       while (cmask) {
         const int k = ffs32(cmask) - 1;
         cmask &= cmask - 1u;
         int ox, oy, oz;
         decode_k(k, ox, oy, oz);
-        if (!hash.claim(bx + ox, by + oy, bz + oz, (uint32_t)r)) ovf = true;
+        const int won = hash.claim(bx + ox, by + oy, bz + oz, (uint32_t)r);
+        if (won == 0) ovf = true;
+        if (won == 2) tentative |= 1u << k;
       }
+      A.mask[r] = tentative;
     }
     g.converge();
   }
