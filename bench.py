@@ -323,7 +323,7 @@ def run_own_arm(args):
   achieved = alg_bytes / (dom_ms / 1000.0) / 1e9
   kname = {"warp_tier_ms": "area_warp_kernel", "mid_tier_ms": "area_mid_kernel", "big_tier_ms": "area_block_kernel<BigTier>", "polygon_ms": "poly_eval_kernel"}[dom]
   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
-  # (profiles/r1d_ncu_full_summary.txt)
+  # (profiles/r1e_ncu_full_summary.txt, profiles/r1e_per_kernel_hbm_l2.txt)
   ncu_traffic = {"area_warp_kernel": 2857728 + 4352, "area_mid_kernel": 2069504, "poly_eval_kernel": 16358656, "combine_kernel": 12110592}
   roofline = {"bound": "hbm", "kernel": kname,
               "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic.get(kname),

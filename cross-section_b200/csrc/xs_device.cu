@@ -772,7 +772,7 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
   RET(v->qinfo.ensure(n * sizeof(QInfo) + 64));
   if (v->poly_cap == 0) {
     // first guess: ~1k polygons per query (a neurite-scale section needs 200-600); grown on demand
-    v->poly_cap = std::max<uint64_t>(1ull << 20, n * 1024ull);
+    v->poly_cap = std::min<uint64_t>(std::max<uint64_t>(1ull << 20, n * 1024ull), 1ull << 26);
     v->item_cap = v->poly_cap / 2;
   }
   RET(v->polys.ensure(v->poly_cap * sizeof(PolyRec) + 64));
