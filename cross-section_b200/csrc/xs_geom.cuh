@@ -92,31 +92,28 @@ XS_HD void plane_cube_points(float x, float y, float z, const PlaneGeom& g, Poly
     const int k = i & 3, a = i >> 2;
     const float proj = cproj[k];
     const V3 c = corner[k];
-    if (done) continue;
-    if (proj == 0.0f) {
-      if (i < 4) {
-        if (!poly_has(q, c)) poly_push(q, c);
-      }
-      continue;
-    }
+    // Evaluate the edge unconditionally and fold the reference's chain of `continue`s (xs3d.hpp:308-345) into
+    // predicates: 32 different cubes per warp would otherwise diverge at every one of them.
     const float na = (a == 0) ? g.n.x : (a == 1 ? g.n.y : g.n.z);
-    if (na == 0.0f) continue;
     const float t = fmul(proj, g.inv[a]);
     const float at = fabsf(t);
-    if (at > tmax) continue;
     V3 hit = c;
     if (a == 0) hit.x = fadd(c.x, t);
     else if (a == 1) hit.y = fadd(c.y, t);
     else hit.z = fadd(c.z, t);
-    if (fabsf(fsub(hit.x, centre.x)) >= bound) continue;
-    if (fabsf(fsub(hit.y, centre.y)) >= bound) continue;
-    if (fabsf(fsub(hit.z, centre.z)) >= bound) continue;
-    const bool oncorner = (at < XS_EPS) || (fabsf(fsub(at, fS)) < XS_EPS);
-    bool dup = false;
-    if (oncorner) dup = poly_has(q, hit);
-    if (!dup) {
-      poly_push(q, hit);
-      if (q.n >= g.max_pts) done = true;
+    const bool on_plane = (proj == 0.0f);
+    const bool inside = !(fabsf(fsub(hit.x, centre.x)) >= bound) & !(fabsf(fsub(hit.y, centre.y)) >= bound) & !(fabsf(fsub(hit.z, centre.z)) >= bound);
+    const bool edge_hit = !done & !on_plane & (na != 0.0f) & !(at > tmax) & inside;
+    const bool corner_hit = !done & on_plane & (i < 4);
+    const bool oncorner = (at < XS_EPS) | (fabsf(fsub(at, fS)) < XS_EPS);
+    const V3 cand = on_plane ? c : hit;
+    bool take = edge_hit | corner_hit;
+    if (take & (corner_hit | oncorner)) {       // rare: only points that may coincide with a cube corner are de-duplicated
+      if (poly_has(q, cand)) take = false;
+    }
+    if (take) {
+      poly_push(q, cand);
+      if (edge_hit & (q.n >= g.max_pts)) done = true;   // the reference only checks the cap after an edge hit (:354-356)
     }
   }
 }
