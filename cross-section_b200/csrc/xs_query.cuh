@@ -578,7 +578,21 @@ XS_HD int dfs_run(const Arena<CellT>& A, Ctl& ctl) {
     const uint32_t* rp = bits + ((v - 1) * stride + (um1 >> 5));
     const uint32_t a0 = rp[0], a1 = rp[1], b0 = rp[stride], b1 = rp[stride + 1], c0 = rp[2 * stride], c1 = rp[2 * stride + 1];
     const uint32_t idx = (funnel_r(a0, a1, sh) & 7u) | ((funnel_r(b0, b1, sh) & 7u) << 3) | ((funnel_r(c0, c1, sh) & 7u) << 6);
-    const uint32_t e = dir_lut(idx);
+    uint32_t e;
+    if (sizeof(CellT) == 2) {
+      e = dir_lut(idx);                       // warp tier (issue-bound): one table load
+    } else {
+      // CTA tiers (latency-bound, one thread): an indexed constant load costs more than the ALU it saves.
+      // idx bits: rm 0..2, r0 3..5, rq 6..8  ->  priority mask [rq2 rq0 rm2 rm0 rq1 rm1 r0_2 r0_0]
+      const uint32_t pm = ((idx >> 8) & 1u) | ((idx >> 5) & 2u) | (idx & 4u) | ((idx << 3) & 8u) | ((idx >> 3) & 16u) | ((idx << 4) & 32u) |
+                          ((idx << 1) & 64u) | ((idx << 4) & 128u);
+      if (pm == 0u) {
+        e = 0xffu;
+      } else {
+        const int d = ffs32(pm) - 1;
+        e = ((0x2522u >> (2 * d)) & 3u) | (((0x520au >> (2 * d)) & 3u) << 2) | ((pm & (pm - 1u)) ? 16u : 0u);
+      }
+    }
     if (e == 0xffu) {
       // backtrack
       depth--;
