@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) area_warp_kernel(BatchArgs a) {
   A.order = reinterpret_cast<uint16_t*>(base + L::O_ORDER); A.max_n = MAXN;
   A.stack = reinterpret_cast<uint16_t*>(base + L::O_STACK); A.stack_cap = MAXN; A.spill = nullptr;
   A.mask = A.bits;
-  A.cells = nullptr; A.wlog = 0;
+  A.cells = nullptr; A.wlog = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
   PackedHash H;
   H.slot = base + L::O_HASH; H.cap = HCAP; H.max_probe = 48;
   int lg = 0;
@@ -291,7 +291,7 @@ __device__ __forceinline__ bool block_arena(Arena<uint32_t>& A, WideHash& H, con
   uint32_t* g_bits = p; p += s.bits_words;
   uint32_t* g_tested = p;
   A.max_n = s.max_n;
-  A.cells = nullptr; A.wlog = 0;
+  A.cells = nullptr; A.wlog = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
   H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
   H.hx = vol.hx; H.hy = vol.hy;
   H.alt_tag = nullptr; H.alt_key = nullptr; H.alt_cap = 0;
@@ -354,9 +354,10 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_BLOCKS) area_block_kernel(B
 }
 
 // ------------------------------------------------------------------------------------------------
-// MID tier: one 256-thread CTA per query, byte-per-cell 256x256 window in shared memory (64 KB) so the
-// single-thread walk has a short dependent chain per step.  Takes the few per cent of sweep queries that
-// do not fit a warp; two CTAs per SM so they all run in one wave.
+// MID tier: one 256-thread CTA per query, 256x256-cell window in shared memory as one neighbour byte per cell
+// (64 KB) + a foreground bitmap (10 KB): the walk is two dependent shared-memory loads per step, run by one
+// warp in lock step (xs_query.cuh, flood_component_nbr).  Takes the few per cent of sweep queries that do not
+// fit a warp.
 // ------------------------------------------------------------------------------------------------
 struct MidTier {
   static constexpr int THREADS = 256;
@@ -364,8 +365,11 @@ struct MidTier {
   static constexpr int RING = 4096;                // DFS stack ring entries (uint16) in shared memory
   static constexpr int O_CTL = 64;
   static constexpr int O_RING = O_CTL + 48;
-  static constexpr int O_CELLS = O_RING + RING / 2;
-  static constexpr int WORDS = O_CELLS + ((1 << (2 * WLOG)) >> 2);
+  static constexpr int O_LUT = O_RING + RING / 2;  // 256 x int16
+  static constexpr int FSTRIDE = (1 << WLOG) / 32 + 2;
+  static constexpr int O_FBITS = O_LUT + 128;
+  static constexpr int O_CELLS = O_FBITS + ((1 << WLOG) + 2) * FSTRIDE;
+  static constexpr int WORDS = O_CELLS + ((1 << (2 * WLOG)) >> 2) + 128;   // the walk may LOAD up to a row past either end
 };
 
 __host__ __device__ inline size_t mid_slab_bytes(const SlabCfg& s) {
@@ -393,6 +397,9 @@ __global__ void __launch_bounds__(MidTier::THREADS, 2) area_mid_kernel(BatchArgs
   A.stack = reinterpret_cast<uint16_t*>(smem + MidTier::O_RING); A.stack_cap = MidTier::RING;
   A.cells = reinterpret_cast<uint8_t*>(smem + MidTier::O_CELLS); A.wlog = MidTier::WLOG;
   A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = (1 << MidTier::WLOG) / 32; A.stride = 0; A.halo = 1;
+  A.fbits = smem + MidTier::O_FBITS; A.fstride = MidTier::FSTRIDE;
+  A.nlut = reinterpret_cast<const int16_t*>(smem + MidTier::O_LUT);
+  nbr_lut_fill(g, reinterpret_cast<int16_t*>(smem + MidTier::O_LUT), MidTier::WLOG);
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) *next = (int)atomicAdd(&a.counters[cnt_next], 1u);
@@ -407,7 +414,7 @@ __global__ void __launch_bounds__(MidTier::THREADS, 2) area_mid_kernel(BatchArgs
       if (threadIdx.x == 0) zero_query(a, q);
       continue;
     }
-    A.ox = A.oy = c.c - (1 << (MidTier::WLOG - 1));
+    A.ox = A.oy = c.c - (1 << (MidTier::WLOG - 1)) - 16;   // the centre cell sits in the middle of tile (4,4)
     H.htag = g_tag; H.hkey = g_key;
     H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
     H.hx = a.vol.hx; H.hy = a.vol.hy;

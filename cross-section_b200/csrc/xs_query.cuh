@@ -400,10 +400,13 @@ struct Arena {
   int stack_cap;                // power of two when `spill` is set, else >= max_n
   CellT* spill;                 // global backing store for the ring, or null when stack_cap >= max_n
   uint32_t* mask;               // per-sample 27-bit candidate / kept-item masks (warp tier: aliases `bits`)
-  // byte-per-cell variant of the window (mid tier): (1<<wlog)^2 cells, local cell index u | v<<wlog.
-  // States: 0 background or visited, 1 foreground-unvisited, 2 not sampled yet, 3 foreground on the guard ring.
+  // neighbour-mask variant of the window (mid tier): (1<<wlog)^2 cells, local cell index u | v<<wlog; one byte per
+  // cell = which of its 8 neighbours are foreground and unvisited (see flood_component_nbr).
   uint8_t* cells;               // null: use the bitmap
   int wlog;
+  uint32_t* fbits;              // foreground bitmap of the window, one zero row / word of padding all round
+  int fstride;                  //   words per row = (1<<wlog)/32 + 2
+  const int16_t* nlut;          // neighbour byte -> cell-index delta of its first set bit
 };
 
 struct Ctl {          // lives in shared memory (one per group)
@@ -420,6 +423,7 @@ struct Ctl {          // lives in shared memory (one per group)
   uint32_t counter;   // generic atomic counter (path B output length)
   uint32_t item_off, poly_off;
   int tiles;          // lattice tiles sampled (1024 cells each)
+  uint32_t grow[2];   // neighbour-mask flood: tiles wanted by the closure
   long long tmark;    // phase profiling (thread 0): last timestamp and per-phase cycle counts
   uint32_t t[6];      //   0 flood (tiles + walk)  1 claims  2 emit  3 -  4 -  5 walk only
 };
@@ -494,6 +498,13 @@ XS_HD int popc8(uint32_t x) {
   return __popc(x & 0xffu);
 #else
   return __builtin_popcount(x & 0xffu);
+#endif
+}
+XS_HD int popcll64(unsigned long long x) {
+#ifdef __CUDA_ARCH__
+  return __popcll(x);
+#else
+  return __builtin_popcountll(x);
 #endif
 }
 XS_HD int ffs32(uint32_t x) {
@@ -688,42 +699,169 @@ XS_D int flood_component(const G& g, const PlaneCtx& c, const VolView& vol, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// Byte-per-cell flood (mid tier).  Same semantics as the bitmap flood above; the representation trades
-// 8x the shared memory for a much shorter dependent chain per walk step: one address add, eight
-// independent byte loads, a find-first, one byte store — and the "not sampled yet" and "guard ring"
-// conditions ride along in the cell state instead of needing coordinate checks.
+// Neighbour-mask flood (mid tier).  Same semantics as the bitmap flood above, organised so that the
+// sequential part — the depth-first walk — has the shortest dependent chain per step we know how to build:
+//   * tiles are sampled BEFORE the walk by a parallel closure over 32x32-cell tiles (a tile is sampled when a
+//     sampled foreground cell touches it), so the walk never stops to ask for cells;
+//   * every foreground cell then gets one byte M = which of its 8 neighbours are foreground-and-unvisited, bit k
+//     = k-th neighbour in the reference's priority order (+1,+1) (-1,+1) (+1,-1) (-1,-1) (0,+1) (0,-1) (+1,0) (-1,0);
+//   * a walk step is: load M[cell] -> look the byte up in a 256-entry table of cell-index deltas -> add.  Visiting
+//     a cell clears its bit in its eight neighbours' bytes with fire-and-forget atomics, one lane per neighbour;
+//   * the walk is run by one WARP in lock step (every lane holds the same state): when it hits a dead end the
+//     lanes examine 32 stack frames at once, so unwinding — half of all iterations of a one-thread walk, most of
+//     it the final unwind of a finished component — costs almost nothing.
 // ------------------------------------------------------------------------------------------------
+struct NbrLut { int16_t delta[256]; };
+// delta of the first set bit of m for a window of (1<<wlog)^2 cells (entry 0 unused)
+XS_HD int nbr_delta(uint32_t m, int wlog) {
+  const int d = ffs32(m) - 1;
+  const int du = (int)((0x2522u >> (2 * d)) & 3u) - 1;   // d:0..7 -> +1,-1,+1,-1,0,0,+1,-1
+  const int dv = (int)((0x520au >> (2 * d)) & 3u) - 1;   // d:0..7 -> +1,+1,-1,-1,+1,-1,0,0
+  return du + dv * (1 << wlog);
+}
+template <class G>
+XS_D void nbr_lut_fill(const G& g, int16_t* lut, int wlog) {
+  for (int m = g.tid(); m < 256; m += g.size()) lut[m] = (int16_t)(m ? nbr_delta((uint32_t)m, wlog) : 0);
+}
+
+template <class CellT>
+XS_HD uint32_t* frow(const Arena<CellT>& A, int v) { return A.fbits + (size_t)(v + 1) * A.fstride + 1; }
+
+// Sample the tiles in `todo` (bit = ty * nt + tx) into the foreground bitmap: a warp per lattice row, a lane per cell.
 template <class G, class CellT>
-XS_D void test_tile_bytes(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, int tx, int ty) {
-  // one 32x32 tile: a warp per row, a lane per cell
-  const int W = 1 << A.wlog;
-  for (int row = g.warp(); row < 32; row += g.nwarps()) {
-    const int v = ty * 32 + row;
+XS_D void nbr_sample_tiles(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, unsigned long long todo) {
+  const int ntl = A.wlog - 5;   // log2(tiles per side)
+  while (todo) {
 #ifdef __CUDA_ARCH__
-    {
-      const int u = tx * 32 + g.lane();
-      const bool f = cell_fg(c, vol, A.ox + u, A.oy + v);
-      const bool ring = (u == 0) | (v == 0) | (u == W - 1) | (v == W - 1);
-      A.cells[(v << A.wlog) + u] = (uint8_t)(f ? (ring ? 3 : 1) : 0);
-    }
+    const int t = __ffsll((long long)todo) - 1;
 #else
-    for (int l = 0; l < 32; l++) {
-      const int u = tx * 32 + l;
-      const bool f = cell_fg(c, vol, A.ox + u, A.oy + v);
-      const bool ring = (u == 0) | (v == 0) | (u == W - 1) | (v == W - 1);
-      A.cells[(v << A.wlog) + u] = (uint8_t)(f ? (ring ? 3 : 1) : 0);
-    }
+    const int t = __builtin_ffsll((long long)todo) - 1;
 #endif
+    todo &= todo - 1ull;
+    const int tx = t & ((1 << ntl) - 1), ty = t >> ntl;
+    for (int row = g.warp(); row < 32; row += g.nwarps()) {
+      const int v = ty * 32 + row;
+      uint32_t word;
+#ifdef __CUDA_ARCH__
+      word = __ballot_sync(0xffffffffu, cell_fg(c, vol, A.ox + tx * 32 + g.lane(), A.oy + v));
+      if (g.lane() == 0) frow(A, v)[tx] = word;
+#else
+      word = 0;
+      for (int l = 0; l < 32; l++) word |= (uint32_t)cell_fg(c, vol, A.ox + tx * 32 + l, A.oy + v) << l;
+      frow(A, v)[tx] = word;
+#endif
+    }
   }
 }
 
-// Returns ST_DONE / ST_NEED_TILE (ctl.req_*) / ST_OVERFLOW.  ctl.u holds the current cell index.
+// Which unsampled neighbours of the freshly sampled tiles `fresh` hold cells adjacent to a foreground cell?
+template <class G, class CellT>
+XS_D unsigned long long nbr_grow(const G& g, const Arena<CellT>& A, unsigned long long fresh) {
+  const int ntl = A.wlog - 5, nt = 1 << ntl;
+  unsigned long long want = 0ull;
+  int i = 0;
+  while (fresh) {
+#ifdef __CUDA_ARCH__
+    const int t = __ffsll((long long)fresh) - 1;
+#else
+    const int t = __builtin_ffsll((long long)fresh) - 1;
+#endif
+    fresh &= fresh - 1ull;
+    if ((i++ % g.nwarps()) != g.warp()) continue;
+    const int tx = t & (nt - 1), ty = t >> ntl;
+    uint32_t left, right, top, bottom;
+#ifdef __CUDA_ARCH__
+    {
+      const uint32_t w = frow(A, ty * 32 + g.lane())[tx];
+      left = __ballot_sync(0xffffffffu, w & 1u);
+      right = __ballot_sync(0xffffffffu, w >> 31);
+      top = __shfl_sync(0xffffffffu, w, 0);
+      bottom = __shfl_sync(0xffffffffu, w, 31);
+    }
+#else
+    left = right = 0u;
+    for (int l = 0; l < 32; l++) {
+      const uint32_t w = frow(A, ty * 32 + l)[tx];
+      left |= (w & 1u) << l; right |= (w >> 31) << l;
+    }
+    top = frow(A, ty * 32)[tx]; bottom = frow(A, ty * 32 + 31)[tx];
+#endif
+    const bool okl = tx > 0, okr = tx < nt - 1, okt = ty > 0, okb = ty < nt - 1;
+    if (left && okl) want |= 1ull << (t - 1);
+    if (right && okr) want |= 1ull << (t + 1);
+    if (top && okt) want |= 1ull << (t - nt);
+    if (bottom && okb) want |= 1ull << (t + nt);
+    if ((top & 1u) && okl && okt) want |= 1ull << (t - nt - 1);
+    if ((top >> 31) && okr && okt) want |= 1ull << (t - nt + 1);
+    if ((bottom & 1u) && okl && okb) want |= 1ull << (t + nt - 1);
+    if ((bottom >> 31) && okr && okb) want |= 1ull << (t + nt + 1);
+  }
+  return want;
+}
+
+// Neighbour bytes of every foreground cell of the sampled tiles `done` (cells on the window's outer ring excepted:
+// the walk stops when it steps on one).
+template <class G, class CellT>
+XS_D void nbr_masks(const G& g, const Arena<CellT>& A, unsigned long long done) {
+  const int ntl = A.wlog - 5, W = 1 << A.wlog;
+  while (done) {
+#ifdef __CUDA_ARCH__
+    const int t = __ffsll((long long)done) - 1;
+#else
+    const int t = __builtin_ffsll((long long)done) - 1;
+#endif
+    done &= done - 1ull;
+    const int tx = t & ((1 << ntl) - 1), ty = t >> ntl;
+    for (int row = g.warp(); row < 32; row += g.nwarps()) {
+      const int v = ty * 32 + row;
+      const uint32_t* rm = frow(A, v - 1) + tx;
+      const uint32_t* r0 = frow(A, v) + tx;
+      const uint32_t* rq = frow(A, v + 1) + tx;
+      const uint32_t cur = r0[0];
+      if (cur == 0u) continue;                     // warp-uniform
+      // bit (l + 1) of x?? = cell (32 tx + l) of the row; bits 0 and 33 come from the neighbouring words
+      const unsigned long long xm = ((unsigned long long)rm[0] << 1) | (rm[-1] >> 31) | ((unsigned long long)(rm[1] & 1u) << 33);
+      const unsigned long long x0 = ((unsigned long long)cur << 1) | (r0[-1] >> 31) | ((unsigned long long)(r0[1] & 1u) << 33);
+      const unsigned long long xq = ((unsigned long long)rq[0] << 1) | (rq[-1] >> 31) | ((unsigned long long)(rq[1] & 1u) << 33);
+#ifdef __CUDA_ARCH__
+      const int l = g.lane();
+      {
+#else
+      for (int l = 0; l < 32; l++) {
+#endif
+        const int u = tx * 32 + l;
+        const uint32_t am = (uint32_t)(xm >> l) & 7u, a0 = (uint32_t)(x0 >> l) & 7u, aq = (uint32_t)(xq >> l) & 7u;   // bits: u-1, u, u+1
+        if ((a0 & 2u) && u > 0 && v > 0 && u < W - 1 && v < W - 1) {
+          const uint32_t m = ((aq >> 2) & 1u) | ((aq & 1u) << 1) | (((am >> 2) & 1u) << 2) | ((am & 1u) << 3) |
+                             (((aq >> 1) & 1u) << 4) | (((am >> 1) & 1u) << 5) | (((a0 >> 2) & 1u) << 6) | ((a0 & 1u) << 7);
+          A.cells[(v << A.wlog) + u] = (uint8_t)m;
+        }
+      }
+    }
+  }
+}
+
+// Mark cell ci visited: clear its bit in the neighbour bytes of its eight neighbours (the bit a neighbour holds for
+// us is the opposite direction, k^3 for the diagonals and k^1 for the others).  Plain form, one neighbour at a time.
+XS_HD void nbr_visit_one(uint8_t* cells, int ci, int k, int wlog) {
+  const int du = (int)((0x2522u >> (2 * k)) & 3u) - 1, dv = (int)((0x520au >> (2 * k)) & 3u) - 1;
+  const int nb = ci + du + dv * (1 << wlog);
+  const int opp = k < 4 ? (k ^ 3) : (k ^ 1);
+  cells[nb] &= (uint8_t)~(1u << opp);
+}
+// Word form used by the warp walk: the three neighbours of a row are three consecutive bytes, i.e. one or two
+// aligned 32-bit words.  Lane 2r+h (r = row 0..2, h = 0/1) read-modify-writes word h of row r — six lanes, six
+// distinct words, no atomics.  `clr24` = the bits to clear in the three bytes (u-1, u, u+1) of this lane's row.
+XS_HD uint32_t nbr_row_clear(int r) { return r == 0 ? 0x021001u : (r == 1 ? 0x800040u : 0x082004u); }
+
+// The walk, plain form (host test builds; one thread).  Returns ST_DONE / ST_OVERFLOW.
 template <class CellT>
-XS_HD int dfs_run_bytes(const Arena<CellT>& A, Ctl& ctl) {
-  int n = ctl.n, depth = ctl.depth, lo = ctl.lo, ci = ctl.u;
-  const int P = 1 << A.wlog;
+XS_HD int dfs_run_nbr(const Arena<CellT>& A, int& n_io, int& depth_io, int& lo_io, int& ci_io) {
+  int n = n_io, depth = depth_io, lo = lo_io, ci = ci_io;
+  const int W = 1 << A.wlog;
   const int max_n = A.max_n;
   uint8_t* const cells = A.cells;
+  const int16_t* const lut = A.nlut;
   CellT* const stack = A.stack;
   CellT* const order = A.order;
   const bool ring = A.spill != nullptr;
@@ -731,131 +869,233 @@ XS_HD int dfs_run_bytes(const Arena<CellT>& A, Ctl& ctl) {
   const int cap = ring ? A.stack_cap : 0x7fffffff;
   int status;
   for (;;) {
-    const uint8_t* q = cells + ci;
-    // neighbours in the reference's priority order: (+1,+1) (-1,+1) (+1,-1) (-1,-1) (0,+1) (0,-1) (+1,0) (-1,0)
-    const uint32_t b0 = q[P + 1], b1 = q[P - 1], b2 = q[1 - P], b3 = q[-P - 1], b4 = q[P], b5 = q[-P], b6 = q[1], b7 = q[-1];
-    const uint32_t any = b0 | b1 | b2 | b3 | b4 | b5 | b6 | b7;
-    if (any & 2u) {
-      // a neighbour is either not sampled yet (2) or foreground on the guard ring (3)
-      const int off[8] = { P + 1, P - 1, 1 - P, -P - 1, P, -P, 1, -1 };
-      const uint32_t bb[8] = { b0, b1, b2, b3, b4, b5, b6, b7 };
-      int need = -1;
-      bool over = false;
-      for (int d = 0; d < 8; d++) {
-        if (bb[d] == 3u) over = true;
-        else if (bb[d] == 2u && need < 0) need = ci + off[d];
-      }
-      if (over) { status = ST_OVERFLOW; break; }
-      ctl.req_tx = (need & (P - 1)) >> 5; ctl.req_ty = (need >> A.wlog) >> 5;
-      status = ST_NEED_TILE;
-      break;
-    }
-    const uint32_t m = b0 | (b1 << 1) | (b2 << 2) | (b3 << 3) | (b4 << 4) | (b5 << 5) | (b6 << 6) | (b7 << 7);
+    const uint32_t m = cells[ci];
     if (m == 0u) {
+      // dead end: drop the current frame, then find the topmost frame that still has an available neighbour
+      // (examined 32 at a time, like the warp form)
       depth--;
-      if (depth == 0) { status = ST_DONE; break; }
-      if (depth - 1 < lo) {
-        int nlo = lo - A.stack_cap / 2;
-        if (nlo < 0) nlo = 0;
-#pragma unroll 1
-        for (int d = nlo; d < lo; d++) stack[d & smask] = A.spill[d];
-        lo = nlo;
+      bool found = false;
+      while (depth > 0) {
+        if (depth == lo) {
+          int nlo = lo - A.stack_cap / 2;
+          if (nlo < 0) nlo = 0;
+          for (int d = nlo; d < lo; d++) stack[d & smask] = A.spill[d];
+          lo = nlo;
+        }
+        const int avail = depth - lo;
+        const int cnt = avail < 32 ? avail : 32;
+        int l = 0;
+        for (; l < cnt; l++) {
+          const int f = (int)stack[(depth - 1 - l) & smask];
+          if (cells[f] != 0) { ci = f; found = true; break; }
+        }
+        depth -= l;
+        if (found) break;
       }
-      ci = (int)stack[(depth - 1) & smask];
+      if (!found) { status = ST_DONE; break; }
       continue;
     }
-    const int d = ffs32(m) - 1;
-    const int du = (int)((0x2522u >> (2 * d)) & 3u) - 1;   // d:0..7 -> +1,-1,+1,-1,0,0,+1,-1
-    const int dv = (int)((0x520au >> (2 * d)) & 3u) - 1;   // d:0..7 -> +1,+1,-1,-1,+1,-1,0,0
-    ci += du + (dv << A.wlog);
-    cells[ci] = 0;
-    if (n >= max_n) { status = ST_OVERFLOW; break; }
+    ci += (int)lut[m];
+    const int u = ci & (W - 1), v = ci >> A.wlog;
+    if ((u == 0) | (v == 0) | (u == W - 1) | (v == W - 1) | (n >= max_n)) { status = ST_OVERFLOW; break; }
+    for (int k = 0; k < 8; k++) nbr_visit_one(cells, ci, k, A.wlog);
     order[n++] = (CellT)ci;
     if ((m & (m - 1u)) == 0u) depth--;     // tail call: the cell we leave has nothing left, reuse its frame
     if (depth - lo == cap) {
       const int nlo = lo + A.stack_cap / 2;
-#pragma unroll 1
       for (int dd = lo; dd < nlo; dd++) A.spill[dd] = stack[dd & smask];
       lo = nlo;
     }
     stack[depth & smask] = (CellT)ci;
     depth++;
   }
-  ctl.n = n; ctl.depth = depth; ctl.lo = lo; ctl.u = ci;
+  n_io = n; depth_io = depth; lo_io = lo; ci_io = ci;
   return status;
 }
 
-template <class G, class CellT>
-XS_D int flood_component_bytes(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, Ctl& ctl, bool* empty) {
+#ifdef __CUDACC__
+// Round trip through a per-lane shared-memory slot with volatile accesses: a value neither nvvm nor ptxas can
+// re-derive, so it stays in its register.  `slots` = 32 words of scratch, all 32 lanes call.
+__device__ __forceinline__ uint32_t pin_u32(uint32_t x, volatile uint32_t* slots) {
+  slots[threadIdx.x & 31] = x;
+  return slots[threadIdx.x & 31];
+}
+// Shared-memory accessors with explicit 32-bit shared addresses: no generic-address arithmetic on the walk's
+// dependent chain, and (asm volatile + memory clobber) exactly the program order written below.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) { uint32_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ int lds_s16(uint32_t a) { int v; asm volatile("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+// The walk, warp form: called by every lane of ONE warp, all lanes in lock step (they all hold the same state).
+// cells / lut / stack ring must be in SHARED memory; order and spill in global memory; cells are uint16 indices.
+// Per forward step the dependent chain is: neighbour byte -> delta table -> add -> neighbour byte of the new cell,
+// i.e. two shared-memory loads and one add.  The byte of the cell we arrive at is loaded BEFORE that cell is marked
+// visited (marking only rewrites its neighbours' bytes): three rows of three consecutive bytes = at most two
+// aligned words per row, read-modify-written by lanes 2r+h (the other lanes duplicate them: same value, same word).
+// A dead end examines 32 stack frames at once.
+__device__ __forceinline__ int dfs_run_nbr_warp(const Arena<uint16_t>& A, int& n_io, int& depth_io, int& lo_io, int& ci_io, int lane, uint32_t* scratch32) {
+  int n = n_io, depth = depth_io, lo = lo_io, ci = ci_io;
   const int W = 1 << A.wlog;
+  const int max_n = A.max_n;
+  // loop invariants are pinned in registers (opaque moves): ptxas otherwise re-derives them — special-register reads
+  // and the lane arithmetic included — inside the loop, on the dependent chain
+  const uint32_t s_cells = pin_u32((uint32_t)__cvta_generic_to_shared(A.cells), scratch32);
+  const uint32_t s_lut = pin_u32((uint32_t)__cvta_generic_to_shared(A.nlut), scratch32);
+  const uint32_t s_stack = pin_u32((uint32_t)__cvta_generic_to_shared(A.stack), scratch32);
+  uint16_t* const order = A.order;
+  uint16_t* const spill = A.spill;
+  const bool ring = spill != nullptr;
+  const int smask = ring ? (A.stack_cap - 1) : 0x7fffffff;
+  const int cap = ring ? A.stack_cap : 0x7fffffff;
+  const int half = A.stack_cap / 2;
+  const int l6 = lane % 6;
+  const int vr = l6 >> 1;
+  const uint32_t vh4 = pin_u32(4u * (uint32_t)(l6 & 1), scratch32), vh32 = pin_u32(32u * (uint32_t)(l6 & 1), scratch32);
+  const uint32_t vsel = pin_u32(s_cells + (uint32_t)((vr - 1) * W - 1), scratch32);   // + ci = address of the first of this lane's three cells
+  const uint32_t vclr = pin_u32(nbr_row_clear(vr), scratch32);
+  const uint32_t lim = (uint32_t)(W - 2);
+  const bool lane0 = pin_u32((uint32_t)lane, scratch32) == 0u;
+  int status;
+  uint32_t m = lds_u8(s_cells + (uint32_t)ci);
+  for (;;) {
+    while (m != 0u) {
+      ci += lds_s16(s_lut + 2u * m);
+      const uint32_t m_next = lds_u8(s_cells + (uint32_t)ci);     // loads first (in range: the arrays are padded by a row) ...
+      const uint32_t vb = vsel + (uint32_t)ci;
+      const uint32_t va = (vb & ~3u) + vh4;
+      const uint32_t vold = lds_u32(va);
+      if ((m & (m - 1u)) == 0u) depth--;                           // tail call: the cell we leave has nothing left, reuse its frame
+      const uint32_t u = (uint32_t)ci & (uint32_t)(W - 1), v = (uint32_t)ci >> A.wlog;
+      if (((u - 1u) >= lim) | ((v - 1u) >= lim) | (n >= max_n) | (depth - lo == cap)) {   // ... rare cases after
+        if (((u - 1u) >= lim) | ((v - 1u) >= lim) | (n >= max_n)) { status = ST_OVERFLOW; goto out; }
+        // ring full: spill the lower half
+        const int nlo = lo + half;
+        for (int dd = lo + lane; dd < nlo; dd += 32) spill[dd] = (uint16_t)lds_u16(s_stack + 2u * (uint32_t)(dd & smask));
+        __syncwarp();
+        lo = nlo;
+      }
+      const unsigned long long c64 = (unsigned long long)vclr << (8u * (vb & 3u));
+      sts_u32(va, vold & ~(uint32_t)(c64 >> vh32));
+      if (lane0) {
+        order[n] = (uint16_t)ci;
+        sts_u16(s_stack + 2u * (uint32_t)(depth & smask), (uint32_t)ci);
+      }
+      n++;
+      depth++;
+      m = m_next;
+    }
+    // dead end: drop the current frame, then find the topmost frame that still has an available neighbour
+    __syncwarp();
+    depth--;
+    bool found = false;
+    while (depth > 0) {
+      if (depth == lo) {
+        // (ring only) refill the lower half of the ring from the global spill area
+        int nlo = lo - half;
+        if (nlo < 0) nlo = 0;
+        for (int d = nlo + lane; d < lo; d += 32) sts_u16(s_stack + 2u * (uint32_t)(d & smask), (uint32_t)spill[d]);
+        __syncwarp();
+        lo = nlo;
+      }
+      const int avail = depth - lo;
+      const int cnt = avail < 32 ? avail : 32;
+      uint32_t f = 0u, fm = 0u;
+      if (lane < cnt) { f = lds_u16(s_stack + 2u * (uint32_t)((depth - 1 - lane) & smask)); fm = lds_u8(s_cells + f); }
+      const uint32_t ball = __ballot_sync(0xffffffffu, fm != 0u);
+      if (ball) {
+        const int l = __ffs(ball) - 1;
+        depth -= l;
+        ci = (int)__shfl_sync(0xffffffffu, f, l);
+        m = __shfl_sync(0xffffffffu, fm, l);
+        found = true;
+        break;
+      }
+      depth -= cnt;
+    }
+    if (!found) { status = ST_DONE; break; }
+  }
+out:
+  n_io = n; depth_io = depth; lo_io = lo; ci_io = ci;
+  return status;
+}
+#endif
+
+template <class G, class CellT>
+XS_D int flood_component_nbr(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, Ctl& ctl, bool* empty) {
+  const int W = 1 << A.wlog, ntl = A.wlog - 5, nt = 1 << ntl;
   {
-    uint32_t* w32 = reinterpret_cast<uint32_t*>(A.cells);
-    const int words = (W * W) >> 2;
-    for (int i = g.tid(); i < words; i += g.size()) w32[i] = 0x02020202u;
+    const int words = (W + 2) * A.fstride;
+    for (int i = g.tid(); i < words; i += g.size()) A.fbits[i] = 0u;
   }
   const int cu = c.c - A.ox, cv = c.c - A.oy;
   if (g.tid() == 0) {
-    ctl.status = ST_NEED_TILE; ctl.req_tx = cu >> 5; ctl.req_ty = cv >> 5;
+    ctl.status = ST_DONE; ctl.req_tx = 0; ctl.req_ty = 0;
     ctl.n = 0; ctl.depth = 0; ctl.lo = 0; ctl.u = cu + (cv << A.wlog); ctl.v = 0; ctl.m = 0; ctl.npoly = 0; ctl.overflow = 0; ctl.contact = 0u; ctl.counter = 0u; ctl.tiles = 0;
     ctl.item_off = 0u; ctl.poly_off = 0u;
+    ctl.grow[0] = ctl.grow[1] = 0u;
     for (int i = 0; i < 6; i++) ctl.t[i] = 0u;
     ctl.tmark = xs_clock();
   }
   g.sync();
   *empty = false;
-  bool first = true;
-  const int nt = W >> 5;
-  for (;;) {
-    const int rtx = ctl.req_tx, rty = ctl.req_ty;
-    g.sync();
-    // sample the requested tile and (halo) its unsampled neighbours.  Every thread takes the same decisions
-    // from the same snapshot (no cell is written between the sync above and the one below).
-    uint32_t todo = 0u;
-    {
-      int idx = 0;
-      for (int ty = rty - A.halo; ty <= rty + A.halo; ty++)
-        for (int tx = rtx - A.halo; tx <= rtx + A.halo; tx++, idx++) {
-          if (tx < 0 || ty < 0 || tx >= nt || ty >= nt) continue;
-          if (A.cells[((ty * 32) << A.wlog) + tx * 32 + 1] == 2) todo |= 1u << idx;   // tiles are sampled whole
-        }
-    }
-    g.sync();
-    {
-      int idx = 0;
-      for (int ty = rty - A.halo; ty <= rty + A.halo; ty++)
-        for (int tx = rtx - A.halo; tx <= rtx + A.halo; tx++, idx++) {
-          if (!((todo >> idx) & 1u)) continue;
-          test_tile_bytes(g, c, vol, A, tx, ty);
-          if (g.tid() == 0) ctl.tiles++;
-        }
-    }
-    g.sync();
-    if (g.tid() == 0) {
-      int st;
-      const long long w0 = xs_clock();
-      if (first) {
-        uint8_t* cc = A.cells + ctl.u;
-        if (*cc != 1) {
-          st = ST_DONE; ctl.n = 0;
-        } else {
-          *cc = 0;
-          A.order[0] = (CellT)ctl.u; A.stack[0] = (CellT)ctl.u;
-          ctl.n = 1; ctl.depth = 1;
-          st = dfs_run_bytes(A, ctl);
-        }
-      } else {
-        st = dfs_run_bytes(A, ctl);
-      }
-      ctl.t[5] += (uint32_t)(xs_clock() - w0);
-      ctl.status = st;
-    }
-    first = false;
-    g.sync();
-    const int st = ctl.status;
-    if (st == ST_NEED_TILE) continue;
-    if (st == ST_OVERFLOW) return Q_OVERFLOW;
-    break;
+  // closure over tiles, starting from the 3x3 tiles around the centre cell's tile
+  unsigned long long done = 0ull, todo = 0ull;
+  {
+    const int ctx = cu >> 5, cty = cv >> 5;
+    for (int ty = cty - 1; ty <= cty + 1; ty++)
+      for (int tx = ctx - 1; tx <= ctx + 1; tx++)
+        if (tx >= 0 && ty >= 0 && tx < nt && ty < nt) todo |= 1ull << (ty * nt + tx);
   }
+  while (todo) {
+    nbr_sample_tiles(g, c, vol, A, todo);
+    done |= todo;
+    g.sync();
+    const unsigned long long want = nbr_grow(g, A, todo) & ~done;
+    if (want && g.lane() == 0) {
+      atomic_or_u32(&ctl.grow[0], (uint32_t)want);
+      atomic_or_u32(&ctl.grow[1], (uint32_t)(want >> 32));
+    }
+    g.sync();
+    todo = ((unsigned long long)ctl.grow[0] | ((unsigned long long)ctl.grow[1] << 32)) & ~done;   // next write: after the next sync
+  }
+  nbr_masks(g, A, done);
+  g.sync();
+  if (g.warp() == 0) {
+    const long long w0 = xs_clock();
+    int st;
+    const int ci0 = ctl.u;
+    if (!((frow(A, cv)[cu >> 5] >> (cu & 31)) & 1u)) {
+      st = ST_DONE;
+      if (g.lane() == 0) ctl.n = 0;
+    } else {
+      g.converge();
+      if (g.lane() == 0) { A.order[0] = (CellT)ci0; A.stack[0] = (CellT)ci0; }
+      if (g.lane() == 0)
+        for (int k = 0; k < 8; k++) nbr_visit_one(A.cells, ci0, k, A.wlog);
+      g.converge();
+      int n = 1, depth = 1, lo = 0, ci = ci0;
+#ifdef __CUDA_ARCH__
+      if constexpr (sizeof(CellT) == 2) {
+        st = dfs_run_nbr_warp(A, n, depth, lo, ci, g.lane(), A.fbits);   // (the foreground bitmap is dead: 32 words of scratch)
+      } else {
+        st = ST_OVERFLOW;   // the neighbour-mask flood is only instantiated for 16-bit cells on the device
+      }
+#else
+      st = dfs_run_nbr(A, n, depth, lo, ci);
+#endif
+      if (g.lane() == 0) { ctl.n = n; ctl.depth = depth; ctl.lo = lo; ctl.u = ci; }
+    }
+    if (g.lane() == 0) {
+      ctl.status = st;
+      ctl.tiles = popcll64(done);
+      ctl.t[5] += (uint32_t)(xs_clock() - w0);
+    }
+  }
+  g.sync();
+  if (ctl.status == ST_OVERFLOW) return Q_OVERFLOW;
   *empty = (ctl.n == 0);
   return Q_OK;
 }
@@ -1068,7 +1308,7 @@ template <class G, class CellT, class H>
 XS_D int run_area_emit(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, H& hash, Ctl& ctl,
                        uint32_t q, const EmitOut& out) {
   bool empty;
-  const int fst = A.cells ? flood_component_bytes(g, c, vol, A, ctl, &empty) : flood_component(g, c, vol, A, ctl, &empty);
+  const int fst = A.cells ? flood_component_nbr(g, c, vol, A, ctl, &empty) : flood_component(g, c, vol, A, ctl, &empty);
   if (fst != Q_OK) return Q_OVERFLOW;
   if (g.tid() == 0) prof_mark(ctl, 0);
   if (empty) {

@@ -41,6 +41,36 @@ def test_area_neurite_tiers(hostsim, oracle):
   assert np.array_equal(bits(a[:200]), bits(a3)) and np.array_equal(c[:200], c3)
 
 
+def test_area_long_sections_mid_tier(hostsim, oracle):
+  """Neighbour-mask flood (mode 3): sections long enough to grow the sampled tile set beyond the initial 3x3
+  tiles, bent tubes with side branches touching tile borders, and sections that leave the 256-cell window."""
+  rng = np.random.default_rng(77)
+  N = 160
+  g = np.stack(np.meshgrid(*[np.arange(N, dtype=np.float32)] * 3, indexing="ij"), -1)
+  grown = 0
+  for it in range(6):
+    c0 = rng.uniform(60, 100, size=3).astype(np.float32)
+    d = rng.normal(size=3).astype(np.float32); d /= np.linalg.norm(d)
+    r = rng.uniform(3, 7)
+    rel = g - c0
+    t = rel @ d
+    dist2 = (rel ** 2).sum(-1) - t ** 2
+    vol = dist2 <= r * r
+    vol ^= (rng.random(vol.shape) < 0.02) & (dist2 <= (r + 2) ** 2)       # ragged surface, small holes
+    vol[int(c0[0]), int(c0[1]), int(c0[2])] = True
+    e = np.cross(d, rng.normal(size=3)).astype(np.float32); e /= np.linalg.norm(e)
+    qp, qn = [], []
+    for k in range(4):
+      qp.append(np.floor(c0)); qn.append(e + rng.uniform(0.0, 0.12) * d)   # plane (almost) contains the tube axis
+    qp = np.array(qp, np.float32); qn = np.array(qn, np.float32)
+    vol = np.asfortranarray(vol)
+    a, c = oracle.area_batch(vol, qp, qn, [32, 32, 40])
+    a3, c3, st = hostsim.area_batch(vol, qp, qn, [32, 32, 40], 3)
+    assert np.array_equal(bits(a), bits(a3)) and np.array_equal(c, c3), it
+    grown += int(st[1] > 4 * 600)
+  assert grown > 0, "expected sections larger than the initial 96x96-cell tile set"
+
+
 def test_section_random(hostsim, oracle):
   rng = np.random.default_rng(4321)
   for it in range(150):
