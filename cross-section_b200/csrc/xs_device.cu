@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -171,8 +172,13 @@ struct BatchArgs {
   unsigned long long* stats; // [0] samples [1] items [2] tiles, [4..9] warp-tier phase cycles, [10..15] CTA-tier phase cycles
   uint32_t* list_in;         // queries to process (null: 0..nq-1)
   uint32_t* list_out;        // queries this tier could not fit
+  uint32_t* late;            // mid tier: queries the warp tier hands over while both run (tail = counters[CNT_OVER0])
 };
-enum { CNT_NEXT0 = 0, CNT_OVER0 = 1, CNT_NEXT1 = 2, CNT_OVER1 = 3, CNT_NEXT2 = 4, CNT_OVER2 = 5, CNT_NEXT3 = 6, CNT_OVER3 = 7, CNT_WORDS = 8 };
+enum { CNT_NEXT0 = 0, CNT_OVER0 = 1, CNT_NEXT1 = 2, CNT_OVER1 = 3, CNT_NEXT2 = 4, CNT_OVER2 = 5, CNT_NEXT3 = 6, CNT_OVER3 = 7, CNT_WORDS = 8,
+       CNT_NBIG = 48,                  // queries routed straight to the mid tier = prefix of the size-ordered list
+       CNT_HIST = 128, CNT_CURSOR = 384, CNT_TOTAL_WORDS = 640 };
+#define XS_LATE_EMPTY 0xffffffffu
+#define XS_LATE_CLAIMED 0xfffffffeu
 
 __device__ __forceinline__ void finish_query(const BatchArgs& a, const Ctl& ctl, uint32_t q, int st, int cnt_over, int stats_base) {
   // thread 0 of the group
@@ -188,16 +194,17 @@ __device__ __forceinline__ void finish_query(const BatchArgs& a, const Ctl& ctl,
   } else {
     QInfo qi; qi.item_off = 0; qi.n_items = 0; qi.contact = 0; qi.status = QS_PENDING;
     a.out.qinfo[q] = qi;
+    __threadfence();   // the next tier may pick the query up (and write qinfo[q]) while this kernel is still running
     if (st == Q_OVERFLOW) a.list_out[atomicAdd(&a.counters[cnt_over], 1u)] = q;   // Q_CAPACITY: the host re-runs the batch
   }
 }
 __device__ __forceinline__ void zero_query(const BatchArgs& a, uint32_t q) {
-  QInfo qi; qi.item_off = 0; qi.n_items = 0; qi.contact = 0; qi.status = QS_READY;
+  QInfo qi; qi.item_off = 0; qi.n_items = 0; qi.contact = 0; qi.status = a.out.ready;
   a.out.qinfo[q] = qi;
 }
 
 template <int WARPS, int TILES, int MAXN, int HCAP>
-__global__ void __launch_bounds__(WARPS * 32, 2) area_warp_kernel(BatchArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, 3) area_warp_kernel(BatchArgs a) {
   using L = WarpLayout<TILES, MAXN, HCAP>;
   extern __shared__ __align__(16) uint32_t smem[];
   uint32_t* base = smem + (threadIdx.x >> 5) * L::WORDS;
@@ -216,11 +223,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2) area_warp_kernel(BatchArgs a) {
   Ctl& ctl = *reinterpret_cast<Ctl*>(base + L::O_CTL);
   WarpGroup g;
   const V3 w = mk(a.wx, a.wy, a.wz);
+  // size-ordered list (largest estimated section first); its first counters[CNT_NBIG] entries belong to the mid tier
+  const uint32_t first = a.list_in ? a.counters[CNT_NBIG] : 0u;
   for (;;) {
     uint32_t q = 0;
-    if (g.lane() == 0) q = atomicAdd(&a.counters[CNT_NEXT0], 1u);
+    if (g.lane() == 0) q = first + atomicAdd(&a.counters[CNT_NEXT0], 1u);
     q = __shfl_sync(0xffffffffu, q, 0);
     if (q >= a.nq) break;
+    if (a.list_in) q = a.list_in[q];
     PlaneCtx c;
     const V3 p = mk(__ldg(a.pos + 3 * q), __ldg(a.pos + 3 * q + 1), __ldg(a.pos + 3 * q + 2));
     const V3 n = mk(__ldg(a.nrm + 3 * q), __ldg(a.nrm + 3 * q + 1), __ldg(a.nrm + 3 * q + 2));
@@ -362,7 +372,8 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_BLOCKS) area_block_kernel(B
 struct MidTier {
   static constexpr int THREADS = 256;
   static constexpr int WLOG = 8;                   // 256 x 256 cells; uint16 cell index u | v<<8
-  static constexpr int RING = 4096;                // DFS stack ring entries (uint16) in shared memory
+  static constexpr int RING = 1024;                // DFS stack ring entries (uint16) in shared memory (77.5 KB in all: one
+                                                   //   mid-tier CTA fits beside two warp-tier CTAs on an SM)
   static constexpr int O_CTL = 64;
   static constexpr int O_RING = O_CTL + 48;
   static constexpr int O_LUT = O_RING + RING / 2;  // 256 x int16
@@ -377,13 +388,14 @@ __host__ __device__ inline size_t mid_slab_bytes(const SlabCfg& s) {
   return ((bytes + 255) / 256) * 256;
 }
 
-__global__ void __launch_bounds__(MidTier::THREADS, 2) area_mid_kernel(BatchArgs a, SlabCfg s, int cnt_next, int cnt_over, const uint32_t* count_ptr, int stats_base) {
+__global__ void __maxnreg__(96) area_mid_kernel(BatchArgs a, SlabCfg s, int cnt_next, int cnt_over, int stats_base) {
   extern __shared__ __align__(16) uint32_t smem[];
   BlockGroup g(reinterpret_cast<int*>(smem));
   Ctl& ctl = *reinterpret_cast<Ctl*>(smem + MidTier::O_CTL);
   int* next = reinterpret_cast<int*>(smem + MidTier::O_CTL + 42);
   const V3 w = mk(a.wx, a.wy, a.wz);
-  const uint32_t count = count_ptr ? *count_ptr : a.nq;
+  const uint32_t n_big = a.counters[CNT_NBIG];
+  uint32_t late_hint = 0u;
   // per-CTA slab in HBM: order (u16), kept masks (u32), stack spill (u16), first-touch table
   char* slab = s.base + (size_t)blockIdx.x * s.stride;
   Arena<uint16_t> A;
@@ -402,11 +414,29 @@ __global__ void __launch_bounds__(MidTier::THREADS, 2) area_mid_kernel(BatchArgs
   nbr_lut_fill(g, reinterpret_cast<int16_t*>(smem + MidTier::O_LUT), MidTier::WLOG);
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) *next = (int)atomicAdd(&a.counters[cnt_next], 1u);
+    if (threadIdx.x == 0) {
+      // 1. the queries classified as large: the first n_big entries of the size-ordered list, largest first
+      // 2. then whatever the warp tier has handed over SO FAR (it may still be running: this kernel never waits for
+      //    it — a later launch of the same kernel, after the warp tier, takes the stragglers).  An entry is claimed by
+      //    swapping it for XS_LATE_CLAIMED.
+      uint32_t q = XS_LATE_EMPTY;
+      if (a.counters[cnt_next] < n_big) {
+        const uint32_t i = atomicAdd(&a.counters[cnt_next], 1u);
+        if (i < n_big) q = a.list_in[i];
+      }
+      if (q == XS_LATE_EMPTY) {
+        const uint32_t tail = *reinterpret_cast<volatile uint32_t*>(&a.counters[CNT_OVER0]);
+        for (uint32_t j = late_hint; j < tail; j++) {
+          const uint32_t e = *reinterpret_cast<volatile uint32_t*>(&a.late[j]);
+          if (e >= XS_LATE_CLAIMED) continue;
+          if (atomicCAS(&a.late[j], e, XS_LATE_CLAIMED) == e) { q = e; late_hint = j + 1; break; }
+        }
+      }
+      *next = (int)q;
+    }
     __syncthreads();
-    const uint32_t i = (uint32_t)*next;
-    if (i >= count) break;
-    const uint32_t q = a.list_in ? a.list_in[i] : i;
+    const uint32_t q = (uint32_t)*next;
+    if (q == XS_LATE_EMPTY) break;
     PlaneCtx c;
     const V3 p = mk(__ldg(a.pos + 3 * q), __ldg(a.pos + 3 * q + 1), __ldg(a.pos + 3 * q + 2));
     const V3 n = mk(__ldg(a.nrm + 3 * q), __ldg(a.nrm + 3 * q + 1), __ldg(a.nrm + 3 * q + 2));
@@ -469,12 +499,12 @@ __global__ void __launch_bounds__(256) poly_eval_kernel(const PolyRec* __restric
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) combine_kernel(const ItemRec* __restrict__ items, float* __restrict__ vals, const QInfo* __restrict__ qinfo,
                                                       const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count, uint32_t nq,
-                                                      float* __restrict__ area, uint8_t* __restrict__ contact) {
+                                                      float* __restrict__ area, uint8_t* __restrict__ contact, uint32_t want_status) {
   const uint32_t count = list ? *list_count : nq;
   for (uint32_t i = blockIdx.x; i < count; i += gridDim.x) {
     const uint32_t q = list ? list[i] : i;
     const QInfo qi = qinfo[q];
-    if (qi.status != QS_READY) continue;
+    if (qi.status != want_status) continue;     // pending, or owned by the other pipeline
     const ItemRec* it = items + qi.item_off;
     const uint32_t n = qi.n_items;
     for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
@@ -504,22 +534,56 @@ __global__ void __launch_bounds__(128) combine_kernel(const ItemRec* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------
-// classification pre-pass: foreground count of the 32x32 lattice tile around each query's centre cell.
-// Large sections fill that tile; routing them to the mid tier up front lets both tiers start at t = 0.
+// pre-pass: a cheap size estimate per query -> queries ordered largest first.
+// classify_kernel: one warp per query probes the lattice on a 16x16 grid of stride 4 around the centre cell (256
+//   probes, 8 per lane); key = number of foreground probes (each stands for 16 cells), clamped to 255, 0 for queries
+//   the reference answers with zeros.  Keys are histogrammed.
+// order_kernel: counting sort by descending key (order inside a key is arbitrary).  Queries with key >= T go straight
+//   to the mid tier, which therefore starts at t = 0 beside the warp tier; the warp tier takes the rest largest first
+//   (longest-processing-time-first keeps the tail of its persistent warps short).  The estimate only steers
+//   scheduling: a query the warp tier cannot fit is still handed over, and every tier computes the same bits.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) classify_kernel(VolView vol, const float* __restrict__ pos, const float* __restrict__ nrm,
-                                                       float wx, float wy, float wz, uint32_t nq, uint16_t* __restrict__ popc) {
+                                                       float wx, float wy, float wz, uint32_t nq, uint8_t* __restrict__ key,
+                                                       uint32_t* __restrict__ hist, uint32_t* __restrict__ late, QInfo* __restrict__ qinfo) {
   const int lane = threadIdx.x & 31;
   for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += (gridDim.x * blockDim.x) >> 5) {
     PlaneCtx c;
     const V3 p = mk(__ldg(pos + 3 * q), __ldg(pos + 3 * q + 1), __ldg(pos + 3 * q + 2));
     const V3 n = mk(__ldg(nrm + 3 * q), __ldg(nrm + 3 * q + 1), __ldg(nrm + 3 * q + 2));
     int cnt = 0;
-    if (plane_init(c, vol, p, n, mk(wx, wy, wz))) {
-      for (int row = 0; row < 32; row++) cnt += cell_fg(c, vol, c.c - 16 + lane, c.c - 16 + row) ? 1 : 0;
+    const bool ok = plane_init(c, vol, p, n, mk(wx, wy, wz));
+    if (ok) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) {
+        const int pi = lane * 8 + k;
+        cnt += cell_fg(c, vol, c.c + ((pi & 15) - 8) * 4 + 2, c.c + ((pi >> 4) - 8) * 4 + 2) ? 1 : 0;
+      }
     }
     cnt = __reduce_add_sync(0xffffffffu, cnt);
-    if (lane == 0) popc[q] = (uint16_t)cnt;
+    if (lane == 0) {
+      const uint32_t k = ok ? (uint32_t)(cnt < 1 ? 1 : (cnt > 255 ? 255 : cnt)) : 0u;
+      key[q] = (uint8_t)k;
+      atomicAdd(&hist[k], 1u);
+      late[q] = XS_LATE_EMPTY;
+      qinfo[q].status = QS_PENDING;   // (a stale READY from the previous batch would let the wrong pipeline's combine kernel write area[q])
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) order_kernel(const uint8_t* __restrict__ key, const uint32_t* __restrict__ hist, uint32_t* __restrict__ cursor,
+                                                    uint32_t* __restrict__ sorted, uint32_t nq, uint32_t* __restrict__ n_big, int big_key) {
+  __shared__ uint32_t start[256];
+  {
+    uint32_t s = 0;
+    for (int j = threadIdx.x + 1; j < 256; j++) s += hist[j];   // queries with a larger key come first
+    start[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_big = start[big_key - 1];
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
+    const uint32_t k = key[q];
+    sorted[start[k] + atomicAdd(&cursor[k], 1u)] = q;
   }
 }
 
@@ -542,7 +606,9 @@ struct DevBuf {
 };
 
 // warp tier configuration (shared memory per warp = WarpLayout::WORDS * 4 bytes)
-constexpr int T0_WARPS = 15, T0_TILES = 3, T0_MAXN = 384, T0_HCAP = 1024;   // 2 CTAs per SM -> 30 warps per SM
+constexpr int T0_WARPS = 10, T0_TILES = 3, T0_MAXN = 384, T0_HCAP = 1024;   // 3 CTAs per SM -> 30 warps per SM (2 beside a mid-tier CTA)
+constexpr int T0_CTAS_PER_SM = 3;
+constexpr int MID_BIG_KEY = 22;   // >= 22 of 256 probes foreground (~350 cells): the section will not fit a warp (T0_MAXN)
 using T0Layout = WarpLayout<T0_TILES, T0_MAXN, T0_HCAP>;
 #define T0_KERNEL area_warp_kernel<T0_WARPS, T0_TILES, T0_MAXN, T0_HCAP>
 
@@ -558,9 +624,16 @@ struct xs3d_volume {
   bool labels_loaded = false;
   // batch workspace
   DevBuf q_pos, q_nrm, q_area, q_contact, lists, counters, slab1, slab2, sec_idx, sec_val, misc;
-  DevBuf polys, items, vals, geom, qinfo, slab_mid;
+  DevBuf polys, items, vals, geom, qinfo, slab_mid, keys;
+  DevBuf polys2, items2, vals2;                        // record buffers of the second (mid / big tier) pipeline
+  uint64_t poly_cap2 = 0, item_cap2 = 0;
+  cudaEvent_t evb[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // batch timing, launching stream
+  cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};            // batch timing, second stream
+  cudaStream_t stream2 = nullptr;                      // the mid tier runs here, beside the warp tier
+  cudaEvent_t evf[3] = {nullptr, nullptr, nullptr};    // fork, warp tier done, second stream done
   SlabCfg cfg_mid{};
   int mid_ctas = 0;
+  int mid_key = 0;
   uint64_t poly_cap = 0, item_cap = 0;
   SlabCfg cfg1{}, cfg2{};
   uint32_t* h_counters = nullptr;   // pinned: CNT_WORDS counters + 8 u64 stats
@@ -571,7 +644,7 @@ struct xs3d_volume {
   bool kernels_configured = false;
   bool own_stream = true;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  float timing[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // ms: warp / mid / big / worst-case query kernels, ingest, polygon, combine, spare
+  float timing[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // ms, see xs3d_volume_timing
 };
 
 static VolView view_of(const xs3d_volume* v) {
@@ -614,7 +687,11 @@ extern "C" int xs3d_volume_create(int device, uint64_t sx, uint64_t sy, uint64_t
   v->sm_count = prop.multiProcessorCount;
   v->smem_optin = (int)prop.sharedMemPerBlockOptin;
   CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&v->stream2, cudaStreamNonBlocking));
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&v->ev[i]));
+  for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&v->evf[i], cudaEventDisableTiming));
+  for (int i = 0; i < 6; i++) CK(cudaEventCreate(&v->evb[i]));
+  for (int i = 0; i < 5; i++) CK(cudaEventCreate(&v->evs[i]));
   RET(v->cubes.ensure(hx * hy * hz + 64));
   CK(cudaHostAlloc((void**)&v->h_counters, 512, cudaHostAllocDefault));
   *out = v;
@@ -625,10 +702,14 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
   if (!v) return XS3D_OK;
   cudaSetDevice(v->device);
   if (v->stream) { cudaStreamSynchronize(v->stream); if (v->own_stream) cudaStreamDestroy(v->stream); }
+  if (v->stream2) { cudaStreamSynchronize(v->stream2); cudaStreamDestroy(v->stream2); }
   for (int i = 0; i < 8; i++) if (v->ev[i]) cudaEventDestroy(v->ev[i]);
+  for (int i = 0; i < 3; i++) if (v->evf[i]) cudaEventDestroy(v->evf[i]);
+  for (int i = 0; i < 6; i++) if (v->evb[i]) cudaEventDestroy(v->evb[i]);
+  for (int i = 0; i < 5; i++) if (v->evs[i]) cudaEventDestroy(v->evs[i]);
   DevBuf* bufs[] = { &v->cubes, &v->raw, &v->labels, &v->q_pos, &v->q_nrm, &v->q_area, &v->q_contact, &v->lists,
                      &v->counters, &v->slab1, &v->slab2, &v->sec_idx, &v->sec_val, &v->misc,
-                     &v->polys, &v->items, &v->vals, &v->geom, &v->qinfo, &v->slab_mid };
+                     &v->polys, &v->items, &v->vals, &v->geom, &v->qinfo, &v->slab_mid, &v->keys, &v->polys2, &v->items2, &v->vals2 };
   for (DevBuf* b : bufs) b->release();
   if (v->h_counters) cudaFreeHost(v->h_counters);
   delete v;
@@ -764,13 +845,16 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
   RET(v->q_nrm.ensure(n * 12 + 64));
   RET(v->q_area.ensure(n * 4 + 64));
   RET(v->q_contact.ensure(n + 64));
-  RET(v->lists.ensure(n * 4 * 4 + 64));
-  RET(v->counters.ensure(512));
+  RET(v->lists.ensure(n * 5 * 4 + 64));
+  RET(v->keys.ensure(n + 64));
+  RET(v->counters.ensure(CNT_TOTAL_WORDS * 4));
   if (!v->slab_mid.p) {
     SlabCfg m{};
     m.max_n = 1 << 14; m.hcap_max = 1u << 17; m.bits_words = 0; m.tested_words = 0; m.hash_factor = 8; m.max_probe = 256;
     m.stride = mid_slab_bytes(m);
-    v->mid_ctas = v->sm_count * 2;
+    v->mid_ctas = v->sm_count;
+    if (const char* e = getenv("XS3D_MID_CTAS")) v->mid_ctas = std::max(1, atoi(e));          // tuning knobs (dev)
+    if (const char* e = getenv("XS3D_MID_KEY")) v->mid_key = std::min(255, std::max(1, atoi(e)));
     RET(v->slab_mid.ensure(m.stride * (size_t)v->mid_ctas));
     m.base = (char*)v->slab_mid.p;
     v->cfg_mid = m;
@@ -785,6 +869,13 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
   RET(v->polys.ensure(v->poly_cap * sizeof(PolyRec) + 64));
   RET(v->vals.ensure(v->poly_cap * 4 + 64));
   RET(v->items.ensure(v->item_cap * sizeof(ItemRec) + 64));
+  if (v->poly_cap2 == 0) {
+    v->poly_cap2 = std::min<uint64_t>(std::max<uint64_t>(1ull << 19, n * 128ull), 1ull << 26);
+    v->item_cap2 = v->poly_cap2 / 2;
+  }
+  RET(v->polys2.ensure(v->poly_cap2 * sizeof(PolyRec) + 64));
+  RET(v->vals2.ensure(v->poly_cap2 * 4 + 64));
+  RET(v->items2.ensure(v->item_cap2 * sizeof(ItemRec) + 64));
   if (!v->slab1.p) {
     v->cfg1 = make_cfg(v, false);
     v->cfg1.stride = slab_bytes(v->cfg1);
@@ -803,110 +894,166 @@ static int ensure_worst_case_slab(xs3d_volume* v) {
   return XS3D_OK;
 }
 
-// Core of the batched area path; all pointers are device pointers.  Launch sequence (no host synchronisation
-// in between): warp-tier query kernel -> mid-tier -> big-tier (each consumes what the previous tier could not
-// fit) -> polygon kernel -> combine kernel; then one sync to read the counters.  Rare paths after that sync:
-// queries that overflowed the big tier's slab re-run with the worst-case slab; a full record buffer grows and
-// the batch re-runs.  tiny batches skip the warp and mid tiers.
+// Core of the batched area path; all pointers are device pointers.  Two independent pipelines, no host
+// synchronisation until the end:
+//   launching stream: pre-pass (size estimate + ordering) -> warp tier -> polygon kernel -> combine kernel
+//   second stream   : mid tier (queries classified as large + whatever the warp tier hands over while both run)
+//                     -> mid tier again once the warp tier has ended (late hand-overs) -> big tier (what the mid tier
+//                     could not fit) -> polygon kernel -> combine kernel
+// Each pipeline has its own record buffers and emission counters; a query's QInfo.status says which pipeline owns it.
+// Rare paths after the final sync: queries that overflowed the big tier's slab re-run with the worst-case slab; a
+// full record buffer grows and the batch re-runs.  Tiny batches (`single`) go straight to the big tier.
 static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, const float* d_nrm, const float w[3],
                              float* d_area, uint8_t* d_contact, bool single) {
   uint32_t* d_cnt = (uint32_t*)v->counters.p;
   unsigned long long* d_stats = (unsigned long long*)(d_cnt + CNT_WORDS);
-  uint32_t* d_emit = d_cnt + 64;     // [0] polygons [1] items [2] capacity flag
+  uint32_t* d_emit1 = d_cnt + 64;     // [0] polygons [1] items [2] capacity flag
+  uint32_t* d_emit2 = d_cnt + 68;
   uint32_t* list0 = (uint32_t*)v->lists.p;
   uint32_t* list1 = list0 + n;
   uint32_t* list2 = list1 + n;
   uint32_t* list3 = list2 + n;
+  uint32_t* sorted = list3 + n;
+  cudaStream_t s1 = v->stream, s2 = v->stream2;
   int launches = 0;
   for (int attempt = 0; attempt < 8; attempt++) {
-    CK(cudaMemsetAsync(d_cnt, 0, 512, v->stream));
+    CK(cudaMemsetAsync(d_cnt, 0, CNT_TOTAL_WORDS * 4, s1));
     BatchArgs a;
     a.vol = view_of(v);
     a.pos = d_pos; a.nrm = d_nrm; a.wx = w[0]; a.wy = w[1]; a.wz = w[2];
     a.nq = (uint32_t)n; a.counters = d_cnt; a.stats = d_stats;
-    a.out.polys = (PolyRec*)v->polys.p; a.out.items = (ItemRec*)v->items.p; a.out.geom = (PlaneGeom*)v->geom.p;
-    a.out.qinfo = (QInfo*)v->qinfo.p; a.out.counters = d_emit;
-    a.out.poly_cap = (uint32_t)std::min<uint64_t>(v->poly_cap, 0xffffffffull); a.out.item_cap = (uint32_t)std::min<uint64_t>(v->item_cap, 0xffffffffull);
-    CK(cudaEventRecord(v->ev[0], v->stream));
+    a.late = list0;
+    EmitOut out1, out2;
+    out1.polys = (PolyRec*)v->polys.p; out1.items = (ItemRec*)v->items.p; out1.geom = (PlaneGeom*)v->geom.p; out1.qinfo = (QInfo*)v->qinfo.p;
+    out1.counters = d_emit1; out1.ready = QS_READY;
+    out1.poly_cap = (uint32_t)std::min<uint64_t>(v->poly_cap, 0xffffffffull); out1.item_cap = (uint32_t)std::min<uint64_t>(v->item_cap, 0xffffffffull);
+    out2 = out1;
+    out2.polys = (PolyRec*)v->polys2.p; out2.items = (ItemRec*)v->items2.p; out2.counters = d_emit2; out2.ready = QS_READY2;
+    out2.poly_cap = (uint32_t)std::min<uint64_t>(v->poly_cap2, 0xffffffffull); out2.item_cap = (uint32_t)std::min<uint64_t>(v->item_cap2, 0xffffffffull);
+    float* vals1 = (float*)v->vals.p;
+    float* vals2 = (float*)v->vals2.p;
+    const unsigned cgrid_combine = (unsigned)std::min<uint64_t>(n, 65535ull * 16);
+    CK(cudaEventRecord(v->evb[0], s1));
     if (!single) {
-      a.list_in = nullptr; a.list_out = list0;
-      const int grid = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * 2);
-      T0_KERNEL<<<grid, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, v->stream>>>(a);
+      // pre-pass: size estimate per query -> list ordered largest first; its head goes straight to the mid tier
+      const int cgrid = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)v->sm_count * 8);
+      classify_kernel<<<cgrid, 256, 0, s1>>>(a.vol, d_pos, d_nrm, w[0], w[1], w[2], (uint32_t)n, (uint8_t*)v->keys.p, d_cnt + CNT_HIST, list0, out1.qinfo);
       CK(cudaGetLastError());
-      launches++;
-    }
-    CK(cudaEventRecord(v->ev[1], v->stream));
-    if (!single) {
-      a.list_in = list0; a.list_out = list1;
-      area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, v->stream>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, d_cnt + CNT_OVER0, 10);
+      const int ogrid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)v->sm_count);
+      order_kernel<<<ogrid, 256, 0, s1>>>((const uint8_t*)v->keys.p, d_cnt + CNT_HIST, d_cnt + CNT_CURSOR, sorted, (uint32_t)n, d_cnt + CNT_NBIG, v->mid_key ? v->mid_key : MID_BIG_KEY);
       CK(cudaGetLastError());
-      launches++;
-    }
-    CK(cudaEventRecord(v->ev[2], v->stream));
-    if (!single) {
+      launches += 2;
+      CK(cudaEventRecord(v->evb[1], s1));
+      // ---- second stream: mid tier beside the warp tier (it never waits for it)
+      CK(cudaEventRecord(v->evf[0], s1));
+      CK(cudaStreamWaitEvent(s2, v->evf[0], 0));
+      a.out = out2; a.list_in = sorted; a.list_out = list1;
+      CK(cudaEventRecord(v->evs[0], s2));
+      area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(v->evs[1], s2));
+      // ---- launching stream: warp tier
+      a.out = out1; a.list_in = sorted; a.list_out = list0;
+      const int grid = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * T0_CTAS_PER_SM);
+      T0_KERNEL<<<grid, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, s1>>>(a);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(v->evb[2], s1));
+      CK(cudaEventRecord(v->evf[1], s1));
+      launches += 2;
+      // ---- second stream: late hand-overs (after the warp tier), big tier, its own polygon + combine kernels
+      CK(cudaStreamWaitEvent(s2, v->evf[1], 0));
+      a.out = out2; a.list_in = sorted; a.list_out = list1;
+      area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(v->evs[2], s2));
       a.list_in = list1; a.list_out = list2;
-      area_block_kernel<BigTier><<<v->sm_count, BigTier::THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVER1, 10);
-    } else {
-      a.list_in = nullptr; a.list_out = list2;
-      const int grid = (int)std::min<uint64_t>(n, (uint64_t)v->sm_count);
-      area_block_kernel<BigTier><<<grid, BigTier::THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, nullptr, 10);
-    }
-    CK(cudaGetLastError());
-    launches++;
-    CK(cudaEventRecord(v->ev[3], v->stream));
-    poly_eval_kernel<<<v->sm_count * 8, 256, 0, v->stream>>>(a.out.polys, a.out.geom, (float*)v->vals.p, d_emit, 0u, a.out.poly_cap);
-    CK(cudaGetLastError());
-    launches++;
-    CK(cudaEventRecord(v->ev[4], v->stream));
-    combine_kernel<<<(unsigned)std::min<uint64_t>(n, 65535ull * 16), 128, 0, v->stream>>>(a.out.items, (float*)v->vals.p, a.out.qinfo, nullptr, nullptr, (uint32_t)n, d_area, d_contact);
-    CK(cudaGetLastError());
-    launches++;
-    CK(cudaEventRecord(v->ev[5], v->stream));
-    CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, v->stream));
-    CK(cudaStreamSynchronize(v->stream));
-    CK(cudaEventElapsedTime(&v->timing[0], v->ev[0], v->ev[1]));
-    CK(cudaEventElapsedTime(&v->timing[1], v->ev[1], v->ev[2]));
-    CK(cudaEventElapsedTime(&v->timing[2], v->ev[2], v->ev[3]));
-    CK(cudaEventElapsedTime(&v->timing[5], v->ev[3], v->ev[4]));
-    CK(cudaEventElapsedTime(&v->timing[6], v->ev[4], v->ev[5]));
-    v->timing[3] = 0.0f;
-    const uint32_t over0 = v->h_counters[CNT_OVER0], over1 = v->h_counters[CNT_OVER1], over2 = v->h_counters[CNT_OVER2];
-    const uint32_t* he = v->h_counters + 64;
-    uint32_t over3 = 0;
-    bool capacity = he[2] != 0;
-    uint32_t polys_used = he[0];
-    if (!capacity && over2 > 0) {
-      // worst-case slab, one CTA, only for the queries the big tier could not fit
-      RET(ensure_worst_case_slab(v));
-      a.list_in = list2; a.list_out = list3;
-      CK(cudaEventRecord(v->ev[0], v->stream));
-      area_block_kernel<BigTier><<<1, BigTier::THREADS, block_smem_bytes(v), v->stream>>>(a, v->cfg2, block_smem_bits_words(v), CNT_NEXT3, CNT_OVER3, d_cnt + CNT_OVER2, 10);
+      area_block_kernel<BigTier><<<v->sm_count, BigTier::THREADS, block_smem_bytes(v), s2>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVER1, 10);
       CK(cudaGetLastError());
-      CK(cudaEventRecord(v->ev[1], v->stream));
-      poly_eval_kernel<<<v->sm_count * 8, 256, 0, v->stream>>>(a.out.polys, a.out.geom, (float*)v->vals.p, d_emit, polys_used, a.out.poly_cap);
-      combine_kernel<<<1024, 128, 0, v->stream>>>(a.out.items, (float*)v->vals.p, a.out.qinfo, list2, d_cnt + CNT_OVER2, (uint32_t)n, d_area, d_contact);
+      CK(cudaEventRecord(v->evs[3], s2));
+      poly_eval_kernel<<<v->sm_count * 4, 256, 0, s2>>>(out2.polys, out2.geom, vals2, d_emit2, 0u, out2.poly_cap);
+      CK(cudaGetLastError());
+      combine_kernel<<<cgrid_combine, 128, 0, s2>>>(out2.items, vals2, out2.qinfo, nullptr, nullptr, (uint32_t)n, d_area, d_contact, QS_READY2);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(v->evs[4], s2));
+      CK(cudaEventRecord(v->evf[2], s2));
+      launches += 4;
+    } else {
+      CK(cudaEventRecord(v->evb[1], s1));
+      a.out = out1; a.list_in = nullptr; a.list_out = list2;
+      const int grid = (int)std::min<uint64_t>(n, (uint64_t)v->sm_count);
+      area_block_kernel<BigTier><<<grid, BigTier::THREADS, block_smem_bytes(v), s1>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, nullptr, 10);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(v->evb[2], s1));
+      launches++;
+    }
+    poly_eval_kernel<<<v->sm_count * 8, 256, 0, s1>>>(out1.polys, out1.geom, vals1, d_emit1, 0u, out1.poly_cap);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(v->evb[3], s1));
+    combine_kernel<<<cgrid_combine, 128, 0, s1>>>(out1.items, vals1, out1.qinfo, nullptr, nullptr, (uint32_t)n, d_area, d_contact, QS_READY);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(v->evb[4], s1));
+    launches += 2;
+    if (!single) CK(cudaStreamWaitEvent(s1, v->evf[2], 0));   // join
+    CK(cudaEventRecord(v->evb[5], s1));
+    CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, s1));
+    CK(cudaStreamSynchronize(s1));
+    for (int i = 0; i < 12; i++) v->timing[i] = i == 4 ? v->timing[4] : 0.0f;
+    CK(cudaEventElapsedTime(&v->timing[9], v->evb[0], v->evb[1]));                 // pre-pass
+    CK(cudaEventElapsedTime(&v->timing[single ? 2 : 0], v->evb[1], v->evb[2]));   // warp tier (tiny batches: big tier)
+    CK(cudaEventElapsedTime(&v->timing[5], v->evb[2], v->evb[3]));                 // polygon kernel
+    CK(cudaEventElapsedTime(&v->timing[6], v->evb[3], v->evb[4]));                 // combine kernel
+    CK(cudaEventElapsedTime(&v->timing[8], v->evb[4], v->evb[5]));                 // waiting for the second stream
+    if (!single) {
+      CK(cudaEventElapsedTime(&v->timing[1], v->evs[0], v->evs[1]));               // mid tier beside the warp tier
+      CK(cudaEventElapsedTime(&v->timing[10], v->evs[1], v->evs[2]));              // ... its second launch (incl. waiting for the warp tier)
+      CK(cudaEventElapsedTime(&v->timing[2], v->evs[2], v->evs[3]));               // big tier
+      CK(cudaEventElapsedTime(&v->timing[11], v->evs[3], v->evs[4]));              // second stream's polygon + combine kernels
+    }
+    const uint32_t over0 = v->h_counters[CNT_OVER0], over1 = v->h_counters[CNT_OVER1], over2 = v->h_counters[CNT_OVER2];
+    const uint32_t* he1 = v->h_counters + 64;
+    const uint32_t* he2 = v->h_counters + 68;
+    uint32_t over3 = 0;
+    bool capacity = he1[2] != 0 || he2[2] != 0;
+    if (!capacity && over2 > 0) {
+      // worst-case slab, one CTA, only for the queries the big tier could not fit (records go where the big tier's went)
+      RET(ensure_worst_case_slab(v));
+      const EmitOut& ob = single ? out1 : out2;
+      float* valsb = single ? vals1 : vals2;
+      uint32_t* d_emitb = single ? d_emit1 : d_emit2;
+      const uint32_t used = single ? he1[0] : he2[0];
+      a.out = ob; a.list_in = list2; a.list_out = list3;
+      CK(cudaEventRecord(v->ev[0], s1));
+      area_block_kernel<BigTier><<<1, BigTier::THREADS, block_smem_bytes(v), s1>>>(a, v->cfg2, block_smem_bits_words(v), CNT_NEXT3, CNT_OVER3, d_cnt + CNT_OVER2, 10);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(v->ev[1], s1));
+      poly_eval_kernel<<<v->sm_count * 8, 256, 0, s1>>>(ob.polys, ob.geom, valsb, d_emitb, used, ob.poly_cap);
+      combine_kernel<<<1024, 128, 0, s1>>>(ob.items, valsb, ob.qinfo, list2, d_cnt + CNT_OVER2, (uint32_t)n, d_area, d_contact, ob.ready);
       CK(cudaGetLastError());
       launches += 3;
-      CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, v->stream));
-      CK(cudaStreamSynchronize(v->stream));
+      CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, s1));
+      CK(cudaStreamSynchronize(s1));
       CK(cudaEventElapsedTime(&v->timing[3], v->ev[0], v->ev[1]));
       over3 = v->h_counters[CNT_OVER3];
-      capacity = he[2] != 0;
-      polys_used = he[0];
+      capacity = he1[2] != 0 || he2[2] != 0;
     }
     const unsigned long long* hs = (const unsigned long long*)(v->h_counters + CNT_WORDS);
     v->stats[0] = hs[0]; v->stats[1] = hs[1]; v->stats[2] = hs[2] * 1024ull;
-    v->stats[3] = over0; v->stats[4] = over1; v->stats[5] = (uint64_t)launches; v->stats[6] = over2; v->stats[7] = polys_used;
+    v->stats[3] = (single ? 0u : v->h_counters[CNT_NBIG]) + over0; v->stats[4] = over1; v->stats[5] = (uint64_t)launches; v->stats[6] = over2;
+    v->stats[7] = (uint64_t)he1[0] + (uint64_t)he2[0];
     v->stats[8] = over3; v->stats[9] = 0;
     v->tier_stats[0] = hs[16]; v->tier_stats[1] = hs[17];
     for (int i = 0; i < 12; i++) v->prof[i] = hs[4 + i];
     if (capacity) {
       // a record buffer filled up: double it and run the batch again
-      v->poly_cap *= 2; v->item_cap *= 2;
-      if (v->poly_cap > (1ull << 31)) return fail(XS3D_ERR_CAPACITY, "polygon record buffer would exceed 2^31 entries; split the batch");
+      if (he1[2] != 0) { v->poly_cap *= 2; v->item_cap *= 2; }
+      if (he2[2] != 0) { v->poly_cap2 *= 2; v->item_cap2 *= 2; }
+      if (v->poly_cap > (1ull << 31) || v->poly_cap2 > (1ull << 31)) return fail(XS3D_ERR_CAPACITY, "polygon record buffer would exceed 2^31 entries; split the batch");
       RET(v->polys.ensure(v->poly_cap * sizeof(PolyRec) + 64));
       RET(v->vals.ensure(v->poly_cap * 4 + 64));
       RET(v->items.ensure(v->item_cap * sizeof(ItemRec) + 64));
+      RET(v->polys2.ensure(v->poly_cap2 * sizeof(PolyRec) + 64));
+      RET(v->vals2.ensure(v->poly_cap2 * 4 + 64));
+      RET(v->items2.ensure(v->item_cap2 * sizeof(ItemRec) + 64));
       continue;
     }
     if (over3 > 0) return fail(XS3D_ERR_CAPACITY, "a query exceeded the worst-case working set");
@@ -943,22 +1090,6 @@ extern "C" int xs3d_area_batch(xs3d_volume* v, uint64_t n, const float* pos, con
     CK(cudaMemcpyAsync(contact, d_contact, n, cudaMemcpyDeviceToHost, v->stream));
     CK(cudaStreamSynchronize(v->stream));
   }
-  return XS3D_OK;
-}
-
-extern "C" int xs3d_debug_classify(xs3d_volume* v, uint64_t n, const float* pos, const float* normal, const float anisotropy[3], uint16_t* popc_host) {
-  if (!v || !v->loaded) return fail(XS3D_ERR_ARG, "volume not loaded");
-  CK(cudaSetDevice(v->device));
-  RET(ensure_batch_workspace(v, n));
-  RET(v->misc.ensure(n * 2 + 64));
-  CK(cudaMemcpyAsync(v->q_pos.p, pos, n * 12, cudaMemcpyHostToDevice, v->stream));
-  CK(cudaMemcpyAsync(v->q_nrm.p, normal, n * 12, cudaMemcpyHostToDevice, v->stream));
-  CK(cudaEventRecord(v->ev[0], v->stream));
-  classify_kernel<<<v->sm_count * 4, 256, 0, v->stream>>>(view_of(v), (const float*)v->q_pos.p, (const float*)v->q_nrm.p, anisotropy[0], anisotropy[1], anisotropy[2], (uint32_t)n, (uint16_t*)v->misc.p);
-  CK(cudaEventRecord(v->ev[1], v->stream));
-  CK(cudaMemcpyAsync(popc_host, v->misc.p, n * 2, cudaMemcpyDeviceToHost, v->stream));
-  CK(cudaStreamSynchronize(v->stream));
-  CK(cudaEventElapsedTime(&v->timing[7], v->ev[0], v->ev[1]));
   return XS3D_OK;
 }
 
@@ -1001,9 +1132,9 @@ extern "C" int xs3d_volume_stats(xs3d_volume* v, uint64_t stats[10]) {
   return XS3D_OK;
 }
 
-extern "C" int xs3d_volume_timing(xs3d_volume* v, float ms[8]) {
+extern "C" int xs3d_volume_timing(xs3d_volume* v, float ms[12]) {
   if (!v) return fail(XS3D_ERR_ARG, "null volume");
-  for (int i = 0; i < 8; i++) ms[i] = v->timing[i];
+  for (int i = 0; i < 12; i++) ms[i] = v->timing[i];
   return XS3D_OK;
 }
 

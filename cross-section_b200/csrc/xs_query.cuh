@@ -258,7 +258,7 @@ struct QInfo {              // 16 bytes per query
   uint32_t contact;
   uint32_t status;          // QS_*
 };
-enum { QS_PENDING = 0, QS_READY = 1 };
+enum { QS_PENDING = 0, QS_READY = 1, QS_READY2 = 2 };   // READY2: the records live in the second pipeline's buffers
 struct EmitOut {
   PolyRec* polys;
   ItemRec* items;
@@ -266,6 +266,7 @@ struct EmitOut {
   QInfo* qinfo;             // per query
   uint32_t* counters;       // [0] polygons used, [1] items used, [2] capacity overflow flag
   uint32_t poly_cap, item_cap;
+  uint32_t ready;           // QInfo.status to publish (QS_READY / QS_READY2)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -1313,7 +1314,7 @@ XS_D int run_area_emit(const G& g, const PlaneCtx& c, const VolView& vol, const 
   if (g.tid() == 0) prof_mark(ctl, 0);
   if (empty) {
     if (g.tid() == 0) {
-      QInfo qi; qi.item_off = 0; qi.n_items = 0; qi.contact = 0; qi.status = QS_READY;
+      QInfo qi; qi.item_off = 0; qi.n_items = 0; qi.contact = 0; qi.status = out.ready;
       out.qinfo[q] = qi;
     }
     return Q_OK;
@@ -1327,7 +1328,7 @@ XS_D int run_area_emit(const G& g, const PlaneCtx& c, const VolView& vol, const 
   if (g.tid() == 0) {
     prof_mark(ctl, 2);
     out.geom[q] = c.g;
-    QInfo qi; qi.item_off = ctl.item_off; qi.n_items = (uint32_t)ctl.m; qi.contact = ctl.contact; qi.status = QS_READY;
+    QInfo qi; qi.item_off = ctl.item_off; qi.n_items = (uint32_t)ctl.m; qi.contact = ctl.contact; qi.status = out.ready;
     out.qinfo[q] = qi;
   }
   return Q_OK;

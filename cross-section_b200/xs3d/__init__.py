@@ -173,11 +173,13 @@ class Volume:
             "launches": s[5], "escalated_worst_case": s[6], "polygons": s[7], "failed": s[8], "samples_cta_tiers": s[9]}
 
   def timing(self):
-    """CUDA-event kernel durations (ms) of the last call: warp tier, CTA tier, worst-case tier, ingest."""
-    t = (C.c_float * 8)()
+    """CUDA-event durations (ms) of the last call (include/xs3d_b200.h, xs3d_volume_timing).  The mid / big tiers
+    run on a second stream beside the warp tier; mid_exposed_ms is what they add to the launching stream."""
+    t = (C.c_float * 12)()
     _abi.check(self._lib.xs3d_volume_timing(self._h, t))
     return {"warp_tier_ms": t[0], "mid_tier_ms": t[1], "big_tier_ms": t[2], "worst_case_ms": t[3], "ingest_ms": t[4],
-            "polygon_ms": t[5], "combine_ms": t[6]}
+            "polygon_ms": t[5], "combine_ms": t[6], "mid_exposed_ms": t[8], "prepass_ms": t[9],
+            "mid_second_launch_ms": t[10], "second_stream_poly_combine_ms": t[11]}
 
   def set_stream(self, cuda_stream):
     """Launch on the given cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""

@@ -77,10 +77,13 @@ int xs3d_volume_stats(xs3d_volume* vol, uint64_t stats[10]);
  * queries: prof[0..5] warp tier, prof[6..11] CTA tiers (mid + big); phases: [0] lattice flood (tiles + walk), [1] claims,
  * [2] ownership + record emission, [3] [4] unused, [5] walk only. */
 int xs3d_volume_profile(xs3d_volume* vol, uint64_t prof[12]);
-/* CUDA-event durations (ms, measured on the launching stream) of the kernels of the last call on this volume:
- * ms[0] warp-tier, ms[1] mid-tier, ms[2] big-tier, ms[3] worst-case query kernels, ms[4] ingest kernel (last
- * xs3d_volume_load), ms[5] polygon kernel, ms[6] combine kernel, ms[7] reserved. */
-int xs3d_volume_timing(xs3d_volume* vol, float ms[8]);
+/* CUDA-event durations (ms) of the kernels of the last call on this volume:
+ * ms[0] warp-tier, ms[1] mid-tier (on its own stream, concurrent with the warp tier), ms[2] big-tier, ms[3] worst-case
+ * query kernels, ms[4] ingest kernel (last xs3d_volume_load), ms[5] polygon kernel, ms[6] combine kernel, ms[7] reserved,
+ * ms[8] time the launching stream waits for the second stream (mid / big tiers + their polygon and combine kernels)
+ * after its own combine kernel, ms[9] pre-pass (size estimate + ordering), ms[10] second launch of the mid tier
+ * (late hand-overs; includes waiting for the warp tier), ms[11] the second stream's polygon + combine kernels. */
+int xs3d_volume_timing(xs3d_volume* vol, float ms[12]);
 /* Launch on the caller's stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) instead of the
  * volume's own, so the caller's CUDA events bracket the work.  The stream must outlive the volume. */
 int xs3d_volume_set_stream(xs3d_volume* vol, void* cuda_stream);

@@ -37,7 +37,7 @@ struct HostOut {
     polys.assign(poly_cap, PolyRec()); items.assign(item_cap, ItemRec()); geom.assign(nq, PlaneGeom()); qinfo.assign(nq, QInfo());
     counters[0] = counters[1] = counters[2] = counters[3] = 0;
     out.polys = polys.data(); out.items = items.data(); out.geom = geom.data(); out.qinfo = qinfo.data();
-    out.counters = counters; out.poly_cap = (uint32_t)poly_cap; out.item_cap = (uint32_t)item_cap;
+    out.counters = counters; out.poly_cap = (uint32_t)poly_cap; out.item_cap = (uint32_t)item_cap; out.ready = QS_READY;
   }
 };
 
