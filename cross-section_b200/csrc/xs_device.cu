@@ -645,6 +645,7 @@ struct xs3d_volume {
   bool own_stream = true;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float timing[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // ms, see xs3d_volume_timing
+  int timing_pending = 0;   // 1: batch events not yet read, 2: same for a tiny (`single`) batch
 };
 
 static VolView view_of(const xs3d_volume* v) {
@@ -852,7 +853,7 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
     SlabCfg m{};
     m.max_n = 1 << 14; m.hcap_max = 1u << 17; m.bits_words = 0; m.tested_words = 0; m.hash_factor = 8; m.max_probe = 256;
     m.stride = mid_slab_bytes(m);
-    v->mid_ctas = v->sm_count;
+    v->mid_ctas = v->sm_count * 2;
     if (const char* e = getenv("XS3D_MID_CTAS")) v->mid_ctas = std::max(1, atoi(e));          // tuning knobs (dev)
     if (const char* e = getenv("XS3D_MID_KEY")) v->mid_key = std::min(255, std::max(1, atoi(e)));
     RET(v->slab_mid.ensure(m.stride * (size_t)v->mid_ctas));
@@ -997,18 +998,8 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     CK(cudaEventRecord(v->evb[5], s1));
     CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, s1));
     CK(cudaStreamSynchronize(s1));
-    for (int i = 0; i < 12; i++) v->timing[i] = i == 4 ? v->timing[4] : 0.0f;
-    CK(cudaEventElapsedTime(&v->timing[9], v->evb[0], v->evb[1]));                 // pre-pass
-    CK(cudaEventElapsedTime(&v->timing[single ? 2 : 0], v->evb[1], v->evb[2]));   // warp tier (tiny batches: big tier)
-    CK(cudaEventElapsedTime(&v->timing[5], v->evb[2], v->evb[3]));                 // polygon kernel
-    CK(cudaEventElapsedTime(&v->timing[6], v->evb[3], v->evb[4]));                 // combine kernel
-    CK(cudaEventElapsedTime(&v->timing[8], v->evb[4], v->evb[5]));                 // waiting for the second stream
-    if (!single) {
-      CK(cudaEventElapsedTime(&v->timing[1], v->evs[0], v->evs[1]));               // mid tier beside the warp tier
-      CK(cudaEventElapsedTime(&v->timing[10], v->evs[1], v->evs[2]));              // ... its second launch (incl. waiting for the warp tier)
-      CK(cudaEventElapsedTime(&v->timing[2], v->evs[2], v->evs[3]));               // big tier
-      CK(cudaEventElapsedTime(&v->timing[11], v->evs[3], v->evs[4]));              // second stream's polygon + combine kernels
-    }
+    v->timing_pending = single ? 2 : 1;   // event durations are read on demand (xs3d_volume_timing): ten driver calls off the hot path
+    v->timing[3] = 0.0f;
     const uint32_t over0 = v->h_counters[CNT_OVER0], over1 = v->h_counters[CNT_OVER1], over2 = v->h_counters[CNT_OVER2];
     const uint32_t* he1 = v->h_counters + 64;
     const uint32_t* he2 = v->h_counters + 68;
@@ -1134,6 +1125,25 @@ extern "C" int xs3d_volume_stats(xs3d_volume* v, uint64_t stats[10]) {
 
 extern "C" int xs3d_volume_timing(xs3d_volume* v, float ms[12]) {
   if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (v->timing_pending) {
+    const bool single = v->timing_pending == 2;
+    v->timing_pending = 0;
+    CK(cudaSetDevice(v->device));
+    const float ingest = v->timing[4], worst = v->timing[3];
+    for (int i = 0; i < 12; i++) v->timing[i] = 0.0f;
+    v->timing[4] = ingest; v->timing[3] = worst;
+    CK(cudaEventElapsedTime(&v->timing[9], v->evb[0], v->evb[1]));                 // pre-pass
+    CK(cudaEventElapsedTime(&v->timing[single ? 2 : 0], v->evb[1], v->evb[2]));   // warp tier (tiny batches: big tier)
+    CK(cudaEventElapsedTime(&v->timing[5], v->evb[2], v->evb[3]));                 // polygon kernel
+    CK(cudaEventElapsedTime(&v->timing[6], v->evb[3], v->evb[4]));                 // combine kernel
+    CK(cudaEventElapsedTime(&v->timing[8], v->evb[4], v->evb[5]));                 // waiting for the second stream
+    if (!single) {
+      CK(cudaEventElapsedTime(&v->timing[1], v->evs[0], v->evs[1]));               // mid tier beside the warp tier
+      CK(cudaEventElapsedTime(&v->timing[10], v->evs[1], v->evs[2]));              // ... its second launch (incl. waiting for the warp tier)
+      CK(cudaEventElapsedTime(&v->timing[2], v->evs[2], v->evs[3]));               // big tier
+      CK(cudaEventElapsedTime(&v->timing[11], v->evs[3], v->evs[4]));              // second stream's polygon + combine kernels
+    }
+  }
   for (int i = 0; i < 12; i++) ms[i] = v->timing[i];
   return XS3D_OK;
 }
