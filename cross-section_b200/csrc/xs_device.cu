@@ -608,7 +608,8 @@ struct DevBuf {
 // warp tier configuration (shared memory per warp = WarpLayout::WORDS * 4 bytes)
 constexpr int T0_WARPS = 10, T0_TILES = 3, T0_MAXN = 384, T0_HCAP = 1024;   // 3 CTAs per SM -> 30 warps per SM (2 beside a mid-tier CTA)
 constexpr int T0_CTAS_PER_SM = 3;
-constexpr int MID_BIG_KEY = 22;   // >= 22 of 256 probes foreground (~350 cells): the section will not fit a warp (T0_MAXN)
+constexpr int MID_BIG_KEY = 30;   // >= 30 of 256 probes foreground (~480 cells): the section will not fit a warp (T0_MAXN); tuned on the
+                                  //   bench sweep — a query misjudged as small is handed over by the warp tier, only later
 using T0Layout = WarpLayout<T0_TILES, T0_MAXN, T0_HCAP>;
 #define T0_KERNEL area_warp_kernel<T0_WARPS, T0_TILES, T0_MAXN, T0_HCAP>
 
@@ -630,7 +631,8 @@ struct xs3d_volume {
   cudaEvent_t evb[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // batch timing, launching stream
   cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};            // batch timing, second stream
   cudaStream_t stream2 = nullptr;                      // the mid tier runs here, beside the warp tier
-  cudaEvent_t evf[3] = {nullptr, nullptr, nullptr};    // fork, warp tier done, second stream done
+  cudaStream_t stream3 = nullptr;                      // third warp-tier CTA per SM (moves in when the mid-tier CTA retires)
+  cudaEvent_t evf[4] = {nullptr, nullptr, nullptr, nullptr};    // fork, warp-tier grid A done, second stream done, warp-tier grid B done
   SlabCfg cfg_mid{};
   int mid_ctas = 0;
   int mid_key = 0;
@@ -688,9 +690,14 @@ extern "C" int xs3d_volume_create(int device, uint64_t sx, uint64_t sy, uint64_t
   v->sm_count = prop.multiProcessorCount;
   v->smem_optin = (int)prop.sharedMemPerBlockOptin;
   CK(cudaStreamCreateWithFlags(&v->stream, cudaStreamNonBlocking));
-  CK(cudaStreamCreateWithFlags(&v->stream2, cudaStreamNonBlocking));
+  {
+    int prio_lo = 0, prio_hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    CK(cudaStreamCreateWithPriority(&v->stream2, cudaStreamNonBlocking, prio_hi));   // latency-bound tier: its CTAs are placed first
+    CK(cudaStreamCreateWithPriority(&v->stream3, cudaStreamNonBlocking, prio_lo));
+  }
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&v->ev[i]));
-  for (int i = 0; i < 3; i++) CK(cudaEventCreateWithFlags(&v->evf[i], cudaEventDisableTiming));
+  for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&v->evf[i], cudaEventDisableTiming));
   for (int i = 0; i < 6; i++) CK(cudaEventCreate(&v->evb[i]));
   for (int i = 0; i < 5; i++) CK(cudaEventCreate(&v->evs[i]));
   RET(v->cubes.ensure(hx * hy * hz + 64));
@@ -704,8 +711,9 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
   cudaSetDevice(v->device);
   if (v->stream) { cudaStreamSynchronize(v->stream); if (v->own_stream) cudaStreamDestroy(v->stream); }
   if (v->stream2) { cudaStreamSynchronize(v->stream2); cudaStreamDestroy(v->stream2); }
+  if (v->stream3) { cudaStreamSynchronize(v->stream3); cudaStreamDestroy(v->stream3); }
   for (int i = 0; i < 8; i++) if (v->ev[i]) cudaEventDestroy(v->ev[i]);
-  for (int i = 0; i < 3; i++) if (v->evf[i]) cudaEventDestroy(v->evf[i]);
+  for (int i = 0; i < 4; i++) if (v->evf[i]) cudaEventDestroy(v->evf[i]);
   for (int i = 0; i < 6; i++) if (v->evb[i]) cudaEventDestroy(v->evb[i]);
   for (int i = 0; i < 5; i++) if (v->evs[i]) cudaEventDestroy(v->evs[i]);
   DevBuf* bufs[] = { &v->cubes, &v->raw, &v->labels, &v->q_pos, &v->q_nrm, &v->q_area, &v->q_contact, &v->lists,
@@ -853,7 +861,7 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
     SlabCfg m{};
     m.max_n = 1 << 14; m.hcap_max = 1u << 17; m.bits_words = 0; m.tested_words = 0; m.hash_factor = 8; m.max_probe = 256;
     m.stride = mid_slab_bytes(m);
-    v->mid_ctas = v->sm_count * 2;
+    v->mid_ctas = v->sm_count;
     if (const char* e = getenv("XS3D_MID_CTAS")) v->mid_ctas = std::max(1, atoi(e));          // tuning knobs (dev)
     if (const char* e = getenv("XS3D_MID_KEY")) v->mid_key = std::min(255, std::max(1, atoi(e)));
     RET(v->slab_mid.ensure(m.stride * (size_t)v->mid_ctas));
@@ -945,6 +953,11 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(cudaGetLastError());
       launches += 2;
       CK(cudaEventRecord(v->evb[1], s1));
+      // ---- residency plan per SM (228 KB of shared memory): two warp-tier CTAs (2 x 74.4 KB) + one mid-tier CTA
+      //      (78.5 KB).  The warp tier is therefore launched as TWO grids pulling from the same queue: A (2 CTAs per SM)
+      //      on the launching stream and B (1 CTA per SM) on a third stream.  The mid tier's stream has the higher
+      //      priority, so its CTAs are placed before B's; B's CTAs move in as mid-tier CTAs retire.  Whichever of A and
+      //      the mid tier is dispatched first, both fit.
       // ---- second stream: mid tier beside the warp tier (it never waits for it)
       CK(cudaEventRecord(v->evf[0], s1));
       CK(cudaStreamWaitEvent(s2, v->evf[0], 0));
@@ -953,16 +966,24 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10);
       CK(cudaGetLastError());
       CK(cudaEventRecord(v->evs[1], s2));
-      // ---- launching stream: warp tier
+      // ---- third stream: warp-tier grid B
+      CK(cudaStreamWaitEvent(v->stream3, v->evf[0], 0));
       a.out = out1; a.list_in = sorted; a.list_out = list0;
-      const int grid = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * T0_CTAS_PER_SM);
-      T0_KERNEL<<<grid, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, s1>>>(a);
+      const int gridB = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * (T0_CTAS_PER_SM - 2));
+      T0_KERNEL<<<gridB, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, v->stream3>>>(a);
       CK(cudaGetLastError());
-      CK(cudaEventRecord(v->evb[2], s1));
+      CK(cudaEventRecord(v->evf[3], v->stream3));
+      // ---- launching stream: warp-tier grid A
+      const int gridA = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * 2);
+      T0_KERNEL<<<gridA, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, s1>>>(a);
+      CK(cudaGetLastError());
       CK(cudaEventRecord(v->evf[1], s1));
-      launches += 2;
+      CK(cudaStreamWaitEvent(s1, v->evf[3], 0));       // the polygon kernel needs grid B's records too
+      CK(cudaEventRecord(v->evb[2], s1));
+      launches += 3;
       // ---- second stream: late hand-overs (after the warp tier), big tier, its own polygon + combine kernels
       CK(cudaStreamWaitEvent(s2, v->evf[1], 0));
+      CK(cudaStreamWaitEvent(s2, v->evf[3], 0));
       a.out = out2; a.list_in = sorted; a.list_out = list1;
       area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10);
       CK(cudaGetLastError());

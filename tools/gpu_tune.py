@@ -23,8 +23,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
       os.environ.get("TAG", ""), float(np.median(ts[3:])), min(ts), t["warp_tier_ms"], t["mid_tier_ms"], t["mid_exposed_ms"], t["prepass_ms"],
       t["polygon_ms"], t["combine_ms"], st["escalated_mid"], st["escalated_big"]), flush=True)
   sys.exit(0)
-for huge in (256, 96, 56, 40, 30):
-  for xctas in (32, 49, 74):
-    if huge == 256 and xctas != 49: continue
-    env = dict(os.environ, XS3D_HUGE_KEY=str(huge), XS3D_MIDX_CTAS=str(xctas), XS3D_MID_KEY="26", TAG="huge=%d xctas=%d key=26" % (huge, xctas))
+for ctas in (148,):
+  for key in (22, 26, 30, 40):
+    env = dict(os.environ, XS3D_MID_CTAS=str(ctas), XS3D_MID_KEY=str(key), TAG="ctas=%d key=%d" % (ctas, key))
     subprocess.run([sys.executable, __file__, "child"], env=env)
