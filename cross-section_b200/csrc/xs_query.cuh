@@ -561,8 +561,36 @@ XS_HD void clear_bit(uint32_t* w, uint32_t bit) {
 #endif
 }
 
+// 3x3 availability of cell (u,v): bit 3*row + col, rows v-1..v+1, cols u-1..u+1
 template <class CellT>
-XS_HD int dfs_run(const Arena<CellT>& A, Ctl& ctl) {
+XS_HD uint32_t avail3x3(const Arena<CellT>& A, int u, int v) {
+  const int um1 = u - 1;
+  const int sh = um1 & 31;
+  const uint32_t* rp = A.bits + ((v - 1) * A.stride + (um1 >> 5));
+  const int stride = A.stride;
+  const uint32_t a0 = rp[0], a1 = rp[1], b0 = rp[stride], b1 = rp[stride + 1], c0 = rp[2 * stride], c1 = rp[2 * stride + 1];
+  return (funnel_r(a0, a1, sh) & 7u) | ((funnel_r(b0, b1, sh) & 7u) << 3) | ((funnel_r(c0, c1, sh) & 7u) << 6);
+}
+// A cell on a tile border may have neighbours in a tile that has not been sampled yet: which one (or -1)
+template <class CellT>
+XS_HD int missing_tile(const Arena<CellT>& A, int u, int v) {
+  if (!((((u + 1) & 31) < 2) | (((v + 1) & 31) < 2))) return -1;
+  const int ua = (u - 1) >> 5, ub = (u + 1) >> 5, va = (v - 1) >> 5, vb = (v + 1) >> 5;
+  if (!tile_tested(A, ua, va)) return va * A.tx + ua;
+  if (!tile_tested(A, ub, va)) return va * A.tx + ub;
+  if (!tile_tested(A, ua, vb)) return vb * A.tx + ua;
+  if (!tile_tested(A, ub, vb)) return vb * A.tx + ub;
+  return -1;
+}
+
+// Walk, warp form.  Device: called by every lane of ONE warp in lock step (all lanes hold the same state; lane 0
+// does the stores); host: lane = 0.  Forward steps are inherently one at a time.  A dead end, however, unwinds the
+// stack until a frame that still has something to offer — and since availability only ever decreases, every frame
+// can be judged independently: the lanes examine 32 frames at once and the walk resumes at the topmost live one
+// (or at the topmost one that needs an unsampled tile, exactly where the one-at-a-time unwinding would stop).
+// Unwinding is half of all iterations of a one-thread walk, most of it the final unwind of a finished component.
+template <class CellT>
+XS_HD int dfs_run(const Arena<CellT>& A, Ctl& ctl, int lane) {
   typedef CellPack<CellT> P;
   int n = ctl.n, depth = ctl.depth, lo = ctl.lo, u = ctl.u, v = ctl.v;
   const unsigned Wm2 = (unsigned)(A.tx * 32 - 2), Hm2 = (unsigned)(A.ty * 32 - 2);
@@ -574,27 +602,17 @@ XS_HD int dfs_run(const Arena<CellT>& A, Ctl& ctl) {
   const int smask = ring ? (A.stack_cap - 1) : 0x7fffffff;   // no ring wrap when the whole stack is resident
   const int cap = ring ? A.stack_cap : 0x7fffffff;
   int status;
+  int req = -1;
   for (;;) {
     // all four tiles under the 3x3 neighbourhood must have been sampled (only cells on a tile border can miss)
-    if ((((u + 1) & 31) < 2) | (((v + 1) & 31) < 2)) {
-      const int ua = (u - 1) >> 5, ub = (u + 1) >> 5, va = (v - 1) >> 5, vb = (v + 1) >> 5;
-      int need_x = -1, need_y = 0;
-      if (!tile_tested(A, ua, va)) { need_x = ua; need_y = va; }
-      else if (!tile_tested(A, ub, va)) { need_x = ub; need_y = va; }
-      else if (!tile_tested(A, ua, vb)) { need_x = ua; need_y = vb; }
-      else if (!tile_tested(A, ub, vb)) { need_x = ub; need_y = vb; }
-      if (need_x >= 0) { ctl.req_tx = need_x; ctl.req_ty = need_y; status = ST_NEED_TILE; break; }
-    }
-    const int um1 = u - 1;
-    const int sh = um1 & 31;
-    const uint32_t* rp = bits + ((v - 1) * stride + (um1 >> 5));
-    const uint32_t a0 = rp[0], a1 = rp[1], b0 = rp[stride], b1 = rp[stride + 1], c0 = rp[2 * stride], c1 = rp[2 * stride + 1];
-    const uint32_t idx = (funnel_r(a0, a1, sh) & 7u) | ((funnel_r(b0, b1, sh) & 7u) << 3) | ((funnel_r(c0, c1, sh) & 7u) << 6);
+    req = missing_tile(A, u, v);
+    if (req >= 0) { status = ST_NEED_TILE; break; }
+    const uint32_t idx = avail3x3(A, u, v);
     uint32_t e;
     if (sizeof(CellT) == 2) {
       e = dir_lut(idx);                       // warp tier (issue-bound): one table load
     } else {
-      // CTA tiers (latency-bound, one thread): an indexed constant load costs more than the ALU it saves.
+      // CTA tiers (latency-bound): an indexed constant load costs more than the ALU it saves.
       // idx bits: rm 0..2, r0 3..5, rq 6..8  ->  priority mask [rq2 rq0 rm2 rm0 rq1 rm1 r0_2 r0_0]
       const uint32_t pm = ((idx >> 8) & 1u) | ((idx >> 5) & 2u) | (idx & 4u) | ((idx << 3) & 8u) | ((idx >> 3) & 16u) | ((idx << 4) & 32u) |
                           ((idx << 1) & 64u) | ((idx << 4) & 128u);
@@ -606,40 +624,85 @@ XS_HD int dfs_run(const Arena<CellT>& A, Ctl& ctl) {
       }
     }
     if (e == 0xffu) {
-      // backtrack
+      // dead end: drop the current frame, then find the topmost frame that is live or needs a tile
       depth--;
-      if (depth == 0) { status = ST_DONE; break; }
-      if (depth - 1 < lo) {
-        // (ring only) refill the lower half of the ring from the global spill area
-        int nlo = lo - A.stack_cap / 2;
-        if (nlo < 0) nlo = 0;
-#pragma unroll 1
-        for (int d = nlo; d < lo; d++) stack[d & smask] = A.spill[d];
-        lo = nlo;
+      bool found = false;
+      while (depth > 0) {
+        if (depth == lo) {
+          // (ring only) refill the lower half of the ring from the global spill area
+          int nlo = lo - A.stack_cap / 2;
+          if (nlo < 0) nlo = 0;
+#ifdef __CUDA_ARCH__
+          for (int d = nlo + lane; d < lo; d += 32) stack[d & smask] = A.spill[d];
+          __syncwarp();
+#else
+          for (int d = nlo; d < lo; d++) stack[d & smask] = A.spill[d];
+#endif
+          lo = nlo;
+        }
+        const int avail = depth - lo;
+        const int cnt = avail < 32 ? avail : 32;
+#ifdef __CUDA_ARCH__
+        CellT f = 0;
+        bool live = false;
+        if (lane < cnt) {
+          f = stack[(depth - 1 - lane) & smask];
+          const int fu = P::u(f), fv = P::v(f);
+          live = missing_tile(A, fu, fv) >= 0 || (avail3x3(A, fu, fv) & 0x1efu) != 0u;
+        }
+        const uint32_t ball = __ballot_sync(0xffffffffu, live);
+        if (ball) {
+          const int l = __ffs(ball) - 1;
+          depth -= l;
+          const uint32_t ff = __shfl_sync(0xffffffffu, (uint32_t)f, l);
+          u = P::u((CellT)ff); v = P::v((CellT)ff);
+          found = true;
+          break;
+        }
+        depth -= cnt;
+#else
+        int l = 0;
+        for (; l < cnt; l++) {
+          const CellT f = stack[(depth - 1 - l) & smask];
+          const int fu = P::u(f), fv = P::v(f);
+          if (missing_tile(A, fu, fv) >= 0 || (avail3x3(A, fu, fv) & 0x1efu) != 0u) { u = fu; v = fv; found = true; break; }
+        }
+        depth -= l;
+        if (found) break;
+#endif
       }
-      const CellT p = stack[(depth - 1) & smask];
-      u = P::u(p); v = P::v(p);
+      if (!found) { status = ST_DONE; break; }
       continue;
     }
     u += (int)(e & 3u) - 1; v += (int)((e >> 2) & 3u) - 1;
-    bits[v * stride + (u >> 5)] &= ~(1u << (u & 31));
+    if (lane == 0) bits[v * stride + (u >> 5)] &= ~(1u << (u & 31));
     if (((unsigned)(u - 1) >= Wm2) | ((unsigned)(v - 1) >= Hm2) | (n >= max_n)) { status = ST_OVERFLOW; break; }
     const CellT p = P::pack(u, v);
-    order[n++] = p;
+    if (lane == 0) order[n] = p;
+    n++;
     // Tail call: if the cell we are leaving has no other available neighbour NOW it never will (availability only
     // decreases), so coming back to it would find nothing — reuse its frame instead of stacking on top of it.
     if (!(e & 16u)) depth--;
     if (depth - lo == cap) {
       // (ring only) ring full: spill the lower half
       const int nlo = lo + A.stack_cap / 2;
-#pragma unroll 1
+#ifdef __CUDA_ARCH__
+      for (int dd = lo + lane; dd < nlo; dd += 32) A.spill[dd] = stack[dd & smask];
+#else
       for (int dd = lo; dd < nlo; dd++) A.spill[dd] = stack[dd & smask];
+#endif
       lo = nlo;
     }
-    stack[depth & smask] = p;
+    if (lane == 0) stack[depth & smask] = p;
     depth++;
+#ifdef __CUDA_ARCH__
+    __syncwarp();
+#endif
   }
-  ctl.n = n; ctl.depth = depth; ctl.lo = lo; ctl.u = u; ctl.v = v;
+  if (lane == 0) {
+    ctl.n = n; ctl.depth = depth; ctl.lo = lo; ctl.u = u; ctl.v = v;
+    if (status == ST_NEED_TILE) { ctl.req_tx = req % A.tx; ctl.req_ty = req / A.tx; }
+  }
   return status;
 }
 
@@ -668,25 +731,31 @@ XS_D int flood_component(const G& g, const PlaneCtx& c, const VolView& vol, cons
     const int rtx = ctl.req_tx, rty = ctl.req_ty;
     g.sync();
     test_tiles(g, c, vol, A, ctl, rtx - A.halo, rty - A.halo, rtx + A.halo, rty + A.halo);
-    if (g.tid() == 0) {
+    if (g.warp() == 0) {
+      // one warp walks, in lock step (dfs_run)
       int st;
       const long long w0 = xs_clock();
+      bool start = true;
       if (first) {
         uint32_t* w = &A.bits[(size_t)cv * A.stride + (cu >> 5)];
-        if (!((*w >> (cu & 31)) & 1u)) {
-          st = ST_DONE; ctl.n = 0;
-        } else {
+        const bool centre_fg = ((*w >> (cu & 31)) & 1u) != 0u;
+        g.converge();
+        if (!centre_fg) {
+          start = false;
+          if (g.lane() == 0) ctl.n = 0;
+        } else if (g.lane() == 0) {
           *w &= ~(1u << (cu & 31));
           const CellT p = P::pack(cu, cv);
           A.order[0] = p; A.stack[0] = p;
           ctl.n = 1; ctl.depth = 1;
-          st = dfs_run(A, ctl);
         }
-      } else {
-        st = dfs_run(A, ctl);
+        g.converge();
       }
-      ctl.t[5] += (uint32_t)(xs_clock() - w0);
-      ctl.status = st;
+      st = start ? dfs_run(A, ctl, g.lane()) : ST_DONE;
+      if (g.lane() == 0) {
+        ctl.t[5] += (uint32_t)(xs_clock() - w0);
+        ctl.status = st;
+      }
     }
     first = false;
     g.sync();
@@ -1130,6 +1199,7 @@ XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const 
   // data-dependent length, and without the re-join the lanes of a warp drift apart for the rest of the phase
   for (int r0 = 0; r0 < n; r0 += g.size()) {
     const int r = r0 + g.tid();
+    const long long tq0 = xs_clock();
     if (r < n) {
       V3 cur;
       const Sample s = sample_at(c, A, r, &cur);
@@ -1163,6 +1233,7 @@ XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const 
       }
       // claim every probed block; remember only the claims that WON at claim time: a sample can end up owning a
       // block only if it held it at some point, so the ownership pass re-checks those few instead of all ~20
+      if (g.tid() == 0) ctl.t[3] += (uint32_t)(xs_clock() - tq0);
       uint32_t tentative = 0u;
       while (cmask) {
         const int k = ffs32(cmask) - 1;
@@ -1225,6 +1296,7 @@ XS_D int emit_items(const G& g, const PlaneCtx& c, const VolView& vol, const Are
     g.converge();
   }
   g.sync();
+  if (g.tid() == 0) { const long long now = xs_clock(); ctl.t[4] += (uint32_t)(now - ctl.tmark); }
   // reserve the output ranges
   int m, npoly;
   {
