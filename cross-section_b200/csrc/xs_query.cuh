@@ -307,8 +307,11 @@ struct PackedHash {
   }
   // returns 0: table full (probe limit), 1: claimed but a smaller rank holds the block, 2: this rank holds it NOW
   // (it may still lose it to a smaller rank claiming later — "tentative owner")
-  XS_HD int claim(int bx, int by, int bz, uint32_t rank) const {
-    const uint32_t t = tag(bx, by, bz), word = (t << 9) | rank;
+  // tag of block b + o = tag of b + tag_delta(o)  (no carries between the 7-bit fields: blocks stay inside the window)
+  XS_HD uint32_t tag_delta(int ox, int oy, int oz) const { return (uint32_t)(ox + (oy << 7) + (oz << 14)); }
+  XS_HD int claim(int bx, int by, int bz, uint32_t rank) const { return claim_tag(tag(bx, by, bz), rank); }
+  XS_HD int claim_tag(uint32_t t, uint32_t rank) const {
+    const uint32_t word = (t << 9) | rank;
     uint32_t h = (t * 2654435761u) >> shift;
     for (int probes = 0; probes < max_probe; probes++) {
       uint32_t old = slot[h];
@@ -369,8 +372,10 @@ struct WideHash {
   template <class G> XS_D void clear(const G& g) const {
     for (uint32_t i = g.tid(); i < cap; i += g.size()) { htag[i] = XS_HEMPTY; hkey[i] = XS_HEMPTY; }
   }
-  XS_HD int claim(int bx, int by, int bz, uint32_t rank) const {   // 0 full / 1 not owner / 2 tentative owner
-    const uint32_t t = id(bx, by, bz);
+  XS_HD uint32_t tag(int bx, int by, int bz) const { return id(bx, by, bz); }
+  XS_HD uint32_t tag_delta(int ox, int oy, int oz) const { return (uint32_t)(ox + hx * (oy + hy * oz)); }
+  XS_HD int claim(int bx, int by, int bz, uint32_t rank) const { return claim_tag(id(bx, by, bz), rank); }
+  XS_HD int claim_tag(uint32_t t, uint32_t rank) const {   // 0 full / 1 not owner / 2 tentative owner
     uint32_t h = (t * 2654435761u) >> shift;
     for (int probes = 0; probes < max_probe; probes++) {
       const uint32_t old = atomic_cas_u32(&htag[h], XS_HEMPTY, t);
@@ -1199,7 +1204,7 @@ XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const 
   // data-dependent length, and without the re-join the lanes of a warp drift apart for the rest of the phase
   for (int r0 = 0; r0 < n; r0 += g.size()) {
     const int r = r0 + g.tid();
-    const long long tq0 = xs_clock();
+    uint32_t my_cmask = 0u, my_tag = 0u;
     if (r < n) {
       V3 cur;
       const Sample s = sample_at(c, A, r, &cur);
@@ -1231,20 +1236,32 @@ XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const 
           }
         }
       }
-      // claim every probed block; remember only the claims that WON at claim time: a sample can end up owning a
-      // block only if it held it at some point, so the ownership pass re-checks those few instead of all ~20
-      if (g.tid() == 0) ctl.t[3] += (uint32_t)(xs_clock() - tq0);
+      // claim every probed block (below); remember only the claims that WON at claim time: a sample can end up owning
+      // a block only if it held it at some point, so the ownership pass re-checks those few instead of all ~20
+      my_cmask = cmask; my_tag = hash.tag(bx, by, bz);
+    }
+    // claims, offset by offset in lock step: k is the same for every lane, so the offset decoding and the tag delta
+    // are computed once per warp instead of once per claim
+    {
       uint32_t tentative = 0u;
-      while (cmask) {
-        const int k = ffs32(cmask) - 1;
-        cmask &= cmask - 1u;
+#ifdef __CUDA_ARCH__
+      const uint32_t any = __reduce_or_sync(0xffffffffu, my_cmask);
+#else
+      const uint32_t any = my_cmask;
+#endif
+#pragma unroll 1
+      for (int k = 0; k < 27; k++) {
+        if (!((any >> k) & 1u)) continue;            // warp-uniform
         int ox, oy, oz;
         decode_k(k, ox, oy, oz);
-        const int won = hash.claim(bx + ox, by + oy, bz + oz, (uint32_t)r);
-        if (won == 0) ovf = true;
-        if (won == 2) tentative |= 1u << k;
+        const uint32_t dt = hash.tag_delta(ox, oy, oz);
+        if ((my_cmask >> k) & 1u) {
+          const int won = hash.claim_tag(my_tag + dt, (uint32_t)r);
+          if (won == 0) ovf = true;
+          if (won == 2) tentative |= 1u << k;
+        }
       }
-      A.mask[r] = tentative;
+      if (r < n) A.mask[r] = tentative;
     }
     g.converge();
   }
@@ -1296,7 +1313,6 @@ XS_D int emit_items(const G& g, const PlaneCtx& c, const VolView& vol, const Are
     g.converge();
   }
   g.sync();
-  if (g.tid() == 0) { const long long now = xs_clock(); ctl.t[4] += (uint32_t)(now - ctl.tmark); }
   // reserve the output ranges
   int m, npoly;
   {
