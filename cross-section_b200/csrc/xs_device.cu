@@ -480,17 +480,53 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) section_block_kernel(VolView v
 }
 
 // ------------------------------------------------------------------------------------------------
-// polygon kernel: one thread per polygon record, no shared memory, full occupancy
+// polygon kernel.  About half of the records are cubes the plane misses (value exactly 0) and the rest differ in
+// vertex count, so one-thread-per-record leaves most lanes idle.  Each warp therefore FILTERS 32 records at a time
+// (one dot product each), writes the zeros, queues the survivors in shared memory and evaluates them 32 at a time,
+// all lanes busy; unit voxels and 2x2x2 blocks run through the same instruction stream (run-time cube side).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) poly_eval_kernel(const PolyRec* __restrict__ polys, const PlaneGeom* __restrict__ geom,
-                                                        float* __restrict__ vals, const uint32_t* __restrict__ count_ptr,
-                                                        uint32_t start, uint32_t cap) {
+constexpr int POLY_THREADS = 256;
+__global__ void __launch_bounds__(POLY_THREADS) poly_eval_kernel(const PolyRec* __restrict__ polys, const PlaneGeom* __restrict__ geom,
+                                                                 float* __restrict__ vals, const uint32_t* __restrict__ count_ptr,
+                                                                 uint32_t start, uint32_t cap) {
+  __shared__ uint32_t queue_all[POLY_THREADS / 32][64];
+  uint32_t* queue = queue_all[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
   uint32_t n = *count_ptr;
   if (n > cap) n = cap;
-  for (uint32_t i = start + blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const PolyRec r = polys[i];
-    const PlaneGeom g = geom[r.q];
-    vals[i] = poly_eval(r, g);
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int qn = 0;
+  for (uint32_t base = start + wid * 32u; base < n; base += nwarps * 32u) {
+    const uint32_t i = base + (uint32_t)lane;
+    bool near = false;
+    if (i < n) {
+      const PolyRec r = polys[i];
+      const PlaneGeom* gp = geom + r.q;
+      const V3 pos = mk(__ldg(&gp->pos.x), __ldg(&gp->pos.y), __ldg(&gp->pos.z));
+      const V3 nn = mk(__ldg(&gp->n.x), __ldg(&gp->n.y), __ldg(&gp->n.z));
+      near = !plane_cube_far((int)r.kind, (float)r.x, (float)r.y, (float)r.z, pos, nn);
+      if (!near) vals[i] = 0.0f;
+    }
+    const uint32_t ball = __ballot_sync(0xffffffffu, near);
+    if (near) queue[qn + __popc(ball & ((1u << lane) - 1u))] = i;
+    qn += __popc(ball);
+    __syncwarp();
+    if (qn >= 32) {
+      const uint32_t j = queue[lane];
+      const PolyRec r = polys[j];
+      vals[j] = poly_eval(r, geom[r.q]);
+      const uint32_t rest = (lane + 32 < qn) ? queue[lane + 32] : 0u;
+      __syncwarp();
+      queue[lane] = rest;
+      qn -= 32;
+      __syncwarp();
+    }
+  }
+  if (lane < qn) {
+    const uint32_t j = queue[lane];
+    const PolyRec r = polys[j];
+    vals[j] = poly_eval(r, geom[r.q]);
   }
 }
 

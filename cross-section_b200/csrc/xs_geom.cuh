@@ -1,8 +1,8 @@
 // xs_geom.cuh — plane ∩ cube polygon, polygon area, 2x2x2 block value and block adjacency.
 //
 // Behavioural spec: SURVEY.md Appendix A.  Reference functions replaced (file:line in /root/reference/src):
-//   plane_cube_points<1>  <- check_intersections_1x1x1   xs3d.hpp:238-359
-//   plane_cube_points<2>  <- check_intersections_2x2x2   xs3d.hpp:102-236
+//   plane_cube_points(S=1)  <- check_intersections_1x1x1   xs3d.hpp:238-359
+//   plane_cube_points(S=2)  <- check_intersections_2x2x2   xs3d.hpp:102-236
 //   polygon_area          <- xs3d::area::points_to_area   area.hpp:211-228 (+ :14-24, :37-52, :68-143, :147-207)
 //   block_value           <- calc_area_at_point_2x2x2     xs3d.hpp:361-440
 //   blocks_adjacent       <- is_26_connected              xs3d.hpp:537-646
@@ -58,17 +58,25 @@ XS_HD bool poly_has(const Poly& q, V3 v) {
   return dup;
 }
 
+// The plane passes too far from the cube's centre to touch it (xs3d.hpp:270 / :138): the polygon is empty.
+XS_HD bool plane_cube_far(int S, float x, float y, float z, V3 pos, V3 n) {
+  const V3 low = mk(x, y, z);
+  const V3 centre = (S == 1) ? low : vadd(low, mk(0.5f, 0.5f, 0.5f));
+  const float dist = fabsf(vdot(vsub(centre, pos), n));
+  return dist > (S == 1 ? XS_FAR1 : XS_FAR2);
+}
+
 // Intersect the plane with the 12 edges of the cube of side S whose low voxel is (x,y,z)
 // (S=1: the voxel itself, spanning [x-.5,x+.5]; S=2: the block spanning [x-.5,x+1.5]).
 // Edge order, corner de-duplication and the 4/6 vertex cap follow xs3d.hpp:183-233 / 307-358.
-template <int S>
-XS_HD void plane_cube_points(float x, float y, float z, const PlaneGeom& g, Poly& q) {
+// S is a run-time value (1 or 2) so that unit voxels and 2x2x2 blocks share one instruction stream in the polygon
+// kernel; every constant is selected, never computed, so the arithmetic is that of the two reference functions.
+XS_HD void plane_cube_points(int S, float x, float y, float z, const PlaneGeom& g, Poly& q) {
   q.n = 0;
   const float fS = (float)S;
   const V3 low = mk(x, y, z);
   const V3 centre = (S == 1) ? low : vadd(low, mk(0.5f, 0.5f, 0.5f));
-  const float dist = fabsf(vdot(vsub(centre, g.pos), g.n));
-  if (dist > (S == 1 ? XS_FAR1 : XS_FAR2)) return;
+  if (plane_cube_far(S, x, y, z, g.pos, g.n)) return;
 
   const V3 minpt = vadd(low, mk(-0.5f, -0.5f, -0.5f));
   const V3 rel = vsub(g.pos, minpt);
@@ -176,12 +184,18 @@ XS_HD float polygon_area(const Poly& q, const PlaneGeom& g) {
 
 XS_HD float voxel_area(float x, float y, float z, const PlaneGeom& g) {
   Poly q;
-  plane_cube_points<1>(x, y, z, g, q);
+  plane_cube_points(1, x, y, z, g, q);
+  return polygon_area(q, g);
+}
+// kind = cube side (1: unit voxel, 2: 2x2x2 block), one code path for both
+XS_HD float cube_polygon_area(int S, float x, float y, float z, const PlaneGeom& g) {
+  Poly q;
+  plane_cube_points(S, x, y, z, g, q);
   return polygon_area(q, g);
 }
 XS_HD float block_polygon_area(float bx, float by, float bz, const PlaneGeom& g) {
   Poly q;
-  plane_cube_points<2>(bx, by, bz, g, q);
+  plane_cube_points(2, bx, by, bz, g, q);
   return polygon_area(q, g);
 }
 

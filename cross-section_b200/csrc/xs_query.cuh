@@ -1424,8 +1424,7 @@ XS_D int run_area_emit(const G& g, const PlaneCtx& c, const VolView& vol, const 
 
 // Step 5: one polygon record -> its anisotropy-scaled area.
 XS_HD float poly_eval(const PolyRec& r, const PlaneGeom& g) {
-  if (r.kind == 2) return block_polygon_area((float)r.x, (float)r.y, (float)r.z, g);
-  return voxel_area((float)r.x, (float)r.y, (float)r.z, g);
+  return cube_polygon_area((int)r.kind, (float)r.x, (float)r.y, (float)r.z, g);
 }
 
 // Step 6a: value of one item from the values of its polygons (xs3d.hpp:420-437), in record order.
