@@ -176,6 +176,7 @@ struct BatchArgs {
 };
 enum { CNT_NEXT0 = 0, CNT_OVER0 = 1, CNT_NEXT1 = 2, CNT_OVER1 = 3, CNT_NEXT2 = 4, CNT_OVER2 = 5, CNT_NEXT3 = 6, CNT_OVER3 = 7, CNT_WORDS = 8,
        CNT_NBIG = 48,                  // queries routed straight to the mid tier = prefix of the size-ordered list
+       CNT_BADN = 49,                  // a query with an all-zero normal was seen
        CNT_HIST = 128, CNT_CURSOR = 384, CNT_TOTAL_WORDS = 640 };
 #define XS_LATE_EMPTY 0xffffffffu
 #define XS_LATE_CLAIMED 0xfffffffeu
@@ -581,7 +582,8 @@ __global__ void __launch_bounds__(128) combine_kernel(const ItemRec* __restrict_
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) classify_kernel(VolView vol, const float* __restrict__ pos, const float* __restrict__ nrm,
                                                        float wx, float wy, float wz, uint32_t nq, uint8_t* __restrict__ key,
-                                                       uint32_t* __restrict__ hist, uint32_t* __restrict__ late, QInfo* __restrict__ qinfo) {
+                                                       uint32_t* __restrict__ hist, uint32_t* __restrict__ late, QInfo* __restrict__ qinfo,
+                                                       uint32_t* __restrict__ bad_normal) {
   const int lane = threadIdx.x & 31;
   for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < nq; q += (gridDim.x * blockDim.x) >> 5) {
     PlaneCtx c;
@@ -601,6 +603,7 @@ __global__ void __launch_bounds__(256) classify_kernel(VolView vol, const float*
       const uint32_t k = ok ? (uint32_t)(cnt < 1 ? 1 : (cnt > 255 ? 255 : cnt)) : 0u;
       key[q] = (uint8_t)k;
       atomicAdd(&hist[k], 1u);
+      if (n.x == 0.0f && n.y == 0.0f && n.z == 0.0f) *bad_normal = 1u;   // reported as an argument error after the batch
       late[q] = XS_LATE_EMPTY;
       qinfo[q].status = QS_PENDING;   // (a stale READY from the previous batch would let the wrong pipeline's combine kernel write area[q])
     }
@@ -982,7 +985,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     if (!single) {
       // pre-pass: size estimate per query -> list ordered largest first; its head goes straight to the mid tier
       const int cgrid = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)v->sm_count * 8);
-      classify_kernel<<<cgrid, 256, 0, s1>>>(a.vol, d_pos, d_nrm, w[0], w[1], w[2], (uint32_t)n, (uint8_t*)v->keys.p, d_cnt + CNT_HIST, list0, out1.qinfo);
+      classify_kernel<<<cgrid, 256, 0, s1>>>(a.vol, d_pos, d_nrm, w[0], w[1], w[2], (uint32_t)n, (uint8_t*)v->keys.p, d_cnt + CNT_HIST, list0, out1.qinfo, d_cnt + CNT_BADN);
       CK(cudaGetLastError());
       const int ogrid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)v->sm_count);
       order_kernel<<<ogrid, 256, 0, s1>>>((const uint8_t*)v->keys.p, d_cnt + CNT_HIST, d_cnt + CNT_CURSOR, sorted, (uint32_t)n, d_cnt + CNT_NBIG, v->mid_key ? v->mid_key : MID_BIG_KEY);
@@ -1057,6 +1060,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     CK(cudaStreamSynchronize(s1));
     v->timing_pending = single ? 2 : 1;   // event durations are read on demand (xs3d_volume_timing): ten driver calls off the hot path
     v->timing[3] = 0.0f;
+    if (v->h_counters[CNT_BADN]) return fail(XS3D_ERR_ARG, "normal vector must not be a null vector (all zeros).");
     const uint32_t over0 = v->h_counters[CNT_OVER0], over1 = v->h_counters[CNT_OVER1], over2 = v->h_counters[CNT_OVER2];
     const uint32_t* he1 = v->h_counters + 64;
     const uint32_t* he2 = v->h_counters + 68;
@@ -1124,6 +1128,15 @@ extern "C" int xs3d_area_batch(xs3d_volume* v, uint64_t n, const float* pos, con
     return XS3D_OK;
   }
   RET(ensure_batch_workspace(v, n));
+  // an all-zero normal is an argument error (the reference raises ValueError, xs3d/__init__.py:72-75): host buffers and
+  // tiny device batches are checked here, large device batches by the pre-pass kernel
+  if (mem == XS3D_HOST || n < 4) {
+    float tmp[9];
+    const float* hn = normal;
+    if (mem != XS3D_HOST) { CK(cudaMemcpyAsync(tmp, normal, n * 12, cudaMemcpyDeviceToHost, v->stream)); CK(cudaStreamSynchronize(v->stream)); hn = tmp; }
+    for (uint64_t i = 0; i < n; i++)
+      if (hn[3 * i] == 0.0f && hn[3 * i + 1] == 0.0f && hn[3 * i + 2] == 0.0f) return fail(XS3D_ERR_ARG, "normal vector must not be a null vector (all zeros).");
+  }
   const float* d_pos = pos; const float* d_nrm = normal;
   float* d_area = area; uint8_t* d_contact = contact;
   if (mem == XS3D_HOST) {
@@ -1156,6 +1169,8 @@ extern "C" int xs3d_area_sweep_host(xs3d_volume* v, const uint8_t* binimg, int c
     v->loaded = true;
     return XS3D_OK;
   }
+  for (uint64_t i = 0; i < n; i++)
+    if (normal[3 * i] == 0.0f && normal[3 * i + 1] == 0.0f && normal[3 * i + 2] == 0.0f) return fail(XS3D_ERR_ARG, "normal vector must not be a null vector (all zeros).");
   RET(ensure_batch_workspace(v, n));
   RET(v->raw.ensure(voxels + 64));
   CK(cudaMemcpyAsync(v->q_pos.p, pos, n * 12, cudaMemcpyHostToDevice, v->stream));

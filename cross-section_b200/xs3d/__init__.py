@@ -184,6 +184,7 @@ class Volume:
   def set_stream(self, cuda_stream):
     """Launch on the given cudaStream_t handle (e.g. torch.cuda.current_stream().cuda_stream)."""
     _abi.check(self._lib.xs3d_volume_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+    self._stream = int(cuda_stream)
 
   def profile(self):
     """Per-phase SM cycles of the last batch (thread 0 of each query group, summed over queries)."""
@@ -208,14 +209,19 @@ class Volume:
       import torch
       pos = positions.to(dtype=torch.float32).contiguous().reshape(-1, 3)
       nrm = normals.to(dtype=torch.float32, device=pos.device).contiguous().reshape(-1, 3)
-      if bool((nrm == 0).all(dim=1).any()):
-        raise ValueError("normal vector must not be a null vector (all zeros).")
       n = pos.shape[0]
       area = torch.empty(n, dtype=torch.float32, device=pos.device)
       contact = torch.empty(n, dtype=torch.uint8, device=pos.device)
-      torch.cuda.current_stream(pos.device).synchronize()
-      _abi.check(self._lib.xs3d_area_batch(self._h, n, pos.data_ptr(), nrm.data_ptr(), _abi.fptr(w), DEVICE,
-                                           area.data_ptr(), contact.data_ptr()))
+      cur = torch.cuda.current_stream(pos.device)
+      if getattr(self, "_stream", None) != cur.cuda_stream:
+        cur.synchronize()              # the library launches on another stream: order it after the producers of pos / nrm
+      try:
+        _abi.check(self._lib.xs3d_area_batch(self._h, n, pos.data_ptr(), nrm.data_ptr(), _abi.fptr(w), DEVICE,
+                                             area.data_ptr(), contact.data_ptr()))
+      except XS3DError as e:           # null normals are detected on the device (no host round trip before the batch)
+        if "null vector" in str(e):
+          raise ValueError("normal vector must not be a null vector (all zeros).") from None
+        raise
       return (area, contact) if return_contact else area
     pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
     nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)

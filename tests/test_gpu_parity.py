@@ -321,3 +321,23 @@ def test_select_label_and_skeleton_sweep(xs, oracle):
   nrm = xs.skeleton_tangents(verts, edges)
   oa, oc = oracle.area_batch(vol, verts.astype(np.float32), nrm, [32, 32, 40])
   assert np.array_equal(bits(a), bits(oa)) and np.array_equal(c, oc)
+
+
+def test_null_normal_is_rejected_on_every_path(xs):
+  """An all-zero normal is a ValueError in the reference (xs3d/__init__.py:72-75): host arrays are checked before
+  the batch, CUDA tensors by the pre-pass kernel (no host round trip before the launch)."""
+  import torch
+  from xs3d import synthetic
+  vol, verts, tans = synthetic.make_neurite(128, seed=0, n_branches=4)
+  qp, qn = synthetic.draw_queries(verts, tans, 64, seed=1)
+  qn = qn.copy(); qn[17] = 0
+  with xs.Volume(vol) as V:
+    with pytest.raises(ValueError):
+      V.cross_sectional_area_batch(qp, qn, [32, 32, 40])
+    with pytest.raises(ValueError):
+      V.cross_sectional_area_batch(torch.from_numpy(qp).cuda(), torch.from_numpy(qn).cuda(), [32, 32, 40])
+    with pytest.raises(ValueError):
+      V.cross_sectional_area_batch(torch.from_numpy(qp[16:18]).cuda(), torch.from_numpy(qn[16:18]).cuda(), [32, 32, 40])
+    a = V.cross_sectional_area_batch(torch.from_numpy(qp[:16]).cuda(), torch.from_numpy(qn[:16]).cuda(), [32, 32, 40])
+    b = V.cross_sectional_area_batch(qp[:16], qn[:16], [32, 32, 40])
+    assert np.array_equal(bits(a.cpu().numpy()), bits(b))
