@@ -1005,6 +1005,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10);
       CK(cudaGetLastError());
       CK(cudaEventRecord(v->evs[1], s2));
+      if (getenv("XS3D_SERIAL")) { CK(cudaEventRecord(v->evf[2], s2)); CK(cudaStreamWaitEvent(s1, v->evf[2], 0)); CK(cudaStreamWaitEvent(v->stream3, v->evf[2], 0)); }   // dev: no overlap
       // ---- third stream: warp-tier grid B
       CK(cudaStreamWaitEvent(v->stream3, v->evf[0], 0));
       a.out = out1; a.list_in = sorted; a.list_out = list0;

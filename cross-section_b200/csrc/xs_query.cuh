@@ -123,6 +123,23 @@ XS_HD bool cell_fg(const PlaneCtx& c, const VolView& v, int i, int j) {
   return vox_fg(v, (int)r.x, (int)r.y, (int)r.z);
 }
 
+// cell_fg split in two so that several cells' volume loads can be in flight at once: where to look (block index and
+// bit within its occupancy byte), or false when the cell is outside the lattice / the volume.
+XS_HD bool cell_probe(const PlaneCtx& c, const VolView& v, int i, int j, uint32_t* cube, uint32_t* bit) {
+  *cube = 0u; *bit = 0u;
+  if (i < 0 || j < 0 || i >= c.psx || j >= c.psx) return false;
+  const V3 p = cell_point(c, i, j);
+  if (p.x < -0.5f || p.y < -0.5f || p.z < -0.5f) return false;
+  if (p.x >= c.lim[0] || p.y >= c.lim[1] || p.z >= c.lim[2]) return false;
+  if (!(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z)) return false;
+  const V3 r = vround(p);
+  if (r.x < 0.0f || r.y < 0.0f || r.z < 0.0f) return false;
+  const int x = (int)r.x, y = (int)r.y, z = (int)r.z;
+  *cube = cube_index(v, x >> 1, y >> 1, z >> 1);
+  *bit = (uint32_t)((x & 1) | ((y & 1) << 1) | ((z & 1) << 2));
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Thread-group policies.  WarpGroup: one warp per query (T0).  BlockGroup: one CTA per query (T1).
 // HostGroup: a single host thread, test builds only.
@@ -814,18 +831,30 @@ XS_D void nbr_sample_tiles(const G& g, const PlaneCtx& c, const VolView& vol, co
 #endif
     todo &= todo - 1ull;
     const int tx = t & ((1 << ntl) - 1), ty = t >> ntl;
-    for (int row = g.warp(); row < 32; row += g.nwarps()) {
-      const int v = ty * 32 + row;
-      uint32_t word;
 #ifdef __CUDA_ARCH__
-      word = __ballot_sync(0xffffffffu, cell_fg(c, vol, A.ox + tx * 32 + g.lane(), A.oy + v));
-      if (g.lane() == 0) frow(A, v)[tx] = word;
+    // four rows at a time: their four volume loads are issued before the first ballot needs its answer
+    for (int row0 = 4 * g.warp(); row0 < 32; row0 += 4 * g.nwarps()) {
+      uint32_t cube[4], bit[4];
+      bool ok[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) ok[j] = cell_probe(c, vol, A.ox + tx * 32 + g.lane(), A.oy + ty * 32 + row0 + j, &cube[j], &bit[j]);
+      uint32_t cb[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) cb[j] = cube_load(vol, cube[j]);     // (index 0 when the cell is outside: a valid address)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t word = __ballot_sync(0xffffffffu, ok[j] && ((cb[j] >> bit[j]) & 1u));
+        if (g.lane() == 0) frow(A, ty * 32 + row0 + j)[tx] = word;
+      }
+    }
 #else
-      word = 0;
+    for (int row = 0; row < 32; row++) {
+      const int v = ty * 32 + row;
+      uint32_t word = 0;
       for (int l = 0; l < 32; l++) word |= (uint32_t)cell_fg(c, vol, A.ox + tx * 32 + l, A.oy + v) << l;
       frow(A, v)[tx] = word;
-#endif
     }
+#endif
   }
 }
 
@@ -906,10 +935,11 @@ XS_D void nbr_masks(const G& g, const Arena<CellT>& A, unsigned long long done) 
 #endif
         const int u = tx * 32 + l;
         const uint32_t am = (uint32_t)(xm >> l) & 7u, a0 = (uint32_t)(x0 >> l) & 7u, aq = (uint32_t)(xq >> l) & 7u;   // bits: u-1, u, u+1
-        if ((a0 & 2u) && u > 0 && v > 0 && u < W - 1 && v < W - 1) {
+        if (a0 & 2u) {
+          const bool inner = u > 0 && v > 0 && u < W - 1 && v < W - 1;
           const uint32_t m = ((aq >> 2) & 1u) | ((aq & 1u) << 1) | (((am >> 2) & 1u) << 2) | ((am & 1u) << 3) |
                              (((aq >> 1) & 1u) << 4) | (((am >> 1) & 1u) << 5) | (((a0 >> 2) & 1u) << 6) | ((a0 & 1u) << 7);
-          A.cells[(v << A.wlog) + u] = (uint8_t)m;
+          A.cells[(v << A.wlog) + u] = (uint8_t)(inner ? m : 0u);   // a ring cell is a dead end: the walk stops there (overflow)
         }
       }
     }
@@ -1028,32 +1058,37 @@ __device__ __forceinline__ int dfs_run_nbr_warp(const Arena<uint16_t>& A, int& n
   const int half = A.stack_cap / 2;
   const int l6 = lane % 6;
   const int vr = l6 >> 1;
-  const uint32_t vh4 = pin_u32(4u * (uint32_t)(l6 & 1), scratch32), vh32 = pin_u32(32u * (uint32_t)(l6 & 1), scratch32);
+  const bool hiword = (l6 & 1) != 0;
+  const uint32_t vh4 = pin_u32(hiword ? 4u : 0u, scratch32);
   const uint32_t vsel = pin_u32(s_cells + (uint32_t)((vr - 1) * W - 1), scratch32);   // + ci = address of the first of this lane's three cells
-  const uint32_t vclr = pin_u32(nbr_row_clear(vr), scratch32);
+  // the clear mask of this lane's word = upper half of (fhi:flo) << 8 * (address & 3)
+  const uint32_t fhi = pin_u32(hiword ? 0u : nbr_row_clear(vr), scratch32), flo = pin_u32(hiword ? nbr_row_clear(vr) : 0u, scratch32);
   const uint32_t lim = (uint32_t)(W - 2);
   const bool lane0 = pin_u32((uint32_t)lane, scratch32) == 0u;
   int status;
+  int budget = 0;   // steps that can be taken before `order` or the stack ring may be full (re-evaluated when it runs out)
   uint32_t m = lds_u8(s_cells + (uint32_t)ci);
   for (;;) {
     while (m != 0u) {
       ci += lds_s16(s_lut + 2u * m);
-      const uint32_t m_next = lds_u8(s_cells + (uint32_t)ci);     // loads first (in range: the arrays are padded by a row) ...
+      const uint32_t m_next = lds_u8(s_cells + (uint32_t)ci);     // loads first (in range: the arrays are padded by a row)
       const uint32_t vb = vsel + (uint32_t)ci;
       const uint32_t va = (vb & ~3u) + vh4;
       const uint32_t vold = lds_u32(va);
       if ((m & (m - 1u)) == 0u) depth--;                           // tail call: the cell we leave has nothing left, reuse its frame
-      const uint32_t u = (uint32_t)ci & (uint32_t)(W - 1), v = (uint32_t)ci >> A.wlog;
-      if (((u - 1u) >= lim) | ((v - 1u) >= lim) | (n >= max_n) | (depth - lo == cap)) {   // ... rare cases after
-        if (((u - 1u) >= lim) | ((v - 1u) >= lim) | (n >= max_n)) { status = ST_OVERFLOW; goto out; }
-        // ring full: spill the lower half
-        const int nlo = lo + half;
-        for (int dd = lo + lane; dd < nlo; dd += 32) spill[dd] = (uint16_t)lds_u16(s_stack + 2u * (uint32_t)(dd & smask));
-        __syncwarp();
-        lo = nlo;
+      if (--budget < 0) {
+        if (n >= max_n) { status = ST_OVERFLOW; goto out; }
+        if (depth - lo == cap) {
+          // ring full: spill the lower half
+          const int nlo = lo + half;
+          for (int dd = lo + lane; dd < nlo; dd += 32) spill[dd] = (uint16_t)lds_u16(s_stack + 2u * (uint32_t)(dd & smask));
+          __syncwarp();
+          lo = nlo;
+        }
+        const int room_n = max_n - n, room_s = cap - (depth - lo);
+        budget = (room_n < room_s ? room_n : room_s) - 1;
       }
-      const unsigned long long c64 = (unsigned long long)vclr << (8u * (vb & 3u));
-      sts_u32(va, vold & ~(uint32_t)(c64 >> vh32));
+      sts_u32(va, vold & ~__funnelshift_l(flo, fhi, vb << 3));
       if (lane0) {
         order[n] = (uint16_t)ci;
         sts_u16(s_stack + 2u * (uint32_t)(depth & smask), (uint32_t)ci);
@@ -1061,6 +1096,11 @@ __device__ __forceinline__ int dfs_run_nbr_warp(const Arena<uint16_t>& A, int& n
       n++;
       depth++;
       m = m_next;
+    }
+    // dead end.  A cell on the window's outer ring is one by construction (its byte is 0): the section leaves the window.
+    {
+      const uint32_t u = (uint32_t)ci & (uint32_t)(W - 1), v = (uint32_t)ci >> A.wlog;
+      if (((u - 1u) >= lim) | ((v - 1u) >= lim)) { status = ST_OVERFLOW; goto out; }
     }
     // dead end: drop the current frame, then find the topmost frame that still has an available neighbour
     __syncwarp();

@@ -23,7 +23,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
       os.environ.get("TAG", ""), float(np.median(ts[3:])), min(ts), t["warp_tier_ms"], t["mid_tier_ms"], t["mid_exposed_ms"], t["prepass_ms"],
       t["polygon_ms"], t["combine_ms"], st["escalated_mid"], st["escalated_big"]), flush=True)
   sys.exit(0)
-for ctas in (148,):
-  for key in (22, 26, 30, 40):
-    env = dict(os.environ, XS3D_MID_CTAS=str(ctas), XS3D_MID_KEY=str(key), TAG="ctas=%d key=%d" % (ctas, key))
+for serial in (0, 1):
+  for ctas in (148, 296):
+    env = dict(os.environ, XS3D_MID_CTAS=str(ctas), TAG="serial=%d ctas=%d" % (serial, ctas))
+    if serial: env["XS3D_SERIAL"] = "1"
     subprocess.run([sys.executable, __file__, "child"], env=env)
