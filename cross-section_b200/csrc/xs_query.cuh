@@ -112,19 +112,8 @@ XS_HD V3 cell_point(const PlaneCtx& c, int i, int j) {
 // Cell is inside the volume (xs3d.hpp:888-893) and its rounded voxel is foreground (:895-907).
 // A coordinate of exactly -0.5 passes the reference's test and then rounds to -1 (UB cast);
 // such samples are treated as outside (documented divergence).
-XS_HD bool cell_fg(const PlaneCtx& c, const VolView& v, int i, int j) {
-  if (i < 0 || j < 0 || i >= c.psx || j >= c.psx) return false;
-  const V3 p = cell_point(c, i, j);
-  if (p.x < -0.5f || p.y < -0.5f || p.z < -0.5f) return false;
-  if (p.x >= c.lim[0] || p.y >= c.lim[1] || p.z >= c.lim[2]) return false;
-  if (!(p.x == p.x) || !(p.y == p.y) || !(p.z == p.z)) return false;
-  const V3 r = vround(p);
-  if (r.x < 0.0f || r.y < 0.0f || r.z < 0.0f) return false;
-  return vox_fg(v, (int)r.x, (int)r.y, (int)r.z);
-}
-
-// cell_fg split in two so that several cells' volume loads can be in flight at once: where to look (block index and
-// bit within its occupancy byte), or false when the cell is outside the lattice / the volume.
+// Split in two so that several cells' volume loads can be in flight at once: cell_probe says where to look (block
+// index and bit within its occupancy byte), or false when the cell is outside the lattice / the volume.
 XS_HD bool cell_probe(const PlaneCtx& c, const VolView& v, int i, int j, uint32_t* cube, uint32_t* bit) {
   *cube = 0u; *bit = 0u;
   if (i < 0 || j < 0 || i >= c.psx || j >= c.psx) return false;
@@ -138,6 +127,12 @@ XS_HD bool cell_probe(const PlaneCtx& c, const VolView& v, int i, int j, uint32_
   *cube = cube_index(v, x >> 1, y >> 1, z >> 1);
   *bit = (uint32_t)((x & 1) | ((y & 1) << 1) | ((z & 1) << 2));
   return true;
+}
+
+XS_HD bool cell_fg(const PlaneCtx& c, const VolView& v, int i, int j) {
+  uint32_t cube, bit;
+  if (!cell_probe(c, v, i, j, &cube, &bit)) return false;
+  return (cube_load(v, cube) >> bit) & 1u;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -480,22 +475,39 @@ XS_D void test_tiles(const G& g, const PlaneCtx& c, const VolView& vol, const Ar
   tx0 = tx0 < 0 ? 0 : tx0; ty0 = ty0 < 0 ? 0 : ty0;
   tx1 = tx1 >= A.tx ? A.tx - 1 : tx1; ty1 = ty1 >= A.ty ? A.ty - 1 : ty1;
   const int nx = tx1 - tx0 + 1, ny = ty1 - ty0 + 1;
+#ifdef __CUDA_ARCH__
+  // a unit = four consecutive rows of one tile: their four volume loads are issued before the first ballot needs its answer
+  const int units = nx * ny * 8;
+  for (int unit = g.warp(); unit < units; unit += g.nwarps()) {
+    const int row0 = (unit & 7) * 4, t = unit >> 3;
+    const int tx = tx0 + t % nx, ty = ty0 + t / nx;
+    if (tile_tested(A, tx, ty)) continue;   // warp-uniform
+    const int u0 = tx * 32;
+    uint32_t cube[4], bit[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) ok[j] = cell_probe(c, vol, A.ox + u0 + g.lane(), A.oy + ty * 32 + row0 + j, &cube[j], &bit[j]);
+    uint32_t cb[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) cb[j] = cube_load(vol, cube[j]);     // (index 0 when the cell is outside: a valid address)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t word = __ballot_sync(0xffffffffu, ok[j] && ((cb[j] >> bit[j]) & 1u));
+      if (g.lane() == 0) A.bits[(size_t)(ty * 32 + row0 + j) * A.stride + tx] = word;
+    }
+  }
+#else
   const int units = nx * ny * 32;
   for (int unit = g.warp(); unit < units; unit += g.nwarps()) {
     const int row = unit & 31, t = unit >> 5;
     const int tx = tx0 + t % nx, ty = ty0 + t / nx;
-    if (tile_tested(A, tx, ty)) continue;   // warp-uniform
+    if (tile_tested(A, tx, ty)) continue;
     const int v = ty * 32 + row, u0 = tx * 32;
-    uint32_t word;
-#ifdef __CUDA_ARCH__
-    word = __ballot_sync(0xffffffffu, cell_fg(c, vol, A.ox + u0 + g.lane(), A.oy + v));
-    if (g.lane() == 0) A.bits[(size_t)v * A.stride + tx] = word;
-#else
-    word = 0;
+    uint32_t word = 0;
     for (int l = 0; l < 32; l++) word |= (uint32_t)cell_fg(c, vol, A.ox + u0 + l, A.oy + v) << l;
     A.bits[(size_t)v * A.stride + tx] = word;
-#endif
   }
+#endif
   g.sync();
   if (g.tid() == 0) {
     for (int ty = ty0; ty <= ty1; ty++)
