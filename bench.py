@@ -178,7 +178,7 @@ def run_own_arm(args):
   for _ in range(max(3, args.warmup)):
     step_resident()
   sampler = ClockSampler(local)
-  if rank == 0:
+  if rank == 0 and not os.environ.get("XS_BENCH_NO_SMI"):
     sampler.start()
   barrier()
   starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]

@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) area_warp_kernel(BatchArgs a) {
   A.stack = reinterpret_cast<uint16_t*>(base + L::O_STACK); A.stack_cap = MAXN; A.spill = nullptr;
   A.mask = A.bits;
   A.cells = nullptr; A.wlog = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
+  A.compact_pairs = 1;
   PackedHash H;
   H.slot = base + L::O_HASH; H.cap = HCAP; H.max_probe = 48;
   int lg = 0;
@@ -303,6 +304,7 @@ __device__ __forceinline__ bool block_arena(Arena<uint32_t>& A, WideHash& H, con
   uint32_t* g_tested = p;
   A.max_n = s.max_n;
   A.cells = nullptr; A.wlog = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
+  A.compact_pairs = 0;          // masks live in the HBM slab
   H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
   H.hx = vol.hx; H.hy = vol.hy;
   H.alt_tag = nullptr; H.alt_key = nullptr; H.alt_cap = 0;
@@ -410,6 +412,7 @@ __global__ void __maxnreg__(96) area_mid_kernel(BatchArgs a, SlabCfg s, int cnt_
   A.stack = reinterpret_cast<uint16_t*>(smem + MidTier::O_RING); A.stack_cap = MidTier::RING;
   A.cells = reinterpret_cast<uint8_t*>(smem + MidTier::O_CELLS); A.wlog = MidTier::WLOG;
   A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = (1 << MidTier::WLOG) / 32; A.stride = 0; A.halo = 1;
+  A.compact_pairs = 0;          // masks live in the HBM slab
   A.fbits = smem + MidTier::O_FBITS; A.fstride = MidTier::FSTRIDE;
   A.nlut = reinterpret_cast<const int16_t*>(smem + MidTier::O_LUT);
   nbr_lut_fill(g, reinterpret_cast<int16_t*>(smem + MidTier::O_LUT), MidTier::WLOG);
@@ -1005,16 +1008,20 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10);
       CK(cudaGetLastError());
       CK(cudaEventRecord(v->evs[1], s2));
-      if (getenv("XS3D_SERIAL")) { CK(cudaEventRecord(v->evf[2], s2)); CK(cudaStreamWaitEvent(s1, v->evf[2], 0)); CK(cudaStreamWaitEvent(v->stream3, v->evf[2], 0)); }   // dev: no overlap
+      // profiling aid: under ncu every kernel runs alone, so the split of the warp tier into grids A and B would show
+      // grid B (10 warps per SM) doing all the work; XS3D_SINGLE_GRID=1 launches the warp tier as one grid of 3 CTAs per SM
+      const bool single_grid = getenv("XS3D_SINGLE_GRID") != nullptr;
       // ---- third stream: warp-tier grid B
       CK(cudaStreamWaitEvent(v->stream3, v->evf[0], 0));
       a.out = out1; a.list_in = sorted; a.list_out = list0;
       const int gridB = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * (T0_CTAS_PER_SM - 2));
-      T0_KERNEL<<<gridB, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, v->stream3>>>(a);
-      CK(cudaGetLastError());
+      if (!single_grid) {
+        T0_KERNEL<<<gridB, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, v->stream3>>>(a);
+        CK(cudaGetLastError());
+      }
       CK(cudaEventRecord(v->evf[3], v->stream3));
       // ---- launching stream: warp-tier grid A
-      const int gridA = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * 2);
+      const int gridA = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * (single_grid ? T0_CTAS_PER_SM : 2));
       T0_KERNEL<<<gridA, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, s1>>>(a);
       CK(cudaGetLastError());
       CK(cudaEventRecord(v->evf[1], s1));

@@ -162,6 +162,9 @@ struct WarpGroup {
     return inc - v;
   }
   __device__ uint32_t or_reduce(uint32_t v) const { return __reduce_or_sync(0xffffffffu, v); }
+  __device__ int shfl(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+  __device__ int wsize() const { return 32; }
+  __device__ int wexscan(int v, int& total) const { return exscan(v, total); }
 };
 
 struct BlockGroup {
@@ -195,6 +198,19 @@ struct BlockGroup {
     total = tot;
     return base + inc - v;
   }
+  __device__ int shfl(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+  __device__ int wsize() const { return 32; }
+  __device__ int wexscan(int v, int& total) const {   // exclusive scan within the calling warp
+    const int l = lane();
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (l >= d) inc += t;
+    }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+  }
   __device__ uint32_t or_reduce(uint32_t v) const {
     v = __reduce_or_sync(0xffffffffu, v);
     if (threadIdx.x == 0) scratch[34] = 0;
@@ -218,6 +234,9 @@ struct HostGroup {
   void converge() const {}
   int exscan(int v, int& total) const { total = v; return 0; }
   uint32_t or_reduce(uint32_t v) const { return v; }
+  int shfl(int v, int) const { return v; }
+  int wsize() const { return 1; }
+  int wexscan(int v, int& total) const { total = v; return 0; }
 };
 
 XS_HD uint32_t atomic_cas_u32(uint32_t* p, uint32_t cmp, uint32_t val) {
@@ -425,6 +444,7 @@ struct Arena {
   uint32_t* fbits;              // foreground bitmap of the window, one zero row / word of padding all round
   int fstride;                  //   words per row = (1<<wlog)/32 + 2
   const int16_t* nlut;          // neighbour byte -> cell-index delta of its first set bit
+  int compact_pairs;            // emit pass 1 evaluates compacted (sample, offset) pairs (needs `mask` in shared memory)
 };
 
 struct Ctl {          // lives in shared memory (one per group)
@@ -540,6 +560,13 @@ XS_HD int popcll64(unsigned long long x) {
   return __popcll(x);
 #else
   return __builtin_popcountll(x);
+#endif
+}
+XS_HD int popc32(uint32_t x) {
+#ifdef __CUDA_ARCH__
+  return __popc(x);
+#else
+  return __builtin_popcount(x);
 #endif
 }
 XS_HD int ffs32(uint32_t x) {
@@ -1335,30 +1362,77 @@ template <class G, class CellT, class H>
 XS_D int emit_items(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, const H& hash, Ctl& ctl,
                     uint32_t q, const EmitOut& out) {
   const int n = ctl.n;
-  // pass 1: which candidates become items; totals
+  // pass 1: which candidates become items; totals.  A sample has 0-5 tentative blocks, most have one: looping per
+  // sample leaves most lanes idle, so each warp first lists its (sample, offset) pairs in shared memory (the dead DFS
+  // stack) and then evaluates the pairs 32 at a time; the owning sample's block and centre mask arrive by shuffle.
   int my_items = 0, my_polys = 0;
+  const int pcap = A.stack_cap / g.nwarps();
+  CellT* const pairs = A.stack + (size_t)g.warp() * pcap;
   for (int r0 = 0; r0 < n; r0 += g.size()) {
     const int r = r0 + g.tid();
-    if (r < n) {
-      uint32_t cm = A.mask[r], keep = 0u;
-      if (cm) {
-        const Sample s = sample_at(c, A, r, (V3*)nullptr);
-        const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
-        const uint32_t centre = cube_at(vol, bx, by, bz);
-        while (cm) {
-          const int k = ffs32(cm) - 1;
-          cm &= cm - 1u;
+    const uint32_t tent = (r < n) ? A.mask[r] : 0u;
+    int bx = 0, by = 0, bz = 0;
+    uint32_t centre = 0u;
+    if (tent) {
+      const Sample s = sample_at(c, A, r, (V3*)nullptr);
+      bx = s.rx >> 1; by = s.ry >> 1; bz = s.rz >> 1;
+      centre = cube_at(vol, bx, by, bz);
+    }
+    int T;
+    int off = g.wexscan(popc32(tent), T);
+    if (A.compact_pairs && T <= pcap) {
+      if (r < n) A.mask[r] = 0u;                 // kept bits are OR-ed in below
+      uint32_t t = tent;
+      while (t) {
+        const int k = ffs32(t) - 1;
+        t &= t - 1u;
+        pairs[off++] = (CellT)((g.lane() << 5) | k);
+      }
+      g.converge();
+      for (int j0 = 0; j0 < T; j0 += g.wsize()) {
+        const int j = j0 + g.lane();
+        const bool act = j < T;
+        const int pr = act ? (int)pairs[j] : 0;
+        const int sl = pr >> 5, k = pr & 31;
+        const int sbx = g.shfl(bx, sl), sby = g.shfl(by, sl), sbz = g.shfl(bz, sl);
+        const uint32_t scentre = (uint32_t)g.shfl((int)centre, sl);
+        if (act) {
+          const int rr = r - g.lane() + sl;
           int ox, oy, oz;
           decode_k(k, ox, oy, oz);
-          if (hash.owner(bx + ox, by + oy, bz + oz) != (uint32_t)r) continue;         // someone with a smaller rank touched it first
-          const uint32_t cand = cube_at(vol, bx + ox, by + oy, bz + oz);
-          if (!blocks_adjacent(centre, cand, ox, oy, oz)) continue;                    // visited, but contributes nothing
-          const V3 ctr = vadd(mk((float)(2 * (bx + ox)), (float)(2 * (by + oy)), (float)(2 * (bz + oz))), mk(0.5f, 0.5f, 0.5f));
-          if (fabsf(vdot(vsub(ctr, c.g.pos), c.g.n)) > XS_FAR2) continue;             // block value is exactly 0
-          keep |= 1u << k;
-          my_items++;
-          my_polys += item_polys(cand);
+          bool keep = hash.owner(sbx + ox, sby + oy, sbz + oz) == (uint32_t)rr;       // else: someone with a smaller rank touched it first
+          uint32_t cand = 0u;
+          if (keep) {
+            cand = cube_at(vol, sbx + ox, sby + oy, sbz + oz);
+            keep = blocks_adjacent(scentre, cand, ox, oy, oz);                         // else: visited, but contributes nothing
+          }
+          if (keep) {
+            const V3 ctr = vadd(mk((float)(2 * (sbx + ox)), (float)(2 * (sby + oy)), (float)(2 * (sbz + oz))), mk(0.5f, 0.5f, 0.5f));
+            keep = !(fabsf(vdot(vsub(ctr, c.g.pos), c.g.n)) > XS_FAR2);               // else: block value is exactly 0
+          }
+          if (keep) {
+            atomic_or_u32(&A.mask[rr], 1u << k);
+            my_items++;
+            my_polys += item_polys(cand);
+          }
         }
+      }
+    } else if (r < n) {
+      // more pairs than the scratch holds: one sample per lane
+      uint32_t cm = tent, keep = 0u;
+      while (cm) {
+        const int k = ffs32(cm) - 1;
+        cm &= cm - 1u;
+        int ox, oy, oz;
+        decode_k(k, ox, oy, oz);
+        if (hash.owner(bx + ox, by + oy, bz + oz) != (uint32_t)r) continue;
+        const uint32_t cand = cube_at(vol, bx + ox, by + oy, bz + oz);
+        if (!blocks_adjacent(centre, cand, ox, oy, oz)) continue;
+        const V3 ctr = vadd(mk((float)(2 * (bx + ox)), (float)(2 * (by + oy)), (float)(2 * (bz + oz))), mk(0.5f, 0.5f, 0.5f));
+        if (fabsf(vdot(vsub(ctr, c.g.pos), c.g.n)) > XS_FAR2) continue;
+        keep |= 1u << k;
+        my_items++;
+        my_polys += item_polys(cand);
       }
       A.mask[r] = keep;
     }
