@@ -10,7 +10,7 @@ queries of the skeleton sweep against the 512^3 neurite volume.
   e2e   : the same sweep through the C ABI with HOST buffers: every step uploads the 128 MiB volume and the
           queries from pinned host memory, ingests, runs, and reads areas + contact bits back.
   roofline     : the dominant kernel (warp-tier query kernel), algorithmic bytes / CUDA-event duration vs the
-                 measured HBM peak (MEASURED_PEAKS.json).
+                 measured HBM peak (MEASURED_PEAKS.json).  The mid / big tiers run beside it on a second stream.
   cpu_baseline : the compiled reference (oracle/_ref, else the C port) fanned out over all host cores.
 N > 1: one process per GPU (torchrun), queries partitioned with no data-path collective (weak scaling:
 each rank sweeps its own 10 000-query draw); the volume's occupancy bytes are NCCL-broadcast once at setup.
@@ -326,12 +326,12 @@ def run_own_arm(args):
   achieved = alg_bytes / (dom_ms / 1000.0) / 1e9
   kname = {"warp_tier_ms": "area_warp_kernel", "mid_tier_ms": "area_mid_kernel", "big_tier_ms": "area_block_kernel<BigTier>", "polygon_ms": "poly_eval_kernel"}[dom]
   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
-  # (profiles/r1e_ncu_full_summary.txt, profiles/r1e_per_kernel_hbm_l2.txt)
-  ncu_traffic = {"area_warp_kernel": 2857728 + 4352, "area_mid_kernel": 2069504, "poly_eval_kernel": 16358656, "combine_kernel": 12110592}
+  # (profiles/r1g_ncu_full_summary.txt, profiles/r1g_per_kernel_hbm_l2.txt)
+  ncu_traffic = {"area_warp_kernel": 3032320, "area_mid_kernel": 1099520 + 1297152, "poly_eval_kernel": 14566144 + 1940736, "combine_kernel": 10696704 + 1583616}
   roofline = {"bound": "hbm", "kernel": kname,
               "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic.get(kname),
               "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms, "queries_in_kernel": nq_k,
-              "note": "latency/issue-bound graph walk over the L2-resident 16 MiB occupancy volume, not an HBM stream (ncu: DRAM < 0.1 %, L2 hit 69-87 %); the HBM-bound kernel of the path is the ingest, reported beside it",
+              "note": "latency/issue-bound graph walk over the L2-resident 16 MiB occupancy volume, not an HBM stream (ncu: DRAM 0.1 % of peak, L2 hit 82 %, IPC 2.6/SM); the HBM-bound kernel of the path is the ingest, reported beside it",
               "ingest_kernel": {"ms": ingest_ms, "achieved": (vol.size * 1.125) / (ingest_ms / 1000.0) / 1e9 if ingest_ms > 0 else None,
                                 "unit": "GB/s", "frac": ((vol.size * 1.125) / (ingest_ms / 1000.0) / 1e9 / peak) if ingest_ms > 0 else None,
                                 "algorithmic_bytes": int(vol.size * 1.125)}}
