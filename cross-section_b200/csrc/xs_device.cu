@@ -177,6 +177,7 @@ struct BatchArgs {
 enum { CNT_NEXT0 = 0, CNT_OVER0 = 1, CNT_NEXT1 = 2, CNT_OVER1 = 3, CNT_NEXT2 = 4, CNT_OVER2 = 5, CNT_NEXT3 = 6, CNT_OVER3 = 7, CNT_WORDS = 8,
        CNT_NBIG = 48,                  // queries routed straight to the mid tier = prefix of the size-ordered list
        CNT_BADN = 49,                  // a query with an all-zero normal was seen
+       CNT_NEXTW = 50, CNT_OVERW = 51, // wide tier
        CNT_HIST = 128, CNT_CURSOR = 384, CNT_TOTAL_WORDS = 640 };
 #define XS_LATE_EMPTY 0xffffffffu
 #define XS_LATE_CLAIMED 0xfffffffeu
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) area_warp_kernel(BatchArgs a) {
   A.order = reinterpret_cast<uint16_t*>(base + L::O_ORDER); A.max_n = MAXN;
   A.stack = reinterpret_cast<uint16_t*>(base + L::O_STACK); A.stack_cap = MAXN; A.spill = nullptr;
   A.mask = A.bits;
-  A.cells = nullptr; A.wlog = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
+  A.cells = nullptr; A.wside = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
   A.compact_pairs = 1;
   PackedHash H;
   H.slot = base + L::O_HASH; H.cap = HCAP; H.max_probe = 48;
@@ -303,7 +304,7 @@ __device__ __forceinline__ bool block_arena(Arena<uint32_t>& A, WideHash& H, con
   uint32_t* g_bits = p; p += s.bits_words;
   uint32_t* g_tested = p;
   A.max_n = s.max_n;
-  A.cells = nullptr; A.wlog = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
+  A.cells = nullptr; A.wside = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
   A.compact_pairs = 0;          // masks live in the HBM slab
   H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
   H.hx = vol.hx; H.hy = vol.hy;
@@ -374,16 +375,16 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_BLOCKS) area_block_kernel(B
 // ------------------------------------------------------------------------------------------------
 struct MidTier {
   static constexpr int THREADS = 256;
-  static constexpr int WLOG = 8;                   // 256 x 256 cells; uint16 cell index u | v<<8
+  static constexpr int WSIDE = 256;                // 256 x 256 cells; uint16 cell index u | v<<8
   static constexpr int RING = 1024;                // DFS stack ring entries (uint16) in shared memory (77.5 KB in all: one
                                                    //   mid-tier CTA fits beside two warp-tier CTAs on an SM)
   static constexpr int O_CTL = 64;
   static constexpr int O_RING = O_CTL + 48;
   static constexpr int O_LUT = O_RING + RING / 2;  // 256 x int16
-  static constexpr int FSTRIDE = (1 << WLOG) / 32 + 2;
+  static constexpr int FSTRIDE = WSIDE / 32 + 2;
   static constexpr int O_FBITS = O_LUT + 128;
-  static constexpr int O_CELLS = O_FBITS + ((1 << WLOG) + 2) * FSTRIDE;
-  static constexpr int WORDS = O_CELLS + ((1 << (2 * WLOG)) >> 2) + 128;   // the walk may LOAD up to a row past either end
+  static constexpr int O_CELLS = O_FBITS + (WSIDE + 2) * FSTRIDE;
+  static constexpr int WORDS = O_CELLS + WSIDE * WSIDE / 4 + 128;   // the walk may touch up to a row past either end
 };
 
 __host__ __device__ inline size_t mid_slab_bytes(const SlabCfg& s) {
@@ -411,12 +412,12 @@ __global__ void __maxnreg__(96) area_mid_kernel(BatchArgs a, SlabCfg s, int cnt_
   uint32_t* const g_key = g_tag + s.hcap_max;
   A.max_n = s.max_n;
   A.stack = reinterpret_cast<uint16_t*>(smem + MidTier::O_RING); A.stack_cap = MidTier::RING;
-  A.cells = reinterpret_cast<uint8_t*>(smem + MidTier::O_CELLS); A.wlog = MidTier::WLOG;
-  A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = (1 << MidTier::WLOG) / 32; A.stride = 0; A.halo = 1;
+  A.cells = reinterpret_cast<uint8_t*>(smem + MidTier::O_CELLS); A.wside = MidTier::WSIDE;
+  A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = MidTier::WSIDE / 32; A.stride = 0; A.halo = 1;
   A.compact_pairs = 0;          // masks live in the HBM slab
   A.fbits = smem + MidTier::O_FBITS; A.fstride = MidTier::FSTRIDE;
   A.nlut = reinterpret_cast<const int16_t*>(smem + MidTier::O_LUT);
-  nbr_lut_fill(g, reinterpret_cast<int16_t*>(smem + MidTier::O_LUT), MidTier::WLOG);
+  nbr_lut_fill(g, reinterpret_cast<int16_t*>(smem + MidTier::O_LUT), MidTier::WSIDE);
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -449,12 +450,85 @@ __global__ void __maxnreg__(96) area_mid_kernel(BatchArgs a, SlabCfg s, int cnt_
       if (threadIdx.x == 0) zero_query(a, q);
       continue;
     }
-    A.ox = A.oy = c.c - (1 << (MidTier::WLOG - 1)) - 16;   // the centre cell sits in the middle of tile (4,4)
+    A.ox = A.oy = c.c - MidTier::WSIDE / 2 - 16;   // the centre cell sits in the middle of tile (4,4)
     H.htag = g_tag; H.hkey = g_key;
     H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
     H.hx = a.vol.hx; H.hy = a.vol.hy;
     // the 64 KB cell window is dead once the walk is done: 8192-entry first-touch table in shared memory
     H.alt_tag = smem + MidTier::O_CELLS; H.alt_key = H.alt_tag + 8192; H.alt_cap = 8192;
+    int lg = 0;
+    while ((1u << lg) < s.hcap_max) lg++;
+    H.shift = 32 - lg;
+    const int st = run_area_emit(g, c, a.vol, A, H, ctl, q, a.out);
+    if (threadIdx.x == 0) finish_query(a, ctl, q, st, cnt_over, stats_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// WIDE tier: the mid tier's neighbour-byte walk with the largest window one SM holds — 416 x 416 cells (169 KB of
+// neighbour bytes + 25 KB of foreground bitmap), 32-bit cell indices, one 512-thread CTA per SM.  Takes the sections
+// that leave the mid tier's 256-cell window or exceed its 16 Ki samples (BASELINE config 0: a 500^3 sphere cut through
+// its centre, 1.3e5 samples) before they fall back to the big tier's bitmap walk (3-4x slower per step).
+// ------------------------------------------------------------------------------------------------
+struct WideTier {
+  static constexpr int THREADS = 512;
+  static constexpr int WSIDE = 416;                // 13 x 13 tiles; cell index u + 416 v
+  static constexpr int RING = 2048;                // DFS stack ring entries (uint32) in shared memory
+  static constexpr int O_CTL = 64;
+  static constexpr int O_RING = O_CTL + 48;
+  static constexpr int O_LUT = O_RING + RING;      // 256 x int16
+  static constexpr int FSTRIDE = WSIDE / 32 + 2;
+  static constexpr int O_FBITS = O_LUT + 128;
+  static constexpr int O_CELLS = O_FBITS + (WSIDE + 2) * FSTRIDE;
+  static constexpr int WORDS = O_CELLS + WSIDE * WSIDE / 4 + 128;
+  static constexpr int ALT_CAP = 16384;            // first-touch table aliased onto the (dead) neighbour bytes
+  static_assert(2 * ALT_CAP * 4 <= WSIDE * WSIDE, "alt table fits the cell window");
+};
+constexpr int WIDE_SMEM_BYTES = WideTier::WORDS * 4;
+
+__global__ void __launch_bounds__(WideTier::THREADS, 1) area_wide_kernel(BatchArgs a, SlabCfg s, int cnt_next, int cnt_over, const uint32_t* count_ptr, int stats_base) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  BlockGroup g(reinterpret_cast<int*>(smem));
+  Ctl& ctl = *reinterpret_cast<Ctl*>(smem + WideTier::O_CTL);
+  int* next = reinterpret_cast<int*>(smem + WideTier::O_CTL + 42);
+  const V3 w = mk(a.wx, a.wy, a.wz);
+  const uint32_t count = count_ptr ? *count_ptr : a.nq;
+  char* slab = s.base + (size_t)blockIdx.x * s.stride;
+  Arena<uint32_t> A;
+  uint32_t* p = reinterpret_cast<uint32_t*>(slab);
+  A.order = p; p += s.max_n;
+  A.mask = p; p += s.max_n;
+  A.spill = p; p += s.max_n;
+  uint32_t* const g_tag = p; p += s.hcap_max;
+  uint32_t* const g_key = p;
+  A.max_n = s.max_n;
+  A.stack = smem + WideTier::O_RING; A.stack_cap = WideTier::RING;
+  A.cells = reinterpret_cast<uint8_t*>(smem + WideTier::O_CELLS); A.wside = WideTier::WSIDE;
+  A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = WideTier::WSIDE / 32; A.stride = 0; A.halo = 1;
+  A.compact_pairs = 0;          // masks live in the HBM slab
+  A.fbits = smem + WideTier::O_FBITS; A.fstride = WideTier::FSTRIDE;
+  A.nlut = reinterpret_cast<const int16_t*>(smem + WideTier::O_LUT);
+  nbr_lut_fill(g, reinterpret_cast<int16_t*>(smem + WideTier::O_LUT), WideTier::WSIDE);
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) *next = (int)atomicAdd(&a.counters[cnt_next], 1u);
+    __syncthreads();
+    const uint32_t i = (uint32_t)*next;
+    if (i >= count) break;
+    const uint32_t q = a.list_in ? a.list_in[i] : i;
+    PlaneCtx c;
+    const V3 pp = mk(__ldg(a.pos + 3 * q), __ldg(a.pos + 3 * q + 1), __ldg(a.pos + 3 * q + 2));
+    const V3 n = mk(__ldg(a.nrm + 3 * q), __ldg(a.nrm + 3 * q + 1), __ldg(a.nrm + 3 * q + 2));
+    if (!plane_init(c, a.vol, pp, n, w)) {
+      if (threadIdx.x == 0) zero_query(a, q);
+      continue;
+    }
+    A.ox = A.oy = c.c - (WideTier::WSIDE / 64) * 32 - 16;   // the centre cell sits in the middle of the middle tile
+    WideHash H;
+    H.htag = g_tag; H.hkey = g_key;
+    H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
+    H.hx = a.vol.hx; H.hy = a.vol.hy;
+    H.alt_tag = smem + WideTier::O_CELLS; H.alt_key = H.alt_tag + WideTier::ALT_CAP; H.alt_cap = WideTier::ALT_CAP;
     int lg = 0;
     while ((1u << lg) < s.hcap_max) lg++;
     H.shift = 32 - lg;
@@ -676,7 +750,9 @@ struct xs3d_volume {
   cudaStream_t stream2 = nullptr;                      // the mid tier runs here, beside the warp tier
   cudaStream_t stream3 = nullptr;                      // third warp-tier CTA per SM (moves in when the mid-tier CTA retires)
   cudaEvent_t evf[4] = {nullptr, nullptr, nullptr, nullptr};    // fork, warp-tier grid A done, second stream done, warp-tier grid B done
-  SlabCfg cfg_mid{};
+  SlabCfg cfg_mid{}, cfg_wide{};
+  DevBuf slab_wide;
+  int wide_ctas = 0;
   int mid_ctas = 0;
   int mid_key = 0;
   uint64_t poly_cap = 0, item_cap = 0;
@@ -684,6 +760,7 @@ struct xs3d_volume {
   uint32_t* h_counters = nullptr;   // pinned: CNT_WORDS counters + 8 u64 stats
   uint64_t stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t tier_stats[2] = {0, 0};   // samples / items handled by the CTA tiers
+  uint32_t wide_over = 0;            // queries the wide tier passed on to the big tier
   uint64_t prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   int sm_count = 0, smem_optin = 0;
   bool kernels_configured = false;
@@ -711,6 +788,8 @@ static int configure_kernels(xs3d_volume* v) {
   CK(cudaFuncSetAttribute(T0_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, t0_bytes));
   CK(cudaFuncSetAttribute(area_block_kernel<BigTier>, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
   CK(cudaFuncSetAttribute(area_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MID_SMEM_BYTES));
+  if (WIDE_SMEM_BYTES > v->smem_optin) return fail(XS3D_ERR_UNSUPPORTED, "device shared memory too small for the wide tier");
+  CK(cudaFuncSetAttribute(area_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM_BYTES));
   CK(cudaFuncSetAttribute(section_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
   v->kernels_configured = true;
   return XS3D_OK;
@@ -761,7 +840,7 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
   for (int i = 0; i < 5; i++) if (v->evs[i]) cudaEventDestroy(v->evs[i]);
   DevBuf* bufs[] = { &v->cubes, &v->raw, &v->labels, &v->q_pos, &v->q_nrm, &v->q_area, &v->q_contact, &v->lists,
                      &v->counters, &v->slab1, &v->slab2, &v->sec_idx, &v->sec_val, &v->misc,
-                     &v->polys, &v->items, &v->vals, &v->geom, &v->qinfo, &v->slab_mid, &v->keys, &v->polys2, &v->items2, &v->vals2 };
+                     &v->polys, &v->items, &v->vals, &v->geom, &v->qinfo, &v->slab_mid, &v->keys, &v->polys2, &v->items2, &v->vals2, &v->slab_wide };
   for (DevBuf* b : bufs) b->release();
   if (v->h_counters) cudaFreeHost(v->h_counters);
   delete v;
@@ -897,7 +976,7 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
   RET(v->q_nrm.ensure(n * 12 + 64));
   RET(v->q_area.ensure(n * 4 + 64));
   RET(v->q_contact.ensure(n + 64));
-  RET(v->lists.ensure(n * 5 * 4 + 64));
+  RET(v->lists.ensure(n * 6 * 4 + 64));
   RET(v->keys.ensure(n + 64));
   RET(v->counters.ensure(CNT_TOTAL_WORDS * 4));
   if (!v->slab_mid.p) {
@@ -910,6 +989,15 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
     RET(v->slab_mid.ensure(m.stride * (size_t)v->mid_ctas));
     m.base = (char*)v->slab_mid.p;
     v->cfg_mid = m;
+  }
+  if (!v->slab_wide.p) {
+    SlabCfg m{};
+    m.max_n = 1 << 17; m.hcap_max = 1u << 19; m.bits_words = 0; m.tested_words = 0; m.hash_factor = 4; m.max_probe = 1024;
+    m.stride = slab_bytes(m);
+    v->wide_ctas = std::min(v->sm_count, 32);
+    RET(v->slab_wide.ensure(m.stride * (size_t)v->wide_ctas));
+    m.base = (char*)v->slab_wide.p;
+    v->cfg_wide = m;
   }
   RET(v->geom.ensure(n * sizeof(PlaneGeom) + 64));
   RET(v->qinfo.ensure(n * sizeof(QInfo) + 64));
@@ -966,6 +1054,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
   uint32_t* list2 = list1 + n;
   uint32_t* list3 = list2 + n;
   uint32_t* sorted = list3 + n;
+  uint32_t* listw = sorted + n;
   cudaStream_t s1 = v->stream, s2 = v->stream2;
   int launches = 0;
   for (int attempt = 0; attempt < 8; attempt++) {
@@ -1036,9 +1125,14 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, -1);
       CK(cudaGetLastError());
       CK(cudaEventRecord(v->evs[2], s2));
-      a.list_in = list1; a.list_out = list2;
-      area_block_kernel<BigTier><<<v->sm_count, BigTier::THREADS, block_smem_bytes(v), s2>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVER1, 10);
+      // what leaves the mid tier's window: wide tier (same walk, 416-cell window), then the big tier's bitmap walk
+      a.list_in = list1; a.list_out = listw;
+      area_wide_kernel<<<v->wide_ctas, WideTier::THREADS, WIDE_SMEM_BYTES, s2>>>(a, v->cfg_wide, CNT_NEXTW, CNT_OVERW, d_cnt + CNT_OVER1, 10);
       CK(cudaGetLastError());
+      a.list_in = listw; a.list_out = list2;
+      area_block_kernel<BigTier><<<v->sm_count, BigTier::THREADS, block_smem_bytes(v), s2>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVERW, 10);
+      CK(cudaGetLastError());
+      launches++;
       CK(cudaEventRecord(v->evs[3], s2));
       poly_eval_kernel<<<v->sm_count * 4, 256, 0, s2>>>(out2.polys, out2.geom, vals2, d_emit2, 0u, out2.poly_cap);
       CK(cudaGetLastError());
@@ -1054,11 +1148,14 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       a.out = out1; a.list_in = nullptr; a.list_out = list1;
       area_mid_kernel<<<(int)n, MidTier::THREADS, MID_SMEM_BYTES, s1>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, (int)n);
       CK(cudaGetLastError());
-      a.list_in = list1; a.list_out = list2;
-      area_block_kernel<BigTier><<<(int)n, BigTier::THREADS, block_smem_bytes(v), s1>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVER1, 10);
+      a.list_in = list1; a.list_out = listw;
+      area_wide_kernel<<<(int)n, WideTier::THREADS, WIDE_SMEM_BYTES, s1>>>(a, v->cfg_wide, CNT_NEXTW, CNT_OVERW, d_cnt + CNT_OVER1, 10);
+      CK(cudaGetLastError());
+      a.list_in = listw; a.list_out = list2;
+      area_block_kernel<BigTier><<<(int)n, BigTier::THREADS, block_smem_bytes(v), s1>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVERW, 10);
       CK(cudaGetLastError());
       CK(cudaEventRecord(v->evb[2], s1));
-      launches += 2;
+      launches += 3;
     }
     poly_eval_kernel<<<v->sm_count * 8, 256, 0, s1>>>(out1.polys, out1.geom, vals1, d_emit1, 0u, out1.poly_cap);
     CK(cudaGetLastError());
@@ -1075,6 +1172,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     v->timing[3] = 0.0f;
     if (v->h_counters[CNT_BADN]) return fail(XS3D_ERR_ARG, "normal vector must not be a null vector (all zeros).");
     const uint32_t over0 = v->h_counters[CNT_OVER0], over1 = v->h_counters[CNT_OVER1], over2 = v->h_counters[CNT_OVER2];
+    v->wide_over = v->h_counters[CNT_OVERW];
     const uint32_t* he1 = v->h_counters + 64;
     const uint32_t* he2 = v->h_counters + 68;
     uint32_t over3 = 0;

@@ -437,12 +437,12 @@ struct Arena {
   int stack_cap;                // power of two when `spill` is set, else >= max_n
   CellT* spill;                 // global backing store for the ring, or null when stack_cap >= max_n
   uint32_t* mask;               // per-sample 27-bit candidate / kept-item masks (warp tier: aliases `bits`)
-  // neighbour-mask variant of the window (mid tier): (1<<wlog)^2 cells, local cell index u | v<<wlog; one byte per
+  // neighbour-mask variant of the window (mid / wide tiers): wside^2 cells, local cell index u + v * wside; one byte per
   // cell = which of its 8 neighbours are foreground and unvisited (see flood_component_nbr).
   uint8_t* cells;               // null: use the bitmap
-  int wlog;
+  int wside;                    // cells per side, a multiple of 32 (<= 448)
   uint32_t* fbits;              // foreground bitmap of the window, one zero row / word of padding all round
-  int fstride;                  //   words per row = (1<<wlog)/32 + 2
+  int fstride;                  //   words per row = wside/32 + 2
   const int16_t* nlut;          // neighbour byte -> cell-index delta of its first set bit
   int compact_pairs;            // emit pass 1 evaluates compacted (sample, offset) pairs (needs `mask` in shared memory)
 };
@@ -461,7 +461,7 @@ struct Ctl {          // lives in shared memory (one per group)
   uint32_t counter;   // generic atomic counter (path B output length)
   uint32_t item_off, poly_off;
   int tiles;          // lattice tiles sampled (1024 cells each)
-  uint32_t grow[2];   // neighbour-mask flood: tiles wanted by the closure
+  uint32_t grow[7];   // neighbour-mask flood: tiles wanted by the closure (TileSet)
   long long tmark;    // phase profiling (thread 0): last timestamp and per-phase cycle counts
   uint32_t t[6];      //   0 flood (tiles + walk)  1 claims  2 emit  3 -  4 -  5 walk only
 };
@@ -842,154 +842,158 @@ XS_D int flood_component(const G& g, const PlaneCtx& c, const VolView& vol, cons
 //     lanes examine 32 stack frames at once, so unwinding — half of all iterations of a one-thread walk, most of
 //     it the final unwind of a finished component — costs almost nothing.
 // ------------------------------------------------------------------------------------------------
-struct NbrLut { int16_t delta[256]; };
-// delta of the first set bit of m for a window of (1<<wlog)^2 cells (entry 0 unused)
-XS_HD int nbr_delta(uint32_t m, int wlog) {
+// delta of the first set bit of m for a window of W cells per row (entry 0 unused)
+XS_HD int nbr_delta(uint32_t m, int W) {
   const int d = ffs32(m) - 1;
   const int du = (int)((0x2522u >> (2 * d)) & 3u) - 1;   // d:0..7 -> +1,-1,+1,-1,0,0,+1,-1
   const int dv = (int)((0x520au >> (2 * d)) & 3u) - 1;   // d:0..7 -> +1,+1,-1,-1,+1,-1,0,0
-  return du + dv * (1 << wlog);
+  return du + dv * W;
 }
 template <class G>
-XS_D void nbr_lut_fill(const G& g, int16_t* lut, int wlog) {
-  for (int m = g.tid(); m < 256; m += g.size()) lut[m] = (int16_t)(m ? nbr_delta((uint32_t)m, wlog) : 0);
+XS_D void nbr_lut_fill(const G& g, int16_t* lut, int W) {
+  for (int m = g.tid(); m < 256; m += g.size()) lut[m] = (int16_t)(m ? nbr_delta((uint32_t)m, W) : 0);
 }
 
 template <class CellT>
 XS_HD uint32_t* frow(const Arena<CellT>& A, int v) { return A.fbits + (size_t)(v + 1) * A.fstride + 1; }
 
-// Sample the tiles in `todo` (bit = ty * nt + tx) into the foreground bitmap: a warp per lattice row, a lane per cell.
-template <class G, class CellT>
-XS_D void nbr_sample_tiles(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, unsigned long long todo) {
-  const int ntl = A.wlog - 5;   // log2(tiles per side)
-  while (todo) {
-#ifdef __CUDA_ARCH__
-    const int t = __ffsll((long long)todo) - 1;
-#else
-    const int t = __builtin_ffsll((long long)todo) - 1;
-#endif
-    todo &= todo - 1ull;
-    const int tx = t & ((1 << ntl) - 1), ty = t >> ntl;
-#ifdef __CUDA_ARCH__
-    // four rows at a time: their four volume loads are issued before the first ballot needs its answer
-    for (int row0 = 4 * g.warp(); row0 < 32; row0 += 4 * g.nwarps()) {
-      uint32_t cube[4], bit[4];
-      bool ok[4];
+// A set of 32x32-cell tiles of the window (bit = ty * nt + tx), up to 14 x 14 tiles.
+struct TileSet {
+  uint32_t w[7];
+  XS_HD void clear() { for (int i = 0; i < 7; i++) w[i] = 0u; }
+  XS_HD void set(int t) { set_word(t >> 5, 1u << (t & 31)); }
+  XS_HD bool test(int t) const { return (w[t >> 5] >> (t & 31)) & 1u; }
+  XS_HD bool any() const { uint32_t o = 0u; for (int i = 0; i < 7; i++) o |= w[i]; return o != 0u; }
+  XS_HD int count() const { int c = 0; for (int i = 0; i < 7; i++) c += popc32(w[i]); return c; }
+  // f(t) for every tile of the set, ascending; word indices are compile-time constants so the set stays in registers
+  template <class F> XS_HD void for_each(F f) const {
 #pragma unroll
-      for (int j = 0; j < 4; j++) ok[j] = cell_probe(c, vol, A.ox + tx * 32 + g.lane(), A.oy + ty * 32 + row0 + j, &cube[j], &bit[j]);
-      uint32_t cb[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) cb[j] = cube_load(vol, cube[j]);     // (index 0 when the cell is outside: a valid address)
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t word = __ballot_sync(0xffffffffu, ok[j] && ((cb[j] >> bit[j]) & 1u));
-        if (g.lane() == 0) frow(A, ty * 32 + row0 + j)[tx] = word;
+    for (int i = 0; i < 7; i++) {
+      uint32_t m = w[i];
+      while (m) {
+        const int b = ffs32(m) - 1;
+        m &= m - 1u;
+        f(32 * i + b);
       }
     }
-#else
-    for (int row = 0; row < 32; row++) {
-      const int v = ty * 32 + row;
-      uint32_t word = 0;
-      for (int l = 0; l < 32; l++) word |= (uint32_t)cell_fg(c, vol, A.ox + tx * 32 + l, A.oy + v) << l;
-      frow(A, v)[tx] = word;
-    }
-#endif
   }
+  XS_HD void set_word(int i, uint32_t bits) {
+#pragma unroll
+    for (int j = 0; j < 7; j++)
+      if (j == i) w[j] |= bits;
+  }
+};
+
+// Sample tile (tx,ty) into the foreground bitmap: a warp per lattice row, a lane per cell.
+template <class G, class CellT>
+XS_D void nbr_sample_tile(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, int tx, int ty) {
+#ifdef __CUDA_ARCH__
+  // four rows at a time: their four volume loads are issued before the first ballot needs its answer
+  for (int row0 = 4 * g.warp(); row0 < 32; row0 += 4 * g.nwarps()) {
+    uint32_t cube[4], bit[4];
+    bool ok[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) ok[j] = cell_probe(c, vol, A.ox + tx * 32 + g.lane(), A.oy + ty * 32 + row0 + j, &cube[j], &bit[j]);
+    uint32_t cb[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) cb[j] = cube_load(vol, cube[j]);     // (index 0 when the cell is outside: a valid address)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t word = __ballot_sync(0xffffffffu, ok[j] && ((cb[j] >> bit[j]) & 1u));
+      if (g.lane() == 0) frow(A, ty * 32 + row0 + j)[tx] = word;
+    }
+  }
+#else
+  for (int row = 0; row < 32; row++) {
+    const int v = ty * 32 + row;
+    uint32_t word = 0;
+    for (int l = 0; l < 32; l++) word |= (uint32_t)cell_fg(c, vol, A.ox + tx * 32 + l, A.oy + v) << l;
+    frow(A, v)[tx] = word;
+  }
+#endif
 }
 
-// Which unsampled neighbours of the freshly sampled tiles `fresh` hold cells adjacent to a foreground cell?
+// Which neighbours of the freshly sampled tile (tx,ty) hold cells adjacent to one of its foreground cells?
+// (evaluated by one warp; every lane returns the same set)
 template <class G, class CellT>
-XS_D unsigned long long nbr_grow(const G& g, const Arena<CellT>& A, unsigned long long fresh) {
-  const int ntl = A.wlog - 5, nt = 1 << ntl;
-  unsigned long long want = 0ull;
-  int i = 0;
-  while (fresh) {
+XS_D void nbr_grow_tile(const G& g, const Arena<CellT>& A, int tx, int ty, TileSet& want) {
+  const int nt = A.wside >> 5, t = ty * nt + tx;
+  uint32_t left, right, top, bottom;
 #ifdef __CUDA_ARCH__
-    const int t = __ffsll((long long)fresh) - 1;
+  {
+    const uint32_t w = frow(A, ty * 32 + g.lane())[tx];
+    left = __ballot_sync(0xffffffffu, w & 1u);
+    right = __ballot_sync(0xffffffffu, w >> 31);
+    top = __shfl_sync(0xffffffffu, w, 0);
+    bottom = __shfl_sync(0xffffffffu, w, 31);
+  }
 #else
-    const int t = __builtin_ffsll((long long)fresh) - 1;
+  left = right = 0u;
+  for (int l = 0; l < 32; l++) {
+    const uint32_t w = frow(A, ty * 32 + l)[tx];
+    left |= (w & 1u) << l; right |= (w >> 31) << l;
+  }
+  top = frow(A, ty * 32)[tx]; bottom = frow(A, ty * 32 + 31)[tx];
 #endif
-    fresh &= fresh - 1ull;
-    if ((i++ % g.nwarps()) != g.warp()) continue;
-    const int tx = t & (nt - 1), ty = t >> ntl;
-    uint32_t left, right, top, bottom;
+  const bool okl = tx > 0, okr = tx < nt - 1, okt = ty > 0, okb = ty < nt - 1;
+  if (left && okl) want.set(t - 1);
+  if (right && okr) want.set(t + 1);
+  if (top && okt) want.set(t - nt);
+  if (bottom && okb) want.set(t + nt);
+  if ((top & 1u) && okl && okt) want.set(t - nt - 1);
+  if ((top >> 31) && okr && okt) want.set(t - nt + 1);
+  if ((bottom & 1u) && okl && okb) want.set(t + nt - 1);
+  if ((bottom >> 31) && okr && okb) want.set(t + nt + 1);
+}
+
+// Neighbour bytes of every foreground cell of tile (tx,ty).  A cell on the window's outer ring gets 0: the walk
+// stops when it steps on one (the section leaves the window).
+template <class G, class CellT>
+XS_D void nbr_masks_tile(const G& g, const Arena<CellT>& A, int tx, int ty) {
+  const int W = A.wside;
+  for (int row = g.warp(); row < 32; row += g.nwarps()) {
+    const int v = ty * 32 + row;
+    const uint32_t* rm = frow(A, v - 1) + tx;
+    const uint32_t* r0 = frow(A, v) + tx;
+    const uint32_t* rq = frow(A, v + 1) + tx;
+    const uint32_t cur = r0[0];
+    if (cur == 0u) continue;                     // warp-uniform
+    // bit (l + 1) of x? = cell (32 tx + l) of the row; bits 0 and 33 come from the neighbouring words
+    const unsigned long long xm = ((unsigned long long)rm[0] << 1) | (rm[-1] >> 31) | ((unsigned long long)(rm[1] & 1u) << 33);
+    const unsigned long long x0 = ((unsigned long long)cur << 1) | (r0[-1] >> 31) | ((unsigned long long)(r0[1] & 1u) << 33);
+    const unsigned long long xq = ((unsigned long long)rq[0] << 1) | (rq[-1] >> 31) | ((unsigned long long)(rq[1] & 1u) << 33);
 #ifdef __CUDA_ARCH__
+    const int l = g.lane();
     {
-      const uint32_t w = frow(A, ty * 32 + g.lane())[tx];
-      left = __ballot_sync(0xffffffffu, w & 1u);
-      right = __ballot_sync(0xffffffffu, w >> 31);
-      top = __shfl_sync(0xffffffffu, w, 0);
-      bottom = __shfl_sync(0xffffffffu, w, 31);
-    }
 #else
-    left = right = 0u;
     for (int l = 0; l < 32; l++) {
-      const uint32_t w = frow(A, ty * 32 + l)[tx];
-      left |= (w & 1u) << l; right |= (w >> 31) << l;
-    }
-    top = frow(A, ty * 32)[tx]; bottom = frow(A, ty * 32 + 31)[tx];
 #endif
-    const bool okl = tx > 0, okr = tx < nt - 1, okt = ty > 0, okb = ty < nt - 1;
-    if (left && okl) want |= 1ull << (t - 1);
-    if (right && okr) want |= 1ull << (t + 1);
-    if (top && okt) want |= 1ull << (t - nt);
-    if (bottom && okb) want |= 1ull << (t + nt);
-    if ((top & 1u) && okl && okt) want |= 1ull << (t - nt - 1);
-    if ((top >> 31) && okr && okt) want |= 1ull << (t - nt + 1);
-    if ((bottom & 1u) && okl && okb) want |= 1ull << (t + nt - 1);
-    if ((bottom >> 31) && okr && okb) want |= 1ull << (t + nt + 1);
-  }
-  return want;
-}
-
-// Neighbour bytes of every foreground cell of the sampled tiles `done` (cells on the window's outer ring excepted:
-// the walk stops when it steps on one).
-template <class G, class CellT>
-XS_D void nbr_masks(const G& g, const Arena<CellT>& A, unsigned long long done) {
-  const int ntl = A.wlog - 5, W = 1 << A.wlog;
-  while (done) {
-#ifdef __CUDA_ARCH__
-    const int t = __ffsll((long long)done) - 1;
-#else
-    const int t = __builtin_ffsll((long long)done) - 1;
-#endif
-    done &= done - 1ull;
-    const int tx = t & ((1 << ntl) - 1), ty = t >> ntl;
-    for (int row = g.warp(); row < 32; row += g.nwarps()) {
-      const int v = ty * 32 + row;
-      const uint32_t* rm = frow(A, v - 1) + tx;
-      const uint32_t* r0 = frow(A, v) + tx;
-      const uint32_t* rq = frow(A, v + 1) + tx;
-      const uint32_t cur = r0[0];
-      if (cur == 0u) continue;                     // warp-uniform
-      // bit (l + 1) of x?? = cell (32 tx + l) of the row; bits 0 and 33 come from the neighbouring words
-      const unsigned long long xm = ((unsigned long long)rm[0] << 1) | (rm[-1] >> 31) | ((unsigned long long)(rm[1] & 1u) << 33);
-      const unsigned long long x0 = ((unsigned long long)cur << 1) | (r0[-1] >> 31) | ((unsigned long long)(r0[1] & 1u) << 33);
-      const unsigned long long xq = ((unsigned long long)rq[0] << 1) | (rq[-1] >> 31) | ((unsigned long long)(rq[1] & 1u) << 33);
-#ifdef __CUDA_ARCH__
-      const int l = g.lane();
-      {
-#else
-      for (int l = 0; l < 32; l++) {
-#endif
-        const int u = tx * 32 + l;
-        const uint32_t am = (uint32_t)(xm >> l) & 7u, a0 = (uint32_t)(x0 >> l) & 7u, aq = (uint32_t)(xq >> l) & 7u;   // bits: u-1, u, u+1
-        if (a0 & 2u) {
-          const bool inner = u > 0 && v > 0 && u < W - 1 && v < W - 1;
-          const uint32_t m = ((aq >> 2) & 1u) | ((aq & 1u) << 1) | (((am >> 2) & 1u) << 2) | ((am & 1u) << 3) |
-                             (((aq >> 1) & 1u) << 4) | (((am >> 1) & 1u) << 5) | (((a0 >> 2) & 1u) << 6) | ((a0 & 1u) << 7);
-          A.cells[(v << A.wlog) + u] = (uint8_t)(inner ? m : 0u);   // a ring cell is a dead end: the walk stops there (overflow)
-        }
+      const int u = tx * 32 + l;
+      const uint32_t am = (uint32_t)(xm >> l) & 7u, a0 = (uint32_t)(x0 >> l) & 7u, aq = (uint32_t)(xq >> l) & 7u;   // bits: u-1, u, u+1
+      if (a0 & 2u) {
+        const bool inner = u > 0 && v > 0 && u < W - 1 && v < W - 1;
+        const uint32_t m = ((aq >> 2) & 1u) | ((aq & 1u) << 1) | (((am >> 2) & 1u) << 2) | ((am & 1u) << 3) |
+                           (((aq >> 1) & 1u) << 4) | (((am >> 1) & 1u) << 5) | (((a0 >> 2) & 1u) << 6) | ((a0 & 1u) << 7);
+        A.cells[v * W + u] = (uint8_t)(inner ? m : 0u);
       }
     }
   }
+}
+
+// order[] entry of window cell ci = u + v * W: the index itself for 16-bit cells (W = 256: u | v << 8), packed
+// (u | v << 16) for 32-bit cells — what CellPack / sample_at decode
+template <class CellT>
+XS_HD CellT nbr_order_entry(int ci, int W) {
+  if (sizeof(CellT) == 2) return (CellT)ci;
+  const int v = ci / W;
+  return (CellT)((uint32_t)(ci - v * W) | ((uint32_t)v << 16));
 }
 
 // Mark cell ci visited: clear its bit in the neighbour bytes of its eight neighbours (the bit a neighbour holds for
 // us is the opposite direction, k^3 for the diagonals and k^1 for the others).  Plain form, one neighbour at a time.
-XS_HD void nbr_visit_one(uint8_t* cells, int ci, int k, int wlog) {
+XS_HD void nbr_visit_one(uint8_t* cells, int ci, int k, int W) {
   const int du = (int)((0x2522u >> (2 * k)) & 3u) - 1, dv = (int)((0x520au >> (2 * k)) & 3u) - 1;
-  const int nb = ci + du + dv * (1 << wlog);
+  const int nb = ci + du + dv * W;
   const int opp = k < 4 ? (k ^ 3) : (k ^ 1);
   cells[nb] &= (uint8_t)~(1u << opp);
 }
@@ -1002,7 +1006,7 @@ XS_HD uint32_t nbr_row_clear(int r) { return r == 0 ? 0x021001u : (r == 1 ? 0x80
 template <class CellT>
 XS_HD int dfs_run_nbr(const Arena<CellT>& A, int& n_io, int& depth_io, int& lo_io, int& ci_io) {
   int n = n_io, depth = depth_io, lo = lo_io, ci = ci_io;
-  const int W = 1 << A.wlog;
+  const int W = A.wside;
   const int max_n = A.max_n;
   uint8_t* const cells = A.cells;
   const int16_t* const lut = A.nlut;
@@ -1040,10 +1044,10 @@ XS_HD int dfs_run_nbr(const Arena<CellT>& A, int& n_io, int& depth_io, int& lo_i
       continue;
     }
     ci += (int)lut[m];
-    const int u = ci & (W - 1), v = ci >> A.wlog;
+    const int v = ci / W, u = ci - v * W;
     if ((u == 0) | (v == 0) | (u == W - 1) | (v == W - 1) | (n >= max_n)) { status = ST_OVERFLOW; break; }
-    for (int k = 0; k < 8; k++) nbr_visit_one(cells, ci, k, A.wlog);
-    order[n++] = (CellT)ci;
+    for (int k = 0; k < 8; k++) nbr_visit_one(cells, ci, k, W);
+    order[n++] = nbr_order_entry<CellT>(ci, W);
     if ((m & (m - 1u)) == 0u) depth--;     // tail call: the cell we leave has nothing left, reuse its frame
     if (depth - lo == cap) {
       const int nlo = lo + A.stack_cap / 2;
@@ -1072,25 +1076,34 @@ __device__ __forceinline__ int lds_s16(uint32_t a) { int v; asm volatile("ld.sha
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+// stack-ring entries are CellT wide
+template <class CellT> __device__ __forceinline__ uint32_t lds_cell(uint32_t base, int i) {
+  return sizeof(CellT) == 2 ? lds_u16(base + 2u * (uint32_t)i) : lds_u32(base + 4u * (uint32_t)i);
+}
+template <class CellT> __device__ __forceinline__ void sts_cell(uint32_t base, int i, uint32_t v) {
+  if (sizeof(CellT) == 2) sts_u16(base + 2u * (uint32_t)i, v); else sts_u32(base + 4u * (uint32_t)i, v);
+}
 
 // The walk, warp form: called by every lane of ONE warp, all lanes in lock step (they all hold the same state).
-// cells / lut / stack ring must be in SHARED memory; order and spill in global memory; cells are uint16 indices.
+// cells / lut / stack ring must be in SHARED memory; order and spill in global memory.  The stack holds cell indices
+// u + v * W; `order` gets what sample_at decodes (nbr_order_entry).
 // Per forward step the dependent chain is: neighbour byte -> delta table -> add -> neighbour byte of the new cell,
 // i.e. two shared-memory loads and one add.  The byte of the cell we arrive at is loaded BEFORE that cell is marked
 // visited (marking only rewrites its neighbours' bytes): three rows of three consecutive bytes = at most two
 // aligned words per row, read-modify-written by lanes 2r+h (the other lanes duplicate them: same value, same word).
 // A dead end examines 32 stack frames at once.
-__device__ __forceinline__ int dfs_run_nbr_warp(const Arena<uint16_t>& A, int& n_io, int& depth_io, int& lo_io, int& ci_io, int lane, uint32_t* scratch32) {
+template <class CellT>
+__device__ __forceinline__ int dfs_run_nbr_warp(const Arena<CellT>& A, int& n_io, int& depth_io, int& lo_io, int& ci_io, int lane, uint32_t* scratch32) {
   int n = n_io, depth = depth_io, lo = lo_io, ci = ci_io;
-  const int W = 1 << A.wlog;
+  const int W = A.wside;
   const int max_n = A.max_n;
   // loop invariants are pinned in registers (opaque moves): ptxas otherwise re-derives them — special-register reads
   // and the lane arithmetic included — inside the loop, on the dependent chain
   const uint32_t s_cells = pin_u32((uint32_t)__cvta_generic_to_shared(A.cells), scratch32);
   const uint32_t s_lut = pin_u32((uint32_t)__cvta_generic_to_shared(A.nlut), scratch32);
   const uint32_t s_stack = pin_u32((uint32_t)__cvta_generic_to_shared(A.stack), scratch32);
-  uint16_t* const order = A.order;
-  uint16_t* const spill = A.spill;
+  CellT* const order = A.order;
+  CellT* const spill = A.spill;
   const bool ring = spill != nullptr;
   const int smask = ring ? (A.stack_cap - 1) : 0x7fffffff;
   const int cap = ring ? A.stack_cap : 0x7fffffff;
@@ -1120,7 +1133,7 @@ __device__ __forceinline__ int dfs_run_nbr_warp(const Arena<uint16_t>& A, int& n
         if (depth - lo == cap) {
           // ring full: spill the lower half
           const int nlo = lo + half;
-          for (int dd = lo + lane; dd < nlo; dd += 32) spill[dd] = (uint16_t)lds_u16(s_stack + 2u * (uint32_t)(dd & smask));
+          for (int dd = lo + lane; dd < nlo; dd += 32) spill[dd] = (CellT)lds_cell<CellT>(s_stack, dd & smask);
           __syncwarp();
           lo = nlo;
         }
@@ -1129,8 +1142,8 @@ __device__ __forceinline__ int dfs_run_nbr_warp(const Arena<uint16_t>& A, int& n
       }
       sts_u32(va, vold & ~__funnelshift_l(flo, fhi, vb << 3));
       if (lane0) {
-        order[n] = (uint16_t)ci;
-        sts_u16(s_stack + 2u * (uint32_t)(depth & smask), (uint32_t)ci);
+        order[n] = nbr_order_entry<CellT>(ci, W);
+        sts_cell<CellT>(s_stack, depth & smask, (uint32_t)ci);
       }
       n++;
       depth++;
@@ -1138,7 +1151,7 @@ __device__ __forceinline__ int dfs_run_nbr_warp(const Arena<uint16_t>& A, int& n
     }
     // dead end.  A cell on the window's outer ring is one by construction (its byte is 0): the section leaves the window.
     {
-      const uint32_t u = (uint32_t)ci & (uint32_t)(W - 1), v = (uint32_t)ci >> A.wlog;
+      const uint32_t v = (uint32_t)ci / (uint32_t)W, u = (uint32_t)ci - v * (uint32_t)W;
       if (((u - 1u) >= lim) | ((v - 1u) >= lim)) { status = ST_OVERFLOW; goto out; }
     }
     // dead end: drop the current frame, then find the topmost frame that still has an available neighbour
@@ -1150,14 +1163,14 @@ __device__ __forceinline__ int dfs_run_nbr_warp(const Arena<uint16_t>& A, int& n
         // (ring only) refill the lower half of the ring from the global spill area
         int nlo = lo - half;
         if (nlo < 0) nlo = 0;
-        for (int d = nlo + lane; d < lo; d += 32) sts_u16(s_stack + 2u * (uint32_t)(d & smask), (uint32_t)spill[d]);
+        for (int d = nlo + lane; d < lo; d += 32) sts_cell<CellT>(s_stack, d & smask, (uint32_t)spill[d]);
         __syncwarp();
         lo = nlo;
       }
       const int avail = depth - lo;
       const int cnt = avail < 32 ? avail : 32;
       uint32_t f = 0u, fm = 0u;
-      if (lane < cnt) { f = lds_u16(s_stack + 2u * (uint32_t)((depth - 1 - lane) & smask)); fm = lds_u8(s_cells + f); }
+      if (lane < cnt) { f = lds_cell<CellT>(s_stack, (depth - 1 - lane) & smask); fm = lds_u8(s_cells + f); }
       const uint32_t ball = __ballot_sync(0xffffffffu, fm != 0u);
       if (ball) {
         const int l = __ffs(ball) - 1;
@@ -1179,7 +1192,7 @@ out:
 
 template <class G, class CellT>
 XS_D int flood_component_nbr(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, Ctl& ctl, bool* empty) {
-  const int W = 1 << A.wlog, ntl = A.wlog - 5, nt = 1 << ntl;
+  const int W = A.wside, nt = W >> 5;
   {
     const int words = (W + 2) * A.fstride;
     for (int i = g.tid(); i < words; i += g.size()) A.fbits[i] = 0u;
@@ -1187,35 +1200,45 @@ XS_D int flood_component_nbr(const G& g, const PlaneCtx& c, const VolView& vol, 
   const int cu = c.c - A.ox, cv = c.c - A.oy;
   if (g.tid() == 0) {
     ctl.status = ST_DONE; ctl.req_tx = 0; ctl.req_ty = 0;
-    ctl.n = 0; ctl.depth = 0; ctl.lo = 0; ctl.u = cu + (cv << A.wlog); ctl.v = 0; ctl.m = 0; ctl.npoly = 0; ctl.overflow = 0; ctl.contact = 0u; ctl.counter = 0u; ctl.tiles = 0;
+    ctl.n = 0; ctl.depth = 0; ctl.lo = 0; ctl.u = cu + cv * W; ctl.v = 0; ctl.m = 0; ctl.npoly = 0; ctl.overflow = 0; ctl.contact = 0u; ctl.counter = 0u; ctl.tiles = 0;
     ctl.item_off = 0u; ctl.poly_off = 0u;
-    ctl.grow[0] = ctl.grow[1] = 0u;
+    for (int i = 0; i < 7; i++) ctl.grow[i] = 0u;
     for (int i = 0; i < 6; i++) ctl.t[i] = 0u;
     ctl.tmark = xs_clock();
   }
   g.sync();
   *empty = false;
-  // closure over tiles, starting from the 3x3 tiles around the centre cell's tile
-  unsigned long long done = 0ull, todo = 0ull;
+  // closure over tiles, starting from the 3x3 tiles around the centre cell's tile: a tile is sampled as soon as a
+  // sampled foreground cell touches it, so the walk never has to stop and ask for cells
+  TileSet done, todo;
+  done.clear(); todo.clear();
   {
     const int ctx = cu >> 5, cty = cv >> 5;
     for (int ty = cty - 1; ty <= cty + 1; ty++)
       for (int tx = ctx - 1; tx <= ctx + 1; tx++)
-        if (tx >= 0 && ty >= 0 && tx < nt && ty < nt) todo |= 1ull << (ty * nt + tx);
+        if (tx >= 0 && ty >= 0 && tx < nt && ty < nt) todo.set(ty * nt + tx);
   }
-  while (todo) {
-    nbr_sample_tiles(g, c, vol, A, todo);
-    done |= todo;
+  while (todo.any()) {
+    todo.for_each([&](int t) { nbr_sample_tile(g, c, vol, A, t % nt, t / nt); });
+#pragma unroll
+    for (int i = 0; i < 7; i++) done.w[i] |= todo.w[i];
     g.sync();
-    const unsigned long long want = nbr_grow(g, A, todo) & ~done;
-    if (want && g.lane() == 0) {
-      atomic_or_u32(&ctl.grow[0], (uint32_t)want);
-      atomic_or_u32(&ctl.grow[1], (uint32_t)(want >> 32));
+    TileSet want;
+    want.clear();
+    int k = 0;
+    todo.for_each([&](int t) {
+      if ((k++ % g.nwarps()) == g.warp()) nbr_grow_tile(g, A, t % nt, t / nt, want);
+    });
+    if (g.lane() == 0) {
+#pragma unroll
+      for (int i = 0; i < 7; i++)
+        if (want.w[i] & ~done.w[i]) atomic_or_u32(&ctl.grow[i], want.w[i] & ~done.w[i]);
     }
     g.sync();
-    todo = ((unsigned long long)ctl.grow[0] | ((unsigned long long)ctl.grow[1] << 32)) & ~done;   // next write: after the next sync
+#pragma unroll
+    for (int i = 0; i < 7; i++) todo.w[i] = ctl.grow[i] & ~done.w[i];   // (next write to ctl.grow: after the next sync)
   }
-  nbr_masks(g, A, done);
+  done.for_each([&](int t) { nbr_masks_tile(g, A, t % nt, t / nt); });
   g.sync();
   if (g.warp() == 0) {
     const long long w0 = xs_clock();
@@ -1226,17 +1249,14 @@ XS_D int flood_component_nbr(const G& g, const PlaneCtx& c, const VolView& vol, 
       if (g.lane() == 0) ctl.n = 0;
     } else {
       g.converge();
-      if (g.lane() == 0) { A.order[0] = (CellT)ci0; A.stack[0] = (CellT)ci0; }
-      if (g.lane() == 0)
-        for (int k = 0; k < 8; k++) nbr_visit_one(A.cells, ci0, k, A.wlog);
+      if (g.lane() == 0) {
+        A.order[0] = nbr_order_entry<CellT>(ci0, W); A.stack[0] = (CellT)ci0;
+        for (int k = 0; k < 8; k++) nbr_visit_one(A.cells, ci0, k, W);
+      }
       g.converge();
       int n = 1, depth = 1, lo = 0, ci = ci0;
 #ifdef __CUDA_ARCH__
-      if constexpr (sizeof(CellT) == 2) {
-        st = dfs_run_nbr_warp(A, n, depth, lo, ci, g.lane(), A.fbits);   // (the foreground bitmap is dead: 32 words of scratch)
-      } else {
-        st = ST_OVERFLOW;   // the neighbour-mask flood is only instantiated for 16-bit cells on the device
-      }
+      st = dfs_run_nbr_warp(A, n, depth, lo, ci, g.lane(), A.fbits);   // (the foreground bitmap is dead: 32 words of scratch)
 #else
       st = dfs_run_nbr(A, n, depth, lo, ci);
 #endif
@@ -1244,7 +1264,7 @@ XS_D int flood_component_nbr(const G& g, const PlaneCtx& c, const VolView& vol, 
     }
     if (g.lane() == 0) {
       ctl.status = st;
-      ctl.tiles = popcll64(done);
+      ctl.tiles = done.count();
       ctl.t[5] += (uint32_t)(xs_clock() - w0);
     }
   }

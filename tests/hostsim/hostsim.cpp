@@ -54,7 +54,7 @@ struct SmallArena {
     order.assign(max_n, 0); stack.assign(max_n, 0); slots.assign(hcap, 0);
     A.bits = bits.data(); A.tested = tested.data(); A.order = order.data(); A.stack = stack.data();
     A.max_n = max_n; A.stack_cap = max_n; A.spill = nullptr; A.mask = A.bits;   // masks alias the (dead) bitmap
-    A.cells = nullptr; A.wlog = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr; A.compact_pairs = 1;
+    A.cells = nullptr; A.wside = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr; A.compact_pairs = 1;
     H.slot = slots.data(); H.cap = hcap; H.shift = 32 - __builtin_ctz(hcap); H.max_probe = 64;
     H.cbx = centre.rx >> 1; H.cby = centre.ry >> 1; H.cbz = centre.rz >> 1;
   }
@@ -77,7 +77,7 @@ struct BigArena {
     const uint32_t hcap = pow2_at_least((uint64_t)max_n * (uint64_t)factor + 64);
     htag.assign(hcap, 0); hkey.assign(hcap, 0);
     A.bits = bits.data(); A.tested = tested.data(); A.order = order.data(); A.stack = stack.data(); A.mask = mask.data();
-    A.cells = nullptr; A.wlog = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr; A.compact_pairs = 1;
+    A.cells = nullptr; A.wside = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr; A.compact_pairs = 1;
     H.htag = htag.data(); H.hkey = hkey.data(); H.cap = hcap; H.cap_max = hcap; H.shift = 32 - __builtin_ctz(hcap);
     H.hx = v.hx; H.hy = v.hy; H.max_probe = 1 << 30; H.factor = factor;
     H.alt_tag = nullptr; H.alt_key = nullptr; H.alt_cap = 0;
@@ -98,9 +98,9 @@ struct ByteArena {
     const uint32_t hcap = pow2_at_least((uint64_t)max_n * 16 + 64);
     htag.assign(hcap, 0); hkey.assign(hcap, 0);
     fbits.assign((size_t)(256 + 2) * 10, 0xdeadbeefu); lut.assign(256, 0);
-    for (int m = 1; m < 256; m++) lut[m] = (int16_t)nbr_delta((uint32_t)m, 8);
+    for (int m = 1; m < 256; m++) lut[m] = (int16_t)nbr_delta((uint32_t)m, 256);
     A.fbits = fbits.data(); A.fstride = 10; A.nlut = lut.data(); A.compact_pairs = 0;
-    A.cells = cells.data(); A.wlog = 8; A.ox = A.oy = c.c - 128 - 16; A.halo = 1;
+    A.cells = cells.data(); A.wside = 256; A.ox = A.oy = c.c - 128 - 16; A.halo = 1;
     A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = 8; A.stride = 0;
     A.order = order.data(); A.max_n = max_n; A.stack = stack.data(); A.stack_cap = ring; A.spill = spill.data(); A.mask = mask.data();
     H.htag = htag.data(); H.hkey = hkey.data(); H.cap = hcap; H.cap_max = hcap; H.shift = 32 - __builtin_ctz(hcap);
@@ -110,11 +110,37 @@ struct ByteArena {
   }
 };
 
+// wide-tier-like arena: neighbour-byte window of WS x WS cells (WS a multiple of 32, not a power of two), uint32 cells
+struct WideArena {
+  static constexpr int WS = 160;
+  std::vector<uint8_t> cells;
+  std::vector<uint32_t> fbits, order, stack, spill, mask, htag, hkey;
+  std::vector<int16_t> lut;
+  Arena<uint32_t> A;
+  WideHash H;
+  void setup(const PlaneCtx& c, const VolView& v, int max_n, int ring) {
+    cells.assign((size_t)WS * WS + 1024, 0xee); order.assign(max_n, 0); stack.assign(ring, 0); spill.assign(max_n, 0); mask.assign(max_n, 0);
+    const uint32_t hcap = pow2_at_least((uint64_t)max_n * 16 + 64);
+    htag.assign(hcap, 0); hkey.assign(hcap, 0);
+    const int fs = WS / 32 + 2;
+    fbits.assign((size_t)(WS + 2) * fs, 0xdeadbeefu); lut.assign(256, 0);
+    for (int m = 1; m < 256; m++) lut[m] = (int16_t)nbr_delta((uint32_t)m, WS);
+    A.fbits = fbits.data(); A.fstride = fs; A.nlut = lut.data(); A.compact_pairs = 0;
+    A.cells = cells.data() + 512; A.wside = WS; A.ox = A.oy = c.c - (WS / 64) * 32 - 16; A.halo = 1;
+    A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = WS / 32; A.stride = 0;
+    A.order = order.data(); A.max_n = max_n; A.stack = stack.data(); A.stack_cap = ring; A.spill = spill.data(); A.mask = mask.data();
+    H.htag = htag.data(); H.hkey = hkey.data(); H.cap = hcap; H.cap_max = hcap; H.shift = 32 - __builtin_ctz(hcap);
+    H.hx = v.hx; H.hy = v.hy; H.max_probe = 1 << 30; H.factor = 16;
+    H.alt_tag = nullptr; H.alt_key = nullptr; H.alt_cap = 0;
+  }
+};
+
 extern "C" {
 
 // mode 0: big arena only.  mode 1: small (warp-tier-like) arena first, big arena on overflow.
 // mode 2: like 0 but with a tiny DFS stack ring (exercises spill/refill).
-// mode 3: byte-per-cell (mid-tier-like) arena with a 64-entry ring first, big arena on overflow.
+// mode 3: neighbour-byte (mid-tier-like) arena with a 64-entry ring first, big arena on overflow.
+// mode 4: neighbour-byte arena with a 160-cell window and 32-bit cells (wide-tier-like) first, big arena on overflow.
 // stats[0] = queries that overflowed the small arena, stats[1] = total samples, stats[2] = total items, stats[3] = polygons
 void hostsim_area_batch(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t sz, uint64_t nq, const float* pos,
                         const float* nrm, const float* w, float* area, uint8_t* contact, int mode, int64_t* stats) {
@@ -146,6 +172,12 @@ void hostsim_area_batch(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t s
       ByteArena ya;
       ya.setup(c, v, 4096, 64);
       st = run_area_emit(g, c, v, ya.A, ya.H, ctl, (uint32_t)q, O.out);
+      if (st != Q_OK) n_over++;
+    }
+    if (mode == 4) {
+      WideArena wa;
+      wa.setup(c, v, 8192, 128);
+      st = run_area_emit(g, c, v, wa.A, wa.H, ctl, (uint32_t)q, O.out);
       if (st != Q_OK) n_over++;
     }
     if (st != Q_OK) {

@@ -10,7 +10,7 @@ import golden_util as gu
 from conftest import bits
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 def test_area_random(hostsim, oracle, mode):
   rng = np.random.default_rng(1234 + mode)
   for it in range(250):
@@ -37,8 +37,10 @@ def test_area_neurite_tiers(hostsim, oracle):
   assert st[0] > 0, "expected some queries to overflow the small arena"
   a2, c2, _ = hostsim.area_batch(vol, qp[:60], qn[:60], [32, 32, 40], 2)
   assert np.array_equal(bits(a[:60]), bits(a2)) and np.array_equal(c[:60], c2)
-  a3, c3, st3 = hostsim.area_batch(vol, qp[:200], qn[:200], [32, 32, 40], 3)   # byte-per-cell (mid tier) flood
+  a3, c3, st3 = hostsim.area_batch(vol, qp[:200], qn[:200], [32, 32, 40], 3)   # neighbour-byte (mid tier) flood
   assert np.array_equal(bits(a[:200]), bits(a3)) and np.array_equal(c[:200], c3)
+  a4, c4, st4 = hostsim.area_batch(vol, qp[:200], qn[:200], [32, 32, 40], 4)   # ... with 32-bit cells and a 160-cell window (wide tier)
+  assert np.array_equal(bits(a[:200]), bits(a4)) and np.array_equal(c[:200], c4)
 
 
 def test_area_long_sections_mid_tier(hostsim, oracle):
@@ -67,6 +69,8 @@ def test_area_long_sections_mid_tier(hostsim, oracle):
     a, c = oracle.area_batch(vol, qp, qn, [32, 32, 40])
     a3, c3, st = hostsim.area_batch(vol, qp, qn, [32, 32, 40], 3)
     assert np.array_equal(bits(a), bits(a3)) and np.array_equal(c, c3), it
+    a4, c4, st4 = hostsim.area_batch(vol, qp, qn, [32, 32, 40], 4)       # wide-tier-like: 160-cell window, 32-bit cells
+    assert np.array_equal(bits(a), bits(a4)) and np.array_equal(c, c4), it
     grown += int(st[1] > 4 * 600)
   assert grown > 0, "expected sections larger than the initial 96x96-cell tile set"
 
