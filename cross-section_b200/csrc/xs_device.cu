@@ -725,7 +725,7 @@ struct DevBuf {
 // warp tier configuration (shared memory per warp = WarpLayout::WORDS * 4 bytes)
 constexpr int T0_WARPS = 10, T0_TILES = 3, T0_MAXN = 384, T0_HCAP = 1024;   // 3 CTAs per SM -> 30 warps per SM (2 beside a mid-tier CTA)
 constexpr int T0_CTAS_PER_SM = 3;
-constexpr int MID_BIG_KEY = 30;   // >= 30 of 256 probes foreground (~480 cells): the section will not fit a warp (T0_MAXN); tuned on the
+constexpr int MID_BIG_KEY = 26;   // >= 26 of 256 probes foreground (~420 cells): the section will not fit a warp (T0_MAXN); tuned on the
                                   //   bench sweep — a query misjudged as small is handed over by the warp tier, only later
 using T0Layout = WarpLayout<T0_TILES, T0_MAXN, T0_HCAP>;
 #define T0_KERNEL area_warp_kernel<T0_WARPS, T0_TILES, T0_MAXN, T0_HCAP>
