@@ -341,3 +341,43 @@ def test_null_normal_is_rejected_on_every_path(xs):
     a = V.cross_sectional_area_batch(torch.from_numpy(qp[:16]).cuda(), torch.from_numpy(qn[:16]).cuda(), [32, 32, 40])
     b = V.cross_sectional_area_batch(qp[:16], qn[:16], [32, 32, 40])
     assert np.array_equal(bits(a.cpu().numpy()), bits(b))
+
+
+def test_long_and_wide_sections_all_cta_tiers(xs, oracle):
+  """Sections of every size class through the device tiers: tubes cut (almost) along their axis give sections
+  hundreds of cells long — beyond the warp tier, the mid tier's 256-cell window (wide tier) and the wide tier's
+  416-cell window (big tier).  Batched (tier hand-overs while the tiers run side by side) and one by one."""
+  rng = np.random.default_rng(5)
+  N = 352
+  g = np.stack(np.meshgrid(*[np.arange(N, dtype=np.float32)] * 3, indexing="ij"), -1)
+  vol = np.zeros((N, N, N), bool)
+  qp, qn = [], []
+  for it in range(5):
+    c0 = rng.uniform(120, 230, size=3).astype(np.float32)
+    d = rng.normal(size=3).astype(np.float32); d /= np.linalg.norm(d)
+    r = rng.uniform(3, 8)
+    rel = g - c0
+    t = rel @ d
+    dist2 = (rel ** 2).sum(-1) - t ** 2
+    half = [40, 90, 150, 230, 400][it]                       # half-length of the tube in voxels
+    tube = (dist2 <= r * r) & (np.abs(t) <= half)
+    tube ^= (rng.random(tube.shape) < 0.02) & (dist2 <= (r + 2) ** 2) & (np.abs(t) <= half)
+    vol |= tube
+    vol[int(c0[0]), int(c0[1]), int(c0[2])] = True
+    e = np.cross(d, rng.normal(size=3)).astype(np.float32); e /= np.linalg.norm(e)
+    for k in range(3):
+      qp.append(np.floor(c0)); qn.append(e + rng.uniform(0.0, 0.1) * d)   # the plane (almost) contains the tube axis
+    qp.append(np.floor(c0)); qn.append(d)                                  # and one cut across the tube
+  del g
+  vol = np.asfortranarray(vol)
+  qp = np.array(qp, np.float32); qn = np.array(qn, np.float32)
+  w = [32, 32, 40]
+  oa, oc = oracle.area_batch(vol, qp, qn, w)
+  with xs.Volume(vol) as V:
+    a, c = V.cross_sectional_area_batch(qp, qn, w, return_contact=True)
+    st = V.stats()
+    singles = [V.cross_sectional_area(qp[i], qn[i], w, return_contact=True) for i in range(len(qp))]
+  assert np.array_equal(bits(a), bits(oa)) and np.array_equal(c, oc)
+  for i, (sa, sc) in enumerate(singles):
+    assert bits(np.float32(sa)) == bits(oa[i]) and sc == oc[i], i
+  assert st["escalated_mid"] > 0 and st["escalated_big"] > 0, st     # the mid tier handed sections on to the wide / big tiers
