@@ -407,7 +407,7 @@ __global__ void __maxnreg__(96) area_mid_kernel(BatchArgs a, SlabCfg s, int cnt_
   A.mask = reinterpret_cast<uint32_t*>(slab);
   A.order = reinterpret_cast<uint16_t*>(slab + (size_t)s.max_n * 4);
   A.spill = reinterpret_cast<uint16_t*>(slab + (size_t)s.max_n * 6);
-  WideHash H;
+  WideHashSeq H;
   uint32_t* const g_tag = reinterpret_cast<uint32_t*>(slab + (size_t)s.max_n * 8);
   uint32_t* const g_key = g_tag + s.hcap_max;
   A.max_n = s.max_n;

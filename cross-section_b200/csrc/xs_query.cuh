@@ -324,6 +324,7 @@ template <> struct CellPack<uint32_t> {
 // claims on a slot that already holds the same tag share the upper bits, atomicMin on the whole word is
 // atomicMin on the rank.
 struct PackedHash {
+  static constexpr bool kBatch = false;
   XS_HD void fit(int) {}
   uint32_t* slot;
   uint32_t cap;        // power of two
@@ -356,6 +357,8 @@ struct PackedHash {
     }
     return 0;
   }
+  XS_HD bool batched() const { return false; }     // shared-memory table: claims go offset by offset (claim_blocks)
+  XS_HD uint32_t claim9(uint32_t, uint32_t, uint32_t, bool*) const { return 0u; }
   XS_HD uint32_t owner(int bx, int by, int bz) const {
     const uint32_t t = tag(bx, by, bz);
     uint32_t h = (t * 2654435761u) >> shift;
@@ -368,7 +371,10 @@ struct PackedHash {
 };
 
 // First-touch table, wide form (CTA tier): separate tag (linear block id) and rank arrays in HBM.
-struct WideHash {
+// kBatch: compile the batched claim path (claim9) in — for the tiers whose table can be in HBM and large
+template <bool BATCH>
+struct WideHashT {
+  static constexpr bool kBatch = BATCH;
   uint32_t* htag;
   uint32_t* hkey;
   uint32_t cap;        // capacity in use (power of two)
@@ -415,6 +421,50 @@ struct WideHash {
     }
     return 0;
   }
+  XS_HD bool batched() const { return htag != alt_tag; }   // table in HBM (not the shared-memory alternative)
+  // Claims for one z-layer of the 3x3x3 neighbourhood: bit j = oy * 3 + ox of m9 set -> claim block (tag tbase + delta_j);
+  // returns the bits that are tentative owners.  With the table in HBM a claim is two dependent L2 round trips
+  // (tag, then rank), so the nine claims of a layer are issued as batches of independent operations: nine tag loads,
+  // the few compare-and-swaps that are needed, nine rank loads, the few atomicMins that can win.  Plain loads first
+  // are safe even when stale: a tag never changes once set, a rank only decreases.
+  XS_HD uint32_t claim9(uint32_t tbase, uint32_t m9, uint32_t rank, bool* full) const {
+    uint32_t t[9], h[9], e[9];
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      t[j] = tbase + tag_delta(j % 3 - 1, j / 3 - 1, 0);
+      h[j] = (t[j] * 2654435761u) >> shift;
+      e[j] = ((m9 >> j) & 1u) ? htag[h[j]] : t[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 9; j++)
+      if (((m9 >> j) & 1u) && e[j] == XS_HEMPTY) e[j] = atomic_cas_u32(&htag[h[j]], XS_HEMPTY, t[j]);
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      if (((m9 >> j) & 1u) && e[j] != XS_HEMPTY && e[j] != t[j]) {
+        // slot taken by another block: linear probing, one at a time (rare)
+        uint32_t hh = h[j];
+        bool ok = false;
+        for (int probes = 1; probes < max_probe; probes++) {
+          hh = (hh + 1u) & (cap - 1u);
+          const uint32_t old = atomic_cas_u32(&htag[hh], XS_HEMPTY, t[j]);
+          if (old == XS_HEMPTY || old == t[j]) { ok = true; break; }
+        }
+        if (!ok) { *full = true; m9 &= ~(1u << j); }
+        h[j] = hh;
+      }
+    }
+    uint32_t k[9];
+#pragma unroll
+    for (int j = 0; j < 9; j++) k[j] = ((m9 >> j) & 1u) ? hkey[h[j]] : 0u;
+    uint32_t won = 0u;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      if (((m9 >> j) & 1u) && k[j] > rank) {
+        if (atomic_min_u32(&hkey[h[j]], rank) > rank) won |= 1u << j;
+      }
+    }
+    return won;
+  }
   XS_HD uint32_t owner(int bx, int by, int bz) const {
     const uint32_t t = id(bx, by, bz);
     uint32_t h = (t * 2654435761u) >> shift;
@@ -422,6 +472,9 @@ struct WideHash {
     return hkey[h];
   }
 };
+using WideHash = WideHashT<true>;        // wide / big tiers, path B
+using WideHashSeq = WideHashT<false>;    // mid tier: its table is in shared memory except for the very largest sections
+
 
 template <class CellT>
 struct Arena {
@@ -1339,8 +1392,6 @@ XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const 
       // a block only if it held it at some point, so the ownership pass re-checks those few instead of all ~20
       my_cmask = cmask; my_tag = hash.tag(bx, by, bz);
     }
-    // claims, offset by offset in lock step: k is the same for every lane, so the offset decoding and the tag delta
-    // are computed once per warp instead of once per claim
     {
       uint32_t tentative = 0u;
 #ifdef __CUDA_ARCH__
@@ -1348,16 +1399,30 @@ XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const 
 #else
       const uint32_t any = my_cmask;
 #endif
+      bool use_batch = false;
+      if constexpr (H::kBatch) use_batch = hash.batched();
+      if (use_batch) {
+        // table in HBM: one z-layer (nine offsets) at a time, the nine claims overlapping their L2 round trips
 #pragma unroll 1
-      for (int k = 0; k < 27; k++) {
-        if (!((any >> k) & 1u)) continue;            // warp-uniform
-        int ox, oy, oz;
-        decode_k(k, ox, oy, oz);
-        const uint32_t dt = hash.tag_delta(ox, oy, oz);
-        if ((my_cmask >> k) & 1u) {
-          const int won = hash.claim_tag(my_tag + dt, (uint32_t)r);
-          if (won == 0) ovf = true;
-          if (won == 2) tentative |= 1u << k;
+        for (int oz = 0; oz < 3; oz++) {
+          if (!((any >> (9 * oz)) & 0x1ffu)) continue;            // warp-uniform
+          const uint32_t m9 = (my_cmask >> (9 * oz)) & 0x1ffu;
+          if (m9) tentative |= hash.claim9(my_tag + hash.tag_delta(0, 0, oz - 1), m9, (uint32_t)r, &ovf) << (9 * oz);
+        }
+      } else {
+        // table in shared memory: offset by offset in lock step — k is the same for every lane, so the offset decoding
+        // and the tag delta are computed once per warp instead of once per claim
+#pragma unroll 1
+        for (int k = 0; k < 27; k++) {
+          if (!((any >> k) & 1u)) continue;            // warp-uniform
+          int ox, oy, oz;
+          decode_k(k, ox, oy, oz);
+          const uint32_t dt = hash.tag_delta(ox, oy, oz);
+          if ((my_cmask >> k) & 1u) {
+            const int won = hash.claim_tag(my_tag + dt, (uint32_t)r);
+            if (won == 0) ovf = true;
+            if (won == 2) tentative |= 1u << k;
+          }
         }
       }
       if (r < n) A.mask[r] = tentative;
