@@ -545,16 +545,35 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) section_block_kernel(VolView v
   BlockGroup g(reinterpret_cast<int*>(smem));
   Ctl& ctl = *reinterpret_cast<Ctl*>(smem + BigTier::O_CTL);
   uint8_t* ct = reinterpret_cast<uint8_t*>(smem + BigTier::O_CTL + 42);
+  static_assert(BigTier::O_CTL == WideTier::O_CTL, "both layouts keep the control block in the same place");
   PlaneCtx c;
   if (threadIdx.x == 0) { result[0] = Q_OK; result[1] = 0; result[2] = 0; }
   if (!plane_init(c, vol, p, n, w)) return;
   Arena<uint32_t> A;
   WideHash H;
   int st = Q_OVERFLOW;
-  if (threadIdx.x == 0) ctl.counter = 0u;
-  __syncthreads();
-  if (block_arena<BigTier>(A, H, s, smem, smem_bits_words, c, vol)) st = run_section_emit(g, c, vol, A, H, ctl, out_rec, out_idx, out_cap, ct);
-  __syncthreads();
+  // first the neighbour-byte flood in the wide tier's 416-cell window (3-4x faster per walk step) ...
+  if (s.max_n >= WideTier::WSIDE * WideTier::WSIDE && WIDE_SMEM_BYTES <= (smem_bits_words + BigTier::FIXED_WORDS) * 4) {
+    block_arena<BigTier>(A, H, s, smem, smem_bits_words, c, vol);        // slab pointers and the HBM table
+    A.stack = smem + WideTier::O_RING; A.stack_cap = WideTier::RING;
+    A.cells = reinterpret_cast<uint8_t*>(smem + WideTier::O_CELLS); A.wside = WideTier::WSIDE;
+    A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = WideTier::WSIDE / 32; A.stride = 0; A.halo = 1;
+    A.fbits = smem + WideTier::O_FBITS; A.fstride = WideTier::FSTRIDE;
+    A.nlut = reinterpret_cast<const int16_t*>(smem + WideTier::O_LUT);
+    A.ox = A.oy = c.c - (WideTier::WSIDE / 64) * 32 - 16;
+    nbr_lut_fill(g, reinterpret_cast<int16_t*>(smem + WideTier::O_LUT), WideTier::WSIDE);
+    if (threadIdx.x == 0) ctl.counter = 0u;
+    __syncthreads();
+    st = run_section_emit(g, c, vol, A, H, ctl, out_rec, out_idx, out_cap, ct);
+    __syncthreads();
+  }
+  // ... then, for sections wider than that, the whole-plane bitmap
+  if (st == Q_OVERFLOW) {
+    if (threadIdx.x == 0) ctl.counter = 0u;
+    __syncthreads();
+    if (block_arena<BigTier>(A, H, s, smem, smem_bits_words, c, vol)) st = run_section_emit(g, c, vol, A, H, ctl, out_rec, out_idx, out_cap, ct);
+    __syncthreads();
+  }
   if (threadIdx.x == 0) { geom[0] = c.g; result[0] = (uint32_t)st; result[1] = ctl.counter; result[2] = (st == Q_OK) ? *ct : 0u; }
 }
 

@@ -1672,7 +1672,7 @@ XS_D int run_section_emit(const G& g, const PlaneCtx& c, const VolView& vol, con
                           PolyRec* out_rec, uint64_t* out_idx, uint32_t out_cap, uint8_t* contact) {
   typedef CellPack<CellT> P;
   bool empty;
-  if (flood_component(g, c, vol, A, ctl, &empty) != Q_OK) return Q_OVERFLOW;
+  if ((A.cells ? flood_component_nbr(g, c, vol, A, ctl, &empty) : flood_component(g, c, vol, A, ctl, &empty)) != Q_OK) return Q_OVERFLOW;
   if (empty) {
     if (g.tid() == 0) *contact = 0;
     return Q_OK;

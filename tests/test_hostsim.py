@@ -82,6 +82,8 @@ def test_section_random(hostsim, oracle):
     s, c = oracle.section(vol, p, n, w, method=0)
     s2, c2 = hostsim.section(vol, p, n, w)
     assert gu.same_bits(s, s2) and c == c2, it
+    s3, c3 = hostsim.section(vol, p, n, w, mode=1)          # neighbour-byte flood first
+    assert gu.same_bits(s, s3) and c == c3, it
 
 
 @pytest.mark.parametrize("mode", [0, 1])
