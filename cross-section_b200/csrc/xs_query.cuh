@@ -1693,35 +1693,66 @@ XS_D int run_section_emit(const G& g, const PlaneCtx& c, const VolView& vol, con
     lo[0] = (fsub(cur.x, 1.0f) >= 0.0f) ? -1 : 0; lo[1] = (fsub(cur.y, 1.0f) >= 0.0f) ? -1 : 0; lo[2] = (fsub(cur.z, 1.0f) >= 0.0f) ? -1 : 0;
     hi[0] = (fadd(cur.x, 1.0f) < fsx) ? 1 : 0; hi[1] = (fadd(cur.y, 1.0f) < fsy) ? 1 : 0; hi[2] = (fadd(cur.z, 1.0f) < fsz) ? 1 : 0;
     if (c.axis_aligned) { lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0; }
-    for (int dz = lo[2]; dz <= hi[2]; dz++)
-      for (int dy = lo[1]; dy <= hi[1]; dy++)
-        for (int dx = lo[0]; dx <= hi[0]; dx++) {
-          const V3 qv = vround(vadd(mk((float)dx, (float)dy, (float)dz), cur));
-          if (qv.x < 0.0f || qv.x >= fsx || qv.y < 0.0f || qv.y >= fsy || qv.z < 0.0f || qv.z >= fsz) continue;
-          const int x = (int)qv.x, y = (int)qv.y, z = (int)qv.z;
-          if (!vox_fg(vol, x, y, z)) continue;
-          // dedupe on the voxel: the wide table keyed by (x,y,z) as if they were block coordinates of a
-          // volume with hx=sx, hy=sy; rank 0 everywhere, "fresh" = we created the entry
-          const uint32_t id = (uint32_t)x + (uint32_t)vol.sx * ((uint32_t)y + (uint32_t)vol.sy * (uint32_t)z);
-          uint32_t h = (id * 2654435761u) >> hash.shift;
-          bool fresh = false;
+    // one z-layer (up to nine voxels) at a time, every stage as a batch of independent memory operations: occupancy
+    // bytes, then the table slots (plain loads: 13 of 14 voxels have been seen already and need no atomic), then the
+    // compare-and-swaps for the empty slots
+    for (int dz = lo[2]; dz <= hi[2]; dz++) {
+      uint32_t id[9], hh[9], cube[9], e[9];
+      uint32_t live = 0u;
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        const int dx = j % 3 - 1, dy = j / 3 - 1;
+        id[j] = 0u; hh[j] = 0u; cube[j] = 0u;
+        if (dx < lo[0] || dx > hi[0] || dy < lo[1] || dy > hi[1]) continue;
+        const V3 qv = vround(vadd(mk((float)dx, (float)dy, (float)dz), cur));
+        if (qv.x < 0.0f || qv.x >= fsx || qv.y < 0.0f || qv.y >= fsy || qv.z < 0.0f || qv.z >= fsz) continue;
+        const int x = (int)qv.x, y = (int)qv.y, z = (int)qv.z;
+        id[j] = (uint32_t)x + (uint32_t)vol.sx * ((uint32_t)y + (uint32_t)vol.sy * (uint32_t)z);
+        hh[j] = (uint32_t)((x & 1) | ((y & 1) << 1) | ((z & 1) << 2));        // bit within the occupancy byte (for now)
+        cube[j] = cube_index(vol, x >> 1, y >> 1, z >> 1);
+        live |= 1u << j;
+      }
+#pragma unroll
+      for (int j = 0; j < 9; j++) e[j] = ((live >> j) & 1u) ? cube_load(vol, cube[j]) : 0u;
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        if (!((e[j] >> hh[j]) & 1u)) live &= ~(1u << j);                       // background voxel
+        // dedupe on the voxel: the wide table keyed by the linear voxel index; "fresh" = we created the entry
+        hh[j] = (id[j] * 2654435761u) >> hash.shift;
+      }
+#pragma unroll
+      for (int j = 0; j < 9; j++) e[j] = ((live >> j) & 1u) ? hash.htag[hh[j]] : id[j];
+#pragma unroll
+      for (int j = 0; j < 9; j++)
+        if (((live >> j) & 1u) && e[j] == XS_HEMPTY) { e[j] = atomic_cas_u32(&hash.htag[hh[j]], XS_HEMPTY, id[j]); if (e[j] == XS_HEMPTY) e[j] = XS_HEMPTY - 1u; }
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        if (!((live >> j) & 1u)) continue;
+        bool fresh = e[j] == XS_HEMPTY - 1u;                                    // (marker: our compare-and-swap created the entry)
+        if (!fresh && e[j] != id[j]) {
+          // slot held by another voxel: linear probing, one at a time (rare)
+          uint32_t h = hh[j];
           for (int probes = 0;; probes++) {
-            const uint32_t t = atomic_cas_u32(&hash.htag[h], XS_HEMPTY, id);
-            if (t == XS_HEMPTY) { fresh = true; break; }
-            if (t == id) break;
             h = (h + 1u) & (hash.cap - 1u);
+            const uint32_t t = atomic_cas_u32(&hash.htag[h], XS_HEMPTY, id[j]);
+            if (t == XS_HEMPTY) { fresh = true; break; }
+            if (t == id[j]) break;
             if (probes == hash.max_probe) { ovf = true; break; }
           }
-          if (!fresh) continue;                  // first touch only (xs3d.hpp:511-512)
-          const uint32_t slot = atomic_add_u32(&ctl.counter, 1u);
-          if (slot < out_cap) {
-            PolyRec pr; pr.q = 0; pr.x = (uint16_t)x; pr.y = (uint16_t)y; pr.z = (uint16_t)z; pr.kind = 1;
-            out_rec[slot] = pr;
-            out_idx[slot] = (uint64_t)id;
-          } else {
-            ovf = true;
-          }
         }
+        if (!fresh) continue;                  // first touch only (xs3d.hpp:511-512)
+        const uint32_t slot = atomic_add_u32(&ctl.counter, 1u);
+        if (slot < out_cap) {
+          const uint32_t v0 = id[j];
+          const uint32_t x = v0 % (uint32_t)vol.sx, yz = v0 / (uint32_t)vol.sx;
+          PolyRec pr; pr.q = 0; pr.x = (uint16_t)x; pr.y = (uint16_t)(yz % (uint32_t)vol.sy); pr.z = (uint16_t)(yz / (uint32_t)vol.sy); pr.kind = 1;
+          out_rec[slot] = pr;
+          out_idx[slot] = (uint64_t)v0;
+        } else {
+          ovf = true;
+        }
+      }
+    }
   }
   ct = g.or_reduce(ct);
   if (ovf) ctl.overflow = 1;
