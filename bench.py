@@ -333,7 +333,7 @@ def run_own_arm(args):
   kname = {"warp_tier_ms": "area_warp_kernel", "mid_tier_ms": "area_mid_kernel", "big_tier_ms": "area_block_kernel<BigTier>", "polygon_ms": "poly_eval_kernel"}[dom]
   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
   # (profiles/r1g_ncu_full_summary.txt, profiles/r1g_per_kernel_hbm_l2.txt)
-  ncu_traffic = {"area_warp_kernel": 3032320, "area_mid_kernel": 1099520 + 1297152, "poly_eval_kernel": 14566144 + 1940736, "combine_kernel": 10696704 + 1583616}
+  ncu_traffic = {"area_warp_kernel": 2850000, "area_mid_kernel": 1700000 + 360000, "poly_eval_kernel": 14440000 + 2080000, "combine_kernel": 10600000 + 1680000}
   roofline = {"bound": "hbm", "kernel": kname,
               "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic.get(kname),
               "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms, "queries_in_kernel": nq_k,

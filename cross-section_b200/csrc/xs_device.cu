@@ -4,11 +4,16 @@
 //   ingest_f16_kernel / ingest_generic_kernel : uint8 volume -> 2x2x2 occupancy bytes ("cubes"),
 //        the only HBM-streaming kernel of the area path (reads V bytes, writes V/8).  Replaces the
 //        host-side np.asfortranarray + per-query compute_cube() loads (xs3d.hpp:26-48).
+//   classify_kernel / order_kernel : size estimate per query -> queries ordered largest first.
 //   area_warp_kernel  (T0): persistent, one WARP per query, whole working set in shared memory.
-//   area_block_kernel (T1/T2): persistent, one CTA per query; lattice bitmap + DFS stack ring in
-//        shared memory, everything else in a per-CTA slab in HBM.  Takes the queries T0 could not
-//        fit (and single-query calls).  T2 is the same kernel with one CTA and a worst-case slab.
+//   area_mid_kernel   (T1): persistent, one CTA per query, 256x256-cell window as one neighbour byte per cell
+//        in shared memory; runs on a second stream beside T0 and takes what T0 hands over.
+//   area_wide_kernel  (T2): the same walk with a 416x416-cell window, one CTA per SM.
+//   area_block_kernel (T3/T4): whole-plane bitmap (shared memory when it fits, HBM otherwise) + DFS stack ring;
+//        T4 is the same kernel with one CTA and a worst-case slab.
+//   poly_eval_kernel / combine_kernel : polygon areas of the emitted records; ordered float32 sums per query.
 //   section_block_kernel : path B (xs3d.cross_section) for one query, sparse output.
+// The batched launch sequence (two pipelines on three streams) is in area_batch_device.
 // No CPU implementation exists behind the ABI: without a device every call fails loudly.
 #include <cuda_runtime.h>
 #include <stdint.h>

@@ -11,16 +11,18 @@
 //   1. lattice tiles   : the plane lattice (basis b1,b2, unit spacing, centred on the vertex) is
 //                        sampled in 32x32-cell tiles ON DEMAND into a foreground bitmap (one ballot
 //                        per lattice row) — work scales with the section, not with the volume;
-//   2. component + rank: thread 0 walks the bitmap depth-first from the centre cell with the
+//   2. component + rank: one warp, in lock step, walks depth-first from the centre cell with the
 //                        reference's neighbour priority; the walk both delimits the 8-connected
-//                        component and yields its DFS preorder (`order[]`);
+//                        component and yields its DFS preorder (`order[]`).  Two forms: over the tile
+//                        bitmap (dfs_run: warp tier, big tier) and over one neighbour byte per cell with
+//                        the tiles sampled up front (flood_component_nbr: mid and wide tiers);
 //   3. claims          : every sample claims the <=27 neighbouring 2x2x2 blocks whose probe voxel
 //                        is set: atomicMin of its rank into a hash table keyed by block —
 //                        "first touch wins" without the sequential visit;
 //   4. emit            : owners that pass the adjacency and plane-distance tests become ITEMS, in
 //                        (rank,k) order; each item lists the plane∩cube POLYGONS it needs (the block
 //                        polygon and/or unit-voxel polygons) as 12-byte records in HBM.
-//   POLYGON KERNEL (one thread per polygon record, full occupancy; poly_eval)
+//   POLYGON KERNEL (records filtered and compacted per warp, then one thread per polygon; poly_eval)
 //   5. evaluate        : intersect the 12 cube edges with the plane, order the vertices, area.
 //   COMBINE KERNEL (one CTA per query; combine_query)
 //   6. ordered sum     : block value from its polygons, float32 sum per sample in k order, then
