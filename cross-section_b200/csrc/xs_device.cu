@@ -178,11 +178,13 @@ struct BatchArgs {
   uint32_t* list_in;         // queries to process (null: 0..nq-1)
   uint32_t* list_out;        // queries this tier could not fit
   uint32_t* late;            // mid tier: queries the warp tier hands over while both run (tail = counters[CNT_OVER0])
+  uint32_t* done_list;       // second pipeline: queries it has finished (count = counters[CNT_DONE2]), for its combine kernel
 };
 enum { CNT_NEXT0 = 0, CNT_OVER0 = 1, CNT_NEXT1 = 2, CNT_OVER1 = 3, CNT_NEXT2 = 4, CNT_OVER2 = 5, CNT_NEXT3 = 6, CNT_OVER3 = 7, CNT_WORDS = 8,
        CNT_NBIG = 48,                  // queries routed straight to the mid tier = prefix of the size-ordered list
        CNT_BADN = 49,                  // a query with an all-zero normal was seen
        CNT_NEXTW = 50, CNT_OVERW = 51, // wide tier
+       CNT_DONE2 = 52,                 // queries finished by the second pipeline
        CNT_HIST = 128, CNT_CURSOR = 384, CNT_TOTAL_WORDS = 640 };
 #define XS_LATE_EMPTY 0xffffffffu
 #define XS_LATE_CLAIMED 0xfffffffeu
@@ -190,6 +192,7 @@ enum { CNT_NEXT0 = 0, CNT_OVER0 = 1, CNT_NEXT1 = 2, CNT_OVER1 = 3, CNT_NEXT2 = 4
 __device__ __forceinline__ void finish_query(const BatchArgs& a, const Ctl& ctl, uint32_t q, int st, int cnt_over, int stats_base) {
   // thread 0 of the group
   if (st == Q_OK) {
+    if (a.done_list) a.done_list[atomicAdd(&a.counters[CNT_DONE2], 1u)] = q;
     atomicAdd(&a.stats[0], (unsigned long long)ctl.n);
     atomicAdd(&a.stats[1], (unsigned long long)ctl.m);
     atomicAdd(&a.stats[2], (unsigned long long)ctl.tiles);
@@ -208,6 +211,7 @@ __device__ __forceinline__ void finish_query(const BatchArgs& a, const Ctl& ctl,
 __device__ __forceinline__ void zero_query(const BatchArgs& a, uint32_t q) {
   QInfo qi; qi.item_off = 0; qi.n_items = 0; qi.contact = 0; qi.status = a.out.ready;
   a.out.qinfo[q] = qi;
+  if (a.done_list) a.done_list[atomicAdd(&a.counters[CNT_DONE2], 1u)] = q;
 }
 
 template <int WARPS, int TILES, int MAXN, int HCAP>
@@ -1000,7 +1004,7 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
   RET(v->q_nrm.ensure(n * 12 + 64));
   RET(v->q_area.ensure(n * 4 + 64));
   RET(v->q_contact.ensure(n + 64));
-  RET(v->lists.ensure(n * 6 * 4 + 64));
+  RET(v->lists.ensure(n * 7 * 4 + 64));
   RET(v->keys.ensure(n + 64));
   RET(v->counters.ensure(CNT_TOTAL_WORDS * 4));
   if (!v->slab_mid.p) {
@@ -1079,6 +1083,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
   uint32_t* list3 = list2 + n;
   uint32_t* sorted = list3 + n;
   uint32_t* listw = sorted + n;
+  uint32_t* done2 = listw + n;
   cudaStream_t s1 = v->stream, s2 = v->stream2;
   int launches = 0;
   for (int attempt = 0; attempt < 8; attempt++) {
@@ -1088,6 +1093,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     a.pos = d_pos; a.nrm = d_nrm; a.wx = w[0]; a.wy = w[1]; a.wz = w[2];
     a.nq = (uint32_t)n; a.counters = d_cnt; a.stats = d_stats;
     a.late = list0;
+    a.done_list = nullptr;
     EmitOut out1, out2;
     out1.polys = (PolyRec*)v->polys.p; out1.items = (ItemRec*)v->items.p; out1.geom = (PlaneGeom*)v->geom.p; out1.qinfo = (QInfo*)v->qinfo.p;
     out1.counters = d_emit1; out1.ready = QS_READY;
@@ -1117,7 +1123,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       // ---- second stream: mid tier beside the warp tier (it never waits for it)
       CK(cudaEventRecord(v->evf[0], s1));
       CK(cudaStreamWaitEvent(s2, v->evf[0], 0));
-      a.out = out2; a.list_in = sorted; a.list_out = list1;
+      a.out = out2; a.done_list = done2; a.list_in = sorted; a.list_out = list1;
       CK(cudaEventRecord(v->evs[0], s2));
       area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, -1);
       CK(cudaGetLastError());
@@ -1127,7 +1133,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       const bool single_grid = getenv("XS3D_SINGLE_GRID") != nullptr;
       // ---- third stream: warp-tier grid B
       CK(cudaStreamWaitEvent(v->stream3, v->evf[0], 0));
-      a.out = out1; a.list_in = sorted; a.list_out = list0;
+      a.out = out1; a.done_list = nullptr; a.list_in = sorted; a.list_out = list0;
       const int gridB = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * (T0_CTAS_PER_SM - 2));
       if (!single_grid) {
         T0_KERNEL<<<gridB, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, v->stream3>>>(a);
@@ -1145,7 +1151,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       // ---- second stream: late hand-overs (after the warp tier), big tier, its own polygon + combine kernels
       CK(cudaStreamWaitEvent(s2, v->evf[1], 0));
       CK(cudaStreamWaitEvent(s2, v->evf[3], 0));
-      a.out = out2; a.list_in = sorted; a.list_out = list1;
+      a.out = out2; a.done_list = done2; a.list_in = sorted; a.list_out = list1;
       area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, -1);
       CK(cudaGetLastError());
       CK(cudaEventRecord(v->evs[2], s2));
@@ -1160,7 +1166,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(cudaEventRecord(v->evs[3], s2));
       poly_eval_kernel<<<v->sm_count * 4, 256, 0, s2>>>(out2.polys, out2.geom, vals2, d_emit2, 0u, out2.poly_cap);
       CK(cudaGetLastError());
-      combine_kernel<<<cgrid_combine, 128, 0, s2>>>(out2.items, vals2, out2.qinfo, nullptr, nullptr, (uint32_t)n, d_area, d_contact, QS_READY2);
+      combine_kernel<<<(unsigned)std::min<uint64_t>(n, 1024), 128, 0, s2>>>(out2.items, vals2, out2.qinfo, done2, d_cnt + CNT_DONE2, (uint32_t)n, d_area, d_contact, QS_READY2);
       CK(cudaGetLastError());
       CK(cudaEventRecord(v->evs[4], s2));
       CK(cudaEventRecord(v->evf[2], s2));
@@ -1169,7 +1175,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(cudaEventRecord(v->evb[1], s1));
       // tiny batches (single calls): mid tier first — a section of a few thousand cells takes a fraction of the big
       // tier's time there — then the big tier for what does not fit its window
-      a.out = out1; a.list_in = nullptr; a.list_out = list1;
+      a.out = out1; a.done_list = nullptr; a.list_in = nullptr; a.list_out = list1;
       area_mid_kernel<<<(int)n, MidTier::THREADS, MID_SMEM_BYTES, s1>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, (int)n);
       CK(cudaGetLastError());
       a.list_in = list1; a.list_out = listw;
@@ -1208,7 +1214,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       float* valsb = single ? vals1 : vals2;
       uint32_t* d_emitb = single ? d_emit1 : d_emit2;
       const uint32_t used = single ? he1[0] : he2[0];
-      a.out = ob; a.list_in = list2; a.list_out = list3;
+      a.out = ob; a.done_list = nullptr; a.list_in = list2; a.list_out = list3;
       CK(cudaEventRecord(v->ev[0], s1));
       area_block_kernel<BigTier><<<1, BigTier::THREADS, block_smem_bytes(v), s1>>>(a, v->cfg2, block_smem_bits_words(v), CNT_NEXT3, CNT_OVER3, d_cnt + CNT_OVER2, 10);
       CK(cudaGetLastError());
