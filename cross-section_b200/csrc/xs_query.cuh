@@ -500,6 +500,8 @@ struct Arena {
   int fstride;                  //   words per row = wside/32 + 2
   const int16_t* nlut;          // neighbour byte -> cell-index delta of its first set bit
   int compact_pairs;            // emit pass 1 evaluates compacted (sample, offset) pairs (needs `mask` in shared memory)
+  uint32_t* mask_alt;           // optional shared-memory home for the masks of sections of <= mask_alt_cap samples
+  int mask_alt_cap;             //   (the neighbour-byte tiers: their foreground bitmap is dead after the walk)
 };
 
 struct Ctl {          // lives in shared memory (one per group)
@@ -1621,10 +1623,12 @@ XS_D int run_area_emit(const G& g, const PlaneCtx& c, const VolView& vol, const 
     return Q_OK;
   }
   hash.fit(ctl.n);
-  claim_blocks(g, c, vol, A, hash, ctl);
+  Arena<CellT> B = A;
+  if (A.mask_alt != nullptr && ctl.n <= A.mask_alt_cap) { B.mask = A.mask_alt; B.compact_pairs = 1; }
+  claim_blocks(g, c, vol, B, hash, ctl);
   if (ctl.overflow) return Q_OVERFLOW;
   if (g.tid() == 0) prof_mark(ctl, 1);
-  const int st = emit_items(g, c, vol, A, hash, ctl, q, out);
+  const int st = emit_items(g, c, vol, B, hash, ctl, q, out);
   if (st != Q_OK) return st;
   if (g.tid() == 0) {
     prof_mark(ctl, 2);
