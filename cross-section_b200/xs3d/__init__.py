@@ -16,6 +16,8 @@ import ctypes as C
 from typing import Optional, Union
 
 import numpy as np
+import builtins
+from collections.abc import Sequence
 import numpy.typing as npt
 
 from . import _abi
@@ -26,7 +28,7 @@ VECTOR_T = Union[tuple, npt.NDArray[np.float32]]
 
 __all__ = [
   "cross_sectional_area", "cross_section", "slice", "set_shape", "clear_shape",
-  "Volume", "cross_sectional_area_batch", "skeleton_tangents", "sweep_skeleton", "XS3DError",
+  "Volume", "SliceBatch", "cross_sectional_area_batch", "skeleton_tangents", "sweep_skeleton", "XS3DError",
 ]
 
 
@@ -66,6 +68,27 @@ def _image_pointer(binimg):
   if a.dtype == bool:
     a = a.view(np.uint8)
   return a, a.ctypes.data, c_order
+
+
+class SliceBatch(Sequence):
+  """The cut-outs of Volume.slice_batch: sequence of Fortran-ordered 2-D views into one [n, pitch] buffer
+  (`.buffer`, `.shapes`); a view is built when an element is accessed, so 10^4 tiny slices cost no Python loop."""
+
+  def __init__(self, buffer, shapes):
+    self.buffer, self.shapes = buffer, shapes
+
+  def __len__(self):
+    return len(self.shapes)
+
+  def __getitem__(self, i):
+    if isinstance(i, builtins.slice):      # (this module defines its own `slice`)
+      return [self[j] for j in range(*i.indices(len(self)))]
+    if i < 0:
+      i += len(self)
+    if not 0 <= i < len(self):
+      raise IndexError(i)
+    h, w = int(self.shapes[i, 0]), int(self.shapes[i, 1])
+    return self.buffer[i, : h * w].reshape((h, w), order="F")
 
 
 class Volume:
@@ -269,8 +292,9 @@ class Volume:
     return (float(a[0]), int(c[0])) if return_contact else float(a[0])
 
   def slice_batch(self, positions, normals, anisotropy=None, standardize_basis=True, crop=float("inf"), pitch=None):
-    """xs3d.slice for n planes of the resident label volume.  Returns a list of n 2-D arrays
-    (views into one fixed-pitch buffer).  `pitch` = elements reserved per plane (default: from crop)."""
+    """xs3d.slice for n planes of the resident label volume.  Returns a sequence of n 2-D arrays
+    (`SliceBatch`: views into one fixed-pitch buffer, made on access).  `pitch` = elements reserved per plane
+    (default: from crop)."""
     assert crop >= 0.0
     if getattr(self, "_label_dtype", None) is None:
       raise ValueError("load_labels() with an ndarray first")
@@ -299,7 +323,7 @@ class Volume:
                                                shapes.ctypes.data, over.ctypes.data, HOST))
     if np.any(over):
       raise XS3DError(f"slice_batch: {int(over.sum())} cut-outs exceed the pitch of {pitch} elements; pass a larger pitch")
-    return [out[i, : shapes[i, 0] * shapes[i, 1]].reshape((shapes[i, 0], shapes[i, 1]), order="F") for i in range(n)]
+    return SliceBatch(out, shapes)
 
   def cross_section_sparse(self, pos, normal, anisotropy=None, method=0):
     """(linear F-order voxel indices uint64 [nnz], contributions float32 [nnz], contact)."""
