@@ -3,8 +3,8 @@
 // (xs3d.hpp:1473-1624, fastxs3d.cpp:119-216).
 //
 // Two execution shapes:
-//   * slice_small_kernel : one CTA per plane, window <= 64x64 cells, everything in shared memory —
-//     the batched "10k cropped planes" path (BASELINE config 4);
+//   * slice_cta_kernel   : one CTA per plane, window <= 64x64 cells (then <= 256x256 for the planes that pass
+//     flags), everything in shared memory — the batched "10k cropped planes" path (BASELINE config 4);
 //   * big path           : whole-GPU kernels per stage for windows up to the full lattice
 //     (un-cropped planes, up to ~7000^2 cells): valid -> rows -> scan -> gather.
 #include <cuda_runtime.h>
@@ -128,9 +128,9 @@ __global__ void __launch_bounds__(256) slice_gather_kernel(SliceCtx s, const uin
 }
 
 // ------------------------------------------------------------------------------------------------
-// small path: one CTA per plane, window <= 64 x 64
+// CTA path: one CTA per plane, window <= 64 x 64, then <= 256 x 256
 // ------------------------------------------------------------------------------------------------
-constexpr int SMALL_W = 64;
+constexpr int SMALL_W = 64, MED_W = 256;
 
 struct SliceBatchArgs {
   const float* pos; const float* nrm;
@@ -143,13 +143,19 @@ struct SliceBatchArgs {
   uint32_t n;
 };
 
-static_assert(SMALL_W * 2 == 128, "slice_small_kernel runs 128 threads, one per bitmap word");
-__global__ void __launch_bounds__(128) slice_small_kernel(SliceBatchArgs a) {
-  __shared__ uint32_t V[SMALL_W * 2], R[SMALL_W * 2];
-  __shared__ RowRuns rows[SMALL_W];
+// One CTA per plane, window <= W x W cells, everything in shared memory.  W = 64 (128 threads): the batched "10k
+// cropped planes" shape; W = 256 (256 threads): the planes the first pass flags as too wide (overflow == 2).
+template <int W, int THREADS>
+__global__ void __launch_bounds__(THREADS) slice_cta_kernel(SliceBatchArgs a, int only_flagged) {
+  constexpr int WORDS = W / 32;                 // bitmap words per window row
+  constexpr int NW = W * WORDS;                 // words in the window
+  constexpr int K = (NW + THREADS - 1) / THREADS;
+  __shared__ uint32_t V[NW], R[NW];
+  __shared__ RowRuns rows[W];
   __shared__ SliceResult res;
   __shared__ int changed;
   for (uint32_t q = blockIdx.x; q < a.n; q += gridDim.x) {
+    if (only_flagged && a.overflow[q] != 2) continue;
     SliceCtx s;
     slice_init(s, a.sx, a.sy, a.sz, mk(a.pos[3 * q], a.pos[3 * q + 1], a.pos[3 * q + 2]), mk(a.nrm[3 * q], a.nrm[3 * q + 1], a.nrm[3 * q + 2]),
                mk(a.wx, a.wy, a.wz), a.positive != 0, a.crop);
@@ -163,19 +169,19 @@ __global__ void __launch_bounds__(128) slice_small_kernel(SliceBatchArgs a) {
       }
       continue;
     }
-    if (s.ww > SMALL_W || s.wh > SMALL_W) {
+    if (s.ww > W || s.wh > W) {
       if (threadIdx.x == 0) { a.shapes[2 * q] = -1; a.shapes[2 * q + 1] = -1; a.overflow[q] = 2; }
       continue;
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int wi = warp; wi < SMALL_W * 2; wi += 4) {
-      const int row = wi >> 1, col = (wi & 1) * 32 + lane;
+    for (int wi = warp; wi < NW; wi += THREADS / 32) {
+      const int row = wi / WORDS, col = (wi % WORDS) * 32 + lane;
       const bool ok = (row < s.wh) && (col < s.ww) && slice_cell(s, s.wx0 + col, s.wy0 + row, false, nullptr);
       const uint32_t w = __ballot_sync(0xffffffffu, ok);
       if (lane == 0) V[wi] = w;
     }
     __syncthreads();
-    if (threadIdx.x < SMALL_W) rows[threadIdx.x] = row_runs(V + 2 * threadIdx.x, 2);
+    for (int row = threadIdx.x; row < W; row += THREADS) rows[row] = row_runs(V + WORDS * row, WORDS);
     __syncthreads();
     const int cx = (int)(s.c - s.wx0), cy = (int)(s.c - s.wy0);
     if (threadIdx.x == 0) res = scan_rows(rows, s.wh, cx, cy);
@@ -183,22 +189,26 @@ __global__ void __launch_bounds__(128) slice_small_kernel(SliceBatchArgs a) {
     const uint32_t* mask = V;
     if (res.fallback) {
       // exact fixpoint fill in shared memory
-      if (threadIdx.x < SMALL_W * 2) R[threadIdx.x] = 0u;
+      for (int wi = threadIdx.x; wi < NW; wi += THREADS) R[wi] = 0u;
       __syncthreads();
-      if (threadIdx.x == 0) R[cy * 2 + (cx >> 5)] = V[cy * 2 + (cx >> 5)] & (1u << (cx & 31));
+      if (threadIdx.x == 0) R[cy * WORDS + (cx >> 5)] = V[cy * WORDS + (cx >> 5)] & (1u << (cx & 31));
       do {
         __syncthreads();
         if (threadIdx.x == 0) changed = 0;
         __syncthreads();
-        {
-          // blockDim.x == SMALL_W * 2: one bitmap word per thread
-          const int wi = threadIdx.x, row = wi >> 1, col = wi & 1;
+        uint32_t gnew[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const int wi = threadIdx.x + k * THREADS;
+          gnew[k] = 0u;
+          if (wi >= NW) continue;
+          const int row = wi / WORDS, col = wi % WORDS;
           const uint32_t v = V[wi], old = R[wi];
           uint32_t seeds = old;
-          if (row > 0) seeds |= R[wi - 2];
-          if (row + 1 < SMALL_W) seeds |= R[wi + 2];
+          if (row > 0) seeds |= R[wi - WORDS];
+          if (row + 1 < W) seeds |= R[wi + WORDS];
           if (col > 0) seeds |= R[wi - 1] >> 31;
-          if (col + 1 < 2) seeds |= R[wi + 1] << 31;
+          if (col + 1 < WORDS) seeds |= R[wi + 1] << 31;
           seeds &= v;
           uint32_t g = seeds, p = v;
           g |= p & (g << 1); p &= p << 1; g |= p & (g << 2); p &= p << 2; g |= p & (g << 4); p &= p << 4;
@@ -206,12 +216,17 @@ __global__ void __launch_bounds__(128) slice_small_kernel(SliceBatchArgs a) {
           p = v;
           g |= p & (g >> 1); p &= p >> 1; g |= p & (g >> 2); p &= p >> 2; g |= p & (g >> 4); p &= p >> 4;
           g |= p & (g >> 8); p &= p >> 8; g |= p & (g >> 16);
-          __syncthreads();
-          if (g != old) { R[wi] = g; changed = 1; }
+          gnew[k] = g;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          const int wi = threadIdx.x + k * THREADS;
+          if (wi < NW && gnew[k] != R[wi]) { R[wi] = gnew[k]; changed = 1; }
         }
         __syncthreads();
       } while (changed);
-      if (threadIdx.x < SMALL_W) rows[threadIdx.x] = row_runs(R + 2 * threadIdx.x, 2);
+      for (int row = threadIdx.x; row < W; row += THREADS) rows[row] = row_runs(R + WORDS * row, WORDS);
       __syncthreads();
       if (threadIdx.x == 0) {
         SliceResult r;
@@ -234,9 +249,9 @@ __global__ void __launch_bounds__(128) slice_small_kernel(SliceBatchArgs a) {
     const unsigned long long total = (unsigned long long)nx * ny;
     if (threadIdx.x == 0) { a.shapes[2 * q] = nx; a.shapes[2 * q + 1] = ny; a.overflow[q] = total > a.pitch_elems ? 1 : 0; }
     if (total > a.pitch_elems) continue;
-    for (int i = threadIdx.x; i < (int)total; i += blockDim.x) {
+    for (int i = threadIdx.x; i < (int)total; i += THREADS) {
       const int x = r.x0 + i % nx, y = r.y0 + i / nx;
-      const bool on = (res.y0 <= res.y1) && ((mask[y * 2 + (x >> 5)] >> (x & 31)) & 1u) && (res.fallback || (y >= res.y0 && y <= res.y1));
+      const bool on = (res.y0 <= res.y1) && ((mask[y * WORDS + (x >> 5)] >> (x & 31)) & 1u) && (res.fallback || (y >= res.y0 && y <= res.y1));
       size_t loc;
       if (on && slice_cell(s, s.wx0 + x, s.wy0 + y, a.c_order != 0, &loc)) copy_label(outq, i, a.labels, loc, a.itemsize);
       else zero_label(outq, i, a.itemsize);
@@ -419,7 +434,9 @@ extern "C" int xs3d_projection_batch(xs3d_volume* v, uint64_t n, const float* po
   a.labels = labels; a.itemsize = itemsize; a.c_order = c_order;
   a.out = d_out; a.pitch_elems = pitch_elems; a.shapes = d_shapes; a.overflow = d_over; a.n = (uint32_t)n;
   const int grid = (int)std::min<uint64_t>(n, (uint64_t)xs_sm_count(v) * 8);
-  slice_small_kernel<<<grid, 128, 0, st>>>(a);
+  slice_cta_kernel<SMALL_W, 128><<<grid, 128, 0, st>>>(a, 0);
+  XS_CK(cudaGetLastError());
+  slice_cta_kernel<MED_W, 256><<<grid, 256, 0, st>>>(a, 1);      // the planes flagged as wider than 64 cells, up to 256
   XS_CK(cudaGetLastError());
   if (mem == XS3D_HOST) {
     XS_CK(cudaMemcpyAsync(shapes, d_shapes, n * 16, cudaMemcpyDeviceToHost, st));
