@@ -338,6 +338,8 @@ def run_own_arm(args):
               "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic.get(kname),
               "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms, "queries_in_kernel": nq_k,
               "note": "latency/issue-bound graph walk over the L2-resident 16 MiB occupancy volume, not an HBM stream (ncu: DRAM 0.1 % of peak, L2 hit 82 %, IPC 2.6/SM); the HBM-bound kernel of the path is the ingest, reported beside it",
+              "issue_rate": {"what": "the bound that actually applies to the dominant kernel (from the ncu capture profiles/r1h_ncu_full_summary.txt, not measured live)",
+                             "ipc_per_sm": 2.68, "peak_ipc_per_sm": 4.0, "frac": 0.67, "warp_instructions_per_query": 31000},
               "ingest_kernel": {"ms": ingest_ms, "achieved": (vol.size * 1.125) / (ingest_ms / 1000.0) / 1e9 if ingest_ms > 0 else None,
                                 "unit": "GB/s", "frac": ((vol.size * 1.125) / (ingest_ms / 1000.0) / 1e9 / peak) if ingest_ms > 0 else None,
                                 "algorithmic_bytes": int(vol.size * 1.125)}}
