@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) area_warp_kernel(BatchArgs a) {
   A.mask = A.bits;
   A.cells = nullptr; A.wside = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
   A.compact_pairs = 1; A.mask_alt = nullptr; A.mask_alt_cap = 0;
+  A.pairs2 = reinterpret_cast<uint16_t*>(base + L::O_HASH); A.pairs2_cap = 2 * HCAP;   // the table is idle during emit pass 2
   PackedHash H;
   H.slot = base + L::O_HASH; H.cap = HCAP; H.max_probe = 48;
   int lg = 0;
@@ -315,6 +316,7 @@ __device__ __forceinline__ bool block_arena(Arena<uint32_t>& A, WideHash& H, con
   A.max_n = s.max_n;
   A.cells = nullptr; A.wside = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
   A.compact_pairs = 0; A.mask_alt = nullptr; A.mask_alt_cap = 0;   // masks live in the HBM slab
+  A.pairs2 = nullptr; A.pairs2_cap = 0;
   H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
   H.hx = vol.hx; H.hy = vol.hy;
   H.alt_tag = nullptr; H.alt_key = nullptr; H.alt_cap = 0;
@@ -424,6 +426,7 @@ __global__ void __maxnreg__(96) area_mid_kernel(BatchArgs a, SlabCfg s, int cnt_
   A.cells = reinterpret_cast<uint8_t*>(smem + MidTier::O_CELLS); A.wside = MidTier::WSIDE;
   A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = MidTier::WSIDE / 32; A.stride = 0; A.halo = 1;
   A.compact_pairs = 0;          // masks live in the HBM slab, except for sections small enough for the (dead) bitmap
+  A.pairs2 = nullptr; A.pairs2_cap = 0;
   A.mask_alt = smem + MidTier::O_FBITS + 32; A.mask_alt_cap = (MidTier::WSIDE + 2) * MidTier::FSTRIDE - 32;
   A.fbits = smem + MidTier::O_FBITS; A.fstride = MidTier::FSTRIDE;
   A.nlut = reinterpret_cast<const int16_t*>(smem + MidTier::O_LUT);
@@ -516,6 +519,7 @@ __global__ void __launch_bounds__(WideTier::THREADS, 1) area_wide_kernel(BatchAr
   A.cells = reinterpret_cast<uint8_t*>(smem + WideTier::O_CELLS); A.wside = WideTier::WSIDE;
   A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = WideTier::WSIDE / 32; A.stride = 0; A.halo = 1;
   A.compact_pairs = 0;          // masks live in the HBM slab, except for sections small enough for the (dead) bitmap
+  A.pairs2 = nullptr; A.pairs2_cap = 0;
   A.mask_alt = smem + WideTier::O_FBITS + 32; A.mask_alt_cap = (WideTier::WSIDE + 2) * WideTier::FSTRIDE - 32;
   A.fbits = smem + WideTier::O_FBITS; A.fstride = WideTier::FSTRIDE;
   A.nlut = reinterpret_cast<const int16_t*>(smem + WideTier::O_LUT);

@@ -500,6 +500,8 @@ struct Arena {
   int fstride;                  //   words per row = wside/32 + 2
   const int16_t* nlut;          // neighbour byte -> cell-index delta of its first set bit
   int compact_pairs;            // emit pass 1 evaluates compacted (sample, offset) pairs (needs `mask` in shared memory)
+  uint16_t* pairs2;             // optional scratch for emit pass 2 on compacted items (>= 27 entries per lane of a
+  int pairs2_cap;               //   one-warp group: the warp tier's first-touch table, idle by then)
   uint32_t* mask_alt;           // optional shared-memory home for the masks of sections of <= mask_alt_cap samples
   int mask_alt_cap;             //   (the neighbour-byte tiers: their foreground bitmap is dead after the walk)
 };
@@ -1548,6 +1550,69 @@ XS_D int emit_items(const G& g, const PlaneCtx& c, const VolView& vol, const Are
   g.sync();
   if (ctl.overflow) return Q_CAPACITY;
   const uint32_t item_off = ctl.item_off, poly_off = ctl.poly_off;
+  // pass 2, one-warp groups with scratch: the kept (sample, offset) pairs of 32 consecutive ranks, listed in (rank, k)
+  // order, are the items; lanes take items 32 at a time (a sample keeps 0-3 items: one loop per sample leaves most
+  // lanes idle), polygon offsets by a warp scan
+  if (g.nwarps() == 1 && A.pairs2 != nullptr && A.pairs2_cap >= 27 * g.wsize()) {
+    int ibase = 0, pbase = 0;
+    const int ws = g.wsize();
+    for (int r0 = 0; r0 < n; r0 += ws) {
+      const int r = r0 + g.lane();
+      const uint32_t keep = (r < n) ? A.mask[r] : 0u;
+      int bx = 0, by = 0, bz = 0;
+      if (keep) {
+        const Sample s = sample_at(c, A, r, (V3*)nullptr);
+        bx = s.rx >> 1; by = s.ry >> 1; bz = s.rz >> 1;
+      }
+      int T;
+      int off = g.wexscan(popc32(keep), T);
+      uint32_t t = keep;
+      while (t) {
+        const int k = ffs32(t) - 1;
+        t &= t - 1u;
+        A.pairs2[off++] = (uint16_t)((g.lane() << 5) | k);
+      }
+      g.converge();
+      for (int j0 = 0; j0 < T; j0 += ws) {
+        const int j = j0 + g.lane();
+        const bool act = j < T;
+        const int pr2 = act ? (int)A.pairs2[j] : 0;
+        const int sl = pr2 >> 5, k = pr2 & 31;
+        const bool first = act && (j == 0 || ((int)A.pairs2[j - 1] >> 5) != sl);
+        const int sbx = g.shfl(bx, sl), sby = g.shfl(by, sl), sbz = g.shfl(bz, sl);
+        int ox, oy, oz;
+        decode_k(k, ox, oy, oz);
+        const int cx = sbx + ox, cy = sby + oy, cz = sbz + oz;
+        const uint32_t cand = act ? cube_at(vol, cx, cy, cz) : 0u;
+        const int pop = popc8(cand);
+        const int cnt = act ? item_polys(cand) : 0;
+        int tp;
+        uint32_t po = poly_off + (uint32_t)(pbase + g.wexscan(cnt, tp));
+        if (act) {
+          ItemRec it;
+          it.poly = po;
+          it.meta = (uint32_t)cnt | (pop >= 5 ? 16u : 0u) | (first ? 32u : 0u);
+          out.items[item_off + (uint32_t)(ibase + j)] = it;
+          PolyRec pr;
+          pr.q = q;
+          if (pop >= 5) {
+            pr.x = (uint16_t)(2 * cx); pr.y = (uint16_t)(2 * cy); pr.z = (uint16_t)(2 * cz); pr.kind = 2;
+            out.polys[po++] = pr;
+          }
+          const uint32_t want = (pop >= 5) ? (~cand & 0xffu) : cand;   // absent voxels are subtracted, present ones added
+          for (int b = 0; b < 8; b++) {
+            if (!((want >> b) & 1u)) continue;
+            pr.x = (uint16_t)(2 * cx + (b & 1)); pr.y = (uint16_t)(2 * cy + ((b >> 1) & 1)); pr.z = (uint16_t)(2 * cz + (b >> 2)); pr.kind = 1;
+            out.polys[po++] = pr;
+          }
+        }
+        pbase += tp;
+      }
+      ibase += T;
+      g.converge();
+    }
+    return Q_OK;
+  }
   // pass 2: write, one chunk of g.size() consecutive ranks at a time
   int ibase = 0, pbase = 0;
   const int gs = g.size();

@@ -55,6 +55,7 @@ struct SmallArena {
     A.bits = bits.data(); A.tested = tested.data(); A.order = order.data(); A.stack = stack.data();
     A.max_n = max_n; A.stack_cap = max_n; A.spill = nullptr; A.mask = A.bits;   // masks alias the (dead) bitmap
     A.cells = nullptr; A.wside = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr; A.compact_pairs = 1; A.mask_alt = nullptr; A.mask_alt_cap = 0;
+    A.pairs2 = reinterpret_cast<uint16_t*>(slots.data()); A.pairs2_cap = 2 * hcap;   // like the warp tier: the table is idle during emit pass 2
     H.slot = slots.data(); H.cap = hcap; H.shift = 32 - __builtin_ctz(hcap); H.max_probe = 64;
     H.cbx = centre.rx >> 1; H.cby = centre.ry >> 1; H.cbz = centre.rz >> 1;
   }
@@ -78,6 +79,7 @@ struct BigArena {
     htag.assign(hcap, 0); hkey.assign(hcap, 0);
     A.bits = bits.data(); A.tested = tested.data(); A.order = order.data(); A.stack = stack.data(); A.mask = mask.data();
     A.cells = nullptr; A.wside = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr; A.compact_pairs = 1; A.mask_alt = nullptr; A.mask_alt_cap = 0;
+    A.pairs2 = nullptr; A.pairs2_cap = 0;
     H.htag = htag.data(); H.hkey = hkey.data(); H.cap = hcap; H.cap_max = hcap; H.shift = 32 - __builtin_ctz(hcap);
     H.hx = v.hx; H.hy = v.hy; H.max_probe = 1 << 30; H.factor = factor;
     H.alt_tag = nullptr; H.alt_key = nullptr; H.alt_cap = 0;
@@ -100,6 +102,7 @@ struct ByteArena {
     fbits.assign((size_t)(256 + 2) * 10, 0xdeadbeefu); lut.assign(256, 0);
     for (int m = 1; m < 256; m++) lut[m] = (int16_t)nbr_delta((uint32_t)m, 256);
     A.fbits = fbits.data(); A.fstride = 10; A.nlut = lut.data(); A.compact_pairs = 0;
+    A.pairs2 = nullptr; A.pairs2_cap = 0;
     A.mask_alt = fbits.data() + 32; A.mask_alt_cap = (int)fbits.size() - 32;   // like the device: small sections keep their masks in the dead bitmap
     A.cells = cells.data(); A.wside = 256; A.ox = A.oy = c.c - 128 - 16; A.halo = 1;
     A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = 8; A.stride = 0;
@@ -126,7 +129,7 @@ struct WideArena {
     const int fs = WS / 32 + 2;
     fbits.assign((size_t)(WS + 2) * fs, 0xdeadbeefu); lut.assign(256, 0);
     for (int m = 1; m < 256; m++) lut[m] = (int16_t)nbr_delta((uint32_t)m, WS);
-    A.fbits = fbits.data(); A.fstride = fs; A.nlut = lut.data(); A.compact_pairs = 0; A.mask_alt = nullptr; A.mask_alt_cap = 0;
+    A.fbits = fbits.data(); A.fstride = fs; A.nlut = lut.data(); A.compact_pairs = 0; A.mask_alt = nullptr; A.mask_alt_cap = 0; A.pairs2 = nullptr; A.pairs2_cap = 0;
     A.cells = cells.data() + 512; A.wside = WS; A.ox = A.oy = c.c - (WS / 64) * 32 - 16; A.halo = 1;
     A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = WS / 32; A.stride = 0;
     A.order = order.data(); A.max_n = max_n; A.stack = stack.data(); A.stack_cap = ring; A.spill = spill.data(); A.mask = mask.data();
