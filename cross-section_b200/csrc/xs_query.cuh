@@ -1416,19 +1416,27 @@ XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const 
           if (m9) tentative |= hash.claim9(my_tag + hash.tag_delta(0, 0, oz - 1), m9, (uint32_t)r, &ovf) << (9 * oz);
         }
       } else {
-        // table in shared memory: offset by offset in lock step — k is the same for every lane, so the offset decoding
-        // and the tag delta are computed once per warp instead of once per claim
+        // table in shared memory: offset by offset in lock step — k is the same for every lane; the tag of block
+        // b + o is linear in o, so the tag delta is carried along with two additions per step instead of decoding k
+        const uint32_t dx = hash.tag_delta(1, 0, 0), dy = hash.tag_delta(0, 1, 0), dz = hash.tag_delta(0, 0, 1);
+        uint32_t dt = 0u - dx - dy - dz;              // o = (-1,-1,-1)
+        int k = 0;
 #pragma unroll 1
-        for (int k = 0; k < 27; k++) {
-          if (!((any >> k) & 1u)) continue;            // warp-uniform
-          int ox, oy, oz;
-          decode_k(k, ox, oy, oz);
-          const uint32_t dt = hash.tag_delta(ox, oy, oz);
-          if ((my_cmask >> k) & 1u) {
-            const int won = hash.claim_tag(my_tag + dt, (uint32_t)r);
-            if (won == 0) ovf = true;
-            if (won == 2) tentative |= 1u << k;
+        for (int oz = 0; oz < 3; oz++) {
+#pragma unroll 1
+          for (int oy = 0; oy < 3; oy++) {
+#pragma unroll 1
+            for (int ox = 0; ox < 3; ox++, k++, dt += dx) {
+              if (!((any >> k) & 1u)) continue;       // warp-uniform
+              if ((my_cmask >> k) & 1u) {
+                const int won = hash.claim_tag(my_tag + dt, (uint32_t)r);
+                if (won == 0) ovf = true;
+                if (won == 2) tentative |= 1u << k;
+              }
+            }
+            dt += dy - 3u * dx;
           }
+          dt += dz - 3u * dy;
         }
       }
       if (r < n) A.mask[r] = tentative;
