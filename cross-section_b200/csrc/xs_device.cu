@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(WARPS * 32, 3) area_warp_kernel(BatchArgs a) {
   A.order = reinterpret_cast<uint16_t*>(base + L::O_ORDER); A.max_n = MAXN;
   A.stack = reinterpret_cast<uint16_t*>(base + L::O_STACK); A.stack_cap = MAXN; A.spill = nullptr;
   A.mask = A.bits;
-  A.cells = nullptr; A.wside = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
+  A.cells = nullptr; A.wside = 0; A.mside = 0; A.moff = 0; A.mlim = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
   A.compact_pairs = 1; A.mask_alt = nullptr; A.mask_alt_cap = 0;
   A.pairs2 = reinterpret_cast<uint16_t*>(base + L::O_HASH); A.pairs2_cap = 2 * HCAP;   // the table is idle during emit pass 2
   PackedHash H;
@@ -252,6 +252,83 @@ __global__ void __launch_bounds__(WARPS * 32, 3) area_warp_kernel(BatchArgs a) {
       continue;
     }
     A.ox = A.oy = c.c - 16 - 32 * (TILES / 2);
+    const V3 rp = vround(p);
+    H.cbx = (int)rp.x >> 1; H.cby = (int)rp.y >> 1; H.cbz = (int)rp.z >> 1;
+    const int st = run_area_emit(g, c, a.vol, A, H, ctl, q, a.out);
+    if (g.lane() == 0) finish_query(a, ctl, q, st, CNT_OVER0, 4);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// T0, neighbour-byte form: one warp per query.  The lattice is sampled into a 96x96-cell bitmap (3x3 tiles, closure
+// from the centre tile) as before, but the walk runs on one neighbour byte per cell for the 63x63 cells around the
+// vertex (sections of <= 384 samples reach at most 31 cells from it) — two shared-memory loads per step, no
+// unwinding iterations, no tile requests.  Per warp: control block, DFS stack, order list, bitmap, neighbour bytes;
+// after the walk the neighbour bytes become the first-touch table (and the pair list of emit pass 2), the bitmap
+// the per-sample masks, the stack the pair list of emit pass 1: 7.35 KB in all.
+// ------------------------------------------------------------------------------------------------
+template <int MAXN, int HCAP>
+struct WarpNLayout {
+  static constexpr int WSIDE = 96, MSIDE = 64, MLIM = 63, MOFF = 17;
+  static constexpr int FSTRIDE = WSIDE / 32 + 1;                 // one shared pad word per bitmap row
+  static constexpr int O_CTL = 0;
+  static constexpr int O_STACK = O_CTL + 36;                     // uint16 cells
+  static constexpr int O_ORDER = O_STACK + MAXN / 2;
+  static constexpr int O_FBITS = O_ORDER + MAXN / 2;             // bitmap; after the walk: per-sample masks
+  static constexpr int F_WORDS = ((WSIDE + 2) * FSTRIDE + 1 + 1) & ~1;
+  static constexpr int O_CELLS = O_FBITS + F_WORDS;              // neighbour bytes; after the walk: first-touch table
+  static constexpr int WORDS = O_CELLS + MSIDE * MSIDE / 4;
+  static_assert(sizeof(Ctl) <= 36 * 4, "ctl slot");
+  static_assert(MAXN <= F_WORDS, "masks alias the bitmap");
+  static_assert(HCAP * 4 == MSIDE * MSIDE, "the first-touch table aliases the neighbour bytes");
+  static_assert(MAXN <= 512, "packed hash rank range");
+  static_assert(MOFF + MLIM <= WSIDE && WSIDE / 2 - MOFF == MLIM / 2, "byte window centred on the vertex, inside the bitmap");
+};
+
+template <int WARPS, int MAXN, int HCAP>
+__global__ void __launch_bounds__(WARPS * 32, 3) area_warpn_kernel(BatchArgs a) {
+  using L = WarpNLayout<MAXN, HCAP>;
+  extern __shared__ __align__(16) uint32_t smem[];
+  int16_t* lut = reinterpret_cast<int16_t*>(smem);               // 256 x int16, shared by the CTA's warps
+  for (int m = threadIdx.x; m < 256; m += blockDim.x) lut[m] = (int16_t)(m ? nbr_delta((uint32_t)m, L::MSIDE) : 0);
+  __syncthreads();
+  uint32_t* base = smem + 128 + (threadIdx.x >> 5) * L::WORDS;
+  Arena<uint16_t> A;
+  A.tx = A.ty = L::WSIDE / 32; A.stride = 0; A.halo = 0;
+  A.bits = nullptr; A.tested = nullptr;
+  A.order = reinterpret_cast<uint16_t*>(base + L::O_ORDER); A.max_n = MAXN;
+  A.stack = reinterpret_cast<uint16_t*>(base + L::O_STACK); A.stack_cap = MAXN; A.spill = nullptr;
+  A.fbits = base + L::O_FBITS; A.fstride = L::FSTRIDE;
+  A.mask = A.fbits;
+  A.cells = reinterpret_cast<uint8_t*>(base + L::O_CELLS);
+  A.wside = L::WSIDE; A.mside = L::MSIDE; A.moff = L::MOFF; A.mlim = L::MLIM;
+  A.nlut = lut;
+  A.compact_pairs = 1; A.mask_alt = nullptr; A.mask_alt_cap = 0;
+  A.pairs2 = reinterpret_cast<uint16_t*>(base + L::O_CELLS); A.pairs2_cap = 2 * HCAP;
+  PackedHash H;
+  H.slot = base + L::O_CELLS; H.cap = HCAP; H.max_probe = 48;
+  int lg = 0;
+  while ((1 << lg) < HCAP) lg++;
+  H.shift = 32 - lg;
+  Ctl& ctl = *reinterpret_cast<Ctl*>(base + L::O_CTL);
+  WarpGroup g;
+  const V3 w = mk(a.wx, a.wy, a.wz);
+  const uint32_t first = a.list_in ? a.counters[CNT_NBIG] : 0u;
+  for (;;) {
+    uint32_t q = 0;
+    if (g.lane() == 0) q = first + atomicAdd(&a.counters[CNT_NEXT0], 1u);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= a.nq) break;
+    if (a.list_in) q = a.list_in[q];
+    PlaneCtx c;
+    const V3 p = mk(__ldg(a.pos + 3 * q), __ldg(a.pos + 3 * q + 1), __ldg(a.pos + 3 * q + 2));
+    const V3 n = mk(__ldg(a.nrm + 3 * q), __ldg(a.nrm + 3 * q + 1), __ldg(a.nrm + 3 * q + 2));
+    if (!plane_init(c, a.vol, p, n, w)) {
+      if (g.lane() == 0) zero_query(a, q);
+      continue;
+    }
+    A.ox = A.oy = c.c - L::WSIDE / 2;       // the vertex's cell sits in the middle of the middle tile
     const V3 rp = vround(p);
     H.cbx = (int)rp.x >> 1; H.cby = (int)rp.y >> 1; H.cbz = (int)rp.z >> 1;
     const int st = run_area_emit(g, c, a.vol, A, H, ctl, q, a.out);
@@ -314,7 +391,7 @@ __device__ __forceinline__ bool block_arena(Arena<uint32_t>& A, WideHash& H, con
   uint32_t* g_bits = p; p += s.bits_words;
   uint32_t* g_tested = p;
   A.max_n = s.max_n;
-  A.cells = nullptr; A.wside = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
+  A.cells = nullptr; A.wside = 0; A.mside = 0; A.moff = 0; A.mlim = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
   A.compact_pairs = 0; A.mask_alt = nullptr; A.mask_alt_cap = 0;   // masks live in the HBM slab
   A.pairs2 = nullptr; A.pairs2_cap = 0;
   H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
@@ -423,7 +500,7 @@ __global__ void __maxnreg__(96) area_mid_kernel(BatchArgs a, SlabCfg s, int cnt_
   uint32_t* const g_key = g_tag + s.hcap_max;
   A.max_n = s.max_n;
   A.stack = reinterpret_cast<uint16_t*>(smem + MidTier::O_RING); A.stack_cap = MidTier::RING;
-  A.cells = reinterpret_cast<uint8_t*>(smem + MidTier::O_CELLS); A.wside = MidTier::WSIDE;
+  A.cells = reinterpret_cast<uint8_t*>(smem + MidTier::O_CELLS); A.wside = MidTier::WSIDE; A.mside = MidTier::WSIDE; A.moff = 0; A.mlim = MidTier::WSIDE;
   A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = MidTier::WSIDE / 32; A.stride = 0; A.halo = 1;
   A.compact_pairs = 0;          // masks live in the HBM slab, except for sections small enough for the (dead) bitmap
   A.pairs2 = nullptr; A.pairs2_cap = 0;
@@ -516,7 +593,7 @@ __global__ void __launch_bounds__(WideTier::THREADS, 1) area_wide_kernel(BatchAr
   uint32_t* const g_key = p;
   A.max_n = s.max_n;
   A.stack = smem + WideTier::O_RING; A.stack_cap = WideTier::RING;
-  A.cells = reinterpret_cast<uint8_t*>(smem + WideTier::O_CELLS); A.wside = WideTier::WSIDE;
+  A.cells = reinterpret_cast<uint8_t*>(smem + WideTier::O_CELLS); A.wside = WideTier::WSIDE; A.mside = WideTier::WSIDE; A.moff = 0; A.mlim = WideTier::WSIDE;
   A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = WideTier::WSIDE / 32; A.stride = 0; A.halo = 1;
   A.compact_pairs = 0;          // masks live in the HBM slab, except for sections small enough for the (dead) bitmap
   A.pairs2 = nullptr; A.pairs2_cap = 0;
@@ -571,7 +648,7 @@ __global__ void __launch_bounds__(BLK_THREADS, 1) section_block_kernel(VolView v
   if (s.max_n >= WideTier::WSIDE * WideTier::WSIDE && WIDE_SMEM_BYTES <= (smem_bits_words + BigTier::FIXED_WORDS) * 4) {
     block_arena<BigTier>(A, H, s, smem, smem_bits_words, c, vol);        // slab pointers and the HBM table
     A.stack = smem + WideTier::O_RING; A.stack_cap = WideTier::RING;
-    A.cells = reinterpret_cast<uint8_t*>(smem + WideTier::O_CELLS); A.wside = WideTier::WSIDE;
+    A.cells = reinterpret_cast<uint8_t*>(smem + WideTier::O_CELLS); A.wside = WideTier::WSIDE; A.mside = WideTier::WSIDE; A.moff = 0; A.mlim = WideTier::WSIDE;
     A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = WideTier::WSIDE / 32; A.stride = 0; A.halo = 1;
     A.fbits = smem + WideTier::O_FBITS; A.fstride = WideTier::FSTRIDE;
     A.nlut = reinterpret_cast<const int16_t*>(smem + WideTier::O_LUT);
@@ -762,7 +839,9 @@ constexpr int T0_CTAS_PER_SM = 3;
 constexpr int MID_BIG_KEY = 26;   // >= 26 of 256 probes foreground (~420 cells): the section will not fit a warp (T0_MAXN); tuned on the
                                   //   bench sweep — a query misjudged as small is handed over by the warp tier, only later
 using T0Layout = WarpLayout<T0_TILES, T0_MAXN, T0_HCAP>;
-#define T0_KERNEL area_warp_kernel<T0_WARPS, T0_TILES, T0_MAXN, T0_HCAP>
+using T0NLayout = WarpNLayout<T0_MAXN, T0_HCAP>;
+#define T0_KERNEL area_warpn_kernel<T0_WARPS, T0_MAXN, T0_HCAP>
+constexpr int T0_SMEM_BYTES = (128 + T0_WARPS * T0NLayout::WORDS) * 4;
 
 struct xs3d_volume {
   int device = 0;
@@ -817,7 +896,7 @@ constexpr int MID_SMEM_BYTES = MidTier::WORDS * 4;
 
 static int configure_kernels(xs3d_volume* v) {
   if (v->kernels_configured) return XS3D_OK;
-  const int t0_bytes = T0_WARPS * T0Layout::WORDS * 4;
+  const int t0_bytes = T0_SMEM_BYTES;
   if (t0_bytes > v->smem_optin) return fail(XS3D_ERR_UNSUPPORTED, "device shared memory too small for the warp tier");
   CK(cudaFuncSetAttribute(T0_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, t0_bytes));
   CK(cudaFuncSetAttribute(area_block_kernel<BigTier>, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
@@ -1142,13 +1221,13 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       a.out = out1; a.done_list = nullptr; a.list_in = sorted; a.list_out = list0;
       const int gridB = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * (T0_CTAS_PER_SM - 2));
       if (!single_grid) {
-        T0_KERNEL<<<gridB, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, v->stream3>>>(a);
+        T0_KERNEL<<<gridB, T0_WARPS * 32, T0_SMEM_BYTES, v->stream3>>>(a);
         CK(cudaGetLastError());
       }
       CK(cudaEventRecord(v->evf[3], v->stream3));
       // ---- launching stream: warp-tier grid A
       const int gridA = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * (single_grid ? T0_CTAS_PER_SM : 2));
-      T0_KERNEL<<<gridA, T0_WARPS * 32, T0_WARPS * T0Layout::WORDS * 4, s1>>>(a);
+      T0_KERNEL<<<gridA, T0_WARPS * 32, T0_SMEM_BYTES, s1>>>(a);
       CK(cudaGetLastError());
       CK(cudaEventRecord(v->evf[1], s1));
       CK(cudaStreamWaitEvent(s1, v->evf[3], 0));       // the polygon kernel needs grid B's records too

@@ -495,7 +495,10 @@ struct Arena {
   // neighbour-mask variant of the window (mid / wide tiers): wside^2 cells, local cell index u + v * wside; one byte per
   // cell = which of its 8 neighbours are foreground and unvisited (see flood_component_nbr).
   uint8_t* cells;               // null: use the bitmap
-  int wside;                    // cells per side, a multiple of 32 (<= 448)
+  int wside;                    // sampled window: cells per side, a multiple of 32 (<= 448)
+  int mside, moff, mlim;        // neighbour bytes: mside bytes per row, for window cells [moff, moff + mlim) of both axes;
+                                //   byte index ci = (u - moff) + (v - moff) * mside; the outermost cells (0 and mlim - 1) are
+                                //   the ring where the walk gives up.  mid / wide tiers: moff 0, mside = mlim = wside.
   uint32_t* fbits;              // foreground bitmap of the window, one zero row / word of padding all round
   int fstride;                  //   words per row = wside/32 + 2
   const int16_t* nlut;          // neighbour byte -> cell-index delta of its first set bit
@@ -916,18 +919,32 @@ XS_D void nbr_lut_fill(const G& g, int16_t* lut, int W) {
 template <class CellT>
 XS_HD uint32_t* frow(const Arena<CellT>& A, int v) { return A.fbits + (size_t)(v + 1) * A.fstride + 1; }
 
-// A set of 32x32-cell tiles of the window (bit = ty * nt + tx), up to 14 x 14 tiles.
-struct TileSet {
-  uint32_t w[7];
-  XS_HD void clear() { for (int i = 0; i < 7; i++) w[i] = 0u; }
+// A set of 32x32-cell tiles of the window (bit = ty * nt + tx), up to 32 * NW tiles.
+template <int NW>
+struct TileSetT {
+  uint32_t w[NW];
+  XS_HD void clear() {
+#pragma unroll
+    for (int i = 0; i < NW; i++) w[i] = 0u;
+  }
   XS_HD void set(int t) { set_word(t >> 5, 1u << (t & 31)); }
   XS_HD bool test(int t) const { return (w[t >> 5] >> (t & 31)) & 1u; }
-  XS_HD bool any() const { uint32_t o = 0u; for (int i = 0; i < 7; i++) o |= w[i]; return o != 0u; }
-  XS_HD int count() const { int c = 0; for (int i = 0; i < 7; i++) c += popc32(w[i]); return c; }
+  XS_HD bool any() const {
+    uint32_t o = 0u;
+#pragma unroll
+    for (int i = 0; i < NW; i++) o |= w[i];
+    return o != 0u;
+  }
+  XS_HD int count() const {
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) c += popc32(w[i]);
+    return c;
+  }
   // f(t) for every tile of the set, ascending; word indices are compile-time constants so the set stays in registers
   template <class F> XS_HD void for_each(F f) const {
 #pragma unroll
-    for (int i = 0; i < 7; i++) {
+    for (int i = 0; i < NW; i++) {
       uint32_t m = w[i];
       while (m) {
         const int b = ffs32(m) - 1;
@@ -938,10 +955,17 @@ struct TileSet {
   }
   XS_HD void set_word(int i, uint32_t bits) {
 #pragma unroll
-    for (int j = 0; j < 7; j++)
+    for (int j = 0; j < NW; j++)
       if (j == i) w[j] |= bits;
   }
 };
+// words a group / cell type pairing needs: one warp per query -> 96-cell window (9 tiles); CTA tiers: 256-cell window
+// (64 tiles) with 16-bit cells, up to 448 cells (196 tiles) with 32-bit cells; host test builds: anything
+template <class G, class CellT> struct TileWords { static constexpr int v = 7; };
+#ifdef __CUDACC__
+template <class CellT> struct TileWords<WarpGroup, CellT> { static constexpr int v = 1; };
+template <> struct TileWords<BlockGroup, uint16_t> { static constexpr int v = 2; };
+#endif
 
 // Sample tile (tx,ty) into the foreground bitmap: a warp per lattice row, a lane per cell.
 template <class G, class CellT>
@@ -974,8 +998,8 @@ XS_D void nbr_sample_tile(const G& g, const PlaneCtx& c, const VolView& vol, con
 
 // Which neighbours of the freshly sampled tile (tx,ty) hold cells adjacent to one of its foreground cells?
 // (evaluated by one warp; every lane returns the same set)
-template <class G, class CellT>
-XS_D void nbr_grow_tile(const G& g, const Arena<CellT>& A, int tx, int ty, TileSet& want) {
+template <class G, class CellT, class TS>
+XS_D void nbr_grow_tile(const G& g, const Arena<CellT>& A, int tx, int ty, TS& want) {
   const int nt = A.wside >> 5, t = ty * nt + tx;
   uint32_t left, right, top, bottom;
 #ifdef __CUDA_ARCH__
@@ -1009,7 +1033,7 @@ XS_D void nbr_grow_tile(const G& g, const Arena<CellT>& A, int tx, int ty, TileS
 // stops when it steps on one (the section leaves the window).
 template <class G, class CellT>
 XS_D void nbr_masks_tile(const G& g, const Arena<CellT>& A, int tx, int ty) {
-  const int W = A.wside;
+  const int MS = A.mside, ML = A.mlim, MO = A.moff;
   for (int row = g.warp(); row < 32; row += g.nwarps()) {
     const int v = ty * 32 + row;
     const uint32_t* rm = frow(A, v - 1) + tx;
@@ -1029,11 +1053,12 @@ XS_D void nbr_masks_tile(const G& g, const Arena<CellT>& A, int tx, int ty) {
 #endif
       const int u = tx * 32 + l;
       const uint32_t am = (uint32_t)(xm >> l) & 7u, a0 = (uint32_t)(x0 >> l) & 7u, aq = (uint32_t)(xq >> l) & 7u;   // bits: u-1, u, u+1
-      if (a0 & 2u) {
-        const bool inner = u > 0 && v > 0 && u < W - 1 && v < W - 1;
+      const int mu = u - MO, mv = v - MO;
+      if ((a0 & 2u) && mu >= 0 && mv >= 0 && mu < ML && mv < ML) {
+        const bool inner = mu > 0 && mv > 0 && mu < ML - 1 && mv < ML - 1;
         const uint32_t m = ((aq >> 2) & 1u) | ((aq & 1u) << 1) | (((am >> 2) & 1u) << 2) | ((am & 1u) << 3) |
                            (((aq >> 1) & 1u) << 4) | (((am >> 1) & 1u) << 5) | (((a0 >> 2) & 1u) << 6) | ((a0 & 1u) << 7);
-        A.cells[v * W + u] = (uint8_t)(inner ? m : 0u);
+        A.cells[mv * MS + mu] = (uint8_t)(inner ? m : 0u);
       }
     }
   }
@@ -1042,10 +1067,10 @@ XS_D void nbr_masks_tile(const G& g, const Arena<CellT>& A, int tx, int ty) {
 // order[] entry of window cell ci = u + v * W: the index itself for 16-bit cells (W = 256: u | v << 8), packed
 // (u | v << 16) for 32-bit cells — what CellPack / sample_at decode
 template <class CellT>
-XS_HD CellT nbr_order_entry(int ci, int W) {
-  if (sizeof(CellT) == 2) return (CellT)ci;
-  const int v = ci / W;
-  return (CellT)((uint32_t)(ci - v * W) | ((uint32_t)v << 16));
+XS_HD CellT nbr_order_entry(int ci, int MS, int MO) {
+  if (sizeof(CellT) == 2 && MS == 256) return (CellT)ci;      // (mid tier: the byte index is the packed cell already)
+  const int v = MS == 64 ? (ci >> 6) : ci / MS, u = ci - v * MS;   // (64: the warp tier's row; spares it an integer division)
+  return CellPack<CellT>::pack(u + MO, v + MO);
 }
 
 // Mark cell ci visited: clear its bit in the neighbour bytes of its eight neighbours (the bit a neighbour holds for
@@ -1065,7 +1090,7 @@ XS_HD uint32_t nbr_row_clear(int r) { return r == 0 ? 0x021001u : (r == 1 ? 0x80
 template <class CellT>
 XS_HD int dfs_run_nbr(const Arena<CellT>& A, int& n_io, int& depth_io, int& lo_io, int& ci_io) {
   int n = n_io, depth = depth_io, lo = lo_io, ci = ci_io;
-  const int W = A.wside;
+  const int W = A.mside, ML = A.mlim;
   const int max_n = A.max_n;
   uint8_t* const cells = A.cells;
   const int16_t* const lut = A.nlut;
@@ -1104,9 +1129,9 @@ XS_HD int dfs_run_nbr(const Arena<CellT>& A, int& n_io, int& depth_io, int& lo_i
     }
     ci += (int)lut[m];
     const int v = ci / W, u = ci - v * W;
-    if ((u == 0) | (v == 0) | (u == W - 1) | (v == W - 1) | (n >= max_n)) { status = ST_OVERFLOW; break; }
+    if ((u == 0) | (v == 0) | (u == ML - 1) | (v == ML - 1) | (n >= max_n)) { status = ST_OVERFLOW; break; }
     for (int k = 0; k < 8; k++) nbr_visit_one(cells, ci, k, W);
-    order[n++] = nbr_order_entry<CellT>(ci, W);
+    order[n++] = nbr_order_entry<CellT>(ci, W, A.moff);
     if ((m & (m - 1u)) == 0u) depth--;     // tail call: the cell we leave has nothing left, reuse its frame
     if (depth - lo == cap) {
       const int nlo = lo + A.stack_cap / 2;
@@ -1154,7 +1179,7 @@ template <class CellT> __device__ __forceinline__ void sts_cell(uint32_t base, i
 template <class CellT>
 __device__ __forceinline__ int dfs_run_nbr_warp(const Arena<CellT>& A, int& n_io, int& depth_io, int& lo_io, int& ci_io, int lane, uint32_t* scratch32) {
   int n = n_io, depth = depth_io, lo = lo_io, ci = ci_io;
-  const int W = A.wside;
+  const int W = A.mside;
   const int max_n = A.max_n;
   // loop invariants are pinned in registers (opaque moves): ptxas otherwise re-derives them — special-register reads
   // and the lane arithmetic included — inside the loop, on the dependent chain
@@ -1174,7 +1199,7 @@ __device__ __forceinline__ int dfs_run_nbr_warp(const Arena<CellT>& A, int& n_io
   const uint32_t vsel = pin_u32(s_cells + (uint32_t)((vr - 1) * W - 1), scratch32);   // + ci = address of the first of this lane's three cells
   // the clear mask of this lane's word = upper half of (fhi:flo) << 8 * (address & 3)
   const uint32_t fhi = pin_u32(hiword ? 0u : nbr_row_clear(vr), scratch32), flo = pin_u32(hiword ? nbr_row_clear(vr) : 0u, scratch32);
-  const uint32_t lim = (uint32_t)(W - 2);
+  const uint32_t lim = (uint32_t)(A.mlim - 2);
   const bool lane0 = pin_u32((uint32_t)lane, scratch32) == 0u;
   int status;
   int budget = 0;   // steps that can be taken before `order` or the stack ring may be full (re-evaluated when it runs out)
@@ -1201,7 +1226,7 @@ __device__ __forceinline__ int dfs_run_nbr_warp(const Arena<CellT>& A, int& n_io
       }
       sts_u32(va, vold & ~__funnelshift_l(flo, fhi, vb << 3));
       if (lane0) {
-        order[n] = nbr_order_entry<CellT>(ci, W);
+        order[n] = nbr_order_entry<CellT>(ci, W, A.moff);
         sts_cell<CellT>(s_stack, depth & smask, (uint32_t)ci);
       }
       n++;
@@ -1251,15 +1276,17 @@ out:
 
 template <class G, class CellT>
 XS_D int flood_component_nbr(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, Ctl& ctl, bool* empty) {
-  const int W = A.wside, nt = W >> 5;
+  const int W = A.wside, nt = W >> 5, MS = A.mside;
   {
-    const int words = (W + 2) * A.fstride;
+    // rows -1 .. W, one pad word either side of each row — or, with fstride = W/32 + 1, a single pad word per row that
+    // serves as the right pad of its row and the left pad of the next (then one word more at the very end)
+    const int words = (W + 2) * A.fstride + (A.fstride == nt + 1 ? 1 : 0);
     for (int i = g.tid(); i < words; i += g.size()) A.fbits[i] = 0u;
   }
   const int cu = c.c - A.ox, cv = c.c - A.oy;
   if (g.tid() == 0) {
     ctl.status = ST_DONE; ctl.req_tx = 0; ctl.req_ty = 0;
-    ctl.n = 0; ctl.depth = 0; ctl.lo = 0; ctl.u = cu + cv * W; ctl.v = 0; ctl.m = 0; ctl.npoly = 0; ctl.overflow = 0; ctl.contact = 0u; ctl.counter = 0u; ctl.tiles = 0;
+    ctl.n = 0; ctl.depth = 0; ctl.lo = 0; ctl.u = (cu - A.moff) + (cv - A.moff) * MS; ctl.v = 0; ctl.m = 0; ctl.npoly = 0; ctl.overflow = 0; ctl.contact = 0u; ctl.counter = 0u; ctl.tiles = 0;
     ctl.item_off = 0u; ctl.poly_off = 0u;
     for (int i = 0; i < 7; i++) ctl.grow[i] = 0u;
     for (int i = 0; i < 6; i++) ctl.t[i] = 0u;
@@ -1267,20 +1294,23 @@ XS_D int flood_component_nbr(const G& g, const PlaneCtx& c, const VolView& vol, 
   }
   g.sync();
   *empty = false;
-  // closure over tiles, starting from the 3x3 tiles around the centre cell's tile: a tile is sampled as soon as a
-  // sampled foreground cell touches it, so the walk never has to stop and ask for cells
+  // closure over tiles, starting from the centre cell's tile (and `halo` tiles around it): a tile is sampled as soon
+  // as a sampled foreground cell touches it, so the walk never has to stop and ask for cells
+  constexpr int NW = TileWords<G, CellT>::v;
+  typedef TileSetT<NW> TileSet;
+  if (nt * nt > 32 * NW) return Q_OVERFLOW;        // (cannot happen with the windows the tiers use)
   TileSet done, todo;
   done.clear(); todo.clear();
   {
     const int ctx = cu >> 5, cty = cv >> 5;
-    for (int ty = cty - 1; ty <= cty + 1; ty++)
-      for (int tx = ctx - 1; tx <= ctx + 1; tx++)
+    for (int ty = cty - A.halo; ty <= cty + A.halo; ty++)
+      for (int tx = ctx - A.halo; tx <= ctx + A.halo; tx++)
         if (tx >= 0 && ty >= 0 && tx < nt && ty < nt) todo.set(ty * nt + tx);
   }
   while (todo.any()) {
     todo.for_each([&](int t) { nbr_sample_tile(g, c, vol, A, t % nt, t / nt); });
 #pragma unroll
-    for (int i = 0; i < 7; i++) done.w[i] |= todo.w[i];
+    for (int i = 0; i < NW; i++) done.w[i] |= todo.w[i];
     g.sync();
     TileSet want;
     want.clear();
@@ -1290,12 +1320,12 @@ XS_D int flood_component_nbr(const G& g, const PlaneCtx& c, const VolView& vol, 
     });
     if (g.lane() == 0) {
 #pragma unroll
-      for (int i = 0; i < 7; i++)
+      for (int i = 0; i < NW; i++)
         if (want.w[i] & ~done.w[i]) atomic_or_u32(&ctl.grow[i], want.w[i] & ~done.w[i]);
     }
     g.sync();
 #pragma unroll
-    for (int i = 0; i < 7; i++) todo.w[i] = ctl.grow[i] & ~done.w[i];   // (next write to ctl.grow: after the next sync)
+    for (int i = 0; i < NW; i++) todo.w[i] = ctl.grow[i] & ~done.w[i];   // (next write to ctl.grow: after the next sync)
   }
   done.for_each([&](int t) { nbr_masks_tile(g, A, t % nt, t / nt); });
   g.sync();
@@ -1309,8 +1339,8 @@ XS_D int flood_component_nbr(const G& g, const PlaneCtx& c, const VolView& vol, 
     } else {
       g.converge();
       if (g.lane() == 0) {
-        A.order[0] = nbr_order_entry<CellT>(ci0, W); A.stack[0] = (CellT)ci0;
-        for (int k = 0; k < 8; k++) nbr_visit_one(A.cells, ci0, k, W);
+        A.order[0] = nbr_order_entry<CellT>(ci0, MS, A.moff); A.stack[0] = (CellT)ci0;
+        for (int k = 0; k < 8; k++) nbr_visit_one(A.cells, ci0, k, MS);
       }
       g.converge();
       int n = 1, depth = 1, lo = 0, ci = ci0;

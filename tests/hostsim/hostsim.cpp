@@ -54,9 +54,36 @@ struct SmallArena {
     order.assign(max_n, 0); stack.assign(max_n, 0); slots.assign(hcap, 0);
     A.bits = bits.data(); A.tested = tested.data(); A.order = order.data(); A.stack = stack.data();
     A.max_n = max_n; A.stack_cap = max_n; A.spill = nullptr; A.mask = A.bits;   // masks alias the (dead) bitmap
-    A.cells = nullptr; A.wside = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr; A.compact_pairs = 1; A.mask_alt = nullptr; A.mask_alt_cap = 0;
+    A.cells = nullptr; A.wside = 0; A.mside = 0; A.moff = 0; A.mlim = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr; A.compact_pairs = 1; A.mask_alt = nullptr; A.mask_alt_cap = 0;
     A.pairs2 = reinterpret_cast<uint16_t*>(slots.data()); A.pairs2_cap = 2 * hcap;   // like the warp tier: the table is idle during emit pass 2
     H.slot = slots.data(); H.cap = hcap; H.shift = 32 - __builtin_ctz(hcap); H.max_probe = 64;
+    H.cbx = centre.rx >> 1; H.cby = centre.ry >> 1; H.cbz = centre.rz >> 1;
+  }
+};
+
+// warp-tier arena, neighbour-byte form (what the device's T0 runs): 96x96-cell bitmap with one shared pad word per
+// row, 64-byte-wide neighbour rows for the 63x63 cells around the vertex; the first-touch table and the pair list of
+// emit pass 2 alias the neighbour bytes, the masks alias the bitmap — exactly the device's aliasing
+struct SmallNbrArena {
+  std::vector<uint32_t> fbits, cellwords;
+  std::vector<uint16_t> order, stack;
+  std::vector<int16_t> lut;
+  Arena<uint16_t> A;
+  PackedHash H;
+  void setup(const PlaneCtx& c, const Sample& centre) {
+    const int max_n = 384, hcap = 1024, WS = 96, MS = 64, ML = 63, MO = 17, fs = WS / 32 + 1;
+    fbits.assign((size_t)(WS + 2) * fs + 2, 0xdeadbeefu);
+    cellwords.assign(64 + MS * MS / 4 + 64, 0xeeeeeeeeu);          // (a row of slack either side, like the device's neighbours)
+    order.assign(max_n, 0); stack.assign(max_n, 0); lut.assign(256, 0);
+    for (int m = 1; m < 256; m++) lut[m] = (int16_t)nbr_delta((uint32_t)m, MS);
+    A.tx = A.ty = WS / 32; A.ox = A.oy = c.c - WS / 2; A.halo = 0; A.stride = 0;
+    A.bits = nullptr; A.tested = nullptr;
+    A.order = order.data(); A.stack = stack.data(); A.max_n = max_n; A.stack_cap = max_n; A.spill = nullptr;
+    A.fbits = fbits.data(); A.fstride = fs; A.mask = A.fbits;
+    A.cells = reinterpret_cast<uint8_t*>(cellwords.data() + 64); A.wside = WS; A.mside = MS; A.moff = MO; A.mlim = ML;
+    A.nlut = lut.data(); A.compact_pairs = 1; A.mask_alt = nullptr; A.mask_alt_cap = 0;
+    A.pairs2 = reinterpret_cast<uint16_t*>(cellwords.data() + 64); A.pairs2_cap = 2 * hcap;
+    H.slot = cellwords.data() + 64; H.cap = hcap; H.shift = 32 - __builtin_ctz(hcap); H.max_probe = 64;
     H.cbx = centre.rx >> 1; H.cby = centre.ry >> 1; H.cbz = centre.rz >> 1;
   }
 };
@@ -78,7 +105,7 @@ struct BigArena {
     const uint32_t hcap = pow2_at_least((uint64_t)max_n * (uint64_t)factor + 64);
     htag.assign(hcap, 0); hkey.assign(hcap, 0);
     A.bits = bits.data(); A.tested = tested.data(); A.order = order.data(); A.stack = stack.data(); A.mask = mask.data();
-    A.cells = nullptr; A.wside = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr; A.compact_pairs = 1; A.mask_alt = nullptr; A.mask_alt_cap = 0;
+    A.cells = nullptr; A.wside = 0; A.mside = 0; A.moff = 0; A.mlim = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr; A.compact_pairs = 1; A.mask_alt = nullptr; A.mask_alt_cap = 0;
     A.pairs2 = nullptr; A.pairs2_cap = 0;
     H.htag = htag.data(); H.hkey = hkey.data(); H.cap = hcap; H.cap_max = hcap; H.shift = 32 - __builtin_ctz(hcap);
     H.hx = v.hx; H.hy = v.hy; H.max_probe = 1 << 30; H.factor = factor;
@@ -104,7 +131,7 @@ struct ByteArena {
     A.fbits = fbits.data(); A.fstride = 10; A.nlut = lut.data(); A.compact_pairs = 0;
     A.pairs2 = nullptr; A.pairs2_cap = 0;
     A.mask_alt = fbits.data() + 32; A.mask_alt_cap = (int)fbits.size() - 32;   // like the device: small sections keep their masks in the dead bitmap
-    A.cells = cells.data(); A.wside = 256; A.ox = A.oy = c.c - 128 - 16; A.halo = 1;
+    A.cells = cells.data(); A.wside = 256; A.mside = 256; A.moff = 0; A.mlim = 256; A.ox = A.oy = c.c - 128 - 16; A.halo = 1;
     A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = 8; A.stride = 0;
     A.order = order.data(); A.max_n = max_n; A.stack = stack.data(); A.stack_cap = ring; A.spill = spill.data(); A.mask = mask.data();
     H.htag = htag.data(); H.hkey = hkey.data(); H.cap = hcap; H.cap_max = hcap; H.shift = 32 - __builtin_ctz(hcap);
@@ -130,7 +157,7 @@ struct WideArena {
     fbits.assign((size_t)(WS + 2) * fs, 0xdeadbeefu); lut.assign(256, 0);
     for (int m = 1; m < 256; m++) lut[m] = (int16_t)nbr_delta((uint32_t)m, WS);
     A.fbits = fbits.data(); A.fstride = fs; A.nlut = lut.data(); A.compact_pairs = 0; A.mask_alt = nullptr; A.mask_alt_cap = 0; A.pairs2 = nullptr; A.pairs2_cap = 0;
-    A.cells = cells.data() + 512; A.wside = WS; A.ox = A.oy = c.c - (WS / 64) * 32 - 16; A.halo = 1;
+    A.cells = cells.data() + 512; A.wside = WS; A.mside = WS; A.moff = 0; A.mlim = WS; A.ox = A.oy = c.c - (WS / 64) * 32 - 16; A.halo = 1;
     A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = WS / 32; A.stride = 0;
     A.order = order.data(); A.max_n = max_n; A.stack = stack.data(); A.stack_cap = ring; A.spill = spill.data(); A.mask = mask.data();
     H.htag = htag.data(); H.hkey = hkey.data(); H.cap = hcap; H.cap_max = hcap; H.shift = 32 - __builtin_ctz(hcap);
@@ -145,6 +172,7 @@ extern "C" {
 // mode 2: like 0 but with a tiny DFS stack ring (exercises spill/refill).
 // mode 3: neighbour-byte (mid-tier-like) arena with a 64-entry ring first, big arena on overflow.
 // mode 4: neighbour-byte arena with a 160-cell window and 32-bit cells (wide-tier-like) first, big arena on overflow.
+// mode 5: the warp tier's neighbour-byte arena first, big arena on overflow.
 // stats[0] = queries that overflowed the small arena, stats[1] = total samples, stats[2] = total items, stats[3] = polygons
 void hostsim_area_batch(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t sz, uint64_t nq, const float* pos,
                         const float* nrm, const float* w, float* area, uint8_t* contact, int mode, int64_t* stats) {
@@ -176,6 +204,14 @@ void hostsim_area_batch(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t s
       ByteArena ya;
       ya.setup(c, v, 4096, 64);
       st = run_area_emit(g, c, v, ya.A, ya.H, ctl, (uint32_t)q, O.out);
+      if (st != Q_OK) n_over++;
+    }
+    if (mode == 5) {
+      SmallNbrArena sn;
+      const V3 rp = vround(c.g.pos);
+      Sample ctr; ctr.rx = (int)rp.x; ctr.ry = (int)rp.y; ctr.rz = (int)rp.z;
+      sn.setup(c, ctr);
+      st = run_area_emit(g, c, v, sn.A, sn.H, ctl, (uint32_t)q, O.out);
       if (st != Q_OK) n_over++;
     }
     if (mode == 4) {

@@ -10,7 +10,7 @@ import golden_util as gu
 from conftest import bits
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4, 5])
 def test_area_random(hostsim, oracle, mode):
   rng = np.random.default_rng(1234 + mode)
   for it in range(250):
@@ -22,8 +22,9 @@ def test_area_random(hostsim, oracle, mode):
 
 def test_area_golden(hostsim, golden):
   for i, vol, p, n, w in gu.small_cases(golden):
-    a2, c2, _ = hostsim.area_batch(vol, p, n, w, 1)
-    assert bits(a2[0]) == bits(golden["small_area"][i]) and c2[0] == golden["small_contact"][i], i
+    for mode in (1, 5):
+      a2, c2, _ = hostsim.area_batch(vol, p, n, w, mode)
+      assert bits(a2[0]) == bits(golden["small_area"][i]) and c2[0] == golden["small_contact"][i], (i, mode)
 
 
 def test_area_neurite_tiers(hostsim, oracle):
@@ -41,6 +42,9 @@ def test_area_neurite_tiers(hostsim, oracle):
   assert np.array_equal(bits(a[:200]), bits(a3)) and np.array_equal(c[:200], c3)
   a4, c4, st4 = hostsim.area_batch(vol, qp[:200], qn[:200], [32, 32, 40], 4)   # ... with 32-bit cells and a 160-cell window (wide tier)
   assert np.array_equal(bits(a[:200]), bits(a4)) and np.array_equal(c[:200], c4)
+  a5, c5, st5 = hostsim.area_batch(vol, qp, qn, [32, 32, 40], 5)               # the warp tier's neighbour-byte arena, big arena on overflow
+  assert np.array_equal(bits(a), bits(a5)) and np.array_equal(c, c5)
+  assert 0 < st5[0] < len(qp) // 2, "some, not most, queries should overflow the warp tier's arena"
 
 
 def test_area_long_sections_mid_tier(hostsim, oracle):
