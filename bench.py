@@ -330,16 +330,16 @@ def run_own_arm(args):
   else:
     alg_bytes = int(frac * (stats["samples"] * 1 + 8 * stats["blocks"])) + 29 * nq_k
   achieved = alg_bytes / (dom_ms / 1000.0) / 1e9
-  kname = {"warp_tier_ms": "area_warp_kernel", "mid_tier_ms": "area_mid_kernel", "big_tier_ms": "area_block_kernel<BigTier>", "polygon_ms": "poly_eval_kernel"}[dom]
+  kname = {"warp_tier_ms": "area_warpn_kernel", "mid_tier_ms": "area_mid_kernel", "big_tier_ms": "area_block_kernel<BigTier>", "polygon_ms": "poly_eval_kernel"}[dom]
   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
   # (profiles/r1g_ncu_full_summary.txt, profiles/r1g_per_kernel_hbm_l2.txt)
-  ncu_traffic = {"area_warp_kernel": 2850000, "area_mid_kernel": 1700000 + 360000, "poly_eval_kernel": 14440000 + 2080000, "combine_kernel": 10600000 + 1680000}
+  ncu_traffic = {"area_warpn_kernel": 3010000, "area_mid_kernel": 1650000 + 620000, "poly_eval_kernel": 14420000 + 2100000, "combine_kernel": 10590000 + 1580000}
   roofline = {"bound": "hbm", "kernel": kname,
               "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic.get(kname),
               "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms, "queries_in_kernel": nq_k,
-              "note": "latency/issue-bound graph walk over the L2-resident 16 MiB occupancy volume, not an HBM stream (ncu: DRAM 0.1 % of peak, L2 hit 82 %, IPC 2.6/SM); the HBM-bound kernel of the path is the ingest, reported beside it",
-              "issue_rate": {"what": "the bound that actually applies to the dominant kernel (from the ncu capture profiles/r1h_ncu_full_summary.txt, not measured live)",
-                             "ipc_per_sm": 2.68, "peak_ipc_per_sm": 4.0, "frac": 0.67, "warp_instructions_per_query": 31000},
+              "note": "latency/issue-bound graph walk over the L2-resident 16 MiB occupancy volume, not an HBM stream (ncu: DRAM 0.1 % of peak, L2 hit 84 %, IPC 2.6/SM); the HBM-bound kernel of the path is the ingest, reported beside it",
+              "issue_rate": {"what": "the bound that actually applies to the dominant kernel (from the ncu capture profiles/r1i_ncu_full_summary.txt, not measured live)",
+                             "ipc_per_sm": 2.57, "peak_ipc_per_sm": 4.0, "frac": 0.64, "warp_instructions_per_query": 24000},
               "ingest_kernel": {"ms": ingest_ms, "achieved": (vol.size * 1.125) / (ingest_ms / 1000.0) / 1e9 if ingest_ms > 0 else None,
                                 "unit": "GB/s", "frac": ((vol.size * 1.125) / (ingest_ms / 1000.0) / 1e9 / peak) if ingest_ms > 0 else None,
                                 "algorithmic_bytes": int(vol.size * 1.125)}}

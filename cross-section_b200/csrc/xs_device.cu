@@ -5,7 +5,8 @@
 //        the only HBM-streaming kernel of the area path (reads V bytes, writes V/8).  Replaces the
 //        host-side np.asfortranarray + per-query compute_cube() loads (xs3d.hpp:26-48).
 //   classify_kernel / order_kernel : size estimate per query -> queries ordered largest first.
-//   area_warp_kernel  (T0): persistent, one WARP per query, whole working set in shared memory.
+//   area_warpn_kernel (T0): persistent, one WARP per query, whole working set in shared memory (96x96-cell lattice
+//        bitmap + one neighbour byte per cell around the vertex).
 //   area_mid_kernel   (T1): persistent, one CTA per query, 256x256-cell window as one neighbour byte per cell
 //        in shared memory; runs on a second stream beside T0 and takes what T0 hands over.
 //   area_wide_kernel  (T2): the same walk with a 416x416-cell window, one CTA per SM.
@@ -146,26 +147,6 @@ __global__ void __launch_bounds__(256) ingest_label_kernel(const T* __restrict__
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// T0: one warp per query, shared-memory arena (7.3 KB per warp -> 30 warps per SM)
-// ------------------------------------------------------------------------------------------------
-template <int TILES, int MAXN, int HCAP>
-struct WarpLayout {
-  static constexpr int W = TILES * 32;
-  static constexpr int STRIDE = TILES + 1;
-  static constexpr int O_BITS = 0;                       // lattice bitmap; after the walk: per-sample masks
-  static constexpr int O_TESTED = O_BITS + W * STRIDE;
-  static constexpr int O_ORDER = O_TESTED + 4;           // uint16 cells
-  static constexpr int O_STACK = O_ORDER + MAXN / 2;
-  static constexpr int O_HASH = O_STACK + MAXN / 2;
-  static constexpr int O_CTL = O_HASH + HCAP;
-  static constexpr int WORDS = O_CTL + 40;
-  static_assert(TILES * TILES <= 128, "tested bitmask");
-  static_assert(MAXN <= W * STRIDE, "masks alias the bitmap");
-  static_assert(MAXN <= 512 && W <= 256, "packed hash rank / uint16 cell range");
-  static_assert(sizeof(Ctl) <= 40 * 4, "ctl slot");
-};
-
 struct BatchArgs {
   VolView vol;
   const float* pos;
@@ -214,54 +195,8 @@ __device__ __forceinline__ void zero_query(const BatchArgs& a, uint32_t q) {
   if (a.done_list) a.done_list[atomicAdd(&a.counters[CNT_DONE2], 1u)] = q;
 }
 
-template <int WARPS, int TILES, int MAXN, int HCAP>
-__global__ void __launch_bounds__(WARPS * 32, 3) area_warp_kernel(BatchArgs a) {
-  using L = WarpLayout<TILES, MAXN, HCAP>;
-  extern __shared__ __align__(16) uint32_t smem[];
-  uint32_t* base = smem + (threadIdx.x >> 5) * L::WORDS;
-  Arena<uint16_t> A;
-  A.tx = A.ty = TILES; A.stride = L::STRIDE; A.halo = 0;
-  A.bits = base + L::O_BITS; A.tested = base + L::O_TESTED;
-  A.order = reinterpret_cast<uint16_t*>(base + L::O_ORDER); A.max_n = MAXN;
-  A.stack = reinterpret_cast<uint16_t*>(base + L::O_STACK); A.stack_cap = MAXN; A.spill = nullptr;
-  A.mask = A.bits;
-  A.cells = nullptr; A.wside = 0; A.mside = 0; A.moff = 0; A.mlim = 0; A.fbits = nullptr; A.fstride = 0; A.nlut = nullptr;
-  A.compact_pairs = 1; A.mask_alt = nullptr; A.mask_alt_cap = 0;
-  A.pairs2 = reinterpret_cast<uint16_t*>(base + L::O_HASH); A.pairs2_cap = 2 * HCAP;   // the table is idle during emit pass 2
-  PackedHash H;
-  H.slot = base + L::O_HASH; H.cap = HCAP; H.max_probe = 48;
-  int lg = 0;
-  while ((1 << lg) < HCAP) lg++;
-  H.shift = 32 - lg;
-  Ctl& ctl = *reinterpret_cast<Ctl*>(base + L::O_CTL);
-  WarpGroup g;
-  const V3 w = mk(a.wx, a.wy, a.wz);
-  // size-ordered list (largest estimated section first); its first counters[CNT_NBIG] entries belong to the mid tier
-  const uint32_t first = a.list_in ? a.counters[CNT_NBIG] : 0u;
-  for (;;) {
-    uint32_t q = 0;
-    if (g.lane() == 0) q = first + atomicAdd(&a.counters[CNT_NEXT0], 1u);
-    q = __shfl_sync(0xffffffffu, q, 0);
-    if (q >= a.nq) break;
-    if (a.list_in) q = a.list_in[q];
-    PlaneCtx c;
-    const V3 p = mk(__ldg(a.pos + 3 * q), __ldg(a.pos + 3 * q + 1), __ldg(a.pos + 3 * q + 2));
-    const V3 n = mk(__ldg(a.nrm + 3 * q), __ldg(a.nrm + 3 * q + 1), __ldg(a.nrm + 3 * q + 2));
-    if (!plane_init(c, a.vol, p, n, w)) {
-      if (g.lane() == 0) zero_query(a, q);
-      continue;
-    }
-    A.ox = A.oy = c.c - 16 - 32 * (TILES / 2);
-    const V3 rp = vround(p);
-    H.cbx = (int)rp.x >> 1; H.cby = (int)rp.y >> 1; H.cbz = (int)rp.z >> 1;
-    const int st = run_area_emit(g, c, a.vol, A, H, ctl, q, a.out);
-    if (g.lane() == 0) finish_query(a, ctl, q, st, CNT_OVER0, 4);
-    __syncwarp();
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// T0, neighbour-byte form: one warp per query.  The lattice is sampled into a 96x96-cell bitmap (3x3 tiles, closure
+// T0: one warp per query.  The lattice is sampled into a 96x96-cell bitmap (3x3 tiles, closure
 // from the centre tile) as before, but the walk runs on one neighbour byte per cell for the 63x63 cells around the
 // vertex (sections of <= 384 samples reach at most 31 cells from it) — two shared-memory loads per step, no
 // unwinding iterations, no tile requests.  Per warp: control block, DFS stack, order list, bitmap, neighbour bytes;
@@ -833,12 +768,11 @@ struct DevBuf {
   void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
-// warp tier configuration (shared memory per warp = WarpLayout::WORDS * 4 bytes)
-constexpr int T0_WARPS = 10, T0_TILES = 3, T0_MAXN = 384, T0_HCAP = 1024;   // 3 CTAs per SM -> 30 warps per SM (2 beside a mid-tier CTA)
+// warp tier configuration (shared memory per warp = WarpNLayout::WORDS * 4 bytes)
+constexpr int T0_WARPS = 10, T0_MAXN = 384, T0_HCAP = 1024;   // 3 CTAs per SM -> 30 warps per SM (2 beside a mid-tier CTA)
 constexpr int T0_CTAS_PER_SM = 3;
 constexpr int MID_BIG_KEY = 26;   // >= 26 of 256 probes foreground (~420 cells): the section will not fit a warp (T0_MAXN); tuned on the
                                   //   bench sweep — a query misjudged as small is handed over by the warp tier, only later
-using T0Layout = WarpLayout<T0_TILES, T0_MAXN, T0_HCAP>;
 using T0NLayout = WarpNLayout<T0_MAXN, T0_HCAP>;
 #define T0_KERNEL area_warpn_kernel<T0_WARPS, T0_MAXN, T0_HCAP>
 constexpr int T0_SMEM_BYTES = (128 + T0_WARPS * T0NLayout::WORDS) * 4;
