@@ -97,3 +97,18 @@ def test_skeleton_tangents():
   assert np.allclose(np.abs(t[2]), np.array([1, 1, 0]) / np.sqrt(2), atol=1e-6)
   assert np.allclose(np.abs(t[3]), [0, 1, 0]) and np.allclose(t[4], [0, 0, 1])
   assert np.allclose(np.linalg.norm(t, axis=1), 1, atol=1e-6)
+
+
+def test_slice_batch_sequence_is_lazy_views():
+  """Volume.slice_batch returns a SliceBatch: a Sequence of Fortran-ordered views into one [n, pitch] buffer."""
+  import numpy as np
+  import xs3d
+  buf = np.arange(36, dtype=np.uint16).reshape(3, 12)
+  b = xs3d.SliceBatch(buf, np.array([[2, 3], [3, 4], [1, 1]]))
+  assert len(b) == 3 and b[0].shape == (2, 3) and b[-1].shape == (1, 1)
+  assert np.array_equal(b[0], np.array([[0, 2, 4], [1, 3, 5]], np.uint16)) and b[1][2, 3] == 12 + 11
+  assert [x.shape for x in b] == [(2, 3), (3, 4), (1, 1)] and [x.shape for x in b[1:]] == [(3, 4), (1, 1)]
+  assert np.shares_memory(b[1], buf)
+  import pytest
+  with pytest.raises(IndexError):
+    b[3]
