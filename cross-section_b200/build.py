@@ -15,7 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libxs3d_b200.so")
 OBJ = os.path.join(HERE, "lib", "obj")
-UNITS = ["xs_device.cu", "xs_slow.cu", "xs_slice.cu"]
+UNITS = ["xs_device.cu", "xs_slow.cu", "xs_slice.cu", "xs_hostpack.cpp"]   # .cpp: host-only code, compiled by g++
+CXX = os.environ.get("CXX", "g++")
 NVCC = os.environ.get("NVCC", "nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
@@ -28,14 +29,17 @@ def _deps():
 
 
 def _compile(unit):
-  obj = os.path.join(OBJ, unit.replace(".cu", ".o"))
+  obj = os.path.join(OBJ, os.path.splitext(unit)[0] + ".o")
   src = os.path.join(SRC, unit)
   newest = max(os.path.getmtime(p) for p in _deps())
   if os.path.exists(obj) and os.path.getmtime(obj) >= newest:
     return obj, ""
-  r = subprocess.run([NVCC, *FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
+  if unit.endswith(".cpp"):
+    r = subprocess.run([CXX, "-std=c++17", "-O3", "-fPIC", "-pthread", "-c", src, "-o", obj], capture_output=True, text=True)
+  else:
+    r = subprocess.run([NVCC, *FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
   if r.returncode != 0:
-    raise RuntimeError(f"nvcc failed on {unit}:\n{r.stdout}\n{r.stderr}")
+    raise RuntimeError(f"compiler failed on {unit}:\n{r.stdout}\n{r.stderr}")
   return obj, r.stderr
 
 
@@ -54,7 +58,7 @@ def build(force=False, verbose=False):
     if verbose:
       print(log)
   if force or not os.path.exists(OUT) or any(os.path.getmtime(o) > os.path.getmtime(OUT) for o in objs):
-    r = subprocess.run([NVCC, "-shared", "-o", OUT, *objs, "-lcudart"], capture_output=True, text=True)
+    r = subprocess.run([NVCC, "-shared", "-o", OUT, *objs, "-lcudart", "-lpthread"], capture_output=True, text=True)
     if r.returncode != 0:
       raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
   return OUT

@@ -125,6 +125,55 @@ __global__ void __launch_bounds__(256) ingest_generic_kernel(const uint8_t* __re
   }
 }
 
+// Bit-packed image (bit i <-> voxel with linear index i != 0, packed on the host by xs_pack_bits) -> occupancy bytes.
+// Fast path: Fortran order, sx % 16 == 0 — each thread turns 16 voxels x 4 rows (four 2-byte loads) into 8 output bytes.
+__global__ void __launch_bounds__(256) ingest_bits_f16_kernel(const uint8_t* __restrict__ bits, uint8_t* __restrict__ cubes,
+                                                              int sx, int sy, int sz, int hx, int hy, int hz) {
+  const int gx = hx >> 3;
+  const size_t total = (size_t)gx * hy * hz;
+  const size_t rowb = (size_t)sx >> 3;          // bytes per x-row of the bit stream
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int xg = (int)(idx % gx);
+    const size_t t = idx / gx;
+    const int by = (int)(t % hy), bz = (int)(t / hy);
+    const int y0 = 2 * by, z0 = 2 * bz;
+    const bool y1ok = (y0 + 1) < sy, z1ok = (z0 + 1) < sz;
+    const uint8_t* p00 = bits + (size_t)2 * xg + rowb * ((size_t)y0 + (size_t)sy * z0);
+    const uint32_t a = *reinterpret_cast<const uint16_t*>(p00);
+    const uint32_t b = y1ok ? *reinterpret_cast<const uint16_t*>(p00 + rowb) : 0u;
+    const uint32_t c = z1ok ? *reinterpret_cast<const uint16_t*>(p00 + rowb * sy) : 0u;
+    const uint32_t d = (y1ok && z1ok) ? *reinterpret_cast<const uint16_t*>(p00 + rowb * sy + rowb) : 0u;
+    uint32_t o[2] = { 0u, 0u };
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t q = ((a >> (2 * j)) & 3u) | (((b >> (2 * j)) & 3u) << 2) | (((c >> (2 * j)) & 3u) << 4) | (((d >> (2 * j)) & 3u) << 6);
+      o[j >> 2] |= q << (8 * (j & 3));
+    }
+    *reinterpret_cast<uint2*>(cubes + (size_t)8 * xg + (size_t)hx * ((size_t)by + (size_t)hy * bz)) = make_uint2(o[0], o[1]);
+  }
+}
+// Generic path: any size / memory order, one thread per output byte.
+__global__ void __launch_bounds__(256) ingest_bits_generic_kernel(const uint8_t* __restrict__ bits, uint8_t* __restrict__ cubes,
+                                                                  int sx, int sy, int sz, int hx, int hy, int hz,
+                                                                  long long stx, long long sty, long long stz) {
+  const size_t total = (size_t)hx * hy * hz;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int bx = (int)(idx % hx);
+    const size_t t = idx / hx;
+    const int by = (int)(t % hy), bz = (int)(t / hy);
+    uint32_t m = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const int x = 2 * bx + (b & 1), y = 2 * by + ((b >> 1) & 1), z = 2 * bz + (b >> 2);
+      if (x < sx && y < sy && z < sz) {
+        const unsigned long long i = (unsigned long long)((long long)x * stx + (long long)y * sty + (long long)z * stz);
+        if ((__ldg(bits + (i >> 3)) >> (i & 7)) & 1u) m |= 1u << b;
+      }
+    }
+    cubes[idx] = (uint8_t)m;
+  }
+}
+
 // Label volume -> occupancy bytes of ONE label: one resident segmentation serves every object in
 // it without materialising (or uploading) a boolean image per object.  One thread per output byte, any item size,
 // either memory order.  HBM-bound: reads V * itemsize bytes, writes V/8.
@@ -805,6 +854,8 @@ struct xs3d_volume {
   uint64_t poly_cap = 0, item_cap = 0;
   SlabCfg cfg1{}, cfg2{};
   uint32_t* h_counters = nullptr;   // pinned: CNT_WORDS counters + 8 u64 stats
+  uint8_t* h_bits = nullptr;        // pinned staging of the bit-packed image (upload_packed_and_ingest)
+  size_t h_bits_cap = 0;
   uint64_t stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t tier_stats[2] = {0, 0};   // samples / items handled by the CTA tiers
   uint32_t wide_over = 0;            // queries the wide tier passed on to the big tier
@@ -890,6 +941,7 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
                      &v->polys, &v->items, &v->vals, &v->geom, &v->qinfo, &v->slab_mid, &v->keys, &v->polys2, &v->items2, &v->vals2, &v->slab_wide };
   for (DevBuf* b : bufs) b->release();
   if (v->h_counters) cudaFreeHost(v->h_counters);
+  if (v->h_bits) cudaFreeHost(v->h_bits);
   delete v;
   return XS3D_OK;
 }
@@ -921,6 +973,60 @@ static int launch_ingest(xs3d_volume* v, const uint8_t* d_img, int c_order) {
   return XS3D_OK;
 }
 
+extern "C" int xs_pack_bits(const uint8_t* in, size_t lo, size_t hi, uint8_t* out);   // xs_hostpack.cpp
+
+extern "C" int xs_pack_threads(void);                                                 // xs_hostpack.cpp
+
+// Host image -> occupancy bytes through the bit-packed upload: the host cores pack the image to one bit per voxel
+// (a quarter of it at a time, so that packing and the transfers overlap), 1/8 of the bytes cross PCIe, the device builds
+// the occupancy bytes from the bits.  Worth it from a few MiB up, and only with enough host threads to out-run the link
+// (measured on a B200 box: 8 threads pack 94 GB/s, 14 threads 130 GB/s; the link carries 54 GB/s); otherwise the image goes up as it is.
+// XS3D_NO_PACK=1 / XS3D_FORCE_PACK=1 override.
+constexpr size_t PACK_MIN_VOXELS = (size_t)8 << 20;
+constexpr int PACK_MIN_THREADS = 6;
+static bool use_packed_upload(size_t voxels) {
+  static const bool off = getenv("XS3D_NO_PACK") != nullptr;
+  static const bool force = getenv("XS3D_FORCE_PACK") != nullptr;
+  if (off || voxels < PACK_MIN_VOXELS) return false;
+  return force || xs_pack_threads() >= PACK_MIN_THREADS;
+}
+static int upload_packed_and_ingest(xs3d_volume* v, const uint8_t* binimg, int c_order) {
+  const size_t voxels = (size_t)v->sx * v->sy * v->sz;
+  const size_t nbytes = (voxels + 7) / 8;
+  if (v->h_bits_cap < nbytes + 64) {
+    if (v->h_bits) cudaFreeHost(v->h_bits);
+    v->h_bits = nullptr; v->h_bits_cap = 0;
+    CK(cudaHostAlloc((void**)&v->h_bits, nbytes + 4096, cudaHostAllocDefault));
+    v->h_bits_cap = nbytes + 4096;
+  }
+  RET(v->raw.ensure(nbytes + 4096));
+  uint8_t* d_bits = (uint8_t*)v->raw.p;
+  const size_t chunk = ((voxels / 4 + 63) / 64) * 64;
+  for (size_t lo = 0; lo < voxels; lo += chunk) {
+    const size_t hi = std::min(voxels, lo + chunk);
+    xs_pack_bits(binimg, lo, hi, v->h_bits);
+    CK(cudaMemcpyAsync(d_bits + lo / 8, v->h_bits + lo / 8, (hi - lo + 7) / 8, cudaMemcpyHostToDevice, v->stream));
+  }
+  CK(cudaEventRecord(v->ev[6], v->stream));
+  const size_t nblocks = (size_t)v->hx * v->hy * v->hz;
+  if (!c_order && (v->sx % 16 == 0)) {
+    const size_t total = nblocks / 8;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
+    ingest_bits_f16_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+  } else {
+    const int grid = (int)std::min<size_t>((nblocks + 255) / 256, (size_t)v->sm_count * 32);
+    if (c_order)
+      ingest_bits_generic_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz,
+                                                              (long long)v->sy * v->sz, (long long)v->sz, 1ll);
+    else
+      ingest_bits_generic_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz,
+                                                              1ll, (long long)v->sx, (long long)v->sx * v->sy);
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(v->ev[7], v->stream));
+  return XS3D_OK;
+}
+
 extern "C" int xs3d_volume_load(xs3d_volume* v, const uint8_t* binimg, int mem, int c_order) {
   if (!v) return fail(XS3D_ERR_ARG, "null volume");
   CK(cudaSetDevice(v->device));
@@ -928,14 +1034,18 @@ extern "C" int xs3d_volume_load(xs3d_volume* v, const uint8_t* binimg, int mem, 
   if (voxels == 0) { v->loaded = true; return XS3D_OK; }
   if (!binimg) return fail(XS3D_ERR_ARG, "null image");
   const uint8_t* d_img = binimg;
-  if (mem == XS3D_HOST) {
-    RET(v->raw.ensure(voxels + 64));
-    CK(cudaMemcpyAsync(v->raw.p, binimg, voxels, cudaMemcpyHostToDevice, v->stream));
-    d_img = (const uint8_t*)v->raw.p;
+  if (mem == XS3D_HOST && use_packed_upload(voxels)) {
+    RET(upload_packed_and_ingest(v, binimg, c_order));
+  } else {
+    if (mem == XS3D_HOST) {
+      RET(v->raw.ensure(voxels + 64));
+      CK(cudaMemcpyAsync(v->raw.p, binimg, voxels, cudaMemcpyHostToDevice, v->stream));
+      d_img = (const uint8_t*)v->raw.p;
+    }
+    CK(cudaEventRecord(v->ev[6], v->stream));
+    RET(launch_ingest(v, d_img, c_order));
+    CK(cudaEventRecord(v->ev[7], v->stream));
   }
-  CK(cudaEventRecord(v->ev[6], v->stream));
-  RET(launch_ingest(v, d_img, c_order));
-  CK(cudaEventRecord(v->ev[7], v->stream));
   CK(cudaStreamSynchronize(v->stream));
   CK(cudaEventElapsedTime(&v->timing[4], v->ev[6], v->ev[7]));
   v->loaded = true;
@@ -1332,13 +1442,17 @@ extern "C" int xs3d_area_sweep_host(xs3d_volume* v, const uint8_t* binimg, int c
   for (uint64_t i = 0; i < n; i++)
     if (normal[3 * i] == 0.0f && normal[3 * i + 1] == 0.0f && normal[3 * i + 2] == 0.0f) return fail(XS3D_ERR_ARG, "normal vector must not be a null vector (all zeros).");
   RET(ensure_batch_workspace(v, n));
-  RET(v->raw.ensure(voxels + 64));
   CK(cudaMemcpyAsync(v->q_pos.p, pos, n * 12, cudaMemcpyHostToDevice, v->stream));
   CK(cudaMemcpyAsync(v->q_nrm.p, normal, n * 12, cudaMemcpyHostToDevice, v->stream));
-  CK(cudaMemcpyAsync(v->raw.p, binimg, voxels, cudaMemcpyHostToDevice, v->stream));
-  CK(cudaEventRecord(v->ev[6], v->stream));
-  RET(launch_ingest(v, (const uint8_t*)v->raw.p, c_order));
-  CK(cudaEventRecord(v->ev[7], v->stream));
+  if (use_packed_upload(voxels)) {
+    RET(upload_packed_and_ingest(v, binimg, c_order));
+  } else {
+    RET(v->raw.ensure(voxels + 64));
+    CK(cudaMemcpyAsync(v->raw.p, binimg, voxels, cudaMemcpyHostToDevice, v->stream));
+    CK(cudaEventRecord(v->ev[6], v->stream));
+    RET(launch_ingest(v, (const uint8_t*)v->raw.p, c_order));
+    CK(cudaEventRecord(v->ev[7], v->stream));
+  }
   v->loaded = true;
   RET(area_batch_device(v, n, (const float*)v->q_pos.p, (const float*)v->q_nrm.p, anisotropy, (float*)v->q_area.p, (uint8_t*)v->q_contact.p, n < 4));
   CK(cudaEventElapsedTime(&v->timing[4], v->ev[6], v->ev[7]));

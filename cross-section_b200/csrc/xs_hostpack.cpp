@@ -1,0 +1,172 @@
+// xs_hostpack.cpp — host side of the bit-packed upload (plain C++, compiled by g++; no CUDA here).
+//
+// A boolean volume crosses PCIe as one BYTE per voxel when uploaded as the reference hands it over (uint8 / bool
+// ndarray): 128 MiB for 512^3, 2.4 ms at the ~54 GB/s a B200 host link sustains — three times the 0.78 ms the sweep
+// itself takes.  The host cores can turn those bytes into bits at memory speed (~100 GB/s with 12-16 threads on the
+// bench box: 1.2 ms for 128 MiB), after which only 16 MiB cross the link.  xs_pack_bits does that with a persistent
+// thread pool; the device then builds its occupancy bytes from the bits (ingest_bits_kernel, xs_device.cu).
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
+#if defined(__linux__)
+#include <sched.h>
+#endif
+
+namespace {
+
+// bytes [lo, hi) of `in` -> bits [lo, hi) of `out` (bit i of the stream = byte i != 0; lo is a multiple of 64)
+void pack_range_scalar(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
+  size_t i = lo;
+  for (; i + 8 <= hi; i += 8) {
+    uint64_t x;
+    memcpy(&x, in + i, 8);
+    // per byte: 0x80 set iff byte != 0, then gather the eight flags into one byte
+    x = ((x & 0x7f7f7f7f7f7f7f7full) + 0x7f7f7f7f7f7f7f7full) | x;
+    x = (x >> 7) & 0x0101010101010101ull;
+    out[i >> 3] = (uint8_t)((x * 0x0102040810204080ull) >> 56);
+  }
+  if (i < hi) {
+    uint8_t b = 0;
+    for (size_t j = i; j < hi; j++) b |= (uint8_t)((in[j] != 0) << (j - i));
+    out[i >> 3] = b;
+  }
+}
+
+#if defined(__x86_64__)
+__attribute__((target("avx2"))) void pack_range_avx2(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
+  const __m256i z = _mm256_setzero_si256();
+  size_t i = lo;
+  for (; i + 32 <= hi; i += 32) {
+    const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i));
+    const uint32_t m = ~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, z));
+    memcpy(out + (i >> 3), &m, 4);
+  }
+  if (i < hi) pack_range_scalar(in, i, hi, out);
+}
+#endif
+
+void pack_range(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
+#if defined(__x86_64__)
+  static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("XS3D_NO_AVX2");
+  if (avx2) { pack_range_avx2(in, lo, hi, out); return; }
+#endif
+  pack_range_scalar(in, lo, hi, out);
+}
+
+// A small persistent pool: workers sleep on a condition variable between jobs (creating 16 threads per call would cost
+// more than the packing itself).  A job is cut into 256 KiB grains handed out through an atomic cursor, so a worker
+// that loses its core for a while (the box also runs the CUDA driver's and the caller's other threads) delays the job
+// by one grain, not by its whole share; the calling thread packs grains too.
+constexpr size_t GRAIN = (size_t)256 << 10;   // a multiple of 64
+
+class Pool {
+ public:
+  explicit Pool(int n) : n_(n) {
+    for (int i = 0; i < n_ - 1; i++) threads_.emplace_back([this] { loop(); });
+  }
+  ~Pool() {
+    { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_++; }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+  }
+  int size() const { return n_; }
+  void run(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      in_ = in; out_ = out; lo_ = lo; hi_ = hi;
+      next_.store(0, std::memory_order_relaxed);
+      pending_ = n_ - 1; gen_++;
+    }
+    cv_.notify_all();
+    work(in, lo, hi, out);
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void work(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
+    for (;;) {
+      const size_t a = lo + GRAIN * next_.fetch_add(1, std::memory_order_relaxed);
+      if (a >= hi) return;
+      pack_range(in, a, std::min(hi, a + GRAIN), out);
+    }
+  }
+  void loop() {
+    uint64_t seen = 0;
+    for (;;) {
+      const uint8_t* in; uint8_t* out; size_t lo, hi;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+        in = in_; out = out_; lo = lo_; hi = hi_;
+      }
+      work(in, lo, hi, out);
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--pending_ == 0) done_.notify_all();
+      }
+    }
+  }
+  int n_;
+  std::vector<std::thread> threads_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const uint8_t* in_ = nullptr; uint8_t* out_ = nullptr;
+  size_t lo_ = 0, hi_ = 0;
+  std::atomic<size_t> next_{0};
+  int pending_ = 0;
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+};
+
+std::mutex g_pool_mu;
+Pool* g_pool = nullptr;
+
+// Threads for the pool: the cores this process may run on (affinity mask, not the machine's core count), shared among
+// the ranks torchrun started on this node (LOCAL_WORLD_SIZE), minus two (the caller's other threads and the CUDA
+// driver's need somewhere to run: on a 16-core B200 box the pipelined sweep takes 1.38 ms with 14 threads, 1.66 ms with
+// 16, 1.79 ms with 8), at most 16.  XS3D_HOST_THREADS overrides.
+int pool_threads() {
+  if (const char* e = getenv("XS3D_HOST_THREADS")) return std::max(1, atoi(e));
+  unsigned hc = std::thread::hardware_concurrency();
+#if defined(__linux__)
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) hc = (unsigned)CPU_COUNT(&set);
+#endif
+  unsigned ranks = 1;
+  if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = (unsigned)std::max(1, atoi(e));
+  const unsigned share = (hc ? hc : 4u) / ranks;
+  return (int)std::min<unsigned>(share > 3u ? share - 2u : 1u, 16u);
+}
+
+}  // namespace
+
+// Pack bytes [lo, hi) of `in` (lo a multiple of 64) into the bit stream `out` (bit i <-> byte i != 0).  Thread safe:
+// concurrent callers take turns on the pool.  Returns the number of threads used.
+extern "C" int xs_pack_threads(void);
+
+extern "C" int xs_pack_bits(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
+  if (hi <= lo) return 0;
+  if (hi - lo < (1u << 20)) { pack_range(in, lo, hi, out); return 1; }
+  std::lock_guard<std::mutex> lk(g_pool_mu);
+  if (!g_pool) g_pool = new Pool(xs_pack_threads());
+  g_pool->run(in, lo, hi, out);
+  return g_pool->size();
+}
+
+// Threads xs_pack_bits would use (decides whether the packed upload is worth it: xs_device.cu, use_packed_upload).
+extern "C" int xs_pack_threads(void) {
+  static const int n = pool_threads();
+  return n;
+}

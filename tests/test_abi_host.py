@@ -112,3 +112,26 @@ def test_slice_batch_sequence_is_lazy_views():
   import pytest
   with pytest.raises(IndexError):
     b[3]
+
+
+def test_host_bit_packing_matches_numpy():
+  """xs_pack_bits (csrc/xs_hostpack.cpp; the host half of the bit-packed volume upload): bit i of the stream is
+  byte i != 0, for single-threaded and pooled sizes, ragged tails, chunked calls and byte values other than 0/1."""
+  from xs3d import _abi
+  lib = C.CDLL(_abi.LIB_PATH)
+  lib.xs_pack_bits.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+  lib.xs_pack_bits.restype = C.c_int
+  rng = np.random.default_rng(5)
+  for n in (1, 7, 8, 63, 64, 65, 1000, 4099, (1 << 20) + 13, (3 << 20) + 5, 9 << 20):
+    img = (rng.random(n) < 0.3).astype(np.uint8) * rng.integers(1, 256, n, dtype=np.uint8)
+    exp = np.packbits(img != 0, bitorder="little")
+    out = np.full((n + 7) // 8 + 8, 0xAA, np.uint8)
+    threads = lib.xs_pack_bits(img.ctypes.data, 0, n, out.ctypes.data)
+    assert threads >= 1 and np.array_equal(out[: len(exp)], exp), n
+    assert np.all(out[len(exp):] == 0xAA), n            # nothing written past the stream
+    # the same stream built a quarter at a time (how the upload overlaps packing with the transfers)
+    out2 = np.zeros_like(out)
+    chunk = ((n // 4 + 63) // 64) * 64
+    for lo in range(0, n, max(chunk, 64)):
+      lib.xs_pack_bits(img.ctypes.data, lo, min(n, lo + max(chunk, 64)), out2.ctypes.data)
+    assert np.array_equal(out2[: len(exp)], exp), n

@@ -27,26 +27,51 @@ def neurite512():
   return vol, verts, tans
 
 
+def _cubes_of(xs, v):
+  import torch
+  with xs.Volume(v) as V:
+    ptr, nbytes = V.cubes()
+    holder = type("H", (), {})()
+    holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(holder, device="cuda").cpu().numpy()
+
+
+def _cubes_numpy(vol):
+  shape = vol.shape
+  h = [(s + 1) // 2 for s in shape]
+  pad = np.zeros([2 * x for x in h], bool)
+  pad[: shape[0], : shape[1], : shape[2]] = vol
+  exp = np.zeros(h, np.uint8)
+  for b in range(8):
+    exp |= (pad[(b & 1)::2, ((b >> 1) & 1)::2, (b >> 2)::2].astype(np.uint8) << b)
+  return exp.ravel(order="F")
+
+
 def test_ingest_matches_numpy(xs):
   """The occupancy-byte volume equals compute_cube() of every block, for aligned/unaligned sizes and both memory orders."""
-  import torch
   rng = np.random.default_rng(0)
   for shape in [(64, 48, 32), (33, 17, 9), (1, 1, 1), (16, 1, 5), (128, 64, 2), (50, 50, 50)]:
     vol = rng.random(shape) < 0.4
     for order in ("F", "C"):
       v = np.asfortranarray(vol) if order == "F" else np.ascontiguousarray(vol)
-      with xs.Volume(v) as V:
-        ptr, nbytes = V.cubes()
-        holder = type("H", (), {})()
-        holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-        got = torch.as_tensor(holder, device="cuda").cpu().numpy()
-      h = [(s + 1) // 2 for s in shape]
-      pad = np.zeros([2 * x for x in h], bool)
-      pad[: shape[0], : shape[1], : shape[2]] = vol
-      exp = np.zeros(h, np.uint8)
-      for b in range(8):
-        exp |= (pad[(b & 1)::2, ((b >> 1) & 1)::2, (b >> 2)::2].astype(np.uint8) << b)
-      assert np.array_equal(got, exp.ravel(order="F")), (shape, order)
+      assert np.array_equal(_cubes_of(xs, v), _cubes_numpy(vol)), (shape, order)
+
+
+def test_bit_packed_upload_matches_numpy(xs):
+  """Host images of >= 8 Mi voxels go up bit-packed (xs_pack_bits on the host cores, ingest_bits_* kernels on the
+  device): same occupancy bytes as the plain upload, for the aligned Fortran fast path, odd sizes and C order, and
+  the same areas as the device-resident plain path."""
+  import torch
+  rng = np.random.default_rng(7)
+  for shape in [(256, 256, 128), (272, 190, 171), (203, 211, 197), (2048, 64, 65)]:
+    vol = rng.random(shape) < 0.35
+    assert vol.size >= (8 << 20)
+    exp = _cubes_numpy(vol)
+    for order in ("F", "C"):
+      v = np.asfortranarray(vol) if order == "F" else np.ascontiguousarray(vol)
+      assert np.array_equal(_cubes_of(xs, v), exp), (shape, order)
+      # the plain (unpacked) path: the same image handed over as a device tensor
+      assert np.array_equal(_cubes_of(xs, torch.from_numpy(v.view(np.uint8)).cuda().view(torch.bool)), exp), (shape, order)
 
 
 def test_golden_small_area_and_sections(xs, golden):

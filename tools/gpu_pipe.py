@@ -32,3 +32,11 @@ for slot, i, a, b, c in sorted(log, key=lambda x: x[2]):
 d = torch.empty(vol.size, dtype=torch.uint8, device="cuda")
 for _ in range(3):
   torch.cuda.synchronize(); t = time.perf_counter(); d.copy_(hvol, non_blocking=True); torch.cuda.synchronize(); print("H2D 128 MiB: %.2f ms" % ((time.perf_counter() - t) * 1e3))
+# host bit-packing rate alone (xs_pack_bits on the pinned image)
+import ctypes as C
+lib = C.CDLL(_abi.LIB_PATH)
+lib.xs_pack_bits.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+hb = torch.empty(vol.size // 8 + 64, dtype=torch.uint8).pin_memory()
+for _ in range(4):
+  t = time.perf_counter(); nt = lib.xs_pack_bits(hvol.data_ptr(), 0, vol.size, hb.data_ptr()); dt = time.perf_counter() - t
+  print("pack 128 MiB with %d threads: %.2f ms (%.1f GB/s)" % (nt, dt * 1e3, vol.size / dt / 1e9))
