@@ -152,6 +152,126 @@ __global__ void __launch_bounds__(256) ingest_bits_f16_kernel(const uint8_t* __r
     *reinterpret_cast<uint2*>(cubes + (size_t)8 * xg + (size_t)hx * ((size_t)by + (size_t)hy * bz)) = make_uint2(o[0], o[1]);
   }
 }
+// Fortran order, sx % 32 == 0: 32 voxels x 4 rows (four 4-byte loads) -> 16 output bytes (one 16-byte store) per thread.
+__device__ __forceinline__ uint32_t spread_pairs(uint32_t x) {
+  // bits (p0 p1 p2 p3), two bits each, of the low byte -> pair j in bits [8j, 8j+2)
+  x &= 0xffu;
+  x = (x | (x << 12)) & 0x000f000fu;
+  return (x | (x << 6)) & 0x03030303u;
+}
+__global__ void __launch_bounds__(256) ingest_bits_f32_kernel(const uint8_t* __restrict__ bits, uint8_t* __restrict__ cubes,
+                                                              int sx, int sy, int sz, int hx, int hy, int hz) {
+  const int gx = hx >> 4;
+  const size_t total = (size_t)gx * hy * hz;
+  const size_t rowb = (size_t)sx >> 3;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int xg = (int)(idx % gx);
+    const size_t t = idx / gx;
+    const int by = (int)(t % hy), bz = (int)(t / hy);
+    const int y0 = 2 * by, z0 = 2 * bz;
+    const bool y1ok = (y0 + 1) < sy, z1ok = (z0 + 1) < sz;
+    const uint8_t* p00 = bits + (size_t)4 * xg + rowb * ((size_t)y0 + (size_t)sy * z0);
+    const uint32_t a = __ldcs(reinterpret_cast<const uint32_t*>(p00));
+    const uint32_t b = y1ok ? __ldcs(reinterpret_cast<const uint32_t*>(p00 + rowb)) : 0u;
+    const uint32_t c = z1ok ? __ldcs(reinterpret_cast<const uint32_t*>(p00 + rowb * sy)) : 0u;
+    const uint32_t d = (y1ok && z1ok) ? __ldcs(reinterpret_cast<const uint32_t*>(p00 + rowb * sy + rowb)) : 0u;
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      o[k] = spread_pairs(a >> (8 * k)) | (spread_pairs(b >> (8 * k)) << 2) | (spread_pairs(c >> (8 * k)) << 4) | (spread_pairs(d >> (8 * k)) << 6);
+    *reinterpret_cast<uint4*>(cubes + (size_t)16 * xg + (size_t)hx * ((size_t)by + (size_t)hy * bz)) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+// C order (z fastest), sz % 8 == 0 (every (x, y) row of the bit stream starts on a byte): reads want z fastest, the
+// occupancy bytes x fastest, so a CTA transposes a tile through shared memory — 32 blocks in x (64 voxel rows) x one block
+// in y (2 voxel rows) x 128 blocks in z (256 voxels = 32 bytes per row): 128 rows of one 32-byte sector in, 128 x 32 bytes out.
+constexpr int BC_BX = 32, BC_BZ = 128, BC_PITCH = 36;
+// second half of the transposing tiles: bit rows [2 * (local voxel x) + dy][byte along z] in shared memory -> the tile's
+// 128 x 32 occupancy bytes, x fastest (32-byte segments)
+__device__ __forceinline__ void emit_tile_from_bit_rows(const uint8_t (*rows)[BC_PITCH], uint8_t* __restrict__ cubes,
+                                                        int bx0, int by, int bz0, int hx, int hy, int hz) {
+#pragma unroll 4
+  for (int k = 0; k < (BC_BX * BC_BZ) / 256; k++) {
+    const int o = threadIdx.x + 256 * k;
+    const int bxl = o % BC_BX, bzl = o / BC_BX;
+    const int bx = bx0 + bxl, bz = bz0 + bzl;
+    if (bx < hx && bz < hz) {
+      const int zbyte = bzl >> 2, sh = 2 * (bzl & 3);
+      uint32_t m = 0;
+#pragma unroll
+      for (int c = 0; c < 4; c++) {                // c = dx + 2 dy  ->  row 2 * (2 bxl + dx) + dy
+        const uint32_t pr = (rows[2 * (2 * bxl + (c & 1)) + (c >> 1)][zbyte] >> sh) & 3u;   // bit 0: dz = 0, bit 1: dz = 1
+        m |= ((pr & 1u) << c) | ((pr >> 1) << (c + 4));
+      }
+      cubes[(size_t)bx + (size_t)hx * ((size_t)by + (size_t)hy * bz)] = (uint8_t)m;
+    }
+  }
+}
+__global__ void __launch_bounds__(256) ingest_bits_c_kernel(const uint8_t* __restrict__ bits, uint8_t* __restrict__ cubes,
+                                                            int sx, int sy, int sz, int hx, int hy, int hz) {
+  __shared__ uint8_t rows[2 * BC_BX * 2][BC_PITCH];   // [2 * (local voxel x) + dy][byte along z]; pitch 36: 2-way bank conflicts at most
+  const int tx = (hx + BC_BX - 1) / BC_BX, tz = (hz + BC_BZ - 1) / BC_BZ;
+  const size_t tiles = (size_t)tx * tz * hy;
+  const size_t rowb = (size_t)sz >> 3;               // bytes per (x, y) row of the bit stream
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int tzi = (int)(tile % tz);
+    const size_t r = tile / tz;
+    const int txi = (int)(r % tx), by = (int)(r / tx);
+    const int bx0 = txi * BC_BX, bz0 = tzi * BC_BZ;
+    // load: row index = 2 * (local voxel x) + dy, 32 bytes each; two threads per row, 16 bytes per thread
+    {
+      const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
+      const int x = 2 * bx0 + (row >> 1), y = 2 * by + (row & 1);
+      const size_t zb0 = (size_t)(2 * bz0) >> 3;     // first byte of the tile along z
+      const bool ok = x < sx && y < sy;
+      const uint8_t* src = bits + rowb * ((size_t)x * sy + y) + zb0 + 16 * half;
+#pragma unroll
+      for (int k = 0; k < 16; k++) {
+        const size_t zb = zb0 + 16 * half + k;
+        rows[row][16 * half + k] = (ok && zb < rowb) ? __ldg(src + k) : (uint8_t)0;
+      }
+    }
+    __syncthreads();
+    emit_tile_from_bit_rows(rows, cubes, bx0, by, bz0, hx, hy, hz);
+    __syncthreads();
+  }
+}
+
+// The same tile for a C-ordered uint8 image in HBM (device tensors are C-ordered), sz % 16 == 0 and a 16-byte aligned
+// base: 128 rows x 256 voxels, sixteen 16-byte streaming loads per row, turned into bit rows on the way into shared memory.
+__global__ void __launch_bounds__(256) ingest_c16_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ cubes,
+                                                         int sx, int sy, int sz, int hx, int hy, int hz) {
+  __shared__ uint8_t rows[2 * BC_BX * 2][BC_PITCH];
+  const int tx = (hx + BC_BX - 1) / BC_BX, tz = (hz + BC_BZ - 1) / BC_BZ;
+  const size_t tiles = (size_t)tx * tz * hy;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int tzi = (int)(tile % tz);
+    const size_t r = tile / tz;
+    const int txi = (int)(r % tx), by = (int)(r / tx);
+    const int bx0 = txi * BC_BX, bz0 = tzi * BC_BZ;
+    uint4 q[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {                    // all eight loads in flight before the first use
+      const int idx = threadIdx.x + 256 * k, row = idx >> 4, seg = idx & 15;
+      const int x = 2 * bx0 + (row >> 1), y = 2 * by + (row & 1), z = 2 * bz0 + 16 * seg;
+      q[k] = (x < sx && y < sy && z < sz) ? __ldcs(reinterpret_cast<const uint4*>(img + ((size_t)x * sy + y) * sz + z)) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int idx = threadIdx.x + 256 * k, row = idx >> 4, seg = idx & 15;
+      const uint32_t w[4] = { q[k].x, q[k].y, q[k].z, q[k].w };
+      uint32_t m16 = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++)                    // four voxel bytes -> four bits (byte j != 0 -> bit j)
+        m16 |= ((((__vcmpne4(w[j], 0u) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * j);
+      *reinterpret_cast<uint16_t*>(&rows[row][2 * seg]) = (uint16_t)m16;
+    }
+    __syncthreads();
+    emit_tile_from_bit_rows(rows, cubes, bx0, by, bz0, hx, hy, hz);
+    __syncthreads();
+  }
+}
+
 // Generic path: any size / memory order, one thread per output byte.
 __global__ void __launch_bounds__(256) ingest_bits_generic_kernel(const uint8_t* __restrict__ bits, uint8_t* __restrict__ cubes,
                                                                   int sx, int sy, int sz, int hx, int hy, int hz,
@@ -960,6 +1080,9 @@ static int launch_ingest(xs3d_volume* v, const uint8_t* d_img, int c_order) {
     const size_t total = nblocks / 8;
     int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
     ingest_f16_kernel<<<grid, 256, 0, v->stream>>>(d_img, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+  } else if (c_order && (v->sz % 16 == 0) && ((uintptr_t)d_img % 16 == 0)) {
+    const size_t tiles = (size_t)((v->hx + BC_BX - 1) / BC_BX) * ((v->hz + BC_BZ - 1) / BC_BZ) * v->hy;
+    ingest_c16_kernel<<<(int)std::min<size_t>(tiles, (size_t)v->sm_count * 32), 256, 0, v->stream>>>(d_img, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
   } else {
     int grid = (int)std::min<size_t>((nblocks + 255) / 256, (size_t)v->sm_count * 32);
     if (c_order)
@@ -973,12 +1096,13 @@ static int launch_ingest(xs3d_volume* v, const uint8_t* d_img, int c_order) {
   return XS3D_OK;
 }
 
-extern "C" int xs_pack_bits(const uint8_t* in, size_t lo, size_t hi, uint8_t* out);   // xs_hostpack.cpp
+extern "C" int xs_pack_bits_parts(const uint8_t* in, size_t lo, size_t hi, uint8_t* out, int nparts,
+                                  void (*done)(void* ctx, size_t lo, size_t hi), void* ctx);   // xs_hostpack.cpp
 
 extern "C" int xs_pack_threads(void);                                                 // xs_hostpack.cpp
 
 // Host image -> occupancy bytes through the bit-packed upload: the host cores pack the image to one bit per voxel
-// (a quarter of it at a time, so that packing and the transfers overlap), 1/8 of the bytes cross PCIe, the device builds
+// (one pool job, its parts sent as they complete, so that packing and the transfers overlap), 1/8 of the bytes cross PCIe, the device builds
 // the occupancy bytes from the bits.  Worth it from a few MiB up, and only with enough host threads to out-run the link
 // (measured on a B200 box: 8 threads pack 94 GB/s, 14 threads 130 GB/s; the link carries 54 GB/s); otherwise the image goes up as it is.
 // XS3D_NO_PACK=1 / XS3D_FORCE_PACK=1 override.
@@ -990,6 +1114,23 @@ static bool use_packed_upload(size_t voxels) {
   if (off || voxels < PACK_MIN_VOXELS) return false;
   return force || xs_pack_threads() >= PACK_MIN_THREADS;
 }
+// dev aid: XS3D_TRACE=1 prints host-side timestamps (microseconds) of the upload / launch / wait phases to stderr
+static void trace(const xs3d_volume* v, const char* tag) {
+  static const bool on = getenv("XS3D_TRACE") != nullptr;
+  if (!on) return;
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  fprintf(stderr, "xs3d-trace %p %s %.1f\n", (const void*)v, tag, ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3);
+}
+
+struct PackUpload { xs3d_volume* v; uint8_t* d_bits; cudaError_t err; };
+// a part of the bit stream is ready on the host: send it (runs on the thread that called xs_pack_bits_parts)
+static void pack_part_ready(void* ctx, size_t lo, size_t hi) {
+  PackUpload* u = (PackUpload*)ctx;
+  if (u->err != cudaSuccess) return;
+  u->err = cudaMemcpyAsync(u->d_bits + lo / 8, u->v->h_bits + lo / 8, (hi - lo + 7) / 8, cudaMemcpyHostToDevice, u->v->stream);
+}
+
 static int upload_packed_and_ingest(xs3d_volume* v, const uint8_t* binimg, int c_order) {
   const size_t voxels = (size_t)v->sx * v->sy * v->sz;
   const size_t nbytes = (voxels + 7) / 8;
@@ -1001,21 +1142,29 @@ static int upload_packed_and_ingest(xs3d_volume* v, const uint8_t* binimg, int c
   }
   RET(v->raw.ensure(nbytes + 4096));
   uint8_t* d_bits = (uint8_t*)v->raw.p;
-  const size_t chunk = ((voxels / 4 + 63) / 64) * 64;
-  for (size_t lo = 0; lo < voxels; lo += chunk) {
-    const size_t hi = std::min(voxels, lo + chunk);
-    xs_pack_bits(binimg, lo, hi, v->h_bits);
-    CK(cudaMemcpyAsync(d_bits + lo / 8, v->h_bits + lo / 8, (hi - lo + 7) / 8, cudaMemcpyHostToDevice, v->stream));
-  }
+  // one job on the host pool, reported in eight parts (256 KiB-grain aligned, hence byte aligned in the bit stream):
+  // each part's copy is enqueued as soon as it is packed, so only the last 2 MiB transfer is exposed
+  trace(v, "pack-begin");
+  PackUpload up{ v, d_bits, cudaSuccess };
+  xs_pack_bits_parts(binimg, 0, voxels, v->h_bits, 8, pack_part_ready, &up);
+  CK(up.err);
+  trace(v, "pack-end");
   CK(cudaEventRecord(v->ev[6], v->stream));
   const size_t nblocks = (size_t)v->hx * v->hy * v->hz;
-  if (!c_order && (v->sx % 16 == 0)) {
+  if (!c_order && (v->sx % 32 == 0)) {
+    const size_t total = nblocks / 16;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
+    ingest_bits_f32_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+  } else if (!c_order && (v->sx % 16 == 0)) {
     const size_t total = nblocks / 8;
     const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
     ingest_bits_f16_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
   } else {
     const int grid = (int)std::min<size_t>((nblocks + 255) / 256, (size_t)v->sm_count * 32);
-    if (c_order)
+    if (c_order && (v->sz % 8 == 0)) {
+      const size_t tiles = (size_t)((v->hx + BC_BX - 1) / BC_BX) * ((v->hz + BC_BZ - 1) / BC_BZ) * v->hy;
+      ingest_bits_c_kernel<<<(int)std::min<size_t>(tiles, (size_t)v->sm_count * 32), 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+    } else if (c_order)
       ingest_bits_generic_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz,
                                                               (long long)v->sy * v->sz, (long long)v->sz, 1ll);
     else
@@ -1326,7 +1475,9 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     if (!single) CK(cudaStreamWaitEvent(s1, v->evf[2], 0));   // join
     CK(cudaEventRecord(v->evb[5], s1));
     CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, s1));
+    trace(v, "launched");
     CK(cudaStreamSynchronize(s1));
+    trace(v, "synced");
     v->timing_pending = single ? 2 : 1;   // event durations are read on demand (xs3d_volume_timing): ten driver calls off the hot path
     v->timing[3] = 0.0f;
     if (v->h_counters[CNT_BADN]) return fail(XS3D_ERR_ARG, "normal vector must not be a null vector (all zeros).");
@@ -1459,6 +1610,7 @@ extern "C" int xs3d_area_sweep_host(xs3d_volume* v, const uint8_t* binimg, int c
   CK(cudaMemcpyAsync(area, v->q_area.p, n * 4, cudaMemcpyDeviceToHost, v->stream));
   CK(cudaMemcpyAsync(contact, v->q_contact.p, n, cudaMemcpyDeviceToHost, v->stream));
   CK(cudaStreamSynchronize(v->stream));
+  trace(v, "results");
   return XS3D_OK;
 }
 

@@ -68,8 +68,11 @@ void pack_range(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
 // by one grain, not by its whole share; the calling thread packs grains too.
 constexpr size_t GRAIN = (size_t)256 << 10;   // a multiple of 64
 
+typedef void (*PartDone)(void* ctx, size_t lo, size_t hi);
+
 class Pool {
  public:
+  static constexpr int MAX_PARTS = 16;
   explicit Pool(int n) : n_(n) {
     for (int i = 0; i < n_ - 1; i++) threads_.emplace_back([this] { loop(); });
   }
@@ -79,26 +82,48 @@ class Pool {
     for (auto& t : threads_) t.join();
   }
   int size() const { return n_; }
-  void run(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
+  // Pack [lo, hi) as ONE job (one wake-up of the workers) reported in `nparts` consecutive parts: as soon as every grain
+  // of the next part is packed, the CALLING thread runs done(ctx, part_lo, part_hi) — the upload enqueues that part's
+  // host-to-device copy there, so the transfers run beside the packing of the rest.
+  void run(const uint8_t* in, size_t lo, size_t hi, uint8_t* out, int nparts, PartDone done, void* ctx) {
+    const size_t grains = (hi - lo + GRAIN - 1) / GRAIN;
+    nparts = (int)std::max<size_t>(1, std::min<size_t>({ (size_t)nparts, (size_t)MAX_PARTS, grains }));
     {
       std::lock_guard<std::mutex> lk(mu_);
-      in_ = in; out_ = out; lo_ = lo; hi_ = hi;
+      in_ = in; out_ = out; lo_ = lo; hi_ = hi; grains_ = grains; nparts_ = nparts;
+      for (int p = 0; p < nparts; p++) left_[p].store(part_begin(p + 1) - part_begin(p), std::memory_order_relaxed);
       next_.store(0, std::memory_order_relaxed);
       pending_ = n_ - 1; gen_++;
     }
     cv_.notify_all();
-    work(in, lo, hi, out);
+    int reported = 0;
+    while (reported < nparts) {
+      if (left_[reported].load(std::memory_order_acquire) == 0) {
+        if (done) done(ctx, lo + GRAIN * part_begin(reported), std::min(hi, lo + GRAIN * part_begin(reported + 1)));
+        reported++;
+      } else if (!work_one(in, lo, hi, out)) {
+        std::this_thread::yield();     // every grain is handed out; the last ones are still being packed
+      }
+    }
     std::unique_lock<std::mutex> lk(mu_);
     done_.wait(lk, [this] { return pending_ == 0; });
   }
 
  private:
-  void work(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
-    for (;;) {
-      const size_t a = lo + GRAIN * next_.fetch_add(1, std::memory_order_relaxed);
-      if (a >= hi) return;
-      pack_range(in, a, std::min(hi, a + GRAIN), out);
-    }
+  size_t part_begin(int p) const { return grains_ * (size_t)p / (size_t)nparts_; }
+  int part_of(size_t g) const {
+    int p = (int)(g * (size_t)nparts_ / grains_);
+    while (p + 1 < nparts_ && part_begin(p + 1) <= g) p++;
+    while (p > 0 && part_begin(p) > g) p--;
+    return p;
+  }
+  bool work_one(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
+    const size_t g = next_.fetch_add(1, std::memory_order_relaxed);
+    if (g >= grains_) return false;
+    const size_t a = lo + GRAIN * g;
+    pack_range(in, a, std::min(hi, a + GRAIN), out);
+    left_[part_of(g)].fetch_sub(1, std::memory_order_release);
+    return true;
   }
   void loop() {
     uint64_t seen = 0;
@@ -111,7 +136,7 @@ class Pool {
         if (stop_) return;
         in = in_; out = out_; lo = lo_; hi = hi_;
       }
-      work(in, lo, hi, out);
+      while (work_one(in, lo, hi, out)) {}
       {
         std::lock_guard<std::mutex> lk(mu_);
         if (--pending_ == 0) done_.notify_all();
@@ -123,8 +148,10 @@ class Pool {
   std::mutex mu_;
   std::condition_variable cv_, done_;
   const uint8_t* in_ = nullptr; uint8_t* out_ = nullptr;
-  size_t lo_ = 0, hi_ = 0;
+  size_t lo_ = 0, hi_ = 0, grains_ = 0;
+  int nparts_ = 1;
   std::atomic<size_t> next_{0};
+  std::atomic<size_t> left_[MAX_PARTS];
   int pending_ = 0;
   uint64_t gen_ = 0;
   bool stop_ = false;
@@ -152,17 +179,27 @@ int pool_threads() {
 
 }  // namespace
 
-// Pack bytes [lo, hi) of `in` (lo a multiple of 64) into the bit stream `out` (bit i <-> byte i != 0).  Thread safe:
-// concurrent callers take turns on the pool.  Returns the number of threads used.
 extern "C" int xs_pack_threads(void);
 
-extern "C" int xs_pack_bits(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
+// Pack bytes [lo, hi) of `in` (lo a multiple of 64) into the bit stream `out` (bit i <-> byte i != 0), reporting progress
+// in `nparts` consecutive parts through done(ctx, part_lo, part_hi), called on the calling thread (may be null).  Thread
+// safe: concurrent callers take turns on the pool.  Returns the number of threads used.
+extern "C" int xs_pack_bits_parts(const uint8_t* in, size_t lo, size_t hi, uint8_t* out, int nparts,
+                                  void (*done)(void* ctx, size_t lo, size_t hi), void* ctx) {
   if (hi <= lo) return 0;
-  if (hi - lo < (1u << 20)) { pack_range(in, lo, hi, out); return 1; }
+  if (hi - lo < (1u << 20)) {
+    pack_range(in, lo, hi, out);
+    if (done) done(ctx, lo, hi);
+    return 1;
+  }
   std::lock_guard<std::mutex> lk(g_pool_mu);
   if (!g_pool) g_pool = new Pool(xs_pack_threads());
-  g_pool->run(in, lo, hi, out);
+  g_pool->run(in, lo, hi, out, nparts, done, ctx);
   return g_pool->size();
+}
+
+extern "C" int xs_pack_bits(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
+  return xs_pack_bits_parts(in, lo, hi, out, 1, nullptr, nullptr);
 }
 
 // Threads xs_pack_bits would use (decides whether the packed upload is worth it: xs_device.cu, use_packed_upload).

@@ -138,6 +138,15 @@ class Volume:
   def __exit__(self, *a):
     self.close()
 
+  def _order_after_producers(self, tensor):
+    """The library launches on its own (non-blocking) stream unless set_stream() handed it torch's: wait for whatever
+    produced a CUDA tensor on torch's current stream (e.g. the .contiguous() copy) before its pointer is read."""
+    if tensor.is_cuda:
+      import torch
+      cur = torch.cuda.current_stream(tensor.device)
+      if getattr(self, "_stream", None) != cur.cuda_stream:
+        cur.synchronize()
+
   # -- loading
   def load(self, binimg):
     if tuple(int(s) for s in binimg.shape) != self.shape:
@@ -149,6 +158,7 @@ class Volume:
       if not binimg.is_contiguous():
         binimg = binimg.contiguous()
       mem = DEVICE if binimg.is_cuda else HOST
+      self._order_after_producers(binimg)
       _abi.check(self._lib.xs3d_volume_load(self._h, binimg.data_ptr(), mem, 1))
       return
     if binimg.dtype != bool and binimg.dtype != np.uint8:
@@ -163,6 +173,7 @@ class Volume:
       if not labels.is_contiguous():
         labels = labels.contiguous()
       mem = DEVICE if labels.is_cuda else HOST
+      self._order_after_producers(labels)
       _abi.check(self._lib.xs3d_volume_load_labels(self._h, labels.data_ptr(), labels.element_size(), mem, 1))
       self._label_dtype = None
       return

@@ -135,3 +135,27 @@ def test_host_bit_packing_matches_numpy():
     for lo in range(0, n, max(chunk, 64)):
       lib.xs_pack_bits(img.ctypes.data, lo, min(n, lo + max(chunk, 64)), out2.ctypes.data)
     assert np.array_equal(out2[: len(exp)], exp), n
+
+
+def test_host_bit_packing_reports_parts_in_order():
+  """xs_pack_bits_parts: one pooled job whose parts are reported in order on the calling thread, each one complete
+  (and byte aligned in the bit stream) when its callback runs — the upload enqueues the part's copy there."""
+  from xs3d import _abi
+  lib = C.CDLL(_abi.LIB_PATH)
+  CB = C.CFUNCTYPE(None, C.c_void_p, C.c_size_t, C.c_size_t)
+  lib.xs_pack_bits_parts.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_int, CB, C.c_void_p]
+  lib.xs_pack_bits_parts.restype = C.c_int
+  rng = np.random.default_rng(6)
+  for n, parts in (((5 << 20) + 77, 8), (3 << 20, 3), (1000, 8), ((2 << 20) + 1, 64)):
+    img = (rng.random(n) < 0.5).astype(np.uint8)
+    exp = np.packbits(img, bitorder="little")
+    out = np.zeros((n + 7) // 8, np.uint8)
+    seen = []
+
+    def done(ctx, lo, hi):
+      assert lo % 8 == 0 and np.array_equal(out[lo // 8:(hi + 7) // 8], exp[lo // 8:(hi + 7) // 8])
+      seen.append((lo, hi))
+
+    assert lib.xs_pack_bits_parts(img.ctypes.data, 0, n, out.ctypes.data, parts, CB(done), None) >= 1
+    assert seen[0][0] == 0 and seen[-1][1] == n and all(a[1] == b[0] for a, b in zip(seen, seen[1:])), seen
+    assert 1 <= len(seen) <= min(parts, 16) and np.array_equal(out, exp)

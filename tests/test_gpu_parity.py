@@ -59,17 +59,24 @@ def test_ingest_matches_numpy(xs):
 
 def test_bit_packed_upload_matches_numpy(xs):
   """Host images of >= 8 Mi voxels go up bit-packed (xs_pack_bits on the host cores, ingest_bits_* kernels on the
-  device): same occupancy bytes as the plain upload, for the aligned Fortran fast path, odd sizes and C order, and
-  the same areas as the device-resident plain path."""
+  device): same occupancy bytes as the plain upload, for the aligned Fortran fast path, odd sizes and C order, from
+  pageable and from page-locked memory, and as the device-resident plain path."""
   import torch
   rng = np.random.default_rng(7)
-  for shape in [(256, 256, 128), (272, 190, 171), (203, 211, 197), (2048, 64, 65)]:
+  for shape in [(256, 256, 128), (272, 190, 171), (203, 211, 197), (2048, 64, 65), (131, 201, 336)]:
     vol = rng.random(shape) < 0.35
     assert vol.size >= (8 << 20)
     exp = _cubes_numpy(vol)
     for order in ("F", "C"):
       v = np.asfortranarray(vol) if order == "F" else np.ascontiguousarray(vol)
       assert np.array_equal(_cubes_of(xs, v), exp), (shape, order)
+      # page-locked source
+      rt = torch.cuda.cudart()
+      assert int(rt.cudaHostRegister(v.ctypes.data, v.nbytes, 0)) == 0
+      try:
+        assert np.array_equal(_cubes_of(xs, v), exp), (shape, order, "pinned")
+      finally:
+        rt.cudaHostUnregister(v.ctypes.data)
       # the plain (unpacked) path: the same image handed over as a device tensor
       assert np.array_equal(_cubes_of(xs, torch.from_numpy(v.view(np.uint8)).cuda().view(torch.bool)), exp), (shape, order)
 
