@@ -185,31 +185,37 @@ __global__ void __launch_bounds__(256) ingest_bits_f32_kernel(const uint8_t* __r
 // C order (z fastest), sz % 8 == 0 (every (x, y) row of the bit stream starts on a byte): reads want z fastest, the
 // occupancy bytes x fastest, so a CTA transposes a tile through shared memory — 32 blocks in x (64 voxel rows) x one block
 // in y (2 voxel rows) x 128 blocks in z (256 voxels = 32 bytes per row): 128 rows of one 32-byte sector in, 128 x 32 bytes out.
-constexpr int BC_BX = 32, BC_BZ = 128, BC_PITCH = 36;
+constexpr int BC_BX = 32, BC_BZ = 128, BC_PITCH = 33;   // odd pitch: the emit pass reads rows 4 apart per lane, conflict free
 // second half of the transposing tiles: bit rows [2 * (local voxel x) + dy][byte along z] in shared memory -> the tile's
-// 128 x 32 occupancy bytes, x fastest (32-byte segments)
+// 128 x 32 occupancy bytes, x fastest (32-byte segments).  One work item = one block column bxl and one byte along z
+// (four blocks in z): four shared-memory bytes in, four occupancy bytes out.
+__device__ __forceinline__ uint32_t gather_low_bits(uint32_t t) {   // bit 0 of byte c -> bit c
+  return (((t & 0x01010101u) * 0x01020408u) >> 24) & 0xfu;
+}
 __device__ __forceinline__ void emit_tile_from_bit_rows(const uint8_t (*rows)[BC_PITCH], uint8_t* __restrict__ cubes,
                                                         int bx0, int by, int bz0, int hx, int hy, int hz) {
-#pragma unroll 4
-  for (int k = 0; k < (BC_BX * BC_BZ) / 256; k++) {
-    const int o = threadIdx.x + 256 * k;
-    const int bxl = o % BC_BX, bzl = o / BC_BX;
-    const int bx = bx0 + bxl, bz = bz0 + bzl;
-    if (bx < hx && bz < hz) {
-      const int zbyte = bzl >> 2, sh = 2 * (bzl & 3);
-      uint32_t m = 0;
 #pragma unroll
-      for (int c = 0; c < 4; c++) {                // c = dx + 2 dy  ->  row 2 * (2 bxl + dx) + dy
-        const uint32_t pr = (rows[2 * (2 * bxl + (c & 1)) + (c >> 1)][zbyte] >> sh) & 3u;   // bit 0: dz = 0, bit 1: dz = 1
-        m |= ((pr & 1u) << c) | ((pr >> 1) << (c + 4));
+  for (int k = 0; k < (BC_BX * BC_BZ / 4) / 256; k++) {
+    const int o = threadIdx.x + 256 * k;
+    const int bxl = o % BC_BX, zb = o / BC_BX;
+    const int bx = bx0 + bxl;
+    // byte c = dx + 2 dy of R: the row of voxel column (2 bxl + dx, dy)
+    const uint32_t R = (uint32_t)rows[4 * bxl][zb] | ((uint32_t)rows[4 * bxl + 2][zb] << 8) |
+                       ((uint32_t)rows[4 * bxl + 1][zb] << 16) | ((uint32_t)rows[4 * bxl + 3][zb] << 24);
+    if (bx < hx) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const int bz = bz0 + 4 * zb + i;
+        const uint32_t t = R >> (2 * i);             // per byte: bit 0 = voxel dz 0, bit 1 = voxel dz 1
+        const uint32_t m = gather_low_bits(t) | (gather_low_bits(t >> 1) << 4);
+        if (bz < hz) cubes[(size_t)bx + (size_t)hx * ((size_t)by + (size_t)hy * bz)] = (uint8_t)m;
       }
-      cubes[(size_t)bx + (size_t)hx * ((size_t)by + (size_t)hy * bz)] = (uint8_t)m;
     }
   }
 }
 __global__ void __launch_bounds__(256) ingest_bits_c_kernel(const uint8_t* __restrict__ bits, uint8_t* __restrict__ cubes,
                                                             int sx, int sy, int sz, int hx, int hy, int hz) {
-  __shared__ uint8_t rows[2 * BC_BX * 2][BC_PITCH];   // [2 * (local voxel x) + dy][byte along z]; pitch 36: 2-way bank conflicts at most
+  __shared__ uint8_t rows[2 * BC_BX * 2][BC_PITCH];   // [2 * (local voxel x) + dy][byte along z]
   const int tx = (hx + BC_BX - 1) / BC_BX, tz = (hz + BC_BZ - 1) / BC_BZ;
   const size_t tiles = (size_t)tx * tz * hy;
   const size_t rowb = (size_t)sz >> 3;               // bytes per (x, y) row of the bit stream
@@ -218,17 +224,23 @@ __global__ void __launch_bounds__(256) ingest_bits_c_kernel(const uint8_t* __res
     const size_t r = tile / tz;
     const int txi = (int)(r % tx), by = (int)(r / tx);
     const int bx0 = txi * BC_BX, bz0 = tzi * BC_BZ;
-    // load: row index = 2 * (local voxel x) + dy, 32 bytes each; two threads per row, 16 bytes per thread
+    // load: row index = 2 * (local voxel x) + dy, 32 bytes each; two threads per row, 16 bytes per thread (four 4-byte
+    // loads when the rows are word aligned)
     {
       const int row = threadIdx.x >> 1, half = threadIdx.x & 1;
       const int x = 2 * bx0 + (row >> 1), y = 2 * by + (row & 1);
       const size_t zb0 = (size_t)(2 * bz0) >> 3;     // first byte of the tile along z
       const bool ok = x < sx && y < sy;
       const uint8_t* src = bits + rowb * ((size_t)x * sy + y) + zb0 + 16 * half;
+      if ((rowb & 3) == 0) {
+        uint32_t w[4];
 #pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const size_t zb = zb0 + 16 * half + k;
-        rows[row][16 * half + k] = (ok && zb < rowb) ? __ldg(src + k) : (uint8_t)0;
+        for (int k = 0; k < 4; k++) w[k] = (ok && zb0 + 16 * half + 4 * k < rowb) ? __ldg(reinterpret_cast<const uint32_t*>(src) + k) : 0u;
+#pragma unroll
+        for (int k = 0; k < 16; k++) rows[row][16 * half + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; k++) rows[row][16 * half + k] = (ok && zb0 + 16 * half + k < rowb) ? __ldg(src + k) : (uint8_t)0;
       }
     }
     __syncthreads();
@@ -264,7 +276,8 @@ __global__ void __launch_bounds__(256) ingest_c16_kernel(const uint8_t* __restri
 #pragma unroll
       for (int j = 0; j < 4; j++)                    // four voxel bytes -> four bits (byte j != 0 -> bit j)
         m16 |= ((((__vcmpne4(w[j], 0u) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * j);
-      *reinterpret_cast<uint16_t*>(&rows[row][2 * seg]) = (uint16_t)m16;
+      rows[row][2 * seg] = (uint8_t)m16;
+      rows[row][2 * seg + 1] = (uint8_t)(m16 >> 8);
     }
     __syncthreads();
     emit_tile_from_bit_rows(rows, cubes, bx0, by, bz0, hx, hy, hz);
