@@ -149,6 +149,9 @@ def run_own_arm(args):
   local = int(os.environ.get("LOCAL_RANK", "0"))
   if not torch.cuda.is_available():
     raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+  if world > 1 and rank == 0:
+    # N > 1: rank 0 alone packs the (single) host volume, so it may use the host cores the other ranks leave idle
+    os.environ.setdefault("XS3D_HOST_THREADS", str(max(4, min(16, (os.cpu_count() or 8) - 2 * world))))
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
   if world > 1:
@@ -258,40 +261,79 @@ def run_own_arm(args):
   del dvol
   ms_e2e_res = time_steps(step_e2e_resident)
 
-  # ---- the same end-to-end step, pipelined across sweeps: two resident-volume handles on their own streams,
-  #      driven by two host threads, so the upload of sweep k+1 overlaps the kernels of sweep k.  Every step
-  #      still uploads its own volume + queries from pinned host memory and reads its results back.
   import threading as _th
-  V2 = [xs3d.Volume(shape=vol.shape, device=local) for _ in range(2)]
-  outs = [(torch.empty(QUERIES, dtype=torch.float32).pin_memory(), torch.empty(QUERIES, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+  psteps = max(2, args.steps)
+  if world == 1:
+    # ---- the same end-to-end step, pipelined across sweeps: two resident-volume handles on their own streams,
+    #      driven by two host threads, so the upload of sweep k+1 overlaps the kernels of sweep k.  Every step
+    #      still takes its own volume + queries from pinned host memory and reads its results back.
+    V2 = [xs3d.Volume(shape=vol.shape, device=local) for _ in range(2)]
+    outs = [(torch.empty(QUERIES, dtype=torch.float32).pin_memory(), torch.empty(QUERIES, dtype=torch.uint8).pin_memory()) for _ in range(2)]
+    pstreams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    for k in range(2):
+      V2[k].set_stream(pstreams[k].cuda_stream)
 
-  pstreams = [torch.cuda.Stream(device=dev) for _ in range(2)]
-  for k in range(2):
-    V2[k].set_stream(pstreams[k].cuda_stream)
+    def sweep(slot):
+      torch.cuda.set_device(local)
+      with torch.cuda.stream(pstreams[slot]):
+        flush.fill_(slot)                    # L2 eviction before every sweep, on the sweep's own stream (inside the timed region)
+      _abi.check(L.xs3d_area_sweep_host(V2[slot]._h, hvol.data_ptr(), 0, QUERIES, hpos.data_ptr(), hnrm.data_ptr(), _abi.fptr(w),
+                                        outs[slot][0].data_ptr(), outs[slot][1].data_ptr()))
 
-  def sweep(slot):
-    torch.cuda.set_device(local)
-    with torch.cuda.stream(pstreams[slot]):
-      flush.fill_(slot)                    # L2 eviction before every sweep, on the sweep's own stream (inside the timed region)
-    _abi.check(L.xs3d_area_sweep_host(V2[slot]._h, hvol.data_ptr(), 0, QUERIES, hpos.data_ptr(), hnrm.data_ptr(), _abi.fptr(w),
-                                      outs[slot][0].data_ptr(), outs[slot][1].data_ptr()))
+    def run_e2e(nsteps):
+      def worker(slot):
+        for _ in range(slot, nsteps, 2):
+          sweep(slot)
+      ts = [_th.Thread(target=worker, args=(k,)) for k in range(2)]
+      for t in ts:
+        t.start()
+      for t in ts:
+        t.join()
+    e2e_mode = "two sweeps in flight (two Volume handles / streams / host threads): upload of sweep k+1 overlaps the kernels of sweep k"
+  else:
+    # ---- N ranks, ONE volume in host memory: rank 0 bit-packs it on its host cores (a helper thread packs
+    #      the image of step k+1 into the other pinned buffer while step k runs), uploads the 16 MiB and ingests; the
+    #      occupancy bytes are NCCL-broadcast to every rank; every rank sweeps its own 10 000 queries from pinned host
+    #      buffers and reads its results back.  The other ranks' host cores stay idle: the box has one memory system.
+    hb = [torch.empty((vol.size + 7) // 8 + 64, dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else None
+    cptr, cbytes = V.cubes()
+    holder = type("H", (), {})()
+    holder.__cuda_array_interface__ = {"shape": (cbytes,), "typestr": "|u1", "data": (cptr, False), "version": 2}
+    cubes_t = torch.as_tensor(holder, device=dev)
+    outs = None
 
-  def run_pipelined(nsteps):
-    def worker(slot):
-      for _ in range(slot, nsteps, 2):
-        sweep(slot)
-    ts = [_th.Thread(target=worker, args=(k,)) for k in range(2)]
-    for t in ts:
-      t.start()
-    for t in ts:
-      t.join()
+    def run_e2e(nsteps):
+      ready = [_th.Semaphore(0), _th.Semaphore(0)]
+      free = [_th.Semaphore(1), _th.Semaphore(1)]
 
-  run_pipelined(max(4, args.warmup))
+      def producer():
+        for k in range(nsteps):
+          free[k & 1].acquire()
+          _abi.check(L.xs3d_pack_bits(hvol.data_ptr(), vol.size, hb[k & 1].data_ptr()))
+          _abi.check(L.xs3d_volume_stage_packed(V._h, hb[k & 1].data_ptr(), k & 1))     # asynchronous copy on the upload stream
+          ready[k & 1].release()
+      th = None
+      if rank == 0:
+        th = _th.Thread(target=producer)
+        th.start()
+      for k in range(nsteps):
+        flush.fill_(k & 255)                 # L2 eviction before every sweep (inside the timed region)
+        if rank == 0:
+          ready[k & 1].acquire()
+          _abi.check(L.xs3d_volume_commit_staged(V._h, k & 1, 0))
+          free[k & 1].release()
+        dist.broadcast(cubes_t, src=0)
+        step_e2e_resident()
+      if th is not None:
+        th.join()
+    e2e_mode = ("one volume in host memory: rank 0 bit-packs and uploads it (double-buffered: image k+1 is packed and copied beside the sweep of image k) and ingests it, "
+                "the 16 MiB occupancy bytes are NCCL-broadcast, every rank sweeps its own 10 000 host-resident queries and reads its results back")
+
+  run_e2e(max(4, args.warmup))
   barrier()
   s_ev = torch.cuda.Event(enable_timing=True); e_ev = torch.cuda.Event(enable_timing=True)
-  psteps = max(2, args.steps)
   s_ev.record()
-  run_pipelined(psteps)
+  run_e2e(psteps)
   torch.cuda.synchronize()
   e_ev.record()
   torch.cuda.synchronize()
@@ -301,13 +343,14 @@ def run_own_arm(args):
     tt = torch.tensor([ms_pipe], dtype=torch.float64, device=dev)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_pipe = float(tt.item())
-  assert np.array_equal(outs[0][0].numpy().view(np.uint32), harea.numpy().view(np.uint32)) and np.array_equal(outs[1][1].numpy(), hct.numpy())
-  for vv in V2:
-    vv.close()
+  if world == 1:
+    assert np.array_equal(outs[0][0].numpy().view(np.uint32), harea.numpy().view(np.uint32)) and np.array_equal(outs[1][1].numpy(), hct.numpy())
+    for vv in V2:
+      vv.close()
   L.xs_pack_threads.restype = C.c_int
   pack_threads = int(L.xs_pack_threads())
   packed = pack_threads >= 6 and not os.environ.get("XS3D_NO_PACK")     # use_packed_upload(), xs_device.cu
-  h2d_volume = (vol.size + 7) // 8 if packed else vol.size
+  h2d_volume = (vol.size + 7) // 8 if (packed or world > 1) else vol.size
   e2e_serial_value = world * QUERIES * args.steps / (ms_e2e / 1000.0)
   e2e_value = world * QUERIES * psteps / (ms_pipe / 1000.0)
   e2e_res_value = world * QUERIES * args.steps / (ms_e2e_res / 1000.0)
@@ -376,14 +419,14 @@ def run_own_arm(args):
     "config": {"workload": WORKLOAD, "volume": [VOLUME_N] * 3, "queries_per_step": QUERIES, "queries_per_rank": QUERIES,
                "anisotropy": list(ANISOTROPY), "l2": "flushed between timed iterations (256 MiB write); in the pipelined e2e loop the write runs on the sweep's stream before every sweep, inside the timed region",
                "parallelism": f"query-sharded x{world}"},
-    "e2e": {"value": e2e_value, "unit": "cross-sections/s", "h2d_bytes_per_step": int(h2d_volume + 2 * pos.nbytes),
-            "d2h_bytes_per_step": int(QUERIES * 5), "ms_per_step": ms_pipe / psteps,
-            "host_input_bytes_per_step": int(vol.size + 2 * pos.nbytes),
-            "upload": (f"bit-packed on {pack_threads} host threads (xs_hostpack.cpp): the 128 MiB boolean image is read once by the host cores, 16 MiB cross PCIe"
-                       if packed else "plain bytes (too few host threads for the bit-packed upload)"),
+    "e2e": {"value": e2e_value, "unit": "cross-sections/s", "h2d_bytes_per_step": int(h2d_volume + world * 2 * pos.nbytes),
+            "d2h_bytes_per_step": int(world * QUERIES * 5), "ms_per_step": ms_pipe / psteps,
+            "host_input_bytes_per_step": int(vol.size + world * 2 * pos.nbytes),
+            "upload": (f"bit-packed on {pack_threads} host threads{' of rank 0' if world > 1 else ''} (xs_hostpack.cpp): the 128 MiB boolean image is read once by the host cores, 16 MiB cross PCIe"
+                       if (packed or world > 1) else "plain bytes (too few host threads for the bit-packed upload)"),
             "includes": "every step: 128 MiB volume + queries taken from pinned host memory, upload, ingest, sweep, areas + contacts read back",
-            "mode": "two sweeps in flight (two Volume handles / streams / host threads): upload of sweep k+1 overlaps the kernels of sweep k",
-            "one_sweep_at_a_time": {"value": e2e_serial_value, "ms_per_step": ms_e2e / args.steps},
+            "mode": e2e_mode,
+            ("one_sweep_at_a_time" if world == 1 else "every_rank_uploads_its_own_copy"): {"value": e2e_serial_value, "ms_per_step": ms_e2e / args.steps},
             "volume_resident": {"value": e2e_res_value, "ms_per_step": ms_e2e_res / args.steps, "h2d_bytes_per_step": int(2 * pos.nbytes)}},
     "gpu_launches": int(launches) * world,
     "kernels_ms_per_step": {k: v / args.steps for k, v in kern.items()},

@@ -989,6 +989,9 @@ struct xs3d_volume {
   uint32_t* h_counters = nullptr;   // pinned: CNT_WORDS counters + 8 u64 stats
   uint8_t* h_bits = nullptr;        // pinned staging of the bit-packed image (upload_packed_and_ingest)
   size_t h_bits_cap = 0;
+  DevBuf staged[2];                 // bit-packed images uploaded ahead of their ingest (xs3d_volume_stage_packed)
+  cudaStream_t stage_stream = nullptr;
+  cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   uint64_t stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t tier_stats[2] = {0, 0};   // samples / items handled by the CTA tiers
   uint32_t wide_over = 0;            // queries the wide tier passed on to the big tier
@@ -1065,6 +1068,8 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
   if (v->stream) { cudaStreamSynchronize(v->stream); if (v->own_stream) cudaStreamDestroy(v->stream); }
   if (v->stream2) { cudaStreamSynchronize(v->stream2); cudaStreamDestroy(v->stream2); }
   if (v->stream3) { cudaStreamSynchronize(v->stream3); cudaStreamDestroy(v->stream3); }
+  if (v->stage_stream) { cudaStreamSynchronize(v->stage_stream); cudaStreamDestroy(v->stage_stream); }
+  for (int i = 0; i < 2; i++) { if (v->stage_ev[i]) cudaEventDestroy(v->stage_ev[i]); v->staged[i].release(); }
   for (int i = 0; i < 8; i++) if (v->ev[i]) cudaEventDestroy(v->ev[i]);
   for (int i = 0; i < 4; i++) if (v->evf[i]) cudaEventDestroy(v->evf[i]);
   for (int i = 0; i < 6; i++) if (v->evb[i]) cudaEventDestroy(v->evb[i]);
@@ -1136,6 +1141,36 @@ static void trace(const xs3d_volume* v, const char* tag) {
   fprintf(stderr, "xs3d-trace %p %s %.1f\n", (const void*)v, tag, ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3);
 }
 
+// bit-packed image in device memory -> occupancy bytes (timed by ev[6], ev[7] like the byte ingest)
+static int launch_ingest_bits(xs3d_volume* v, const uint8_t* d_bits, int c_order) {
+  CK(cudaEventRecord(v->ev[6], v->stream));
+  const size_t nblocks = (size_t)v->hx * v->hy * v->hz;
+  const uintptr_t al = (uintptr_t)d_bits;
+  if (!c_order && (v->sx % 32 == 0) && al % 4 == 0) {
+    const size_t total = nblocks / 16;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
+    ingest_bits_f32_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+  } else if (!c_order && (v->sx % 16 == 0) && al % 2 == 0) {
+    const size_t total = nblocks / 8;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
+    ingest_bits_f16_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+  } else if (c_order && (v->sz % 8 == 0) && al % 4 == 0) {
+    const size_t tiles = (size_t)((v->hx + BC_BX - 1) / BC_BX) * ((v->hz + BC_BZ - 1) / BC_BZ) * v->hy;
+    ingest_bits_c_kernel<<<(int)std::min<size_t>(tiles, (size_t)v->sm_count * 32), 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+  } else {
+    const int grid = (int)std::min<size_t>((nblocks + 255) / 256, (size_t)v->sm_count * 32);
+    if (c_order)
+      ingest_bits_generic_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz,
+                                                              (long long)v->sy * v->sz, (long long)v->sz, 1ll);
+    else
+      ingest_bits_generic_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz,
+                                                              1ll, (long long)v->sx, (long long)v->sx * v->sy);
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(v->ev[7], v->stream));
+  return XS3D_OK;
+}
+
 struct PackUpload { xs3d_volume* v; uint8_t* d_bits; cudaError_t err; };
 // a part of the bit stream is ready on the host: send it (runs on the thread that called xs_pack_bits_parts)
 static void pack_part_ready(void* ctx, size_t lo, size_t hi) {
@@ -1162,30 +1197,7 @@ static int upload_packed_and_ingest(xs3d_volume* v, const uint8_t* binimg, int c
   xs_pack_bits_parts(binimg, 0, voxels, v->h_bits, 8, pack_part_ready, &up);
   CK(up.err);
   trace(v, "pack-end");
-  CK(cudaEventRecord(v->ev[6], v->stream));
-  const size_t nblocks = (size_t)v->hx * v->hy * v->hz;
-  if (!c_order && (v->sx % 32 == 0)) {
-    const size_t total = nblocks / 16;
-    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
-    ingest_bits_f32_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
-  } else if (!c_order && (v->sx % 16 == 0)) {
-    const size_t total = nblocks / 8;
-    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
-    ingest_bits_f16_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
-  } else {
-    const int grid = (int)std::min<size_t>((nblocks + 255) / 256, (size_t)v->sm_count * 32);
-    if (c_order && (v->sz % 8 == 0)) {
-      const size_t tiles = (size_t)((v->hx + BC_BX - 1) / BC_BX) * ((v->hz + BC_BZ - 1) / BC_BZ) * v->hy;
-      ingest_bits_c_kernel<<<(int)std::min<size_t>(tiles, (size_t)v->sm_count * 32), 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
-    } else if (c_order)
-      ingest_bits_generic_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz,
-                                                              (long long)v->sy * v->sz, (long long)v->sz, 1ll);
-    else
-      ingest_bits_generic_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz,
-                                                              1ll, (long long)v->sx, (long long)v->sx * v->sy);
-  }
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(v->ev[7], v->stream));
+  RET(launch_ingest_bits(v, d_bits, c_order));
   return XS3D_OK;
 }
 
@@ -1208,6 +1220,71 @@ extern "C" int xs3d_volume_load(xs3d_volume* v, const uint8_t* binimg, int mem, 
     RET(launch_ingest(v, d_img, c_order));
     CK(cudaEventRecord(v->ev[7], v->stream));
   }
+  CK(cudaStreamSynchronize(v->stream));
+  CK(cudaEventElapsedTime(&v->timing[4], v->ev[6], v->ev[7]));
+  v->loaded = true;
+  return XS3D_OK;
+}
+
+// The two halves of the bit-packed upload as separate calls (a pipeline can pack image k+1 on the host while image k is
+// being swept, or hold bit-packed masks in the first place).
+extern "C" int xs3d_pack_bits(const uint8_t* binimg, uint64_t voxels, uint8_t* bits) {
+  if (voxels && (!binimg || !bits)) return fail(XS3D_ERR_ARG, "null argument");
+  xs_pack_bits_parts(binimg, 0, (size_t)voxels, bits, 1, nullptr, nullptr);
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_volume_load_packed(xs3d_volume* v, const uint8_t* bits, int mem, int c_order) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  CK(cudaSetDevice(v->device));
+  const size_t voxels = (size_t)v->sx * v->sy * v->sz;
+  if (voxels == 0) { v->loaded = true; return XS3D_OK; }
+  if (!bits) return fail(XS3D_ERR_ARG, "null image");
+  const uint8_t* d_bits = bits;
+  if (mem == XS3D_HOST) {
+    const size_t nbytes = (voxels + 7) / 8;
+    RET(v->raw.ensure(nbytes + 4096));
+    CK(cudaMemcpyAsync(v->raw.p, bits, nbytes, cudaMemcpyHostToDevice, v->stream));
+    d_bits = (const uint8_t*)v->raw.p;
+  }
+  RET(launch_ingest_bits(v, d_bits, c_order));
+  CK(cudaStreamSynchronize(v->stream));
+  CK(cudaEventElapsedTime(&v->timing[4], v->ev[6], v->ev[7]));
+  v->loaded = true;
+  return XS3D_OK;
+}
+
+// The upload of a bit-packed host image, ahead of its ingest: the copy runs on the volume's own upload stream (so it
+// overlaps whatever the launching stream is doing, e.g. the sweep of the previous image) into one of two staging
+// buffers; xs3d_volume_commit_staged then makes the launching stream wait for that copy and builds the occupancy bytes.
+// stage may be called from another host thread than commit (the caller orders the two calls for a slot).
+extern "C" int xs3d_volume_stage_packed(xs3d_volume* v, const uint8_t* bits, int slot) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (slot < 0 || slot > 1) return fail(XS3D_ERR_ARG, "slot must be 0 or 1");
+  CK(cudaSetDevice(v->device));
+  const size_t voxels = (size_t)v->sx * v->sy * v->sz;
+  if (voxels == 0) return XS3D_OK;
+  if (!bits) return fail(XS3D_ERR_ARG, "null image");
+  if (!v->stage_stream) {
+    CK(cudaStreamCreateWithFlags(&v->stage_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&v->stage_ev[i], cudaEventDisableTiming));
+  }
+  const size_t nbytes = (voxels + 7) / 8;
+  RET(v->staged[slot].ensure(nbytes + 4096));
+  CK(cudaMemcpyAsync(v->staged[slot].p, bits, nbytes, cudaMemcpyHostToDevice, v->stage_stream));
+  CK(cudaEventRecord(v->stage_ev[slot], v->stage_stream));
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_volume_commit_staged(xs3d_volume* v, int slot, int c_order) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (slot < 0 || slot > 1) return fail(XS3D_ERR_ARG, "slot must be 0 or 1");
+  CK(cudaSetDevice(v->device));
+  const size_t voxels = (size_t)v->sx * v->sy * v->sz;
+  if (voxels == 0) { v->loaded = true; return XS3D_OK; }
+  if (!v->stage_stream || !v->staged[slot].p) return fail(XS3D_ERR_ARG, "nothing staged in this slot");
+  CK(cudaStreamWaitEvent(v->stream, v->stage_ev[slot], 0));
+  RET(launch_ingest_bits(v, (const uint8_t*)v->staged[slot].p, c_order));
   CK(cudaStreamSynchronize(v->stream));
   CK(cudaEventElapsedTime(&v->timing[4], v->ev[6], v->ev[7]));
   v->loaded = true;

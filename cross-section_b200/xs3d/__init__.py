@@ -28,7 +28,7 @@ VECTOR_T = Union[tuple, npt.NDArray[np.float32]]
 
 __all__ = [
   "cross_sectional_area", "cross_section", "slice", "set_shape", "clear_shape",
-  "Volume", "SliceBatch", "cross_sectional_area_batch", "skeleton_tangents", "sweep_skeleton", "XS3DError",
+  "Volume", "SliceBatch", "cross_sectional_area_batch", "skeleton_tangents", "sweep_skeleton", "pack_bits", "XS3DError",
 ]
 
 
@@ -165,6 +165,33 @@ class Volume:
       raise ValueError(f"A boolean image is required. Got: {binimg.dtype}")
     a, ptr, c_order = _image_pointer(binimg)
     _abi.check(self._lib.xs3d_volume_load(self._h, ptr, HOST, c_order))
+
+  def load_packed(self, bits, c_order=False):
+    """Ingest a bit-packed image as xs3d.pack_bits() writes it (uint8 ndarray, or a torch uint8 tensor in host or
+    device memory): 1/8 of the bytes of the boolean image cross PCIe.  c_order: the bits follow the C-contiguous
+    voxel order instead of the Fortran one."""
+    nbytes = (int(np.prod(self.shape)) + 7) // 8
+    if _is_torch_tensor(bits):
+      if bits.numel() * bits.element_size() < nbytes or not bits.is_contiguous():
+        raise ValueError("bit stream too short for the volume (or not contiguous)")
+      self._order_after_producers(bits)
+      _abi.check(self._lib.xs3d_volume_load_packed(self._h, bits.data_ptr(), DEVICE if bits.is_cuda else HOST, int(bool(c_order))))
+      return
+    bits = np.ascontiguousarray(bits, dtype=np.uint8)
+    if bits.size < nbytes:
+      raise ValueError("bit stream too short for the volume")
+    _abi.check(self._lib.xs3d_volume_load_packed(self._h, bits.ctypes.data, HOST, int(bool(c_order))))
+
+  def stage_packed(self, bits, slot=0):
+    """Start the upload of a bit-packed HOST image (pinned memory for an asynchronous copy) into staging buffer `slot`
+    (0 or 1) on the volume's upload stream; returns at once.  commit_staged(slot) ingests it."""
+    ptr = bits.data_ptr() if _is_torch_tensor(bits) else bits.ctypes.data
+    _abi.check(self._lib.xs3d_volume_stage_packed(self._h, ptr, int(slot)))
+    self._keep = bits
+
+  def commit_staged(self, slot=0, c_order=False):
+    """Wait (on the device) for the staged upload of `slot` and build the occupancy bytes from it."""
+    _abi.check(self._lib.xs3d_volume_commit_staged(self._h, int(slot), int(bool(c_order))))
 
   def load_labels(self, labels):
     if tuple(int(s) for s in labels.shape) != self.shape:
@@ -369,6 +396,29 @@ def cross_sectional_area_batch(binimg, positions, normals, anisotropy=None, retu
       return vol.cross_sectional_area_batch(positions, normals, anisotropy, return_contact)
   with Volume(shape=binimg.shape, device=device) as vol:
     return vol.sweep(binimg, positions, normals, anisotropy, return_contact)
+
+
+def pack_bits(binimg, out=None):
+  """Boolean image -> one bit per voxel (bit i & 7 of byte i >> 3 <-> voxel i of the image in its own memory order,
+  i.e. np.packbits(binimg.ravel(order="K"), bitorder="little")), packed by the library's host thread pool at memory
+  speed.  Returns (bits, c_order) for Volume.load_packed.  `out`: optional uint8 buffer (e.g. pinned) of
+  (binimg.size + 7) // 8 bytes, ndarray or CPU torch tensor."""
+  if binimg.dtype != bool and binimg.dtype != np.uint8:
+    raise ValueError(f"A boolean image is required. Got: {binimg.dtype}")
+  a, ptr, c_order = _image_pointer(binimg)
+  nbytes = (a.size + 7) // 8
+  if out is None:
+    out = np.empty(nbytes, dtype=np.uint8)
+  if _is_torch_tensor(out):
+    if out.is_cuda or out.numel() * out.element_size() < nbytes or not out.is_contiguous():
+      raise ValueError("out must be a contiguous CPU buffer of (binimg.size + 7) // 8 bytes")
+    optr = out.data_ptr()
+  else:
+    if out.dtype != np.uint8 or out.size < nbytes or not out.flags.c_contiguous:
+      raise ValueError("out must be a contiguous uint8 buffer of (binimg.size + 7) // 8 bytes")
+    optr = out.ctypes.data
+  _abi.check(_abi.lib().xs3d_pack_bits(ptr, a.size, optr))
+  return out, bool(c_order)
 
 
 def skeleton_tangents(vertices, edges):

@@ -46,6 +46,19 @@ int xs3d_volume_destroy(xs3d_volume* vol);
  * c_order != 0: the buffer is C-contiguous [sx][sy][sz] (index z + sz*(y + sy*x)); this replaces the
  * host-side np.asfortranarray copy of xs3d/__init__.py:77. */
 int xs3d_volume_load(xs3d_volume* vol, const uint8_t* binimg, int mem, int c_order);
+/* The two halves of the bit-packed upload as separate calls.  xs3d_pack_bits: boolean image (1 byte per voxel, any
+ * memory order) -> one bit per voxel, bit (i & 7) of byte (i >> 3) <-> byte i != 0, packed by the library's host thread
+ * pool (`bits` holds (voxels + 7) / 8 bytes).  xs3d_volume_load_packed: ingest such a bit stream (host or device memory;
+ * c_order as in xs3d_volume_load).  xs3d_volume_load does both itself for large host images; the split lets a caller
+ * pack image k+1 while image k is being swept, or keep its masks bit-packed (1/8 of the reference's bool arrays). */
+int xs3d_pack_bits(const uint8_t* binimg, uint64_t voxels, uint8_t* bits);
+int xs3d_volume_load_packed(xs3d_volume* vol, const uint8_t* bits, int mem, int c_order);
+/* Upload ahead of the ingest: stage copies a bit-packed HOST image (pinned, for the copy to be asynchronous) into staging
+ * buffer `slot` (0 or 1) on the volume's own upload stream and returns at once; commit makes the launching stream wait for
+ * that copy, builds the occupancy bytes from it and returns when they are ready.  A pipeline stages image k+1 (from any
+ * host thread) while image k is being swept. */
+int xs3d_volume_stage_packed(xs3d_volume* vol, const uint8_t* bits, int slot);
+int xs3d_volume_commit_staged(xs3d_volume* vol, int slot, int c_order);
 /* Attach a label volume for xs3d_projection_v (any 1/2/4/8-byte dtype, C or F order; fastxs3d.cpp:135,199-215). */
 int xs3d_volume_load_labels(xs3d_volume* vol, const void* labels, int itemsize, int mem, int c_order);
 /* Make the resident image "labels == label" (labels attached with xs3d_volume_load_labels): the occupancy bytes

@@ -159,3 +159,21 @@ def test_host_bit_packing_reports_parts_in_order():
     assert lib.xs_pack_bits_parts(img.ctypes.data, 0, n, out.ctypes.data, parts, CB(done), None) >= 1
     assert seen[0][0] == 0 and seen[-1][1] == n and all(a[1] == b[0] for a, b in zip(seen, seen[1:])), seen
     assert 1 <= len(seen) <= min(parts, 16) and np.array_equal(out, exp)
+
+
+def test_pack_bits_host_api():
+  """xs3d.pack_bits (C ABI xs3d_pack_bits): the bit stream of an image in its own memory order, for Volume.load_packed."""
+  import xs3d
+  rng = np.random.default_rng(8)
+  vol = rng.random((37, 41, 53)) < 0.3
+  for arr, order in ((np.asfortranarray(vol), "F"), (np.ascontiguousarray(vol), "C"), (np.asfortranarray(vol).view(np.uint8) * 7, "F")):
+    bits, c_order = xs3d.pack_bits(arr)
+    assert c_order == (order == "C") and bits.dtype == np.uint8
+    assert np.array_equal(bits, np.packbits(arr.ravel(order=order) != 0, bitorder="little"))
+  out = np.zeros((vol.size + 7) // 8 + 3, np.uint8)
+  bits, _ = xs3d.pack_bits(np.asfortranarray(vol), out=out)
+  assert bits is out and np.array_equal(out[:-3], np.packbits(vol.ravel(order="F"), bitorder="little"))
+  with pytest.raises(ValueError):
+    xs3d.pack_bits(vol.astype(np.float32))
+  with pytest.raises(ValueError):
+    xs3d.pack_bits(vol, out=np.zeros(5, np.uint8))

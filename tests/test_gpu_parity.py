@@ -77,6 +77,27 @@ def test_bit_packed_upload_matches_numpy(xs):
         assert np.array_equal(_cubes_of(xs, v), exp), (shape, order, "pinned")
       finally:
         rt.cudaHostUnregister(v.ctypes.data)
+      # the two halves of the packed upload as separate calls: bits from host memory and from device memory
+      pb, c_order = xs.pack_bits(v)
+      assert c_order == (order == "C")
+      for src in (pb, torch.from_numpy(pb).cuda()):
+        with xs.Volume(shape=shape) as V:
+          V.load_packed(src, c_order=c_order)
+          ptr, nbytes = V.cubes()
+          holder = type("H", (), {})()
+          holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+          assert np.array_equal(torch.as_tensor(holder, device="cuda").cpu().numpy(), exp), (shape, order, "load_packed")
+      # upload ahead of the ingest: stage into either slot (from pinned memory), commit later
+      with xs.Volume(shape=shape) as V:
+        pinned = torch.from_numpy(pb).pin_memory()
+        for slot in (0, 1):
+          V.load(np.zeros(shape, bool, order="F"))
+          V.stage_packed(pinned, slot)
+          V.commit_staged(slot, c_order=c_order)
+          ptr, nbytes = V.cubes()
+          holder = type("H", (), {})()
+          holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+          assert np.array_equal(torch.as_tensor(holder, device="cuda").cpu().numpy(), exp), (shape, order, "staged", slot)
       # the plain (unpacked) path: the same image handed over as a device tensor
       assert np.array_equal(_cubes_of(xs, torch.from_numpy(v.view(np.uint8)).cuda().view(torch.bool)), exp), (shape, order)
 

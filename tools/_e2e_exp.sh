@@ -1,3 +1,2 @@
-python -m pytest tests -m gpu -x -q -k "ingest or packed or sweep or random_vs" 2>&1 | tail -2
-python tools/gpu_ingest.py > gpurun_out/ingest_r1j.log 2>&1; cat gpurun_out/ingest_r1j.log
-ncu --set full --clock-control none --import-source on -k regex:ingest -c 12 -o gpurun_out/prof_r1j_ingest -f python tools/gpu_ingest.py > gpurun_out/ncu_r1j_ingest.log 2>&1
+python -m pytest tests -m gpu -x -q -k "packed" 2>&1 | tail -2
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_r1j_n2.log 2>&1; tail -c 800 gpurun_out/bench_r1j_n2.log
