@@ -8,8 +8,10 @@ queries of the skeleton sweep against the 512^3 neurite volume.
   value : whole-job throughput with inputs resident in HBM (volume ingested, queries and results on the
           device), timed with CUDA events on the launching stream, L2 flushed between steps, max over ranks.
   e2e   : the same sweep through the C ABI with HOST buffers: every step takes the 128 MiB boolean volume and the
-          queries from pinned host memory (the library bit-packs the volume on the host cores, so 16 MiB cross
-          PCIe), ingests, runs, and reads areas + contact bits back.
+          queries from pinned host memory (xs3d_pack_bits packs the volume on the host cores, 16 MiB cross PCIe;
+          the packing + upload of step k+1 run beside the sweep of step k), ingests, sweeps, and reads areas +
+          contact bits back.  N > 1: ONE host volume — rank 0 packs / uploads / ingests, the occupancy bytes are
+          NCCL-broadcast every step, every rank sweeps its own queries.
   roofline     : the dominant kernel (warp-tier query kernel), algorithmic bytes / CUDA-event duration vs the
                  measured HBM peak (MEASURED_PEAKS.json).  The mid / big tiers run beside it on a second stream.
   cpu_baseline : the compiled reference (oracle/_ref, else the C port) fanned out over all host cores.
@@ -149,9 +151,10 @@ def run_own_arm(args):
   local = int(os.environ.get("LOCAL_RANK", "0"))
   if not torch.cuda.is_available():
     raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
-  if world > 1 and rank == 0:
-    # N > 1: rank 0 alone packs the (single) host volume, so it may use the host cores the other ranks leave idle
-    os.environ.setdefault("XS3D_HOST_THREADS", str(max(4, min(16, (os.cpu_count() or 8) - 2 * world))))
+  if rank == 0 and not os.environ.get("XS_BENCH_TWO_HANDLES"):
+    # the e2e loop packs the (single) host volume on rank 0: all host cores but one per rank (each rank's main thread
+    # spins on its GPU); the packing thread itself is one of the pool's workers
+    os.environ.setdefault("XS3D_HOST_THREADS", str(max(4, min(16, (os.cpu_count() or 8) - world))))
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
   if world > 1:
@@ -263,7 +266,8 @@ def run_own_arm(args):
 
   import threading as _th
   psteps = max(2, args.steps)
-  if world == 1:
+  staged_mode = world > 1 or not os.environ.get("XS_BENCH_TWO_HANDLES")
+  if not staged_mode:
     # ---- the same end-to-end step, pipelined across sweeps: two resident-volume handles on their own streams,
     #      driven by two host threads, so the upload of sweep k+1 overlaps the kernels of sweep k.  Every step
     #      still takes its own volume + queries from pinned host memory and reads its results back.
@@ -291,10 +295,11 @@ def run_own_arm(args):
         t.join()
     e2e_mode = "two sweeps in flight (two Volume handles / streams / host threads): upload of sweep k+1 overlaps the kernels of sweep k"
   else:
-    # ---- N ranks, ONE volume in host memory: rank 0 bit-packs it on its host cores (a helper thread packs
-    #      the image of step k+1 into the other pinned buffer while step k runs), uploads the 16 MiB and ingests; the
-    #      occupancy bytes are NCCL-broadcast to every rank; every rank sweeps its own 10 000 queries from pinned host
-    #      buffers and reads its results back.  The other ranks' host cores stay idle: the box has one memory system.
+    # ---- N ranks, ONE volume in host memory: every step, rank 0 bit-packs it on its host cores and starts
+    #      its upload (a helper thread does both for the image of step k+1, into the other pinned / staging buffer, while
+    #      step k runs) and ingests it; for N > 1 the occupancy bytes are NCCL-broadcast to every rank; every rank sweeps
+    #      its own 10 000 queries from pinned host buffers and reads its results back.  The other ranks' host cores stay
+    #      idle: the box has one memory system, which the packing saturates.
     hb = [torch.empty((vol.size + 7) // 8 + 64, dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else None
     cptr, cbytes = V.cubes()
     holder = type("H", (), {})()
@@ -322,12 +327,13 @@ def run_own_arm(args):
           ready[k & 1].acquire()
           _abi.check(L.xs3d_volume_commit_staged(V._h, k & 1, 0))
           free[k & 1].release()
-        dist.broadcast(cubes_t, src=0)
+        if world > 1:
+          dist.broadcast(cubes_t, src=0)
         step_e2e_resident()
       if th is not None:
         th.join()
-    e2e_mode = ("one volume in host memory: rank 0 bit-packs and uploads it (double-buffered: image k+1 is packed and copied beside the sweep of image k) and ingests it, "
-                "the 16 MiB occupancy bytes are NCCL-broadcast, every rank sweeps its own 10 000 host-resident queries and reads its results back")
+    e2e_mode = ("one volume in host memory, taken afresh every step: rank 0 bit-packs and uploads it (double-buffered: image k+1 is packed and copied beside the sweep of image k) and ingests it, "
+                + ("the 16 MiB occupancy bytes are NCCL-broadcast, " if world > 1 else "") + "every rank sweeps its own 10 000 host-resident queries and reads its results back")
 
   run_e2e(max(4, args.warmup))
   barrier()
@@ -343,14 +349,14 @@ def run_own_arm(args):
     tt = torch.tensor([ms_pipe], dtype=torch.float64, device=dev)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_pipe = float(tt.item())
-  if world == 1:
+  if not staged_mode:
     assert np.array_equal(outs[0][0].numpy().view(np.uint32), harea.numpy().view(np.uint32)) and np.array_equal(outs[1][1].numpy(), hct.numpy())
     for vv in V2:
       vv.close()
   L.xs_pack_threads.restype = C.c_int
   pack_threads = int(L.xs_pack_threads())
   packed = pack_threads >= 6 and not os.environ.get("XS3D_NO_PACK")     # use_packed_upload(), xs_device.cu
-  h2d_volume = (vol.size + 7) // 8 if (packed or world > 1) else vol.size
+  h2d_volume = (vol.size + 7) // 8 if (packed or staged_mode) else vol.size
   e2e_serial_value = world * QUERIES * args.steps / (ms_e2e / 1000.0)
   e2e_value = world * QUERIES * psteps / (ms_pipe / 1000.0)
   e2e_res_value = world * QUERIES * args.steps / (ms_e2e_res / 1000.0)
@@ -423,7 +429,7 @@ def run_own_arm(args):
             "d2h_bytes_per_step": int(world * QUERIES * 5), "ms_per_step": ms_pipe / psteps,
             "host_input_bytes_per_step": int(vol.size + world * 2 * pos.nbytes),
             "upload": (f"bit-packed on {pack_threads} host threads{' of rank 0' if world > 1 else ''} (xs_hostpack.cpp): the 128 MiB boolean image is read once by the host cores, 16 MiB cross PCIe"
-                       if (packed or world > 1) else "plain bytes (too few host threads for the bit-packed upload)"),
+                       if (packed or staged_mode) else "plain bytes (too few host threads for the bit-packed upload)"),
             "includes": "every step: 128 MiB volume + queries taken from pinned host memory, upload, ingest, sweep, areas + contacts read back",
             "mode": e2e_mode,
             ("one_sweep_at_a_time" if world == 1 else "every_rank_uploads_its_own_copy"): {"value": e2e_serial_value, "ms_per_step": ms_e2e / args.steps},
