@@ -300,38 +300,13 @@ def run_own_arm(args):
     #      step k runs) and ingests it; for N > 1 the occupancy bytes are NCCL-broadcast to every rank; every rank sweeps
     #      its own 10 000 queries from pinned host buffers and reads its results back.  The other ranks' host cores stay
     #      idle: the box has one memory system, which the packing saturates.
-    hb = [torch.empty((vol.size + 7) // 8 + 64, dtype=torch.uint8).pin_memory() for _ in range(2)] if rank == 0 else None
-    cptr, cbytes = V.cubes()
-    holder = type("H", (), {})()
-    holder.__cuda_array_interface__ = {"shape": (cbytes,), "typestr": "|u1", "data": (cptr, False), "version": 2}
-    cubes_t = torch.as_tensor(holder, device=dev)
+    feed = xdist.VolumeFeed(V)               # two pinned bit buffers + the volume's staging buffers, reused by every call
     outs = None
 
     def run_e2e(nsteps):
-      ready = [_th.Semaphore(0), _th.Semaphore(0)]
-      free = [_th.Semaphore(1), _th.Semaphore(1)]
-
-      def producer():
-        for k in range(nsteps):
-          free[k & 1].acquire()
-          _abi.check(L.xs3d_pack_bits(hvol.data_ptr(), vol.size, hb[k & 1].data_ptr()))
-          _abi.check(L.xs3d_volume_stage_packed(V._h, hb[k & 1].data_ptr(), k & 1))     # asynchronous copy on the upload stream
-          ready[k & 1].release()
-      th = None
-      if rank == 0:
-        th = _th.Thread(target=producer)
-        th.start()
-      for k in range(nsteps):
-        flush.fill_(k & 255)                 # L2 eviction before every sweep (inside the timed region)
-        if rank == 0:
-          ready[k & 1].acquire()
-          _abi.check(L.xs3d_volume_commit_staged(V._h, k & 1, 0))
-          free[k & 1].release()
-        if world > 1:
-          dist.broadcast(cubes_t, src=0)
-        step_e2e_resident()
-      if th is not None:
-        th.join()
+      xdist.stream_volumes(V, [vol] * nsteps if rank == 0 else None, nsteps, lambda k: step_e2e_resident(),
+                           before_step=lambda k: flush.fill_(k & 255),      # L2 eviction before every sweep (inside the timed region)
+                           feed=feed)
     e2e_mode = ("one volume in host memory, taken afresh every step: rank 0 bit-packs and uploads it (double-buffered: image k+1 is packed and copied beside the sweep of image k) and ingests it, "
                 + ("the 16 MiB occupancy bytes are NCCL-broadcast, " if world > 1 else "") + "every rank sweeps its own 10 000 host-resident queries and reads its results back")
 

@@ -7,7 +7,10 @@ query list.  torch.distributed is used only as plumbing:
   * broadcast_volume(): rank `src` ingests the image, the 2x2x2 occupancy bytes (V/8 bytes, e.g.
     16 MiB for 512^3) are broadcast once over NCCL/NVLink into every rank's resident Volume;
   * shard_bounds() / gather_results(): contiguous partition of n queries and the (small: 5 B/query)
-    all-gather of areas and contact bits.
+    all-gather of areas and contact bits;
+  * stream_volumes(): a sequence of host volumes through the ranks' resident Volumes — rank `src` bit-packs and
+    uploads volume k+1 on a helper thread while everybody sweeps volume k; the occupancy bytes are broadcast
+    every step (the end-to-end loop of bench.py).
 
 The same code runs on the gloo backend with CPU tensors (tests/test_dist_gloo.py), where the
 per-rank compute function is injected by the test.
@@ -91,3 +94,96 @@ def sharded_area_batch(compute, positions, normals, group=None, gather=True):
     out_a[rlo:rhi] = p[: 4 * rk].view(np.float32)
     out_c[rlo:rhi] = p[4 * kmax: 4 * kmax + rk]
   return out_a, out_c, (lo, hi)
+
+
+class VolumeFeed:
+  """What stream_volumes does to a real (CUDA) Volume: pack into one of two pinned buffers with the library's host
+  thread pool + start the upload on the volume's upload stream; later ingest the staged bits."""
+
+  def __init__(self, volume):
+    import torch
+    nbytes = (int(np.prod(volume.shape)) + 7) // 8 + 64
+    self.volume = volume
+    self.bufs = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+  def pack_and_stage(self, image, slot):
+    from . import pack_bits
+    _, c_order = pack_bits(image, out=self.bufs[slot])
+    self.volume.stage_packed(self.bufs[slot], slot)
+    return c_order
+
+  def commit(self, slot, c_order):
+    self.volume.commit_staged(slot, c_order)
+
+  def cubes_tensor(self):
+    import torch
+    ptr, nbytes = self.volume.cubes()
+    holder = type("_Holder", (), {})()
+    holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(holder, device=torch.device("cuda", self.volume.device))
+
+  def mark_loaded(self):
+    self.volume.mark_loaded()
+
+
+def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_step=None, feed=None):
+  """Run `sweep(k)` for k = 0 .. n_steps-1 with `volume` holding images[k] (only rank `src` passes `images`; the others
+  may pass None).  Rank `src` packs + uploads image k+1 on a helper thread (double-buffered) while step k runs; per
+  step the staged bits are ingested on `src`, the occupancy bytes are broadcast when there is more than one rank, and
+  every rank calls sweep(k) — normally its own shard of the queries against `volume`.  Returns the list of sweep
+  results.  `before_step(k)` runs at the top of each step (bench.py evicts L2 there); `feed`: a VolumeFeed(volume) to
+  reuse its pinned buffers across calls, or a stand-in for the CUDA plumbing (tests run this loop on the gloo backend)."""
+  import threading
+  import torch.distributed as dist
+  multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+  rank = dist.get_rank(group) if multi else src
+  feed = feed if feed is not None else VolumeFeed(volume)
+  is_src = rank == src
+  ready = [threading.Semaphore(0), threading.Semaphore(0)]
+  free = [threading.Semaphore(1), threading.Semaphore(1)]
+  c_orders = [False, False]
+  failure = []
+  stop = threading.Event()
+
+  def producer():
+    for k in range(n_steps):
+      free[k & 1].acquire()
+      if stop.is_set():
+        return
+      try:
+        c_orders[k & 1] = feed.pack_and_stage(images[k], k & 1)
+      except BaseException as e:      # surfaced by the consumer at step k
+        failure.append(e)
+        ready[k & 1].release()
+        return
+      ready[k & 1].release()
+
+  th = None
+  if is_src:
+    if images is None or len(images) < n_steps:
+      raise ValueError("the source rank must pass one image per step")
+    th = threading.Thread(target=producer, name="xs3d-volume-feed")
+    th.start()
+  results = []
+  try:
+    for k in range(n_steps):
+      if before_step is not None:
+        before_step(k)
+      if is_src:
+        ready[k & 1].acquire()
+        if failure:
+          raise failure[0]
+        feed.commit(k & 1, c_orders[k & 1])
+        free[k & 1].release()
+      if multi:
+        dist.broadcast(feed.cubes_tensor(), src=src, group=group)
+        if not is_src:
+          feed.mark_loaded()
+      results.append(sweep(k))
+  finally:
+    if th is not None:
+      stop.set()                      # a consumer that bailed out must not leave the helper thread waiting
+      for sem in free:
+        sem.release()
+      th.join()
+  return results

@@ -50,3 +50,80 @@ def test_sharded_area_batch_gloo(n):
   res.sort()
   assert all(ok for _, ok, _, _ in res)
   assert res[0][2] == 0 and res[0][3] == res[1][2] and res[1][3] == n
+
+
+def _stream_worker(rank, world, port, q):
+  """stream_volumes on gloo: rank 0 really bit-packs (xs3d.pack_bits is host code), a CPU stand-in plays the upload /
+  ingest, the occupancy bytes travel by gloo broadcast, every rank checks what it holds at every step."""
+  import torch
+  import torch.distributed as dist
+  sys.path.insert(0, os.path.join(ROOT, "cross-section_b200"))
+  import xs3d
+  from xs3d import dist as xdist
+  dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+  try:
+    shape = (20, 13, 9)
+    h = [(s + 1) // 2 for s in shape]
+
+    def occupancy(vol):
+      pad = np.zeros([2 * x for x in h], bool)
+      pad[: shape[0], : shape[1], : shape[2]] = vol
+      out = np.zeros(h, np.uint8)
+      for b in range(8):
+        out |= pad[(b & 1)::2, ((b >> 1) & 1)::2, (b >> 2)::2].astype(np.uint8) << b
+      return out.ravel(order="F")
+
+    rng = np.random.default_rng(3)
+    images = [rng.random(shape) < 0.4 for _ in range(5)]
+    images = [np.asfortranarray(v) if i % 2 == 0 else np.ascontiguousarray(v) for i, v in enumerate(images)]   # both memory orders
+    expected = [occupancy(v) for v in images]
+
+    class CpuFeed:
+      def __init__(self):
+        self.staged = [None, None]
+        self.cubes = torch.zeros(int(np.prod(h)), dtype=torch.uint8)
+        self.loaded = 0
+      def pack_and_stage(self, image, slot):
+        bits, c_order = xs3d.pack_bits(image)
+        self.staged[slot] = bits.copy()
+        return c_order
+      def commit(self, slot, c_order):
+        vox = np.unpackbits(self.staged[slot], bitorder="little")[: int(np.prod(shape))].astype(bool)
+        self.cubes[:] = torch.from_numpy(occupancy(vox.reshape(shape, order="C" if c_order else "F")))
+        self.staged[slot] = None      # a second commit of the same slot without a new stage would fail
+      def cubes_tensor(self):
+        return self.cubes
+      def mark_loaded(self):
+        self.loaded += 1
+
+    feed = CpuFeed()
+    seen = []
+    res = xdist.stream_volumes(None, images if rank == 0 else None, 5, lambda k: feed.cubes.numpy().copy(),
+                               before_step=seen.append, feed=feed)
+    ok = len(res) == 5 and all(np.array_equal(r, e) for r, e in zip(res, expected)) and seen == list(range(5))
+    ok = ok and feed.loaded == (0 if rank == 0 else 5)
+    # a failure while packing surfaces on the source rank at that step instead of hanging the helper thread
+    if rank == 0:
+      try:
+        xdist.stream_volumes(None, [images[0], np.zeros(shape, np.float32)], 2, lambda k: k, feed=CpuFeed(), group=dist.new_group([0]))
+        ok = False
+      except ValueError:
+        pass
+    else:
+      dist.new_group([0])
+    q.put((rank, ok))
+  finally:
+    dist.destroy_process_group()
+
+
+def test_stream_volumes_gloo():
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = 31500 + (os.getpid() % 2000)
+  procs = [ctx.Process(target=_stream_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=180) for _ in procs]
+  for p in procs:
+    p.join(60)
+  assert sorted(res) == [(0, True), (1, True)]
