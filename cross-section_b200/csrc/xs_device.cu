@@ -990,6 +990,10 @@ struct xs3d_volume {
   uint8_t* h_bits = nullptr;        // pinned staging of the bit-packed image (upload_packed_and_ingest)
   size_t h_bits_cap = 0;
   DevBuf staged[2];                 // bit-packed images uploaded ahead of their ingest (xs3d_volume_stage_packed)
+  DevBuf staged_cubes[2];           // ... and the occupancy bytes built from them (swapped with `cubes` by commit_staged)
+  bool staged_ready[2] = {false, false};
+  uint8_t* h_stage_bits[2] = {nullptr, nullptr};   // pinned: where xs3d_volume_pack_and_stage packs
+  size_t h_stage_cap[2] = {0, 0};
   cudaStream_t stage_stream = nullptr;
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
   uint64_t stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1069,7 +1073,7 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
   if (v->stream2) { cudaStreamSynchronize(v->stream2); cudaStreamDestroy(v->stream2); }
   if (v->stream3) { cudaStreamSynchronize(v->stream3); cudaStreamDestroy(v->stream3); }
   if (v->stage_stream) { cudaStreamSynchronize(v->stage_stream); cudaStreamDestroy(v->stage_stream); }
-  for (int i = 0; i < 2; i++) { if (v->stage_ev[i]) cudaEventDestroy(v->stage_ev[i]); v->staged[i].release(); }
+  for (int i = 0; i < 2; i++) { if (v->stage_ev[i]) cudaEventDestroy(v->stage_ev[i]); v->staged[i].release(); v->staged_cubes[i].release(); if (v->h_stage_bits[i]) cudaFreeHost(v->h_stage_bits[i]); }
   for (int i = 0; i < 8; i++) if (v->ev[i]) cudaEventDestroy(v->ev[i]);
   for (int i = 0; i < 4; i++) if (v->evf[i]) cudaEventDestroy(v->evf[i]);
   for (int i = 0; i < 6; i++) if (v->evb[i]) cudaEventDestroy(v->evb[i]);
@@ -1141,42 +1145,47 @@ static void trace(const xs3d_volume* v, const char* tag) {
   fprintf(stderr, "xs3d-trace %p %s %.1f\n", (const void*)v, tag, ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3);
 }
 
-// bit-packed image in device memory -> occupancy bytes (timed by ev[6], ev[7] like the byte ingest)
-static int launch_ingest_bits(xs3d_volume* v, const uint8_t* d_bits, int c_order) {
-  CK(cudaEventRecord(v->ev[6], v->stream));
+// bit-packed image in device memory -> occupancy bytes `dst`, on `stream`
+static int launch_ingest_bits_to(xs3d_volume* v, const uint8_t* d_bits, int c_order, uint8_t* dst, cudaStream_t stream) {
   const size_t nblocks = (size_t)v->hx * v->hy * v->hz;
   const uintptr_t al = (uintptr_t)d_bits;
   if (!c_order && (v->sx % 32 == 0) && al % 4 == 0) {
     const size_t total = nblocks / 16;
     const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
-    ingest_bits_f32_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+    ingest_bits_f32_kernel<<<grid, 256, 0, stream>>>(d_bits, dst, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
   } else if (!c_order && (v->sx % 16 == 0) && al % 2 == 0) {
     const size_t total = nblocks / 8;
     const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
-    ingest_bits_f16_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+    ingest_bits_f16_kernel<<<grid, 256, 0, stream>>>(d_bits, dst, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
   } else if (c_order && (v->sz % 8 == 0) && al % 4 == 0) {
     const size_t tiles = (size_t)((v->hx + BC_BX - 1) / BC_BX) * ((v->hz + BC_BZ - 1) / BC_BZ) * v->hy;
-    ingest_bits_c_kernel<<<(int)std::min<size_t>(tiles, (size_t)v->sm_count * 32), 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+    ingest_bits_c_kernel<<<(int)std::min<size_t>(tiles, (size_t)v->sm_count * 32), 256, 0, stream>>>(d_bits, dst, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
   } else {
     const int grid = (int)std::min<size_t>((nblocks + 255) / 256, (size_t)v->sm_count * 32);
     if (c_order)
-      ingest_bits_generic_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz,
-                                                              (long long)v->sy * v->sz, (long long)v->sz, 1ll);
+      ingest_bits_generic_kernel<<<grid, 256, 0, stream>>>(d_bits, dst, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz,
+                                                           (long long)v->sy * v->sz, (long long)v->sz, 1ll);
     else
-      ingest_bits_generic_kernel<<<grid, 256, 0, v->stream>>>(d_bits, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz,
-                                                              1ll, (long long)v->sx, (long long)v->sx * v->sy);
+      ingest_bits_generic_kernel<<<grid, 256, 0, stream>>>(d_bits, dst, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz,
+                                                           1ll, (long long)v->sx, (long long)v->sx * v->sy);
   }
   CK(cudaGetLastError());
+  return XS3D_OK;
+}
+// ... into the volume's occupancy bytes on its launching stream (timed by ev[6], ev[7] like the byte ingest)
+static int launch_ingest_bits(xs3d_volume* v, const uint8_t* d_bits, int c_order) {
+  CK(cudaEventRecord(v->ev[6], v->stream));
+  RET(launch_ingest_bits_to(v, d_bits, c_order, (uint8_t*)v->cubes.p, v->stream));
   CK(cudaEventRecord(v->ev[7], v->stream));
   return XS3D_OK;
 }
 
-struct PackUpload { xs3d_volume* v; uint8_t* d_bits; cudaError_t err; };
+struct PackUpload { const uint8_t* h_bits; uint8_t* d_bits; cudaStream_t stream; cudaError_t err; };
 // a part of the bit stream is ready on the host: send it (runs on the thread that called xs_pack_bits_parts)
 static void pack_part_ready(void* ctx, size_t lo, size_t hi) {
   PackUpload* u = (PackUpload*)ctx;
   if (u->err != cudaSuccess) return;
-  u->err = cudaMemcpyAsync(u->d_bits + lo / 8, u->v->h_bits + lo / 8, (hi - lo + 7) / 8, cudaMemcpyHostToDevice, u->v->stream);
+  u->err = cudaMemcpyAsync(u->d_bits + lo / 8, u->h_bits + lo / 8, (hi - lo + 7) / 8, cudaMemcpyHostToDevice, u->stream);
 }
 
 static int upload_packed_and_ingest(xs3d_volume* v, const uint8_t* binimg, int c_order) {
@@ -1193,7 +1202,7 @@ static int upload_packed_and_ingest(xs3d_volume* v, const uint8_t* binimg, int c
   // one job on the host pool, reported in eight parts (256 KiB-grain aligned, hence byte aligned in the bit stream):
   // each part's copy is enqueued as soon as it is packed, so only the last 2 MiB transfer is exposed
   trace(v, "pack-begin");
-  PackUpload up{ v, d_bits, cudaSuccess };
+  PackUpload up{ v->h_bits, d_bits, v->stream, cudaSuccess };
   xs_pack_bits_parts(binimg, 0, voxels, v->h_bits, 8, pack_part_ready, &up);
   CK(up.err);
   trace(v, "pack-end");
@@ -1254,39 +1263,78 @@ extern "C" int xs3d_volume_load_packed(xs3d_volume* v, const uint8_t* bits, int 
   return XS3D_OK;
 }
 
-// The upload of a bit-packed host image, ahead of its ingest: the copy runs on the volume's own upload stream (so it
-// overlaps whatever the launching stream is doing, e.g. the sweep of the previous image) into one of two staging
-// buffers; xs3d_volume_commit_staged then makes the launching stream wait for that copy and builds the occupancy bytes.
-// stage may be called from another host thread than commit (the caller orders the two calls for a slot).
-extern "C" int xs3d_volume_stage_packed(xs3d_volume* v, const uint8_t* bits, int slot) {
+// Upload AND ingest ahead of use: the copy and the bits -> occupancy-byte kernel run on the volume's own upload stream
+// (beside whatever the launching stream is doing, e.g. the sweep of the previous image) into one of two spare sets of
+// buffers; xs3d_volume_commit_staged then only makes the launching stream wait for that work and swaps the spare
+// occupancy bytes in.  stage may be called from another host thread than commit (the caller orders the two calls of a
+// slot; a slot may be staged again once it has been committed).
+static int stage_prepare(xs3d_volume* v, int slot, size_t nbytes) {
+  if (!v->stage_stream) {
+    CK(cudaStreamCreateWithFlags(&v->stage_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&v->stage_ev[i], cudaEventDisableTiming));
+  }
+  RET(v->staged[slot].ensure(nbytes + 4096));
+  RET(v->staged_cubes[slot].ensure((size_t)v->hx * v->hy * v->hz + 64));
+  return XS3D_OK;
+}
+static int stage_finish(xs3d_volume* v, int slot, int c_order) {
+  RET(launch_ingest_bits_to(v, (const uint8_t*)v->staged[slot].p, c_order, (uint8_t*)v->staged_cubes[slot].p, v->stage_stream));
+  CK(cudaEventRecord(v->stage_ev[slot], v->stage_stream));
+  v->staged_ready[slot] = true;
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_volume_stage_packed(xs3d_volume* v, const uint8_t* bits, int slot, int c_order) {
   if (!v) return fail(XS3D_ERR_ARG, "null volume");
   if (slot < 0 || slot > 1) return fail(XS3D_ERR_ARG, "slot must be 0 or 1");
   CK(cudaSetDevice(v->device));
   const size_t voxels = (size_t)v->sx * v->sy * v->sz;
   if (voxels == 0) return XS3D_OK;
   if (!bits) return fail(XS3D_ERR_ARG, "null image");
-  if (!v->stage_stream) {
-    CK(cudaStreamCreateWithFlags(&v->stage_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&v->stage_ev[i], cudaEventDisableTiming));
-  }
   const size_t nbytes = (voxels + 7) / 8;
-  RET(v->staged[slot].ensure(nbytes + 4096));
-  CK(cudaMemcpyAsync(v->staged[slot].p, bits, nbytes, cudaMemcpyHostToDevice, v->stage_stream));
-  CK(cudaEventRecord(v->stage_ev[slot], v->stage_stream));
-  return XS3D_OK;
+  RET(stage_prepare(v, slot, nbytes));
+  // in 1 MiB pieces: the small host-to-device copies of a batch running meanwhile (its queries) then wait for one
+  // piece (~20 us) on the copy engine, not for the whole image
+  for (size_t off = 0; off < nbytes; off += (size_t)1 << 20)
+    CK(cudaMemcpyAsync((uint8_t*)v->staged[slot].p + off, bits + off, std::min<size_t>((size_t)1 << 20, nbytes - off), cudaMemcpyHostToDevice, v->stage_stream));
+  return stage_finish(v, slot, c_order);
 }
 
-extern "C" int xs3d_volume_commit_staged(xs3d_volume* v, int slot, int c_order) {
+// The same for a boolean image that is still bytes: packed by the host pool into a pinned buffer of the volume, every
+// eighth of the bit stream copied (upload stream) as soon as it is packed — the transfer ends with the packing.
+extern "C" int xs3d_volume_pack_and_stage(xs3d_volume* v, const uint8_t* binimg, int slot, int c_order) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (slot < 0 || slot > 1) return fail(XS3D_ERR_ARG, "slot must be 0 or 1");
+  CK(cudaSetDevice(v->device));
+  const size_t voxels = (size_t)v->sx * v->sy * v->sz;
+  if (voxels == 0) return XS3D_OK;
+  if (!binimg) return fail(XS3D_ERR_ARG, "null image");
+  const size_t nbytes = (voxels + 7) / 8;
+  RET(stage_prepare(v, slot, nbytes));
+  if (v->h_stage_cap[slot] < nbytes + 64) {
+    if (v->h_stage_bits[slot]) cudaFreeHost(v->h_stage_bits[slot]);
+    v->h_stage_bits[slot] = nullptr; v->h_stage_cap[slot] = 0;
+    CK(cudaHostAlloc((void**)&v->h_stage_bits[slot], nbytes + 4096, cudaHostAllocDefault));
+    v->h_stage_cap[slot] = nbytes + 4096;
+  }
+  PackUpload up{ v->h_stage_bits[slot], (uint8_t*)v->staged[slot].p, v->stage_stream, cudaSuccess };
+  xs_pack_bits_parts(binimg, 0, voxels, v->h_stage_bits[slot], 8, pack_part_ready, &up);
+  CK(up.err);
+  return stage_finish(v, slot, c_order);
+}
+
+extern "C" int xs3d_volume_commit_staged(xs3d_volume* v, int slot) {
   if (!v) return fail(XS3D_ERR_ARG, "null volume");
   if (slot < 0 || slot > 1) return fail(XS3D_ERR_ARG, "slot must be 0 or 1");
   CK(cudaSetDevice(v->device));
   const size_t voxels = (size_t)v->sx * v->sy * v->sz;
   if (voxels == 0) { v->loaded = true; return XS3D_OK; }
-  if (!v->stage_stream || !v->staged[slot].p) return fail(XS3D_ERR_ARG, "nothing staged in this slot");
+  if (!v->stage_stream || !v->staged_ready[slot]) return fail(XS3D_ERR_ARG, "nothing staged in this slot");
+  // every earlier batch has finished with the current occupancy bytes (the batch calls return after a synchronize), so
+  // the buffers can simply change places; what the launching stream does next waits for the staged ingest
   CK(cudaStreamWaitEvent(v->stream, v->stage_ev[slot], 0));
-  RET(launch_ingest_bits(v, (const uint8_t*)v->staged[slot].p, c_order));
-  CK(cudaStreamSynchronize(v->stream));
-  CK(cudaEventElapsedTime(&v->timing[4], v->ev[6], v->ev[7]));
+  std::swap(v->cubes, v->staged_cubes[slot]);
+  v->staged_ready[slot] = false;
   v->loaded = true;
   return XS3D_OK;
 }

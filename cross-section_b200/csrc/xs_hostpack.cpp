@@ -42,9 +42,21 @@ void pack_range_scalar(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
 }
 
 #if defined(__x86_64__)
+// 64 voxels per step, with a software prefetch 8 KiB ahead: one core's demand loads (and the hardware streamer behind
+// them) keep too few cache lines in flight to fill its share of the memory bandwidth — on the bench box (16 Xeon cores)
+// the far prefetch lifts the pool from ~110-120 GB/s to ~165 GB/s (tools/pack_bench.c: distances of 1-4 KiB gain less,
+// prefetchnta loses).  Prefetches past the end of the image are harmless (they never fault).
 __attribute__((target("avx2"))) void pack_range_avx2(const uint8_t* in, size_t lo, size_t hi, uint8_t* out) {
   const __m256i z = _mm256_setzero_si256();
   size_t i = lo;
+  for (; i + 64 <= hi; i += 64) {
+    _mm_prefetch(reinterpret_cast<const char*>(in + i + 8192), _MM_HINT_T2);
+    const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i));
+    const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i + 32));
+    const uint64_t m = (uint64_t)(~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(a, z))) |
+                       ((uint64_t)(~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(b, z))) << 32);
+    memcpy(out + (i >> 3), &m, 8);
+  }
   for (; i + 32 <= hi; i += 32) {
     const __m256i v = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(in + i));
     const uint32_t m = ~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, z));

@@ -182,16 +182,28 @@ class Volume:
       raise ValueError("bit stream too short for the volume")
     _abi.check(self._lib.xs3d_volume_load_packed(self._h, bits.ctypes.data, HOST, int(bool(c_order))))
 
-  def stage_packed(self, bits, slot=0):
-    """Start the upload of a bit-packed HOST image (pinned memory for an asynchronous copy) into staging buffer `slot`
-    (0 or 1) on the volume's upload stream; returns at once.  commit_staged(slot) ingests it."""
+  def stage_packed(self, bits, slot=0, c_order=False):
+    """Start the upload of a bit-packed HOST image (pinned memory for an asynchronous copy) into the spare buffers of
+    `slot` (0 or 1) and its ingest, both on the volume's upload stream; returns at once.  commit_staged(slot) swaps
+    the result in."""
     ptr = bits.data_ptr() if _is_torch_tensor(bits) else bits.ctypes.data
-    _abi.check(self._lib.xs3d_volume_stage_packed(self._h, ptr, int(slot)))
+    _abi.check(self._lib.xs3d_volume_stage_packed(self._h, ptr, int(slot), int(bool(c_order))))
     self._keep = bits
 
-  def commit_staged(self, slot=0, c_order=False):
-    """Wait (on the device) for the staged upload of `slot` and build the occupancy bytes from it."""
-    _abi.check(self._lib.xs3d_volume_commit_staged(self._h, int(slot), int(bool(c_order))))
+  def pack_and_stage(self, binimg, slot=0):
+    """stage_packed for a boolean image that is still bytes (either memory order): bit-packed by the host thread pool,
+    each part of the bit stream copied as soon as it is packed, occupancy bytes built behind the last copy."""
+    if tuple(int(s) for s in binimg.shape) != self.shape:
+      raise ValueError("image shape does not match the volume")
+    if binimg.dtype != bool and binimg.dtype != np.uint8:
+      raise ValueError(f"A boolean image is required. Got: {binimg.dtype}")
+    a, ptr, c_order = _image_pointer(binimg)
+    _abi.check(self._lib.xs3d_volume_pack_and_stage(self._h, ptr, int(slot), int(c_order)))
+
+  def commit_staged(self, slot=0):
+    """Make the image staged in `slot` the resident one: the launching stream waits (on the device) for the staged
+    upload + ingest, the occupancy bytes change places.  No kernel, no host synchronisation."""
+    _abi.check(self._lib.xs3d_volume_commit_staged(self._h, int(slot)))
 
   def load_labels(self, labels):
     if tuple(int(s) for s in labels.shape) != self.shape:

@@ -97,23 +97,22 @@ def sharded_area_batch(compute, positions, normals, group=None, gather=True):
 
 
 class VolumeFeed:
-  """What stream_volumes does to a real (CUDA) Volume: pack into one of two pinned buffers with the library's host
-  thread pool + start the upload on the volume's upload stream; later ingest the staged bits."""
+  """What stream_volumes does to a real (CUDA) Volume: bit-pack the image with the library's host thread pool while the
+  packed parts go up and are ingested on the volume's upload stream (Volume.pack_and_stage); later swap the result in."""
 
   def __init__(self, volume):
-    import torch
-    nbytes = (int(np.prod(volume.shape)) + 7) // 8 + 64
     self.volume = volume
-    self.bufs = [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
 
   def pack_and_stage(self, image, slot):
-    from . import pack_bits
-    _, c_order = pack_bits(image, out=self.bufs[slot])
-    self.volume.stage_packed(self.bufs[slot], slot)
-    return c_order
+    self.volume.pack_and_stage(image, slot)
 
-  def commit(self, slot, c_order):
-    self.volume.commit_staged(slot, c_order)
+  def commit(self, slot):
+    import torch
+    self.volume.commit_staged(slot)
+    # the swap is ordered on the volume's launching stream; a broadcast issued on torch's current stream must come after
+    # it, so unless the two are the same stream (Volume.set_stream) wait for the staged work here
+    if getattr(self.volume, "_stream", None) != torch.cuda.current_stream(self.volume.device).cuda_stream:
+      torch.cuda.synchronize(self.volume.device)
 
   def cubes_tensor(self):
     import torch
@@ -129,7 +128,7 @@ class VolumeFeed:
 def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_step=None, feed=None):
   """Run `sweep(k)` for k = 0 .. n_steps-1 with `volume` holding images[k] (only rank `src` passes `images`; the others
   may pass None).  Rank `src` packs + uploads image k+1 on a helper thread (double-buffered) while step k runs; per
-  step the staged bits are ingested on `src`, the occupancy bytes are broadcast when there is more than one rank, and
+  step the staged occupancy bytes are swapped in on `src`, broadcast when there is more than one rank, and
   every rank calls sweep(k) — normally its own shard of the queries against `volume`.  Returns the list of sweep
   results.  `before_step(k)` runs at the top of each step (bench.py evicts L2 there); `feed`: a VolumeFeed(volume) to
   reuse its pinned buffers across calls, or a stand-in for the CUDA plumbing (tests run this loop on the gloo backend)."""
@@ -141,7 +140,6 @@ def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_ste
   is_src = rank == src
   ready = [threading.Semaphore(0), threading.Semaphore(0)]
   free = [threading.Semaphore(1), threading.Semaphore(1)]
-  c_orders = [False, False]
   failure = []
   stop = threading.Event()
 
@@ -151,7 +149,7 @@ def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_ste
       if stop.is_set():
         return
       try:
-        c_orders[k & 1] = feed.pack_and_stage(images[k], k & 1)
+        feed.pack_and_stage(images[k], k & 1)
       except BaseException as e:      # surfaced by the consumer at step k
         failure.append(e)
         ready[k & 1].release()
@@ -173,7 +171,7 @@ def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_ste
         ready[k & 1].acquire()
         if failure:
           raise failure[0]
-        feed.commit(k & 1, c_orders[k & 1])
+        feed.commit(k & 1)
         free[k & 1].release()
       if multi:
         dist.broadcast(feed.cubes_tensor(), src=src, group=group)

@@ -53,12 +53,17 @@ int xs3d_volume_load(xs3d_volume* vol, const uint8_t* binimg, int mem, int c_ord
  * pack image k+1 while image k is being swept, or keep its masks bit-packed (1/8 of the reference's bool arrays). */
 int xs3d_pack_bits(const uint8_t* binimg, uint64_t voxels, uint8_t* bits);
 int xs3d_volume_load_packed(xs3d_volume* vol, const uint8_t* bits, int mem, int c_order);
-/* Upload ahead of the ingest: stage copies a bit-packed HOST image (pinned, for the copy to be asynchronous) into staging
- * buffer `slot` (0 or 1) on the volume's own upload stream and returns at once; commit makes the launching stream wait for
- * that copy, builds the occupancy bytes from it and returns when they are ready.  A pipeline stages image k+1 (from any
- * host thread) while image k is being swept. */
-int xs3d_volume_stage_packed(xs3d_volume* vol, const uint8_t* bits, int slot);
-int xs3d_volume_commit_staged(xs3d_volume* vol, int slot, int c_order);
+/* Upload and ingest ahead of use.  stage copies a bit-packed HOST image (pinned, for the copy to be asynchronous) into
+ * the spare buffers of `slot` (0 or 1) and builds occupancy bytes from it, all on the volume's own upload stream, and
+ * returns at once; commit makes the launching stream wait for that work and swaps the spare occupancy bytes in (no
+ * kernel, no host synchronisation).  A pipeline stages image k+1 (from any host thread) while image k is being swept;
+ * a slot may be staged again once it has been committed.  c_order as in xs3d_volume_load. */
+int xs3d_volume_stage_packed(xs3d_volume* vol, const uint8_t* bits, int slot, int c_order);
+/* stage for an image that is still bytes (1 per voxel, host memory, pinned or not): packed by the host pool, each eighth
+ * of the bit stream copied as soon as it is packed, so that the transfer ends with the packing.  Returns when the image
+ * has been read (the caller may reuse it); copy and ingest may still be in flight. */
+int xs3d_volume_pack_and_stage(xs3d_volume* vol, const uint8_t* binimg, int slot, int c_order);
+int xs3d_volume_commit_staged(xs3d_volume* vol, int slot);
 /* Attach a label volume for xs3d_projection_v (any 1/2/4/8-byte dtype, C or F order; fastxs3d.cpp:135,199-215). */
 int xs3d_volume_load_labels(xs3d_volume* vol, const void* labels, int itemsize, int mem, int c_order);
 /* Make the resident image "labels == label" (labels attached with xs3d_volume_load_labels): the occupancy bytes

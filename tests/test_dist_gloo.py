@@ -85,10 +85,10 @@ def _stream_worker(rank, world, port, q):
         self.loaded = 0
       def pack_and_stage(self, image, slot):
         bits, c_order = xs3d.pack_bits(image)
-        self.staged[slot] = bits.copy()
-        return c_order
-      def commit(self, slot, c_order):
-        vox = np.unpackbits(self.staged[slot], bitorder="little")[: int(np.prod(shape))].astype(bool)
+        self.staged[slot] = (bits.copy(), c_order)
+      def commit(self, slot):
+        bits, c_order = self.staged[slot]
+        vox = np.unpackbits(bits, bitorder="little")[: int(np.prod(shape))].astype(bool)
         self.cubes[:] = torch.from_numpy(occupancy(vox.reshape(shape, order="C" if c_order else "F")))
         self.staged[slot] = None      # a second commit of the same slot without a new stage would fail
       def cubes_tensor(self):

@@ -87,13 +87,17 @@ def test_bit_packed_upload_matches_numpy(xs):
           holder = type("H", (), {})()
           holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
           assert np.array_equal(torch.as_tensor(holder, device="cuda").cpu().numpy(), exp), (shape, order, "load_packed")
-      # upload ahead of the ingest: stage into either slot (from pinned memory), commit later
+      # upload + ingest ahead of use: stage into either slot, commit (a buffer swap) later
       with xs.Volume(shape=shape) as V:
         pinned = torch.from_numpy(pb).pin_memory()
         for slot in (0, 1):
           V.load(np.zeros(shape, bool, order="F"))
-          V.stage_packed(pinned, slot)
-          V.commit_staged(slot, c_order=c_order)
+          if slot == 0:
+            V.stage_packed(pinned, slot, c_order=c_order)
+          else:
+            V.pack_and_stage(v, slot)                        # packing, upload and ingest in one call, from the byte image
+          V.commit_staged(slot)
+          torch.cuda.synchronize()
           ptr, nbytes = V.cubes()
           holder = type("H", (), {})()
           holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}

@@ -1,3 +1,3 @@
-python bench.py --steps 20 > gpurun_out/bench_r1j.log 2>&1 || tail -20 gpurun_out/bench_r1j.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 3 > gpurun_out/bench_r1j_n2.log 2>&1 || tail -20 gpurun_out/bench_r1j_n2.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/dist_check.py 2>&1 | tail -3
+python -m pytest tests -m gpu -x -q -k "packed or ingest or sweep" 2>&1 | tail -2
+XS3D_HOST_THREADS=12 python tools/gpu_stream_trace.py 2>&1 | tail -14
+for t in 10 12 14 15; do XS3D_HOST_THREADS=$t XS_BENCH_NO_SMI=1 python bench.py --steps 20 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); e=d['e2e']; print('threads $t', e['value'], e['ms_per_step'], e['one_sweep_at_a_time']['ms_per_step'])"; done
