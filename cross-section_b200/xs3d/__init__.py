@@ -155,11 +155,15 @@ class Volume:
       import torch
       if binimg.dtype not in (torch.bool, torch.uint8):
         raise ValueError(f"A boolean image is required. Got: {binimg.dtype}")
+      c_order = 1
       if not binimg.is_contiguous():
-        binimg = binimg.contiguous()
+        if binimg.permute(2, 1, 0).is_contiguous():
+          c_order = 0                    # Fortran-ordered tensor: ingested as it is, no transposing copy
+        else:
+          binimg = binimg.contiguous()
       mem = DEVICE if binimg.is_cuda else HOST
       self._order_after_producers(binimg)
-      _abi.check(self._lib.xs3d_volume_load(self._h, binimg.data_ptr(), mem, 1))
+      _abi.check(self._lib.xs3d_volume_load(self._h, binimg.data_ptr(), mem, c_order))
       return
     if binimg.dtype != bool and binimg.dtype != np.uint8:
       raise ValueError(f"A boolean image is required. Got: {binimg.dtype}")

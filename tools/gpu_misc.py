@@ -30,9 +30,11 @@ t = time.time()
 for i in range(200): xs3d.cross_sectional_area(vol, qp[i], qn[i], w, use_persistent_data=True)
 print("single-call latency (resident image): %.3f ms/query" % ((time.time() - t) / 200 * 1e3))
 xs3d.clear_shape()
+t = time.time(); xs3d.cross_sectional_area(vol, qp[0], qn[0], w)
+print("single call, first after clear_shape (buffers re-created): %.2f ms" % ((time.time() - t) * 1e3))
 t = time.time()
-for i in range(5): xs3d.cross_sectional_area(vol, qp[i], qn[i], w)
-print("single-call latency (upload every call): %.2f ms/query" % ((time.time() - t) / 5 * 1e3))
+for i in range(20): xs3d.cross_sectional_area(vol, qp[i], qn[i], w)
+print("single-call latency (upload every call, pageable numpy image): %.2f ms/query" % ((time.time() - t) / 20 * 1e3))
 # unaligned ingest (500^3)
 sph = syn.make_sphere()
 Vs = xs3d.Volume(sph)
