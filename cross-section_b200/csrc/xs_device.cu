@@ -182,7 +182,43 @@ __global__ void __launch_bounds__(256) ingest_bits_f32_kernel(const uint8_t* __r
     *reinterpret_cast<uint4*>(cubes + (size_t)16 * xg + (size_t)hx * ((size_t)by + (size_t)hy * bz)) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
-// C order (z fastest), sz % 8 == 0 (every (x, y) row of the bit stream starts on a byte): reads want z fastest, the
+// Fortran order, any sx: rows of the bit stream start at any bit, so each of the four rows is cut out of three bytes.
+// 16 voxels x 4 rows -> up to 8 occupancy bytes per thread.
+__global__ void __launch_bounds__(256) ingest_bits_fx_kernel(const uint8_t* __restrict__ bits, uint8_t* __restrict__ cubes,
+                                                             int sx, int sy, int sz, int hx, int hy, int hz) {
+  const int gx = (hx + 7) >> 3;
+  const size_t total = (size_t)gx * hy * hz;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int xg = (int)(idx % gx);
+    const size_t t = idx / gx;
+    const int by = (int)(t % hy), bz = (int)(t / hy);
+    const int nv = min(16, sx - 16 * xg);            // voxels of this group that exist along x (>= 1)
+    uint32_t rw[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {                    // c = dy + 2 dz
+      const int y = 2 * by + (c & 1), z = 2 * bz + (c >> 1);
+      uint32_t a = 0u;
+      if (y < sy && z < sz) {
+        const size_t first = ((size_t)z * sy + y) * sx + (size_t)16 * xg;
+        const size_t byte0 = first >> 3;
+        const int sh = (int)(first & 7);
+        uint32_t w = __ldg(bits + byte0);
+        if (sh + nv > 8) w |= (uint32_t)__ldg(bits + byte0 + 1) << 8;
+        if (sh + nv > 16) w |= (uint32_t)__ldg(bits + byte0 + 2) << 16;
+        a = (w >> sh) & ((1u << nv) - 1u);
+      }
+      rw[c] = a;
+    }
+    uint8_t* dst = cubes + (size_t)8 * xg + (size_t)hx * ((size_t)by + (size_t)hy * bz);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t q = ((rw[0] >> (2 * j)) & 3u) | (((rw[1] >> (2 * j)) & 3u) << 2) | (((rw[2] >> (2 * j)) & 3u) << 4) | (((rw[3] >> (2 * j)) & 3u) << 6);
+      if (8 * xg + j < hx) dst[j] = (uint8_t)q;
+    }
+  }
+}
+
+// C order (z fastest; fastest when sz % 8 == 0 and every (x, y) row of the bit stream starts on a byte): reads want z fastest, the
 // occupancy bytes x fastest, so a CTA transposes a tile through shared memory — 32 blocks in x (64 voxel rows) x one block
 // in y (2 voxel rows) x 128 blocks in z (256 voxels = 32 bytes per row): 128 rows of one 32-byte sector in, 128 x 32 bytes out.
 constexpr int BC_BX = 32, BC_BZ = 128, BC_PITCH = 33;   // odd pitch: the emit pass reads rows 4 apart per lane, conflict free
@@ -232,15 +268,33 @@ __global__ void __launch_bounds__(256) ingest_bits_c_kernel(const uint8_t* __res
       const size_t zb0 = (size_t)(2 * bz0) >> 3;     // first byte of the tile along z
       const bool ok = x < sx && y < sy;
       const uint8_t* src = bits + rowb * ((size_t)x * sy + y) + zb0 + 16 * half;
-      if ((rowb & 3) == 0) {
+      if ((sz & 31) == 0) {
         uint32_t w[4];
 #pragma unroll
         for (int k = 0; k < 4; k++) w[k] = (ok && zb0 + 16 * half + 4 * k < rowb) ? __ldg(reinterpret_cast<const uint32_t*>(src) + k) : 0u;
 #pragma unroll
         for (int k = 0; k < 16; k++) rows[row][16 * half + k] = (uint8_t)(w[k >> 2] >> (8 * (k & 3)));
-      } else {
+      } else if ((sz & 7) == 0) {
 #pragma unroll
         for (int k = 0; k < 16; k++) rows[row][16 * half + k] = (ok && zb0 + 16 * half + k < rowb) ? __ldg(src + k) : (uint8_t)0;
+      } else {
+        // sz not a multiple of 8: a row starts at any bit of the stream — shift 17 bytes into 16 and cut the row off at sz
+        const size_t first = ((size_t)x * sy + y) * sz + 2 * bz0 + 128 * half;   // first bit this thread wants
+        const int nvalid = ok ? max(0, min(128, sz - (2 * bz0 + 128 * half))) : 0;
+        const size_t byte0 = first >> 3;
+        const int sh = (int)(first & 7);
+        uint32_t lo = (nvalid > 0) ? __ldg(bits + byte0) : 0u;
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+          uint32_t hi = 0u, val = 0u;
+          if (8 * k < nvalid) {
+            if (sh + nvalid > 8 * (k + 1)) hi = __ldg(bits + byte0 + k + 1);   // a bit of that byte is wanted, so it exists
+            val = ((lo >> sh) | (hi << (8 - sh))) & 0xffu;
+            if (nvalid < 8 * (k + 1)) val &= (1u << (nvalid - 8 * k)) - 1u;
+          }
+          rows[row][16 * half + k] = (uint8_t)val;
+          lo = hi;
+        }
       }
     }
     __syncthreads();
@@ -1157,9 +1211,13 @@ static int launch_ingest_bits_to(xs3d_volume* v, const uint8_t* d_bits, int c_or
     const size_t total = nblocks / 8;
     const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
     ingest_bits_f16_kernel<<<grid, 256, 0, stream>>>(d_bits, dst, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
-  } else if (c_order && (v->sz % 8 == 0) && al % 4 == 0) {
+  } else if (c_order && al % 4 == 0) {
     const size_t tiles = (size_t)((v->hx + BC_BX - 1) / BC_BX) * ((v->hz + BC_BZ - 1) / BC_BZ) * v->hy;
     ingest_bits_c_kernel<<<(int)std::min<size_t>(tiles, (size_t)v->sm_count * 32), 256, 0, stream>>>(d_bits, dst, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+  } else if (!c_order) {
+    const size_t total = (size_t)((v->hx + 7) / 8) * v->hy * v->hz;
+    const int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
+    ingest_bits_fx_kernel<<<grid, 256, 0, stream>>>(d_bits, dst, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
   } else {
     const int grid = (int)std::min<size_t>((nblocks + 255) / 256, (size_t)v->sm_count * 32);
     if (c_order)

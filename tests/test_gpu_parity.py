@@ -57,6 +57,27 @@ def test_ingest_matches_numpy(xs):
       assert np.array_equal(_cubes_of(xs, v), _cubes_numpy(vol)), (shape, order)
 
 
+def test_bit_ingest_kernels_any_size(xs):
+  """pack_bits + load_packed on small volumes of awkward sizes: rows of the bit stream that start at any bit (Fortran
+  order with sx % 16 != 0, C order with sz % 8 != 0), partial tiles, single voxels."""
+  import torch
+  rng = np.random.default_rng(11)
+  shapes = [(1, 1, 1), (3, 5, 7), (17, 9, 33), (33, 17, 9), (50, 50, 50), (64, 48, 32), (65, 3, 260), (130, 7, 66), (31, 2, 300), (16, 16, 40)]
+  for shape in shapes:
+    vol = rng.random(shape) < 0.45
+    exp = _cubes_numpy(vol)
+    for order in ("F", "C"):
+      v = np.asfortranarray(vol) if order == "F" else np.ascontiguousarray(vol)
+      pb, c_order = xs.pack_bits(v)
+      with xs.Volume(shape=shape) as V:
+        V.load_packed(pb, c_order=c_order)
+        ptr, nbytes = V.cubes()
+        holder = type("H", (), {})()
+        holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+        got = torch.as_tensor(holder, device="cuda").cpu().numpy()
+      assert np.array_equal(got, exp), (shape, order)
+
+
 def test_bit_packed_upload_matches_numpy(xs):
   """Host images of >= 8 Mi voxels go up bit-packed (xs_pack_bits on the host cores, ingest_bits_* kernels on the
   device): same occupancy bytes as the plain upload, for the aligned Fortran fast path, odd sizes and C order, from
