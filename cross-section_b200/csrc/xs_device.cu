@@ -305,8 +305,9 @@ __global__ void __launch_bounds__(256) ingest_bits_c_kernel(const uint8_t* __res
 
 // The same tile for a C-ordered uint8 image in HBM (device tensors are C-ordered), sz % 16 == 0 and a 16-byte aligned
 // base: 128 rows x 256 voxels, sixteen 16-byte streaming loads per row, turned into bit rows on the way into shared memory.
+// eq != 0: a voxel counts when its byte equals the one replicated in want4 (uint8 label volumes) instead of when it is non-zero.
 __global__ void __launch_bounds__(256) ingest_c16_kernel(const uint8_t* __restrict__ img, uint8_t* __restrict__ cubes,
-                                                         int sx, int sy, int sz, int hx, int hy, int hz) {
+                                                         int sx, int sy, int sz, int hx, int hy, int hz, uint32_t want4, int eq) {
   __shared__ uint8_t rows[2 * BC_BX * 2][BC_PITCH];
   const int tx = (hx + BC_BX - 1) / BC_BX, tz = (hz + BC_BZ - 1) / BC_BZ;
   const size_t tiles = (size_t)tx * tz * hy;
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(256) ingest_c16_kernel(const uint8_t* __restri
       uint32_t m16 = 0;
 #pragma unroll
       for (int j = 0; j < 4; j++)                    // four voxel bytes -> four bits (byte j != 0 -> bit j)
-        m16 |= ((((__vcmpne4(w[j], 0u) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * j);
+        m16 |= (((((eq ? __vcmpeq4(w[j], want4) : __vcmpne4(w[j], 0u)) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * j);
       rows[row][2 * seg] = (uint8_t)m16;
       rows[row][2 * seg + 1] = (uint8_t)(m16 >> 8);
     }
@@ -380,6 +381,112 @@ __global__ void __launch_bounds__(256) ingest_label_kernel(const T* __restrict__
       if (x < sx && y < sy && z < sz && __ldg(labels + (long long)x * stx + (long long)y * sty + (long long)z * stz) == want) m |= 1u << b;
     }
     cubes[idx] = (uint8_t)m;
+  }
+}
+
+// Fast path of the same: Fortran order, rows of whole 16-byte groups (sx * itemsize % 16 == 0), 16-byte aligned base.
+// One 16-byte streaming load per voxel row and thread (2 / 4 / 8 / 16 labels), four rows -> 1 / 2 / 4 / 8 occupancy bytes,
+// stored as one item: fully coalesced both ways, the label volume is read exactly once.
+template <typename T> __device__ __forceinline__ uint32_t label_eq_mask(uint4 q, T want);   // bit i <-> label i of the group == want
+template <> __device__ __forceinline__ uint32_t label_eq_mask<unsigned long long>(uint4 q, unsigned long long want) {
+  const uint32_t lo = (uint32_t)want, hi = (uint32_t)(want >> 32);
+  return (uint32_t)(q.x == lo && q.y == hi) | ((uint32_t)(q.z == lo && q.w == hi) << 1);
+}
+template <> __device__ __forceinline__ uint32_t label_eq_mask<uint32_t>(uint4 q, uint32_t want) {
+  return (uint32_t)(q.x == want) | ((uint32_t)(q.y == want) << 1) | ((uint32_t)(q.z == want) << 2) | ((uint32_t)(q.w == want) << 3);
+}
+template <> __device__ __forceinline__ uint32_t label_eq_mask<uint16_t>(uint4 q, uint16_t want) {
+  const uint32_t w2 = (uint32_t)want * 0x00010001u;
+  const uint32_t c[4] = { __vcmpeq2(q.x, w2), __vcmpeq2(q.y, w2), __vcmpeq2(q.z, w2), __vcmpeq2(q.w, w2) };
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) m |= ((c[j] & 1u) | ((c[j] >> 15) & 2u)) << (2 * j);
+  return m;
+}
+template <> __device__ __forceinline__ uint32_t label_eq_mask<uint8_t>(uint4 q, uint8_t want) {
+  const uint32_t w4 = (uint32_t)want * 0x01010101u;
+  const uint32_t c[4] = { __vcmpeq4(q.x, w4), __vcmpeq4(q.y, w4), __vcmpeq4(q.z, w4), __vcmpeq4(q.w, w4) };
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) m |= ((((c[j] & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (4 * j);
+  return m;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) ingest_label_f16_kernel(const T* __restrict__ labels, T want, uint8_t* __restrict__ cubes,
+                                                               int sx, int sy, int sz, int hx, int hy, int hz) {
+  constexpr int VPT = 16 / (int)sizeof(T);           // labels per 16-byte load
+  constexpr int OUT = VPT / 2;                       // occupancy bytes per thread
+  const int gx = hx / OUT;                           // sx % VPT == 0
+  const size_t total = (size_t)gx * hy * hz;
+  const size_t row = (size_t)sx;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int xg = (int)(idx % gx);
+    const size_t t = idx / gx;
+    const int by = (int)(t % hy), bz = (int)(t / hy);
+    const int y0 = 2 * by, z0 = 2 * bz;
+    const bool y1ok = (y0 + 1) < sy, z1ok = (z0 + 1) < sz;
+    const T* p00 = labels + (size_t)VPT * xg + row * ((size_t)y0 + (size_t)sy * z0);
+    const uint4 a = __ldcs(reinterpret_cast<const uint4*>(p00));
+    uint4 b = a, c = a, d = a;
+    if (y1ok) b = __ldcs(reinterpret_cast<const uint4*>(p00 + row));
+    if (z1ok) c = __ldcs(reinterpret_cast<const uint4*>(p00 + row * sy));
+    if (y1ok && z1ok) d = __ldcs(reinterpret_cast<const uint4*>(p00 + row * sy + row));
+    const uint32_t ra = label_eq_mask<T>(a, want);
+    const uint32_t rb = y1ok ? label_eq_mask<T>(b, want) : 0u;
+    const uint32_t rc = z1ok ? label_eq_mask<T>(c, want) : 0u;
+    const uint32_t rd = (y1ok && z1ok) ? label_eq_mask<T>(d, want) : 0u;
+    unsigned long long o = 0ull;
+#pragma unroll
+    for (int j = 0; j < OUT; j++) {
+      const uint32_t q = ((ra >> (2 * j)) & 3u) | (((rb >> (2 * j)) & 3u) << 2) | (((rc >> (2 * j)) & 3u) << 4) | (((rd >> (2 * j)) & 3u) << 6);
+      o |= (unsigned long long)q << (8 * j);
+    }
+    uint8_t* dst = cubes + (size_t)OUT * xg + (size_t)hx * ((size_t)by + (size_t)hy * bz);
+    if (OUT == 1) *dst = (uint8_t)o;
+    else if (OUT == 2) *reinterpret_cast<uint16_t*>(dst) = (uint16_t)o;
+    else if (OUT == 4) *reinterpret_cast<uint32_t*>(dst) = (uint32_t)o;
+    else *reinterpret_cast<uint2*>(dst) = make_uint2((uint32_t)o, (uint32_t)(o >> 32));
+  }
+}
+
+// C-ordered label volumes of 2 / 4 / 8-byte items (sz % 8 == 0, 16-byte aligned base): the transposing tile of
+// ingest_c16_kernel.  8 labels along z make one byte of a bit row = 1 / 2 / 4 sixteen-byte groups.
+template <typename T>
+__global__ void __launch_bounds__(256) ingest_label_c_kernel(const T* __restrict__ labels, T want, uint8_t* __restrict__ cubes,
+                                                             int sx, int sy, int sz, int hx, int hy, int hz) {
+  constexpr int S = (int)sizeof(T), LPB = S / 2, VPT = 16 / S;
+  __shared__ uint8_t rows[2 * BC_BX * 2][BC_PITCH];
+  const int tx = (hx + BC_BX - 1) / BC_BX, tz = (hz + BC_BZ - 1) / BC_BZ;
+  const size_t tiles = (size_t)tx * tz * hy;
+  for (size_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int tzi = (int)(tile % tz);
+    const size_t r = tile / tz;
+    const int txi = (int)(r % tx), by = (int)(r / tx);
+    const int bx0 = txi * BC_BX, bz0 = tzi * BC_BZ;
+    // one 16-byte load per thread and step, consecutive lanes on consecutive groups of a row (fully coalesced whatever the
+    // item size); the LPB lanes that share a bit-row byte merge their bits by shuffle
+    for (int k0 = 0; k0 < 16 * LPB; k0 += 8) {
+      uint4 q[8];
+      bool ok[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {                  // eight loads in flight before the first compare
+        const int gidx = threadIdx.x + 256 * (k0 + u), unit = gidx / LPB, j = gidx % LPB, row = unit >> 5, ub = unit & 31;
+        const int x = 2 * bx0 + (row >> 1), y = 2 * by + (row & 1), z = 2 * bz0 + 8 * ub;
+        ok[u] = x < sx && y < sy && z < sz;
+        q[u] = ok[u] ? __ldcs(reinterpret_cast<const uint4*>(labels + ((size_t)x * sy + y) * sz + z) + j) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int gidx = threadIdx.x + 256 * (k0 + u), unit = gidx / LPB, j = gidx % LPB, row = unit >> 5, ub = unit & 31;
+        uint32_t m = ok[u] ? (label_eq_mask<T>(q[u], want) << (VPT * j)) : 0u;
+#pragma unroll
+        for (int o = 1; o < LPB; o <<= 1) m |= __shfl_xor_sync(0xffffffffu, m, o);
+        if (j == 0) rows[row][ub] = (uint8_t)m;
+      }
+    }
+    __syncthreads();
+    emit_tile_from_bit_rows(rows, cubes, bx0, by, bz0, hx, hy, hz);
+    __syncthreads();
   }
 }
 
@@ -1158,7 +1265,7 @@ static int launch_ingest(xs3d_volume* v, const uint8_t* d_img, int c_order) {
     ingest_f16_kernel<<<grid, 256, 0, v->stream>>>(d_img, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
   } else if (c_order && (v->sz % 16 == 0) && ((uintptr_t)d_img % 16 == 0)) {
     const size_t tiles = (size_t)((v->hx + BC_BX - 1) / BC_BX) * ((v->hz + BC_BZ - 1) / BC_BZ) * v->hy;
-    ingest_c16_kernel<<<(int)std::min<size_t>(tiles, (size_t)v->sm_count * 32), 256, 0, v->stream>>>(d_img, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+    ingest_c16_kernel<<<(int)std::min<size_t>(tiles, (size_t)v->sm_count * 32), 256, 0, v->stream>>>(d_img, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz, 0u, 0);
   } else {
     int grid = (int)std::min<size_t>((nblocks + 255) / 256, (size_t)v->sm_count * 32);
     if (c_order)
@@ -1409,6 +1516,27 @@ extern "C" int xs3d_volume_select_label(xs3d_volume* v, uint64_t label) {
   const int grid = (int)std::min<size_t>((nblocks + 255) / 256, (size_t)v->sm_count * 32);
   uint8_t* cubes = (uint8_t*)v->cubes.p;
   CK(cudaEventRecord(v->ev[6], v->stream));
+  static const bool label_generic = getenv("XS3D_LABEL_GENERIC") != nullptr;      // dev aid: force the one-thread-per-byte kernel
+  const int vpt = 16 / std::max(1, v->itemsize);
+  if (!label_generic && !v->labels_c_order && v->sx % vpt == 0 && (uintptr_t)v->labels.p % 16 == 0) {
+    const size_t total = nblocks / (size_t)(vpt / 2);
+    const int fgrid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
+    switch (v->itemsize) {
+      case 1: ingest_label_f16_kernel<uint8_t><<<fgrid, 256, 0, v->stream>>>((const uint8_t*)v->labels.p, (uint8_t)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz); break;
+      case 2: ingest_label_f16_kernel<uint16_t><<<fgrid, 256, 0, v->stream>>>((const uint16_t*)v->labels.p, (uint16_t)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz); break;
+      case 4: ingest_label_f16_kernel<uint32_t><<<fgrid, 256, 0, v->stream>>>((const uint32_t*)v->labels.p, (uint32_t)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz); break;
+      default: ingest_label_f16_kernel<unsigned long long><<<fgrid, 256, 0, v->stream>>>((const unsigned long long*)v->labels.p, (unsigned long long)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz); break;
+    }
+  } else if (!label_generic && v->labels_c_order && (uintptr_t)v->labels.p % 16 == 0 && v->sz % (v->itemsize == 1 ? 16 : 8) == 0) {
+    const size_t tiles = (size_t)((v->hx + BC_BX - 1) / BC_BX) * ((v->hz + BC_BZ - 1) / BC_BZ) * v->hy;
+    const int cgrid = (int)std::min<size_t>(tiles, (size_t)v->sm_count * 32);
+    switch (v->itemsize) {
+      case 1: ingest_c16_kernel<<<cgrid, 256, 0, v->stream>>>((const uint8_t*)v->labels.p, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz, (uint32_t)(label & 0xff) * 0x01010101u, 1); break;
+      case 2: ingest_label_c_kernel<uint16_t><<<cgrid, 256, 0, v->stream>>>((const uint16_t*)v->labels.p, (uint16_t)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz); break;
+      case 4: ingest_label_c_kernel<uint32_t><<<cgrid, 256, 0, v->stream>>>((const uint32_t*)v->labels.p, (uint32_t)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz); break;
+      default: ingest_label_c_kernel<unsigned long long><<<cgrid, 256, 0, v->stream>>>((const unsigned long long*)v->labels.p, (unsigned long long)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz); break;
+    }
+  } else
   switch (v->itemsize) {
     case 1: ingest_label_kernel<uint8_t><<<grid, 256, 0, v->stream>>>((const uint8_t*)v->labels.p, (uint8_t)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz, stx, sty, stz); break;
     case 2: ingest_label_kernel<uint16_t><<<grid, 256, 0, v->stream>>>((const uint16_t*)v->labels.p, (uint16_t)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz, stx, sty, stz); break;

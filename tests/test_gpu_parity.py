@@ -401,6 +401,29 @@ def test_select_label_and_skeleton_sweep(xs, oracle):
   assert np.array_equal(bits(a), bits(oa)) and np.array_equal(c, oc)
 
 
+def test_select_label_occupancy_all_dtypes(xs):
+  """xs3d_volume_select_label builds exactly the occupancy bytes of (labels == L): every item size, both memory orders,
+  row lengths that take the 16-byte fast path and ones that do not, labels with set high bits / equal low halves."""
+  import torch
+  rng = np.random.default_rng(21)
+  for shape in [(64, 23, 17), (48, 9, 31), (50, 20, 10), (7, 5, 3), (20, 9, 48), (70, 5, 272), (33, 4, 24)]:
+    for dt in (np.uint8, np.uint16, np.uint32, np.uint64, np.int16, np.int64):
+      top = np.iinfo(dt).max
+      palette = np.array([0, 1, top, top - 1, top // 2 + 1, 258 % (int(top) + 1)], dtype=dt)
+      if np.dtype(dt).itemsize == 8:
+        palette = np.concatenate([palette, np.array([(5 << 32) | 7, (6 << 32) | 7, (5 << 32) | 8], dtype=dt)])   # halves that collide
+      lab = palette[rng.integers(0, len(palette), shape)]
+      for arr in (np.asfortranarray(lab), np.ascontiguousarray(lab)):
+        with xs.Volume(labels=arr) as V:
+          for L in palette[1:]:
+            V.select_label(int(L))
+            ptr, nbytes = V.cubes()
+            holder = type("H", (), {})()
+            holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+            got = torch.as_tensor(holder, device="cuda").cpu().numpy()
+            assert np.array_equal(got, _cubes_numpy(lab == L)), (shape, dt, int(L), arr.flags.f_contiguous)
+
+
 def test_null_normal_is_rejected_on_every_path(xs):
   """An all-zero normal is a ValueError in the reference (xs3d/__init__.py:72-75): host arrays are checked before
   the batch, CUDA tensors by the pre-pass kernel (no host round trip before the launch)."""
