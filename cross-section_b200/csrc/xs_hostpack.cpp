@@ -2,9 +2,11 @@
 //
 // A boolean volume crosses PCIe as one BYTE per voxel when uploaded as the reference hands it over (uint8 / bool
 // ndarray): 128 MiB for 512^3, 2.4 ms at the ~54 GB/s a B200 host link sustains — three times the 0.78 ms the sweep
-// itself takes.  The host cores can turn those bytes into bits at memory speed (~100 GB/s with 12-16 threads on the
-// bench box: 1.2 ms for 128 MiB), after which only 16 MiB cross the link.  xs_pack_bits does that with a persistent
-// thread pool; the device then builds its occupancy bytes from the bits (ingest_bits_kernel, xs_device.cu).
+// itself takes.  The host cores can turn those bytes into bits at memory speed (~155 GB/s with 12-16 threads on the
+// bench box: 0.85 ms for 128 MiB), after which only 16 MiB cross the link.  xs_pack_bits_parts does that with a
+// persistent thread pool, reporting finished parts so that their copies can start while the rest is being packed; the
+// device then builds its occupancy bytes from the bits (ingest_bits_*_kernel, xs_device.cu).  This is a format
+// conversion only: no part of the cross-section algorithm runs on the host.
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>

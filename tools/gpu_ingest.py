@@ -21,3 +21,16 @@ for name, fn in (("bits, Fortran order (ingest_bits_f32_kernel)", lambda: V.load
     fn()
     best = min(best, V.timing()["ingest_ms"])
   print("%-55s %.4f ms" % (name, best))
+# awkward sizes, device-resident uint8 image: bytes -> bits on the device, then the any-size bit ingest
+rng = np.random.default_rng(0)
+for shape in ((500, 500, 500), (501, 499, 503)):
+  vol2 = rng.random(shape) < 0.3
+  with xs3d.Volume(shape=shape) as V2:
+    for name, arr, c in (("F", np.asfortranarray(vol2), 0), ("C", np.ascontiguousarray(vol2), 1)):
+      dv2 = torch.from_numpy(arr.view(np.uint8).ravel(order="K").copy()).cuda()
+      best = 1e9
+      for i in range(3):
+        flush.fill_(i); torch.cuda.synchronize()
+        _abi.check(L.xs3d_volume_load(V2._h, dv2.data_ptr(), _abi.DEVICE, c))
+        best = min(best, V2.timing()["ingest_ms"])
+      print("uint8 in HBM %s, %s order (pack_bits_device + bit ingest): %.4f ms  (%.0f GB/s algorithmic)" % (shape, name, best, vol2.size * 1.125 / best / 1e6))
