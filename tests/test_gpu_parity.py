@@ -250,6 +250,29 @@ def test_host_sweep_entry_point_and_threads(xs, golden):
     assert np.array_equal(bits(res[k][0]), bits(a)) and np.array_equal(res[k][1], c)
 
 
+def test_stream_volumes_single_rank(xs, golden):
+  """xs3d.dist.stream_volumes on one GPU: a sequence of different host volumes (both memory orders) goes through one
+  resident Volume — packed + uploaded + ingested ahead on a helper thread, swapped in per step — and every step's
+  sweep sees exactly its own volume."""
+  from xs3d import synthetic, dist as xdist
+  w = [32, 32, 40]
+  vols, queries, expected = [], [], []
+  for seed in (0, 5, 9, 0):
+    vol, verts, tans = synthetic.make_neurite(256, seed=seed)
+    qp, qn = synthetic.draw_queries(verts, tans, 400, seed=seed + 1)
+    vols.append(vol if seed != 5 else np.ascontiguousarray(vol))
+    queries.append((qp, qn))
+    expected.append(xs.cross_sectional_area_batch(vol, qp, qn, w, return_contact=True))
+  assert np.array_equal(bits(expected[0][0]), bits(xs.cross_sectional_area_batch(vols[0], *queries[0], w)))
+  with xs.Volume(shape=vols[0].shape) as V:
+    res = xdist.stream_volumes(V, vols, len(vols), lambda k: V.cross_sectional_area_batch(*queries[k], w, return_contact=True))
+    for k in range(len(vols)):
+      assert np.array_equal(bits(res[k][0]), bits(expected[k][0])) and np.array_equal(res[k][1], expected[k][1]), k
+    # a second pass over the same handle (the staging slots are reused), fewer steps than slots
+    res = xdist.stream_volumes(V, vols[1:2], 1, lambda k: V.cross_sectional_area_batch(*queries[1], w, return_contact=True))
+    assert np.array_equal(bits(res[0][0]), bits(expected[1][0]))
+
+
 def test_neurite512_sweep_parity_and_properties(xs, oracle, neurite512):
   """BASELINE config 3: the 10k-vertex sweep.  Oracle parity on a 1500-query sample, then
   size-independent properties on all 10k: determinism, order independence (permuting the batch
