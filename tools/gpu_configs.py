@@ -35,6 +35,14 @@ if psutil.virtual_memory().available > 40 * 2 ** 30:
     V.slice_batch(qp2[:n], qn2[:n], w, crop=crop)
     t = time.time(); r = V.slice_batch(qp2[:n], qn2[:n], w, crop=crop); dt = time.time() - t
     print("config 4: slice_batch crop=%d: %d planes in %.4fs -> %.0f planes/s, shape[0]=%s" % (crop, n, dt, n / dt, r[0].shape), flush=True)
+  # the same 8 GiB label volume as the source of per-object masks: mask of one label built on the device
+  for L in (int(lab[tuple(np.round(qp2[0]).astype(int))]), 12345):
+    V.select_label(L)
+    best = 1e9
+    for i in range(3):
+      flush.fill_(i); torch.cuda.synchronize()
+      V.select_label(L); best = min(best, V.timing()["ingest_ms"])
+    print("select_label on the 1024^3 uint64 volume: %.3f ms (%.0f GB/s)" % (best, (lab.nbytes + lab.size / 8) / best / 1e6), flush=True)
   t = time.time(); k = 200
   for i in range(k): ref.projection(lab, qp2[i], qn2[i], w, True, 100.0)
   print("reference slice crop=100: %.0f planes/s (1 core)" % (k / (time.time() - t)))
