@@ -82,6 +82,10 @@ def cpu_sweep_rate(vol, pos, nrm, passes, warm=1):
       t = time.perf_counter()
       pool.map(_cpu_chunk, chunks)
       times.append(time.perf_counter() - t)
+  # one core, for scale: the first 1000 queries in this process
+  t = time.perf_counter()
+  chk.area_batch(vol, pos[:1000], nrm[:1000], ANISOTROPY, nthreads=1)
+  _G["one_core_rate"] = min(1000, n) / (time.perf_counter() - t)
   return n / (sum(times) / len(times)), cores, kind, times
 
 
@@ -97,7 +101,7 @@ def run_reference_arm(args):
     "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
     "config": {"workload": WORKLOAD, "volume": [VOLUME_N] * 3, "queries_per_step": QUERIES, "anisotropy": list(ANISOTROPY)},
-    "cpu_baseline": {"value": rate, "unit": "cross-sections/s", "cores": cores, "kind": kind,
+    "cpu_baseline": {"value": rate, "unit": "cross-sections/s", "cores": cores, "kind": kind, "one_core": _G.get("one_core_rate"),
                      "sample": f"{len(times)} passes of the full {QUERIES}-query sweep, fork()ed workers, one chunk per core"},
     "e2e": {"value": rate, "unit": "cross-sections/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     "gpu_launches": 0,
@@ -415,7 +419,7 @@ def run_own_arm(args):
     "kernels_note": "launching stream: prepass -> warp_tier -> polygon -> combine -> mid_exposed (wait for the second stream); second stream, concurrent: mid_tier -> mid_second_launch -> big_tier -> second_stream_poly_combine",
     "work_per_step": {k: int(stats[k]) for k in ("samples", "blocks", "polygons", "cells_tested", "escalated_mid", "escalated_big", "escalated_worst_case")},
     "roofline": roofline,
-    "cpu_baseline": {"value": rate, "unit": "cross-sections/s", "cores": cores, "kind": kind,
+    "cpu_baseline": {"value": rate, "unit": "cross-sections/s", "cores": cores, "kind": kind, "one_core": _G.get("one_core_rate"),
                      "sample": f"{len(times)} passes of the full {QUERIES}-query sweep, fork()ed workers, one chunk per core"},
     "clocks": clocks,
   }
