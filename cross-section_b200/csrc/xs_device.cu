@@ -1521,6 +1521,36 @@ extern "C" int xs3d_volume_pack_and_stage(xs3d_volume* v, const uint8_t* binimg,
   return stage_finish(v, slot, c_order);
 }
 
+// For a host layer that fills the spare occupancy bytes of a slot itself (an NCCL broadcast into them on its own stream):
+// the buffer, the "wait for what was staged" hook for that stream, and the call that marks the slot as staged.
+extern "C" int xs3d_volume_staged_cubes(xs3d_volume* v, int slot, void** device_ptr, uint64_t* bytes) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (slot < 0 || slot > 1) return fail(XS3D_ERR_ARG, "slot must be 0 or 1");
+  CK(cudaSetDevice(v->device));
+  const size_t voxels = (size_t)v->sx * v->sy * v->sz;
+  RET(stage_prepare(v, slot, (voxels + 7) / 8));
+  *device_ptr = v->staged_cubes[slot].p;
+  *bytes = (uint64_t)v->hx * v->hy * v->hz;
+  return XS3D_OK;
+}
+extern "C" int xs3d_volume_wait_staged(xs3d_volume* v, int slot, void* cuda_stream) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (slot < 0 || slot > 1 || !v->stage_stream) return fail(XS3D_ERR_ARG, "nothing staged in this slot");
+  CK(cudaSetDevice(v->device));
+  CK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, v->stage_ev[slot], 0));
+  return XS3D_OK;
+}
+// The spare occupancy bytes of `slot` were written on `cuda_stream` (everything enqueued there so far): commit_staged
+// will wait for exactly that.
+extern "C" int xs3d_volume_mark_staged(xs3d_volume* v, int slot, void* cuda_stream) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (slot < 0 || slot > 1 || !v->stage_stream) return fail(XS3D_ERR_ARG, "slot not prepared (xs3d_volume_staged_cubes first)");
+  CK(cudaSetDevice(v->device));
+  CK(cudaEventRecord(v->stage_ev[slot], (cudaStream_t)cuda_stream));
+  v->staged_ready[slot] = true;
+  return XS3D_OK;
+}
+
 extern "C" int xs3d_volume_commit_staged(xs3d_volume* v, int slot) {
   if (!v) return fail(XS3D_ERR_ARG, "null volume");
   if (slot < 0 || slot > 1) return fail(XS3D_ERR_ARG, "slot must be 0 or 1");

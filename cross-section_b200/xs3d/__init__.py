@@ -209,6 +209,21 @@ class Volume:
     upload + ingest, the occupancy bytes change places.  No kernel, no host synchronisation."""
     _abi.check(self._lib.xs3d_volume_commit_staged(self._h, int(slot)))
 
+  def staged_cubes(self, slot=0):
+    """(device pointer, bytes) of the spare occupancy bytes of `slot` (for an NCCL broadcast into / out of them)."""
+    p = C.c_void_p()
+    n = C.c_uint64()
+    _abi.check(self._lib.xs3d_volume_staged_cubes(self._h, int(slot), C.byref(p), C.byref(n)))
+    return p.value, n.value
+
+  def wait_staged(self, slot, cuda_stream):
+    """Make `cuda_stream` wait (on the device) for what stage_packed / pack_and_stage put into `slot`."""
+    _abi.check(self._lib.xs3d_volume_wait_staged(self._h, int(slot), C.c_void_p(int(cuda_stream))))
+
+  def mark_staged(self, slot, cuda_stream):
+    """Declare the spare occupancy bytes of `slot` written by everything enqueued on `cuda_stream` so far."""
+    _abi.check(self._lib.xs3d_volume_mark_staged(self._h, int(slot), C.c_void_p(int(cuda_stream))))
+
   def load_labels(self, labels):
     if tuple(int(s) for s in labels.shape) != self.shape:
       raise ValueError("labels shape does not match the volume")

@@ -124,6 +124,29 @@ class VolumeFeed:
   def mark_loaded(self):
     self.volume.mark_loaded()
 
+  # -- broadcast of the STAGED occupancy bytes on a side stream (beside the sweep of the previous image)
+  def bcast_stream(self):
+    import torch
+    if getattr(self, "_bstream", None) is None:
+      self._bstream = torch.cuda.Stream(device=torch.device("cuda", self.volume.device))
+    return self._bstream
+
+  def staged_tensor(self, slot):
+    import torch
+    ptr, nbytes = self.volume.staged_cubes(slot)
+    holder = type("_Holder", (), {})()
+    holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+    return torch.as_tensor(holder, device=torch.device("cuda", self.volume.device))
+
+  def wait_staged(self, slot, stream):
+    self.volume.wait_staged(slot, stream.cuda_stream)
+
+  def mark_staged(self, slot, stream):
+    self.volume.mark_staged(slot, stream.cuda_stream)
+
+  def commit_swap(self, slot):
+    self.volume.commit_staged(slot)
+
 
 def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_step=None, feed=None):
   """Run `sweep(k)` for k = 0 .. n_steps-1 with `volume` holding images[k] (only rank `src` passes `images`; the others
@@ -156,10 +179,64 @@ def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_ste
         return
       ready[k & 1].release()
 
+  if is_src and (images is None or len(images) < n_steps):
+    raise ValueError("the source rank must pass one image per step")
+  if multi and hasattr(feed, "staged_tensor"):
+    # More than one GPU: a third thread per rank broadcasts the STAGED occupancy bytes of image k+1 on a side stream while
+    # the main thread sweeps image k, so that neither the transfer nor the rendezvous of the ranks is on the step's path;
+    # the step itself is then a buffer swap + the sweep, as on one GPU.  Every rank issues the broadcasts in step order.
+    import torch
+    bready = [threading.Semaphore(0), threading.Semaphore(0)]
+    bstream = feed.bcast_stream()
+    device = feed.volume.device
+
+    def broadcaster():
+      torch.cuda.set_device(device)
+      for k in range(n_steps):
+        slot = k & 1
+        if is_src:
+          ready[slot].acquire()
+          if stop.is_set() or failure:
+            bready[slot].release()
+            return
+          feed.wait_staged(slot, bstream)
+        else:
+          free[slot].acquire()
+          if stop.is_set():
+            return
+        try:
+          with torch.cuda.stream(bstream):
+            dist.broadcast(feed.staged_tensor(slot), src=src, group=group)
+          feed.mark_staged(slot, bstream)
+        except BaseException as e:
+          failure.append(e)
+        bready[slot].release()
+
+    threads = [threading.Thread(target=broadcaster, name="xs3d-volume-bcast")]
+    if is_src:
+      threads.append(threading.Thread(target=producer, name="xs3d-volume-feed"))
+    for t in threads:
+      t.start()
+    results = []
+    try:
+      for k in range(n_steps):
+        if before_step is not None:
+          before_step(k)
+        bready[k & 1].acquire()
+        if failure:
+          raise failure[0]
+        feed.commit_swap(k & 1)
+        free[k & 1].release()
+        results.append(sweep(k))
+    finally:
+      stop.set()
+      for sem in free + ready:
+        sem.release()
+      for t in threads:
+        t.join()
+    return results
   th = None
   if is_src:
-    if images is None or len(images) < n_steps:
-      raise ValueError("the source rank must pass one image per step")
     th = threading.Thread(target=producer, name="xs3d-volume-feed")
     th.start()
   results = []

@@ -64,6 +64,13 @@ int xs3d_volume_stage_packed(xs3d_volume* vol, const uint8_t* bits, int slot, in
  * has been read (the caller may reuse it); copy and ingest may still be in flight. */
 int xs3d_volume_pack_and_stage(xs3d_volume* vol, const uint8_t* binimg, int slot, int c_order);
 int xs3d_volume_commit_staged(xs3d_volume* vol, int slot);
+/* For a host layer that moves staged occupancy bytes between GPUs itself (NCCL broadcast on its own stream, beside the
+ * sweep of the previous image): the spare occupancy buffer of a slot; a hook that makes `cuda_stream` wait for what
+ * stage_packed / pack_and_stage put there; and the call that declares the buffer written by everything enqueued on
+ * `cuda_stream` so far, so that commit_staged waits for exactly that. */
+int xs3d_volume_staged_cubes(xs3d_volume* vol, int slot, void** device_ptr, uint64_t* bytes);
+int xs3d_volume_wait_staged(xs3d_volume* vol, int slot, void* cuda_stream);
+int xs3d_volume_mark_staged(xs3d_volume* vol, int slot, void* cuda_stream);
 /* Attach a label volume for xs3d_projection_v (any 1/2/4/8-byte dtype, C or F order; fastxs3d.cpp:135,199-215). */
 int xs3d_volume_load_labels(xs3d_volume* vol, const void* labels, int itemsize, int mem, int c_order);
 /* Make the resident image "labels == label" (labels attached with xs3d_volume_load_labels): the occupancy bytes
