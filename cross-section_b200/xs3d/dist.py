@@ -131,6 +131,16 @@ class VolumeFeed:
       self._bstream = torch.cuda.Stream(device=torch.device("cuda", self.volume.device))
     return self._bstream
 
+  def bind_thread(self):
+    """Called first thing on the broadcaster thread."""
+    import torch
+    torch.cuda.set_device(self.volume.device)
+
+  def bcast_ctx(self):
+    """Context in which the broadcast of a staged buffer is issued (the side stream)."""
+    import torch
+    return torch.cuda.stream(self.bcast_stream())
+
   def staged_tensor(self, slot):
     import torch
     ptr, nbytes = self.volume.staged_cubes(slot)
@@ -138,11 +148,11 @@ class VolumeFeed:
     holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
     return torch.as_tensor(holder, device=torch.device("cuda", self.volume.device))
 
-  def wait_staged(self, slot, stream):
-    self.volume.wait_staged(slot, stream.cuda_stream)
+  def wait_staged(self, slot):
+    self.volume.wait_staged(slot, self.bcast_stream().cuda_stream)
 
-  def mark_staged(self, slot, stream):
-    self.volume.mark_staged(slot, stream.cuda_stream)
+  def mark_staged(self, slot):
+    self.volume.mark_staged(slot, self.bcast_stream().cuda_stream)
 
   def commit_swap(self, slot):
     self.volume.commit_staged(slot)
@@ -185,13 +195,10 @@ def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_ste
     # More than one GPU: a third thread per rank broadcasts the STAGED occupancy bytes of image k+1 on a side stream while
     # the main thread sweeps image k, so that neither the transfer nor the rendezvous of the ranks is on the step's path;
     # the step itself is then a buffer swap + the sweep, as on one GPU.  Every rank issues the broadcasts in step order.
-    import torch
     bready = [threading.Semaphore(0), threading.Semaphore(0)]
-    bstream = feed.bcast_stream()
-    device = feed.volume.device
 
     def broadcaster():
-      torch.cuda.set_device(device)
+      feed.bind_thread()
       for k in range(n_steps):
         slot = k & 1
         if is_src:
@@ -199,15 +206,15 @@ def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_ste
           if stop.is_set() or failure:
             bready[slot].release()
             return
-          feed.wait_staged(slot, bstream)
+          feed.wait_staged(slot)
         else:
           free[slot].acquire()
           if stop.is_set():
             return
         try:
-          with torch.cuda.stream(bstream):
+          with feed.bcast_ctx():
             dist.broadcast(feed.staged_tensor(slot), src=src, group=group)
-          feed.mark_staged(slot, bstream)
+          feed.mark_staged(slot)
         except BaseException as e:
           failure.append(e)
         bready[slot].release()

@@ -54,7 +54,8 @@ def test_sharded_area_batch_gloo(n):
 
 def _stream_worker(rank, world, port, q):
   """stream_volumes on gloo: rank 0 really bit-packs (xs3d.pack_bits is host code), a CPU stand-in plays the upload /
-  ingest, the occupancy bytes travel by gloo broadcast, every rank checks what it holds at every step."""
+  ingest, the occupancy bytes travel by gloo broadcast, every rank checks what it holds at every step — both the
+  plain loop (broadcast on the step's path) and the several-GPU loop (a broadcaster thread moves the staged buffers)."""
   import torch
   import torch.distributed as dist
   sys.path.insert(0, os.path.join(ROOT, "cross-section_b200"))
@@ -96,12 +97,44 @@ def _stream_worker(rank, world, port, q):
       def mark_loaded(self):
         self.loaded += 1
 
+    class CpuStagedFeed(CpuFeed):
+      """adds what the several-GPU path of stream_volumes needs: spare occupancy buffers per slot, filled by the
+      'ingest' on the source rank and by the broadcast elsewhere, swapped in at commit"""
+      def __init__(self):
+        super().__init__()
+        self.spare = [torch.zeros_like(self.cubes), torch.zeros_like(self.cubes)]
+        self.marked = [False, False]
+        self.bound = 0
+      def pack_and_stage(self, image, slot):
+        super().pack_and_stage(image, slot)
+        bits, c_order = self.staged[slot]
+        vox = np.unpackbits(bits, bitorder="little")[: int(np.prod(shape))].astype(bool)
+        self.spare[slot][:] = torch.from_numpy(occupancy(vox.reshape(shape, order="C" if c_order else "F")))
+      def bind_thread(self):
+        self.bound += 1
+      def bcast_ctx(self):
+        import contextlib
+        return contextlib.nullcontext()
+      def staged_tensor(self, slot):
+        return self.spare[slot]
+      def wait_staged(self, slot):
+        assert self.staged[slot] is not None
+      def mark_staged(self, slot):
+        self.marked[slot] = True
+      def commit_swap(self, slot):
+        assert self.marked[slot]
+        self.marked[slot] = False
+        self.cubes, self.spare[slot] = self.spare[slot], self.cubes
+
+    sfeed = CpuStagedFeed()
+    res2 = xdist.stream_volumes(None, images if rank == 0 else None, 5, lambda k: sfeed.cubes.numpy().copy(), feed=sfeed)
+    ok2 = len(res2) == 5 and all(np.array_equal(r, e) for r, e in zip(res2, expected)) and sfeed.bound == 1
     feed = CpuFeed()
     seen = []
     res = xdist.stream_volumes(None, images if rank == 0 else None, 5, lambda k: feed.cubes.numpy().copy(),
                                before_step=seen.append, feed=feed)
     ok = len(res) == 5 and all(np.array_equal(r, e) for r, e in zip(res, expected)) and seen == list(range(5))
-    ok = ok and feed.loaded == (0 if rank == 0 else 5)
+    ok = ok and ok2 and feed.loaded == (0 if rank == 0 else 5)
     # a failure while packing surfaces on the source rank at that step instead of hanging the helper thread
     if rank == 0:
       try:
