@@ -40,6 +40,9 @@ VOLUME_N = 512
 ANISOTROPY = (32.0, 32.0, 40.0)
 METRIC = "cross-sections/sec (batched skeleton vertices, 512^3 vol)"
 WORKLOAD = "neurite512_sweep10k"
+SUSTAINED_SWEEPS = 200
+# the same `config` object in both arms (the driver compares them key by key)
+CONFIG = {"workload": WORKLOAD, "volume": [VOLUME_N] * 3, "queries_per_step": QUERIES, "anisotropy": list(ANISOTROPY)}
 
 
 def make_workload(rank=0):
@@ -100,7 +103,7 @@ def run_reference_arm(args):
     "impl": "reference", "metric": METRIC, "value": rate, "unit": "cross-sections/s", "n_gpus": args.gpus,
     "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
     "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-    "config": {"workload": WORKLOAD, "volume": [VOLUME_N] * 3, "queries_per_step": QUERIES, "anisotropy": list(ANISOTROPY)},
+    "config": dict(CONFIG),
     "cpu_baseline": {"value": rate, "unit": "cross-sections/s", "cores": cores, "kind": kind, "one_core": _G.get("one_core_rate"),
                      "sample": f"{len(times)} passes of the full {QUERIES}-query sweep, fork()ed workers, one chunk per core"},
     "e2e": {"value": rate, "unit": "cross-sections/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -158,7 +161,7 @@ def run_own_arm(args):
   if rank == 0 and not os.environ.get("XS_BENCH_TWO_HANDLES"):
     # the e2e loop packs the (single) host volume on rank 0: all host cores but one per rank (each rank's main thread
     # spins on its GPU); the packing thread itself is one of the pool's workers
-    os.environ.setdefault("XS3D_HOST_THREADS", str(max(4, min(16, (os.cpu_count() or 8) - world))))
+    os.environ.setdefault("XS3D_HOST_THREADS", str(max(4, min(32, (os.cpu_count() or 8) - world))))
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
   if world > 1:
@@ -225,6 +228,98 @@ def run_own_arm(args):
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_total = float(tt.item())
   value = world * QUERIES * args.steps / (ms_total / 1000.0)
+
+  # ---- the same resident step over a longer region (>= ~150 ms of sweeps, so that the clock sampler sees the load):
+  #      SUSTAINED_SWEEPS back-to-back flush + sweep pairs, only the sweeps between event pairs are summed
+  n_sus = max(args.steps, SUSTAINED_SWEEPS)
+  sus_s = [torch.cuda.Event(enable_timing=True) for _ in range(n_sus)]
+  sus_e = [torch.cuda.Event(enable_timing=True) for _ in range(n_sus)]
+  barrier()
+  for i in range(n_sus):
+    flush.fill_(i & 255)
+    sus_s[i].record()
+    step_resident()
+    sus_e[i].record()
+  barrier()
+  sus_ms = sorted(s.elapsed_time(e) for s, e in zip(sus_s, sus_e))
+  sus_total = sum(sus_ms)
+  if world > 1:
+    tt = torch.tensor([sus_total], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    sus_total = float(tt.item())
+  sustained = {"sweeps": n_sus, "value": world * QUERIES * n_sus / (sus_total / 1000.0), "ms_per_step": sus_total / n_sus,
+               "ms_median_rank0": sus_ms[len(sus_ms) // 2], "ms_min_rank0": sus_ms[0], "ms_max_rank0": sus_ms[-1],
+               "what": "the `value` step repeated over a longer timed region (L2 flushed before every sweep, CUDA events around each sweep, max over ranks of the per-rank totals)"}
+
+  # ---- strong scaling (BASELINE config 3/4 wording: ONE 10k-query list sharded over the ranks): rank r sweeps its
+  #      contiguous slice of rank 0's draw with device-resident queries, then areas + contacts are all-gathered (NCCL)
+  #      inside the timed region, so every rank ends up with all 10 000 answers
+  pos0, nrm0 = (pos, nrm) if rank == 0 else make_workload(0)[1:]
+  lo, hi = xdist.shard_bounds(QUERIES, world, rank)
+  kmax = xdist.shard_bounds(QUERIES, world, 0)[1]
+  spos = torch.from_numpy(np.ascontiguousarray(pos0[lo:hi])).to(dev)
+  snrm = torch.from_numpy(np.ascontiguousarray(nrm0[lo:hi])).to(dev)
+  sarea = torch.zeros(kmax, dtype=torch.float32, device=dev)
+  sct = torch.zeros(kmax, dtype=torch.uint8, device=dev)
+  garea = torch.empty(world * kmax, dtype=torch.float32, device=dev)
+  gct = torch.empty(world * kmax, dtype=torch.uint8, device=dev)
+
+  def step_strong():
+    _abi.check(L.xs3d_area_batch(V._h, hi - lo, spos.data_ptr(), snrm.data_ptr(), wp, _abi.DEVICE, sarea.data_ptr(), sct.data_ptr()))
+    if world > 1:
+      dist.all_gather_into_tensor(garea, sarea)
+      dist.all_gather_into_tensor(gct, sct)
+
+  for _ in range(max(3, args.warmup)):
+    step_strong()
+  barrier()
+  st_tot = 0.0
+  for i in range(args.steps):
+    flush.fill_(i & 255)
+    s_ = torch.cuda.Event(enable_timing=True); e_ = torch.cuda.Event(enable_timing=True)
+    s_.record(); step_strong(); e_.record()
+    torch.cuda.synchronize()
+    st_tot += s_.elapsed_time(e_)
+  barrier()
+  strong_kernel_ms = V.timing()
+  if world > 1:
+    tt = torch.tensor([st_tot], dtype=torch.float64, device=dev)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    st_tot = float(tt.item())
+  strong = {"queries_total": QUERIES, "queries_per_rank": hi - lo, "value": QUERIES * args.steps / (st_tot / 1000.0), "ms_per_step": st_tot / args.steps,
+            "collective": "all-gather of areas (4 B) + contacts (1 B) per query inside the timed region" if world > 1 else "none (one rank)",
+            "rank0_kernels_ms_last_step": {k: strong_kernel_ms[k] for k in ("prepass_ms", "warp_tier_ms", "polygon_ms", "combine_ms", "mid_tier_ms", "mid_exposed_ms")},
+            "limiter": "the longest single section: the mid tier walks it on one SM (latency chain) while the other SMs run out of queries; plus the fixed pre-pass / polygon / combine launches"}
+  # every rank: a 200-query sample of what ITS GPU computed (weak draw and strong shard) against the CPU checker,
+  # outside the timed regions; the gathered strong result against rank 0's own full sweep
+  sys.path.insert(0, os.path.join(ROOT, "oracle"))
+  import refapi
+  chk = refapi.Ref() if refapi.have_ref() else refapi.Oracle()
+  da_, dc_ = step_resident()
+  torch.cuda.synchronize()
+  ga, gc = da_.cpu().numpy(), dc_.cpu().numpy()
+  sel = np.linspace(0, QUERIES - 1, 200).astype(np.int64)
+  oa, oc = chk.area_batch(vol, pos[sel], nrm[sel], ANISOTROPY)
+  ok_weak = bool(np.array_equal(ga[sel].view(np.uint32), oa.view(np.uint32)) and np.array_equal(gc[sel], oc))
+  step_strong()
+  torch.cuda.synchronize()
+  ssel = np.linspace(0, hi - lo - 1, min(200, hi - lo)).astype(np.int64)
+  oa, oc = chk.area_batch(vol, pos0[lo:hi][ssel], nrm0[lo:hi][ssel], ANISOTROPY)
+  ok_strong = bool(np.array_equal(sarea.cpu().numpy()[ssel].view(np.uint32), oa.view(np.uint32)) and np.array_equal(sct.cpu().numpy()[ssel], oc))
+  if world > 1:
+    full_a = torch.cat([garea[r * kmax: r * kmax + (xdist.shard_bounds(QUERIES, world, r)[1] - xdist.shard_bounds(QUERIES, world, r)[0])] for r in range(world)])
+    full_c = torch.cat([gct[r * kmax: r * kmax + (xdist.shard_bounds(QUERIES, world, r)[1] - xdist.shard_bounds(QUERIES, world, r)[0])] for r in range(world)])
+    ref_a = da_ if rank == 0 else torch.empty_like(da_)
+    ref_c = dc_ if rank == 0 else torch.empty_like(dc_)
+    dist.broadcast(ref_a, src=0); dist.broadcast(ref_c, src=0)
+    ok_strong = ok_strong and bool(torch.equal(full_a.view(torch.int32), ref_a.view(torch.int32)) and torch.equal(full_c, ref_c))
+  oks = torch.tensor([int(ok_weak), int(ok_strong)], dtype=torch.int32, device=dev)
+  if world > 1:
+    dist.all_reduce(oks, op=dist.ReduceOp.MIN)
+  rank_checks = {"checker": "reference" if refapi.have_ref() else "port", "queries_per_rank_checked": int(len(sel) + len(ssel)),
+                 "all_ranks_bit_exact": bool(int(oks[0]) == 1 and int(oks[1]) == 1),
+                 "what": "every rank compares 200 queries of its own weak-scaling sweep and 200 of its strong-scaling shard with the CPU checker (float32 bit patterns + contact bytes); the all-gathered strong result equals rank 0's single-GPU sweep of the same list"}
+  assert rank_checks["all_ranks_bit_exact"], "a rank's results differ from the CPU checker"
 
   # ---- end to end through the C ABI with host buffers (`e2e`): volume + queries up, results down, every step
   hvol = torch.from_numpy(np.ascontiguousarray(vol.view(np.uint8).ravel(order="F"))).pin_memory()
@@ -377,21 +472,31 @@ def run_own_arm(args):
     alg_bytes = int(frac * (stats["samples"] * 1 + 8 * stats["blocks"])) + 29 * nq_k
   achieved = alg_bytes / (dom_ms / 1000.0) / 1e9
   kname = {"warp_tier_ms": "area_warpn_kernel", "mid_tier_ms": "area_mid_kernel", "big_tier_ms": "area_block_kernel<BigTier>", "polygon_ms": "poly_eval_kernel"}[dom]
-  # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
-  # (profiles/r1i_ncu_full_summary.txt, profiles/r1i_per_kernel_hbm_l2.txt; ingest kernels: profiles/r1j_ingest_kernels_hbm_l2.txt)
-  ncu_traffic = {"area_warpn_kernel": 3010000, "area_mid_kernel": 1650000 + 620000, "poly_eval_kernel": 14420000 + 2100000, "combine_kernel": 10590000 + 1580000}
+  # ncu figures (dram__bytes_read.sum + dram__bytes_write.sum per launch, IPC, lanes, warp instructions) come from
+  # profiles/ncu_current.json, which tools/ncu_current.py writes from the latest `ncu --set full` capture of this
+  # workload; absent file -> null (never a literal typed in here)
+  ncu = {}
+  ncu_path = os.path.join(ROOT, "profiles", "ncu_current.json")
+  if os.path.exists(ncu_path):
+    ncu = json.load(open(ncu_path))
+  nk = ncu.get("kernels", {})
+  def ncu_of(name, key):
+    return nk.get(name, {}).get(key)
   roofline = {"bound": "hbm", "kernel": kname,
-              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic.get(kname),
+              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_of(kname, "dram_bytes"),
+              "traffic_source": ncu.get("capture"),
               "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms, "queries_in_kernel": nq_k,
-              "note": "latency/issue-bound graph walk over the L2-resident 16 MiB occupancy volume, not an HBM stream (ncu: DRAM 0.1 % of peak, L2 hit 84 %, IPC 2.6/SM); the HBM-bound kernel of the path is the ingest, reported beside it",
-              "issue_rate": {"what": "the bound that actually applies to the dominant kernel (from the ncu capture profiles/r1i_ncu_full_summary.txt, not measured live)",
-                             "ipc_per_sm": 2.57, "peak_ipc_per_sm": 4.0, "frac": 0.64, "warp_instructions_per_query": 24000},
+              "note": "latency/issue-bound graph walk over the L2-resident 16 MiB occupancy volume, not an HBM stream; the HBM-bound kernel of the path is the ingest, reported beside it",
+              "issue_rate": {"what": "the bound that actually applies to the dominant kernel, from the ncu capture named in traffic_source (not measured live)",
+                             "ipc_per_sm": ncu_of(kname, "ipc"), "peak_ipc_per_sm": 4.0, "active_lanes": ncu_of(kname, "active_lanes"), "l2_hit_pct": ncu_of(kname, "l2_hit_pct"),
+                             "warp_instructions_per_query": (ncu_of(kname, "warp_inst") / ncu["queries"]) if ncu_of(kname, "warp_inst") and ncu.get("queries") else None},
               "ingest_kernel": {"kernel": "ingest_f16_kernel (uint8 image in HBM -> occupancy bytes)", "ms": ingest_ms,
                                 "achieved": (vol.size * 1.125) / (ingest_ms / 1000.0) / 1e9, "unit": "GB/s",
                                 "frac": (vol.size * 1.125) / (ingest_ms / 1000.0) / 1e9 / peak, "algorithmic_bytes": int(vol.size * 1.125),
-                                "traffic": 139600000, "traffic_note": "ncu: 25 us, 5.5 TB/s of DRAM traffic = 84 % of the peak (the 16 MiB written stay in L2)"},
+                                "traffic": ncu_of("ingest_f16_kernel", "dram_bytes")},
               "ingest_e2e_kernel": {"kernel": "ingest_bits_f32_kernel (bit-packed image -> occupancy bytes)" if packed else "ingest_f16_kernel",
-                                    "ms": ingest_e2e_ms, "algorithmic_bytes": int(vol.size * (0.25 if packed else 1.125)), "traffic": 16790000 if packed else 139600000,
+                                    "ms": ingest_e2e_ms, "algorithmic_bytes": int(vol.size * (0.25 if packed else 1.125)),
+                                    "traffic": ncu_of("ingest_bits_f32_kernel" if packed else "ingest_f16_kernel", "dram_bytes"),
                                     "achieved": vol.size * (0.25 if packed else 1.125) / (ingest_e2e_ms / 1000.0) / 1e9 if ingest_e2e_ms > 0 else None,
                                     "unit": "GB/s",
                                     "frac": vol.size * (0.25 if packed else 1.125) / (ingest_e2e_ms / 1000.0) / 1e9 / peak if ingest_e2e_ms > 0 else None}}
@@ -402,9 +507,12 @@ def run_own_arm(args):
     "metric": METRIC, "value": value, "unit": "cross-sections/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
     "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
     "dtype": "f32", "data": "synthetic",
-    "config": {"workload": WORKLOAD, "volume": [VOLUME_N] * 3, "queries_per_step": QUERIES, "queries_per_rank": QUERIES,
-               "anisotropy": list(ANISOTROPY), "l2": "flushed between timed iterations (256 MiB write); in the pipelined e2e loop the write runs on the sweep's stream before every sweep, inside the timed region",
-               "parallelism": f"query-sharded x{world}"},
+    "config": dict(CONFIG),
+    "run": {"queries_per_rank": QUERIES, "parallelism": f"query-sharded x{world}",
+            "l2": "flushed between timed iterations (256 MiB write); in the pipelined e2e loop the write runs on the sweep's stream before every sweep, inside the timed region"},
+    "sustained": sustained,
+    "strong_scaling": strong,
+    "rank_checks": rank_checks,
     "e2e": {"value": e2e_value, "unit": "cross-sections/s", "h2d_bytes_per_step": int(h2d_volume + world * 2 * pos.nbytes),
             "d2h_bytes_per_step": int(world * QUERIES * 5), "ms_per_step": ms_pipe / psteps,
             "host_input_bytes_per_step": int(vol.size + world * 2 * pos.nbytes),

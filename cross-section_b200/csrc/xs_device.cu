@@ -1157,6 +1157,8 @@ struct xs3d_volume {
   size_t h_stage_cap[2] = {0, 0};
   cudaStream_t stage_stream = nullptr;
   cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+  cudaEvent_t stage_copy_ev[2] = {nullptr, nullptr};   // recorded behind the last host-to-device copy of a slot: its host buffer may be rewritten
+  bool stage_copy_pending[2] = {false, false};
   uint64_t stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t tier_stats[2] = {0, 0};   // samples / items handled by the CTA tiers
   uint32_t wide_over = 0;            // queries the wide tier passed on to the big tier
@@ -1234,7 +1236,7 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
   if (v->stream2) { cudaStreamSynchronize(v->stream2); cudaStreamDestroy(v->stream2); }
   if (v->stream3) { cudaStreamSynchronize(v->stream3); cudaStreamDestroy(v->stream3); }
   if (v->stage_stream) { cudaStreamSynchronize(v->stage_stream); cudaStreamDestroy(v->stage_stream); }
-  for (int i = 0; i < 2; i++) { if (v->stage_ev[i]) cudaEventDestroy(v->stage_ev[i]); v->staged[i].release(); v->staged_cubes[i].release(); if (v->h_stage_bits[i]) cudaFreeHost(v->h_stage_bits[i]); }
+  for (int i = 0; i < 2; i++) { if (v->stage_ev[i]) cudaEventDestroy(v->stage_ev[i]); if (v->stage_copy_ev[i]) cudaEventDestroy(v->stage_copy_ev[i]); v->staged[i].release(); v->staged_cubes[i].release(); if (v->h_stage_bits[i]) cudaFreeHost(v->h_stage_bits[i]); }
   for (int i = 0; i < 8; i++) if (v->ev[i]) cudaEventDestroy(v->ev[i]);
   for (int i = 0; i < 4; i++) if (v->evf[i]) cudaEventDestroy(v->evf[i]);
   for (int i = 0; i < 6; i++) if (v->evb[i]) cudaEventDestroy(v->evb[i]);
@@ -1470,12 +1472,24 @@ static int stage_prepare(xs3d_volume* v, int slot, size_t nbytes) {
   if (!v->stage_stream) {
     CK(cudaStreamCreateWithFlags(&v->stage_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&v->stage_ev[i], cudaEventDisableTiming));
+    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&v->stage_copy_ev[i], cudaEventDisableTiming));
   }
   RET(v->staged[slot].ensure(nbytes + 4096));
   RET(v->staged_cubes[slot].ensure((size_t)v->hx * v->hy * v->hz + 64));
   return XS3D_OK;
 }
+// The previous image staged through this slot may still be on its way up: its host buffer (the volume's pinned buffer,
+// or the caller's) must not be rewritten before those copies are done.  Called at the top of the two staging calls.
+static int stage_wait_copies(xs3d_volume* v, int slot) {
+  if (v->stage_copy_pending[slot]) {
+    CK(cudaEventSynchronize(v->stage_copy_ev[slot]));
+    v->stage_copy_pending[slot] = false;
+  }
+  return XS3D_OK;
+}
 static int stage_finish(xs3d_volume* v, int slot, int c_order) {
+  CK(cudaEventRecord(v->stage_copy_ev[slot], v->stage_stream));
+  v->stage_copy_pending[slot] = true;
   RET(launch_ingest_bits_to(v, (const uint8_t*)v->staged[slot].p, c_order, (uint8_t*)v->staged_cubes[slot].p, v->stage_stream));
   CK(cudaEventRecord(v->stage_ev[slot], v->stage_stream));
   v->staged_ready[slot] = true;
@@ -1490,6 +1504,7 @@ extern "C" int xs3d_volume_stage_packed(xs3d_volume* v, const uint8_t* bits, int
   if (voxels == 0) return XS3D_OK;
   if (!bits) return fail(XS3D_ERR_ARG, "null image");
   const size_t nbytes = (voxels + 7) / 8;
+  RET(stage_wait_copies(v, slot));
   RET(stage_prepare(v, slot, nbytes));
   // in 1 MiB pieces: the small host-to-device copies of a batch running meanwhile (its queries) then wait for one
   // piece (~20 us) on the copy engine, not for the whole image
@@ -1508,6 +1523,7 @@ extern "C" int xs3d_volume_pack_and_stage(xs3d_volume* v, const uint8_t* binimg,
   if (voxels == 0) return XS3D_OK;
   if (!binimg) return fail(XS3D_ERR_ARG, "null image");
   const size_t nbytes = (voxels + 7) / 8;
+  RET(stage_wait_copies(v, slot));
   RET(stage_prepare(v, slot, nbytes));
   if (v->h_stage_cap[slot] < nbytes + 64) {
     if (v->h_stage_bits[slot]) cudaFreeHost(v->h_stage_bits[slot]);
@@ -2124,13 +2140,11 @@ extern "C" int xs3d_section_sparse(xs3d_volume* v, const float pos[3], const flo
 // ---- process-wide default volume backing the drop-in single-call entry points ------------------------
 static std::mutex g_mu;
 static xs3d_volume* g_default = nullptr;   // last image seen by a single-call entry point
-static bool g_persistent_image = false;    // set by xs3d_set_shape_image
 
 static int default_volume(uint64_t sx, uint64_t sy, uint64_t sz, xs3d_volume** out) {
   if (g_default && ((uint64_t)g_default->sx != sx || (uint64_t)g_default->sy != sy || (uint64_t)g_default->sz != sz)) {
     xs3d_volume_destroy(g_default);
     g_default = nullptr;
-    g_persistent_image = false;
   }
   if (!g_default) {
     int dev = 0;
@@ -2141,20 +2155,33 @@ static int default_volume(uint64_t sx, uint64_t sy, uint64_t sz, xs3d_volume** o
   return XS3D_OK;
 }
 
-extern "C" int xs3d_set_shape(uint64_t, uint64_t, uint64_t) { return XS3D_OK; }
-extern "C" int xs3d_set_shape_image(const uint8_t* binimg, uint64_t sx, uint64_t sy, uint64_t sz, int c_order) {
+// fastxs3d.set_shape (xs3d.hpp:1295-1298 sizes the reusable visited buffer): here it creates the process-wide default
+// volume of that shape with its batch workspaces, so that the first query does not pay for the allocations.
+extern "C" int xs3d_set_shape(uint64_t sx, uint64_t sy, uint64_t sz) {
   std::lock_guard<std::mutex> lk(g_mu);
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) return fail(XS3D_ERR_CUDA, "no CUDA device");
+  if (sx * sy * sz == 0) return XS3D_OK;
   xs3d_volume* v;
   RET(default_volume(sx, sy, sz, &v));
-  RET(xs3d_volume_load(v, binimg, XS3D_HOST, c_order));
-  g_persistent_image = true;
-  return XS3D_OK;
+  CK(cudaSetDevice(v->device));
+  return ensure_batch_workspace(v, 1);
+}
+// set_shape + upload of the image (a warm start for callers that go on with the same image; later calls still upload
+// the image they are given)
+extern "C" int xs3d_set_shape_image(const uint8_t* binimg, uint64_t sx, uint64_t sy, uint64_t sz, int c_order) {
+  RET(xs3d_set_shape(sx, sy, sz));
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (sx * sy * sz == 0) return XS3D_OK;
+  xs3d_volume* v;
+  RET(default_volume(sx, sy, sz, &v));
+  return xs3d_volume_load(v, binimg, XS3D_HOST, c_order);
 }
 extern "C" int xs3d_clear_shape(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_default) xs3d_volume_destroy(g_default);
   g_default = nullptr;
-  g_persistent_image = false;
   return XS3D_OK;
 }
 
@@ -2168,10 +2195,11 @@ extern "C" int xs3d_area(const uint8_t* binimg, uint64_t sx, uint64_t sy, uint64
   if (sx * sy * sz == 0) return XS3D_OK;
   xs3d_volume* v;
   RET(default_volume(sx, sy, sz, &v));
-  if (!(use_persistent_data && g_persistent_image && v->loaded)) {
-    RET(xs3d_volume_load(v, binimg, XS3D_HOST, 0));
-    g_persistent_image = false;
-  }
+  // The reference's persistent data is only a reusable visited buffer (xs3d.hpp:963-971): `binimg` is always the image
+  // that is evaluated.  Here the reusable part is the default volume with its workspaces (created by xs3d_set_shape);
+  // the image itself goes up on every call, whatever use_persistent_data says.
+  (void)use_persistent_data;
+  RET(xs3d_volume_load(v, binimg, XS3D_HOST, 0));
   if (slow_method) return xs_area_slow(v, pos, normal, anisotropy, area, contact);
   return xs3d_area_batch(v, 1, pos, normal, anisotropy, XS3D_HOST, area, contact);
 }
@@ -2187,7 +2215,6 @@ extern "C" int xs3d_section(const uint8_t* binimg, uint64_t sx, uint64_t sy, uin
   xs3d_volume* v;
   RET(default_volume(sx, sy, sz, &v));
   RET(xs3d_volume_load(v, binimg, XS3D_HOST, 0));
-  g_persistent_image = false;
   uint64_t* d_idx = nullptr; float* d_val = nullptr; uint64_t nnz = 0;
   if (method == 0) RET(section_fast_sparse(v, pos, normal, anisotropy, &d_idx, &d_val, &nnz, contact));
   else RET(xs_section_slow_sparse(v, pos, normal, anisotropy, method, &d_idx, &d_val, &nnz, contact));

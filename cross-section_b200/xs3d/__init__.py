@@ -70,6 +70,34 @@ def _image_pointer(binimg):
   return a, a.ctypes.data, c_order
 
 
+def _check_out(out, n):
+  """User-supplied result buffers are written through raw pointers by the C ABI: refuse anything that is not exactly
+  what it writes (float32 areas, uint8 contacts, >= n elements, C-contiguous, writeable)."""
+  try:
+    area, contact = out
+  except Exception:
+    raise ValueError("out must be a pair (area float32 [n], contact uint8 [n])") from None
+  for a, dt, name in ((area, np.float32, "area"), (contact, np.uint8, "contact")):
+    if not isinstance(a, np.ndarray) or a.dtype != dt or a.ndim != 1 or a.size < n or not a.flags.c_contiguous or not a.flags.writeable:
+      raise ValueError(f"out: {name} must be a writeable C-contiguous 1-D {np.dtype(dt).name} ndarray of at least {n} elements")
+  return area, contact
+
+
+def _queries(positions, normals):
+  """float32 [n,3] positions and normals of equal length (ValueError otherwise, as the single-query API raises)."""
+  pos = np.ascontiguousarray(positions, dtype=np.float32)
+  nrm = np.ascontiguousarray(normals, dtype=np.float32)
+  if pos.size % 3 or nrm.size % 3:
+    raise ValueError("positions and normals must be [n,3] arrays")
+  pos = pos.reshape(-1, 3)
+  nrm = nrm.reshape(-1, 3)
+  if pos.shape != nrm.shape:
+    raise ValueError("positions and normals must have the same length")
+  if np.any(np.all(nrm == 0, axis=1)):
+    raise ValueError("normal vector must not be a null vector (all zeros).")
+  return pos, nrm
+
+
 class SliceBatch(Sequence):
   """The cut-outs of Volume.slice_batch: sequence of Fortran-ordered 2-D views into one [n, pitch] buffer
   (`.buffer`, `.shapes`); a view is built when an element is accessed, so 10^4 tiny slices cost no Python loop."""
@@ -114,7 +142,7 @@ class Volume:
     h = C.c_void_p()
     _abi.check(self._lib.xs3d_volume_create(self.device, *self.shape, C.byref(h)))
     self._h = h
-    self._keep = None
+    self._keep = [None, None]          # host buffers whose asynchronous upload may still be in flight, per staging slot
     if binimg is not None:
       self.load(binimg)
     if labels is not None:
@@ -190,9 +218,20 @@ class Volume:
     """Start the upload of a bit-packed HOST image (pinned memory for an asynchronous copy) into the spare buffers of
     `slot` (0 or 1) and its ingest, both on the volume's upload stream; returns at once.  commit_staged(slot) swaps
     the result in."""
-    ptr = bits.data_ptr() if _is_torch_tensor(bits) else bits.ctypes.data
+    nbytes = (int(np.prod(self.shape)) + 7) // 8
+    if _is_torch_tensor(bits):
+      if bits.is_cuda or bits.numel() * bits.element_size() < nbytes or not bits.is_contiguous():
+        raise ValueError("stage_packed needs a contiguous HOST buffer of (voxels + 7) // 8 bytes")
+      ptr = bits.data_ptr()
+    else:
+      if not isinstance(bits, np.ndarray) or bits.nbytes < nbytes or not bits.flags.c_contiguous:
+        raise ValueError("stage_packed needs a contiguous HOST buffer of (voxels + 7) // 8 bytes")
+      ptr = bits.ctypes.data
+    if int(slot) not in (0, 1):
+      raise ValueError("slot must be 0 or 1")
+    # the call first waits for the copies of this slot's previous image, so the buffer kept for it can go afterwards
     _abi.check(self._lib.xs3d_volume_stage_packed(self._h, ptr, int(slot), int(bool(c_order))))
-    self._keep = bits
+    self._keep[int(slot)] = bits
 
   def pack_and_stage(self, binimg, slot=0):
     """stage_packed for a boolean image that is still bytes (either memory order): bit-packed by the host thread pool,
@@ -299,8 +338,16 @@ class Volume:
       raise ValueError(f"anisotropy values must be > 0. Got: {w}")
     if _is_torch_tensor(positions):
       import torch
+      if not _is_torch_tensor(normals):
+        normals = torch.as_tensor(np.asarray(normals, dtype=np.float32))
+      if positions.numel() % 3 or normals.numel() % 3:
+        raise ValueError("positions and normals must be [n,3] arrays")
       pos = positions.to(dtype=torch.float32).contiguous().reshape(-1, 3)
       nrm = normals.to(dtype=torch.float32, device=pos.device).contiguous().reshape(-1, 3)
+      if pos.shape != nrm.shape:
+        raise ValueError("positions and normals must have the same length")
+      if not pos.is_cuda:
+        raise ValueError("torch inputs must be CUDA tensors (pass ndarrays for host buffers)")
       n = pos.shape[0]
       area = torch.empty(n, dtype=torch.float32, device=pos.device)
       contact = torch.empty(n, dtype=torch.uint8, device=pos.device)
@@ -315,15 +362,10 @@ class Volume:
           raise ValueError("normal vector must not be a null vector (all zeros).") from None
         raise
       return (area, contact) if return_contact else area
-    pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
-    nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
-    if pos.shape != nrm.shape:
-      raise ValueError("positions and normals must have the same length")
-    if np.any(np.all(nrm == 0, axis=1)):
-      raise ValueError("normal vector must not be a null vector (all zeros).")
+    pos, nrm = _queries(positions, normals)
     n = pos.shape[0]
     if out is not None:
-      area, contact = out
+      area, contact = _check_out(out, n)
     else:
       area = np.empty(n, dtype=np.float32)
       contact = np.empty(n, dtype=np.uint8)
@@ -345,12 +387,9 @@ class Volume:
     if np.any(w <= 0):
       raise ValueError(f"anisotropy values must be > 0. Got: {w}")
     a, ptr, c_order = _image_pointer(binimg)
-    pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
-    nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
-    if np.any(np.all(nrm == 0, axis=1)):
-      raise ValueError("normal vector must not be a null vector (all zeros).")
+    pos, nrm = _queries(positions, normals)
     n = pos.shape[0]
-    area, contact = out if out is not None else (np.empty(n, dtype=np.float32), np.empty(n, dtype=np.uint8))
+    area, contact = _check_out(out, n) if out is not None else (np.empty(n, dtype=np.float32), np.empty(n, dtype=np.uint8))
     _abi.check(self._lib.xs3d_area_sweep_host(self._h, ptr, c_order, n, pos.ctypes.data, nrm.ctypes.data, _abi.fptr(w),
                                               area.ctypes.data, contact.ctypes.data))
     return (area, contact) if return_contact else area
@@ -370,10 +409,7 @@ class Volume:
     if anisotropy is None:
       anisotropy = (1.0, 1.0, 1.0)
     w = _abi.f3(anisotropy)
-    pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
-    nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
-    if np.any(np.all(nrm == 0, axis=1)):
-      raise ValueError("normal vector must not be a null vector (all zeros).")
+    pos, nrm = _queries(positions, normals)
     n = pos.shape[0]
     if crop == 0:
       return [np.zeros((0, 0), dtype=self._label_dtype, order="F") for _ in range(n)]
@@ -511,8 +547,9 @@ def cross_sectional_area(
   return_contact: if true, return (area, contact); contact is the bitfield
     0: 0 X  1: Max X  2: 0 Y  3: Max Y  4: 0 Z  5: Max Z
   slow_method: evaluate every foreground voxel (no connected-component restriction).
-  use_persistent_data: reuse the image made resident by xs3d.set_shape(image) instead of
-    uploading `binimg` again (the caller promises it is the same image, as in the reference).
+  use_persistent_data: reuse the scratch that xs3d.set_shape allocated (as in the reference, where it is
+    a pre-allocated visited buffer: xs3d.hpp:963-971).  `binimg` is always the image that is evaluated;
+    keep a `Volume` to skip the upload of an unchanged image.
 
   Returns: physical area covered by the section plane
   """
@@ -529,7 +566,7 @@ def cross_sectional_area(
   area = C.c_float(0)
   contact = C.c_uint8(0)
   sx, sy, sz = binimg.shape
-  if use_persistent_data or slow_method or binimg.flags.f_contiguous or not binimg.flags.c_contiguous:
+  if slow_method or binimg.flags.f_contiguous or not binimg.flags.c_contiguous:
     a = np.asfortranarray(binimg).view(np.uint8)   # no copy when already Fortran-ordered
     _abi.check(L.xs3d_area(a.ctypes.data, sx, sy, sz, _abi.fptr(_abi.f3(pos)), _abi.fptr(_abi.f3(normal)),
                            _abi.fptr(_abi.f3(anisotropy)), int(slow_method), int(use_persistent_data),
@@ -633,16 +670,12 @@ def slice(
 
 def set_shape(image):
   """
-  Make `image` resident on the GPU so that repeated `cross_sectional_area(..., use_persistent_data=True)`
-  calls skip the upload (the GPU meaning of the reference's pre-allocated visited buffer,
-  xs3d/__init__.py:234-243).  As in the reference, the persisted image must match the later inputs.
+  Pre-allocate the GPU-side scratch (default volume + workspaces) for images of `image.shape`, the GPU meaning of
+  the reference's pre-allocated visited buffer (xs3d/__init__.py:234-243).  Later calls still evaluate — and
+  upload — the image they are given; only the shape has to match for the scratch to be reused.
   """
-  L = _abi.lib()
-  if isinstance(image, np.ndarray) and image.ndim == 3 and image.dtype in (bool, np.uint8):
-    a, ptr, c_order = _image_pointer(image)
-    _abi.check(L.xs3d_set_shape_image(ptr, image.shape[0], image.shape[1], image.shape[2], c_order))
-  else:
-    _abi.check(L.xs3d_set_shape(image.shape[0], image.shape[1], image.shape[2]))
+  sx, sy, sz = (int(s) for s in image.shape)
+  _abi.check(_abi.lib().xs3d_set_shape(sx, sy, sz))
 
 
 def clear_shape():

@@ -10,7 +10,10 @@ query list.  torch.distributed is used only as plumbing:
     all-gather of areas and contact bits;
   * stream_volumes(): a sequence of host volumes through the ranks' resident Volumes — rank `src` bit-packs and
     uploads volume k+1 on a helper thread while everybody sweeps volume k; the occupancy bytes are broadcast
-    every step (the end-to-end loop of bench.py).
+    every step by a helper thread on a communicator of its own (broadcast_group), followed by a status byte
+    that turns a failure of the source rank into an exception on every rank (the end-to-end loop of bench.py);
+  * broadcast_labels() / sharded_slice_batch(): the same for xs3d.slice — the label volume is broadcast once,
+    the planes are partitioned (BASELINE config 5).
 
 The same code runs on the gloo backend with CPU tensors (tests/test_dist_gloo.py), where the
 per-rank compute function is injected by the test.
@@ -157,6 +160,75 @@ class VolumeFeed:
   def commit_swap(self, slot):
     self.volume.commit_staged(slot)
 
+  # -- status byte behind every payload (stream_volumes): device byte broadcast on the side stream, copied to pinned host
+  #    memory behind it, an event says when it can be read.  Four status slots (step & 3): the broadcast of step k+2 can
+  #    be issued before the main thread has read the status of step k, that of step k+4 cannot
+  def _status_bufs(self):
+    import torch
+    if getattr(self, "_st_dev", None) is None:
+      dev = torch.device("cuda", self.volume.device)
+      self._st_dev = [torch.zeros(1, dtype=torch.uint8, device=dev) for _ in range(4)]
+      self._st_host = [torch.zeros(1, dtype=torch.uint8).pin_memory() for _ in range(4)]
+      self._st_ev = [torch.cuda.Event() for _ in range(4)]
+      self._st_issued = [False] * 4
+    return self._st_dev, self._st_host, self._st_ev
+
+  def bcast_status(self, slot, value, src, group):
+    """Called inside bcast_ctx() (the side stream is current)."""
+    import torch.distributed as dist
+    d, h, ev = self._status_bufs()
+    if value is not None:
+      d[slot].fill_(int(value))
+    dist.broadcast(d[slot], src=src, group=group)
+    h[slot].copy_(d[slot], non_blocking=True)
+    ev[slot].record()
+    self._st_issued[slot] = True
+
+  def read_status(self, slot, wait=True):
+    d, h, ev = self._status_bufs()
+    if not self._st_issued[slot]:
+      return 0
+    if wait:
+      ev[slot].synchronize()
+    elif not ev[slot].query():
+      return 0
+    return int(h[slot][0])
+
+
+class _HostStatus:
+  """Status byte that travels behind every staged payload (stream_volumes): generic form for feeds whose tensors live
+  in host memory (the gloo tests).  VolumeFeed has the CUDA form (side stream, pinned copy, event)."""
+
+  def __init__(self):
+    import torch
+    self.t = [torch.zeros(1, dtype=torch.uint8) for _ in range(4)]
+
+  def bcast_status(self, slot, value, src, group):
+    import torch.distributed as dist
+    if value is not None:
+      self.t[slot][0] = int(value)
+    dist.broadcast(self.t[slot], src=src, group=group)
+
+  def read_status(self, slot, wait=True):
+    return int(self.t[slot][0])
+
+
+_bcast_groups = {}
+
+
+def broadcast_group(group=None):
+  """The process group stream_volumes' broadcaster threads use: a communicator of its own over the ranks of `group`,
+  so that the broadcasts issued from the helper thread never share a communicator with the collectives the caller's
+  sweep runs on `group` (two threads enqueueing on one NCCL communicator in rank-dependent order deadlock).
+  Collective: the first call for a given `group` must be made by every rank of the default group at the same point
+  (torch.distributed.new_group's rule); later calls return the cached group."""
+  import torch.distributed as dist
+  key = id(group) if group is not None else None
+  if key not in _bcast_groups:
+    ranks = dist.get_process_group_ranks(group) if group is not None else list(range(dist.get_world_size()))
+    _bcast_groups[key] = dist.new_group(ranks=ranks, backend=dist.get_backend(group))
+  return _bcast_groups[key]
+
 
 def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_step=None, feed=None):
   """Run `sweep(k)` for k = 0 .. n_steps-1 with `volume` holding images[k] (only rank `src` passes `images`; the others
@@ -164,7 +236,14 @@ def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_ste
   step the staged occupancy bytes are swapped in on `src`, broadcast when there is more than one rank, and
   every rank calls sweep(k) — normally its own shard of the queries against `volume`.  Returns the list of sweep
   results.  `before_step(k)` runs at the top of each step (bench.py evicts L2 there); `feed`: a VolumeFeed(volume) to
-  reuse its pinned buffers across calls, or a stand-in for the CUDA plumbing (tests run this loop on the gloo backend)."""
+  reuse its pinned buffers across calls, or a stand-in for the CUDA plumbing (tests run this loop on the gloo backend).
+
+  Several ranks: the broadcasts are issued by a helper thread per rank on a process group of their own
+  (broadcast_group(group), created collectively on first use) — `sweep` is free to run collectives on `group`
+  (sharded_area_batch's all-gather, barriers), but must not use that broadcast group.  A status byte follows every
+  payload: when the source rank fails to produce an image, the other ranks raise RuntimeError at that step instead of
+  waiting for a broadcast that never comes.  (A failure on a NON-source rank cannot be signalled this way: the others
+  find out through the communicator's own timeout.)"""
   import threading
   import torch.distributed as dist
   multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
@@ -184,40 +263,62 @@ def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_ste
       try:
         feed.pack_and_stage(images[k], k & 1)
       except BaseException as e:      # surfaced by the consumer at step k
-        failure.append(e)
+        failure.append((k, e))
         ready[k & 1].release()
         return
       ready[k & 1].release()
+
+  def failed(k):
+    for kk, e in failure:
+      if kk <= k:
+        return e
+    return None
 
   if is_src and (images is None or len(images) < n_steps):
     raise ValueError("the source rank must pass one image per step")
   if multi and hasattr(feed, "staged_tensor"):
     # More than one GPU: a third thread per rank broadcasts the STAGED occupancy bytes of image k+1 on a side stream while
     # the main thread sweeps image k, so that neither the transfer nor the rendezvous of the ranks is on the step's path;
-    # the step itself is then a buffer swap + the sweep, as on one GPU.  Every rank issues the broadcasts in step order.
+    # the step itself is then a buffer swap + the sweep, as on one GPU.  Every rank issues the broadcasts in step order,
+    # on the broadcasters' own communicator.
+    bgroup = broadcast_group(group)
+    gsrc = dist.get_global_rank(group, src) if group is not None else src
+    status = feed if hasattr(feed, "bcast_status") else _HostStatus()
     bready = [threading.Semaphore(0), threading.Semaphore(0)]
+    if hasattr(status, "_st_issued"):
+      status._status_bufs()
+      status._st_issued = [False] * 4      # (a feed is reused across calls)
 
     def broadcaster():
       feed.bind_thread()
       for k in range(n_steps):
         slot = k & 1
+        bad = 0
         if is_src:
           ready[slot].acquire()
-          if stop.is_set() or failure:
-            bready[slot].release()
-            return
-          feed.wait_staged(slot)
+          # a source rank that gives up — its producer failed, or its main thread bailed out — still sends this step's
+          # broadcast, flagged, so that the other ranks raise instead of waiting for it
+          bad = 1 if (failed(k) is not None or stop.is_set()) else 0
+          if not bad:
+            feed.wait_staged(slot)
         else:
           free[slot].acquire()
           if stop.is_set():
             return
         try:
           with feed.bcast_ctx():
-            dist.broadcast(feed.staged_tensor(slot), src=src, group=group)
+            dist.broadcast(feed.staged_tensor(slot), src=gsrc, group=bgroup)     # (the payload of a failed step is whatever the buffer holds)
+            status.bcast_status(k & 3, bad if is_src else None, gsrc, bgroup)
           feed.mark_staged(slot)
         except BaseException as e:
-          failure.append(e)
+          failure.append((k, e))
+          bready[slot].release()
+          return
         bready[slot].release()
+        # the status of this step decides whether another broadcast will come: wait for it (on this thread; the main
+        # thread is sweeping the previous image meanwhile) before issuing the next one
+        if bad or status.read_status(k & 3, wait=True):
+          return
 
     threads = [threading.Thread(target=broadcaster, name="xs3d-volume-bcast")]
     if is_src:
@@ -230,11 +331,17 @@ def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_ste
         if before_step is not None:
           before_step(k)
         bready[k & 1].acquire()
-        if failure:
-          raise failure[0]
+        if failed(k) is not None:
+          raise failed(k)
+        if status.read_status(k & 3, wait=False):
+          raise RuntimeError(f"stream_volumes: the source rank failed to produce image {k}")
         feed.commit_swap(k & 1)
         free[k & 1].release()
-        results.append(sweep(k))
+        r = sweep(k)
+        # the sweep waited (on the device) for broadcast k, so its status byte has arrived by now
+        if status.read_status(k & 3, wait=True):
+          raise RuntimeError(f"stream_volumes: the source rank failed to produce image {k}")
+        results.append(r)
     finally:
       stop.set()
       for sem in free + ready:
@@ -253,8 +360,8 @@ def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_ste
         before_step(k)
       if is_src:
         ready[k & 1].acquire()
-        if failure:
-          raise failure[0]
+        if failed(k) is not None:
+          raise failed(k)
         feed.commit(k & 1)
         free[k & 1].release()
       if multi:

@@ -57,7 +57,10 @@ int xs3d_volume_load_packed(xs3d_volume* vol, const uint8_t* bits, int mem, int 
  * the spare buffers of `slot` (0 or 1) and builds occupancy bytes from it, all on the volume's own upload stream, and
  * returns at once; commit makes the launching stream wait for that work and swaps the spare occupancy bytes in (no
  * kernel, no host synchronisation).  A pipeline stages image k+1 (from any host thread) while image k is being swept;
- * a slot may be staged again once it has been committed.  c_order as in xs3d_volume_load. */
+ * a slot may be staged again once it has been committed; that call first waits (on the host) until the copies of the
+ * slot's previous image have left its host buffer — `bits` must stay untouched until then, i.e. until the next stage
+ * call on the same slot returns, or until a batch that followed commit_staged(slot) has returned.  c_order as in
+ * xs3d_volume_load. */
 int xs3d_volume_stage_packed(xs3d_volume* vol, const uint8_t* bits, int slot, int c_order);
 /* stage for an image that is still bytes (1 per voxel, host memory, pinned or not): packed by the host pool, each eighth
  * of the bit stream copied as soon as it is packed, so that the transfer ends with the packing.  Returns when the image
@@ -114,9 +117,10 @@ int xs3d_volume_timing(xs3d_volume* vol, float ms[12]);
 int xs3d_volume_set_stream(xs3d_volume* vol, void* cuda_stream);
 
 /* ---- drop-in single-call entry points: one per fastxs3d export ------------------------------------- */
-/* fastxs3d.area (fastxs3d.cpp:82-117).  use_persistent_data != 0 reuses the volume uploaded by the
- * last xs3d_set_shape_image() instead of re-uploading binimg (the caller promises it is the same image,
- * the reference's own contract: xs3d/__init__.py:239-241). */
+/* fastxs3d.area (fastxs3d.cpp:82-117).  `binimg` is always the image that is evaluated (it is uploaded on every
+ * call).  use_persistent_data has the reference's meaning (xs3d.hpp:963-971): only scratch is reused — here the
+ * process-wide default volume and its workspaces, which xs3d_set_shape() creates ahead of time — so the flag never
+ * changes a result.  Callers that want to skip the upload keep a resident volume (xs3d_volume_* + xs3d_area_batch). */
 int xs3d_area(const uint8_t* binimg, uint64_t sx, uint64_t sy, uint64_t sz,
               const float pos[3], const float normal[3], const float anisotropy[3],
               int slow_method, int use_persistent_data, float* area, uint8_t* contact);
@@ -140,8 +144,9 @@ int xs3d_projection(const void* labels, uint64_t sx, uint64_t sy, uint64_t sz, i
 int xs3d_projection_batch(xs3d_volume* vol, uint64_t n, const float* pos, const float* normal,
                           const float anisotropy[3], int standardize_basis, float crop_distance,
                           void* out, uint64_t pitch_elems, int64_t* shapes, uint8_t* overflow, int mem);
-/* fastxs3d.set_shape / clear_shape (fastxs3d.cpp:224-225).  set_shape only records the shape (as the
- * reference does); xs3d_set_shape_image additionally makes the image resident for use_persistent_data. */
+/* fastxs3d.set_shape / clear_shape (fastxs3d.cpp:224-225).  set_shape creates the default volume of that shape and
+ * its workspaces (the GPU counterpart of the reference's pre-sized visited buffer); xs3d_set_shape_image also uploads
+ * an image into it (a warm start only: later calls still upload the image they are given); clear_shape frees it. */
 int xs3d_set_shape(uint64_t sx, uint64_t sy, uint64_t sz);
 int xs3d_set_shape_image(const uint8_t* binimg, uint64_t sx, uint64_t sy, uint64_t sz, int c_order);
 int xs3d_clear_shape(void);

@@ -129,6 +129,26 @@ def _stream_worker(rank, world, port, q):
     sfeed = CpuStagedFeed()
     res2 = xdist.stream_volumes(None, images if rank == 0 else None, 5, lambda k: sfeed.cubes.numpy().copy(), feed=sfeed)
     ok2 = len(res2) == 5 and all(np.array_equal(r, e) for r, e in zip(res2, expected)) and sfeed.bound == 1
+    # the sweep may run collectives on the caller's group while the broadcaster thread works (on its own communicator)
+    sfeed2 = CpuStagedFeed()
+
+    def sweep_with_collective(k):
+      t = torch.tensor([float(sfeed2.cubes.sum())], dtype=torch.float64)
+      dist.all_reduce(t)
+      return float(t.item())
+    res3 = xdist.stream_volumes(None, images if rank == 0 else None, 5, sweep_with_collective, feed=sfeed2)
+    ok2 = ok2 and all(r == 2.0 * float(e.sum()) for r, e in zip(res3, expected))
+    # a failure of the source rank while producing image 2 reaches the other rank as an exception at that step
+    sfeed3 = CpuStagedFeed()
+    bad = [images[0], images[1], np.zeros(shape, np.float32), images[3]]
+    done = []
+    try:
+      xdist.stream_volumes(None, bad if rank == 0 else None, 4, done.append, feed=sfeed3)
+      ok2 = False
+    except ValueError:
+      ok2 = ok2 and rank == 0 and done == [0, 1]
+    except RuntimeError:
+      ok2 = ok2 and rank == 1 and done in ([0, 1], [0, 1, 2])
     feed = CpuFeed()
     seen = []
     res = xdist.stream_volumes(None, images if rank == 0 else None, 5, lambda k: feed.cubes.numpy().copy(),

@@ -505,3 +505,118 @@ def test_long_and_wide_sections_all_cta_tiers(xs, oracle):
   for i, (sa, sc) in enumerate(singles):
     assert bits(np.float32(sa)) == bits(oa[i]) and sc == oc[i], i
   assert st["escalated_mid"] > 0 and st["escalated_big"] > 0, st     # the mid tier handed sections on to the wide / big tiers
+
+
+def _sparse_of(img):
+  flat = img.ravel(order="F")
+  idx = np.flatnonzero(flat)
+  return idx.astype(np.uint64), flat[idx]
+
+
+def test_config1_config2_sections_bitwise(xs, oracle):
+  """BASELINE configs 1 and 2 as written: the cross_section contribution image AND the contact bitfield, at full size,
+  voxel by voxel as float32 bit patterns against the oracle — the 500^3 sphere and all three vertices of the 512^3
+  cylinder, two of which sit where the tube leaves the volume (contact != 0)."""
+  from xs3d import synthetic
+  w = [32, 32, 40]
+  sph = synthetic.make_sphere()
+  p, n = [250, 250, 250], [0.01, 0.033, 0.9]
+  oimg, oct_ = oracle.section(sph, p, n, w)
+  oidx, oval = _sparse_of(oimg)
+  del oimg
+  with xs.Volume(sph) as V:
+    idx, val, ct = V.cross_section_sparse(p, n, w)
+  order = np.argsort(idx)
+  assert ct == oct_ and np.array_equal(idx[order], oidx) and np.array_equal(bits(val[order]), bits(oval))
+  del sph
+  cyl, axis = synthetic.make_cylinder()
+  verts = [(256, 256, 256), (496, 352, 316), (12, 158, 195)]          # SURVEY.md §8d; tests/golden: cyl_verts
+  contacts = []
+  with xs.Volume(cyl) as V:
+    for v in verts:
+      oimg, oct_ = oracle.section(cyl, v, axis, w)
+      oidx, oval = _sparse_of(oimg)
+      del oimg
+      idx, val, ct = V.cross_section_sparse(v, axis, w)
+      order = np.argsort(idx)
+      assert ct == oct_, (v, ct, oct_)
+      assert len(oidx) > 0 and np.array_equal(idx[order], oidx) and np.array_equal(bits(val[order]), bits(oval)), v
+      a, c = V.cross_sectional_area(v, axis, w, return_contact=True)
+      oa, oc = oracle.area(cyl, v, axis, w)
+      assert bits(a) == bits(oa) and c == oc, v
+      contacts.append(ct)
+  assert contacts[0] == 0 and contacts[1] != 0 and contacts[2] != 0     # the border vertices do touch the volume faces
+  # the drop-in call (dense image + return_contact) on a border vertex
+  img, ct = xs.cross_section(cyl, verts[1], axis, w, return_contact=True)
+  oimg, oct_ = oracle.section(cyl, verts[1], axis, w)
+  assert ct == oct_ and img.flags.f_contiguous and np.array_equal(img.view(np.uint32), oimg.view(np.uint32))
+
+
+def test_use_persistent_data_evaluates_the_image_it_is_given(xs, oracle):
+  """The reference's persistent data is scratch only (xs3d.hpp:963-971): after set_shape(img_a), a call with img_b of
+  the same shape must answer for img_b."""
+  rng = np.random.default_rng(4)
+  shape = (40, 36, 28)
+  img_a = np.asfortranarray(rng.random(shape) < 0.6)
+  img_b = np.asfortranarray(rng.random(shape) < 0.6)
+  img_a[20, 18, 14] = img_b[20, 18, 14] = True
+  p, n, w = [20, 18, 14], [0.2, -0.5, 0.8], [4, 4, 40]
+  xs.set_shape(img_a)
+  try:
+    got_a = xs.cross_sectional_area(img_a, p, n, w, return_contact=True, use_persistent_data=True)
+    got_b = xs.cross_sectional_area(img_b, p, n, w, return_contact=True, use_persistent_data=True)
+    got_bc = xs.cross_sectional_area(np.ascontiguousarray(img_b), p, n, w, return_contact=True, use_persistent_data=True)
+  finally:
+    xs.clear_shape()
+  oa, ob = oracle.area(img_a, p, n, w), oracle.area(img_b, p, n, w)
+  assert bits(oa[0]) != bits(ob[0])
+  assert bits(got_a[0]) == bits(oa[0]) and got_a[1] == oa[1]
+  assert bits(got_b[0]) == bits(ob[0]) and got_b[1] == ob[1]
+  assert bits(got_bc[0]) == bits(ob[0]) and got_bc[1] == ob[1]
+
+
+def test_batch_argument_validation(xs):
+  """Lengths, dtypes and sizes are checked before raw pointers cross the C ABI."""
+  import torch
+  from xs3d import synthetic
+  vol, verts, tans = synthetic.make_neurite(128, seed=0, n_branches=4)
+  qp, qn = synthetic.draw_queries(verts, tans, 64, seed=1)
+  w = [32, 32, 40]
+  with xs.Volume(vol) as V:
+    with pytest.raises(ValueError):
+      V.cross_sectional_area_batch(qp, qn[:32], w)
+    with pytest.raises(ValueError):
+      V.cross_sectional_area_batch(torch.from_numpy(qp).cuda(), torch.from_numpy(qn[:32]).cuda(), w)
+    with pytest.raises(ValueError):
+      V.sweep(vol, qp, qn[:10], w)
+    for bad in [(np.empty(63, np.float32), np.empty(64, np.uint8)), (np.empty(64, np.float64), np.empty(64, np.uint8)),
+                (np.empty(64, np.float32), np.empty(64, np.int32)), (np.empty(128, np.float32)[::2], np.empty(64, np.uint8)),
+                (np.empty(64, np.float32),)]:
+      with pytest.raises(ValueError):
+        V.cross_sectional_area_batch(qp, qn, w, out=bad)
+      with pytest.raises(ValueError):
+        V.sweep(vol, qp, qn, w, out=bad)
+    out = (np.empty(80, np.float32), np.empty(64, np.uint8))
+    a, c = V.cross_sectional_area_batch(qp, qn, w, return_contact=True, out=out)
+    b = V.cross_sectional_area_batch(qp, qn, w)
+    assert a is out[0] and np.array_equal(bits(a[:64]), bits(b))
+    with pytest.raises(ValueError):
+      V.stage_packed(np.zeros(100, np.uint8), 0)
+    with pytest.raises(ValueError):
+      V.stage_packed(np.zeros(vol.size // 8, np.uint8), 2)
+
+
+def test_multi_gpu_every_rank_against_the_oracle():
+  """N > 1 (skipped on a one-GPU box): torchrun, one process per GPU — the occupancy bytes NCCL-broadcast from rank 0,
+  the query list sharded, results all-gathered; EVERY rank compares the gathered answers, its own shard computed by its
+  own GPU included, with the oracle (tools/dist_check.py), and the same for the sharded slices."""
+  import subprocess, sys, os
+  import torch
+  n = torch.cuda.device_count()
+  if n < 2:
+    pytest.skip("needs >= 2 GPUs")
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 8)}", "--master-addr", "127.0.0.1",
+                      "--master-port", "29631", os.path.join(root, "tools", "dist_check.py")], capture_output=True, text=True, timeout=900)
+  assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+  assert r.stdout.count("bit-identical to the oracle: True") >= min(n, 8), r.stdout[-2000:]
