@@ -1134,6 +1134,9 @@ struct xs3d_volume {
   DevBuf q_pos, q_nrm, q_area, q_contact, lists, counters, slab1, slab2, sec_idx, sec_val, misc;
   DevBuf polys, items, vals, geom, qinfo, slab_mid, keys;
   DevBuf polys2, items2, vals2;                        // record buffers of the second (mid / big tier) pipeline
+  DevBuf slice_bufs[4];                                // batched slices: plan, row summaries, fill meta, host staging
+  void* slice_state = nullptr;                         // xs_slice.cu's host-side plan
+  void (*slice_state_free)(void*) = nullptr;
   uint64_t poly_cap2 = 0, item_cap2 = 0;
   cudaEvent_t evb[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // batch timing, launching stream
   cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};            // batch timing, second stream
@@ -1245,6 +1248,8 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
                      &v->counters, &v->slab1, &v->slab2, &v->sec_idx, &v->sec_val, &v->misc,
                      &v->polys, &v->items, &v->vals, &v->geom, &v->qinfo, &v->slab_mid, &v->keys, &v->polys2, &v->items2, &v->vals2, &v->slab_wide };
   for (DevBuf* b : bufs) b->release();
+  for (DevBuf& b : v->slice_bufs) b.release();
+  if (v->slice_state && v->slice_state_free) v->slice_state_free(v->slice_state);
   if (v->h_counters) cudaFreeHost(v->h_counters);
   if (v->h_bits) cudaFreeHost(v->h_bits);
   delete v;
@@ -2236,7 +2241,7 @@ cudaStream_t xs_stream(const xs3d_volume* v) { return v->stream; }
 int xs_sm_count(const xs3d_volume* v) { return v->sm_count; }
 int xs_fail(int code, const char* msg) { return fail(code, msg); }
 int xs_buf(xs3d_volume* v, int which, size_t bytes, void** p) {
-  DevBuf* b = which == 0 ? &v->sec_idx : (which == 1 ? &v->sec_val : (which == 2 ? &v->misc : &v->counters));
+  DevBuf* b = which >= 4 ? &v->slice_bufs[which - 4] : (which == 0 ? &v->sec_idx : (which == 1 ? &v->sec_val : (which == 2 ? &v->misc : &v->counters)));
   int r = b->ensure(bytes);
   *p = b->p;
   return r;
@@ -2246,6 +2251,8 @@ int xs_default_volume(uint64_t sx, uint64_t sy, uint64_t sz, xs3d_volume** out) 
   return default_volume(sx, sy, sz, out);
 }
 std::mutex& xs_mutex() { return g_mu; }
+int xs_set_device(const xs3d_volume* v) { CK(cudaSetDevice(v->device)); return XS3D_OK; }
+void** xs_slice_state_slot(xs3d_volume* v, void (*free_fn)(void*)) { v->slice_state_free = free_fn; return &v->slice_state; }
 void xs_labels(xs3d_volume* v, void** p, int* itemsize, int* c_order, bool* loaded) {
   *p = v->labels.p; *itemsize = v->itemsize; *c_order = v->labels_c_order; *loaded = v->labels_loaded;
 }
@@ -2254,8 +2261,10 @@ int xs_labels_set(xs3d_volume* v, const void* labels, int itemsize, int mem, int
   v->itemsize = itemsize; v->labels_c_order = c_order;
   if (bytes == 0) { v->labels_loaded = true; return XS3D_OK; }
   RET(v->labels.ensure(bytes + 64));
-  CK(cudaMemcpyAsync(v->labels.p, labels, bytes, mem == XS3D_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, v->stream));
-  CK(cudaStreamSynchronize(v->stream));
+  if (labels) {            // (null: allocate only — the caller fills the buffer, xs3d_volume_labels_buffer)
+    CK(cudaMemcpyAsync(v->labels.p, labels, bytes, mem == XS3D_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, v->stream));
+    CK(cudaStreamSynchronize(v->stream));
+  }
   v->labels_loaded = true;
   return XS3D_OK;
 }

@@ -11,13 +11,17 @@ xs::VolView xs_view(const xs3d_volume* v);
 cudaStream_t xs_stream(const xs3d_volume* v);
 int xs_sm_count(const xs3d_volume* v);
 int xs_fail(int code, const char* msg);
-// growable device buffers owned by the volume: 0 sparse idx, 1 sparse val, 2 misc, 3 counters
+// growable device buffers owned by the volume: 0 sparse idx, 1 sparse val, 2 misc, 3 counters, 4-7 batched slices
+// (plan, row summaries, fill meta, host staging)
 int xs_buf(xs3d_volume* v, int which, size_t bytes, void** p);
 uint32_t* xs_pinned(xs3d_volume* v);   // 256 bytes of pinned host memory
 int xs_default_volume(uint64_t sx, uint64_t sy, uint64_t sz, xs3d_volume** out);
 std::mutex& xs_mutex();
 void xs_labels(xs3d_volume* v, void** p, int* itemsize, int* c_order, bool* loaded);
 int xs_labels_set(xs3d_volume* v, const void* labels, int itemsize, int mem, int c_order);
+int xs_set_device(const xs3d_volume* v);
+// opaque per-volume state of the batched slice path (freed with `free_fn` when the volume is destroyed)
+void** xs_slice_state_slot(xs3d_volume* v, void (*free_fn)(void*));
 
 #define XS_CK(call)                                                                                  \
   do {                                                                                               \

@@ -3,10 +3,10 @@
 // (xs3d.hpp:1473-1624, fastxs3d.cpp:119-216).
 //
 // Two execution shapes:
-//   * slice_cta_kernel   : one CTA per plane, window <= 64x64 cells (then <= 256x256 for the planes that pass
-//     flags), everything in shared memory — the batched "10k cropped planes" path (BASELINE config 4);
-//   * big path           : whole-GPU kernels per stage for windows up to the full lattice
-//     (un-cropped planes, up to ~7000^2 cells): valid -> rows -> scan -> gather.
+//   * batched path (xs3d_projection_plan / _fill / _batch): n planes of any size at once, no bitmap at all — a warp
+//     per window row for the shapes, a warp per 512 output elements for the gather (BASELINE configs 4 and 5);
+//   * big path (slice_big): whole-GPU kernels per stage with a dense bitmap — valid -> rows -> scan -> gather — for
+//     the single-call drop-in and for the planes that need the exact iterative fill.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -128,133 +128,194 @@ __global__ void __launch_bounds__(256) slice_gather_kernel(SliceCtx s, const uin
 }
 
 // ------------------------------------------------------------------------------------------------
-// CTA path: one CTA per plane, window <= 64 x 64, then <= 256 x 256
+// batched path: PLAN (shapes of n planes) + FILL (ragged or fixed-pitch gather)
+//
+// Neither step stores a validity bitmap.  PLAN: one thread per plane sets up its SliceCtx; one WARP per lattice row of
+// every plane's window evaluates the row's cells (ballots) into a RowRuns summary — first / last valid column and the
+// number of runs —; one warp per plane then finds the rows the reference's 4-connected fill reaches: the maximal range
+// of consecutive rows around the centre row whose runs overlap column-wise (every link between two consecutive rows is
+// an independent test, so the lanes test 32 links at a time).  When every reached row is a single run, the reached
+// cells are exactly the valid cells of those rows, so FILL needs no mask either: one warp per 512 output elements
+// evaluates slice_cell for its cells and gathers the labels.  A reachable row with more than one run (float noise on a
+// row that grazes a volume face) flags the plane for the exact iterative fill (slice_big), one plane at a time.
+// Work scales with the planes' windows: a 7 x 7 cropped slice costs a dozen row-warps, an un-cropped plane through a
+// 1024^3 volume ~1800 row-warps of ~56 ballots and a gather of the bounding box.
 // ------------------------------------------------------------------------------------------------
-constexpr int SMALL_W = 64, MED_W = 256;
+struct PlanRec {
+  int x0, x1, y0, y1;   // bounding box of the reached cells, window coordinates (x0 > x1: nothing reached)
+  int flags;            // PLAN_*
+};
+enum { PLAN_FALLBACK = 1, PLAN_INACTIVE = 2, PLAN_NOTHING = 4 };
 
-struct SliceBatchArgs {
+struct SlicePlanArgs {
   const float* pos; const float* nrm;
   float wx, wy, wz;
   int positive; float crop;
   int sx, sy, sz;
-  const void* labels; int itemsize; int c_order;
-  void* out; unsigned long long pitch_elems;
-  long long* shapes; uint8_t* overflow;   // overflow: 1 = cut-out larger than pitch, 2 = window too large for this kernel
   uint32_t n;
 };
 
-// One CTA per plane, window <= W x W cells, everything in shared memory.  W = 64 (128 threads): the batched "10k
-// cropped planes" shape; W = 256 (256 threads): the planes the first pass flags as too wide (overflow == 2).
-template <int W, int THREADS>
-__global__ void __launch_bounds__(THREADS) slice_cta_kernel(SliceBatchArgs a, int only_flagged) {
-  constexpr int WORDS = W / 32;                 // bitmap words per window row
-  constexpr int NW = W * WORDS;                 // words in the window
-  constexpr int K = (NW + THREADS - 1) / THREADS;
-  __shared__ uint32_t V[NW], R[NW];
-  __shared__ RowRuns rows[W];
-  __shared__ SliceResult res;
-  __shared__ int changed;
-  for (uint32_t q = blockIdx.x; q < a.n; q += gridDim.x) {
-    if (only_flagged && a.overflow[q] != 2) continue;
-    SliceCtx s;
-    slice_init(s, a.sx, a.sy, a.sz, mk(a.pos[3 * q], a.pos[3 * q + 1], a.pos[3 * q + 2]), mk(a.nrm[3 * q], a.nrm[3 * q + 1], a.nrm[3 * q + 2]),
-               mk(a.wx, a.wy, a.wz), a.positive != 0, a.crop);
-    char* outq = reinterpret_cast<char*>(a.out) + (size_t)q * a.pitch_elems * a.itemsize;
-    __syncthreads();
-    if (!s.active) {
-      // bbox stays at its initial value: 1x1 cut-out holding 0 (fastxs3d.cpp:179-183)
-      if (threadIdx.x == 0) {
-        a.shapes[2 * q] = 1; a.shapes[2 * q + 1] = 1; a.overflow[q] = (a.pitch_elems < 1) ? 1 : 0;
-        if (a.pitch_elems >= 1) zero_label(outq, 0, a.itemsize);
-      }
-      continue;
-    }
-    if (s.ww > W || s.wh > W) {
-      if (threadIdx.x == 0) { a.shapes[2 * q] = -1; a.shapes[2 * q + 1] = -1; a.overflow[q] = 2; }
-      continue;
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int wi = warp; wi < NW; wi += THREADS / 32) {
-      const int row = wi / WORDS, col = (wi % WORDS) * 32 + lane;
-      const bool ok = (row < s.wh) && (col < s.ww) && slice_cell(s, s.wx0 + col, s.wy0 + row, false, nullptr);
+__global__ void __launch_bounds__(256) slice_plan_init_kernel(SlicePlanArgs a, SliceCtx* __restrict__ ctx, uint32_t* __restrict__ nrows) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.n) return;
+  SliceCtx s;
+  slice_init(s, a.sx, a.sy, a.sz, mk(a.pos[3 * q], a.pos[3 * q + 1], a.pos[3 * q + 2]), mk(a.nrm[3 * q], a.nrm[3 * q + 1], a.nrm[3 * q + 2]),
+             mk(a.wx, a.wy, a.wz), a.positive != 0, a.crop);
+  ctx[q] = s;
+  nrows[q] = s.active ? (uint32_t)s.wh : 0u;
+}
+
+// exclusive prefix sums of `in` (n values) into `out` (n + 1 values), one CTA
+__global__ void __launch_bounds__(1024) scan_u32_kernel(const uint32_t* __restrict__ in, uint32_t n, unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long part[1024];
+  const uint32_t per = (n + 1023u) / 1024u;
+  const uint32_t lo = min(n, threadIdx.x * per), hi = min(n, lo + per);
+  unsigned long long s = 0;
+  for (uint32_t i = lo; i < hi; i++) s += in[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int i = 0; i < 1024; i++) { const unsigned long long t = part[i]; part[i] = run; run += t; }
+    out[n] = run;
+  }
+  __syncthreads();
+  s = part[threadIdx.x];
+  for (uint32_t i = lo; i < hi; i++) { out[i] = s; s += in[i]; }
+}
+
+// largest i in [0, n) with off[i] <= x  (off ascending, off[0] = 0 <= x < off[n])
+__device__ __forceinline__ uint32_t find_owner(const unsigned long long* __restrict__ off, uint32_t n, unsigned long long x) {
+  uint32_t lo = 0, hi = n;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(off + mid) <= x) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// one warp per window row of every plane: the row's RowRuns without storing its bitmap
+__global__ void __launch_bounds__(256) slice_plan_rows_kernel(const SliceCtx* __restrict__ ctx, const unsigned long long* __restrict__ row_off, uint32_t n,
+                                                              RowRuns* __restrict__ rows) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long total = row_off[n];
+  const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long r = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < total; r += nwarps) {
+    const uint32_t q = find_owner(row_off, n, r);
+    const SliceCtx* sp = ctx + q;
+    SliceCtx s = *sp;
+    const int row = (int)(r - row_off[q]);
+    int a = 0x7fffffff, b = -1, runs = 0;
+    uint32_t carry = 0u;
+    for (int x0 = 0; x0 < s.ww; x0 += 32) {
+      const int col = x0 + lane;
+      const bool ok = (col < s.ww) && slice_cell(s, s.wx0 + col, s.wy0 + row, false, nullptr);
       const uint32_t w = __ballot_sync(0xffffffffu, ok);
-      if (lane == 0) V[wi] = w;
-    }
-    __syncthreads();
-    for (int row = threadIdx.x; row < W; row += THREADS) rows[row] = row_runs(V + WORDS * row, WORDS);
-    __syncthreads();
-    const int cx = (int)(s.c - s.wx0), cy = (int)(s.c - s.wy0);
-    if (threadIdx.x == 0) res = scan_rows(rows, s.wh, cx, cy);
-    __syncthreads();
-    const uint32_t* mask = V;
-    if (res.fallback) {
-      // exact fixpoint fill in shared memory
-      for (int wi = threadIdx.x; wi < NW; wi += THREADS) R[wi] = 0u;
-      __syncthreads();
-      if (threadIdx.x == 0) R[cy * WORDS + (cx >> 5)] = V[cy * WORDS + (cx >> 5)] & (1u << (cx & 31));
-      do {
-        __syncthreads();
-        if (threadIdx.x == 0) changed = 0;
-        __syncthreads();
-        uint32_t gnew[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-          const int wi = threadIdx.x + k * THREADS;
-          gnew[k] = 0u;
-          if (wi >= NW) continue;
-          const int row = wi / WORDS, col = wi % WORDS;
-          const uint32_t v = V[wi], old = R[wi];
-          uint32_t seeds = old;
-          if (row > 0) seeds |= R[wi - WORDS];
-          if (row + 1 < W) seeds |= R[wi + WORDS];
-          if (col > 0) seeds |= R[wi - 1] >> 31;
-          if (col + 1 < WORDS) seeds |= R[wi + 1] << 31;
-          seeds &= v;
-          uint32_t g = seeds, p = v;
-          g |= p & (g << 1); p &= p << 1; g |= p & (g << 2); p &= p << 2; g |= p & (g << 4); p &= p << 4;
-          g |= p & (g << 8); p &= p << 8; g |= p & (g << 16);
-          p = v;
-          g |= p & (g >> 1); p &= p >> 1; g |= p & (g >> 2); p &= p >> 2; g |= p & (g >> 4); p &= p >> 4;
-          g |= p & (g >> 8); p &= p >> 8; g |= p & (g >> 16);
-          gnew[k] = g;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < K; k++) {
-          const int wi = threadIdx.x + k * THREADS;
-          if (wi < NW && gnew[k] != R[wi]) { R[wi] = gnew[k]; changed = 1; }
-        }
-        __syncthreads();
-      } while (changed);
-      for (int row = threadIdx.x; row < W; row += THREADS) rows[row] = row_runs(R + WORDS * row, WORDS);
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        SliceResult r;
-        r.y0 = 0x7fffffff; r.y1 = -1; r.x0 = 0x7fffffff; r.x1 = -1; r.fallback = 1;
-        for (int y = 0; y < s.wh; y++) {
-          if (rows[y].runs == 0) continue;
-          if (y < r.y0) r.y0 = y;
-          r.y1 = y;
-          if (rows[y].a < r.x0) r.x0 = rows[y].a;
-          if (rows[y].b > r.x1) r.x1 = rows[y].b;
-        }
-        res = r;
+      if (w) {
+        runs += __popc(w & ~((w << 1) | carry));
+        if (a == 0x7fffffff) a = x0 + __ffs(w) - 1;
+        b = x0 + 31 - __clz(w);
       }
-      __syncthreads();
-      mask = R;
+      carry = w >> 31;
     }
-    SliceResult r = res;
-    if (r.y0 > r.y1) { r.x0 = r.x1 = cx; r.y0 = r.y1 = cy; }   // nothing reached: bbox stays on the centre cell
-    const int nx = r.x1 - r.x0 + 1, ny = r.y1 - r.y0 + 1;
-    const unsigned long long total = (unsigned long long)nx * ny;
-    if (threadIdx.x == 0) { a.shapes[2 * q] = nx; a.shapes[2 * q + 1] = ny; a.overflow[q] = total > a.pitch_elems ? 1 : 0; }
-    if (total > a.pitch_elems) continue;
-    for (int i = threadIdx.x; i < (int)total; i += THREADS) {
-      const int x = r.x0 + i % nx, y = r.y0 + i / nx;
-      const bool on = (res.y0 <= res.y1) && ((mask[y * WORDS + (x >> 5)] >> (x & 31)) & 1u) && (res.fallback || (y >= res.y0 && y <= res.y1));
+    if (lane == 0) { RowRuns rr; rr.a = a; rr.b = b; rr.runs = runs; rows[r] = rr; }
+  }
+}
+
+// one warp per plane: the reached row range and its column bounding box (scan_rows, 32 rows at a time)
+__global__ void __launch_bounds__(256) slice_plan_scan_kernel(const SliceCtx* __restrict__ ctx, const unsigned long long* __restrict__ row_off, uint32_t n,
+                                                              const RowRuns* __restrict__ rows_all, PlanRec* __restrict__ plan) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < n; q += nwarps) {
+    const SliceCtx* s = ctx + q;
+    PlanRec pr;
+    pr.x0 = 1; pr.x1 = 0; pr.y0 = 1; pr.y1 = 0; pr.flags = 0;
+    if (!s->active) {
+      pr.flags = PLAN_INACTIVE;
+      if (lane == 0) plan[q] = pr;
+      continue;
+    }
+    const RowRuns* rows = rows_all + row_off[q];
+    const int nrows = s->wh;
+    const int cx = (int)(s->c - s->wx0), cy = (int)(s->c - s->wy0);
+    bool dead = cy < 0 || cy >= nrows;
+    RowRuns c; c.a = 0; c.b = -1; c.runs = 0;
+    if (!dead) c = rows[cy];
+    if (dead || c.runs == 0 || cx < c.a || cx > c.b) {            // the centre cell itself is not valid
+      pr.flags = PLAN_NOTHING;
+      if (lane == 0) plan[q] = pr;
+      continue;
+    }
+    bool fallback = c.runs > 1;
+    int lo = c.a, hi = c.b, y0 = cy, y1 = cy;
+    for (int dir = -1; dir <= 1 && !fallback; dir += 2) {
+      // link k (k = 1, 2, ...): row cy + dir*k is non-empty and overlaps row cy + dir*(k-1); the fill advances while links hold
+      int k0 = 1;
+      for (;;) {
+        const int k = k0 + lane;
+        const int y = cy + dir * k;
+        bool link = false, multi = false;
+        int qa = 0x7fffffff, qb = -1;
+        if (y >= 0 && y < nrows) {
+          const RowRuns q1 = rows[y], p1 = rows[y - dir];
+          link = q1.runs != 0 && !(q1.a > p1.b || q1.b < p1.a);
+          multi = q1.runs > 1;
+          qa = q1.a; qb = q1.b;
+        }
+        const uint32_t broken = __ballot_sync(0xffffffffu, !link);
+        const int good = broken ? (__ffs(broken) - 1) : 32;        // links k0 .. k0 + good - 1 hold
+        const bool mine = lane < good;
+        if (__ballot_sync(0xffffffffu, mine && multi)) { fallback = true; break; }
+        const int ma = __reduce_min_sync(0xffffffffu, mine ? qa : 0x7fffffff);
+        const int mb = __reduce_max_sync(0xffffffffu, mine ? qb : -1);
+        if (good > 0) {
+          lo = min(lo, ma); hi = max(hi, mb);
+          if (dir < 0) y0 = cy - (k0 + good - 1); else y1 = cy + (k0 + good - 1);
+        }
+        if (good < 32) break;
+        k0 += 32;
+      }
+    }
+    pr.x0 = lo; pr.x1 = hi; pr.y0 = y0; pr.y1 = y1;
+    pr.flags = fallback ? PLAN_FALLBACK : 0;
+    if (lane == 0) plan[q] = pr;
+  }
+}
+
+// FILL: one warp per unit of FILL_UNIT output elements of one plane.  unit_off[i] = first unit of plane first + i;
+// plane i's cut-out (F order [nx][ny]) goes to out + dst_off[i] elements.  Planes flagged skip (exact-fill fallback,
+// or larger than the caller's pitch) are left alone.
+constexpr int FILL_UNIT = 512;
+__global__ void __launch_bounds__(256) slice_fill_kernel(const SliceCtx* __restrict__ ctx, const PlanRec* __restrict__ plan, const unsigned long long* __restrict__ unit_off,
+                                                         const unsigned long long* __restrict__ dst_off, const uint8_t* __restrict__ skip, uint32_t count,
+                                                         const void* __restrict__ labels, int itemsize, int c_order, void* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned long long total = unit_off[count];
+  const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  for (unsigned long long u = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; u < total; u += nwarps) {
+    const uint32_t i = find_owner(unit_off, count, u);
+    if (skip[i]) continue;
+    const PlanRec pr = plan[i];
+    const unsigned long long base = __ldg(dst_off + i);
+    if (pr.flags & (PLAN_INACTIVE | PLAN_NOTHING)) {              // 1 x 1 cut-out holding 0 (fastxs3d.cpp:179-183)
+      if (lane == 0) zero_label(out, base, itemsize);
+      continue;
+    }
+    const SliceCtx s = ctx[i];
+    const int nx = pr.x1 - pr.x0 + 1, ny = pr.y1 - pr.y0 + 1;
+    const unsigned long long cells = (unsigned long long)nx * ny;
+    const unsigned long long e0 = (u - unit_off[i]) * FILL_UNIT;
+#pragma unroll 4
+    for (int j = 0; j < FILL_UNIT / 32; j++) {
+      const unsigned long long e = e0 + (unsigned long long)(j * 32 + lane);
+      if (e >= cells) break;
+      int yy, xx;
+      if (cells <= 0xffffffffull) { yy = (int)((uint32_t)e / (uint32_t)nx); xx = (int)((uint32_t)e - (uint32_t)yy * (uint32_t)nx); }
+      else { yy = (int)(e / (unsigned long long)nx); xx = (int)(e - (unsigned long long)yy * nx); }
       size_t loc;
-      if (on && slice_cell(s, s.wx0 + x, s.wy0 + y, a.c_order != 0, &loc)) copy_label(outq, i, a.labels, loc, a.itemsize);
-      else zero_label(outq, i, a.itemsize);
+      if (slice_cell(s, s.wx0 + pr.x0 + xx, s.wy0 + pr.y0 + yy, c_order != 0, &loc)) copy_label(out, base + e, labels, loc, itemsize);
+      else zero_label(out, base + e, itemsize);
     }
   }
 }
@@ -266,6 +327,23 @@ extern "C" int xs3d_volume_load_labels(xs3d_volume* v, const void* labels, int i
   if (!v) return xs_fail(XS3D_ERR_ARG, "null volume");
   if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8) return xs_fail(XS3D_ERR_ARG, "label itemsize must be 1, 2, 4 or 8");
   return xs_labels_set(v, labels, itemsize, mem, c_order);
+}
+
+// The device buffer that holds the label volume, (re)allocated for `itemsize` / `c_order` without uploading anything —
+// for a host layer that fills it itself (NCCL broadcast from the rank that uploaded the labels, xs3d.dist.broadcast_labels).
+// The labels count as loaded afterwards: the caller writes the buffer before the next slice / select_label call.
+extern "C" int xs3d_volume_labels_buffer(xs3d_volume* v, int itemsize, int c_order, void** device_ptr, uint64_t* bytes) {
+  if (!v) return xs_fail(XS3D_ERR_ARG, "null volume");
+  if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8) return xs_fail(XS3D_ERR_ARG, "label itemsize must be 1, 2, 4 or 8");
+  XS_RET(xs_set_device(v));
+  XS_RET(xs_labels_set(v, nullptr, itemsize, XS3D_DEVICE, c_order));
+  void* p; int is, co; bool loaded;
+  xs_labels(v, &p, &is, &co, &loaded);
+  uint64_t dims[3];
+  XS_RET(xs3d_volume_shape(v, dims));
+  *device_ptr = p;
+  *bytes = dims[0] * dims[1] * dims[2] * (uint64_t)itemsize;
+  return XS3D_OK;
 }
 
 // One plane through the big path.  Leaves the cut-out on the device in buffer 0 (sec_idx) and returns its shape.
@@ -397,67 +475,211 @@ extern "C" int xs3d_projection(const void* labels, uint64_t sx, uint64_t sy, uin
   return XS3D_OK;
 }
 
-extern "C" int xs3d_projection_batch(xs3d_volume* v, uint64_t n, const float* pos, const float* normal, const float anisotropy[3],
-                                     int standardize_basis, float crop_distance, void* out, uint64_t pitch_elems,
-                                     int64_t* shapes, uint8_t* overflow, int mem) {
+// ---- batched planes: plan + fill ---------------------------------------------------------------------
+struct SliceState {        // what xs3d_projection_plan leaves behind for xs3d_projection_fill (host side; device side: buffers 4-6)
+  uint64_t n = 0;
+  bool empty = false;      // crop == 0: every cut-out is 0 x 0
+  std::vector<PlanRec> plan;
+  std::vector<int64_t> shapes;       // 2 per plane
+  std::vector<uint64_t> offsets;     // n + 1, elements
+  std::vector<float> pos, nrm;       // host copies (the exact-fill fallback runs plane by plane)
+  float w[3] = {1, 1, 1}, crop = 0;
+  int positive = 0;
+};
+static void slice_state_free(void* p) { delete (SliceState*)p; }
+
+static SliceState* slice_state(xs3d_volume* v) {
+  void** slot = xs_slice_state_slot(v, slice_state_free);
+  if (!*slot) *slot = new SliceState();
+  return (SliceState*)*slot;
+}
+
+// device layout of buffer 4 after a plan of n planes
+struct PlanBufs { SliceCtx* ctx; uint32_t* nrows; unsigned long long* row_off; PlanRec* plan; float* pos; float* nrm; };
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static int plan_bufs(xs3d_volume* v, uint64_t n, PlanBufs* b) {
+  const size_t s_ctx = align256(n * sizeof(SliceCtx)), s_nr = align256(n * 4), s_ro = align256((n + 1) * 8), s_pl = align256(n * sizeof(PlanRec)), s_q = align256(n * 12);
+  char* p;
+  XS_RET(xs_buf(v, 4, s_ctx + s_nr + s_ro + s_pl + 2 * s_q + 256, (void**)&p));
+  b->ctx = (SliceCtx*)p; p += s_ctx;
+  b->nrows = (uint32_t*)p; p += s_nr;
+  b->row_off = (unsigned long long*)p; p += s_ro;
+  b->plan = (PlanRec*)p; p += s_pl;
+  b->pos = (float*)p; p += s_q;
+  b->nrm = (float*)p;
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_projection_plan(xs3d_volume* v, uint64_t n, const float* pos, const float* normal, const float anisotropy[3],
+                                    int standardize_basis, float crop_distance, int mem, int64_t* shapes, uint64_t* offsets) {
   if (!v) return xs_fail(XS3D_ERR_ARG, "null volume");
   void* labels; int itemsize, c_order; bool loaded;
   xs_labels(v, &labels, &itemsize, &c_order, &loaded);
   if (!loaded) return xs_fail(XS3D_ERR_ARG, "volume has no labels loaded");
+  if (n >= 0x7fffffffull) return xs_fail(XS3D_ERR_ARG, "too many planes in one batch");
+  if (n && (!pos || !normal || !anisotropy || !shapes || !offsets)) return xs_fail(XS3D_ERR_ARG, "null argument");
+  if (!(crop_distance >= 0.0f)) return xs_fail(XS3D_ERR_ARG, "crop distance must be >= 0");
+  XS_RET(xs_set_device(v));
+  SliceState* st = slice_state(v);
+  st->n = n; st->empty = false;
+  st->plan.clear(); st->shapes.assign(2 * n, 0); st->offsets.assign(n + 1, 0);
+  if (offsets) offsets[0] = 0;
   if (n == 0) return XS3D_OK;
-  uint64_t dims[3];
-  XS_RET(xs3d_volume_shape(v, dims));
-  cudaStream_t st = xs_stream(v);
-  if (crop_distance == 0.0f) {
-    if (mem == XS3D_HOST) { memset(shapes, 0, n * 16); memset(overflow, 0, n); }
-    else { XS_CK(cudaMemsetAsync(shapes, 0, n * 16, st)); XS_CK(cudaMemsetAsync(overflow, 0, n, st)); XS_CK(cudaStreamSynchronize(st)); }
+  if (crop_distance == 0.0f) {                                   // fastxs3d.cpp:160-162
+    st->empty = true;
+    memset(shapes, 0, n * 16); memset(offsets, 0, (n + 1) * 8);
     return XS3D_OK;
   }
-  // staging for host callers
-  const size_t out_bytes = (size_t)n * pitch_elems * itemsize;
-  char* stage = nullptr;
-  const float *d_pos = pos, *d_nrm = normal;
-  void* d_out = out; long long* d_shapes = (long long*)shapes; uint8_t* d_over = overflow;
+  uint64_t dims[3];
+  XS_RET(xs3d_volume_shape(v, dims));
+  cudaStream_t sm = xs_stream(v);
+  PlanBufs b;
+  XS_RET(plan_bufs(v, n, &b));
+  st->pos.resize(3 * n); st->nrm.resize(3 * n);
   if (mem == XS3D_HOST) {
-    XS_RET(xs_buf(v, 1, n * 24 + n * 16 + n + out_bytes + 1024, (void**)&stage));
-    XS_CK(cudaMemcpyAsync(stage, pos, n * 12, cudaMemcpyHostToDevice, st));
-    XS_CK(cudaMemcpyAsync(stage + n * 12, normal, n * 12, cudaMemcpyHostToDevice, st));
-    d_pos = (const float*)stage; d_nrm = (const float*)(stage + n * 12);
-    d_shapes = (long long*)(stage + n * 24);
-    d_out = stage + n * 24 + n * 16;
-    d_over = (uint8_t*)(stage + n * 24 + n * 16 + ((out_bytes + 15) / 16) * 16);
-  }
-  SliceBatchArgs a;
-  a.pos = d_pos; a.nrm = d_nrm; a.wx = anisotropy[0]; a.wy = anisotropy[1]; a.wz = anisotropy[2];
-  a.positive = standardize_basis; a.crop = crop_distance;
-  a.sx = (int)dims[0]; a.sy = (int)dims[1]; a.sz = (int)dims[2];
-  a.labels = labels; a.itemsize = itemsize; a.c_order = c_order;
-  a.out = d_out; a.pitch_elems = pitch_elems; a.shapes = d_shapes; a.overflow = d_over; a.n = (uint32_t)n;
-  const int grid = (int)std::min<uint64_t>(n, (uint64_t)xs_sm_count(v) * 8);
-  slice_cta_kernel<SMALL_W, 128><<<grid, 128, 0, st>>>(a, 0);
-  XS_CK(cudaGetLastError());
-  slice_cta_kernel<MED_W, 256><<<grid, 256, 0, st>>>(a, 1);      // the planes flagged as wider than 64 cells, up to 256
-  XS_CK(cudaGetLastError());
-  if (mem == XS3D_HOST) {
-    XS_CK(cudaMemcpyAsync(shapes, d_shapes, n * 16, cudaMemcpyDeviceToHost, st));
-    XS_CK(cudaMemcpyAsync(overflow, d_over, n, cudaMemcpyDeviceToHost, st));
-    if (out_bytes) XS_CK(cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, st));
-    XS_CK(cudaStreamSynchronize(st));
-    // planes whose window does not fit the one-CTA kernel go through the whole-GPU path one by one
-    for (uint64_t q = 0; q < n; q++) {
-      if (overflow[q] != 2) continue;
-      int64_t shp[2]; void* d_cut;
-      XS_RET(slice_big(v, pos + 3 * q, normal + 3 * q, anisotropy, standardize_basis, crop_distance, shp, &d_cut));
-      shapes[2 * q] = shp[0]; shapes[2 * q + 1] = shp[1];
-      const uint64_t total = (uint64_t)shp[0] * shp[1];
-      overflow[q] = total > pitch_elems ? 1 : 0;
-      if (total <= pitch_elems) {
-        XS_CK(cudaMemcpyAsync((char*)out + (size_t)q * pitch_elems * itemsize, d_cut, total * itemsize, cudaMemcpyDeviceToHost, st));
-        XS_CK(cudaStreamSynchronize(st));
-      }
-    }
+    memcpy(st->pos.data(), pos, n * 12); memcpy(st->nrm.data(), normal, n * 12);
+    XS_CK(cudaMemcpyAsync(b.pos, pos, n * 12, cudaMemcpyHostToDevice, sm));
+    XS_CK(cudaMemcpyAsync(b.nrm, normal, n * 12, cudaMemcpyHostToDevice, sm));
   } else {
-    XS_CK(cudaStreamSynchronize(st));
+    XS_CK(cudaMemcpyAsync(b.pos, pos, n * 12, cudaMemcpyDeviceToDevice, sm));
+    XS_CK(cudaMemcpyAsync(b.nrm, normal, n * 12, cudaMemcpyDeviceToDevice, sm));
+    XS_CK(cudaMemcpyAsync(st->pos.data(), pos, n * 12, cudaMemcpyDeviceToHost, sm));
+    XS_CK(cudaMemcpyAsync(st->nrm.data(), normal, n * 12, cudaMemcpyDeviceToHost, sm));
   }
+  memcpy(st->w, anisotropy, 12); st->crop = crop_distance; st->positive = standardize_basis;
+  SlicePlanArgs a;
+  a.pos = b.pos; a.nrm = b.nrm; a.wx = anisotropy[0]; a.wy = anisotropy[1]; a.wz = anisotropy[2];
+  a.positive = standardize_basis; a.crop = crop_distance;
+  a.sx = (int)dims[0]; a.sy = (int)dims[1]; a.sz = (int)dims[2]; a.n = (uint32_t)n;
+  slice_plan_init_kernel<<<(unsigned)((n + 255) / 256), 256, 0, sm>>>(a, b.ctx, b.nrows);
+  scan_u32_kernel<<<1, 1024, 0, sm>>>(b.nrows, (uint32_t)n, b.row_off);
+  XS_CK(cudaGetLastError());
+  unsigned long long* h_total = (unsigned long long*)xs_pinned(v);
+  XS_CK(cudaMemcpyAsync(h_total, b.row_off + n, 8, cudaMemcpyDeviceToHost, sm));
+  XS_CK(cudaStreamSynchronize(sm));
+  const unsigned long long total_rows = *h_total;
+  RowRuns* rows;
+  XS_RET(xs_buf(v, 5, (size_t)total_rows * sizeof(RowRuns) + 256, (void**)&rows));
+  const int sms = xs_sm_count(v);
+  if (total_rows) {
+    const unsigned rgrid = (unsigned)std::min<unsigned long long>((total_rows + 7) / 8, (unsigned long long)sms * 16);
+    slice_plan_rows_kernel<<<rgrid, 256, 0, sm>>>(b.ctx, b.row_off, (uint32_t)n, rows);
+  }
+  const unsigned sgrid = (unsigned)std::min<uint64_t>((n + 7) / 8, (uint64_t)sms * 16);
+  slice_plan_scan_kernel<<<sgrid, 256, 0, sm>>>(b.ctx, b.row_off, (uint32_t)n, rows, b.plan);
+  XS_CK(cudaGetLastError());
+  st->plan.resize(n);
+  XS_CK(cudaMemcpyAsync(st->plan.data(), b.plan, n * sizeof(PlanRec), cudaMemcpyDeviceToHost, sm));
+  XS_CK(cudaStreamSynchronize(sm));
+  uint64_t off = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    const PlanRec& pr = st->plan[i];
+    int64_t nx = 1, ny = 1;
+    if (pr.flags & PLAN_FALLBACK) {
+      int64_t shp[2]; void* d_cut;
+      XS_RET(slice_big(v, st->pos.data() + 3 * i, st->nrm.data() + 3 * i, anisotropy, standardize_basis, crop_distance, shp, &d_cut));
+      nx = shp[0]; ny = shp[1];
+    } else if (!(pr.flags & (PLAN_INACTIVE | PLAN_NOTHING))) {
+      nx = pr.x1 - pr.x0 + 1; ny = pr.y1 - pr.y0 + 1;
+    }
+    st->shapes[2 * i] = nx; st->shapes[2 * i + 1] = ny;
+    st->offsets[i] = off;
+    off += (uint64_t)nx * (uint64_t)ny;
+  }
+  st->offsets[n] = off;
+  memcpy(shapes, st->shapes.data(), n * 16);
+  memcpy(offsets, st->offsets.data(), (n + 1) * 8);
   return XS3D_OK;
+}
+
+// gather planes [first, first + count) of the last plan; plane i goes to element dst[i - first] of `out`, planes with
+// skip[i - first] != 0 are left out.  `out_elems`: size of the destination in elements (for the host staging copy).
+static int fill_impl(xs3d_volume* v, uint64_t first, uint64_t count, const std::vector<uint64_t>& dst, const std::vector<uint8_t>& skip_in,
+                     uint64_t out_elems, void* out, int mem) {
+  SliceState* st = slice_state(v);
+  void* labels; int itemsize, c_order; bool loaded;
+  xs_labels(v, &labels, &itemsize, &c_order, &loaded);
+  if (!loaded) return xs_fail(XS3D_ERR_ARG, "volume has no labels loaded");
+  if (count == 0 || out_elems == 0) return XS3D_OK;
+  cudaStream_t sm = xs_stream(v);
+  PlanBufs b;
+  XS_RET(plan_bufs(v, st->n, &b));
+  // per-plane meta for the kernel: unit offsets, destination offsets, skip flags
+  std::vector<unsigned long long> meta(2 * count + 1);
+  std::vector<uint8_t> skip(skip_in);
+  unsigned long long units = 0;
+  bool any_fallback = false;
+  for (uint64_t i = 0; i < count; i++) {
+    const PlanRec& pr = st->plan[first + i];
+    if (pr.flags & PLAN_FALLBACK) { any_fallback = any_fallback || !skip[i]; skip[i] = 1; }
+    meta[i] = units;
+    const uint64_t cells = (uint64_t)st->shapes[2 * (first + i)] * (uint64_t)st->shapes[2 * (first + i) + 1];
+    units += skip[i] ? 1 : (cells + FILL_UNIT - 1) / FILL_UNIT;
+    meta[count + 1 + i] = dst[i];
+  }
+  meta[count] = units;
+  char* dmeta;
+  const size_t meta_bytes = align256(meta.size() * 8);
+  XS_RET(xs_buf(v, 6, meta_bytes + align256(count) + 256, (void**)&dmeta));
+  XS_CK(cudaMemcpyAsync(dmeta, meta.data(), meta.size() * 8, cudaMemcpyHostToDevice, sm));
+  XS_CK(cudaMemcpyAsync(dmeta + meta_bytes, skip.data(), count, cudaMemcpyHostToDevice, sm));
+  void* d_out = out;
+  if (mem == XS3D_HOST) XS_RET(xs_buf(v, 7, (size_t)out_elems * itemsize + 256, &d_out));
+  const unsigned grid = (unsigned)std::min<unsigned long long>((units + 7) / 8, (unsigned long long)xs_sm_count(v) * 32);
+  slice_fill_kernel<<<grid, 256, 0, sm>>>(b.ctx + first, b.plan + first, (const unsigned long long*)dmeta, (const unsigned long long*)dmeta + count + 1,
+                                          (const uint8_t*)(dmeta + meta_bytes), (uint32_t)count, labels, itemsize, c_order, d_out);
+  XS_CK(cudaGetLastError());
+  if (any_fallback) {
+    for (uint64_t i = 0; i < count; i++) {
+      if (!(st->plan[first + i].flags & PLAN_FALLBACK) || skip_in[i]) continue;
+      int64_t shp[2]; void* d_cut;
+      XS_RET(slice_big(v, st->pos.data() + 3 * (first + i), st->nrm.data() + 3 * (first + i), st->w, st->positive, st->crop, shp, &d_cut));
+      XS_CK(cudaMemcpyAsync((char*)d_out + dst[i] * itemsize, d_cut, (size_t)shp[0] * shp[1] * itemsize, cudaMemcpyDeviceToDevice, sm));
+    }
+  }
+  if (mem == XS3D_HOST) XS_CK(cudaMemcpyAsync(out, d_out, (size_t)out_elems * itemsize, cudaMemcpyDeviceToHost, sm));
+  XS_CK(cudaStreamSynchronize(sm));
+  return XS3D_OK;
+}
+
+extern "C" int xs3d_projection_fill(xs3d_volume* v, uint64_t first, uint64_t count, void* out, int mem) {
+  if (!v) return xs_fail(XS3D_ERR_ARG, "null volume");
+  XS_RET(xs_set_device(v));
+  SliceState* st = slice_state(v);
+  if (first > st->n || count > st->n - first) return xs_fail(XS3D_ERR_ARG, "plane range outside the last plan");
+  if (count == 0 || st->empty) return XS3D_OK;
+  const uint64_t base = st->offsets[first], total = st->offsets[first + count] - base;
+  if (total && !out) return xs_fail(XS3D_ERR_ARG, "null output");
+  std::vector<uint64_t> dst(count);
+  for (uint64_t i = 0; i < count; i++) dst[i] = st->offsets[first + i] - base;
+  return fill_impl(v, first, count, dst, std::vector<uint8_t>(count, 0), total, out, mem);
+}
+
+// fixed-pitch form: plan, then every cut-out that fits at out + i * pitch_elems
+extern "C" int xs3d_projection_batch(xs3d_volume* v, uint64_t n, const float* pos, const float* normal, const float anisotropy[3],
+                                     int standardize_basis, float crop_distance, void* out, uint64_t pitch_elems,
+                                     int64_t* shapes, uint8_t* overflow, int mem) {
+  if (!v) return xs_fail(XS3D_ERR_ARG, "null volume");
+  if (n == 0) return XS3D_OK;
+  if (!shapes || !overflow) return xs_fail(XS3D_ERR_ARG, "null argument");
+  std::vector<int64_t> h_shapes(2 * n);
+  std::vector<uint64_t> h_off(n + 1);
+  XS_RET(xs3d_projection_plan(v, n, pos, normal, anisotropy, standardize_basis, crop_distance, mem, h_shapes.data(), h_off.data()));
+  std::vector<uint8_t> over(n, 0);
+  std::vector<uint64_t> dst(n);
+  for (uint64_t i = 0; i < n; i++) {
+    over[i] = (uint64_t)h_shapes[2 * i] * (uint64_t)h_shapes[2 * i + 1] > pitch_elems ? 1 : 0;
+    dst[i] = i * pitch_elems;
+  }
+  cudaStream_t sm = xs_stream(v);
+  if (mem == XS3D_HOST) {
+    memcpy(shapes, h_shapes.data(), n * 16); memcpy(overflow, over.data(), n);
+  } else {
+    XS_CK(cudaMemcpyAsync(shapes, h_shapes.data(), n * 16, cudaMemcpyHostToDevice, sm));
+    XS_CK(cudaMemcpyAsync(overflow, over.data(), n, cudaMemcpyHostToDevice, sm));
+    XS_CK(cudaStreamSynchronize(sm));
+  }
+  if (crop_distance == 0.0f || pitch_elems == 0) return XS3D_OK;
+  if (!out) return xs_fail(XS3D_ERR_ARG, "null output");
+  return fill_impl(v, 0, n, dst, over, n * pitch_elems, out, mem);
 }

@@ -99,11 +99,14 @@ def _queries(positions, normals):
 
 
 class SliceBatch(Sequence):
-  """The cut-outs of Volume.slice_batch: sequence of Fortran-ordered 2-D views into one [n, pitch] buffer
-  (`.buffer`, `.shapes`); a view is built when an element is accessed, so 10^4 tiny slices cost no Python loop."""
+  """The cut-outs of Volume.slice_batch: a sequence of Fortran-ordered 2-D arrays, built as views when an element is
+  accessed (10^4 tiny slices cost no Python loop).  Ragged form: `chunks` = [(first plane, 1-D buffer)] + `offsets`
+  (elements, per plane) + `shapes`; fixed-pitch form: `buffer` [n, pitch] + `shapes`."""
 
-  def __init__(self, buffer, shapes):
-    self.buffer, self.shapes = buffer, shapes
+  def __init__(self, buffer, shapes, offsets=None, chunks=None):
+    self.buffer, self.shapes, self.offsets, self.chunks = buffer, shapes, offsets, chunks
+    if chunks is not None:
+      self._firsts = np.array([c[0] for c in chunks], dtype=np.int64)
 
   def __len__(self):
     return len(self.shapes)
@@ -116,7 +119,12 @@ class SliceBatch(Sequence):
     if not 0 <= i < len(self):
       raise IndexError(i)
     h, w = int(self.shapes[i, 0]), int(self.shapes[i, 1])
-    return self.buffer[i, : h * w].reshape((h, w), order="F")
+    if self.chunks is None:
+      return self.buffer[i, : h * w].reshape((h, w), order="F")
+    k = int(np.searchsorted(self._firsts, i, side="right")) - 1
+    first, buf = self.chunks[k]
+    lo = int(self.offsets[i] - self.offsets[first])
+    return buf[lo: lo + h * w].reshape((h, w), order="F")
 
 
 class Volume:
@@ -282,6 +290,16 @@ class Volume:
     self._label_dtype = labels.dtype
     _abi.check(self._lib.xs3d_volume_load_labels(self._h, labels.ctypes.data, labels.dtype.itemsize, HOST, c_order))
 
+  def labels_buffer(self, dtype, c_order):
+    """(device pointer, nbytes) of the label buffer, allocated for `dtype` / memory order without an upload (the caller
+    fills it: xs3d.dist.broadcast_labels)."""
+    dt = np.dtype(dtype)
+    p = C.c_void_p()
+    n = C.c_uint64()
+    _abi.check(self._lib.xs3d_volume_labels_buffer(self._h, dt.itemsize, int(bool(c_order)), C.byref(p), C.byref(n)))
+    self._label_dtype = dt
+    return p.value, int(n.value)
+
   def select_label(self, label):
     """Make the resident binary image `labels == label` (labels loaded with load_labels / Volume(labels=...)):
     rebuilt on the device, nothing is uploaded.  One resident segmentation then serves every object in it."""
@@ -399,36 +417,96 @@ class Volume:
     a, c = self.cross_sectional_area_batch(pos[None], normal[None], anisotropy, return_contact=True)
     return (float(a[0]), int(c[0])) if return_contact else float(a[0])
 
-  def slice_batch(self, positions, normals, anisotropy=None, standardize_basis=True, crop=float("inf"), pitch=None):
-    """xs3d.slice for n planes of the resident label volume.  Returns a sequence of n 2-D arrays
-    (`SliceBatch`: views into one fixed-pitch buffer, made on access).  `pitch` = elements reserved per plane
-    (default: from crop)."""
+  def slice_plan(self, positions, normals, anisotropy=None, standardize_basis=True, crop=float("inf")):
+    """Sizes of the cut-outs of n planes through the resident label volume (no labels are read yet):
+    (shapes int64 [n,2], offsets uint64 [n+1] in elements).  slice_fill() then gathers any sub-range of the plan."""
     assert crop >= 0.0
-    if getattr(self, "_label_dtype", None) is None:
-      raise ValueError("load_labels() with an ndarray first")
     if anisotropy is None:
       anisotropy = (1.0, 1.0, 1.0)
     w = _abi.f3(anisotropy)
+    if np.any(w <= 0):
+      raise ValueError(f"anisotropy values must be > 0. Got: {w}")
+    shapes_of = lambda n: (np.zeros((n, 2), dtype=np.int64), np.zeros(n + 1, dtype=np.uint64))
+    if _is_torch_tensor(positions):
+      import torch
+      if not _is_torch_tensor(normals) or not positions.is_cuda or not normals.is_cuda:
+        raise ValueError("positions and normals must both be ndarrays or both CUDA tensors")
+      pos = positions.to(dtype=torch.float32).contiguous().reshape(-1, 3)
+      nrm = normals.to(dtype=torch.float32).contiguous().reshape(-1, 3)
+      if pos.shape != nrm.shape:
+        raise ValueError("positions and normals must have the same length")
+      if bool((nrm == 0).all(dim=1).any()):
+        raise ValueError("normal vector must not be a null vector (all zeros).")
+      self._order_after_producers(pos)
+      shapes, offsets = shapes_of(pos.shape[0])
+      _abi.check(self._lib.xs3d_projection_plan(self._h, pos.shape[0], pos.data_ptr(), nrm.data_ptr(), _abi.fptr(w), int(standardize_basis),
+                                                C.c_float(crop), DEVICE, shapes.ctypes.data, offsets.ctypes.data))
+      return shapes, offsets
     pos, nrm = _queries(positions, normals)
-    n = pos.shape[0]
-    if crop == 0:
-      return [np.zeros((0, 0), dtype=self._label_dtype, order="F") for _ in range(n)]
-    if pitch is None:
-      if np.isfinite(crop):
-        side = 2 * int(np.ceil(crop / float(w.min()) * float(w.max() / w.min()))) + 8
-      else:
-        side = int(2 * 97 * max(self.shape) / 56 * np.ceil(w.max() / w.min())) + 8
-      pitch = side * side
+    shapes, offsets = shapes_of(pos.shape[0])
+    _abi.check(self._lib.xs3d_projection_plan(self._h, pos.shape[0], pos.ctypes.data, nrm.ctypes.data, _abi.fptr(w), int(standardize_basis),
+                                              C.c_float(crop), HOST, shapes.ctypes.data, offsets.ctypes.data))
+    return shapes, offsets
+
+  def slice_fill(self, first, count, out):
+    """Gather planes [first, first + count) of the last slice_plan() into `out`: a 1-D ndarray (host) or CUDA torch
+    tensor of the labels' dtype holding at least offsets[first + count] - offsets[first] elements."""
+    if _is_torch_tensor(out):
+      if not out.is_cuda or not out.is_contiguous():
+        raise ValueError("out must be a contiguous CUDA tensor (or an ndarray)")
+      self._order_after_producers(out)
+      _abi.check(self._lib.xs3d_projection_fill(self._h, int(first), int(count), out.data_ptr(), DEVICE))
+    else:
+      if not isinstance(out, np.ndarray) or not out.flags.c_contiguous or not out.flags.writeable:
+        raise ValueError("out must be a writeable contiguous ndarray")
+      _abi.check(self._lib.xs3d_projection_fill(self._h, int(first), int(count), out.ctypes.data, HOST))
+    return out
+
+  def slice_batch(self, positions, normals, anisotropy=None, standardize_basis=True, crop=float("inf"), pitch=None, max_bytes=1 << 31):
+    """xs3d.slice for n planes of the resident label volume, cropped or not.  Returns a `SliceBatch`: a sequence of n
+    Fortran-ordered 2-D arrays (views, made on access) over ragged buffers of at most `max_bytes` each (an un-cropped
+    plane through a 1024^3 uint64 volume is ~25 MB, so a long list is gathered in pieces).  `pitch` (elements per
+    plane) selects the fixed-pitch form instead: one [n, pitch] buffer, XS3DError if a cut-out does not fit."""
+    assert crop >= 0.0
+    if getattr(self, "_label_dtype", None) is None:
+      raise ValueError("load_labels() with an ndarray first")
     dt = self._label_dtype
-    out = np.zeros((n, pitch), dtype=dt)
-    shapes = np.zeros((n, 2), dtype=np.int64)
-    over = np.zeros(n, dtype=np.uint8)
-    _abi.check(self._lib.xs3d_projection_batch(self._h, n, pos.ctypes.data, nrm.ctypes.data, _abi.fptr(w),
-                                               int(standardize_basis), C.c_float(crop), out.ctypes.data, pitch,
-                                               shapes.ctypes.data, over.ctypes.data, HOST))
-    if np.any(over):
-      raise XS3DError(f"slice_batch: {int(over.sum())} cut-outs exceed the pitch of {pitch} elements; pass a larger pitch")
-    return SliceBatch(out, shapes)
+    if pitch is not None:
+      if anisotropy is None:
+        anisotropy = (1.0, 1.0, 1.0)
+      w = _abi.f3(anisotropy)
+      pos, nrm = _queries(positions, normals)
+      n = pos.shape[0]
+      if crop == 0:
+        return [np.zeros((0, 0), dtype=dt, order="F") for _ in range(n)]
+      out = np.zeros((n, pitch), dtype=dt)
+      shapes = np.zeros((n, 2), dtype=np.int64)
+      over = np.zeros(n, dtype=np.uint8)
+      _abi.check(self._lib.xs3d_projection_batch(self._h, n, pos.ctypes.data, nrm.ctypes.data, _abi.fptr(w),
+                                                 int(standardize_basis), C.c_float(crop), out.ctypes.data, pitch,
+                                                 shapes.ctypes.data, over.ctypes.data, HOST))
+      if np.any(over):
+        raise XS3DError(f"slice_batch: {int(over.sum())} cut-outs exceed the pitch of {pitch} elements; pass a larger pitch")
+      return SliceBatch(out, shapes)
+    shapes, offsets = self.slice_plan(positions, normals, anisotropy, standardize_basis, crop)
+    n = len(shapes)
+    budget = max(1, int(max_bytes) // dt.itemsize)
+    chunks, first = [], 0
+    while first < n:
+      last = int(np.searchsorted(offsets, offsets[first] + np.uint64(budget), side="right")) - 1   # planes [first, last) fit the budget
+      last = min(n, max(last, first + 1))
+      buf = np.empty(int(offsets[last] - offsets[first]), dtype=dt)
+      if buf.size:
+        self.slice_fill(first, last - first, buf)
+      chunks.append((first, buf))
+      first = last
+    return SliceBatch(None, shapes, offsets, chunks)
+
+  def slice(self, pos, normal, anisotropy=None, standardize_basis=True, crop=float("inf")):
+    """xs3d.slice of the RESIDENT label volume: no upload, one plane."""
+    pos, normal, anisotropy = _validate_vectors(pos, normal, anisotropy, 3)
+    r = self.slice_batch(pos[None], normal[None], anisotropy, standardize_basis, crop)
+    return np.asfortranarray(r[0])
 
   def cross_section_sparse(self, pos, normal, anisotropy=None, method=0):
     """(linear F-order voxel indices uint64 [nnz], contributions float32 [nnz], contact)."""
@@ -635,10 +713,14 @@ def slice(
   """
   Oblique 2-D resampling of a label volume through `pos` with plane normal `normal`
   (reference: xs3d/__init__.py:166-232).  The orientation of the projection is not guaranteed.
+  `labels` may also be a `Volume` holding the labels (Volume(labels=...)): the ndarray form uploads the label volume
+  on every call, which is what a single call costs; a resident Volume serves any number of planes without it.
 
   crop: distance in physical units to limit the slice to.
   """
   assert crop >= 0.0
+  if isinstance(labels, Volume):          # resident labels: nothing is uploaded
+    return labels.slice(pos, normal, anisotropy, standardize_basis, crop)
   if anisotropy is None:
     anisotropy = (1.0, 1.0, 1.0)
     if labels.ndim == 2:

@@ -20,7 +20,8 @@ SYMBOLS = [
   "xs3d_volume_create", "xs3d_volume_destroy", "xs3d_volume_load", "xs3d_pack_bits", "xs3d_volume_load_packed", "xs3d_volume_stage_packed", "xs3d_volume_pack_and_stage", "xs3d_volume_commit_staged", "xs3d_volume_staged_cubes", "xs3d_volume_wait_staged", "xs3d_volume_mark_staged", "xs3d_volume_load_labels",
   "xs3d_volume_select_label", "xs3d_volume_cubes", "xs3d_volume_mark_loaded", "xs3d_volume_shape",
   "xs3d_area_batch", "xs3d_area_sweep_host", "xs3d_volume_stats", "xs3d_volume_profile", "xs3d_volume_timing", "xs3d_volume_set_stream",
-  "xs3d_area", "xs3d_section", "xs3d_section_sparse", "xs3d_projection", "xs3d_projection_batch",
+  "xs3d_area", "xs3d_section", "xs3d_section_sparse", "xs3d_projection", "xs3d_projection_batch", "xs3d_projection_plan", "xs3d_projection_fill",
+  "xs3d_volume_labels_buffer",
   "xs3d_set_shape", "xs3d_set_shape_image", "xs3d_clear_shape",
 ]
 
@@ -74,6 +75,9 @@ def lib():
   L.xs3d_section_sparse.argtypes = [vp, fp, fp, fp, C.c_int, vp, vp, u64, C.POINTER(u64), u8p]
   L.xs3d_projection.argtypes = [vp, u64, u64, u64, C.c_int, C.c_int, fp, fp, fp, C.c_int, C.c_float, vp, C.POINTER(C.c_int64)]
   L.xs3d_projection_batch.argtypes = [vp, u64, vp, vp, fp, C.c_int, C.c_float, vp, u64, vp, vp, C.c_int]
+  L.xs3d_projection_plan.argtypes = [vp, u64, vp, vp, fp, C.c_int, C.c_float, C.c_int, vp, vp]
+  L.xs3d_projection_fill.argtypes = [vp, u64, u64, vp, C.c_int]
+  L.xs3d_volume_labels_buffer.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(u64)]
   L.xs3d_set_shape.argtypes = [u64, u64, u64]
   L.xs3d_set_shape_image.argtypes = [vp, u64, u64, u64, C.c_int]
   for name in SYMBOLS:

@@ -59,6 +59,80 @@ def broadcast_volume(volume, binimg=None, src=0, group=None):
   return volume
 
 
+def _device_bytes(ptr, nbytes, device):
+  import torch
+  holder = type("_Holder", (), {})()
+  holder.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+  return torch.as_tensor(holder, device=torch.device("cuda", device))
+
+
+def broadcast_labels(volume, labels=None, src=0, group=None, chunk_bytes=1 << 30):
+  """Make every rank's `volume` hold the label volume rank `src` passes (BASELINE config 5: an 8 GiB uint64
+  segmentation is uploaded over PCIe once, by one rank, and travels to the others over NVLink): src uploads, then the
+  device buffer is NCCL-broadcast in `chunk_bytes` pieces.  dtype and memory order travel with it."""
+  import torch
+  import torch.distributed as dist
+  rank = dist.get_rank(group)
+  gsrc = dist.get_global_rank(group, src) if group is not None else src
+  meta = [None]
+  if rank == src:
+    if labels is None:
+      raise ValueError("the source rank must pass the labels")
+    if not labels.flags.f_contiguous:
+      labels = np.ascontiguousarray(labels)
+    volume.load_labels(labels)
+    meta = [(labels.dtype.str, bool(labels.flags.c_contiguous))]
+  dist.broadcast_object_list(meta, src=gsrc, group=group)
+  dtype, c_order = np.dtype(meta[0][0]), meta[0][1]
+  ptr, nbytes = volume.labels_buffer(dtype, c_order)          # (on src: the buffer load_labels just filled)
+  if dist.get_backend(group) != "nccl":
+    raise RuntimeError("broadcast_labels moves device buffers: it needs the nccl backend")
+  t = _device_bytes(ptr, nbytes, volume.device)
+  torch.cuda.synchronize(volume.device)
+  for lo in range(0, nbytes, int(chunk_bytes)):
+    dist.broadcast(t[lo: lo + int(chunk_bytes)], src=gsrc, group=group)
+  torch.cuda.synchronize(volume.device)
+  return volume
+
+
+def sharded_slice_batch(slicer, positions, normals, group=None):
+  """Run `slicer(pos_chunk, normal_chunk) -> sequence of 2-D arrays` (normally Volume.slice_batch with the anisotropy /
+  crop bound) on this rank's contiguous share of the planes.  Returns (cut-outs of the share, (lo, hi)): slices are
+  consumed where they are made — gathering 10^4 ragged images on every rank would cost more than making them — so there
+  is no collective here at all; `gather_slice_shapes` exchanges just the shapes when a rank needs the global picture."""
+  import torch.distributed as dist
+  world = dist.get_world_size(group)
+  rank = dist.get_rank(group)
+  pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+  nrm = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+  if pos.shape != nrm.shape:
+    raise ValueError("positions and normals must have the same length")
+  lo, hi = shard_bounds(pos.shape[0], world, rank)
+  return slicer(pos[lo:hi], nrm[lo:hi]), (lo, hi)
+
+
+def gather_slice_shapes(shapes, n, group=None):
+  """All-gather of the [k,2] int64 shapes of every rank's share into the [n,2] array of the whole plane list."""
+  import torch
+  import torch.distributed as dist
+  world = dist.get_world_size(group)
+  rank = dist.get_rank(group)
+  backend = dist.get_backend(group)
+  dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+  kmax = shard_bounds(n, world, 0)[1]
+  buf = torch.zeros((kmax, 2), dtype=torch.int64, device=dev)
+  lo, hi = shard_bounds(n, world, rank)
+  if hi > lo:
+    buf[: hi - lo] = torch.from_numpy(np.ascontiguousarray(shapes, dtype=np.int64).reshape(-1, 2)).to(dev)
+  parts = [torch.empty_like(buf) for _ in range(world)]
+  dist.all_gather(parts, buf, group=group)
+  out = np.empty((n, 2), dtype=np.int64)
+  for r in range(world):
+    rlo, rhi = shard_bounds(n, world, r)
+    out[rlo:rhi] = parts[r][: rhi - rlo].cpu().numpy()
+  return out
+
+
 def sharded_area_batch(compute, positions, normals, group=None, gather=True):
   """Run `compute(pos_chunk, normal_chunk) -> (area float32 [k], contact uint8 [k])` on this rank's
   contiguous slice of the queries and (optionally) all-gather the results so every rank returns the

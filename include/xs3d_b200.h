@@ -76,6 +76,9 @@ int xs3d_volume_wait_staged(xs3d_volume* vol, int slot, void* cuda_stream);
 int xs3d_volume_mark_staged(xs3d_volume* vol, int slot, void* cuda_stream);
 /* Attach a label volume for xs3d_projection_v (any 1/2/4/8-byte dtype, C or F order; fastxs3d.cpp:135,199-215). */
 int xs3d_volume_load_labels(xs3d_volume* vol, const void* labels, int itemsize, int mem, int c_order);
+/* The device buffer of the label volume, (re)allocated for that item size / order without an upload: for a host layer
+ * that fills it itself (an NCCL broadcast from the rank that uploaded the labels).  Counts as loaded afterwards. */
+int xs3d_volume_labels_buffer(xs3d_volume* vol, int itemsize, int c_order, void** device_ptr, uint64_t* bytes);
 /* Make the resident image "labels == label" (labels attached with xs3d_volume_load_labels): the occupancy bytes
  * are rebuilt on the device from the label volume, so one uploaded segmentation serves every object in it. */
 int xs3d_volume_select_label(xs3d_volume* vol, uint64_t label);
@@ -138,9 +141,22 @@ int xs3d_section_sparse(xs3d_volume* vol, const float pos[3], const float normal
 int xs3d_projection(const void* labels, uint64_t sx, uint64_t sy, uint64_t sz, int itemsize, int c_order,
                     const float pos[3], const float normal[3], const float anisotropy[3],
                     int standardize_basis, float crop_distance, void* out, int64_t shape[2]);
-/* Batched slices on a resident label volume: n planes, fixed-pitch output.  Plane i's cut-out
- * (shapes[2i] x shapes[2i+1], F-order) is written at out + i*pitch_elems*itemsize; planes whose cut-out
- * exceeds pitch_elems are reported with shapes but not written (status XS3D_OK, flag in overflow[i]). */
+/* Batched slices on a resident label volume (fastxs3d.cpp:119-216 for n planes at once; cropped or not — an
+ * un-cropped plane through a 1024^3 volume is a ~1700 x 1700 cut-out).  Ragged output in two steps:
+ *   xs3d_projection_plan : sizes the cut-outs of n planes (fastxs3d.cpp:137-154 lattice, xs3d.hpp:1554-1621 fill as
+ *        row summaries, :1585-1588 bounding box).  pos / normal: float32[n][3] in `mem`; shapes (int64[2n]) and offsets
+ *        (uint64[n+1], in elements, offsets[n] = total) are HOST arrays.  crop_distance == 0 gives 0 x 0 cut-outs.
+ *   xs3d_projection_fill : gathers planes [first, first + count) of the LAST plan on this volume into `out` (host or
+ *        device memory per `mem`): plane i's cut-out, F-order [shapes[2i]][shapes[2i+1]], starts at element
+ *        offsets[i] - offsets[first].  Any sub-range, any number of times — a caller bounds its buffer by filling the
+ *        plan in pieces.
+ * xs3d_projection_batch is the fixed-pitch form (plan + fill in one call): plane i at out + i * pitch_elems * itemsize;
+ * a cut-out larger than pitch_elems is reported in shapes, flagged overflow[i] = 1 and not written (status XS3D_OK).
+ * shapes / overflow live in `mem` like out.  The labels' dtype is only an item size (fastxs3d.cpp:199-215). */
+int xs3d_projection_plan(xs3d_volume* vol, uint64_t n, const float* pos, const float* normal,
+                         const float anisotropy[3], int standardize_basis, float crop_distance, int mem,
+                         int64_t* shapes, uint64_t* offsets);
+int xs3d_projection_fill(xs3d_volume* vol, uint64_t first, uint64_t count, void* out, int mem);
 int xs3d_projection_batch(xs3d_volume* vol, uint64_t n, const float* pos, const float* normal,
                           const float anisotropy[3], int standardize_basis, float crop_distance,
                           void* out, uint64_t pitch_elems, int64_t* shapes, uint8_t* overflow, int mem);

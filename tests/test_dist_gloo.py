@@ -52,6 +52,50 @@ def test_sharded_area_batch_gloo(n):
   assert res[0][2] == 0 and res[0][3] == res[1][2] and res[1][3] == n
 
 
+def _slice_worker(rank, world, port, q):
+  import torch.distributed as dist
+  sys.path.insert(0, os.path.join(ROOT, "cross-section_b200"))
+  sys.path.insert(0, os.path.join(ROOT, "oracle"))
+  from xs3d import dist as xdist
+  import refapi
+  dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+  try:
+    orc = refapi.Oracle()
+    rng = np.random.default_rng(8)
+    lab = rng.integers(1, 1 << 40, size=(24, 20, 18)).astype(np.uint64)
+    n = 11
+    pos = rng.uniform(0, lab.shape, size=(n, 3)).astype(np.float32)
+    nrm = rng.normal(size=(n, 3)).astype(np.float32)
+    slicer = lambda p, m: [orc.projection(lab, p[i], m[i], [4, 4, 40], True, 30.0) for i in range(len(p))]
+    mine, (lo, hi) = xdist.sharded_slice_batch(slicer, pos, nrm)
+    shapes = xdist.gather_slice_shapes(np.array([s.shape for s in mine], np.int64).reshape(-1, 2), n)
+    full = slicer(pos, nrm)
+    ok = (lo, hi) == xdist.shard_bounds(n, world, rank) and len(mine) == hi - lo
+    ok = ok and all(np.array_equal(a, b) for a, b in zip(mine, full[lo:hi]))
+    ok = ok and [tuple(s) for s in shapes] == [f.shape for f in full]
+    q.put((rank, ok))
+  finally:
+    dist.destroy_process_group()
+
+
+def test_sharded_slice_batch_gloo():
+  sys.path.insert(0, os.path.join(ROOT, "oracle"))
+  import refapi
+  if not refapi.have_oracle():
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"])
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = 33500 + (os.getpid() % 2000)
+  procs = [ctx.Process(target=_slice_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=180) for _ in procs]
+  for p in procs:
+    p.join(60)
+  assert sorted(res) == [(0, True), (1, True)]
+
+
 def _stream_worker(rank, world, port, q):
   """stream_volumes on gloo: rank 0 really bit-packs (xs3d.pack_bits is host code), a CPU stand-in plays the upload /
   ingest, the occupancy bytes travel by gloo broadcast, every rank checks what it holds at every step — both the

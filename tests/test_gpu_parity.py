@@ -620,3 +620,70 @@ def test_multi_gpu_every_rank_against_the_oracle():
                       "--master-port", "29631", os.path.join(root, "tools", "dist_check.py")], capture_output=True, text=True, timeout=900)
   assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
   assert r.stdout.count("bit-identical to the oracle: True") >= min(n, 8), r.stdout[-2000:]
+
+
+def test_slice_batch_random_volumes_vs_oracle(xs, oracle):
+  """The batched slice path (plan + fill, ragged output) on random small label volumes: every dtype, both memory orders,
+  vertices outside the volume, axis-aligned and degenerate normals, every crop — 16 planes per volume in one batch,
+  each cut-out bit-identical to the oracle's (and so are the shapes the plan reports before any label is read)."""
+  rng = np.random.default_rng(2024)
+  for it in range(60):
+    lab, p, n, w, sb, crop = cases.rand_labels_case(rng, max_side=40)
+    if crop == 0.0:
+      crop = 5.0
+    ps = [p] + [rng.uniform(-1, np.array(lab.shape) + 1).astype(np.float32) for _ in range(15)]
+    ns = [n] + [cases.rand_normal(rng) for _ in range(15)]
+    with xs.Volume(labels=lab) as V:
+      shapes, offsets = V.slice_plan(ps, ns, w, sb, crop)
+      res = V.slice_batch(ps, ns, w, sb, crop)
+      one = V.slice(ps[0], ns[0], w, sb, crop)
+    assert len(res) == 16
+    for k in range(16):
+      o = oracle.projection(lab, ps[k], ns[k], w, sb, crop)
+      assert tuple(shapes[k]) == o.shape and int(offsets[k + 1] - offsets[k]) == o.size, (it, k)
+      assert gu.same_bits(np.asfortranarray(res[k]), o), (it, k, lab.shape, lab.dtype, ps[k], ns[k], w, sb, crop)
+    assert gu.same_bits(one, np.asfortranarray(res[0]))
+  lab = np.arange(24, dtype=np.uint16).reshape(2, 3, 4)
+  with xs.Volume(labels=lab) as V:
+    assert all(r.shape == (0, 0) for r in V.slice_batch([[0, 0, 0]] * 3, [[0, 0, 1]] * 3, crop=0)[:])
+    with pytest.raises(ValueError):
+      V.slice_batch([[0, 0, 0]], [[0, 0, 0]])
+
+
+def test_slice_batch_uncropped_planes_and_fixed_pitch(xs, oracle, neurite512):
+  """un-cropped planes through a 512^3 uint64 label volume (cut-outs of up to ~870 x 870 cells) as ONE
+  ragged batch, gathered in pieces (max_bytes smaller than the whole), against the oracle; the fixed-pitch entry point
+  with device-resident inputs and outputs, where a cut-out larger than the pitch is flagged and left unwritten."""
+  import ctypes as C
+  import torch
+  from xs3d import synthetic, _abi
+  vol, verts, tans = neurite512
+  lab = synthetic.make_labels(vol, np.uint64, hashed=True)
+  qp, qn = synthetic.draw_queries(verts, tans, 12, seed=4)
+  qn[3] = [0, 0, 1]; qn[4] = [1, 0, 0]; qn[5] = [1, 1, 0]
+  w = [32, 32, 40]
+  with xs.Volume(labels=lab) as V:
+    res = V.slice_batch(qp, qn, w, crop=float("inf"), max_bytes=16 << 20)
+    assert len(res.chunks) > 1                                     # gathered in several fills of one plan
+    for i in range(12):
+      o = oracle.projection(lab, qp[i], qn[i], w, True, float("inf"))
+      assert o.shape[0] > 400 and gu.same_bits(np.asfortranarray(res[i]), o), i
+    assert gu.same_bits(xs.slice(V, qp[0], qn[0], w), np.asfortranarray(res[0]))       # resident labels behind xs3d.slice
+    # fixed pitch, everything on the device: crop = 300 gives ~30 x 30 cut-outs, pitch 600 holds only some of them
+    n, pitch = 12, 600
+    dp, dn = torch.from_numpy(qp).cuda(), torch.from_numpy(qn).cuda()
+    out = torch.full((n, pitch), 0xDEAD, dtype=torch.int64, device="cuda")
+    shapes = torch.zeros((n, 2), dtype=torch.int64, device="cuda")
+    over = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    _abi.check(V._lib.xs3d_projection_batch(V._h, n, dp.data_ptr(), dn.data_ptr(), _abi.fptr(_abi.f3(w)), 1, C.c_float(300.0),
+                                            out.data_ptr(), pitch, shapes.data_ptr(), over.data_ptr(), _abi.DEVICE))
+    out, shapes, over = out.cpu().numpy().view(np.uint64), shapes.cpu().numpy(), over.cpu().numpy()
+    assert set(over.tolist()) == {0, 1}
+    for i in range(n):
+      o = oracle.projection(lab, qp[i], qn[i], w, True, 300.0)
+      assert tuple(shapes[i]) == o.shape, i
+      if over[i]:
+        assert o.size > pitch and np.all(out[i] == 0xDEAD)
+      else:
+        assert gu.same_bits(out[i, : o.size].reshape(o.shape, order="F"), o), i
