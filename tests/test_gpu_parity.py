@@ -669,8 +669,10 @@ def test_slice_batch_uncropped_planes_and_fixed_pitch(xs, oracle, neurite512):
       o = oracle.projection(lab, qp[i], qn[i], w, True, float("inf"))
       assert o.shape[0] > 400 and gu.same_bits(np.asfortranarray(res[i]), o), i
     assert gu.same_bits(xs.slice(V, qp[0], qn[0], w), np.asfortranarray(res[0]))       # resident labels behind xs3d.slice
-    # fixed pitch, everything on the device: crop = 300 gives ~30 x 30 cut-outs, pitch 600 holds only some of them
-    n, pitch = 12, 600
+    # fixed pitch, everything on the device: crop = 300 gives ~24 x 24 cut-outs; the pitch holds only the smaller ones
+    sizes = np.prod(V.slice_plan(qp, qn, w, True, 300.0)[0], axis=1)
+    n, pitch = 12, int(np.sort(sizes)[n_small := 6])
+    assert sizes.min() < sizes.max()
     dp, dn = torch.from_numpy(qp).cuda(), torch.from_numpy(qn).cuda()
     out = torch.full((n, pitch), 0xDEAD, dtype=torch.int64, device="cuda")
     shapes = torch.zeros((n, 2), dtype=torch.int64, device="cuda")
@@ -684,6 +686,6 @@ def test_slice_batch_uncropped_planes_and_fixed_pitch(xs, oracle, neurite512):
       o = oracle.projection(lab, qp[i], qn[i], w, True, 300.0)
       assert tuple(shapes[i]) == o.shape, i
       if over[i]:
-        assert o.size > pitch and np.all(out[i] == 0xDEAD)
+        assert o.size > pitch and np.all(out[i] == np.uint64(0xDEAD))
       else:
         assert gu.same_bits(out[i, : o.size].reshape(o.shape, order="F"), o), i
