@@ -13,7 +13,7 @@
 //   area_block_kernel (T3/T4): whole-plane bitmap (shared memory when it fits, HBM otherwise) + DFS stack ring;
 //        T4 is the same kernel with one CTA and a worst-case slab.
 //   poly_eval_kernel / combine_kernel : polygon areas of the emitted records; ordered float32 sums per query.
-//   section_block_kernel : path B (xs3d.cross_section) for one query, sparse output.
+//   (path B, xs3d.cross_section, lives in xs_section.cu: grid-wide kernels, union-find over lattice row runs.)
 // The batched launch sequence (two pipelines on three streams) is in area_batch_device.
 // No CPU implementation exists behind the ABI: without a device every call fails loudly.
 #include <cuda_runtime.h>
@@ -907,46 +907,6 @@ __global__ void __launch_bounds__(WideTier::THREADS, 1) area_wide_kernel(BatchAr
   }
 }
 
-// Path B for one query.  result[0] = status, result[1] = records, result[2] = contact; geom[0] = the plane.
-__global__ void __launch_bounds__(BLK_THREADS, 1) section_block_kernel(VolView vol, V3 p, V3 n, V3 w, SlabCfg s, int smem_bits_words,
-                                                                        PolyRec* out_rec, uint64_t* out_idx, uint32_t out_cap,
-                                                                        PlaneGeom* geom, uint32_t* result) {
-  extern __shared__ __align__(16) uint32_t smem[];
-  BlockGroup g(reinterpret_cast<int*>(smem));
-  Ctl& ctl = *reinterpret_cast<Ctl*>(smem + BigTier::O_CTL);
-  uint8_t* ct = reinterpret_cast<uint8_t*>(smem + BigTier::O_CTL + 42);
-  static_assert(BigTier::O_CTL == WideTier::O_CTL, "both layouts keep the control block in the same place");
-  PlaneCtx c;
-  if (threadIdx.x == 0) { result[0] = Q_OK; result[1] = 0; result[2] = 0; }
-  if (!plane_init(c, vol, p, n, w)) return;
-  Arena<uint32_t> A;
-  WideHash H;
-  int st = Q_OVERFLOW;
-  // first the neighbour-byte flood in the wide tier's 416-cell window (3-4x faster per walk step) ...
-  if (s.max_n >= WideTier::WSIDE * WideTier::WSIDE && WIDE_SMEM_BYTES <= (smem_bits_words + BigTier::FIXED_WORDS) * 4) {
-    block_arena<BigTier>(A, H, s, smem, smem_bits_words, c, vol);        // slab pointers and the HBM table
-    A.stack = smem + WideTier::O_RING; A.stack_cap = WideTier::RING;
-    A.cells = reinterpret_cast<uint8_t*>(smem + WideTier::O_CELLS); A.wside = WideTier::WSIDE; A.mside = WideTier::WSIDE; A.moff = 0; A.mlim = WideTier::WSIDE;
-    A.bits = nullptr; A.tested = nullptr; A.tx = A.ty = WideTier::WSIDE / 32; A.stride = 0; A.halo = 1;
-    A.fbits = smem + WideTier::O_FBITS; A.fstride = WideTier::FSTRIDE;
-    A.nlut = reinterpret_cast<const int16_t*>(smem + WideTier::O_LUT);
-    A.ox = A.oy = c.c - (WideTier::WSIDE / 64) * 32 - 16;
-    nbr_lut_fill(g, reinterpret_cast<int16_t*>(smem + WideTier::O_LUT), WideTier::WSIDE);
-    if (threadIdx.x == 0) ctl.counter = 0u;
-    __syncthreads();
-    st = run_section_emit(g, c, vol, A, H, ctl, out_rec, out_idx, out_cap, ct);
-    __syncthreads();
-  }
-  // ... then, for sections wider than that, the whole-plane bitmap
-  if (st == Q_OVERFLOW) {
-    if (threadIdx.x == 0) ctl.counter = 0u;
-    __syncthreads();
-    if (block_arena<BigTier>(A, H, s, smem, smem_bits_words, c, vol)) st = run_section_emit(g, c, vol, A, H, ctl, out_rec, out_idx, out_cap, ct);
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { geom[0] = c.g; result[0] = (uint32_t)st; result[1] = ctl.counter; result[2] = (st == Q_OK) ? *ct : 0u; }
-}
-
 // ------------------------------------------------------------------------------------------------
 // polygon kernel.  About half of the records are cubes the plane misses (value exactly 0) and the rest differ in
 // vertex count, so one-thread-per-record leaves most lanes idle.  Each warp therefore FILTERS 32 records at a time
@@ -1134,7 +1094,8 @@ struct xs3d_volume {
   DevBuf q_pos, q_nrm, q_area, q_contact, lists, counters, slab1, slab2, sec_idx, sec_val, misc;
   DevBuf polys, items, vals, geom, qinfo, slab_mid, keys;
   DevBuf polys2, items2, vals2;                        // record buffers of the second (mid / big tier) pipeline
-  DevBuf slice_bufs[4];                                // batched slices: plan, row summaries, fill meta, host staging
+  DevBuf slice_bufs[5];                                // batched slices: plan, row summaries, fill meta, host staging; path B workspace
+  DevBuf visited;                                      // path B: one bit per voxel, all zero between calls
   void* slice_state = nullptr;                         // xs_slice.cu's host-side plan
   void (*slice_state_free)(void*) = nullptr;
   uint64_t poly_cap2 = 0, item_cap2 = 0;
@@ -1194,7 +1155,6 @@ static int configure_kernels(xs3d_volume* v) {
   CK(cudaFuncSetAttribute(area_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MID_SMEM_BYTES));
   if (WIDE_SMEM_BYTES > v->smem_optin) return fail(XS3D_ERR_UNSUPPORTED, "device shared memory too small for the wide tier");
   CK(cudaFuncSetAttribute(area_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(section_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
   v->kernels_configured = true;
   return XS3D_OK;
 }
@@ -1249,6 +1209,7 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
                      &v->polys, &v->items, &v->vals, &v->geom, &v->qinfo, &v->slab_mid, &v->keys, &v->polys2, &v->items2, &v->vals2, &v->slab_wide };
   for (DevBuf* b : bufs) b->release();
   for (DevBuf& b : v->slice_bufs) b.release();
+  v->visited.release();
   if (v->slice_state && v->slice_state_free) v->slice_state_free(v->slice_state);
   if (v->h_counters) cudaFreeHost(v->h_counters);
   if (v->h_bits) cudaFreeHost(v->h_bits);
@@ -2071,40 +2032,14 @@ extern "C" int xs3d_volume_profile(xs3d_volume* v, uint64_t prof[12]) {
 }
 
 // ---- path B ----------------------------------------------------------------------------------------
-// One CTA floods the section and emits one record per distinct foreground voxel it touches; the polygon
-// kernel values them; entries with value > 0 are the reference's non-zero voxels (xs3d.hpp:526-528).
+// xs_section.cu: grid-wide kernels (lattice bitmap -> union-find over row runs -> component -> voxels -> polygon kernel
+// -> compaction); leaves the non-zero (index, value) pairs on the device.
+int xs_section_fast_sparse(xs3d_volume* v, const float p[3], const float n[3], const float w[3],
+                           uint64_t** d_idx, float** d_val, uint64_t* nnz, uint8_t* contact);
 static int section_fast_sparse(xs3d_volume* v, const float p[3], const float n[3], const float w[3],
                                uint64_t** d_idx, float** d_val, uint64_t* nnz, uint8_t* contact) {
   RET(configure_kernels(v));
-  RET(ensure_worst_case_slab(v));
-  RET(v->counters.ensure(512));
-  const unsigned long long voxels = (unsigned long long)v->sx * v->sy * v->sz;
-  if (voxels >= 0xffffffffull) return fail(XS3D_ERR_UNSUPPORTED, "cross_section on volumes with >= 2^32 voxels");
-  // every sample can introduce at most 27 voxels, bounded by the volume
-  unsigned long long cap = std::min<unsigned long long>(27ull * (unsigned long long)v->cfg2.max_n, voxels);
-  cap = std::min<unsigned long long>(cap, 0x7fffffffull);
-  RET(v->sec_idx.ensure(cap * 8 + 64));
-  RET(v->sec_val.ensure(cap * 4 + 64));
-  RET(v->misc.ensure(cap * sizeof(PolyRec) + 1024));
-  SlabCfg s = v->cfg2;
-  s.hash_factor = 32;   // >= 27 voxels per sample: the dedupe set can never fill
-  uint32_t* d_res = (uint32_t*)v->counters.p + 96;
-  PlaneGeom* d_geom = (PlaneGeom*)((char*)v->misc.p + ((cap * sizeof(PolyRec) + 255) / 256) * 256);
-  PolyRec* d_rec = (PolyRec*)v->misc.p;
-  section_block_kernel<<<1, BLK_THREADS, block_smem_bytes(v), v->stream>>>(view_of(v), mk(p[0], p[1], p[2]), mk(n[0], n[1], n[2]), mk(w[0], w[1], w[2]),
-                                                                            s, block_smem_bits_words(v), d_rec, (uint64_t*)v->sec_idx.p,
-                                                                            (uint32_t)cap, d_geom, d_res);
-  CK(cudaGetLastError());
-  poly_eval_kernel<<<v->sm_count * 8, 256, 0, v->stream>>>(d_rec, d_geom, (float*)v->sec_val.p, d_res + 1, 0u, (uint32_t)cap);
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(v->h_counters, d_res, 16, cudaMemcpyDeviceToHost, v->stream));
-  CK(cudaStreamSynchronize(v->stream));
-  if (v->h_counters[0] != Q_OK) return fail(XS3D_ERR_CAPACITY, "cross_section exceeded the worst-case working set");
-  *nnz = v->h_counters[1];        // touched voxels; callers keep those with value > 0
-  *contact = (uint8_t)v->h_counters[2];
-  *d_idx = (uint64_t*)v->sec_idx.p;
-  *d_val = (float*)v->sec_val.p;
-  return XS3D_OK;
+  return xs_section_fast_sparse(v, p, n, w, d_idx, d_val, nnz, contact);
 }
 
 int xs_section_slow_sparse(xs3d_volume* v, const float p[3], const float n[3], const float w[3], int method,
@@ -2121,23 +2056,13 @@ extern "C" int xs3d_section_sparse(xs3d_volume* v, const float pos[3], const flo
   uint64_t* d_idx = nullptr; float* d_val = nullptr;
   if (method == 0) RET(section_fast_sparse(v, pos, normal, anisotropy, &d_idx, &d_val, nnz, contact));
   else RET(xs_section_slow_sparse(v, pos, normal, anisotropy, method, &d_idx, &d_val, nnz, contact));
-  // bring the touched entries back and keep the non-zero ones (method 0 emits every touched voxel)
-  const uint64_t touched = *nnz;
-  std::vector<uint64_t> hi(touched);
-  std::vector<float> hv(touched);
-  if (touched) {
-    CK(cudaMemcpyAsync(hi.data(), d_idx, touched * 8, cudaMemcpyDeviceToHost, v->stream));
-    CK(cudaMemcpyAsync(hv.data(), d_val, touched * 4, cudaMemcpyDeviceToHost, v->stream));
-    CK(cudaStreamSynchronize(v->stream));
-  }
-  uint64_t k = 0;
-  for (uint64_t i = 0; i < touched; i++) k += (method == 0) ? (hv[i] > 0.0f) : 1;
-  *nnz = k;
+  // both paths leave exactly the non-zero voxels on the device
+  const uint64_t k = *nnz;
   if (k > cap) return fail(XS3D_ERR_ARG, "sparse output buffers too small (nnz returned)");
-  k = 0;
-  for (uint64_t i = 0; i < touched; i++) {
-    if (method == 0 && !(hv[i] > 0.0f)) continue;
-    idx[k] = hi[i]; val[k] = hv[i]; k++;
+  if (k) {
+    CK(cudaMemcpyAsync(idx, d_idx, k * 8, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaMemcpyAsync(val, d_val, k * 4, cudaMemcpyDeviceToHost, v->stream));
+    CK(cudaStreamSynchronize(v->stream));
   }
   return XS3D_OK;
 }
@@ -2229,8 +2154,7 @@ extern "C" int xs3d_section(const uint8_t* binimg, uint64_t sx, uint64_t sy, uin
     CK(cudaMemcpyAsync(idx.data(), d_idx, nnz * 8, cudaMemcpyDeviceToHost, v->stream));
     CK(cudaMemcpyAsync(val.data(), d_val, nnz * 4, cudaMemcpyDeviceToHost, v->stream));
     CK(cudaStreamSynchronize(v->stream));
-    for (uint64_t i = 0; i < nnz; i++)
-      if (method != 0 || val[i] > 0.0f) out[idx[i]] = val[i];   // scatter into the caller's zero-filled image (xs3d.hpp:526-528)
+    for (uint64_t i = 0; i < nnz; i++) out[idx[i]] = val[i];     // scatter into the caller's zero-filled image (xs3d.hpp:526-528)
   }
   return XS3D_OK;
 }
@@ -2252,6 +2176,20 @@ int xs_default_volume(uint64_t sx, uint64_t sy, uint64_t sz, xs3d_volume** out) 
 }
 std::mutex& xs_mutex() { return g_mu; }
 int xs_set_device(const xs3d_volume* v) { CK(cudaSetDevice(v->device)); return XS3D_OK; }
+int xs_visited_bits(xs3d_volume* v, uint32_t** p) {
+  const size_t bytes = (((size_t)v->sx * v->sy * v->sz + 31) / 32) * 4 + 64;
+  if (v->visited.cap < bytes) {
+    RET(v->visited.ensure(bytes));
+    CK(cudaMemsetAsync(v->visited.p, 0, v->visited.cap, v->stream));
+  }
+  *p = (uint32_t*)v->visited.p;
+  return XS3D_OK;
+}
+int xs_launch_poly_eval(xs3d_volume* v, const PolyRec* polys, const PlaneGeom* geom, float* vals, const uint32_t* count_ptr, uint32_t cap) {
+  poly_eval_kernel<<<v->sm_count * 8, 256, 0, v->stream>>>(polys, geom, vals, count_ptr, 0u, cap);
+  CK(cudaGetLastError());
+  return XS3D_OK;
+}
 void** xs_slice_state_slot(xs3d_volume* v, void (*free_fn)(void*)) { v->slice_state_free = free_fn; return &v->slice_state; }
 void xs_labels(xs3d_volume* v, void** p, int* itemsize, int* c_order, bool* loaded) {
   *p = v->labels.p; *itemsize = v->itemsize; *c_order = v->labels_c_order; *loaded = v->labels_loaded;

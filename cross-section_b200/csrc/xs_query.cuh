@@ -27,8 +27,8 @@
 //   COMBINE KERNEL (one CTA per query; combine_query)
 //   6. ordered sum     : block value from its polygons, float32 sum per sample in k order, then
 //                        over samples in rank order — the reference's exact summation order.
-// Path B (cross_section) shares 1-2, replaces 3-4 by a per-voxel dedupe that emits voxel polygons,
-// and needs no combine.
+// Path B (cross_section) is order-free and runs as grid-wide kernels of its own (xs_section.cu); it shares the
+// lattice sampling (cell_probe), the window (bbox_window) and the polygon kernel.
 //
 // Volume layout ("cubes"): one byte per 2x2x2 block = the reference's compute_cube() mask
 // (xs3d.hpp:26-48), bit = dx + 2dy + 4dz, out-of-volume voxels 0; x fastest.  A voxel test and a
@@ -79,14 +79,16 @@ struct PlaneCtx {
 
 // Seed validation + per-query constants.  Returns false when the reference returns (0, 0)
 // (xs3d.hpp:1315-1345): vertex outside the volume or on background.
-XS_HD bool plane_init(PlaneCtx& c, const VolView& v, V3 pos, V3 nraw, V3 w) {
+// check_seed = false: skip the read of the seed voxel (host callers: the occupancy bytes live in device memory; the
+// centre lattice cell, whose sample point IS the vertex, is then tested on the device).
+XS_HD bool plane_init(PlaneCtx& c, const VolView& v, V3 pos, V3 nraw, V3 w, bool check_seed = true) {
   if (v.sx <= 0 || v.sy <= 0 || v.sz <= 0) return false;
   if (!(pos.x >= 0.0f) || pos.x >= (float)v.sx) return false;
   if (!(pos.y >= 0.0f) || pos.y >= (float)v.sy) return false;
   if (!(pos.z >= 0.0f) || pos.z >= (float)v.sz) return false;
   const V3 r = vround(pos);
   if (r.x >= (float)v.sx || r.y >= (float)v.sy || r.z >= (float)v.sz) return false;
-  if (!vox_fg(v, (int)r.x, (int)r.y, (int)r.z)) return false;
+  if (check_seed && !vox_fg(v, (int)r.x, (int)r.y, (int)r.z)) return false;
   const V3 n = vdivs(nraw, vnorm(nraw));
   geom_init(c.g, pos, n, w);
   int m = v.sx > v.sy ? v.sx : v.sy;
@@ -525,7 +527,7 @@ struct Ctl {          // lives in shared memory (one per group)
   int tiles;          // lattice tiles sampled (1024 cells each)
   uint32_t grow[7];   // neighbour-mask flood: tiles wanted by the closure (TileSet)
   long long tmark;    // phase profiling (thread 0): last timestamp and per-phase cycle counts
-  uint32_t t[6];      //   0 flood (tiles + walk)  1 claims  2 emit  3 -  4 -  5 walk only
+  uint32_t t[6];      //   0 flood (tiles + walk)  1 claims  2 emit  3 tile sampling (of 0)  4 emit pass 1 (of 2)  5 walk only (of 0)
 };
 
 XS_HD long long xs_clock() {
@@ -1327,6 +1329,7 @@ XS_D int flood_component_nbr(const G& g, const PlaneCtx& c, const VolView& vol, 
 #pragma unroll
     for (int i = 0; i < NW; i++) todo.w[i] = ctl.grow[i] & ~done.w[i];   // (next write to ctl.grow: after the next sync)
   }
+  if (g.tid() == 0) ctl.t[3] += (uint32_t)(xs_clock() - ctl.tmark);      // tile sampling + closure (part of phase 0)
   done.for_each([&](int t) { nbr_masks_tile(g, A, t % nt, t / nt); });
   g.sync();
   if (g.warp() == 0) {
@@ -1568,6 +1571,7 @@ XS_D int emit_items(const G& g, const PlaneCtx& c, const VolView& vol, const Are
     g.converge();
   }
   g.sync();
+  if (g.tid() == 0) ctl.t[4] += (uint32_t)(xs_clock() - ctl.tmark);      // emit pass 1 (part of phase 2)
   // reserve the output ranges
   int m, npoly;
   {
@@ -1772,104 +1776,6 @@ struct OrderedSum {
   }
   XS_HD float finish() { return fadd(total, sub); }
 };
-
-// Path B, query side: xs3d.cross_section for one query.  Emits one record per distinct foreground voxel
-// the fill touches (kind 1) plus its linear index; the polygon kernel then gives each its value.
-// Neighbourhood and contact follow the UNROUNDED sample (xs3d.hpp:458-478, :1215-1220).
-template <class G, class CellT, class H>
-XS_D int run_section_emit(const G& g, const PlaneCtx& c, const VolView& vol, const Arena<CellT>& A, H& hash, Ctl& ctl,
-                          PolyRec* out_rec, uint64_t* out_idx, uint32_t out_cap, uint8_t* contact) {
-  typedef CellPack<CellT> P;
-  bool empty;
-  if ((A.cells ? flood_component_nbr(g, c, vol, A, ctl, &empty) : flood_component(g, c, vol, A, ctl, &empty)) != Q_OK) return Q_OVERFLOW;
-  if (empty) {
-    if (g.tid() == 0) *contact = 0;
-    return Q_OK;
-  }
-  const int n = ctl.n;
-  hash.fit(n);
-  hash.clear(g);
-  g.sync();
-  uint32_t ct = 0u;
-  bool ovf = false;
-  const float fsx = (float)vol.sx, fsy = (float)vol.sy, fsz = (float)vol.sz;
-  for (int r = g.tid(); r < n; r += g.size()) {
-    const CellT p = A.order[r];
-    const V3 cur = cell_point(c, A.ox + P::u(p), A.oy + P::v(p));
-    ct |= (uint32_t)(cur.x < 0.5f) | ((uint32_t)(cur.x >= c.hi[0]) << 1) | ((uint32_t)(cur.y < 0.5f) << 2) |
-          ((uint32_t)(cur.y >= c.hi[1]) << 3) | ((uint32_t)(cur.z < 0.5f) << 4) | ((uint32_t)(cur.z >= c.hi[2]) << 5);
-    int lo[3], hi[3];
-    lo[0] = (fsub(cur.x, 1.0f) >= 0.0f) ? -1 : 0; lo[1] = (fsub(cur.y, 1.0f) >= 0.0f) ? -1 : 0; lo[2] = (fsub(cur.z, 1.0f) >= 0.0f) ? -1 : 0;
-    hi[0] = (fadd(cur.x, 1.0f) < fsx) ? 1 : 0; hi[1] = (fadd(cur.y, 1.0f) < fsy) ? 1 : 0; hi[2] = (fadd(cur.z, 1.0f) < fsz) ? 1 : 0;
-    if (c.axis_aligned) { lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0; }
-    // one z-layer (up to nine voxels) at a time, every stage as a batch of independent memory operations: occupancy
-    // bytes, then the table slots (plain loads: 13 of 14 voxels have been seen already and need no atomic), then the
-    // compare-and-swaps for the empty slots
-    for (int dz = lo[2]; dz <= hi[2]; dz++) {
-      uint32_t id[9], hh[9], cube[9], e[9];
-      uint32_t live = 0u;
-#pragma unroll
-      for (int j = 0; j < 9; j++) {
-        const int dx = j % 3 - 1, dy = j / 3 - 1;
-        id[j] = 0u; hh[j] = 0u; cube[j] = 0u;
-        if (dx < lo[0] || dx > hi[0] || dy < lo[1] || dy > hi[1]) continue;
-        const V3 qv = vround(vadd(mk((float)dx, (float)dy, (float)dz), cur));
-        if (qv.x < 0.0f || qv.x >= fsx || qv.y < 0.0f || qv.y >= fsy || qv.z < 0.0f || qv.z >= fsz) continue;
-        const int x = (int)qv.x, y = (int)qv.y, z = (int)qv.z;
-        id[j] = (uint32_t)x + (uint32_t)vol.sx * ((uint32_t)y + (uint32_t)vol.sy * (uint32_t)z);
-        hh[j] = (uint32_t)((x & 1) | ((y & 1) << 1) | ((z & 1) << 2));        // bit within the occupancy byte (for now)
-        cube[j] = cube_index(vol, x >> 1, y >> 1, z >> 1);
-        live |= 1u << j;
-      }
-#pragma unroll
-      for (int j = 0; j < 9; j++) e[j] = ((live >> j) & 1u) ? cube_load(vol, cube[j]) : 0u;
-#pragma unroll
-      for (int j = 0; j < 9; j++) {
-        if (!((e[j] >> hh[j]) & 1u)) live &= ~(1u << j);                       // background voxel
-        // dedupe on the voxel: the wide table keyed by the linear voxel index; "fresh" = we created the entry
-        hh[j] = (id[j] * 2654435761u) >> hash.shift;
-      }
-#pragma unroll
-      for (int j = 0; j < 9; j++) e[j] = ((live >> j) & 1u) ? hash.htag[hh[j]] : id[j];
-#pragma unroll
-      for (int j = 0; j < 9; j++)
-        if (((live >> j) & 1u) && e[j] == XS_HEMPTY) { e[j] = atomic_cas_u32(&hash.htag[hh[j]], XS_HEMPTY, id[j]); if (e[j] == XS_HEMPTY) e[j] = XS_HEMPTY - 1u; }
-#pragma unroll
-      for (int j = 0; j < 9; j++) {
-        if (!((live >> j) & 1u)) continue;
-        bool fresh = e[j] == XS_HEMPTY - 1u;                                    // (marker: our compare-and-swap created the entry)
-        if (!fresh && e[j] != id[j]) {
-          // slot held by another voxel: linear probing, one at a time (rare)
-          uint32_t h = hh[j];
-          for (int probes = 0;; probes++) {
-            h = (h + 1u) & (hash.cap - 1u);
-            const uint32_t t = atomic_cas_u32(&hash.htag[h], XS_HEMPTY, id[j]);
-            if (t == XS_HEMPTY) { fresh = true; break; }
-            if (t == id[j]) break;
-            if (probes == hash.max_probe) { ovf = true; break; }
-          }
-        }
-        if (!fresh) continue;                  // first touch only (xs3d.hpp:511-512)
-        const uint32_t slot = atomic_add_u32(&ctl.counter, 1u);
-        if (slot < out_cap) {
-          const uint32_t v0 = id[j];
-          const uint32_t x = v0 % (uint32_t)vol.sx, yz = v0 / (uint32_t)vol.sx;
-          PolyRec pr; pr.q = 0; pr.x = (uint16_t)x; pr.y = (uint16_t)(yz % (uint32_t)vol.sy); pr.z = (uint16_t)(yz / (uint32_t)vol.sy); pr.kind = 1;
-          out_rec[slot] = pr;
-          out_idx[slot] = (uint64_t)v0;
-        } else {
-          ovf = true;
-        }
-      }
-    }
-  }
-  ct = g.or_reduce(ct);
-  if (ovf) ctl.overflow = 1;
-  g.sync();
-  if (ctl.overflow) return Q_OVERFLOW;
-  if (g.tid() == 0) *contact = (uint8_t)ct;
-  return Q_OK;
-}
 
 // Lattice window that provably contains every in-volume lattice cell of the plane: the projection
 // of the volume box onto (b1,b2), padded, clipped to the lattice plus one ring of outside cells.

@@ -339,7 +339,7 @@ class Volume:
     """Per-phase SM cycles of the last batch (thread 0 of each query group, summed over queries)."""
     p = (C.c_uint64 * 12)()
     _abi.check(self._lib.xs3d_volume_profile(self._h, p))
-    names = ["flood", "claims", "emit", "claims_candidates", "emit_pass1", "walk_only"]
+    names = ["flood", "claims", "emit", "tile_sampling", "emit_pass1", "walk_only"]
     return {"warp_tier": dict(zip(names, p[0:6])), "cta_tier": dict(zip(names, p[6:12]))}
 
   # -- queries

@@ -245,49 +245,6 @@ void hostsim_area_batch(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t s
   if (stats) { stats[0] = n_over; stats[1] = n_samples; stats[2] = O.counters[1]; }
 }
 
-// Dense float32 F-order image (zeroed by the caller), like fastxs3d.section method 0.
-// mode 1: neighbour-byte flood in a 160-cell window first (as the device does with its 416-cell window), bitmap flood on overflow.
-int hostsim_section_mode(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t sz, const float* p, const float* n,
-                         const float* w, float* out, uint8_t* contact, int mode);
-int hostsim_section(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t sz, const float* p, const float* n,
-                    const float* w, float* out, uint8_t* contact) {
-  return hostsim_section_mode(img, sx, sy, sz, p, n, w, out, contact, 0);
-}
-int hostsim_section_mode(const uint8_t* img, uint64_t sx, uint64_t sy, uint64_t sz, const float* p, const float* n,
-                         const float* w, float* out, uint8_t* contact, int mode) {
-  std::vector<uint8_t> cubes;
-  host_ingest(img, (int)sx, (int)sy, (int)sz, cubes);
-  VolView v = { cubes.data(), (int)sx, (int)sy, (int)sz, ((int)sx + 1) >> 1, ((int)sy + 1) >> 1, ((int)sz + 1) >> 1 };
-  HostGroup g;
-  PlaneCtx c;
-  *contact = 0;
-  if (!plane_init(c, v, mk(p[0], p[1], p[2]), mk(n[0], n[1], n[2]), mk(w[0], w[1], w[2]))) return 0;
-  BigArena ba;
-  ba.setup(c, v, 0, 64);
-  const size_t cap = (size_t)ba.A.max_n * 27;
-  std::vector<uint64_t> idx(cap);
-  std::vector<PolyRec> rec(cap);
-  Ctl ctl;
-  int st = Q_OVERFLOW;
-  if (mode == 1) {
-    WideArena wa;
-    wa.setup(c, v, ba.A.max_n, 128);
-    wa.H = ba.H;                       // same (large) voxel table
-    ctl.counter = 0u;
-    st = run_section_emit(g, c, v, wa.A, wa.H, ctl, rec.data(), idx.data(), (uint32_t)cap, contact);
-  }
-  if (st != Q_OK) {
-    ctl.counter = 0u;
-    st = run_section_emit(g, c, v, ba.A, ba.H, ctl, rec.data(), idx.data(), (uint32_t)cap, contact);
-  }
-  if (st != Q_OK) return -1;
-  for (uint32_t i = 0; i < ctl.counter; i++) {
-    const float a = poly_eval(rec[i], c.g);
-    if (a > 0.0f) out[idx[i]] = a;          // xs3d.hpp:526-528
-  }
-  return (int)ctl.counter;
-}
-
 float hostsim_voxel_area(uint64_t x, uint64_t y, uint64_t z, const float* p, const float* n, const float* w) {
   PlaneGeom g;
   geom_init(g, mk(p[0], p[1], p[2]), mk(n[0], n[1], n[2]), mk(w[0], w[1], w[2]));

@@ -23,10 +23,6 @@ class HostSim:
   def __init__(self, lib):
     self.lib = lib
     lib.hostsim_area_batch.argtypes = [u8p, u64, u64, u64, u64, fp, fp, fp, fp, u8p, C.c_int, C.POINTER(C.c_int64)]
-    lib.hostsim_section.argtypes = [u8p, u64, u64, u64, fp, fp, fp, fp, u8p]
-    lib.hostsim_section.restype = C.c_int
-    lib.hostsim_section_mode.argtypes = [u8p, u64, u64, u64, fp, fp, fp, fp, u8p, C.c_int]
-    lib.hostsim_section_mode.restype = C.c_int
     lib.hostsim_projection.argtypes = [C.c_void_p, u64, u64, u64, C.c_int, C.c_int, fp, fp, fp, C.c_int, C.c_float,
                                        C.c_void_p, C.POINTER(C.c_int64), C.c_int]
     lib.hostsim_projection.restype = C.c_int
@@ -53,17 +49,6 @@ class HostSim:
     self.lib.hostsim_area_batch(a.ctypes.data_as(u8p), *a.shape, nq, pos.ctypes.data_as(fp), nrm.ctypes.data_as(fp),
                                 w.ctypes.data_as(fp), area.ctypes.data_as(fp), ct.ctypes.data_as(u8p), mode, st)
     return area, ct, list(st)
-
-  def section(self, vol, p, n, w, mode=0):
-    a = np.asfortranarray(vol)
-    a = a.view(np.uint8) if a.dtype == bool else a
-    out = np.zeros(a.shape, np.float32, order="F")
-    ct = C.c_uint8(0)
-    p, n, w = _f3(p), _f3(n), _f3(w)
-    k = self.lib.hostsim_section_mode(a.ctypes.data_as(u8p), *a.shape, p.ctypes.data_as(fp), n.ctypes.data_as(fp),
-                                      w.ctypes.data_as(fp), out.ctypes.data_as(fp), C.byref(ct), mode)
-    assert k >= 0
-    return out, ct.value
 
   def projection(self, labels, pos, normal, w, sb=True, crop=float("inf"), mode=0):
     if not labels.flags.f_contiguous:

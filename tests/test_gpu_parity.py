@@ -689,3 +689,40 @@ def test_slice_batch_uncropped_planes_and_fixed_pitch(xs, oracle, neurite512):
         assert o.size > pitch and np.all(out[i] == np.uint64(0xDEAD))
       else:
         assert gu.same_bits(out[i, : o.size].reshape(o.shape, order="F"), o), i
+
+
+def test_cross_section_component_topologies(xs, oracle):
+  """Path B's union-find over lattice row runs on the shapes that stress it: dense random noise (thousands of short
+  runs, components that merge late), a comb and a spiral (one component whose runs are linked through long detours,
+  so roots change many times), rings around the vertex that must NOT be reached, planes along the axes and oblique."""
+  rng = np.random.default_rng(77)
+  N = 72
+  g = np.stack(np.meshgrid(*[np.arange(N, dtype=np.float32)] * 3, indexing="ij"), -1)
+  c0 = np.array([36, 36, 36], np.float32)
+  rad = np.sqrt(((g[..., :2] - c0[:2]) ** 2).sum(-1))
+  ang = np.arctan2(g[..., 1] - 36, g[..., 0] - 36)
+  shapes = {
+    "noise55": rng.random((N, N, N)) < 0.55,
+    "noise62": rng.random((N, N, N)) < 0.62,
+    "comb": ((g[..., 0].astype(int) % 4 < 2) | (g[..., 1] < 6)) & (g[..., 2] > 20) & (g[..., 2] < 50),
+    "spiral": (np.abs(((rad - 2.2 * (ang + np.pi)) % 13.8) - 3) < 1.6) & (rad < 34),
+    "rings": ((rad < 5) | ((rad > 9) & (rad < 13)) | ((rad > 20) & (rad < 25))),
+  }
+  for name, vol in shapes.items():
+    vol = np.asfortranarray(vol)
+    fg = np.argwhere(vol)
+    for k in range(6):
+      p = fg[rng.integers(len(fg))].astype(np.float32) if k else np.array([36, 36, 36], np.float32)
+      if not vol[tuple(p.astype(int))]:
+        vol[tuple(p.astype(int))] = True
+      n = [[0, 0, 1], [1, 0, 0], [0.3, -0.2, 0.9], [1, 1, 0], [0.05, 0.02, 1], [0.7, 0.1, -0.4]][k]
+      w = [[1, 1, 1], [32, 32, 40], [4, 4, 40]][k % 3]
+      oimg, oct_ = oracle.section(vol, p, n, w)
+      with xs.Volume(vol) as V:
+        idx, val, ct = V.cross_section_sparse(p, n, w)
+        idx2, val2, ct2 = V.cross_section_sparse(p, n, w)       # the visited set is all-zero again after a call
+      oidx, oval = _sparse_of(oimg)
+      order = np.argsort(idx)
+      assert ct == oct_ and np.array_equal(idx[order], oidx) and np.array_equal(bits(val[order]), bits(oval)), (name, k)
+      order2 = np.argsort(idx2)
+      assert ct2 == ct and np.array_equal(idx2[order2], oidx) and np.array_equal(bits(val2[order2]), bits(oval)), (name, k, "second call")

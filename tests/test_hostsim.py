@@ -79,17 +79,6 @@ def test_area_long_sections_mid_tier(hostsim, oracle):
   assert grown > 0, "expected sections larger than the initial 96x96-cell tile set"
 
 
-def test_section_random(hostsim, oracle):
-  rng = np.random.default_rng(4321)
-  for it in range(150):
-    vol, p, n, w = cases.rand_case(rng, max_side=14)
-    s, c = oracle.section(vol, p, n, w, method=0)
-    s2, c2 = hostsim.section(vol, p, n, w)
-    assert gu.same_bits(s, s2) and c == c2, it
-    s3, c3 = hostsim.section(vol, p, n, w, mode=1)          # neighbour-byte flood first
-    assert gu.same_bits(s, s3) and c == c3, it
-
-
 @pytest.mark.parametrize("mode", [0, 1])
 def test_slice_golden(hostsim, golden, mode):
   for i, lab, p, n, w, sb, crop, exp, ub in gu.slice_cases(golden):

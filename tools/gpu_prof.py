@@ -23,6 +23,14 @@ st = V.stats()
 nq0 = NQ - st["escalated_mid"]
 print("warp tier: mean cycles/query %.0f ; cta tier: mean cycles/query %.0f" % (sum(list(p["warp_tier"].values())[:3]) / max(nq0, 1), sum(list(p["cta_tier"].values())[:3]) / max(st["escalated_mid"], 1)))
 print(V.timing())
+if os.environ.get("XS_MID_ALONE"):
+  # the CTA tiers alone: only the queries the pre-pass sends to the mid tier (sizes from a first full batch)
+  a_all = da.cpu().numpy()
+  big = np.argsort(-a_all)[:st["escalated_mid"]]
+  bp = torch.from_numpy(pos[big]).cuda(); bn = torch.from_numpy(nrm[big]).cuda()
+  for rep in range(3):
+    torch.cuda.synchronize(); t = time.time(); V.cross_sectional_area_batch(bp, bn, w); torch.cuda.synchronize(); print("largest %d queries alone: %.5fs" % (len(big), time.time() - t))
+  print(V.stats()); p2 = V.profile(); print(p2); print(V.timing())
 t = time.time(); V.load(vol); print("upload+ingest %.4fs" % (time.time() - t))
 dv = torch.from_numpy(vol.view(np.uint8).ravel(order="K")).cuda()
 torch.cuda.synchronize()
