@@ -490,7 +490,40 @@ __global__ void __launch_bounds__(256) ingest_label_c_kernel(const T* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Second half of the CTA tiers ("P2").  A CTA-tier query (mid / wide / big) keeps an SM's shared memory only for what
+// needs it — lattice tiles, neighbour bytes, the sequential walk.  When the walk is done the CTA parks the query in
+// HBM pools (its rank -> cell list, a cleared first-touch table of its own, one chunk entry per 256 ranks) and takes
+// the next query; claims, ownership and record emission then run as grid-wide kernels over ALL parked chunks
+// (p2_claims / p2_emit1 / p2_scan / p2_emit2), hundreds of CTAs at full occupancy whatever the sizes of the individual
+// sections — one 1.3e5-sample section (BASELINE config 0) is 490 chunks spread over the whole GPU instead of 20 ms on
+// one SM, and in a sweep the mid tier's CTAs spend their time on walks only.
+// ------------------------------------------------------------------------------------------------
+struct P2Rec {               // one parked query
+  uint32_t q, n;
+  int32_t ox, oy;            // lattice cell of window cell (0, 0)
+  uint32_t order_off;        // first entry in the order / mask pools
+  uint32_t hash_off, hash_cap;   // first-touch table: tags at hash_off, ranks at hash_off + hash_cap (power of two)
+  uint32_t chunk0;           // first of its ceil(n / 256) chunks
+  uint32_t contact;
+  uint32_t pad[3];
+  PlaneCtx c;                // the query's plane, as the flood CTA set it up
+};
+enum { P2_CHUNK = 256,
+       P2C_ORDER = 0, P2C_HASH = 1, P2C_CHUNK = 2, P2C_REC = 3, P2C_FULL = 4 /* a pool overflowed */, P2C_HASHFULL = 5 /* a table filled up */,
+       P2C_DONE = 6 /* chunks the P2 kernels have finished with */, P2C_EXITED = 7 /* CTAs of the running p2_emit2 that are through */,
+       P2C_WORDS = 8 };
+struct P2Pools {
+  uint32_t* cursors;         // P2C_*
+  uint32_t* order;  uint32_t* mask;  uint32_t order_cap;
+  uint32_t* hash;   uint32_t hash_cap;
+  uint32_t* chunk_rec; uint32_t* chunk_items; uint32_t* chunk_polys; uint32_t* item_off; uint32_t* poly_off; uint32_t chunk_cap;
+  P2Rec* recs; uint32_t rec_cap;
+  int hash_factor;
+};
+
 struct BatchArgs {
+  P2Pools p2;
   VolView vol;
   const float* pos;
   const float* nrm;
@@ -516,15 +549,13 @@ enum { CNT_NEXT0 = 0, CNT_OVER0 = 1, CNT_NEXT1 = 2, CNT_OVER1 = 3, CNT_NEXT2 = 4
 __device__ __forceinline__ void finish_query(const BatchArgs& a, const Ctl& ctl, uint32_t q, int st, int cnt_over, int stats_base) {
   // thread 0 of the group
   if (st == Q_OK) {
-    if (a.done_list) a.done_list[atomicAdd(&a.counters[CNT_DONE2], 1u)] = q;
+    // CTA tiers: a non-empty query is parked (p2_handoff) and joins the done list when p2_emit2 has written its records
+    if (a.done_list && (stats_base == 4 || ctl.n == 0)) a.done_list[atomicAdd(&a.counters[CNT_DONE2], 1u)] = q;
     atomicAdd(&a.stats[0], (unsigned long long)ctl.n);
     atomicAdd(&a.stats[1], (unsigned long long)ctl.m);
     atomicAdd(&a.stats[2], (unsigned long long)ctl.tiles);
     for (int i = 0; i < 6; i++) atomicAdd(&a.stats[stats_base + i], (unsigned long long)ctl.t[i]);
-    if (stats_base != 4) {   // CTA tiers: their own share of the work counters (the warp tier's is the remainder)
-      atomicAdd(&a.stats[16], (unsigned long long)ctl.n);
-      atomicAdd(&a.stats[17], (unsigned long long)ctl.m);
-    }
+    if (stats_base != 4) atomicAdd(&a.stats[16], (unsigned long long)ctl.n);   // CTA tiers' share of the samples (items: p2_emit2)
   } else {
     QInfo qi; qi.item_off = 0; qi.n_items = 0; qi.contact = 0; qi.status = QS_PENDING;
     a.out.qinfo[q] = qi;
@@ -615,6 +646,62 @@ __global__ void __launch_bounds__(WARPS * 32, 3) area_warpn_kernel(BatchArgs a) 
   }
 }
 
+// CTA tiers, first half: flood (tiles + walk); a non-empty section is parked in the P2 pools.  Every thread returns the
+// same status: Q_OK (parked, or answered with zeros), Q_OVERFLOW (this tier's window / slab cannot hold the section),
+// Q_CAPACITY (a pool is full: the host grows it and runs the batch again).  `slot`: 8 words of shared memory.
+template <class CellT>
+__device__ __forceinline__ int run_area_flood(const BlockGroup& g, const BatchArgs& a, const PlaneCtx& c, const Arena<CellT>& A, Ctl& ctl,
+                                              uint32_t q, uint32_t* slot) {
+  typedef CellPack<CellT> P;
+  bool empty;
+  const int fst = A.cells ? flood_component_nbr(g, c, a.vol, A, ctl, &empty) : flood_component(g, c, a.vol, A, ctl, &empty);
+  if (fst != Q_OK) return Q_OVERFLOW;
+  if (g.tid() == 0) prof_mark(ctl, 0);
+  if (empty) {
+    if (g.tid() == 0) {
+      QInfo qi; qi.item_off = 0; qi.n_items = 0; qi.contact = 0; qi.status = a.out.ready;
+      a.out.qinfo[q] = qi;
+    }
+    return Q_OK;
+  }
+  const P2Pools& p = a.p2;
+  const uint32_t n = (uint32_t)ctl.n;
+  if (g.tid() == 0) {
+    const uint32_t nch = (n + P2_CHUNK - 1) / P2_CHUNK;
+    uint32_t cap = 1024u;
+    while (cap < (uint32_t)p.hash_factor * n && cap < (1u << 30)) cap <<= 1;
+    slot[0] = atomicAdd(&p.cursors[P2C_ORDER], n);
+    slot[1] = atomicAdd(&p.cursors[P2C_HASH], 2u * cap);
+    slot[2] = atomicAdd(&p.cursors[P2C_CHUNK], nch);
+    slot[3] = atomicAdd(&p.cursors[P2C_REC], 1u);
+    slot[4] = cap;
+    const bool full = (uint64_t)slot[0] + n > p.order_cap || (uint64_t)slot[1] + 2ull * cap > p.hash_cap ||
+                      (uint64_t)slot[2] + nch > p.chunk_cap || slot[3] >= p.rec_cap;
+    slot[5] = full ? 1u : 0u;
+    if (full) p.cursors[P2C_FULL] = 1u;
+  }
+  g.sync();
+  if (slot[5]) return Q_CAPACITY;
+  const uint32_t order_off = slot[0], hash_off = slot[1], chunk0 = slot[2], rec = slot[3], cap = slot[4];
+  for (uint32_t i = g.tid(); i < n; i += g.size()) {
+    const CellT e = A.order[i];
+    p.order[order_off + i] = CellPack<uint32_t>::pack(P::u(e), P::v(e));
+  }
+  for (uint32_t i = g.tid(); i < 2u * cap; i += g.size()) p.hash[hash_off + i] = XS_HEMPTY;
+  const uint32_t nch = (n + P2_CHUNK - 1) / P2_CHUNK;
+  for (uint32_t j = g.tid(); j < nch; j += g.size()) p.chunk_rec[chunk0 + j] = rec;
+  if (g.tid() == 0) {
+    P2Rec r;
+    r.q = q; r.n = n; r.ox = A.ox; r.oy = A.oy; r.order_off = order_off; r.hash_off = hash_off; r.hash_cap = cap; r.chunk0 = chunk0; r.contact = 0u;
+    r.pad[0] = r.pad[1] = r.pad[2] = 0u;
+    r.c = c;
+    p.recs[rec] = r;
+    prof_mark(ctl, 1);
+  }
+  g.sync();
+  return Q_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // T1 / T2: one CTA per query
 // ------------------------------------------------------------------------------------------------
@@ -643,7 +730,7 @@ struct BlockTier {
   static constexpr int WIN_TILES = WIN_TILES_;     // > 0: centred window of WIN_TILES^2 tiles; 0: whole-plane (bbox) window
   static constexpr int TESTED = TESTED_;           // tile-mask words in shared memory
   static constexpr int MIN_BLOCKS = MIN_BLOCKS_;
-  static constexpr int CTL_WORDS = 48;
+  static constexpr int CTL_WORDS = 56;            // Ctl (<= 40 words), next-query word (42), hand-off slot (43..48)
   static constexpr int O_CTL = 64;
   static constexpr int O_RING = O_CTL + CTL_WORDS;
   static constexpr int O_TESTED = O_RING + RING;
@@ -728,7 +815,7 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_BLOCKS) area_block_kernel(B
     Arena<uint32_t> A;
     WideHash H;
     int st = Q_OVERFLOW;
-    if (block_arena<T>(A, H, s, smem, smem_bits_words, c, a.vol)) st = run_area_emit(g, c, a.vol, A, H, ctl, q, a.out);
+    if (block_arena<T>(A, H, s, smem, smem_bits_words, c, a.vol)) st = run_area_flood(g, a, c, A, ctl, q, smem + T::O_CTL + 43);
     if (threadIdx.x == 0) finish_query(a, ctl, q, st, cnt_over, stats_base);
   }
 }
@@ -745,7 +832,7 @@ struct MidTier {
   static constexpr int RING = 1024;                // DFS stack ring entries (uint16) in shared memory (77.5 KB in all: one
                                                    //   mid-tier CTA fits beside two warp-tier CTAs on an SM)
   static constexpr int O_CTL = 64;
-  static constexpr int O_RING = O_CTL + 48;
+  static constexpr int O_RING = O_CTL + 56;
   static constexpr int O_LUT = O_RING + RING / 2;  // 256 x int16
   static constexpr int FSTRIDE = WSIDE / 32 + 2;
   static constexpr int O_FBITS = O_LUT + 128;
@@ -827,7 +914,7 @@ __global__ void __maxnreg__(96) area_mid_kernel(BatchArgs a, SlabCfg s, int cnt_
     int lg = 0;
     while ((1u << lg) < s.hcap_max) lg++;
     H.shift = 32 - lg;
-    const int st = run_area_emit(g, c, a.vol, A, H, ctl, q, a.out);
+    const int st = run_area_flood(g, a, c, A, ctl, q, smem + MidTier::O_CTL + 43);
     if (threadIdx.x == 0) finish_query(a, ctl, q, st, cnt_over, stats_base);
   }
 }
@@ -843,7 +930,7 @@ struct WideTier {
   static constexpr int WSIDE = 416;                // 13 x 13 tiles; cell index u + 416 v
   static constexpr int RING = 2048;                // DFS stack ring entries (uint32) in shared memory
   static constexpr int O_CTL = 64;
-  static constexpr int O_RING = O_CTL + 48;
+  static constexpr int O_RING = O_CTL + 56;
   static constexpr int O_LUT = O_RING + RING;      // 256 x int16
   static constexpr int FSTRIDE = WSIDE / 32 + 2;
   static constexpr int O_FBITS = O_LUT + 128;
@@ -902,8 +989,289 @@ __global__ void __launch_bounds__(WideTier::THREADS, 1) area_wide_kernel(BatchAr
     int lg = 0;
     while ((1u << lg) < s.hcap_max) lg++;
     H.shift = 32 - lg;
-    const int st = run_area_emit(g, c, a.vol, A, H, ctl, q, a.out);
+    const int st = run_area_flood(g, a, c, A, ctl, q, smem + WideTier::O_CTL + 43);
     if (threadIdx.x == 0) finish_query(a, ctl, q, st, cnt_over, stats_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// P2 kernels: one 256-thread CTA per chunk of 256 consecutive ranks of a parked query (grid-stride over the chunks
+// parked since `chunk_start`).  The query's plane is rebuilt from its vertex and normal (plane_init is deterministic),
+// its window origin comes from the P2Rec, its first-touch table is its own region of the hash pool (L2-resident).
+// ------------------------------------------------------------------------------------------------
+struct P2Chunk {
+  Arena<uint32_t> A;        // only order / mask / ox / oy are meaningful
+  WideHash H;
+  const P2Rec* rec;
+  uint32_t rec_index, n, q;
+  int r;                    // this thread's rank (may be >= n)
+};
+__device__ __forceinline__ void p2_chunk_setup(const BatchArgs& a, uint32_t chunk, P2Chunk& k) {
+  const P2Pools& p = a.p2;
+  k.rec_index = __ldg(p.chunk_rec + chunk);
+  const P2Rec* rec = p.recs + k.rec_index;
+  k.rec = rec;
+  k.n = rec->n; k.q = rec->q;
+  const uint32_t cap = rec->hash_cap;
+  k.A.order = p.order + rec->order_off; k.A.ox = rec->ox; k.A.oy = rec->oy;
+  k.A.mask = p.mask + rec->order_off;
+  k.H.htag = p.hash + rec->hash_off; k.H.hkey = k.H.htag + cap;
+  k.H.cap = cap; k.H.cap_max = cap; k.H.factor = 0; k.H.max_probe = (int)min(cap, 1u << 20);
+  k.H.hx = a.vol.hx; k.H.hy = a.vol.hy;
+  k.H.alt_tag = nullptr; k.H.alt_key = nullptr; k.H.alt_cap = 0;
+  k.H.shift = 32 - (31 - __clz(cap));
+  k.r = (int)((chunk - rec->chunk0) * P2_CHUNK + threadIdx.x);
+}
+
+// contact bits + first-touch claims.  All chunks of all parked sections claim at once, and neighbouring samples probe
+// the same blocks (~16 claims per distinct block): sent straight to the tables in L2 that is ~9 M atomics on ~0.5 M
+// addresses, and the L2 atomic units become the bottleneck (146 us for the bench sweep).  So a chunk first settles its
+// claims among its own 256 samples in a shared-memory table (tag -> smallest rank), and only the winners — one claim
+// per distinct block and chunk — go to the section's table; a sample is a tentative owner of a block when it won both.
+constexpr int P2_LCAP = 2048;               // local table slots (a chunk touches a few hundred distinct blocks)
+constexpr int P2_LPROBE = 32;
+__global__ void __launch_bounds__(P2_CHUNK) p2_claims_kernel(BatchArgs a) {
+  __shared__ uint32_t s_tag[P2_LCAP], s_key[P2_LCAP];
+  const uint32_t nchunks = min(a.p2.cursors[P2C_CHUNK], a.p2.chunk_cap), chunk_start = a.p2.cursors[P2C_DONE];
+  if (a.p2.cursors[P2C_FULL]) return;
+  for (uint32_t chunk = chunk_start + blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    P2Chunk k;
+    p2_chunk_setup(a, chunk, k);
+    const PlaneCtx& c = k.rec->c;
+    __syncthreads();
+    for (int i = threadIdx.x; i < P2_LCAP; i += P2_CHUNK) { s_tag[i] = XS_HEMPTY; s_key[i] = XS_HEMPTY; }
+    __syncthreads();
+    uint32_t ct = 0u, cmask = 0u, tag = 0u, tentative = 0u, direct = 0u;
+    bool ovf = false;
+    const bool live = k.r < (int)k.n;
+    if (live) {
+      V3 cur;
+      const Sample s = sample_at(c, k.A, k.r, &cur);
+      ct = contact_bits_rounded(c, cur);
+      cmask = probe_candidates(c, a.vol, s);
+      tag = k.H.tag(s.rx >> 1, s.ry >> 1, s.rz >> 1);
+      uint32_t m = cmask;
+      while (m) {
+        const int kk = __ffs(m) - 1;
+        m &= m - 1u;
+        int ox, oy, oz;
+        decode_k(kk, ox, oy, oz);
+        const uint32_t t = tag + k.H.tag_delta(ox, oy, oz);
+        uint32_t h = (t * 2654435761u) >> (32 - 11);
+        bool placed = false;
+        for (int probes = 0; probes < P2_LPROBE; probes++) {
+          const uint32_t old = atomicCAS(&s_tag[h], XS_HEMPTY, t);
+          if (old == XS_HEMPTY || old == t) { atomicMin(&s_key[h], (uint32_t)k.r); placed = true; break; }
+          h = (h + 1u) & (P2_LCAP - 1u);
+        }
+        if (!placed) {                                           // local table crowded: this claim goes to the section's table itself
+          direct |= 1u << kk;
+          const int won = k.H.claim_tag(t, (uint32_t)k.r);
+          if (won == 0) ovf = true;
+          if (won == 2) tentative |= 1u << kk;
+        }
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < P2_LCAP; i += P2_CHUNK) {
+      const uint32_t t = s_tag[i];
+      if (t == XS_HEMPTY) continue;
+      const int won = k.H.claim_tag(t, s_key[i]);
+      if (won == 0) ovf = true;
+      if (won != 2) s_key[i] = XS_HEMPTY;                        // a smaller rank of another chunk holds the block
+    }
+    __syncthreads();
+    if (live) {
+      uint32_t m = cmask & ~direct;
+      while (m) {
+        const int kk = __ffs(m) - 1;
+        m &= m - 1u;
+        int ox, oy, oz;
+        decode_k(kk, ox, oy, oz);
+        const uint32_t t = tag + k.H.tag_delta(ox, oy, oz);
+        uint32_t h = (t * 2654435761u) >> (32 - 11);
+        while (s_tag[h] != t) h = (h + 1u) & (P2_LCAP - 1u);
+        if (s_key[h] == (uint32_t)k.r) tentative |= 1u << kk;
+      }
+      k.A.mask[k.r] = tentative;
+    }
+    ct = __reduce_or_sync(0xffffffffu, ct);
+    if ((threadIdx.x & 31) == 0 && ct) atomicOr(&a.p2.recs[k.rec_index].contact, ct);
+    if (ovf) a.p2.cursors[P2C_HASHFULL] = 1u;
+  }
+}
+
+// ownership -> adjacency -> plane distance: kept masks, items / polygons per chunk (emit_items pass 1)
+__global__ void __launch_bounds__(P2_CHUNK) p2_emit1_kernel(BatchArgs a) {
+  __shared__ int sh_sum[2][P2_CHUNK / 32];
+  const uint32_t nchunks = min(a.p2.cursors[P2C_CHUNK], a.p2.chunk_cap), chunk_start = a.p2.cursors[P2C_DONE];
+  if (a.p2.cursors[P2C_FULL] || a.p2.cursors[P2C_HASHFULL]) return;
+  for (uint32_t chunk = chunk_start + blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    P2Chunk k;
+    p2_chunk_setup(a, chunk, k);
+    const PlaneCtx& c = k.rec->c;
+    int my_items = 0, my_polys = 0;
+    __syncthreads();                       // (sh_sum of the previous chunk has been read)
+    if (k.r < (int)k.n) {
+      uint32_t tent = k.A.mask[k.r], keep = 0u;
+      if (tent) {
+        const Sample s = sample_at(c, k.A, k.r, (V3*)nullptr);
+        const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
+        const uint32_t centre = cube_at(a.vol, bx, by, bz);
+        while (tent) {
+          const int kk = __ffs(tent) - 1;
+          tent &= tent - 1u;
+          int ox, oy, oz;
+          decode_k(kk, ox, oy, oz);
+          if (k.H.owner(bx + ox, by + oy, bz + oz) != (uint32_t)k.r) continue;     // someone with a smaller rank touched it first
+          const uint32_t cand = cube_at(a.vol, bx + ox, by + oy, bz + oz);
+          if (!blocks_adjacent(centre, cand, ox, oy, oz)) continue;                // visited, but contributes nothing
+          const V3 ctr = vadd(mk((float)(2 * (bx + ox)), (float)(2 * (by + oy)), (float)(2 * (bz + oz))), mk(0.5f, 0.5f, 0.5f));
+          if (fabsf(vdot(vsub(ctr, c.g.pos), c.g.n)) > XS_FAR2) continue;          // block value is exactly 0
+          keep |= 1u << kk;
+          my_items++;
+          my_polys += item_polys(cand);
+        }
+      }
+      k.A.mask[k.r] = keep;
+    }
+    __syncwarp();
+    my_items = __reduce_add_sync(0xffffffffu, my_items);
+    my_polys = __reduce_add_sync(0xffffffffu, my_polys);
+    if ((threadIdx.x & 31) == 0) { sh_sum[0][threadIdx.x >> 5] = my_items; sh_sum[1][threadIdx.x >> 5] = my_polys; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int ti = 0, tp = 0;
+      for (int w = 0; w < P2_CHUNK / 32; w++) { ti += sh_sum[0][w]; tp += sh_sum[1][w]; }
+      a.p2.chunk_items[chunk] = (uint32_t)ti; a.p2.chunk_polys[chunk] = (uint32_t)tp;
+    }
+  }
+}
+
+// exclusive prefix sums of the chunk totals, continuing from the records already emitted (one CTA)
+__global__ void __launch_bounds__(1024) p2_scan_kernel(BatchArgs a) {
+  __shared__ unsigned long long wsum[2][32];
+  const P2Pools& p = a.p2;
+  const uint32_t nchunks = min(p.cursors[P2C_CHUNK], p.chunk_cap), chunk_start = p.cursors[P2C_DONE];
+  if (p.cursors[P2C_FULL] || p.cursors[P2C_HASHFULL] || nchunks <= chunk_start) return;
+  const uint32_t cnt = nchunks - chunk_start;
+  const uint32_t per = (cnt + 1023u) / 1024u;
+  const uint32_t lo = min(cnt, threadIdx.x * per), hi = min(cnt, lo + per);
+  unsigned long long si = 0, sp = 0;
+  for (uint32_t i = lo; i < hi; i++) { si += p.chunk_items[chunk_start + i]; sp += p.chunk_polys[chunk_start + i]; }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long ii = si, ip = sp;                       // inclusive over the warp
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const unsigned long long ti = __shfl_up_sync(0xffffffffu, ii, d), tp = __shfl_up_sync(0xffffffffu, ip, d);
+    if (lane >= d) { ii += ti; ip += tp; }
+  }
+  if (lane == 31) { wsum[0][warp] = ii; wsum[1][warp] = ip; }
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long wi = wsum[0][lane], wp = wsum[1][lane];
+    const unsigned long long mi = wi, mp = wp;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const unsigned long long ti = __shfl_up_sync(0xffffffffu, wi, d), tp = __shfl_up_sync(0xffffffffu, wp, d);
+      if (lane >= d) { wi += ti; wp += tp; }
+    }
+    wsum[0][lane] = wi - mi; wsum[1][lane] = wp - mp;        // exclusive over the warps
+    if (lane == 31) {
+      const unsigned long long ri = (unsigned long long)a.out.counters[1] + wi, rp = (unsigned long long)a.out.counters[0] + wp;
+      p.item_off[nchunks] = (uint32_t)min(ri, 0xffffffffull); p.poly_off[nchunks] = (uint32_t)min(rp, 0xffffffffull);
+      if (ri > a.out.item_cap || rp > a.out.poly_cap) a.out.counters[2] = 1u;    // the host grows the buffers and runs the batch again
+    }
+  }
+  __syncthreads();
+  const unsigned long long bi = a.out.counters[1], bp = a.out.counters[0];
+  si = bi + wsum[0][warp] + ii - si; sp = bp + wsum[1][warp] + ip - sp;
+  for (uint32_t i = lo; i < hi; i++) {
+    p.item_off[chunk_start + i] = (uint32_t)si; p.poly_off[chunk_start + i] = (uint32_t)sp;
+    si += p.chunk_items[chunk_start + i]; sp += p.chunk_polys[chunk_start + i];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { a.out.counters[1] = p.item_off[nchunks]; a.out.counters[0] = p.poly_off[nchunks]; }
+}
+
+// item and polygon records in (rank, k) order (emit_items pass 2); the first chunk of a query publishes its QInfo
+__global__ void __launch_bounds__(P2_CHUNK) p2_emit2_kernel(BatchArgs a) {
+  __shared__ int scratch[40];
+  const P2Pools& p = a.p2;
+  const uint32_t nchunks = min(p.cursors[P2C_CHUNK], p.chunk_cap), chunk_start = p.cursors[P2C_DONE];
+  if (p.cursors[P2C_FULL] || p.cursors[P2C_HASHFULL] || a.out.counters[2]) return;
+  BlockGroup g(scratch);
+  const EmitOut& out = a.out;
+  for (uint32_t chunk = chunk_start + blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    P2Chunk k;
+    p2_chunk_setup(a, chunk, k);
+    const PlaneCtx& c = k.rec->c;
+    const uint32_t q = k.q;
+    const uint32_t keep = (k.r < (int)k.n) ? k.A.mask[k.r] : 0u;
+    int bx = 0, by = 0, bz = 0, ni = 0, np = 0;
+    if (keep) {
+      const Sample s = sample_at(c, k.A, k.r, (V3*)nullptr);
+      bx = s.rx >> 1; by = s.ry >> 1; bz = s.rz >> 1;
+      uint32_t km = keep;
+      while (km) {
+        const int kk = __ffs(km) - 1;
+        km &= km - 1u;
+        ni++;
+        int ox, oy, oz;
+        decode_k(kk, ox, oy, oz);
+        np += item_polys(cube_at(a.vol, bx + ox, by + oy, bz + oz));
+      }
+    }
+    int ti, tp;
+    uint32_t io = p.item_off[chunk] + (uint32_t)g.exscan(ni, ti);
+    uint32_t po = p.poly_off[chunk] + (uint32_t)g.exscan(np, tp);
+    uint32_t km = keep;
+    bool first = true;
+    while (km) {
+      const int kk = __ffs(km) - 1;
+      km &= km - 1u;
+      int ox, oy, oz;
+      decode_k(kk, ox, oy, oz);
+      const int cx = bx + ox, cy = by + oy, cz = bz + oz;
+      const uint32_t cand = cube_at(a.vol, cx, cy, cz);
+      const int pop = popc8(cand);
+      const int cnt = item_polys(cand);
+      ItemRec it;
+      it.poly = po;
+      it.meta = (uint32_t)cnt | (pop >= 5 ? 16u : 0u) | (first ? 32u : 0u);
+      out.items[io++] = it;
+      first = false;
+      PolyRec pr;
+      pr.q = q;
+      if (pop >= 5) {
+        pr.x = (uint16_t)(2 * cx); pr.y = (uint16_t)(2 * cy); pr.z = (uint16_t)(2 * cz); pr.kind = 2;
+        out.polys[po++] = pr;
+      }
+      const uint32_t want = (pop >= 5) ? (~cand & 0xffu) : cand;   // absent voxels are subtracted, present ones added
+      for (int b = 0; b < 8; b++) {
+        if (!((want >> b) & 1u)) continue;
+        pr.x = (uint16_t)(2 * cx + (b & 1)); pr.y = (uint16_t)(2 * cy + ((b >> 1) & 1)); pr.z = (uint16_t)(2 * cz + (b >> 2)); pr.kind = 1;
+        out.polys[po++] = pr;
+      }
+    }
+    if (chunk == k.rec->chunk0 && threadIdx.x == 0) {
+      const uint32_t nch = (k.n + P2_CHUNK - 1) / P2_CHUNK;
+      QInfo qi;
+      qi.item_off = p.item_off[chunk]; qi.n_items = p.item_off[chunk + nch] - p.item_off[chunk];
+      qi.contact = *reinterpret_cast<volatile uint32_t*>(&p.recs[k.rec_index].contact); qi.status = out.ready;
+      out.geom[q] = c.g;
+      out.qinfo[q] = qi;
+      if (a.done_list) a.done_list[atomicAdd(&a.counters[CNT_DONE2], 1u)] = q;
+      atomicAdd(&a.stats[1], (unsigned long long)qi.n_items);
+      atomicAdd(&a.stats[17], (unsigned long long)qi.n_items);
+    }
+  }
+  // the last CTA through declares the chunks done: the next chain of P2 kernels starts behind them (nobody parks a
+  // section while a chain runs: the flood kernels of this stream come before or after it)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&p.cursors[P2C_EXITED], 1u) == gridDim.x - 1u) { p.cursors[P2C_EXITED] = 0u; p.cursors[P2C_DONE] = nchunks; }
   }
 }
 
@@ -976,6 +1344,31 @@ __global__ void __launch_bounds__(128) combine_kernel(const ItemRec* __restrict_
       vals[e.poly] = item_value(e, vals);       // an item's polygons are its own: safe to overwrite its first slot
     }
     __syncthreads();
+    if (n > 256u) {
+      // a large section (up to ~1e5 items): the ordered sum is one dependent chain of float additions whatever we do, so
+      // make each link as short as possible — all threads stage 1024 (value, first) pairs in shared memory, thread 0
+      // adds them up from there (a handful of cycles per item instead of two shuffles and a select)
+      __shared__ float tile_v[1024];
+      __shared__ uint8_t tile_f[1024];
+      __shared__ float carry[2];
+      if (threadIdx.x == 0) { carry[0] = 0.0f; carry[1] = 0.0f; }
+      for (uint32_t b = 0; b < n; b += 1024u) {
+        __syncthreads();
+        const uint32_t len = min(1024u, n - b);
+        for (uint32_t j = threadIdx.x; j < len; j += blockDim.x) { const ItemRec e = it[b + j]; tile_v[j] = vals[e.poly]; tile_f[j] = (uint8_t)((e.meta >> 5) & 1u); }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          OrderedSum s;
+          s.total = carry[0]; s.sub = carry[1];
+          for (uint32_t j = 0; j < len; j++) s.add(tile_v[j], tile_f[j] != 0);
+          carry[0] = s.total; carry[1] = s.sub;
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) { area[q] = fadd(carry[0], carry[1]); contact[q] = (uint8_t)qi.contact; }
+      __syncthreads();
+      continue;
+    }
     if (threadIdx.x < 32) {
       OrderedSum s;
       s.init();
@@ -1094,13 +1487,16 @@ struct xs3d_volume {
   DevBuf q_pos, q_nrm, q_area, q_contact, lists, counters, slab1, slab2, sec_idx, sec_val, misc;
   DevBuf polys, items, vals, geom, qinfo, slab_mid, keys;
   DevBuf polys2, items2, vals2;                        // record buffers of the second (mid / big tier) pipeline
+  DevBuf p2_order, p2_mask, p2_hash, p2_chunks, p2_recs;   // pools of the CTA tiers' second half (P2Pools)
+  uint64_t p2_order_cap = 0, p2_rec_cap = 0;
+  int p2_factor = 8;                                   // first-touch table slots per sample (x4 when a table fills up)
   DevBuf slice_bufs[5];                                // batched slices: plan, row summaries, fill meta, host staging; path B workspace
   DevBuf visited;                                      // path B: one bit per voxel, all zero between calls
   void* slice_state = nullptr;                         // xs_slice.cu's host-side plan
   void (*slice_state_free)(void*) = nullptr;
   uint64_t poly_cap2 = 0, item_cap2 = 0;
   cudaEvent_t evb[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // batch timing, launching stream
-  cudaEvent_t evs[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};            // batch timing, second stream
+  cudaEvent_t evs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // batch timing, second stream
   cudaStream_t stream2 = nullptr;                      // the mid tier runs here, beside the warp tier
   cudaStream_t stream3 = nullptr;                      // third warp-tier CTA per SM (moves in when the mid-tier CTA retires)
   cudaEvent_t evf[4] = {nullptr, nullptr, nullptr, nullptr};    // fork, warp-tier grid A done, second stream done, warp-tier grid B done
@@ -1185,7 +1581,7 @@ extern "C" int xs3d_volume_create(int device, uint64_t sx, uint64_t sy, uint64_t
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&v->ev[i]));
   for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&v->evf[i], cudaEventDisableTiming));
   for (int i = 0; i < 6; i++) CK(cudaEventCreate(&v->evb[i]));
-  for (int i = 0; i < 5; i++) CK(cudaEventCreate(&v->evs[i]));
+  for (int i = 0; i < 6; i++) CK(cudaEventCreate(&v->evs[i]));
   RET(v->cubes.ensure(hx * hy * hz + 64));
   CK(cudaHostAlloc((void**)&v->h_counters, 512, cudaHostAllocDefault));
   *out = v;
@@ -1203,10 +1599,11 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
   for (int i = 0; i < 8; i++) if (v->ev[i]) cudaEventDestroy(v->ev[i]);
   for (int i = 0; i < 4; i++) if (v->evf[i]) cudaEventDestroy(v->evf[i]);
   for (int i = 0; i < 6; i++) if (v->evb[i]) cudaEventDestroy(v->evb[i]);
-  for (int i = 0; i < 5; i++) if (v->evs[i]) cudaEventDestroy(v->evs[i]);
+  for (int i = 0; i < 6; i++) if (v->evs[i]) cudaEventDestroy(v->evs[i]);
   DevBuf* bufs[] = { &v->cubes, &v->raw, &v->dbits, &v->labels, &v->q_pos, &v->q_nrm, &v->q_area, &v->q_contact, &v->lists,
                      &v->counters, &v->slab1, &v->slab2, &v->sec_idx, &v->sec_val, &v->misc,
-                     &v->polys, &v->items, &v->vals, &v->geom, &v->qinfo, &v->slab_mid, &v->keys, &v->polys2, &v->items2, &v->vals2, &v->slab_wide };
+                     &v->polys, &v->items, &v->vals, &v->geom, &v->qinfo, &v->slab_mid, &v->keys, &v->polys2, &v->items2, &v->vals2, &v->slab_wide,
+                     &v->p2_order, &v->p2_mask, &v->p2_hash, &v->p2_chunks, &v->p2_recs };
   for (DevBuf* b : bufs) b->release();
   for (DevBuf& b : v->slice_bufs) b.release();
   v->visited.release();
@@ -1691,6 +2088,20 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
   RET(v->polys2.ensure(v->poly_cap2 * sizeof(PolyRec) + 64));
   RET(v->vals2.ensure(v->poly_cap2 * 4 + 64));
   RET(v->items2.ensure(v->item_cap2 * sizeof(ItemRec) + 64));
+  {
+    // P2 pools: room for the largest section the volume can hold plus a sweep's worth of mid-tier sections; a full
+    // pool doubles and the batch runs again (like the record buffers)
+    const long long m = std::max(v->sx, std::max(v->sy, v->sz));
+    const uint64_t worst_n = (uint64_t)(1.5 * (double)m * (double)m) + 16ull * m + 4096ull;
+    if (v->p2_order_cap == 0) v->p2_order_cap = std::max<uint64_t>(1ull << 20, worst_n + (1ull << 19));
+    v->p2_order_cap = std::min<uint64_t>(v->p2_order_cap, 0x7fffffffull);
+    v->p2_rec_cap = std::max<uint64_t>(v->p2_rec_cap, n);
+    RET(v->p2_order.ensure(v->p2_order_cap * 4 + 64));
+    RET(v->p2_mask.ensure(v->p2_order_cap * 4 + 64));
+    RET(v->p2_hash.ensure(std::min<uint64_t>(v->p2_order_cap * 4ull * (uint64_t)v->p2_factor + 4096ull * v->p2_rec_cap, 0xffffffffull) * 4 + 64));
+    RET(v->p2_chunks.ensure((v->p2_order_cap / P2_CHUNK + v->p2_rec_cap + 64) * 5 * 4 + 64));
+    RET(v->p2_recs.ensure(v->p2_rec_cap * sizeof(P2Rec) + 64));
+  }
   if (!v->slab1.p) {
     v->cfg1 = make_cfg(v, false);
     v->cfg1.stride = slab_bytes(v->cfg1);
@@ -1741,6 +2152,30 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     a.nq = (uint32_t)n; a.counters = d_cnt; a.stats = d_stats;
     a.late = list0;
     a.done_list = nullptr;
+    {
+      P2Pools& p = a.p2;
+      p.cursors = d_cnt + 72;
+      p.order = (uint32_t*)v->p2_order.p; p.mask = (uint32_t*)v->p2_mask.p; p.order_cap = (uint32_t)v->p2_order_cap;
+      p.hash = (uint32_t*)v->p2_hash.p;
+      p.hash_cap = (uint32_t)std::min<uint64_t>(v->p2_order_cap * 4ull * (uint64_t)v->p2_factor + 4096ull * v->p2_rec_cap, 0xffffffffull);
+      p.chunk_cap = (uint32_t)(v->p2_order_cap / P2_CHUNK + v->p2_rec_cap + 32);
+      uint32_t* c5 = (uint32_t*)v->p2_chunks.p;
+      const size_t cs = (size_t)p.chunk_cap + 1;
+      p.chunk_rec = c5; p.chunk_items = c5 + cs; p.chunk_polys = c5 + 2 * cs; p.item_off = c5 + 3 * cs; p.poly_off = c5 + 4 * cs;
+      p.recs = (P2Rec*)v->p2_recs.p; p.rec_cap = (uint32_t)v->p2_rec_cap;
+      p.hash_factor = v->p2_factor;
+    }
+    // the second half of the CTA tiers (claims, ownership, records) for everything parked since chunk `c0`
+    auto launch_p2 = [&](cudaStream_t st) -> int {
+      const int pgrid = v->sm_count * 8;
+      p2_claims_kernel<<<pgrid, P2_CHUNK, 0, st>>>(a);
+      p2_emit1_kernel<<<pgrid, P2_CHUNK, 0, st>>>(a);
+      p2_scan_kernel<<<1, 1024, 0, st>>>(a);
+      p2_emit2_kernel<<<pgrid, P2_CHUNK, 0, st>>>(a);
+      CK(cudaGetLastError());
+      launches += 4;
+      return XS3D_OK;
+    };
     EmitOut out1, out2;
     out1.polys = (PolyRec*)v->polys.p; out1.items = (ItemRec*)v->items.p; out1.geom = (PlaneGeom*)v->geom.p; out1.qinfo = (QInfo*)v->qinfo.p;
     out1.counters = d_emit1; out1.ready = QS_READY;
@@ -1775,6 +2210,8 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, -1);
       CK(cudaGetLastError());
       CK(cudaEventRecord(v->evs[1], s2));
+      RET(launch_p2(s2));        // the sections parked so far: their second half runs beside the rest of the warp tier
+      CK(cudaEventRecord(v->evs[5], s2));
       // profiling aid: under ncu every kernel runs alone, so the split of the warp tier into grids A and B would show
       // grid B (10 warps per SM) doing all the work; XS3D_SINGLE_GRID=1 launches the warp tier as one grid of 3 CTAs per SM
       const bool single_grid = getenv("XS3D_SINGLE_GRID") != nullptr;
@@ -1811,6 +2248,8 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(cudaGetLastError());
       launches++;
       CK(cudaEventRecord(v->evs[3], s2));
+      a.out = out2; a.done_list = done2;
+      RET(launch_p2(s2));        // what the late hand-overs, the wide and the big tier parked
       poly_eval_kernel<<<v->sm_count * 4, 256, 0, s2>>>(out2.polys, out2.geom, vals2, d_emit2, 0u, out2.poly_cap);
       CK(cudaGetLastError());
       combine_kernel<<<(unsigned)std::min<uint64_t>(n, 1024), 128, 0, s2>>>(out2.items, vals2, out2.qinfo, done2, d_cnt + CNT_DONE2, (uint32_t)n, d_area, d_contact, QS_READY2);
@@ -1831,6 +2270,8 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       a.list_in = listw; a.list_out = list2;
       area_block_kernel<BigTier><<<(int)n, BigTier::THREADS, block_smem_bytes(v), s1>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVERW, 10);
       CK(cudaGetLastError());
+      a.out = out1; a.done_list = nullptr;
+      RET(launch_p2(s1));
       CK(cudaEventRecord(v->evb[2], s1));
       launches += 3;
     }
@@ -1855,7 +2296,9 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     const uint32_t* he1 = v->h_counters + 64;
     const uint32_t* he2 = v->h_counters + 68;
     uint32_t over3 = 0;
-    bool capacity = he1[2] != 0 || he2[2] != 0;
+    const uint32_t* hp2 = v->h_counters + 72;
+    bool p2_full = hp2[P2C_FULL] != 0, p2_hashfull = hp2[P2C_HASHFULL] != 0;
+    bool capacity = he1[2] != 0 || he2[2] != 0 || p2_full || p2_hashfull;
     if (!capacity && over2 > 0) {
       // worst-case slab, one CTA, only for the queries the big tier could not fit (records go where the big tier's went)
       RET(ensure_worst_case_slab(v));
@@ -1867,6 +2310,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(cudaEventRecord(v->ev[0], s1));
       area_block_kernel<BigTier><<<1, BigTier::THREADS, block_smem_bytes(v), s1>>>(a, v->cfg2, block_smem_bits_words(v), CNT_NEXT3, CNT_OVER3, d_cnt + CNT_OVER2, 10);
       CK(cudaGetLastError());
+      RET(launch_p2(s1));
       CK(cudaEventRecord(v->ev[1], s1));
       poly_eval_kernel<<<v->sm_count * 8, 256, 0, s1>>>(ob.polys, ob.geom, valsb, d_emitb, used, ob.poly_cap);
       combine_kernel<<<1024, 128, 0, s1>>>(ob.items, valsb, ob.qinfo, list2, d_cnt + CNT_OVER2, (uint32_t)n, d_area, d_contact, ob.ready);
@@ -1876,7 +2320,8 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(cudaStreamSynchronize(s1));
       CK(cudaEventElapsedTime(&v->timing[3], v->ev[0], v->ev[1]));
       over3 = v->h_counters[CNT_OVER3];
-      capacity = he1[2] != 0 || he2[2] != 0;
+      p2_full = hp2[P2C_FULL] != 0; p2_hashfull = hp2[P2C_HASHFULL] != 0;
+      capacity = he1[2] != 0 || he2[2] != 0 || p2_full || p2_hashfull;
     }
     const unsigned long long* hs = (const unsigned long long*)(v->h_counters + CNT_WORDS);
     v->stats[0] = hs[0]; v->stats[1] = hs[1]; v->stats[2] = hs[2] * 1024ull;
@@ -1889,6 +2334,15 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       // a record buffer filled up: double it and run the batch again
       if (he1[2] != 0) { v->poly_cap *= 2; v->item_cap *= 2; }
       if (he2[2] != 0) { v->poly_cap2 *= 2; v->item_cap2 *= 2; }
+      if (p2_full) {
+        if (v->p2_order_cap >= 0x7fffffffull) return fail(XS3D_ERR_CAPACITY, "sample pool would exceed 2^31 entries; split the batch");
+        v->p2_order_cap *= 2;
+      }
+      if (p2_hashfull) {
+        if (v->p2_factor >= 512) return fail(XS3D_ERR_CAPACITY, "a first-touch table filled up at 512 slots per sample");
+        v->p2_factor *= 4;
+      }
+      if (p2_full || p2_hashfull) RET(ensure_batch_workspace(v, n));
       if (v->poly_cap > (1ull << 31) || v->poly_cap2 > (1ull << 31)) return fail(XS3D_ERR_CAPACITY, "polygon record buffer would exceed 2^31 entries; split the batch");
       RET(v->polys.ensure(v->poly_cap * sizeof(PolyRec) + 64));
       RET(v->vals.ensure(v->poly_cap * 4 + 64));
@@ -2006,9 +2460,10 @@ extern "C" int xs3d_volume_timing(xs3d_volume* v, float ms[12]) {
     CK(cudaEventElapsedTime(&v->timing[8], v->evb[4], v->evb[5]));                 // waiting for the second stream
     if (!single) {
       CK(cudaEventElapsedTime(&v->timing[1], v->evs[0], v->evs[1]));               // mid tier beside the warp tier
-      CK(cudaEventElapsedTime(&v->timing[10], v->evs[1], v->evs[2]));              // ... its second launch (incl. waiting for the warp tier)
+      CK(cudaEventElapsedTime(&v->timing[10], v->evs[5], v->evs[2]));              // ... its second launch (incl. waiting for the warp tier)
       CK(cudaEventElapsedTime(&v->timing[2], v->evs[2], v->evs[3]));               // big tier
-      CK(cudaEventElapsedTime(&v->timing[11], v->evs[3], v->evs[4]));              // second stream's polygon + combine kernels
+      CK(cudaEventElapsedTime(&v->timing[7], v->evs[1], v->evs[5]));               // second half of the CTA tiers (P2 kernels), first chain
+      CK(cudaEventElapsedTime(&v->timing[11], v->evs[3], v->evs[4]));              // second chain of P2 kernels + second stream's polygon + combine kernels
     }
   }
   for (int i = 0; i < 12; i++) ms[i] = v->timing[i];

@@ -1380,6 +1380,41 @@ XS_HD Sample sample_at(const PlaneCtx& c, const Arena<CellT>& A, int r, V3* roun
   return s;
 }
 
+// Contact bits of a sample from its ROUNDED point (path A, xs3d.hpp:909-914).
+XS_HD uint32_t contact_bits_rounded(const PlaneCtx& c, V3 cur) {
+  return (uint32_t)(cur.x < 1.0f) | ((uint32_t)(cur.x >= c.hi[0]) << 1) | ((uint32_t)(cur.y < 1.0f) << 2) |
+         ((uint32_t)(cur.y >= c.hi[1]) << 3) | ((uint32_t)(cur.z < 1.0f) << 4) | ((uint32_t)(cur.z >= c.hi[2]) << 5);
+}
+
+// Which of the 27 neighbouring 2x2x2 blocks a sample probes with a SET probe voxel (bit k = (ox+1) + 3(oy+1) + 9(oz+1)):
+// probe voxel r + 2o must be inside the volume (xs3d.hpp:665-671) and set (:704); axis-aligned planes only look at the
+// sample's own block (:677-685).  Branch-free: an out-of-volume probe reads the sample's own block and is masked off.
+XS_HD uint32_t probe_candidates(const PlaneCtx& c, const VolView& vol, const Sample& s) {
+  const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
+  const int pb = (s.rx & 1) | ((s.ry & 1) << 1) | ((s.rz & 1) << 2);
+  const uint32_t base = cube_index(vol, bx, by, bz);
+  if (c.axis_aligned) return ((cube_load(vol, base) >> pb) & 1u) << 13;
+  const int hx = vol.hx, hxy = vol.hx * vol.hy;
+  const uint32_t okx = (s.rx - 2 >= 0 ? 1u : 0u) | 2u | (s.rx + 2 < vol.sx ? 4u : 0u);
+  const uint32_t oky = (s.ry - 2 >= 0 ? 1u : 0u) | 2u | (s.ry + 2 < vol.sy ? 4u : 0u);
+  const uint32_t okz = (s.rz - 2 >= 0 ? 1u : 0u) | 2u | (s.rz + 2 < vol.sz ? 4u : 0u);
+  uint32_t cmask = 0u;
+#pragma unroll
+  for (int oz = 0; oz < 3; oz++) {
+#pragma unroll
+    for (int oy = 0; oy < 3; oy++) {
+#pragma unroll
+      for (int ox = 0; ox < 3; ox++) {
+        const uint32_t ok = (okx >> ox) & (oky >> oy) & (okz >> oz) & 1u;
+        const uint32_t off = (uint32_t)((ox - 1) + (oy - 1) * hx + (oz - 1) * hxy);
+        const uint32_t cb = cube_load(vol, base + (ok ? off : 0u));
+        cmask |= ((cb >> pb) & ok) << (ox + 3 * oy + 9 * oz);
+      }
+    }
+  }
+  return cmask;
+}
+
 // Step 3: contact bits (xs3d.hpp:909-914) and first-touch claims (xs3d.hpp:689-708).
 // The owner of a block is the claimer with the smallest DFS rank; since a sample probes each block at
 // most once, the rank alone identifies the (rank,k) pair the reference would have visited first.
@@ -1390,7 +1425,6 @@ XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const 
   g.sync();
   uint32_t ct = 0u;
   bool ovf = false;
-  const int hx = vol.hx, hxy = vol.hx * vol.hy;
   // uniform trip count + an explicit reconvergence point per chunk: the per-lane claim loop below has a
   // data-dependent length, and without the re-join the lanes of a warp drift apart for the rest of the phase
   for (int r0 = 0; r0 < n; r0 += g.size()) {
@@ -1399,37 +1433,11 @@ XS_D void claim_blocks(const G& g, const PlaneCtx& c, const VolView& vol, const 
     if (r < n) {
       V3 cur;
       const Sample s = sample_at(c, A, r, &cur);
-      ct |= (uint32_t)(cur.x < 1.0f) | ((uint32_t)(cur.x >= c.hi[0]) << 1) | ((uint32_t)(cur.y < 1.0f) << 2) |
-            ((uint32_t)(cur.y >= c.hi[1]) << 3) | ((uint32_t)(cur.z < 1.0f) << 4) | ((uint32_t)(cur.z >= c.hi[2]) << 5);
-      const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
-      const int pb = (s.rx & 1) | ((s.ry & 1) << 1) | ((s.rz & 1) << 2);
-      const uint32_t base = cube_index(vol, bx, by, bz);
-      uint32_t cmask = 0u;
-      if (c.axis_aligned) {                                              // xs3d.hpp:677-685: only the sample's own block
-        cmask = ((cube_load(vol, base) >> pb) & 1u) << 13;
-      } else {
-        // probe voxel r + 2o must be inside the volume (xs3d.hpp:665-671) and set (:704).  Branch-free: an
-        // out-of-volume probe reads the sample's own block instead and is masked off.
-        const uint32_t okx = (s.rx - 2 >= 0 ? 1u : 0u) | 2u | (s.rx + 2 < vol.sx ? 4u : 0u);
-        const uint32_t oky = (s.ry - 2 >= 0 ? 1u : 0u) | 2u | (s.ry + 2 < vol.sy ? 4u : 0u);
-        const uint32_t okz = (s.rz - 2 >= 0 ? 1u : 0u) | 2u | (s.rz + 2 < vol.sz ? 4u : 0u);
-#pragma unroll
-        for (int oz = 0; oz < 3; oz++) {
-#pragma unroll
-          for (int oy = 0; oy < 3; oy++) {
-#pragma unroll
-            for (int ox = 0; ox < 3; ox++) {
-              const uint32_t ok = (okx >> ox) & (oky >> oy) & (okz >> oz) & 1u;
-              const uint32_t off = (uint32_t)((ox - 1) + (oy - 1) * hx + (oz - 1) * hxy);
-              const uint32_t cb = cube_load(vol, base + (ok ? off : 0u));
-              cmask |= ((cb >> pb) & ok) << (ox + 3 * oy + 9 * oz);
-            }
-          }
-        }
-      }
+      ct |= contact_bits_rounded(c, cur);
       // claim every probed block (below); remember only the claims that WON at claim time: a sample can end up owning
       // a block only if it held it at some point, so the ownership pass re-checks those few instead of all ~20
-      my_cmask = cmask; my_tag = hash.tag(bx, by, bz);
+      my_cmask = probe_candidates(c, vol, s);
+      my_tag = hash.tag(s.rx >> 1, s.ry >> 1, s.rz >> 1);
     }
     {
       uint32_t tentative = 0u;
