@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib", "libxs3d_b200.so")
 OBJ = os.path.join(HERE, "lib", "obj")
-UNITS = ["xs_device.cu", "xs_slow.cu", "xs_slice.cu", "xs_section.cu", "xs_hostpack.cpp"]   # .cpp: host-only code, compiled by g++
+UNITS = ["xs_device.cu", "xs_slow.cu", "xs_slice.cu", "xs_section.cu", "xs_skeleton.cu", "xs_hostpack.cpp"]   # .cpp: host-only code, compiled by g++
 CXX = os.environ.get("CXX", "g++")
 NVCC = os.environ.get("NVCC", "nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",

@@ -16,6 +16,7 @@
 //   (path B, xs3d.cross_section, lives in xs_section.cu: grid-wide kernels, union-find over lattice row runs.)
 // The batched launch sequence (two pipelines on three streams) is in area_batch_device.
 // No CPU implementation exists behind the ABI: without a device every call fails loudly.
+#include <cuda.h>            // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, libcuda is not linked)
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -336,6 +337,127 @@ __global__ void __launch_bounds__(256) ingest_c16_kernel(const uint8_t* __restri
     }
     __syncthreads();
     emit_tile_from_bit_rows(rows, cubes, bx0, by, bz0, hx, hy, hz);
+    __syncthreads();
+  }
+}
+
+// ---- the same tile, fetched by TMA -----------------------------------------------------------------------
+// ingest_c16_kernel spends most of its issue slots on moving the tile: eight 16-byte loads per thread with their
+// address arithmetic and bounds tests (31.7 M warp-instructions per 512^3 volume, IPC 2.5: instruction-bound at 51 % of the
+// HBM peak).  Here one elected thread asks the TMA unit for the whole 64 x 2 x 256-voxel box (cp.async.bulk.tensor.3d:
+// 32 KiB, out-of-volume parts zero-filled by the hardware) into one of two shared-memory stages while the CTA turns the
+// previous box into bit rows (one 16-byte shared-memory load per 16 voxels) and occupancy bytes (four table look-ups per
+// four bytes: spread2[] moves the bit pair of each 2x2x2 block of a bit-row byte to bits 0 and 4 of its own byte).
+// Persistent CTAs, mbarrier per stage (complete_tx), tiles taken in launch order so that neighbouring CTAs stream
+// neighbouring z-tiles of the same rows.
+constexpr int TMA_TILE_BYTES = 2 * BC_BX * 2 * 2 * BC_BZ;       // 64 x 2 x 256 voxels
+constexpr int TMA_SMEM_BYTES = 2 * TMA_TILE_BYTES;              // dynamic part (the bit rows, the table and the barriers are static)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "XS_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra XS_DONE;\n"
+      "bra XS_WAIT;\n"
+      "XS_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+template <bool EQ>
+__global__ void __launch_bounds__(256) ingest_c_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t* __restrict__ cubes,
+                                                           int hx, int hy, int hz, uint32_t want4) {
+  extern __shared__ __align__(128) uint8_t tma_smem[];          // two stages of TMA_TILE_BYTES
+  __shared__ uint8_t rows[2 * BC_BX * 2][BC_PITCH];
+  __shared__ uint32_t spread2[256];
+  __shared__ __align__(8) unsigned long long bars[2];
+  const int tx = (hx + BC_BX - 1) / BC_BX, tz = (hz + BC_BZ - 1) / BC_BZ;
+  const uint32_t tiles = (uint32_t)tx * (uint32_t)tz * (uint32_t)hy;
+  // spread2[b]: the bit pair (2i, 2i+1) of b to bits (0, 4) of byte i
+  {
+    const uint32_t b = threadIdx.x;
+    uint32_t v = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) v |= (((b >> (2 * i)) & 1u) | (((b >> (2 * i + 1)) & 1u) << 4)) << (8 * i);
+    spread2[b] = v;
+  }
+  const uint32_t bar0 = smem_u32(&bars[0]), bar1 = smem_u32(&bars[1]);
+  const uint32_t tile0 = smem_u32(tma_smem);
+  auto coords = [&](uint32_t t, int* bx0, int* by, int* bz0) {
+    const uint32_t tzi = t % (uint32_t)tz, r = t / (uint32_t)tz;
+    *bx0 = (int)(r % (uint32_t)tx) * BC_BX; *by = (int)(r / (uint32_t)tx); *bz0 = (int)tzi * BC_BZ;
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(bar0, 1); mbar_init(bar1, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  uint32_t t = blockIdx.x;
+  if (t < tiles && threadIdx.x == 0) {
+    int bx0, by, bz0;
+    coords(t, &bx0, &by, &bz0);
+    mbar_expect_tx(bar0, TMA_TILE_BYTES);
+    tma_load_3d(tile0, &tmap, 2 * bz0, 2 * by, 2 * bx0, bar0);
+  }
+  const int bxl = threadIdx.x & (BC_BX - 1), zb_lo = threadIdx.x / BC_BX;         // emit: block column and first bit-row byte of this thread
+  const size_t zs = (size_t)hx * hy;
+  for (uint32_t it = 0; t < tiles; it++, t += gridDim.x) {
+    const uint32_t st = it & 1u;
+    const uint32_t tn = t + gridDim.x;
+    if (tn < tiles && threadIdx.x == 0) {            // the other stage was released by the barrier that ended the previous iteration
+      int bx0, by, bz0;
+      coords(tn, &bx0, &by, &bz0);
+      mbar_expect_tx(st ? bar0 : bar1, TMA_TILE_BYTES);
+      tma_load_3d(tile0 + (st ^ 1u) * TMA_TILE_BYTES, &tmap, 2 * bz0, 2 * by, 2 * bx0, st ? bar0 : bar1);
+    }
+    int bx0, by, bz0;
+    coords(t, &bx0, &by, &bz0);
+    mbar_wait(st ? bar1 : bar0, (it >> 1) & 1u);
+    const uint4* src = reinterpret_cast<const uint4*>(tma_smem + st * TMA_TILE_BYTES);
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int idx = threadIdx.x + 256 * k, row = idx >> 4, seg = idx & 15;      // box layout: [x 64][y 2][z 256] = 128 rows of 256 bytes
+      const uint4 q = src[idx];
+      const uint32_t w[4] = { q.x, q.y, q.z, q.w };
+      uint32_t m16 = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        // bit 7 of every byte <- byte != 0 (== want in EQ mode); then the four flags to bits 0..3 with one multiply
+        const uint32_t x = EQ ? (w[j] ^ want4) : w[j];
+        uint32_t nz = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+        if (EQ) nz ^= 0x80808080u;
+        m16 |= (((nz >> 7) * 0x01020408u) >> 24) << (4 * j);
+      }
+      rows[row][2 * seg] = (uint8_t)m16;
+      rows[row][2 * seg + 1] = (uint8_t)(m16 >> 8);
+    }
+    __syncthreads();
+    if (bx0 + bxl < hx) {
+      uint8_t* dst0 = cubes + (size_t)(bx0 + bxl) + (size_t)hx * (size_t)by + zs * (size_t)bz0;
+#pragma unroll
+      for (int k = 0; k < (BC_BX * BC_BZ / 4) / 256; k++) {
+        const int zb = zb_lo + 8 * k;
+        const uint32_t m = spread2[rows[4 * bxl][zb]] | (spread2[rows[4 * bxl + 2][zb]] << 1) | (spread2[rows[4 * bxl + 1][zb]] << 2) |
+                           (spread2[rows[4 * bxl + 3][zb]] << 3);                  // byte i: the occupancy byte of block (bxl, 4 zb + i)
+        uint8_t* dst = dst0 + zs * (size_t)(4 * zb);
+        if (bz0 + 4 * zb + 3 < hz) {
+          dst[0] = (uint8_t)m; dst[zs] = (uint8_t)(m >> 8); dst[2 * zs] = (uint8_t)(m >> 16); dst[3 * zs] = (uint8_t)(m >> 24);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            if (bz0 + 4 * zb + i < hz) dst[zs * i] = (uint8_t)(m >> (8 * i));
+        }
+      }
+    }
     __syncthreads();
   }
 }
@@ -1490,7 +1612,7 @@ struct xs3d_volume {
   DevBuf p2_order, p2_mask, p2_hash, p2_chunks, p2_recs;   // pools of the CTA tiers' second half (P2Pools)
   uint64_t p2_order_cap = 0, p2_rec_cap = 0;
   int p2_factor = 8;                                   // first-touch table slots per sample (x4 when a table fills up)
-  DevBuf slice_bufs[5];                                // batched slices: plan, row summaries, fill meta, host staging; path B workspace
+  DevBuf slice_bufs[6];                                // batched slices: plan, row summaries, fill meta, host staging; path B workspace; skeleton tangents
   DevBuf visited;                                      // path B: one bit per voxel, all zero between calls
   void* slice_state = nullptr;                         // xs_slice.cu's host-side plan
   void (*slice_state_free)(void*) = nullptr;
@@ -1527,9 +1649,24 @@ struct xs3d_volume {
   bool kernels_configured = false;
   bool own_stream = true;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_block = nullptr;    // blocking host wait (XS3D_BLOCKING_SYNC)
   float timing[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // ms, see xs3d_volume_timing
   int timing_pending = 0;   // 1: batch events not yet read, 2: same for a tiny (`single`) batch
 };
+
+// Wait for `st` on the host.  XS3D_BLOCKING_SYNC=1: sleep on a blocking event instead of spinning in the driver — for
+// processes that share their cores with others (several ranks on one host while rank 0's pool packs the next image).
+static cudaError_t host_wait(xs3d_volume* v, cudaStream_t st) {
+  static const bool blocking = getenv("XS3D_BLOCKING_SYNC") != nullptr;
+  if (!blocking) return cudaStreamSynchronize(st);
+  if (!v->ev_block) {
+    cudaError_t e = cudaEventCreateWithFlags(&v->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e != cudaSuccess) return e;
+  }
+  cudaError_t e = cudaEventRecord(v->ev_block, st);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(v->ev_block);
+}
 
 static VolView view_of(const xs3d_volume* v) {
   VolView r;
@@ -1597,6 +1734,7 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
   if (v->stage_stream) { cudaStreamSynchronize(v->stage_stream); cudaStreamDestroy(v->stage_stream); }
   for (int i = 0; i < 2; i++) { if (v->stage_ev[i]) cudaEventDestroy(v->stage_ev[i]); if (v->stage_copy_ev[i]) cudaEventDestroy(v->stage_copy_ev[i]); v->staged[i].release(); v->staged_cubes[i].release(); if (v->h_stage_bits[i]) cudaFreeHost(v->h_stage_bits[i]); }
   for (int i = 0; i < 8; i++) if (v->ev[i]) cudaEventDestroy(v->ev[i]);
+  if (v->ev_block) cudaEventDestroy(v->ev_block);
   for (int i = 0; i < 4; i++) if (v->evf[i]) cudaEventDestroy(v->evf[i]);
   for (int i = 0; i < 6; i++) if (v->evb[i]) cudaEventDestroy(v->evb[i]);
   for (int i = 0; i < 6; i++) if (v->evs[i]) cudaEventDestroy(v->evs[i]);
@@ -1644,6 +1782,39 @@ __global__ void __launch_bounds__(256) pack_bits_device_kernel(const uint8_t* __
 
 static int launch_ingest_bits_to(xs3d_volume* v, const uint8_t* d_bits, int c_order, uint8_t* dst, cudaStream_t stream);
 
+// C-ordered 1-byte image (sz % 16 == 0, 16-byte aligned) -> occupancy bytes through the TMA tile kernel.  Returns false
+// when the tensor map cannot be made (then the caller uses ingest_c16_kernel); XS3D_NO_TMA=1 forces that too.
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool launch_ingest_c_tma(xs3d_volume* v, const uint8_t* d_img, uint8_t* cubes, uint32_t want4, int eq, cudaStream_t stream) {
+  static const bool off = getenv("XS3D_NO_TMA") != nullptr;
+  if (off) return false;
+  static TensorMapEncodeFn encode = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess) encode = (TensorMapEncodeFn)fn;
+    if (cudaFuncSetAttribute(ingest_c_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES) != cudaSuccess ||
+        cudaFuncSetAttribute(ingest_c_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES) != cudaSuccess) encode = nullptr;
+    cudaGetLastError();
+  }
+  if (!encode) return false;
+  CUtensorMap tmap;
+  const cuuint64_t dims[3] = { (cuuint64_t)v->sz, (cuuint64_t)v->sy, (cuuint64_t)v->sx };           // innermost first: z, y, x
+  const cuuint64_t strides[2] = { (cuuint64_t)v->sz, (cuuint64_t)v->sz * (cuuint64_t)v->sy };       // bytes, for y and x
+  const cuuint32_t box[3] = { 2 * BC_BZ, 2, 2 * BC_BX };
+  const cuuint32_t estr[3] = { 1, 1, 1 };
+  if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)d_img, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+  const size_t tiles = (size_t)((v->hx + BC_BX - 1) / BC_BX) * ((v->hz + BC_BZ - 1) / BC_BZ) * v->hy;
+  const int grid = (int)std::min<size_t>(tiles, (size_t)v->sm_count * 3);
+  if (eq) ingest_c_tma_kernel<true><<<grid, 256, TMA_SMEM_BYTES, stream>>>(tmap, cubes, v->hx, v->hy, v->hz, want4);
+  else ingest_c_tma_kernel<false><<<grid, 256, TMA_SMEM_BYTES, stream>>>(tmap, cubes, v->hx, v->hy, v->hz, want4);
+  return cudaGetLastError() == cudaSuccess;
+}
+
 static int launch_ingest(xs3d_volume* v, const uint8_t* d_img, int c_order) {
   const size_t nblocks = (size_t)v->hx * v->hy * v->hz;
   if (nblocks == 0) return XS3D_OK;
@@ -1652,6 +1823,8 @@ static int launch_ingest(xs3d_volume* v, const uint8_t* d_img, int c_order) {
     const size_t total = nblocks / 8;
     int grid = (int)std::min<size_t>((total + 255) / 256, (size_t)v->sm_count * 32);
     ingest_f16_kernel<<<grid, 256, 0, v->stream>>>(d_img, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz);
+  } else if (c_order && (v->sz % 16 == 0) && ((uintptr_t)d_img % 16 == 0) && launch_ingest_c_tma(v, d_img, (uint8_t*)v->cubes.p, 0u, 0, v->stream)) {
+    // (launched)
   } else if (c_order && (v->sz % 16 == 0) && ((uintptr_t)d_img % 16 == 0)) {
     const size_t tiles = (size_t)((v->hx + BC_BX - 1) / BC_BX) * ((v->hz + BC_BZ - 1) / BC_BZ) * v->hy;
     ingest_c16_kernel<<<(int)std::min<size_t>(tiles, (size_t)v->sm_count * 32), 256, 0, v->stream>>>(d_img, (uint8_t*)v->cubes.p, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz, 0u, 0);
@@ -1973,7 +2146,10 @@ extern "C" int xs3d_volume_select_label(xs3d_volume* v, uint64_t label) {
     const size_t tiles = (size_t)((v->hx + BC_BX - 1) / BC_BX) * ((v->hz + BC_BZ - 1) / BC_BZ) * v->hy;
     const int cgrid = (int)std::min<size_t>(tiles, (size_t)v->sm_count * 32);
     switch (v->itemsize) {
-      case 1: ingest_c16_kernel<<<cgrid, 256, 0, v->stream>>>((const uint8_t*)v->labels.p, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz, (uint32_t)(label & 0xff) * 0x01010101u, 1); break;
+      case 1:
+        if (!launch_ingest_c_tma(v, (const uint8_t*)v->labels.p, cubes, (uint32_t)(label & 0xff) * 0x01010101u, 1, v->stream))
+          ingest_c16_kernel<<<cgrid, 256, 0, v->stream>>>((const uint8_t*)v->labels.p, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz, (uint32_t)(label & 0xff) * 0x01010101u, 1);
+        break;
       case 2: ingest_label_c_kernel<uint16_t><<<cgrid, 256, 0, v->stream>>>((const uint16_t*)v->labels.p, (uint16_t)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz); break;
       case 4: ingest_label_c_kernel<uint32_t><<<cgrid, 256, 0, v->stream>>>((const uint32_t*)v->labels.p, (uint32_t)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz); break;
       default: ingest_label_c_kernel<unsigned long long><<<cgrid, 256, 0, v->stream>>>((const unsigned long long*)v->labels.p, (unsigned long long)label, cubes, v->sx, v->sy, v->sz, v->hx, v->hy, v->hz); break;
@@ -2130,7 +2306,7 @@ static int ensure_worst_case_slab(xs3d_volume* v) {
 // Rare paths after the final sync: queries that overflowed the big tier's slab re-run with the worst-case slab; a
 // full record buffer grows and the batch re-runs.  Tiny batches (`single`) go straight to the big tier.
 static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, const float* d_nrm, const float w[3],
-                             float* d_area, uint8_t* d_contact, bool single) {
+                             float* d_area, uint8_t* d_contact, bool single, float* h_area = nullptr, uint8_t* h_contact = nullptr) {
   uint32_t* d_cnt = (uint32_t*)v->counters.p;
   unsigned long long* d_stats = (unsigned long long*)(d_cnt + CNT_WORDS);
   uint32_t* d_emit1 = d_cnt + 64;     // [0] polygons [1] items [2] capacity flag
@@ -2285,8 +2461,12 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     if (!single) CK(cudaStreamWaitEvent(s1, v->evf[2], 0));   // join
     CK(cudaEventRecord(v->evb[5], s1));
     CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, s1));
+    if (h_area) {            // host callers: the results come down behind the kernels, under the same (single) host wait
+      CK(cudaMemcpyAsync(h_area, d_area, n * 4, cudaMemcpyDeviceToHost, s1));
+      CK(cudaMemcpyAsync(h_contact, d_contact, n, cudaMemcpyDeviceToHost, s1));
+    }
     trace(v, "launched");
-    CK(cudaStreamSynchronize(s1));
+    CK(host_wait(v, s1));
     trace(v, "synced");
     v->timing_pending = single ? 2 : 1;   // event durations are read on demand (xs3d_volume_timing): ten driver calls off the hot path
     v->timing[3] = 0.0f;
@@ -2317,6 +2497,10 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(cudaGetLastError());
       launches += 3;
       CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, s1));
+      if (h_area) {
+        CK(cudaMemcpyAsync(h_area, d_area, n * 4, cudaMemcpyDeviceToHost, s1));
+        CK(cudaMemcpyAsync(h_contact, d_contact, n, cudaMemcpyDeviceToHost, s1));
+      }
       CK(cudaStreamSynchronize(s1));
       CK(cudaEventElapsedTime(&v->timing[3], v->ev[0], v->ev[1]));
       over3 = v->h_counters[CNT_OVER3];
@@ -2389,12 +2573,7 @@ extern "C" int xs3d_area_batch(xs3d_volume* v, uint64_t n, const float* pos, con
     d_pos = (const float*)v->q_pos.p; d_nrm = (const float*)v->q_nrm.p;
     d_area = (float*)v->q_area.p; d_contact = (uint8_t*)v->q_contact.p;
   }
-  RET(area_batch_device(v, n, d_pos, d_nrm, anisotropy, d_area, d_contact, n < 4));
-  if (mem == XS3D_HOST) {
-    CK(cudaMemcpyAsync(area, d_area, n * 4, cudaMemcpyDeviceToHost, v->stream));
-    CK(cudaMemcpyAsync(contact, d_contact, n, cudaMemcpyDeviceToHost, v->stream));
-    CK(cudaStreamSynchronize(v->stream));
-  }
+  RET(area_batch_device(v, n, d_pos, d_nrm, anisotropy, d_area, d_contact, n < 4, mem == XS3D_HOST ? area : nullptr, mem == XS3D_HOST ? contact : nullptr));
   return XS3D_OK;
 }
 
@@ -2428,11 +2607,8 @@ extern "C" int xs3d_area_sweep_host(xs3d_volume* v, const uint8_t* binimg, int c
     CK(cudaEventRecord(v->ev[7], v->stream));
   }
   v->loaded = true;
-  RET(area_batch_device(v, n, (const float*)v->q_pos.p, (const float*)v->q_nrm.p, anisotropy, (float*)v->q_area.p, (uint8_t*)v->q_contact.p, n < 4));
+  RET(area_batch_device(v, n, (const float*)v->q_pos.p, (const float*)v->q_nrm.p, anisotropy, (float*)v->q_area.p, (uint8_t*)v->q_contact.p, n < 4, area, contact));
   CK(cudaEventElapsedTime(&v->timing[4], v->ev[6], v->ev[7]));
-  CK(cudaMemcpyAsync(area, v->q_area.p, n * 4, cudaMemcpyDeviceToHost, v->stream));
-  CK(cudaMemcpyAsync(contact, v->q_contact.p, n, cudaMemcpyDeviceToHost, v->stream));
-  CK(cudaStreamSynchronize(v->stream));
   trace(v, "results");
   return XS3D_OK;
 }

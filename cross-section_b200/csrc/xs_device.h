@@ -12,7 +12,7 @@ cudaStream_t xs_stream(const xs3d_volume* v);
 int xs_sm_count(const xs3d_volume* v);
 int xs_fail(int code, const char* msg);
 // growable device buffers owned by the volume: 0 sparse idx, 1 sparse val, 2 misc, 3 counters, 4-7 batched slices
-// (plan, row summaries, fill meta, host staging), 8 path B workspace
+// (plan, row summaries, fill meta, host staging), 8 path B workspace, 9 skeleton tangents
 int xs_buf(xs3d_volume* v, int which, size_t bytes, void** p);
 uint32_t* xs_pinned(xs3d_volume* v);   // 256 bytes of pinned host memory
 int xs_default_volume(uint64_t sx, uint64_t sy, uint64_t sz, xs3d_volume** out);

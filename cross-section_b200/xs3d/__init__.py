@@ -412,6 +412,37 @@ class Volume:
                                               area.ctypes.data, contact.ctypes.data))
     return (area, contact) if return_contact else area
 
+  def skeleton_tangents(self, vertices, edges):
+    """Unit tangent per skeleton vertex, computed on this volume's GPU (same definition as xs3d.skeleton_tangents).
+    vertices [M,3] (voxel coordinates) and edges [E,2]: ndarrays -> float32 ndarray; CUDA torch tensors -> CUDA tensor,
+    nothing crosses PCIe."""
+    if _is_torch_tensor(vertices):
+      import torch
+      if not vertices.is_cuda:
+        raise ValueError("torch inputs must be CUDA tensors (pass ndarrays for host buffers)")
+      vv = vertices.to(dtype=torch.float32).contiguous().reshape(-1, 3)
+      ee = (edges if _is_torch_tensor(edges) else torch.as_tensor(np.asarray(edges, dtype=np.int64))).to(device=vv.device, dtype=torch.int64).contiguous().reshape(-1, 2)
+      out = torch.empty_like(vv)
+      self._order_after_producers(vv)
+      _abi.check(self._lib.xs3d_skeleton_tangents(self._h, vv.shape[0], vv.data_ptr(), ee.shape[0], ee.data_ptr(), DEVICE, out.data_ptr()))
+      return out
+    vv = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    ee = np.ascontiguousarray(edges, dtype=np.int64).reshape(-1, 2)
+    out = np.empty_like(vv)
+    _abi.check(self._lib.xs3d_skeleton_tangents(self._h, vv.shape[0], vv.ctypes.data, ee.shape[0], ee.ctypes.data, HOST, out.ctypes.data))
+    return out
+
+  def sweep_skeleton(self, vertices, edges, anisotropy=None, return_contact=False):
+    """Cross-sectional area at every skeleton vertex, planes normal to the skeleton: tangents and sections both on the
+    device.  With CUDA tensors for vertices / edges the whole sweep stays in HBM."""
+    normals = self.skeleton_tangents(vertices, edges)
+    if _is_torch_tensor(vertices):
+      import torch
+      pos = vertices.to(dtype=torch.float32).contiguous().reshape(-1, 3)
+    else:
+      pos = np.ascontiguousarray(vertices, dtype=np.float32).reshape(-1, 3)
+    return self.cross_sectional_area_batch(pos, normals, anisotropy, return_contact)
+
   def cross_sectional_area(self, pos, normal, anisotropy=None, return_contact=False):
     pos, normal, anisotropy = _validate_vectors(pos, normal, anisotropy, 3)
     a, c = self.cross_sectional_area_batch(pos[None], normal[None], anisotropy, return_contact=True)
@@ -599,10 +630,12 @@ def skeleton_tangents(vertices, edges):
 def sweep_skeleton(binimg, vertices, edges, anisotropy=None, return_contact=False, device=0):
   """Cross-sectional area at every vertex of a skeleton (vertices [M,3] in voxel coordinates, edges [E,2]),
   section planes normal to the skeleton tangent — the use the reference is written for (README.md:59-71),
-  as one batched call.  `binimg` may be a bool ndarray or a resident Volume."""
-  normals = skeleton_tangents(vertices, edges)
-  pos = np.asarray(vertices, dtype=np.float32).reshape(-1, 3)
-  return cross_sectional_area_batch(binimg, pos, normals, anisotropy, return_contact, device=device)
+  as one batched call: tangents (Volume.skeleton_tangents) and sections are both computed on the device.
+  `binimg` may be a bool ndarray or a resident Volume."""
+  if isinstance(binimg, Volume):
+    return binimg.sweep_skeleton(vertices, edges, anisotropy, return_contact)
+  with Volume(binimg, device=device) as vol:
+    return vol.sweep_skeleton(vertices, edges, anisotropy, return_contact)
 
 
 def cross_sectional_area(

@@ -21,7 +21,7 @@ SYMBOLS = [
   "xs3d_volume_select_label", "xs3d_volume_cubes", "xs3d_volume_mark_loaded", "xs3d_volume_shape",
   "xs3d_area_batch", "xs3d_area_sweep_host", "xs3d_volume_stats", "xs3d_volume_profile", "xs3d_volume_timing", "xs3d_volume_set_stream",
   "xs3d_area", "xs3d_section", "xs3d_section_sparse", "xs3d_projection", "xs3d_projection_batch", "xs3d_projection_plan", "xs3d_projection_fill",
-  "xs3d_volume_labels_buffer",
+  "xs3d_volume_labels_buffer", "xs3d_skeleton_tangents",
   "xs3d_set_shape", "xs3d_set_shape_image", "xs3d_clear_shape",
 ]
 
@@ -78,6 +78,7 @@ def lib():
   L.xs3d_projection_plan.argtypes = [vp, u64, vp, vp, fp, C.c_int, C.c_float, C.c_int, vp, vp]
   L.xs3d_projection_fill.argtypes = [vp, u64, u64, vp, C.c_int]
   L.xs3d_volume_labels_buffer.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp), C.POINTER(u64)]
+  L.xs3d_skeleton_tangents.argtypes = [vp, u64, vp, u64, vp, C.c_int, vp]
   L.xs3d_set_shape.argtypes = [u64, u64, u64]
   L.xs3d_set_shape_image.argtypes = [vp, u64, u64, u64, C.c_int]
   for name in SYMBOLS:

@@ -92,6 +92,12 @@ int xs3d_volume_shape(xs3d_volume* vol, uint64_t shape[3]);
  *      Same per-query semantics as fastxs3d.area(..., slow_method=False)  (xs3d.hpp:1305-1365). */
 int xs3d_area_batch(xs3d_volume* vol, uint64_t n, const float* pos, const float* normal,
                     const float anisotropy[3], int mem, float* area, uint8_t* contact);
+/* Skeleton sweeps (the use the reference is written for, README.md:59-71): unit tangent per skeleton
+ * vertex from (vertices float32[n][3] in voxel coordinates, edges int64[m][2]), computed on the device — the normals
+ * of the section planes, ready for xs3d_area_batch with the same `mem`.  tangent = normalised sum of the incident edge
+ * directions, each flipped to agree with the vertex's first incident half-edge; (0, 0, 1) for an isolated vertex. */
+int xs3d_skeleton_tangents(xs3d_volume* vol, uint64_t n_vertices, const float* vertices, uint64_t n_edges,
+                           const int64_t* edges, int mem, float* normals);
 /* One whole sweep from host buffers in a single call: upload the queries, upload + ingest `binimg` into `vol`
  * (which must have the image's shape), run the batch, read areas + contacts back.  Equivalent to
  * xs3d_volume_load(HOST) followed by xs3d_area_batch(HOST), but with the copies ordered so that several sweeps in

@@ -417,11 +417,27 @@ def test_select_label_and_skeleton_sweep(xs, oracle):
           a, c = V.cross_sectional_area_batch(idx, nr, [32, 32, 40], return_contact=True)
           oa, oc = oracle.area_batch(mask, idx, nr, [32, 32, 40])
           assert np.array_equal(bits(a), bits(oa)) and np.array_equal(c, oc), (dt, label)
+  # skeleton sweep: tangents on the device (deterministic fixed-point sums), sections of the planes normal to them
+  import torch
   edges = np.stack([np.arange(len(verts) - 1), np.arange(1, len(verts))], 1)
-  a, c = xs.sweep_skeleton(vol, verts, edges, [32, 32, 40], return_contact=True)
-  nrm = xs.skeleton_tangents(verts, edges)
+  edges = np.concatenate([edges, [[5, 5], [0, len(verts) - 1]], edges[::7][:, ::-1]])      # a zero-length edge, a long one, reversed duplicates
+  with xs.Volume(vol) as V:
+    nrm = V.skeleton_tangents(verts, edges)
+    nrm2 = V.skeleton_tangents(verts, edges)
+    dn = V.skeleton_tangents(torch.from_numpy(verts.astype(np.float32)).cuda(), torch.from_numpy(edges).cuda())
+    a, c = V.sweep_skeleton(verts, edges, [32, 32, 40], return_contact=True)
+    da, dc = V.sweep_skeleton(torch.from_numpy(verts.astype(np.float32)).cuda(), torch.from_numpy(edges).cuda(), [32, 32, 40], return_contact=True)
+  host = xs.skeleton_tangents(verts, edges)
+  assert nrm.dtype == np.float32 and np.array_equal(bits(nrm), bits(nrm2)) and np.array_equal(bits(nrm), bits(dn.cpu().numpy()))
+  assert np.allclose(nrm, host, atol=2e-6) and np.allclose(np.linalg.norm(nrm, axis=1), 1, atol=1e-6)
   oa, oc = oracle.area_batch(vol, verts.astype(np.float32), nrm, [32, 32, 40])
   assert np.array_equal(bits(a), bits(oa)) and np.array_equal(c, oc)
+  assert np.array_equal(bits(da.cpu().numpy()), bits(oa)) and np.array_equal(dc.cpu().numpy(), oc)
+  a2 = xs.sweep_skeleton(vol, verts, edges, [32, 32, 40])
+  assert np.array_equal(bits(a2), bits(oa))
+  lone = xs.Volume(vol)
+  assert np.array_equal(lone.skeleton_tangents(verts[:3], np.zeros((0, 2), np.int64)), np.tile(np.float32([0, 0, 1]), (3, 1)))
+  lone.close()
 
 
 def test_select_label_occupancy_all_dtypes(xs):
