@@ -23,6 +23,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
       os.environ.get("TAG", ""), float(np.median(ts[3:])), min(ts), t["warp_tier_ms"], t["mid_tier_ms"], t["mid_exposed_ms"], t["prepass_ms"],
       t["polygon_ms"], t["combine_ms"], st["escalated_mid"], st["escalated_big"]), flush=True)
   sys.exit(0)
-for key in (20, 23, 26, 30):
+for key in (10, 14, 18, 22, 26, 32):
   env = dict(os.environ, XS3D_MID_KEY=str(key), TAG="key=%d" % key)
   subprocess.run([sys.executable, __file__, "child"], env=env)
