@@ -254,7 +254,9 @@ def run_own_arm(args):
   if rank == 0 and not os.environ.get("XS_BENCH_TWO_HANDLES"):
     # the e2e loop packs the (single) host volume on rank 0: all host cores but one per rank (each rank's main thread
     # spins on its GPU); the packing thread itself is one of the pool's workers
-    os.environ.setdefault("XS3D_HOST_THREADS", str(max(4, min(32, (os.cpu_count() or 8) - world))))
+    # (measured: 16-core box, N = 1: 14-15 threads best; 32-core box, N = 8: 16 threads 1.15-1.22 ms per step, 24 threads 1.37 ms —
+    # the other ranks' main threads and the broadcasters need cores too)
+    os.environ.setdefault("XS3D_HOST_THREADS", str(max(4, min(16, (os.cpu_count() or 8) - world))))
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
   if world > 1:
