@@ -261,6 +261,11 @@ def run_own_arm(args):
   dev = torch.device("cuda", local)
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
+  # everything below runs on a stream of its own, made torch's current stream: the library launches there
+  # (xs3d_volume_set_stream), torch's CUDA events bracket its work, and — unlike the legacy default stream — the stream can
+  # be captured, so the library replays each batch's launch sequence as a CUDA graph
+  bench_stream = torch.cuda.Stream(device=dev)
+  torch.cuda.set_stream(bench_stream)
 
   vol, pos, nrm = make_workload(rank)
   w = np.asarray(ANISOTROPY, np.float32)

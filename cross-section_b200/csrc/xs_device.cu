@@ -1571,11 +1571,13 @@ __global__ void __launch_bounds__(256) order_kernel(const uint8_t* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+static unsigned long long g_alloc_gen = 0;   // bumped whenever a device buffer moves: captured launch sequences are stale then
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
   int ensure(size_t bytes) {
     if (bytes <= cap) return XS3D_OK;
+    g_alloc_gen++;
     if (p) { cudaFree(p); p = nullptr; cap = 0; }
     size_t want = bytes + bytes / 8;
     cudaError_t e = cudaMalloc(&p, want);
@@ -1609,6 +1611,14 @@ struct xs3d_volume {
   DevBuf q_pos, q_nrm, q_area, q_contact, lists, counters, slab1, slab2, sec_idx, sec_val, misc;
   DevBuf polys, items, vals, geom, qinfo, slab_mid, keys;
   DevBuf polys2, items2, vals2;                        // record buffers of the second (mid / big tier) pipeline
+  // captured launch sequences of area_batch_device (CUDA graphs), keyed by everything baked into their nodes
+  struct BatchGraph {
+    unsigned long long gen = 0; uint64_t n = 0; const void* ptr[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float w[3] = {0, 0, 0}; int single = 0, mid_key = 0, factor = 0; uint64_t caps[5] = {0, 0, 0, 0, 0};
+    cudaGraphExec_t exec = nullptr; int launches = 0; unsigned long long used = 0;
+  };
+  std::vector<BatchGraph> graphs;
+  unsigned long long graph_clock = 0;
   DevBuf p2_order, p2_mask, p2_hash, p2_chunks, p2_recs;   // pools of the CTA tiers' second half (P2Pools)
   uint64_t p2_order_cap = 0, p2_rec_cap = 0;
   int p2_factor = 8;                                   // first-touch table slots per sample (x4 when a table fills up)
@@ -1742,6 +1752,7 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
                      &v->counters, &v->slab1, &v->slab2, &v->sec_idx, &v->sec_val, &v->misc,
                      &v->polys, &v->items, &v->vals, &v->geom, &v->qinfo, &v->slab_mid, &v->keys, &v->polys2, &v->items2, &v->vals2, &v->slab_wide,
                      &v->p2_order, &v->p2_mask, &v->p2_hash, &v->p2_chunks, &v->p2_recs };
+  for (auto& g : v->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (DevBuf* b : bufs) b->release();
   for (DevBuf& b : v->slice_bufs) b.release();
   v->visited.release();
@@ -2321,7 +2332,6 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
   cudaStream_t s1 = v->stream, s2 = v->stream2;
   int launches = 0;
   for (int attempt = 0; attempt < 8; attempt++) {
-    CK(cudaMemsetAsync(d_cnt, 0, CNT_TOTAL_WORDS * 4, s1));
     BatchArgs a;
     a.vol = view_of(v);
     a.pos = d_pos; a.nrm = d_nrm; a.wx = w[0]; a.wy = w[1]; a.wz = w[2];
@@ -2362,7 +2372,20 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     float* vals1 = (float*)v->vals.p;
     float* vals2 = (float*)v->vals2.p;
     const unsigned cgrid_combine = (unsigned)std::min<uint64_t>(n, 65535ull * 16);
-    CK(cudaEventRecord(v->evb[0], s1));
+    // ---- everything from here to the read-back of the counters is one fixed launch sequence for given buffers and n.
+    //      XS3D_GRAPH=1 captures it into a CUDA graph the first time and replays it afterwards (one driver call instead
+    //      of ~50 on the host; timing events become external event nodes so that xs3d_volume_timing keeps working).
+    //      OFF by default: measured on B200 (profiles/r2j_cuda_graph_replay.txt) the replayed sweep takes 1.05 ms against
+    //      0.74 ms launched directly — the graph executor does not reproduce the co-residency of the three streams (the
+    //      mid tier runs alone first: 0.21 ms, then the warp tier: 0.49 ms), which is what the launch order and the stream
+    //      priorities of the direct path arrange.
+    bool capturing = false;
+    auto rec_t = [&](cudaEvent_t ev, cudaStream_t st) -> cudaError_t {
+      return capturing ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
+    };
+    auto enqueue = [&]() -> int {
+    CK(cudaMemsetAsync(d_cnt, 0, CNT_TOTAL_WORDS * 4, s1));
+    CK(rec_t(v->evb[0], s1));
     if (!single) {
       // pre-pass: size estimate per query -> list ordered largest first; its head goes straight to the mid tier
       const int cgrid = (int)std::min<uint64_t>((n + 7) / 8, (uint64_t)v->sm_count * 8);
@@ -2372,7 +2395,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       order_kernel<<<ogrid, 256, 0, s1>>>((const uint8_t*)v->keys.p, d_cnt + CNT_HIST, d_cnt + CNT_CURSOR, sorted, (uint32_t)n, d_cnt + CNT_NBIG, v->mid_key ? v->mid_key : MID_BIG_KEY);
       CK(cudaGetLastError());
       launches += 2;
-      CK(cudaEventRecord(v->evb[1], s1));
+      CK(rec_t(v->evb[1], s1));
       // ---- residency plan per SM (228 KB of shared memory): two warp-tier CTAs (2 x 74.4 KB) + one mid-tier CTA
       //      (78.5 KB).  The warp tier is therefore launched as TWO grids pulling from the same queue: A (2 CTAs per SM)
       //      on the launching stream and B (1 CTA per SM) on a third stream.  The mid tier's stream has the higher
@@ -2382,12 +2405,12 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(cudaEventRecord(v->evf[0], s1));
       CK(cudaStreamWaitEvent(s2, v->evf[0], 0));
       a.out = out2; a.done_list = done2; a.list_in = sorted; a.list_out = list1;
-      CK(cudaEventRecord(v->evs[0], s2));
+      CK(rec_t(v->evs[0], s2));
       area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, -1);
       CK(cudaGetLastError());
-      CK(cudaEventRecord(v->evs[1], s2));
+      CK(rec_t(v->evs[1], s2));
       RET(launch_p2(s2));        // the sections parked so far: their second half runs beside the rest of the warp tier
-      CK(cudaEventRecord(v->evs[5], s2));
+      CK(rec_t(v->evs[5], s2));
       // profiling aid: under ncu every kernel runs alone, so the split of the warp tier into grids A and B would show
       // grid B (10 warps per SM) doing all the work; XS3D_SINGLE_GRID=1 launches the warp tier as one grid of 3 CTAs per SM
       const bool single_grid = getenv("XS3D_SINGLE_GRID") != nullptr;
@@ -2406,7 +2429,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(cudaGetLastError());
       CK(cudaEventRecord(v->evf[1], s1));
       CK(cudaStreamWaitEvent(s1, v->evf[3], 0));       // the polygon kernel needs grid B's records too
-      CK(cudaEventRecord(v->evb[2], s1));
+      CK(rec_t(v->evb[2], s1));
       launches += 3;
       // ---- second stream: late hand-overs (after the warp tier), big tier, its own polygon + combine kernels
       CK(cudaStreamWaitEvent(s2, v->evf[1], 0));
@@ -2414,7 +2437,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       a.out = out2; a.done_list = done2; a.list_in = sorted; a.list_out = list1;
       area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, -1);
       CK(cudaGetLastError());
-      CK(cudaEventRecord(v->evs[2], s2));
+      CK(rec_t(v->evs[2], s2));
       // what leaves the mid tier's window: wide tier (same walk, 416-cell window), then the big tier's bitmap walk
       a.list_in = list1; a.list_out = listw;
       area_wide_kernel<<<v->wide_ctas, WideTier::THREADS, WIDE_SMEM_BYTES, s2>>>(a, v->cfg_wide, CNT_NEXTW, CNT_OVERW, d_cnt + CNT_OVER1, 10);
@@ -2423,18 +2446,18 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       area_block_kernel<BigTier><<<v->sm_count, BigTier::THREADS, block_smem_bytes(v), s2>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVERW, 10);
       CK(cudaGetLastError());
       launches++;
-      CK(cudaEventRecord(v->evs[3], s2));
+      CK(rec_t(v->evs[3], s2));
       a.out = out2; a.done_list = done2;
       RET(launch_p2(s2));        // what the late hand-overs, the wide and the big tier parked
       poly_eval_kernel<<<v->sm_count * 4, 256, 0, s2>>>(out2.polys, out2.geom, vals2, d_emit2, 0u, out2.poly_cap);
       CK(cudaGetLastError());
       combine_kernel<<<(unsigned)std::min<uint64_t>(n, 1024), 128, 0, s2>>>(out2.items, vals2, out2.qinfo, done2, d_cnt + CNT_DONE2, (uint32_t)n, d_area, d_contact, QS_READY2);
       CK(cudaGetLastError());
-      CK(cudaEventRecord(v->evs[4], s2));
+      CK(rec_t(v->evs[4], s2));
       CK(cudaEventRecord(v->evf[2], s2));
       launches += 4;
     } else {
-      CK(cudaEventRecord(v->evb[1], s1));
+      CK(rec_t(v->evb[1], s1));
       // tiny batches (single calls): mid tier first — a section of a few thousand cells takes a fraction of the big
       // tier's time there — then the big tier for what does not fit its window
       a.out = out1; a.done_list = nullptr; a.list_in = nullptr; a.list_out = list1;
@@ -2448,22 +2471,81 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(cudaGetLastError());
       a.out = out1; a.done_list = nullptr;
       RET(launch_p2(s1));
-      CK(cudaEventRecord(v->evb[2], s1));
+      CK(rec_t(v->evb[2], s1));
       launches += 3;
     }
     poly_eval_kernel<<<v->sm_count * 8, 256, 0, s1>>>(out1.polys, out1.geom, vals1, d_emit1, 0u, out1.poly_cap);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(v->evb[3], s1));
+    CK(rec_t(v->evb[3], s1));
     combine_kernel<<<cgrid_combine, 128, 0, s1>>>(out1.items, vals1, out1.qinfo, nullptr, nullptr, (uint32_t)n, d_area, d_contact, QS_READY);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(v->evb[4], s1));
+    CK(rec_t(v->evb[4], s1));
     launches += 2;
     if (!single) CK(cudaStreamWaitEvent(s1, v->evf[2], 0));   // join
-    CK(cudaEventRecord(v->evb[5], s1));
+    CK(rec_t(v->evb[5], s1));
     CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, s1));
     if (h_area) {            // host callers: the results come down behind the kernels, under the same (single) host wait
       CK(cudaMemcpyAsync(h_area, d_area, n * 4, cudaMemcpyDeviceToHost, s1));
       CK(cudaMemcpyAsync(h_contact, d_contact, n, cudaMemcpyDeviceToHost, s1));
+    }
+    return XS3D_OK;
+    };   // enqueue
+    static const bool no_graph = getenv("XS3D_GRAPH") == nullptr;
+    // (a pageable result buffer makes cudaMemcpyAsync synchronous, which a capture forbids: only pinned / device results)
+    bool use_graph = !no_graph && s1 != nullptr && s1 != cudaStreamLegacy && s1 != cudaStreamPerThread;   // (the default streams cannot be captured)
+    if (use_graph && h_area) {
+      cudaPointerAttributes pa;
+      if (cudaPointerGetAttributes(&pa, h_area) != cudaSuccess || pa.type != cudaMemoryTypeHost) use_graph = false;
+      if (use_graph && (cudaPointerGetAttributes(&pa, h_contact) != cudaSuccess || pa.type != cudaMemoryTypeHost)) use_graph = false;
+      cudaGetLastError();
+    }
+    if (!use_graph) {
+      launches = 0;
+      RET(enqueue());
+    } else {
+      xs3d_volume::BatchGraph key;
+      key.gen = g_alloc_gen; key.n = n;
+      const void* kp[7] = { d_pos, d_nrm, d_area, d_contact, h_area, h_contact, v->cubes.p };
+      for (int i = 0; i < 7; i++) key.ptr[i] = kp[i];
+      key.w[0] = w[0]; key.w[1] = w[1]; key.w[2] = w[2];
+      key.single = single ? 1 : 0; key.mid_key = v->mid_key; key.factor = v->p2_factor;
+      key.caps[0] = v->poly_cap; key.caps[1] = v->poly_cap2; key.caps[2] = v->p2_order_cap; key.caps[3] = v->p2_rec_cap; key.caps[4] = (uint64_t)(uintptr_t)s1;
+      xs3d_volume::BatchGraph* hit = nullptr;
+      for (auto& g : v->graphs)
+        if (g.exec && g.gen == key.gen && g.n == key.n && !memcmp(g.ptr, key.ptr, sizeof(key.ptr)) && !memcmp(g.w, key.w, 12) && g.single == key.single &&
+            g.mid_key == key.mid_key && g.factor == key.factor && !memcmp(g.caps, key.caps, sizeof(key.caps))) { hit = &g; break; }
+      if (!hit) {
+        launches = 0;
+        CK(cudaStreamBeginCapture(s1, cudaStreamCaptureModeThreadLocal));
+        capturing = true;
+        const int rc = enqueue();
+        capturing = false;
+        cudaGraph_t graph = nullptr;
+        const cudaError_t ee = cudaStreamEndCapture(s1, &graph);
+        if (rc != XS3D_OK) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+        CK(ee);
+        cudaGraphExec_t exec = nullptr;
+        const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CK(ei);
+        // keep at most 8 sequences per volume: drop the least recently used one (and every stale one)
+        for (auto& g : v->graphs)
+          if (g.exec && g.gen != key.gen) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+        xs3d_volume::BatchGraph* slot = nullptr;
+        for (auto& g : v->graphs) if (!g.exec) { slot = &g; break; }
+        if (!slot && v->graphs.size() < 8) { v->graphs.emplace_back(); slot = &v->graphs.back(); }
+        if (!slot) {
+          slot = &v->graphs[0];
+          for (auto& g : v->graphs) if (g.used < slot->used) slot = &g;
+          cudaGraphExecDestroy(slot->exec);
+        }
+        key.exec = exec; key.launches = launches;
+        *slot = key;
+        hit = slot;
+      }
+      hit->used = ++v->graph_clock;
+      launches = hit->launches;
+      CK(cudaGraphLaunch(hit->exec, s1));
     }
     trace(v, "launched");
     CK(host_wait(v, s1));

@@ -8,6 +8,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
   from xs3d import synthetic as syn
   vol, verts, tans = syn.make_neurite(512)
   pos, nrm = syn.draw_queries(verts, tans, 10000)
+  torch.cuda.set_stream(torch.cuda.Stream())
   V = xs3d.Volume(vol)
   V.set_stream(torch.cuda.current_stream().cuda_stream)
   dpos = torch.from_numpy(pos).cuda(); dnrm = torch.from_numpy(nrm).cuda()
