@@ -1620,7 +1620,7 @@ struct xs3d_volume {
   std::vector<BatchGraph> graphs;
   unsigned long long graph_clock = 0;
   DevBuf p2_order, p2_mask, p2_hash, p2_chunks, p2_recs;   // pools of the CTA tiers' second half (P2Pools)
-  uint64_t p2_order_cap = 0, p2_rec_cap = 0;
+  uint64_t p2_order_cap = 0, p2_rec_cap = 0, p2_hash_min_words = 0;
   int p2_factor = 8;                                   // first-touch table slots per sample (x4 when a table fills up)
   DevBuf slice_bufs[6];                                // batched slices: plan, row summaries, fill meta, host staging; path B workspace; skeleton tangents
   DevBuf visited;                                      // path B: one bit per voxel, all zero between calls
@@ -2229,6 +2229,12 @@ static SlabCfg make_cfg(const xs3d_volume* v, bool worst_case) {
   return s;
 }
 
+// words of the first-touch table pool: 2 x pow2(>= factor x samples) per parked section, at least 2 x 1024
+static uint64_t p2_hash_words(const xs3d_volume* v) {
+  const uint64_t w = std::max<uint64_t>(v->p2_order_cap * 4ull * (uint64_t)v->p2_factor + 4096ull * v->p2_rec_cap, v->p2_hash_min_words);
+  return std::min<uint64_t>(w, 0xffffffffull);
+}
+
 static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
   RET(configure_kernels(v));
   RET(v->q_pos.ensure(n * 12 + 64));
@@ -2280,12 +2286,17 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
     // pool doubles and the batch runs again (like the record buffers)
     const long long m = std::max(v->sx, std::max(v->sy, v->sz));
     const uint64_t worst_n = (uint64_t)(1.5 * (double)m * (double)m) + 16ull * m + 4096ull;
-    if (v->p2_order_cap == 0) v->p2_order_cap = std::max<uint64_t>(1ull << 20, worst_n + (1ull << 19));
+    if (v->p2_order_cap == 0) {
+      v->p2_order_cap = std::max<uint64_t>(1ull << 20, worst_n + (1ull << 19));
+      // dev / test knobs: start with small pools or sparse tables so that the grow-and-rerun paths are exercised
+      if (const char* e = getenv("XS3D_P2_ORDER_CAP")) v->p2_order_cap = std::max<uint64_t>(256, strtoull(e, nullptr, 10));
+      if (const char* e = getenv("XS3D_P2_FACTOR")) v->p2_factor = std::max(1, atoi(e));
+    }
     v->p2_order_cap = std::min<uint64_t>(v->p2_order_cap, 0x7fffffffull);
     v->p2_rec_cap = std::max<uint64_t>(v->p2_rec_cap, n);
     RET(v->p2_order.ensure(v->p2_order_cap * 4 + 64));
     RET(v->p2_mask.ensure(v->p2_order_cap * 4 + 64));
-    RET(v->p2_hash.ensure(std::min<uint64_t>(v->p2_order_cap * 4ull * (uint64_t)v->p2_factor + 4096ull * v->p2_rec_cap, 0xffffffffull) * 4 + 64));
+    RET(v->p2_hash.ensure(p2_hash_words(v) * 4 + 64));
     RET(v->p2_chunks.ensure((v->p2_order_cap / P2_CHUNK + v->p2_rec_cap + 64) * 5 * 4 + 64));
     RET(v->p2_recs.ensure(v->p2_rec_cap * sizeof(P2Rec) + 64));
   }
@@ -2343,7 +2354,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       p.cursors = d_cnt + 72;
       p.order = (uint32_t*)v->p2_order.p; p.mask = (uint32_t*)v->p2_mask.p; p.order_cap = (uint32_t)v->p2_order_cap;
       p.hash = (uint32_t*)v->p2_hash.p;
-      p.hash_cap = (uint32_t)std::min<uint64_t>(v->p2_order_cap * 4ull * (uint64_t)v->p2_factor + 4096ull * v->p2_rec_cap, 0xffffffffull);
+      p.hash_cap = (uint32_t)p2_hash_words(v);
       p.chunk_cap = (uint32_t)(v->p2_order_cap / P2_CHUNK + v->p2_rec_cap + 32);
       uint32_t* c5 = (uint32_t*)v->p2_chunks.p;
       const size_t cs = (size_t)p.chunk_cap + 1;
@@ -2601,8 +2612,11 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       if (he1[2] != 0) { v->poly_cap *= 2; v->item_cap *= 2; }
       if (he2[2] != 0) { v->poly_cap2 *= 2; v->item_cap2 *= 2; }
       if (p2_full) {
+        // the cursors kept counting past the capacities: they say how much this batch needs
         if (v->p2_order_cap >= 0x7fffffffull) return fail(XS3D_ERR_CAPACITY, "sample pool would exceed 2^31 entries; split the batch");
-        v->p2_order_cap *= 2;
+        const uint64_t need_order = (uint64_t)hp2[P2C_ORDER] + (uint64_t)hp2[P2C_ORDER] / 4 + 1024, need_hash = (uint64_t)hp2[P2C_HASH] + (uint64_t)hp2[P2C_HASH] / 4 + 4096;
+        v->p2_order_cap = std::min<uint64_t>(std::max<uint64_t>(2 * v->p2_order_cap, need_order), 0x7fffffffull);
+        v->p2_hash_min_words = std::max<uint64_t>(v->p2_hash_min_words, need_hash);
       }
       if (p2_hashfull) {
         if (v->p2_factor >= 512) return fail(XS3D_ERR_CAPACITY, "a first-touch table filled up at 512 slots per sample");

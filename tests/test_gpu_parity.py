@@ -742,3 +742,36 @@ def test_cross_section_component_topologies(xs, oracle):
       assert ct == oct_ and np.array_equal(idx[order], oidx) and np.array_equal(bits(val[order]), bits(oval)), (name, k)
       order2 = np.argsort(idx2)
       assert ct2 == ct and np.array_equal(idx2[order2], oidx) and np.array_equal(bits(val2[order2]), bits(oval)), (name, k, "second call")
+
+
+def test_p2_pools_grow_and_rerun(xs, oracle):
+  """The rarely taken paths of the CTA tiers' second half: a sample pool that is too small (doubles, the batch runs
+  again) and first-touch tables that fill up (slots per sample x4, again) — forced through the dev knobs in a fresh
+  process, results bit-identical to the oracle."""
+  import subprocess, sys, os, textwrap
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  code = textwrap.dedent('''
+    import sys, numpy as np
+    sys.path.insert(0, r"%s/cross-section_b200"); sys.path.insert(0, r"%s/oracle")
+    import xs3d, refapi
+    from xs3d import synthetic
+    vol, verts, tans = synthetic.make_neurite(256, seed=0)
+    qp, qn = synthetic.draw_queries(verts, tans, 600, seed=3)
+    cyl, axis = synthetic.make_cylinder()
+    w = [32, 32, 40]
+    orc = refapi.Oracle()
+    with xs3d.Volume(vol) as V:
+      a, c = V.cross_sectional_area_batch(qp, qn, w, return_contact=True)
+      st = V.stats()
+    oa, oc = orc.area_batch(vol, qp, qn, w)
+    assert st["escalated_mid"] > 0
+    assert np.array_equal(a.view(np.uint32), oa.view(np.uint32)) and np.array_equal(c, oc)
+    with xs3d.Volume(cyl) as V:
+      r = V.cross_sectional_area((256, 256, 256), axis, w, return_contact=True)
+    o = orc.area(cyl, (256, 256, 256), axis, w)
+    assert np.float32(r[0]).view(np.uint32) == np.float32(o[0]).view(np.uint32) and r[1] == o[1]
+    print("ok")
+  ''' % (root, root))
+  for env in ({"XS3D_P2_ORDER_CAP": "300"}, {"XS3D_P2_FACTOR": "1"}, {"XS3D_P2_ORDER_CAP": "256", "XS3D_P2_FACTOR": "1"}):
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, (env, (r.stdout + r.stderr)[-2000:])
