@@ -1154,6 +1154,8 @@ constexpr int P2_LCAP = 2048;               // local table slots (a chunk touche
 constexpr int P2_LPROBE = 32;
 __global__ void __launch_bounds__(P2_CHUNK) p2_claims_kernel(BatchArgs a) {
   __shared__ uint32_t s_tag[P2_LCAP], s_key[P2_LCAP];
+  __shared__ uint16_t s_list[P2_LCAP];
+  __shared__ int s_wsum[P2_CHUNK / 32];
   const uint32_t nchunks = min(a.p2.cursors[P2C_CHUNK], a.p2.chunk_cap), chunk_start = a.p2.cursors[P2C_DONE];
   if (a.p2.cursors[P2C_FULL]) return;
   for (uint32_t chunk = chunk_start + blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
@@ -1195,12 +1197,35 @@ __global__ void __launch_bounds__(P2_CHUNK) p2_claims_kernel(BatchArgs a) {
       }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < P2_LCAP; i += P2_CHUNK) {
-      const uint32_t t = s_tag[i];
-      if (t == XS_HEMPTY) continue;
-      const int won = k.H.claim_tag(t, s_key[i]);
-      if (won == 0) ovf = true;
-      if (won != 2) s_key[i] = XS_HEMPTY;                        // a smaller rank of another chunk holds the block
+    // the occupied slots (a few hundred of 2048), listed densely so that every thread sends one or two claims instead of
+    // walking eight mostly empty slots with their dependent L2 round trips
+    {
+      uint32_t mine = 0u;
+#pragma unroll
+      for (int j = 0; j < P2_LCAP / P2_CHUNK; j++) mine |= (s_tag[threadIdx.x * (P2_LCAP / P2_CHUNK) + j] != XS_HEMPTY ? 1u : 0u) << j;
+      const int cnt = __popc(mine);
+      int inc = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if ((threadIdx.x & 31) >= d) inc += t;
+      }
+      if ((threadIdx.x & 31) == 31) s_wsum[threadIdx.x >> 5] = inc;
+      __syncthreads();
+      int base = 0, total = 0;
+#pragma unroll
+      for (int w = 0; w < P2_CHUNK / 32; w++) { const int t = s_wsum[w]; if (w < (int)(threadIdx.x >> 5)) base += t; total += t; }
+      int o = base + inc - cnt;
+#pragma unroll
+      for (int j = 0; j < P2_LCAP / P2_CHUNK; j++)
+        if ((mine >> j) & 1u) s_list[o++] = (uint16_t)(threadIdx.x * (P2_LCAP / P2_CHUNK) + j);
+      __syncthreads();
+      for (int e = threadIdx.x; e < total; e += P2_CHUNK) {
+        const int i = s_list[e];
+        const int won = k.H.claim_tag(s_tag[i], s_key[i]);
+        if (won == 0) ovf = true;
+        if (won != 2) s_key[i] = XS_HEMPTY;                      // a smaller rank of another chunk holds the block
+      }
     }
     __syncthreads();
     if (live) {
@@ -1223,44 +1248,85 @@ __global__ void __launch_bounds__(P2_CHUNK) p2_claims_kernel(BatchArgs a) {
   }
 }
 
-// ownership -> adjacency -> plane distance: kept masks, items / polygons per chunk (emit_items pass 1)
+// ownership -> adjacency -> plane distance: kept masks, items / polygons per chunk (emit_items pass 1).  A sample has 0-5
+// tentative blocks, most have one or two: the (sample, offset) pairs of the chunk are listed densely in shared memory and
+// evaluated one per thread, so that the three dependent L2 round trips of a pair (table tag, table rank, occupancy byte)
+// are paid once or twice per chunk instead of up to five times by a few lanes.
+constexpr int P2_PAIRS = 2048;
+__device__ __forceinline__ bool p2_keep_pair(const BatchArgs& a, const P2Chunk& k, const PlaneCtx& c, int r, int kk, int* polys) {
+  const Sample s = sample_at(c, k.A, r, (V3*)nullptr);
+  const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
+  int ox, oy, oz;
+  decode_k(kk, ox, oy, oz);
+  if (k.H.owner(bx + ox, by + oy, bz + oz) != (uint32_t)r) return false;          // someone with a smaller rank touched it first
+  const uint32_t centre = cube_at(a.vol, bx, by, bz);
+  const uint32_t cand = cube_at(a.vol, bx + ox, by + oy, bz + oz);
+  if (!blocks_adjacent(centre, cand, ox, oy, oz)) return false;                   // visited, but contributes nothing
+  const V3 ctr = vadd(mk((float)(2 * (bx + ox)), (float)(2 * (by + oy)), (float)(2 * (bz + oz))), mk(0.5f, 0.5f, 0.5f));
+  if (fabsf(vdot(vsub(ctr, c.g.pos), c.g.n)) > XS_FAR2) return false;             // block value is exactly 0
+  *polys = item_polys(cand);
+  return true;
+}
 __global__ void __launch_bounds__(P2_CHUNK) p2_emit1_kernel(BatchArgs a) {
   __shared__ int sh_sum[2][P2_CHUNK / 32];
+  __shared__ int s_wsum[P2_CHUNK / 32];
+  __shared__ uint32_t s_keep[P2_CHUNK];
+  __shared__ uint16_t s_pairs[P2_PAIRS];
   const uint32_t nchunks = min(a.p2.cursors[P2C_CHUNK], a.p2.chunk_cap), chunk_start = a.p2.cursors[P2C_DONE];
   if (a.p2.cursors[P2C_FULL] || a.p2.cursors[P2C_HASHFULL]) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (uint32_t chunk = chunk_start + blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
     P2Chunk k;
     p2_chunk_setup(a, chunk, k);
     const PlaneCtx& c = k.rec->c;
     int my_items = 0, my_polys = 0;
-    __syncthreads();                       // (sh_sum of the previous chunk has been read)
-    if (k.r < (int)k.n) {
-      uint32_t tent = k.A.mask[k.r], keep = 0u;
-      if (tent) {
-        const Sample s = sample_at(c, k.A, k.r, (V3*)nullptr);
-        const int bx = s.rx >> 1, by = s.ry >> 1, bz = s.rz >> 1;
-        const uint32_t centre = cube_at(a.vol, bx, by, bz);
-        while (tent) {
-          const int kk = __ffs(tent) - 1;
-          tent &= tent - 1u;
-          int ox, oy, oz;
-          decode_k(kk, ox, oy, oz);
-          if (k.H.owner(bx + ox, by + oy, bz + oz) != (uint32_t)k.r) continue;     // someone with a smaller rank touched it first
-          const uint32_t cand = cube_at(a.vol, bx + ox, by + oy, bz + oz);
-          if (!blocks_adjacent(centre, cand, ox, oy, oz)) continue;                // visited, but contributes nothing
-          const V3 ctr = vadd(mk((float)(2 * (bx + ox)), (float)(2 * (by + oy)), (float)(2 * (bz + oz))), mk(0.5f, 0.5f, 0.5f));
-          if (fabsf(vdot(vsub(ctr, c.g.pos), c.g.n)) > XS_FAR2) continue;          // block value is exactly 0
-          keep |= 1u << kk;
-          my_items++;
-          my_polys += item_polys(cand);
-        }
+    const bool live = k.r < (int)k.n;
+    const uint32_t tent = live ? k.A.mask[k.r] : 0u;
+    const int cnt = __popc(tent);
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    __syncthreads();                       // (the shared arrays of the previous chunk have been read)
+    if (lane == 31) s_wsum[warp] = inc;
+    s_keep[threadIdx.x] = 0u;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < P2_CHUNK / 32; w++) { const int t = s_wsum[w]; if (w < warp) base += t; total += t; }
+    const int r0 = k.r - (int)threadIdx.x;                       // rank of thread 0
+    if (total <= P2_PAIRS) {
+      int o = base + inc - cnt;
+      uint32_t m = tent;
+      while (m) {
+        const int kk = __ffs(m) - 1;
+        m &= m - 1u;
+        s_pairs[o++] = (uint16_t)((threadIdx.x << 5) | kk);
+      }
+      __syncthreads();
+      for (int e = threadIdx.x; e < total; e += P2_CHUNK) {
+        const int pr = s_pairs[e], t = pr >> 5, kk = pr & 31;
+        int polys;
+        if (p2_keep_pair(a, k, c, r0 + t, kk, &polys)) { atomicOr(&s_keep[t], 1u << kk); my_items++; my_polys += polys; }
+      }
+      __syncthreads();
+      if (live) k.A.mask[k.r] = s_keep[threadIdx.x];
+    } else if (live) {
+      uint32_t m = tent, keep = 0u;
+      while (m) {
+        const int kk = __ffs(m) - 1;
+        m &= m - 1u;
+        int polys;
+        if (p2_keep_pair(a, k, c, k.r, kk, &polys)) { keep |= 1u << kk; my_items++; my_polys += polys; }
       }
       k.A.mask[k.r] = keep;
     }
     __syncwarp();
     my_items = __reduce_add_sync(0xffffffffu, my_items);
     my_polys = __reduce_add_sync(0xffffffffu, my_polys);
-    if ((threadIdx.x & 31) == 0) { sh_sum[0][threadIdx.x >> 5] = my_items; sh_sum[1][threadIdx.x >> 5] = my_polys; }
+    if (lane == 0) { sh_sum[0][warp] = my_items; sh_sum[1][warp] = my_polys; }
     __syncthreads();
     if (threadIdx.x == 0) {
       int ti = 0, tp = 0;
