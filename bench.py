@@ -307,7 +307,7 @@ def run_own_arm(args):
   starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
   ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
   kern = {"prepass_ms": 0.0, "warp_tier_ms": 0.0, "polygon_ms": 0.0, "combine_ms": 0.0, "mid_exposed_ms": 0.0,
-          "mid_tier_ms": 0.0, "mid_second_launch_ms": 0.0, "big_tier_ms": 0.0, "second_stream_poly_combine_ms": 0.0, "worst_case_ms": 0.0}
+          "mid_tier_ms": 0.0, "mid_second_launch_ms": 0.0, "p2_ms": 0.0, "second_stream_poly_combine_ms": 0.0, "second_round_ms": 0.0, "worst_case_ms": 0.0}
   launches = 0
   stats = None
   for i in range(args.steps):
@@ -627,7 +627,7 @@ def run_own_arm(args):
             "volume_resident": {"value": e2e_res_value, "ms_per_step": ms_e2e_res / args.steps, "h2d_bytes_per_step": int(2 * pos.nbytes)}},
     "gpu_launches": int(launches) * world,
     "kernels_ms_per_step": {k: v / args.steps for k, v in kern.items()},
-    "kernels_note": "launching stream: prepass -> warp_tier -> polygon -> combine -> mid_exposed (wait for the second stream); second stream, concurrent: mid_tier -> mid_second_launch -> big_tier -> second_stream_poly_combine",
+    "kernels_note": "launching stream: prepass -> warp_tier -> polygon -> combine -> mid_exposed (wait for the second stream); second stream, concurrent: mid_tier (floods) -> mid_second_launch (late hand-overs, after the warp tier) -> p2 (claims / ownership / records of the parked sections) -> second_stream_poly_combine; second_round: wide / big tiers after a host round trip, only when a section left the mid tier's window",
     "work_per_step": {k: int(stats[k]) for k in ("samples", "blocks", "polygons", "cells_tested", "escalated_mid", "escalated_big", "escalated_worst_case")},
     "roofline": roofline,
     "cpu_baseline": {"value": rate, "unit": "cross-sections/s", "cores": cores, "kind": kind, "one_core": _G.get("one_core_rate"),

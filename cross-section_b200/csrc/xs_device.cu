@@ -1697,7 +1697,7 @@ struct xs3d_volume {
   cudaEvent_t evs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // batch timing, second stream
   cudaStream_t stream2 = nullptr;                      // the mid tier runs here, beside the warp tier
   cudaStream_t stream3 = nullptr;                      // third warp-tier CTA per SM (moves in when the mid-tier CTA retires)
-  cudaEvent_t evf[4] = {nullptr, nullptr, nullptr, nullptr};    // fork, warp-tier grid A done, second stream done, warp-tier grid B done
+  cudaEvent_t evf[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};    // fork, warp-tier grid A done, second stream done, warp-tier grid B done, mid tier's first launch done
   SlabCfg cfg_mid{}, cfg_wide{};
   DevBuf slab_wide;
   int wide_ctas = 0;
@@ -1792,7 +1792,7 @@ extern "C" int xs3d_volume_create(int device, uint64_t sx, uint64_t sy, uint64_t
     CK(cudaStreamCreateWithPriority(&v->stream3, cudaStreamNonBlocking, prio_lo));
   }
   for (int i = 0; i < 8; i++) CK(cudaEventCreate(&v->ev[i]));
-  for (int i = 0; i < 4; i++) CK(cudaEventCreateWithFlags(&v->evf[i], cudaEventDisableTiming));
+  for (int i = 0; i < 5; i++) CK(cudaEventCreateWithFlags(&v->evf[i], cudaEventDisableTiming));
   for (int i = 0; i < 6; i++) CK(cudaEventCreate(&v->evb[i]));
   for (int i = 0; i < 6; i++) CK(cudaEventCreate(&v->evs[i]));
   RET(v->cubes.ensure(hx * hy * hz + 64));
@@ -1811,7 +1811,7 @@ extern "C" int xs3d_volume_destroy(xs3d_volume* v) {
   for (int i = 0; i < 2; i++) { if (v->stage_ev[i]) cudaEventDestroy(v->stage_ev[i]); if (v->stage_copy_ev[i]) cudaEventDestroy(v->stage_copy_ev[i]); v->staged[i].release(); v->staged_cubes[i].release(); if (v->h_stage_bits[i]) cudaFreeHost(v->h_stage_bits[i]); }
   for (int i = 0; i < 8; i++) if (v->ev[i]) cudaEventDestroy(v->ev[i]);
   if (v->ev_block) cudaEventDestroy(v->ev_block);
-  for (int i = 0; i < 4; i++) if (v->evf[i]) cudaEventDestroy(v->evf[i]);
+  for (int i = 0; i < 5; i++) if (v->evf[i]) cudaEventDestroy(v->evf[i]);
   for (int i = 0; i < 6; i++) if (v->evb[i]) cudaEventDestroy(v->evb[i]);
   for (int i = 0; i < 6; i++) if (v->evs[i]) cudaEventDestroy(v->evs[i]);
   DevBuf* bufs[] = { &v->cubes, &v->raw, &v->dbits, &v->labels, &v->q_pos, &v->q_nrm, &v->q_area, &v->q_contact, &v->lists,
@@ -2486,16 +2486,19 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, -1);
       CK(cudaGetLastError());
       CK(rec_t(v->evs[1], s2));
-      RET(launch_p2(s2));        // the sections parked so far: their second half runs beside the rest of the warp tier
-      CK(rec_t(v->evs[5], s2));
+      CK(cudaEventRecord(v->evf[4], s2));
       // profiling aid: under ncu every kernel runs alone, so the split of the warp tier into grids A and B would show
       // grid B (10 warps per SM) doing all the work; XS3D_SINGLE_GRID=1 launches the warp tier as one grid of 3 CTAs per SM
       const bool single_grid = getenv("XS3D_SINGLE_GRID") != nullptr;
-      // ---- third stream: warp-tier grid B
+      // ---- third stream: warp-tier grid B, the third warp-tier CTA per SM.  It starts when the mid tier's first launch has
+      //      ended: launched beside it, its CTAs sometimes took the third slot of every SM before the mid tier's did, and
+      //      the mid tier then ran after the warp tier instead of beside it (0.77 instead of 0.69 ms, for a whole process)
       CK(cudaStreamWaitEvent(v->stream3, v->evf[0], 0));
+      CK(cudaStreamWaitEvent(v->stream3, v->evf[4], 0));
       a.out = out1; a.done_list = nullptr; a.list_in = sorted; a.list_out = list0;
       const int gridB = (int)std::min<uint64_t>((n + T0_WARPS - 1) / T0_WARPS, (uint64_t)v->sm_count * (T0_CTAS_PER_SM - 2));
-      if (!single_grid) {
+      static const bool no_grid_b = getenv("XS3D_NO_GRIDB") != nullptr;
+      if (!single_grid && !no_grid_b) {
         T0_KERNEL<<<gridB, T0_WARPS * 32, T0_SMEM_BYTES, v->stream3>>>(a);
         CK(cudaGetLastError());
       }
@@ -2515,24 +2518,18 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, -1);
       CK(cudaGetLastError());
       CK(rec_t(v->evs[2], s2));
-      // what leaves the mid tier's window: wide tier (same walk, 416-cell window), then the big tier's bitmap walk
-      a.list_in = list1; a.list_out = listw;
-      area_wide_kernel<<<v->wide_ctas, WideTier::THREADS, WIDE_SMEM_BYTES, s2>>>(a, v->cfg_wide, CNT_NEXTW, CNT_OVERW, d_cnt + CNT_OVER1, 10);
-      CK(cudaGetLastError());
-      a.list_in = listw; a.list_out = list2;
-      area_block_kernel<BigTier><<<v->sm_count, BigTier::THREADS, block_smem_bytes(v), s2>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVERW, 10);
-      CK(cudaGetLastError());
-      launches++;
-      CK(rec_t(v->evs[3], s2));
+      // the second half of every section the mid tier parked (sections that leave its window are rare: they get a
+      // second round after the host has seen the counters, see below)
       a.out = out2; a.done_list = done2;
-      RET(launch_p2(s2));        // what the late hand-overs, the wide and the big tier parked
+      RET(launch_p2(s2));
+      CK(rec_t(v->evs[3], s2));
       poly_eval_kernel<<<v->sm_count * 4, 256, 0, s2>>>(out2.polys, out2.geom, vals2, d_emit2, 0u, out2.poly_cap);
       CK(cudaGetLastError());
       combine_kernel<<<(unsigned)std::min<uint64_t>(n, 1024), 128, 0, s2>>>(out2.items, vals2, out2.qinfo, done2, d_cnt + CNT_DONE2, (uint32_t)n, d_area, d_contact, QS_READY2);
       CK(cudaGetLastError());
       CK(rec_t(v->evs[4], s2));
       CK(cudaEventRecord(v->evf[2], s2));
-      launches += 4;
+      launches += 3;
     } else {
       CK(rec_t(v->evb[1], s1));
       // tiny batches (single calls): mid tier first — a section of a few thousand cells takes a fraction of the big
@@ -2540,16 +2537,10 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       a.out = out1; a.done_list = nullptr; a.list_in = nullptr; a.list_out = list1;
       area_mid_kernel<<<(int)n, MidTier::THREADS, MID_SMEM_BYTES, s1>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, (int)n);
       CK(cudaGetLastError());
-      a.list_in = list1; a.list_out = listw;
-      area_wide_kernel<<<(int)n, WideTier::THREADS, WIDE_SMEM_BYTES, s1>>>(a, v->cfg_wide, CNT_NEXTW, CNT_OVERW, d_cnt + CNT_OVER1, 10);
-      CK(cudaGetLastError());
-      a.list_in = listw; a.list_out = list2;
-      area_block_kernel<BigTier><<<(int)n, BigTier::THREADS, block_smem_bytes(v), s1>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVERW, 10);
-      CK(cudaGetLastError());
       a.out = out1; a.done_list = nullptr;
       RET(launch_p2(s1));
       CK(rec_t(v->evb[2], s1));
-      launches += 3;
+      launches += 1;
     }
     poly_eval_kernel<<<v->sm_count * 8, 256, 0, s1>>>(out1.polys, out1.geom, vals1, d_emit1, 0u, out1.poly_cap);
     CK(cudaGetLastError());
@@ -2630,20 +2621,53 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     v->timing_pending = single ? 2 : 1;   // event durations are read on demand (xs3d_volume_timing): ten driver calls off the hot path
     v->timing[3] = 0.0f;
     if (v->h_counters[CNT_BADN]) return fail(XS3D_ERR_ARG, "normal vector must not be a null vector (all zeros).");
-    const uint32_t over0 = v->h_counters[CNT_OVER0], over1 = v->h_counters[CNT_OVER1], over2 = v->h_counters[CNT_OVER2];
-    v->wide_over = v->h_counters[CNT_OVERW];
+    const uint32_t over0 = v->h_counters[CNT_OVER0], over1 = v->h_counters[CNT_OVER1];
     const uint32_t* he1 = v->h_counters + 64;
     const uint32_t* he2 = v->h_counters + 68;
     uint32_t over3 = 0;
     const uint32_t* hp2 = v->h_counters + 72;
     bool p2_full = hp2[P2C_FULL] != 0, p2_hashfull = hp2[P2C_HASHFULL] != 0;
     bool capacity = he1[2] != 0 || he2[2] != 0 || p2_full || p2_hashfull;
+    const EmitOut& ob = single ? out1 : out2;            // where the CTA tiers' records go
+    float* valsb = single ? vals1 : vals2;
+    uint32_t* d_emitb = single ? d_emit1 : d_emit2;
+    v->timing[2] = 0.0f;
+    if (!capacity && over1 > 0) {
+      // SECOND ROUND: sections that left the mid tier's 256-cell window (or exceeded its 16 Ki samples) — the wide tier
+      // (same walk, 416-cell window), the big tier's whole-plane bitmap walk for what leaves that too, their second half,
+      // polygons and sums.  Rare in sweeps of thin objects (none in the 512^3 bench, four in the 1024^3 one), so the common
+      // path does not pay for five launches that find nothing; a large single section pays one extra host round trip.
+      const uint32_t used = single ? he1[0] : he2[0];
+      a.out = ob; a.done_list = nullptr;
+      const int wg = single ? (int)std::min<uint64_t>(over1, (uint64_t)v->wide_ctas) : v->wide_ctas;
+      CK(cudaEventRecord(v->ev[2], s1));
+      a.list_in = list1; a.list_out = listw;
+      area_wide_kernel<<<wg, WideTier::THREADS, WIDE_SMEM_BYTES, s1>>>(a, v->cfg_wide, CNT_NEXTW, CNT_OVERW, d_cnt + CNT_OVER1, 10);
+      CK(cudaGetLastError());
+      a.list_in = listw; a.list_out = list2;
+      area_block_kernel<BigTier><<<(int)std::min<uint64_t>(over1, (uint64_t)v->sm_count), BigTier::THREADS, block_smem_bytes(v), s1>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVERW, 10);
+      CK(cudaGetLastError());
+      RET(launch_p2(s1));
+      poly_eval_kernel<<<v->sm_count * 8, 256, 0, s1>>>(ob.polys, ob.geom, valsb, d_emitb, used, ob.poly_cap);
+      combine_kernel<<<(unsigned)std::min<uint64_t>(over1, 1024), 128, 0, s1>>>(ob.items, valsb, ob.qinfo, list1, d_cnt + CNT_OVER1, (uint32_t)n, d_area, d_contact, ob.ready);
+      CK(cudaGetLastError());
+      CK(cudaEventRecord(v->ev[3], s1));
+      launches += 4;
+      CK(cudaMemcpyAsync(v->h_counters, d_cnt, 512, cudaMemcpyDeviceToHost, s1));
+      if (h_area) {
+        CK(cudaMemcpyAsync(h_area, d_area, n * 4, cudaMemcpyDeviceToHost, s1));
+        CK(cudaMemcpyAsync(h_contact, d_contact, n, cudaMemcpyDeviceToHost, s1));
+      }
+      CK(host_wait(v, s1));
+      CK(cudaEventElapsedTime(&v->timing[2], v->ev[2], v->ev[3]));
+      p2_full = hp2[P2C_FULL] != 0; p2_hashfull = hp2[P2C_HASHFULL] != 0;
+      capacity = he1[2] != 0 || he2[2] != 0 || p2_full || p2_hashfull;
+    }
+    const uint32_t over2 = v->h_counters[CNT_OVER2];
+    v->wide_over = v->h_counters[CNT_OVERW];
     if (!capacity && over2 > 0) {
       // worst-case slab, one CTA, only for the queries the big tier could not fit (records go where the big tier's went)
       RET(ensure_worst_case_slab(v));
-      const EmitOut& ob = single ? out1 : out2;
-      float* valsb = single ? vals1 : vals2;
-      uint32_t* d_emitb = single ? d_emit1 : d_emit2;
       const uint32_t used = single ? he1[0] : he2[0];
       a.out = ob; a.done_list = nullptr; a.list_in = list2; a.list_out = list3;
       CK(cudaEventRecord(v->ev[0], s1));
@@ -2788,20 +2812,19 @@ extern "C" int xs3d_volume_timing(xs3d_volume* v, float ms[12]) {
     const bool single = v->timing_pending == 2;
     v->timing_pending = 0;
     CK(cudaSetDevice(v->device));
-    const float ingest = v->timing[4], worst = v->timing[3];
+    const float ingest = v->timing[4], worst = v->timing[3], second = v->timing[2];
     for (int i = 0; i < 12; i++) v->timing[i] = 0.0f;
-    v->timing[4] = ingest; v->timing[3] = worst;
+    v->timing[4] = ingest; v->timing[3] = worst; v->timing[2] = second;
     CK(cudaEventElapsedTime(&v->timing[9], v->evb[0], v->evb[1]));                 // pre-pass
-    CK(cudaEventElapsedTime(&v->timing[single ? 2 : 0], v->evb[1], v->evb[2]));   // warp tier (tiny batches: big tier)
+    CK(cudaEventElapsedTime(&v->timing[single ? 1 : 0], v->evb[1], v->evb[2]));   // warp tier (tiny batches: mid tier + its second half)
     CK(cudaEventElapsedTime(&v->timing[5], v->evb[2], v->evb[3]));                 // polygon kernel
     CK(cudaEventElapsedTime(&v->timing[6], v->evb[3], v->evb[4]));                 // combine kernel
     CK(cudaEventElapsedTime(&v->timing[8], v->evb[4], v->evb[5]));                 // waiting for the second stream
     if (!single) {
       CK(cudaEventElapsedTime(&v->timing[1], v->evs[0], v->evs[1]));               // mid tier beside the warp tier
-      CK(cudaEventElapsedTime(&v->timing[10], v->evs[5], v->evs[2]));              // ... its second launch (incl. waiting for the warp tier)
-      CK(cudaEventElapsedTime(&v->timing[2], v->evs[2], v->evs[3]));               // big tier
-      CK(cudaEventElapsedTime(&v->timing[7], v->evs[1], v->evs[5]));               // second half of the CTA tiers (P2 kernels), first chain
-      CK(cudaEventElapsedTime(&v->timing[11], v->evs[3], v->evs[4]));              // second chain of P2 kernels + second stream's polygon + combine kernels
+      CK(cudaEventElapsedTime(&v->timing[10], v->evs[1], v->evs[2]));              // ... its second launch (incl. waiting for the warp tier)
+      CK(cudaEventElapsedTime(&v->timing[7], v->evs[2], v->evs[3]));               // second half of the CTA tiers (P2 kernels)
+      CK(cudaEventElapsedTime(&v->timing[11], v->evs[3], v->evs[4]));              // second stream's polygon + combine kernels
     }
   }
   for (int i = 0; i < 12; i++) ms[i] = v->timing[i];

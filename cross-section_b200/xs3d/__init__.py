@@ -326,7 +326,7 @@ class Volume:
     run on a second stream beside the warp tier; mid_exposed_ms is what they add to the launching stream."""
     t = (C.c_float * 12)()
     _abi.check(self._lib.xs3d_volume_timing(self._h, t))
-    return {"warp_tier_ms": t[0], "mid_tier_ms": t[1], "big_tier_ms": t[2], "worst_case_ms": t[3], "ingest_ms": t[4],
+    return {"warp_tier_ms": t[0], "mid_tier_ms": t[1], "second_round_ms": t[2], "big_tier_ms": t[2], "worst_case_ms": t[3], "ingest_ms": t[4],
             "polygon_ms": t[5], "combine_ms": t[6], "p2_ms": t[7], "mid_exposed_ms": t[8], "prepass_ms": t[9],
             "mid_second_launch_ms": t[10], "second_stream_poly_combine_ms": t[11]}
 

@@ -115,8 +115,9 @@ int xs3d_volume_stats(xs3d_volume* vol, uint64_t stats[10]);
  * [2] ownership + record emission, [3] [4] unused, [5] walk only. */
 int xs3d_volume_profile(xs3d_volume* vol, uint64_t prof[12]);
 /* CUDA-event durations (ms) of the kernels of the last call on this volume:
- * ms[0] warp-tier, ms[1] mid-tier (on its own stream, concurrent with the warp tier), ms[2] big-tier, ms[3] worst-case
- * query kernels, ms[4] ingest kernel (last xs3d_volume_load), ms[5] polygon kernel, ms[6] combine kernel, ms[7] the CTA
+ * ms[0] warp-tier, ms[1] mid-tier (on its own stream, concurrent with the warp tier; tiny batches: mid tier + its second
+ * half), ms[2] second round (wide + big tiers and everything behind them, only when a section left the mid tier's window),
+ * ms[3] worst-case query kernels, ms[4] ingest kernel (last xs3d_volume_load), ms[5] polygon kernel, ms[6] combine kernel, ms[7] the CTA
  * tiers' second half (claims / ownership / record kernels over the parked sections, second stream),
  * ms[8] time the launching stream waits for the second stream (mid / big tiers + their polygon and combine kernels)
  * after its own combine kernel, ms[9] pre-pass (size estimate + ordering), ms[10] second launch of the mid tier
