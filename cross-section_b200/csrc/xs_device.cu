@@ -948,11 +948,11 @@ __global__ void __launch_bounds__(T::THREADS, T::MIN_BLOCKS) area_block_kernel(B
 // warp in lock step (xs_query.cuh, flood_component_nbr).  Takes the few per cent of sweep queries that do not
 // fit a warp.
 // ------------------------------------------------------------------------------------------------
-struct MidTier {
-  static constexpr int THREADS = 256;
-  static constexpr int WSIDE = 256;                // 256 x 256 cells; uint16 cell index u | v<<8
-  static constexpr int RING = 1024;                // DFS stack ring entries (uint16) in shared memory (77.5 KB in all: one
-                                                   //   mid-tier CTA fits beside two warp-tier CTAs on an SM)
+template <int THREADS_, int WSIDE_>
+struct MidTierT {
+  static constexpr int THREADS = THREADS_;
+  static constexpr int WSIDE = WSIDE_;             // WSIDE x WSIDE cells; uint16 cell index u | v<<8
+  static constexpr int RING = 1024;                // DFS stack ring entries (uint16) in shared memory
   static constexpr int O_CTL = 64;
   static constexpr int O_RING = O_CTL + 56;
   static constexpr int O_LUT = O_RING + RING / 2;  // 256 x int16
@@ -960,13 +960,20 @@ struct MidTier {
   static constexpr int O_FBITS = O_LUT + 128;
   static constexpr int O_CELLS = O_FBITS + (WSIDE + 2) * FSTRIDE;
   static constexpr int WORDS = O_CELLS + WSIDE * WSIDE / 4 + 128;   // the walk may touch up to a row past either end
+  static constexpr int SMEM_BYTES = WORDS * 4;
+  static_assert(WSIDE % 32 == 0 && WSIDE <= 256, "uint16 cell packing");
 };
+// 256 x 256-cell window, 256 threads, 77.5 KB: one such CTA fits beside two warp-tier CTAs on an SM.  (Tried in round 2:
+// a 160-cell window with 128 threads and TWO CTAs per SM, so that two walks hide each other's latency — the mid tier got
+// slower, 0.39 -> 0.50 ms, its parallel phases having half the threads, and the warp tier beside it 0.42 -> 0.55 ms.)
+using MidTier = MidTierT<256, 256>;
 
 __host__ __device__ inline size_t mid_slab_bytes(const SlabCfg& s) {
   size_t bytes = (size_t)s.max_n * (2 + 4 + 2) + (size_t)s.hcap_max * 8;
   return ((bytes + 255) / 256) * 256;
 }
 
+template <class MidTier>
 __global__ void __maxnreg__(96) area_mid_kernel(BatchArgs a, SlabCfg s, int cnt_next, int cnt_over, int stats_base, int n_direct) {
   extern __shared__ __align__(16) uint32_t smem[];
   BlockGroup g(reinterpret_cast<int*>(smem));
@@ -1027,12 +1034,12 @@ __global__ void __maxnreg__(96) area_mid_kernel(BatchArgs a, SlabCfg s, int cnt_
       if (threadIdx.x == 0) zero_query(a, q);
       continue;
     }
-    A.ox = A.oy = c.c - MidTier::WSIDE / 2 - 16;   // the centre cell sits in the middle of tile (4,4)
+    A.ox = A.oy = c.c - (MidTier::WSIDE / 64) * 32 - 16;   // the centre cell sits in the middle of tile (2,2) / (4,4)
     H.htag = g_tag; H.hkey = g_key;
     H.cap = s.hcap_max; H.cap_max = s.hcap_max; H.factor = s.hash_factor; H.max_probe = s.max_probe;
     H.hx = a.vol.hx; H.hy = a.vol.hy;
     // the 64 KB cell window is dead once the walk is done: 8192-entry first-touch table in shared memory
-    H.alt_tag = smem + MidTier::O_CELLS; H.alt_key = H.alt_tag + 8192; H.alt_cap = 8192;
+    H.alt_tag = nullptr; H.alt_key = nullptr; H.alt_cap = 0;
     int lg = 0;
     while ((1u << lg) < s.hcap_max) lg++;
     H.shift = 32 - lg;
@@ -1517,6 +1524,9 @@ __global__ void __launch_bounds__(POLY_THREADS) poly_eval_kernel(const PolyRec* 
 // ------------------------------------------------------------------------------------------------
 // combine kernel: one CTA per query; item values in parallel, then the reference's ordered sums
 // ------------------------------------------------------------------------------------------------
+#ifndef XS_COMBINE_TILED_FROM
+#define XS_COMBINE_TILED_FROM 256u
+#endif
 __global__ void __launch_bounds__(128) combine_kernel(const ItemRec* __restrict__ items, float* __restrict__ vals, const QInfo* __restrict__ qinfo,
                                                       const uint32_t* __restrict__ list, const uint32_t* __restrict__ list_count, uint32_t nq,
                                                       float* __restrict__ area, uint8_t* __restrict__ contact, uint32_t want_status) {
@@ -1532,7 +1542,7 @@ __global__ void __launch_bounds__(128) combine_kernel(const ItemRec* __restrict_
       vals[e.poly] = item_value(e, vals);       // an item's polygons are its own: safe to overwrite its first slot
     }
     __syncthreads();
-    if (n > 256u) {
+    if (n > XS_COMBINE_TILED_FROM) {
       // a large section (up to ~1e5 items): the ordered sum is one dependent chain of float additions whatever we do, so
       // make each link as short as possible — all threads stage 1024 (value, first) pairs in shared memory, thread 0
       // adds them up from there (a handful of cycles per item instead of two shuffles and a select)
@@ -1753,7 +1763,6 @@ static VolView view_of(const xs3d_volume* v) {
 
 static int block_smem_bytes(const xs3d_volume* v) { return v->smem_optin; }
 static int block_smem_bits_words(const xs3d_volume* v) { return v->smem_optin / 4 - BigTier::FIXED_WORDS; }
-constexpr int MID_SMEM_BYTES = MidTier::WORDS * 4;
 
 static int configure_kernels(xs3d_volume* v) {
   if (v->kernels_configured) return XS3D_OK;
@@ -1761,7 +1770,7 @@ static int configure_kernels(xs3d_volume* v) {
   if (t0_bytes > v->smem_optin) return fail(XS3D_ERR_UNSUPPORTED, "device shared memory too small for the warp tier");
   CK(cudaFuncSetAttribute(T0_KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, t0_bytes));
   CK(cudaFuncSetAttribute(area_block_kernel<BigTier>, cudaFuncAttributeMaxDynamicSharedMemorySize, block_smem_bytes(v)));
-  CK(cudaFuncSetAttribute(area_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MID_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(area_mid_kernel<MidTier>, cudaFuncAttributeMaxDynamicSharedMemorySize, MidTier::SMEM_BYTES));
   if (WIDE_SMEM_BYTES > v->smem_optin) return fail(XS3D_ERR_UNSUPPORTED, "device shared memory too small for the wide tier");
   CK(cudaFuncSetAttribute(area_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM_BYTES));
   v->kernels_configured = true;
@@ -2312,7 +2321,7 @@ static int ensure_batch_workspace(xs3d_volume* v, uint64_t n) {
   RET(v->counters.ensure(CNT_TOTAL_WORDS * 4));
   if (!v->slab_mid.p) {
     SlabCfg m{};
-    m.max_n = 1 << 14; m.hcap_max = 1u << 17; m.bits_words = 0; m.tested_words = 0; m.hash_factor = 8; m.max_probe = 256;
+    m.max_n = 1 << 14; m.hcap_max = 0; m.bits_words = 0; m.tested_words = 0; m.hash_factor = 8; m.max_probe = 256;   // (no per-CTA table: P2 has the sections' tables)
     m.stride = mid_slab_bytes(m);
     v->mid_ctas = v->sm_count;
     if (const char* e = getenv("XS3D_MID_CTAS")) v->mid_ctas = std::max(1, atoi(e));          // tuning knobs (dev)
@@ -2483,10 +2492,11 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(cudaStreamWaitEvent(s2, v->evf[0], 0));
       a.out = out2; a.done_list = done2; a.list_in = sorted; a.list_out = list1;
       CK(rec_t(v->evs[0], s2));
-      area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, -1);
+      area_mid_kernel<MidTier><<<v->mid_ctas, MidTier::THREADS, MidTier::SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, -1);
       CK(cudaGetLastError());
       CK(rec_t(v->evs[1], s2));
       CK(cudaEventRecord(v->evf[4], s2));
+      CK(rec_t(v->evs[5], s2));
       // profiling aid: under ncu every kernel runs alone, so the split of the warp tier into grids A and B would show
       // grid B (10 warps per SM) doing all the work; XS3D_SINGLE_GRID=1 launches the warp tier as one grid of 3 CTAs per SM
       const bool single_grid = getenv("XS3D_SINGLE_GRID") != nullptr;
@@ -2515,7 +2525,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(cudaStreamWaitEvent(s2, v->evf[1], 0));
       CK(cudaStreamWaitEvent(s2, v->evf[3], 0));
       a.out = out2; a.done_list = done2; a.list_in = sorted; a.list_out = list1;
-      area_mid_kernel<<<v->mid_ctas, MidTier::THREADS, MID_SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, -1);
+      area_mid_kernel<MidTier><<<v->mid_ctas, MidTier::THREADS, MidTier::SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, -1);
       CK(cudaGetLastError());
       CK(rec_t(v->evs[2], s2));
       // the second half of every section the mid tier parked (sections that leave its window are rare: they get a
@@ -2535,7 +2545,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       // tiny batches (single calls): mid tier first — a section of a few thousand cells takes a fraction of the big
       // tier's time there — then the big tier for what does not fit its window
       a.out = out1; a.done_list = nullptr; a.list_in = nullptr; a.list_out = list1;
-      area_mid_kernel<<<(int)n, MidTier::THREADS, MID_SMEM_BYTES, s1>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, (int)n);
+      area_mid_kernel<MidTier><<<(int)n, MidTier::THREADS, MidTier::SMEM_BYTES, s1>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, (int)n);
       CK(cudaGetLastError());
       a.out = out1; a.done_list = nullptr;
       RET(launch_p2(s1));
@@ -2822,8 +2832,13 @@ extern "C" int xs3d_volume_timing(xs3d_volume* v, float ms[12]) {
     CK(cudaEventElapsedTime(&v->timing[8], v->evb[4], v->evb[5]));                 // waiting for the second stream
     if (!single) {
       CK(cudaEventElapsedTime(&v->timing[1], v->evs[0], v->evs[1]));               // mid tier beside the warp tier
-      CK(cudaEventElapsedTime(&v->timing[10], v->evs[1], v->evs[2]));              // ... its second launch (incl. waiting for the warp tier)
-      CK(cudaEventElapsedTime(&v->timing[7], v->evs[2], v->evs[3]));               // second half of the CTA tiers (P2 kernels)
+      CK(cudaEventElapsedTime(&v->timing[10], v->evs[5], v->evs[2]));              // ... its second launch (incl. waiting for the warp tier)
+      CK(cudaEventElapsedTime(&v->timing[7], v->evs[1], v->evs[5]));               // second half of the CTA tiers (P2 kernels), first chain
+      {
+        float t2 = 0.0f;
+        CK(cudaEventElapsedTime(&t2, v->evs[2], v->evs[3]));                       // ... second chain (late hand-overs)
+        v->timing[7] += t2;
+      }
       CK(cudaEventElapsedTime(&v->timing[11], v->evs[3], v->evs[4]));              // second stream's polygon + combine kernels
     }
   }

@@ -1070,8 +1070,8 @@ XS_D void nbr_masks_tile(const G& g, const Arena<CellT>& A, int tx, int ty) {
 // (u | v << 16) for 32-bit cells — what CellPack / sample_at decode
 template <class CellT>
 XS_HD CellT nbr_order_entry(int ci, int MS, int MO) {
-  if (sizeof(CellT) == 2 && MS == 256) return (CellT)ci;      // (mid tier: the byte index is the packed cell already)
-  const int v = MS == 64 ? (ci >> 6) : ci / MS, u = ci - v * MS;   // (64: the warp tier's row; spares it an integer division)
+  if (sizeof(CellT) == 2 && MS == 256) return (CellT)ci;      // (256-cell mid tier: the byte index is the packed cell already)
+  const int v = MS == 64 ? (ci >> 6) : (MS == 160 ? ci / 160 : ci / MS), u = ci - v * MS;   // (constant divisors spare an integer division)
   return CellPack<CellT>::pack(u + MO, v + MO);
 }
 
