@@ -256,7 +256,7 @@ def run_own_arm(args):
     # spins on its GPU); the packing thread itself is one of the pool's workers
     # (measured: 16-core box, N = 1: 14-15 threads best; 32-core box, N = 8: 16 threads 1.15-1.22 ms per step, 24 threads 1.37 ms —
     # the other ranks' main threads and the broadcasters need cores too)
-    os.environ.setdefault("XS3D_HOST_THREADS", str(max(4, min(16, (os.cpu_count() or 8) - world))))
+    os.environ.setdefault("XS3D_HOST_THREADS", str(max(4, min(16, (os.cpu_count() or 8) - world - 1))))
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
   if world > 1:

@@ -22,6 +22,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <string>
 #include <vector>
 #include <mutex>
@@ -1744,6 +1745,16 @@ struct xs3d_volume {
 // processes that share their cores with others (several ranks on one host while rank 0's pool packs the next image).
 static cudaError_t host_wait(xs3d_volume* v, cudaStream_t st) {
   static const bool blocking = getenv("XS3D_BLOCKING_SYNC") != nullptr;
+  static const int poll_us = getenv("XS3D_POLL_SLEEP_US") ? atoi(getenv("XS3D_POLL_SLEEP_US")) : 0;
+  if (poll_us > 0) {
+    // dev knob: poll with short sleeps instead of spinning (frees the hyperthread sibling for the packing pool)
+    for (;;) {
+      const cudaError_t q = cudaStreamQuery(st);
+      if (q != cudaErrorNotReady) return q;
+      timespec ts{0, poll_us * 1000L};
+      nanosleep(&ts, nullptr);
+    }
+  }
   if (!blocking) return cudaStreamSynchronize(st);
   if (!v->ev_block) {
     cudaError_t e = cudaEventCreateWithFlags(&v->ev_block, cudaEventBlockingSync | cudaEventDisableTiming);

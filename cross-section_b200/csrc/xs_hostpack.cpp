@@ -21,6 +21,7 @@
 #endif
 #if defined(__linux__)
 #include <sched.h>
+#include <pthread.h>
 #endif
 
 namespace {
@@ -89,6 +90,18 @@ class Pool {
   static constexpr int MAX_PARTS = 16;
   explicit Pool(int n) : n_(n) {
     for (int i = 0; i < n_ - 1; i++) threads_.emplace_back([this] { loop(); });
+#if defined(__linux__)
+    // dev knob XS3D_PIN_POOL=first_cpu: worker i runs on cpu first_cpu + i only (keeps the pool off the caller's cores)
+    if (const char* e = getenv("XS3D_PIN_POOL")) {
+      const int first = atoi(e);
+      for (int i = 0; i < (int)threads_.size(); i++) {
+        cpu_set_t set;
+        CPU_ZERO(&set);
+        CPU_SET(first + i, &set);
+        pthread_setaffinity_np(threads_[i].native_handle(), sizeof(set), &set);
+      }
+    }
+#endif
   }
   ~Pool() {
     { std::lock_guard<std::mutex> lk(mu_); stop_ = true; gen_++; }

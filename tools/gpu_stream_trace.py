@@ -30,11 +30,15 @@ def before(k):
   t0 = T(); 
   if not os.environ.get("NO_FLUSH"): flush.fill_(k & 255)
   log.append(("flush-launch", k, t0, T()))
-n = 12
+n = int(os.environ.get('XS_TRACE_STEPS', '12'))
 xdist.stream_volumes(V, [vol] * 4, 4, sweep, before_step=before, feed=TracedFeed()); log.clear()
 torch.cuda.synchronize(); t0 = T()
 xdist.stream_volumes(V, [vol] * n, n, sweep, before_step=before, feed=TracedFeed())
 torch.cuda.synchronize(); t1 = T()
 print("total %.3f ms/step" % ((t1 - t0) * 1e3 / n))
+if os.environ.get('XS_TRACE_QUIET'):
+  pk = [b - a for name, k, a, b in log if name == 'pack+stage']; sw = [b - a for name, k, a, b in log if name == 'sweep']
+  print("   pack+stage median %.3f ms, sweep median %.3f ms" % (np.median(pk) * 1e3, np.median(sw) * 1e3))
+  sys.exit(0)
 for name, k, a, b in sorted(log, key=lambda r: r[2]):
   print("%-12s %2d  %8.3f -> %8.3f  (%.3f)" % (name, k, (a - t0) * 1e3, (b - t0) * 1e3, (b - a) * 1e3))
