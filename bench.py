@@ -257,6 +257,9 @@ def run_own_arm(args):
     # (measured: 16-core box, N = 1: 14-15 threads best; 32-core box, N = 8: 16 threads 1.15-1.22 ms per step, 24 threads 1.37 ms —
     # the other ranks' main threads and the broadcasters need cores too)
     os.environ.setdefault("XS3D_HOST_THREADS", str(max(4, min(16, (os.cpu_count() or 8) - world - 1))))
+  if world > 1 and rank != 0 and os.environ.get("XS_BENCH_POLL_RANKS"):
+    # dev knob: the ranks that do not pack poll their GPU with short sleeps instead of spinning (their cores go to rank 0's pool)
+    os.environ.setdefault("XS3D_POLL_SLEEP_US", os.environ["XS_BENCH_POLL_RANKS"])
   torch.cuda.set_device(local)
   dev = torch.device("cuda", local)
   if world > 1:

@@ -13,13 +13,15 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "lib", "libxs3d_b200.so")
-OBJ = os.path.join(HERE, "lib", "obj")
+# dev aid for A/B runs: XS3D_BUILD_TAG=x XS3D_EXTRA_FLAGS="-DFOO=1" builds lib/libxs3d_b200_x.so beside the product library
+TAG = os.environ.get("XS3D_BUILD_TAG", "")
+OUT = os.path.join(HERE, "lib", "libxs3d_b200%s.so" % ("_" + TAG if TAG else ""))
+OBJ = os.path.join(HERE, "lib", "obj" + ("_" + TAG if TAG else ""))
 UNITS = ["xs_device.cu", "xs_slow.cu", "xs_slice.cu", "xs_section.cu", "xs_skeleton.cu", "xs_hostpack.cpp"]   # .cpp: host-only code, compiled by g++
 CXX = os.environ.get("CXX", "g++")
 NVCC = os.environ.get("NVCC", "nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"] + os.environ.get("XS3D_EXTRA_FLAGS", "").split()
 
 
 def _deps():
@@ -53,7 +55,7 @@ def build(force=False, verbose=False):
   objs = [o for o, _ in results]
   log = "\n".join(l for _, l in results if l)
   if log:
-    with open(os.path.join(HERE, "lib", "ptxas.log"), "w") as f:
+    with open(os.path.join(HERE, "lib", "ptxas%s.log" % ("_" + TAG if TAG else "")), "w") as f:
       f.write(log)
     if verbose:
       print(log)

@@ -1472,13 +1472,15 @@ __global__ void __launch_bounds__(P2_CHUNK) p2_emit2_kernel(BatchArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// polygon kernel.  About half of the records are cubes the plane misses (value exactly 0) and the rest differ in
+// polygon kernel.  Two thirds of the records are cubes the plane does not cut (value exactly 0) and the rest differ in
 // vertex count, so one-thread-per-record leaves most lanes idle.  Each warp therefore FILTERS 32 records at a time
-// (one dot product each), writes the zeros, queues the survivors in shared memory and evaluates them 32 at a time,
-// all lanes busy; unit voxels and 2x2x2 blocks run through the same instruction stream (run-time cube side).
+// (plane_cube_miss: the reach of the cube along the normal, one dot product), writes the zeros, queues the survivors in
+// shared memory and evaluates them 32 at a time, all lanes busy; unit voxels and 2x2x2 blocks run through the same
+// instruction stream (run-time cube side).  The evaluation is ~3000 instructions long: it exists ONCE in the kernel (the
+// loop drains the queue through the same call site), a second inlined copy thrashed the instruction cache.
 // ------------------------------------------------------------------------------------------------
 constexpr int POLY_THREADS = 256;
-__global__ void __launch_bounds__(POLY_THREADS) poly_eval_kernel(const PolyRec* __restrict__ polys, const PlaneGeom* __restrict__ geom,
+__global__ void __launch_bounds__(POLY_THREADS, 4) poly_eval_kernel(const PolyRec* __restrict__ polys, const PlaneGeom* __restrict__ geom,
                                                                  float* __restrict__ vals, const uint32_t* __restrict__ count_ptr,
                                                                  uint32_t start, uint32_t cap) {
   __shared__ uint32_t queue_all[POLY_THREADS / 32][64];
@@ -1489,36 +1491,40 @@ __global__ void __launch_bounds__(POLY_THREADS) poly_eval_kernel(const PolyRec* 
   const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int qn = 0;
-  for (uint32_t base = start + wid * 32u; base < n; base += nwarps * 32u) {
-    const uint32_t i = base + (uint32_t)lane;
-    bool near = false;
-    if (i < n) {
-      const PolyRec r = polys[i];
-      const PlaneGeom* gp = geom + r.q;
-      const V3 pos = mk(__ldg(&gp->pos.x), __ldg(&gp->pos.y), __ldg(&gp->pos.z));
-      const V3 nn = mk(__ldg(&gp->n.x), __ldg(&gp->n.y), __ldg(&gp->n.z));
-      near = !plane_cube_far((int)r.kind, (float)r.x, (float)r.y, (float)r.z, pos, nn);
-      if (!near) vals[i] = 0.0f;
+  uint32_t base = start + wid * 32u;
+#pragma unroll 1
+  for (;;) {
+    const bool more = base < n;                 // warp-uniform
+    if (more) {
+      const uint32_t i = base + (uint32_t)lane;
+      bool near = false;
+      if (i < n) {
+        const PolyRec r = polys[i];
+        const PlaneGeom* gp = geom + r.q;
+        const V3 pos = mk(__ldg(&gp->pos.x), __ldg(&gp->pos.y), __ldg(&gp->pos.z));
+        const V3 nn = mk(__ldg(&gp->n.x), __ldg(&gp->n.y), __ldg(&gp->n.z));
+        near = !plane_cube_miss((int)r.kind, (float)r.x, (float)r.y, (float)r.z, pos, nn);
+        if (!near) vals[i] = 0.0f;
+      }
+      const uint32_t ball = __ballot_sync(0xffffffffu, near);
+      if (near) queue[qn + __popc(ball & ((1u << lane) - 1u))] = i;
+      qn += __popc(ball);
+      base += nwarps * 32u;
+      __syncwarp();
+      if (qn < 32) continue;
+    } else if (qn == 0) {
+      break;
     }
-    const uint32_t ball = __ballot_sync(0xffffffffu, near);
-    if (near) queue[qn + __popc(ball & ((1u << lane) - 1u))] = i;
-    qn += __popc(ball);
-    __syncwarp();
-    if (qn >= 32) {
+    if (lane < qn) {
       const uint32_t j = queue[lane];
       const PolyRec r = polys[j];
       vals[j] = poly_eval(r, geom[r.q]);
-      const uint32_t rest = (lane + 32 < qn) ? queue[lane + 32] : 0u;
-      __syncwarp();
-      queue[lane] = rest;
-      qn -= 32;
-      __syncwarp();
     }
-  }
-  if (lane < qn) {
-    const uint32_t j = queue[lane];
-    const PolyRec r = polys[j];
-    vals[j] = poly_eval(r, geom[r.q]);
+    const uint32_t rest = (lane + 32 < qn) ? queue[lane + 32] : 0u;
+    __syncwarp();
+    queue[lane] = rest;
+    qn = qn > 32 ? qn - 32 : 0;
+    __syncwarp();
   }
 }
 

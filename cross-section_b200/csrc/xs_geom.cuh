@@ -66,6 +66,26 @@ XS_HD bool plane_cube_far(int S, float x, float y, float z, V3 pos, V3 n) {
   return dist > (S == 1 ? XS_FAR1 : XS_FAR2);
 }
 
+// Conservative pre-filter for the polygon kernel: true only when the plane cannot reach the cube, so that
+// plane_cube_points() is certain to find no point (polygon area exactly 0).  A point of the cube is at most
+// (S/2)(|nx|+|ny|+|nz|) from the plane through the centre.  The reference accepts hits up to eps = 2e-5 outside the cube
+// and computes them in float32: the hit point carries <= 6e-8 of its coordinates, the corner projections <= 3e-7 of the
+// distance plane point - cube; the margin below is 0.01 plus 16 and 6 times those bounds (tests/test_hostsim.py probes it
+// with planes through and next to corners, edges and faces up to coordinates of 60 000).
+// (plane_cube_far — the reference's own test against the circumscribed sphere — lets about 40 % more cubes through.)
+#ifndef XS_MISS_MARGIN
+#define XS_MISS_MARGIN 0.01f
+#endif
+XS_HD bool plane_cube_miss(int S, float x, float y, float z, V3 pos, V3 n) {
+  const V3 low = mk(x, y, z);
+  const V3 centre = (S == 1) ? low : vadd(low, mk(0.5f, 0.5f, 0.5f));
+  const V3 rel = vsub(centre, pos);
+  const float dist = fabsf(vdot(rel, n));
+  const float mag = fadd(fmul(fadd(fadd(x, y), z), 1e-6f), fmul(fadd(fadd(fabsf(rel.x), fabsf(rel.y)), fabsf(rel.z)), 2e-6f));
+  const float reach = fadd(fadd(fmul(fadd(fadd(fabsf(n.x), fabsf(n.y)), fabsf(n.z)), S == 1 ? 0.5f : 1.0f), XS_MISS_MARGIN), mag);
+  return dist > reach;
+}
+
 // Intersect the plane with the 12 edges of the cube of side S whose low voxel is (x,y,z)
 // (S=1: the voxel itself, spanning [x-.5,x+.5]; S=2: the block spanning [x-.5,x+1.5]).
 // Edge order, corner de-duplication and the 4/6 vertex cap follow xs3d.hpp:183-233 / 307-358.

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libxs3d_b200.so")
+LIB_PATH = os.environ.get("XS3D_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libxs3d_b200.so")   # XS3D_LIB: dev aid (A/B builds)
 
 HOST, DEVICE = 0, 1
 

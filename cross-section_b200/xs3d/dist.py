@@ -263,7 +263,11 @@ class VolumeFeed:
     if not self._st_issued[slot]:
       return 0
     if wait:
-      ev[slot].synchronize()
+      # wait without burning a core: the packing pool of the source rank needs them (eight broadcaster threads spinning
+      # in a synchronize cost the 8-GPU end-to-end step 0.1 ms); nobody waits for this thread within a step
+      import time
+      while not ev[slot].query():
+        time.sleep(20e-6)
     elif not ev[slot].query():
       return 0
     return int(h[slot][0])
@@ -299,8 +303,22 @@ def broadcast_group(group=None):
   import torch.distributed as dist
   key = id(group) if group is not None else None
   if key not in _bcast_groups:
+    import os
     ranks = dist.get_process_group_ranks(group) if group is not None else list(range(dist.get_world_size()))
-    _bcast_groups[key] = dist.new_group(ranks=ranks, backend=dist.get_backend(group))
+    backend = dist.get_backend(group)
+    opts = None
+    if backend == "nccl" and hasattr(dist, "ProcessGroupNCCL"):
+      # The broadcast of image k+1 is enqueued a step ahead and its kernel WAITS on the GPU for the source rank's data while
+      # the sweep of image k runs: with NCCL's default channel count that is a dozen or more resident CTAs taking shared
+      # memory and registers from the query tiers for most of the sweep.  16 MiB a step ahead needs no bandwidth to speak
+      # of, so this communicator is limited to a few CTAs (ncclConfig max_ctas).
+      try:
+        opts = dist.ProcessGroupNCCL.Options()
+        opts.config.max_ctas = int(os.environ.get("XS3D_BCAST_CTAS", "2"))
+        opts.config.min_ctas = 1
+      except Exception:
+        opts = None
+    _bcast_groups[key] = dist.new_group(ranks=ranks, backend=backend, pg_options=opts) if opts is not None else dist.new_group(ranks=ranks, backend=backend)
   return _bcast_groups[key]
 
 

@@ -257,6 +257,61 @@ float hostsim_block_area(uint8_t cube, const float* cur, const float* p, const f
   return block_value(cube, (float)((uint64_t)cur[0] & ~1ull), (float)((uint64_t)cur[1] & ~1ull), (float)((uint64_t)cur[2] & ~1ull), g);
 }
 
+// plane_cube_miss must never drop a cube for which plane_cube_points finds a point.  Random and adversarial planes
+// (through / next to corners, edges and faces, tiny and zero normal components, coordinates up to `span`).
+// out[0] cases, out[1] violations, out[2] dropped by plane_cube_miss, out[3] dropped by plane_cube_far, out[4] polygons (>= 3 points)
+static uint64_t hs_rng(uint64_t& s) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; }
+static float hs_unit(uint64_t& s) { return (float)((hs_rng(s) >> 11) * (1.0 / 9007199254740992.0)); }
+void hostsim_miss_check(uint64_t n_cases, uint64_t seed, float span, int64_t* out) {
+  uint64_t s = seed * 2654435761ull + 88172645463325252ull;
+  for (int i = 0; i < 5; i++) out[i] = 0;
+  for (uint64_t it = 0; it < n_cases; it++) {
+    const int S = 1 + (int)(hs_rng(s) & 1);
+    V3 n = mk(hs_unit(s) * 2 - 1, hs_unit(s) * 2 - 1, hs_unit(s) * 2 - 1);
+    const int style = (int)(hs_rng(s) % 8);
+    if (style == 1) n.x = 0.0f;
+    if (style == 2) { n.x = 0.0f; n.y = 0.0f; }
+    if (style == 3) n.z *= 1e-6f;
+    if (style == 4) { n.x *= 1e-4f; n.y *= 1e-7f; }
+    if (style == 5) { n.x = n.y; n.z = -n.y; }
+    if (vnull(n)) n.z = 1.0f;
+    n = vdivs(n, vnorm(n));
+    const float x = floorf(hs_unit(s) * span), y = floorf(hs_unit(s) * span), z = floorf(hs_unit(s) * span);
+    // a point of (or right next to) the cube: on a corner, an edge, a face, inside, or up to 2.5 cells away
+    const float fS = (float)S;
+    V3 q = mk(x - 0.5f, y - 0.5f, z - 0.5f);
+    const int where = (int)(hs_rng(s) % 6);
+    float fx = hs_unit(s), fy = hs_unit(s), fz = hs_unit(s);
+    if (where <= 2) fx = (hs_rng(s) & 1) ? 1.0f : 0.0f;
+    if (where <= 1) fy = (hs_rng(s) & 1) ? 1.0f : 0.0f;
+    if (where == 0) fz = (hs_rng(s) & 1) ? 1.0f : 0.0f;
+    q = vadd(q, mk(fx * fS, fy * fS, fz * fS));
+    float push = 0.0f;
+    const int pk = (int)(hs_rng(s) % 6);
+    if (pk == 1) push = (hs_unit(s) * 2 - 1) * 1e-4f;
+    if (pk == 2) push = (hs_unit(s) * 2 - 1) * 3e-2f;
+    if (pk >= 4 || where == 5) push = (hs_unit(s) * 2 - 1) * 2.5f;
+    // the plane point: q moved along the normal by `push` and anywhere within the plane (up to 40 cells, like a query vertex; a quarter of the cases up to 3000)
+    V3 t1 = vcross(n, mk(1.0f, 0.0f, 0.0f));
+    if (vnorm(t1) < 1e-3f) t1 = vcross(n, mk(0.0f, 1.0f, 0.0f));
+    t1 = vdivs(t1, vnorm(t1));
+    const V3 t2 = vcross(n, t1);
+    const float reachab = (hs_rng(s) % 4 == 0) ? 3000.0f : 40.0f;
+    const float a = (hs_unit(s) * 2 - 1) * reachab, b = (hs_unit(s) * 2 - 1) * reachab;
+    const V3 pos = vadd(vadd(vadd(q, vscale(n, push)), vscale(t1, a)), vscale(t2, b));
+    PlaneGeom g;
+    geom_init(g, pos, n, mk(1.0f, 1.0f, 1.0f));
+    Poly poly;
+    plane_cube_points(S, x, y, z, g, poly);
+    const bool miss = plane_cube_miss(S, x, y, z, pos, n);
+    out[0]++;
+    if (miss && poly.n > 0) out[1]++;
+    if (miss) out[2]++;
+    if (plane_cube_far(S, x, y, z, pos, n)) out[3]++;
+    if (poly.n >= 3) out[4]++;
+  }
+}
+
 int hostsim_is_26_connected(uint8_t centre, uint8_t cand, int x, int y, int z) { return blocks_adjacent(centre, cand, x, y, z) ? 1 : 0; }
 
 float hostsim_round(float x) { return fround(x); }

@@ -35,6 +35,13 @@ class HostSim:
     lib.hostsim_voxel_area.restype = C.c_float
     lib.hostsim_block_area.argtypes = [C.c_uint8, fp, fp, fp, fp]
     lib.hostsim_block_area.restype = C.c_float
+    lib.hostsim_miss_check.argtypes = [u64, u64, C.c_float, C.POINTER(C.c_int64)]
+    lib.hostsim_miss_check.restype = None
+
+  def miss_check(self, n_cases, seed, span):
+    out = (C.c_int64 * 5)()
+    self.lib.hostsim_miss_check(n_cases, seed, C.c_float(span), out)
+    return dict(zip(("cases", "violations", "miss", "far", "polygons"), list(out)))
 
   def area_batch(self, vol, pos, nrm, w, mode=0):
     a = np.asfortranarray(vol)

@@ -104,3 +104,12 @@ def test_round_half_away(hostsim):
   for x in xs:
     exp = np.float32(np.sign(x) * np.floor(np.abs(np.float64(x)) + 0.5))
     assert hostsim.lib.hostsim_round(float(x)) == exp, x
+
+
+def test_polygon_prefilter_never_drops_a_cut_cube(hostsim):
+  """plane_cube_miss (the polygon kernel's pre-filter) may only drop cubes for which plane_cube_points finds no point:
+  planes through / next to corners, edges and faces, zero and tiny normal components, coordinates up to 60 000."""
+  for span, seed in ((64.0, 1), (1100.0, 2), (60000.0, 3)):
+    r = hostsim.miss_check(2_000_000, seed, span)
+    assert r["violations"] == 0, r
+    assert r["miss"] > r["far"] > 0 and r["polygons"] > 0, r   # it filters more than the sphere test, and cut cubes are present
