@@ -1551,22 +1551,54 @@ __global__ void __launch_bounds__(128) combine_kernel(const ItemRec* __restrict_
     __syncthreads();
     if (n > XS_COMBINE_TILED_FROM) {
       // a large section (up to ~1e5 items): the ordered sum is one dependent chain of float additions whatever we do, so
-      // make each link as short as possible — all threads stage 1024 (value, first) pairs in shared memory, thread 0
-      // adds them up from there (a handful of cycles per item instead of two shuffles and a select)
+      // make the chain as short as it can be.  Per tile of 1024 items: all threads stage (value, first) pairs in shared
+      // memory; every thread sums the items of the samples that START in its eight slots (a sample's own sum is a short
+      // chain of 1-27 additions, independent of every other sample's) and the sums are compacted in order; thread 0 then
+      // runs the one chain that is inherently serial — total += sum of the next sample — one addition per SAMPLE with
+      // nothing else on the dependency path (it used to walk every item through two shared loads and a select).
       __shared__ float tile_v[1024];
       __shared__ uint8_t tile_f[1024];
+      __shared__ __align__(16) float dense[1024];
+      __shared__ int wcount[4];
       __shared__ float carry[2];
       if (threadIdx.x == 0) { carry[0] = 0.0f; carry[1] = 0.0f; }
+      const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
       for (uint32_t b = 0; b < n; b += 1024u) {
         __syncthreads();
-        const uint32_t len = min(1024u, n - b);
-        for (uint32_t j = threadIdx.x; j < len; j += blockDim.x) { const ItemRec e = it[b + j]; tile_v[j] = vals[e.poly]; tile_f[j] = (uint8_t)((e.meta >> 5) & 1u); }
+        const int len = (int)min(1024u, n - b);
+        for (int j = threadIdx.x; j < len; j += blockDim.x) { const ItemRec e = it[b + j]; tile_v[j] = vals[e.poly]; tile_f[j] = (uint8_t)((e.meta >> 5) & 1u); }
+        __syncthreads();
+        const int j0 = (int)threadIdx.x * 8;
+        int mine = 0;
+#pragma unroll
+        for (int t = 0; t < 8; t++) mine += (j0 + t < len && tile_f[j0 + t]) ? 1 : 0;
+        int inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+        if (lane == 31) wcount[wrp] = inc;
+        __syncthreads();
+        int off = inc - mine, nseg = 0;
+        for (int i = 0; i < 4; i++) { if (i < wrp) off += wcount[i]; nseg += wcount[i]; }
+        for (int t = 0; t < 8; t++) {
+          const int j = j0 + t;
+          if (j < len && tile_f[j]) {
+            float sub = fadd(0.0f, tile_v[j]);
+            for (int k = j + 1; k < len && !tile_f[k]; k++) sub = fadd(sub, tile_v[k]);
+            dense[off++] = sub;
+          }
+        }
         __syncthreads();
         if (threadIdx.x == 0) {
-          OrderedSum s;
-          s.total = carry[0]; s.sub = carry[1];
-          for (uint32_t j = 0; j < len; j++) s.add(tile_v[j], tile_f[j] != 0);
-          carry[0] = s.total; carry[1] = s.sub;
+          float total = carry[0], sub = carry[1];
+          for (int j = 0; j < len && !tile_f[j]; j++) sub = fadd(sub, tile_v[j]);      // the tail of a sample that began in the previous tile
+          int i = 0;
+          for (; i + 4 <= nseg; i += 4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(&dense[i]);
+            total = fadd(total, sub); total = fadd(total, d4.x); total = fadd(total, d4.y); total = fadd(total, d4.z);
+            sub = d4.w;
+          }
+          for (; i < nseg; i++) { total = fadd(total, sub); sub = dense[i]; }
+          carry[0] = total; carry[1] = sub;
         }
       }
       __syncthreads();
@@ -1737,6 +1769,8 @@ struct xs3d_volume {
   uint64_t stats[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t tier_stats[2] = {0, 0};   // samples / items handled by the CTA tiers
   uint32_t wide_over = 0;            // queries the wide tier passed on to the big tier
+  bool expect_wide = false;          // the previous batch had sections that left the mid tier's window: launch the wide / big
+                                     //   tiers in the first round of the next one (no host round trip in between)
   uint64_t prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   int sm_count = 0, smem_optin = 0;
   bool kernels_configured = false;
@@ -2176,6 +2210,72 @@ extern "C" int xs3d_volume_pack_and_stage(xs3d_volume* v, const uint8_t* binimg,
   return stage_finish(v, slot, c_order);
 }
 
+// Several processes (one per GPU) that can all read ONE host image (shared memory, or a replica each): every process
+// packs and uploads only its part of the bit stream, the parts are all-gathered between the GPUs by the host layer on a
+// stream of its own, and each GPU builds its occupancy bytes from the whole stream — the packing (the host-memory-bound
+// part of the end-to-end step) is spread over the cores of every rank instead of the source rank's.
+//   staged_bits        : the slot's device bit buffer (at least min_bytes long: the all-gather wants world * part bytes)
+//   pack_and_stage_part: voxels [lo, hi) -> bits, copied to their place in that buffer on the upload stream
+//   wait_staged_bits   : `cuda_stream` waits for that copy (then runs the all-gather into the buffer)
+//   ingest_staged      : bits -> spare occupancy bytes on `cuda_stream`, behind the all-gather; marks the slot staged
+extern "C" int xs3d_volume_staged_bits(xs3d_volume* v, int slot, uint64_t min_bytes, void** device_ptr, uint64_t* bytes) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (slot < 0 || slot > 1 || !device_ptr || !bytes) return fail(XS3D_ERR_ARG, "slot must be 0 or 1");
+  CK(cudaSetDevice(v->device));
+  const size_t voxels = (size_t)v->sx * v->sy * v->sz;
+  const size_t nbytes = (voxels + 7) / 8;
+  RET(stage_prepare(v, slot, std::max<size_t>(nbytes, (size_t)min_bytes)));
+  *device_ptr = v->staged[slot].p;
+  *bytes = (uint64_t)nbytes;
+  return XS3D_OK;
+}
+extern "C" int xs3d_volume_pack_and_stage_part(xs3d_volume* v, const uint8_t* binimg, int slot, uint64_t lo_voxel, uint64_t hi_voxel) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (slot < 0 || slot > 1) return fail(XS3D_ERR_ARG, "slot must be 0 or 1");
+  CK(cudaSetDevice(v->device));
+  const size_t voxels = (size_t)v->sx * v->sy * v->sz;
+  if (voxels == 0) return XS3D_OK;
+  if (!binimg) return fail(XS3D_ERR_ARG, "null image");
+  if ((hi_voxel > lo_voxel && lo_voxel % 4096 != 0) || hi_voxel > voxels || lo_voxel > hi_voxel) return fail(XS3D_ERR_ARG, "part must start at a multiple of 4096 voxels and end inside the image");
+  const size_t nbytes = (voxels + 7) / 8;
+  RET(stage_wait_copies(v, slot));
+  RET(stage_prepare(v, slot, nbytes));
+  if (v->h_stage_cap[slot] < nbytes + 64) {
+    if (v->h_stage_bits[slot]) cudaFreeHost(v->h_stage_bits[slot]);
+    v->h_stage_bits[slot] = nullptr; v->h_stage_cap[slot] = 0;
+    CK(cudaHostAlloc((void**)&v->h_stage_bits[slot], nbytes + 4096, cudaHostAllocDefault));
+    v->h_stage_cap[slot] = nbytes + 4096;
+  }
+  // the ingest of the image that went through this slot before read the device bit buffer on the caller's stream
+  CK(cudaStreamWaitEvent(v->stage_stream, v->stage_ev[slot], 0));
+  if (hi_voxel > lo_voxel) {
+    PackUpload up{ v->h_stage_bits[slot], (uint8_t*)v->staged[slot].p, v->stage_stream, cudaSuccess };
+    xs_pack_bits_parts(binimg, (size_t)lo_voxel, (size_t)hi_voxel, v->h_stage_bits[slot], 4, pack_part_ready, &up);
+    CK(up.err);
+  }
+  CK(cudaEventRecord(v->stage_copy_ev[slot], v->stage_stream));
+  v->stage_copy_pending[slot] = true;
+  return XS3D_OK;
+}
+extern "C" int xs3d_volume_wait_staged_bits(xs3d_volume* v, int slot, void* cuda_stream) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (slot < 0 || slot > 1 || !v->stage_stream) return fail(XS3D_ERR_ARG, "nothing staged in this slot");
+  CK(cudaSetDevice(v->device));
+  CK(cudaStreamWaitEvent((cudaStream_t)cuda_stream, v->stage_copy_ev[slot], 0));
+  return XS3D_OK;
+}
+extern "C" int xs3d_volume_ingest_staged(xs3d_volume* v, int slot, int c_order, void* cuda_stream) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  if (slot < 0 || slot > 1 || !v->stage_stream) return fail(XS3D_ERR_ARG, "slot not prepared (xs3d_volume_staged_bits first)");
+  CK(cudaSetDevice(v->device));
+  const size_t voxels = (size_t)v->sx * v->sy * v->sz;
+  if (voxels == 0) return XS3D_OK;
+  RET(launch_ingest_bits_to(v, (const uint8_t*)v->staged[slot].p, c_order, (uint8_t*)v->staged_cubes[slot].p, (cudaStream_t)cuda_stream));
+  CK(cudaEventRecord(v->stage_ev[slot], (cudaStream_t)cuda_stream));
+  v->staged_ready[slot] = true;
+  return XS3D_OK;
+}
+
 // For a host layer that fills the spare occupancy bytes of a slot itself (an NCCL broadcast into them on its own stream):
 // the buffer, the "wait for what was staged" hook for that stream, and the call that marks the slot as staged.
 extern "C" int xs3d_volume_staged_cubes(xs3d_volume* v, int slot, void** device_ptr, uint64_t* bytes) {
@@ -2482,6 +2582,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     //      0.74 ms launched directly — the graph executor does not reproduce the co-residency of the three streams (the
     //      mid tier runs alone first: 0.21 ms, then the warp tier: 0.49 ms), which is what the launch order and the stream
     //      priorities of the direct path arrange.
+    const bool speculate_wide = !single && v->expect_wide;
     bool capturing = false;
     auto rec_t = [&](cudaEvent_t ev, cudaStream_t st) -> cudaError_t {
       return capturing ? cudaEventRecordWithFlags(ev, st, cudaEventRecordExternal) : cudaEventRecord(ev, st);
@@ -2545,8 +2646,21 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       area_mid_kernel<MidTier><<<v->mid_ctas, MidTier::THREADS, MidTier::SMEM_BYTES, s2>>>(a, v->cfg_mid, CNT_NEXT1, CNT_OVER1, 10, -1);
       CK(cudaGetLastError());
       CK(rec_t(v->evs[2], s2));
-      // the second half of every section the mid tier parked (sections that leave its window are rare: they get a
-      // second round after the host has seen the counters, see below)
+      // Sections that leave the mid tier's window are rare (none in the 512^3 bench, four in the 1024^3 one): normally
+      // they get a second round after the host has seen the counters (below).  A sweep that had some is likely to be
+      // followed by another that has some (same object, same scale), so after such a batch the wide and big tiers are
+      // launched here, behind the mid tier's second launch, and their sections join the same P2 chain: no host round
+      // trip, no second chain of launches (1024^3 sweep: 0.33 ms of exposed tail).  Empty lists cost two launches.
+      if (speculate_wide) {
+        a.out = out2; a.done_list = done2; a.list_in = list1; a.list_out = listw;
+        area_wide_kernel<<<v->wide_ctas, WideTier::THREADS, WIDE_SMEM_BYTES, s2>>>(a, v->cfg_wide, CNT_NEXTW, CNT_OVERW, d_cnt + CNT_OVER1, 10);
+        CK(cudaGetLastError());
+        a.list_in = listw; a.list_out = list2;
+        area_block_kernel<BigTier><<<std::min(v->sm_count, 16), BigTier::THREADS, block_smem_bytes(v), s2>>>(a, v->cfg1, block_smem_bits_words(v), CNT_NEXT2, CNT_OVER2, d_cnt + CNT_OVERW, 10);
+        CK(cudaGetLastError());
+        launches += 2;
+      }
+      // the second half of every section the CTA tiers parked
       a.out = out2; a.done_list = done2;
       RET(launch_p2(s2));
       CK(rec_t(v->evs[3], s2));
@@ -2603,7 +2717,7 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       const void* kp[7] = { d_pos, d_nrm, d_area, d_contact, h_area, h_contact, v->cubes.p };
       for (int i = 0; i < 7; i++) key.ptr[i] = kp[i];
       key.w[0] = w[0]; key.w[1] = w[1]; key.w[2] = w[2];
-      key.single = single ? 1 : 0; key.mid_key = v->mid_key; key.factor = v->p2_factor;
+      key.single = (single ? 1 : 0) | (speculate_wide ? 2 : 0); key.mid_key = v->mid_key; key.factor = v->p2_factor;
       key.caps[0] = v->poly_cap; key.caps[1] = v->poly_cap2; key.caps[2] = v->p2_order_cap; key.caps[3] = v->p2_rec_cap; key.caps[4] = (uint64_t)(uintptr_t)s1;
       xs3d_volume::BatchGraph* hit = nullptr;
       for (auto& g : v->graphs)
@@ -2659,7 +2773,8 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
     float* valsb = single ? vals1 : vals2;
     uint32_t* d_emitb = single ? d_emit1 : d_emit2;
     v->timing[2] = 0.0f;
-    if (!capacity && over1 > 0) {
+    if (!single) v->expect_wide = over1 > 0;
+    if (!capacity && over1 > 0 && !speculate_wide) {
       // SECOND ROUND: sections that left the mid tier's 256-cell window (or exceeded its 16 Ki samples) — the wide tier
       // (same walk, 416-cell window), the big tier's whole-plane bitmap walk for what leaves that too, their second half,
       // polygons and sums.  Rare in sweeps of thin objects (none in the 512^3 bench, four in the 1024^3 one), so the common

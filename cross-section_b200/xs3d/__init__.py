@@ -271,6 +271,32 @@ class Volume:
     """Declare the spare occupancy bytes of `slot` written by everything enqueued on `cuda_stream` so far."""
     _abi.check(self._lib.xs3d_volume_mark_staged(self._h, int(slot), C.c_void_p(int(cuda_stream))))
 
+  # -- one host image that every rank can read: each rank packs and uploads its part (xs3d.dist.stream_shared_volumes)
+  def staged_bits(self, slot=0, min_bytes=0):
+    """(device pointer, bytes of the image's bit stream) of the bit buffer of `slot`, at least `min_bytes` long."""
+    p = C.c_void_p()
+    n = C.c_uint64()
+    _abi.check(self._lib.xs3d_volume_staged_bits(self._h, int(slot), int(min_bytes), C.byref(p), C.byref(n)))
+    return p.value, n.value
+
+  def pack_and_stage_part(self, binimg, slot, lo_voxel, hi_voxel):
+    """Bit-pack voxels [lo, hi) of the boolean image (in memory order; lo a multiple of 4096) and copy them to their place
+    in the bit buffer of `slot` on the upload stream.  Returns (c_order of the image) once the part has been read."""
+    if tuple(int(s) for s in binimg.shape) != self.shape:
+      raise ValueError("image shape does not match the volume")
+    if binimg.dtype != bool and binimg.dtype != np.uint8:
+      raise ValueError(f"A boolean image is required. Got: {binimg.dtype}")
+    a, ptr, c_order = _image_pointer(binimg)
+    _abi.check(self._lib.xs3d_volume_pack_and_stage_part(self._h, ptr, int(slot), int(lo_voxel), int(hi_voxel)))
+    return bool(c_order)
+
+  def wait_staged_bits(self, slot, cuda_stream):
+    _abi.check(self._lib.xs3d_volume_wait_staged_bits(self._h, int(slot), C.c_void_p(int(cuda_stream))))
+
+  def ingest_staged(self, slot, c_order, cuda_stream):
+    """Bit buffer of `slot` -> its spare occupancy bytes on `cuda_stream`; commit_staged(slot) then swaps them in."""
+    _abi.check(self._lib.xs3d_volume_ingest_staged(self._h, int(slot), int(bool(c_order)), C.c_void_p(int(cuda_stream))))
+
   def load_labels(self, labels):
     if tuple(int(s) for s in labels.shape) != self.shape:
       raise ValueError("labels shape does not match the volume")

@@ -12,6 +12,9 @@ query list.  torch.distributed is used only as plumbing:
     uploads volume k+1 on a helper thread while everybody sweeps volume k; the occupancy bytes are broadcast
     every step by a helper thread on a communicator of its own (broadcast_group), followed by a status byte
     that turns a failure of the source rank into an exception on every rank (the end-to-end loop of bench.py);
+  * stream_shared_volumes(): the same sequence when every rank can read the host images (shared memory, or a replica
+    each): every rank bit-packs and uploads 1/world of each image, the bit stream is all-gathered over NVLink and each
+    GPU ingests it — the host-memory-bound packing is spread over the cores of all ranks, not the source rank's;
   * broadcast_labels() / sharded_slice_batch(): the same for xs3d.slice — the label volume is broadcast once,
     the planes are partitioned (BASELINE config 5).
 
@@ -273,6 +276,72 @@ class VolumeFeed:
     return int(h[slot][0])
 
 
+def part_bounds(voxels, world_size, rank, align=32768):
+  """(part, lo, hi): the image is cut into `world_size` parts of `part` voxels (a multiple of `align`, so that every part
+  of the bit stream starts on a 4 KiB boundary); rank's part is [lo, hi) — empty, or shorter, at the end of the image."""
+  voxels, world_size = int(voxels), int(world_size)
+  per = -(-voxels // world_size)
+  part = -(-per // align) * align
+  lo = min(rank * part, voxels)
+  return part, lo, min(lo + part, voxels)
+
+
+class SharedVolumeFeed(VolumeFeed):
+  """What stream_shared_volumes does to a real (CUDA) Volume: pack + upload this rank's part, all-gather the bit stream
+  on the side stream, ingest it there."""
+
+  def prepare_parts(self, world_size):
+    voxels = int(np.prod(self.volume.shape))
+    part, _, _ = part_bounds(voxels, world_size, 0)
+    self._part_bytes = part // 8
+    self._bits = []
+    for slot in (0, 1):
+      ptr, _ = self.volume.staged_bits(slot, world_size * self._part_bytes)
+      self.volume.staged_cubes(slot)
+      self._bits.append(_device_bytes(ptr, world_size * self._part_bytes, self.volume.device))
+
+  def pack_part(self, image, slot, lo, hi):
+    return self.volume.pack_and_stage_part(image, slot, lo, hi)
+
+  def bits_tensor(self, slot):
+    return self._bits[slot]
+
+  def wait_bits(self, slot):
+    self.volume.wait_staged_bits(slot, self.bcast_stream().cuda_stream)
+
+  def ingest(self, slot, c_order):
+    self.volume.ingest_staged(slot, c_order, self.bcast_stream().cuda_stream)
+
+  # status bytes, one per rank, all-gathered behind every payload (same four-slot scheme as VolumeFeed's)
+  def gather_status(self, slot, value, rank, group):
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if getattr(self, "_gs_dev", None) is None or self._gs_dev[0].numel() != world:
+      dev = torch.device("cuda", self.volume.device)
+      self._gs_dev = [torch.zeros(world, dtype=torch.uint8, device=dev) for _ in range(4)]
+      self._gs_host = [torch.zeros(world, dtype=torch.uint8).pin_memory() for _ in range(4)]
+      self._gs_ev = [torch.cuda.Event() for _ in range(4)]
+      self._gs_issued = [False] * 4
+    d = self._gs_dev[slot]
+    d[rank: rank + 1].fill_(int(value))
+    dist.all_gather_into_tensor(d, d[rank: rank + 1], group=group)
+    self._gs_host[slot].copy_(d, non_blocking=True)
+    self._gs_ev[slot].record()
+    self._gs_issued[slot] = True
+
+  def read_gathered_status(self, slot, wait=True):
+    if getattr(self, "_gs_dev", None) is None or not self._gs_issued[slot]:
+      return 0
+    if wait:
+      import time
+      while not self._gs_ev[slot].query():
+        time.sleep(20e-6)
+    elif not self._gs_ev[slot].query():
+      return 0
+    return int(self._gs_host[slot].max())
+
+
 class _HostStatus:
   """Status byte that travels behind every staged payload (stream_volumes): generic form for feeds whose tensors live
   in host memory (the gloo tests).  VolumeFeed has the CUDA form (side stream, pinned copy, event)."""
@@ -467,4 +536,103 @@ def stream_volumes(volume, images, n_steps, sweep, src=0, group=None, before_ste
       for sem in free:
         sem.release()
       th.join()
+  return results
+
+
+def stream_shared_volumes(volume, images, n_steps, sweep, group=None, before_step=None, feed=None):
+  """stream_volumes for host images EVERY rank can read (one copy in shared memory mapped by all the processes of the
+  node, or a replica per rank): run `sweep(k)` for k = 0 .. n_steps-1 with `volume` holding images[k].  Every rank
+  bit-packs and uploads only its 1/world part of image k+1 (part_bounds) on a helper thread while step k runs; the
+  helper all-gathers the parts of the bit stream on a side stream and a communicator of its own (broadcast_group) and
+  builds the occupancy bytes from the whole stream behind it; the step itself is a buffer swap + the sweep.  Compared
+  with stream_volumes the host work per image — reading it once, the part of the end-to-end step that is bound by host
+  memory — is spread over the cores of all ranks, and 1/world of the bits crosses each GPU's PCIe link.
+
+  Every rank must pass the same `n_steps` images (same content, shape and memory order).  `sweep` may run collectives
+  on `group` but must not use broadcast_group(group).  A status byte per rank is all-gathered behind every payload: if
+  any rank fails to pack its part, every rank raises at that step.  `feed`: a SharedVolumeFeed(volume), or a stand-in
+  for the CUDA plumbing (the gloo tests).  One rank (or no process group): plain stream_volumes."""
+  import threading
+  import torch.distributed as dist
+  multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+  if not multi:
+    return stream_volumes(volume, images, n_steps, sweep, src=0, group=group, before_step=before_step,
+                          feed=feed if feed is not None and hasattr(feed, "pack_and_stage") else None)
+  if images is None or len(images) < n_steps:
+    raise ValueError("every rank must pass one image per step")
+  world = dist.get_world_size(group)
+  rank = dist.get_rank(group)
+  feed = feed if feed is not None else SharedVolumeFeed(volume)
+  bgroup = broadcast_group(group)
+  feed.prepare_parts(world)
+  voxels = int(np.prod(images[0].shape))
+  part, lo, hi = part_bounds(voxels, world, rank)
+  pbytes = part // 8
+  free = [threading.Semaphore(1), threading.Semaphore(1)]
+  bready = [threading.Semaphore(0), threading.Semaphore(0)]
+  failure = []
+  stop = threading.Event()
+  if hasattr(feed, "_gs_issued"):
+    feed._gs_issued = [False] * 4
+
+  def failed(k):
+    for kk, e in failure:
+      if kk <= k:
+        return e
+    return None
+
+  def helper():
+    feed.bind_thread()
+    for k in range(n_steps):
+      slot = k & 1
+      free[slot].acquire()
+      bad = 1 if stop.is_set() else 0
+      c_order = False
+      if not bad:
+        try:
+          if tuple(images[k].shape) != tuple(images[0].shape):
+            raise ValueError("image shape does not match the volume")
+          c_order = feed.pack_part(images[k], slot, lo, hi)
+        except BaseException as e:      # flagged to every rank below; raised here by the main thread at step k
+          failure.append((k, e))
+          bad = 1
+      try:
+        with feed.bcast_ctx():
+          feed.wait_bits(slot)
+          full = feed.bits_tensor(slot)
+          dist.all_gather_into_tensor(full, full[rank * pbytes: (rank + 1) * pbytes], group=bgroup)
+          feed.gather_status(k & 3, bad, rank, bgroup)
+          feed.ingest(slot, c_order)
+      except BaseException as e:
+        failure.append((k, e))
+        bready[slot].release()
+        return
+      bready[slot].release()
+      if bad or feed.read_gathered_status(k & 3, wait=True):
+        return
+
+  th = threading.Thread(target=helper, name="xs3d-volume-parts")
+  th.start()
+  results = []
+  try:
+    for k in range(n_steps):
+      if before_step is not None:
+        before_step(k)
+      bready[k & 1].acquire()
+      if failed(k) is not None:
+        raise failed(k)
+      if feed.read_gathered_status(k & 3, wait=False):
+        raise RuntimeError(f"stream_shared_volumes: a rank failed to produce its part of image {k}")
+      feed.commit_swap(k & 1)
+      free[k & 1].release()
+      r = sweep(k)
+      # the sweep waited (on the device) for the all-gather of step k, so its status bytes have arrived by now
+      if feed.read_gathered_status(k & 3, wait=True):
+        raise RuntimeError(f"stream_shared_volumes: a rank failed to produce its part of image {k}")
+      results.append(r)
+  finally:
+    stop.set()
+    for sem in free:
+      sem.release()
+    th.join()
   return results

@@ -74,6 +74,18 @@ int xs3d_volume_commit_staged(xs3d_volume* vol, int slot);
 int xs3d_volume_staged_cubes(xs3d_volume* vol, int slot, void** device_ptr, uint64_t* bytes);
 int xs3d_volume_wait_staged(xs3d_volume* vol, int slot, void* cuda_stream);
 int xs3d_volume_mark_staged(xs3d_volume* vol, int slot, void* cuda_stream);
+/* One host image that several processes (one per GPU) can all read — shared memory, or a replica each: every process
+ * packs and uploads only ITS part of the bit stream, so the host-memory-bound packing is spread over the cores of all
+ * ranks.  staged_bits: the slot's device bit buffer, at least min_bytes long ((voxels + 7) / 8 bytes are the image; an
+ * all-gather of equal parts may need a little more).  pack_and_stage_part: voxels [lo, hi) (lo a multiple of 4096) ->
+ * bits -> their place in that buffer, on the volume's upload stream; returns when the part has been read.
+ * wait_staged_bits: `cuda_stream` waits for that copy; the host layer then all-gathers the parts into the buffer on that
+ * stream.  ingest_staged: bits -> the slot's spare occupancy bytes on `cuda_stream` (behind the all-gather) and marks
+ * the slot staged, so that commit_staged waits for exactly that.  c_order as in xs3d_volume_load. */
+int xs3d_volume_staged_bits(xs3d_volume* vol, int slot, uint64_t min_bytes, void** device_ptr, uint64_t* bytes);
+int xs3d_volume_pack_and_stage_part(xs3d_volume* vol, const uint8_t* binimg, int slot, uint64_t lo_voxel, uint64_t hi_voxel);
+int xs3d_volume_wait_staged_bits(xs3d_volume* vol, int slot, void* cuda_stream);
+int xs3d_volume_ingest_staged(xs3d_volume* vol, int slot, int c_order, void* cuda_stream);
 /* Attach a label volume for xs3d_projection_v (any 1/2/4/8-byte dtype, C or F order; fastxs3d.cpp:135,199-215). */
 int xs3d_volume_load_labels(xs3d_volume* vol, const void* labels, int itemsize, int mem, int c_order);
 /* The device buffer of the label volume, (re)allocated for that item size / order without an upload: for a host layer

@@ -224,3 +224,121 @@ def test_stream_volumes_gloo():
   for p in procs:
     p.join(60)
   assert sorted(res) == [(0, True), (1, True)]
+
+
+def _shared_worker(rank, world, port, q):
+  """stream_shared_volumes on gloo: every rank really bit-packs ITS part of every image (xs3d_pack_bits is host code),
+  the parts travel by gloo all-gather, a CPU stand-in plays upload / ingest; every rank checks what it holds at every
+  step, a sweep runs a collective beside the helper thread, and a rank that cannot pack its part makes every rank raise."""
+  import ctypes as C
+  import torch
+  import torch.distributed as dist
+  sys.path.insert(0, os.path.join(ROOT, "cross-section_b200"))
+  from xs3d import _abi
+  from xs3d import dist as xdist
+  dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+  try:
+    shape = (64, 40, 33)          # 84 480 voxels: parts of 65 536 and 18 944
+    voxels = int(np.prod(shape))
+    h = [(s + 1) // 2 for s in shape]
+
+    def occupancy(vol):
+      pad = np.zeros([2 * x for x in h], bool)
+      pad[: shape[0], : shape[1], : shape[2]] = vol
+      out = np.zeros(h, np.uint8)
+      for b in range(8):
+        out |= pad[(b & 1)::2, ((b >> 1) & 1)::2, (b >> 2)::2].astype(np.uint8) << b
+      return out.ravel(order="F")
+
+    rng = np.random.default_rng(5)
+    images = [rng.random(shape) < 0.4 for _ in range(5)]
+    images = [np.asfortranarray(v) if i % 2 == 0 else np.ascontiguousarray(v) for i, v in enumerate(images)]
+    expected = [occupancy(v) for v in images]
+    part, lo, hi = xdist.part_bounds(voxels, world, rank)
+    assert part % 32768 == 0 and (lo, hi) == ((0, 65536) if rank == 0 else (65536, voxels))
+    lib = _abi.lib()
+
+    class CpuPartFeed:
+      def __init__(self):
+        self.cubes = torch.zeros(int(np.prod(h)), dtype=torch.uint8)
+        self.spare = [torch.zeros_like(self.cubes), torch.zeros_like(self.cubes)]
+        self.bits = None
+        self.status = [torch.zeros(world, dtype=torch.uint8) for _ in range(4)]
+        self.ready = [False, False]
+        self.bound = 0
+      def prepare_parts(self, world_size):
+        self.bits = [torch.zeros(world_size * part // 8, dtype=torch.uint8) for _ in range(2)]
+      def bind_thread(self):
+        self.bound += 1
+      def bcast_ctx(self):
+        import contextlib
+        return contextlib.nullcontext()
+      def pack_part(self, image, slot, plo, phi):
+        if image.dtype != bool:
+          raise ValueError("A boolean image is required")
+        flat = image.view(np.uint8).ravel(order="K")
+        dst = self.bits[slot].numpy()
+        if phi > plo:
+          rc = lib.xs3d_pack_bits(C.c_void_p(flat.ctypes.data + plo), phi - plo, C.c_void_p(dst.ctypes.data + plo // 8))
+          assert rc == 0
+        return bool(image.flags.c_contiguous and not image.flags.f_contiguous)
+      def wait_bits(self, slot):
+        pass
+      def bits_tensor(self, slot):
+        return self.bits[slot]
+      def gather_status(self, slot, value, r, group):
+        t = self.status[slot]
+        t[r] = int(value)
+        dist.all_gather_into_tensor(t, t[r: r + 1].clone(), group=group)
+      def read_gathered_status(self, slot, wait=True):
+        return int(self.status[slot].max())
+      def ingest(self, slot, c_order):
+        vox = np.unpackbits(self.bits[slot].numpy(), bitorder="little")[:voxels].astype(bool)
+        self.spare[slot][:] = torch.from_numpy(occupancy(vox.reshape(shape, order="C" if c_order else "F")))
+        self.ready[slot] = True
+      def commit_swap(self, slot):
+        assert self.ready[slot]
+        self.ready[slot] = False
+        self.cubes, self.spare[slot] = self.spare[slot], self.cubes
+
+    feed = CpuPartFeed()
+    seen = []
+    res = xdist.stream_shared_volumes(None, images, 5, lambda k: feed.cubes.numpy().copy(), before_step=seen.append, feed=feed)
+    ok = len(res) == 5 and all(np.array_equal(r, e) for r, e in zip(res, expected)) and seen == list(range(5)) and feed.bound == 1
+    feed2 = CpuPartFeed()
+
+    def sweep_with_collective(k):
+      t = torch.tensor([float(feed2.cubes.sum())], dtype=torch.float64)
+      dist.all_reduce(t)
+      return float(t.item())
+    res2 = xdist.stream_shared_volumes(None, images, 5, sweep_with_collective, feed=feed2)
+    ok = ok and all(r == 2.0 * float(e.sum()) for r, e in zip(res2, expected))
+    # rank 1 cannot pack its part of image 2: it raises its own error, rank 0 a RuntimeError, both at step 2
+    feed3 = CpuPartFeed()
+    bad = list(images[:4])
+    if rank == 1:
+      bad[2] = np.zeros(shape, np.float32)
+    done = []
+    try:
+      xdist.stream_shared_volumes(None, bad, 4, done.append, feed=feed3)
+      ok = False
+    except ValueError:
+      ok = ok and rank == 1 and done == [0, 1]
+    except RuntimeError:
+      ok = ok and rank == 0 and done == [0, 1]
+    q.put((rank, ok))
+  finally:
+    dist.destroy_process_group()
+
+
+def test_stream_shared_volumes_gloo():
+  ctx = mp.get_context("spawn")
+  q = ctx.Queue()
+  port = 35500 + (os.getpid() % 2000)
+  procs = [ctx.Process(target=_shared_worker, args=(r, 2, port, q)) for r in range(2)]
+  for p in procs:
+    p.start()
+  res = [q.get(timeout=180) for _ in procs]
+  for p in procs:
+    p.join(60)
+  assert sorted(res) == [(0, True), (1, True)]

@@ -516,8 +516,19 @@ def test_long_and_wide_sections_all_cta_tiers(xs, oracle):
   with xs.Volume(vol) as V:
     a, c = V.cross_sectional_area_batch(qp, qn, w, return_contact=True)
     st = V.stats()
+    # a batch that follows one with wide sections launches the wide / big tiers in its first round (no host round trip)
+    a2, c2 = V.cross_sectional_area_batch(qp, qn, w, return_contact=True)
+    st2 = V.stats()
+    # ... and one without wide sections switches that off again for the batch after it
+    small = [i for i in range(len(qp)) if i % 4 == 3]
+    a3, c3 = V.cross_sectional_area_batch(np.repeat(qp[small], 2, 0), np.repeat(qn[small], 2, 0), w, return_contact=True)
+    a4, c4 = V.cross_sectional_area_batch(qp, qn, w, return_contact=True)
     singles = [V.cross_sectional_area(qp[i], qn[i], w, return_contact=True) for i in range(len(qp))]
   assert np.array_equal(bits(a), bits(oa)) and np.array_equal(c, oc)
+  assert np.array_equal(bits(a2), bits(oa)) and np.array_equal(c2, oc)
+  assert np.array_equal(bits(a4), bits(oa)) and np.array_equal(c4, oc)
+  assert np.array_equal(bits(a3), bits(np.repeat(oa[small], 2))) and np.array_equal(c3, np.repeat(oc[small], 2))
+  assert st2["escalated_big"] == st["escalated_big"], (st, st2)
   for i, (sa, sc) in enumerate(singles):
     assert bits(np.float32(sa)) == bits(oa[i]) and sc == oc[i], i
   assert st["escalated_mid"] > 0 and st["escalated_big"] > 0, st     # the mid tier handed sections on to the wide / big tiers

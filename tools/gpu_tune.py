@@ -24,6 +24,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
       os.environ.get("TAG", ""), float(np.median(ts[3:])), min(ts), t["warp_tier_ms"], t["mid_tier_ms"], t["mid_exposed_ms"], t["prepass_ms"],
       t["polygon_ms"], t["combine_ms"], st["escalated_mid"], st["escalated_big"]), flush=True)
   sys.exit(0)
-for key in (10, 14, 18, 22, 26, 32):
+for key in [int(k) for k in os.environ.get("XS_KEYS", "18,22,26,30,34,40,48").split(",")]:
   env = dict(os.environ, XS3D_MID_KEY=str(key), TAG="key=%d" % key)
   subprocess.run([sys.executable, __file__, "child"], env=env)
