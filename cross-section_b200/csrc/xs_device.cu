@@ -1163,6 +1163,7 @@ constexpr int P2_LPROBE = 32;
 __global__ void __launch_bounds__(P2_CHUNK) p2_claims_kernel(BatchArgs a) {
   __shared__ uint32_t s_tag[P2_LCAP], s_key[P2_LCAP];
   __shared__ uint16_t s_list[P2_LCAP];
+  __shared__ uint32_t s_tent[P2_CHUNK];
   __shared__ int s_wsum[P2_CHUNK / 32];
   const uint32_t nchunks = min(a.p2.cursors[P2C_CHUNK], a.p2.chunk_cap), chunk_start = a.p2.cursors[P2C_DONE];
   if (a.p2.cursors[P2C_FULL]) return;
@@ -1172,17 +1173,17 @@ __global__ void __launch_bounds__(P2_CHUNK) p2_claims_kernel(BatchArgs a) {
     const PlaneCtx& c = k.rec->c;
     __syncthreads();
     for (int i = threadIdx.x; i < P2_LCAP; i += P2_CHUNK) { s_tag[i] = XS_HEMPTY; s_key[i] = XS_HEMPTY; }
+    s_tent[threadIdx.x] = 0u;
     __syncthreads();
-    uint32_t ct = 0u, cmask = 0u, tag = 0u, tentative = 0u, direct = 0u;
+    uint32_t ct = 0u, tentative = 0u;
     bool ovf = false;
     const bool live = k.r < (int)k.n;
     if (live) {
       V3 cur;
       const Sample s = sample_at(c, k.A, k.r, &cur);
       ct = contact_bits_rounded(c, cur);
-      cmask = probe_candidates(c, a.vol, s);
-      tag = k.H.tag(s.rx >> 1, s.ry >> 1, s.rz >> 1);
-      uint32_t m = cmask;
+      const uint32_t tag = k.H.tag(s.rx >> 1, s.ry >> 1, s.rz >> 1);
+      uint32_t m = probe_candidates(c, a.vol, s);
       while (m) {
         const int kk = __ffs(m) - 1;
         m &= m - 1u;
@@ -1191,13 +1192,15 @@ __global__ void __launch_bounds__(P2_CHUNK) p2_claims_kernel(BatchArgs a) {
         const uint32_t t = tag + k.H.tag_delta(ox, oy, oz);
         uint32_t h = (t * 2654435761u) >> (32 - 11);
         bool placed = false;
+        // the local key is (thread << 5 | offset): ordered by rank (a sample probes a block once), and the slot's winner
+        // is known with its offset — it gets its tentative bit from whoever sends the slot's claim on (no second walk
+        // over the 27 offsets to ask the table who won)
         for (int probes = 0; probes < P2_LPROBE; probes++) {
           const uint32_t old = atomicCAS(&s_tag[h], XS_HEMPTY, t);
-          if (old == XS_HEMPTY || old == t) { atomicMin(&s_key[h], (uint32_t)k.r); placed = true; break; }
+          if (old == XS_HEMPTY || old == t) { atomicMin(&s_key[h], (threadIdx.x << 5) | (uint32_t)kk); placed = true; break; }
           h = (h + 1u) & (P2_LCAP - 1u);
         }
         if (!placed) {                                           // local table crowded: this claim goes to the section's table itself
-          direct |= 1u << kk;
           const int won = k.H.claim_tag(t, (uint32_t)k.r);
           if (won == 0) ovf = true;
           if (won == 2) tentative |= 1u << kk;
@@ -1228,28 +1231,17 @@ __global__ void __launch_bounds__(P2_CHUNK) p2_claims_kernel(BatchArgs a) {
       for (int j = 0; j < P2_LCAP / P2_CHUNK; j++)
         if ((mine >> j) & 1u) s_list[o++] = (uint16_t)(threadIdx.x * (P2_LCAP / P2_CHUNK) + j);
       __syncthreads();
+      const uint32_t rank0 = (uint32_t)(k.r - (int)threadIdx.x);  // rank of the chunk's first sample
       for (int e = threadIdx.x; e < total; e += P2_CHUNK) {
         const int i = s_list[e];
-        const int won = k.H.claim_tag(s_tag[i], s_key[i]);
+        const uint32_t key = s_key[i];
+        const int won = k.H.claim_tag(s_tag[i], rank0 + (key >> 5));
         if (won == 0) ovf = true;
-        if (won != 2) s_key[i] = XS_HEMPTY;                      // a smaller rank of another chunk holds the block
+        if (won == 2) atomicOr(&s_tent[key >> 5], 1u << (key & 31u));   // else: a smaller rank of another chunk holds the block
       }
     }
     __syncthreads();
-    if (live) {
-      uint32_t m = cmask & ~direct;
-      while (m) {
-        const int kk = __ffs(m) - 1;
-        m &= m - 1u;
-        int ox, oy, oz;
-        decode_k(kk, ox, oy, oz);
-        const uint32_t t = tag + k.H.tag_delta(ox, oy, oz);
-        uint32_t h = (t * 2654435761u) >> (32 - 11);
-        while (s_tag[h] != t) h = (h + 1u) & (P2_LCAP - 1u);
-        if (s_key[h] == (uint32_t)k.r) tentative |= 1u << kk;
-      }
-      k.A.mask[k.r] = tentative;
-    }
+    if (live) k.A.mask[k.r] = tentative | s_tent[threadIdx.x];
     ct = __reduce_or_sync(0xffffffffu, ct);
     if ((threadIdx.x & 31) == 0 && ct) atomicOr(&a.p2.recs[k.rec_index].contact, ct);
     if (ovf) a.p2.cursors[P2C_HASHFULL] = 1u;
