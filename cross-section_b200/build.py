@@ -17,7 +17,7 @@ SRC = os.path.join(HERE, "csrc")
 TAG = os.environ.get("XS3D_BUILD_TAG", "")
 OUT = os.path.join(HERE, "lib", "libxs3d_b200%s.so" % ("_" + TAG if TAG else ""))
 OBJ = os.path.join(HERE, "lib", "obj" + ("_" + TAG if TAG else ""))
-UNITS = ["xs_device.cu", "xs_slow.cu", "xs_slice.cu", "xs_section.cu", "xs_skeleton.cu", "xs_hostpack.cpp"]   # .cpp: host-only code, compiled by g++
+UNITS = ["xs_device.cu", "xs_slow.cu", "xs_slice.cu", "xs_section.cu", "xs_skeleton.cu", "xs_twod.cu", "xs_hostpack.cpp"]   # .cpp: host-only code, compiled by g++
 CXX = os.environ.get("CXX", "g++")
 NVCC = os.environ.get("NVCC", "nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=false",

@@ -696,7 +696,19 @@ def cross_sectional_area(
   if binimg.dtype != bool:
     raise ValueError(f"A boolean image is required. Got: {binimg.dtype}")
   if binimg.ndim == 2:
-    raise NotImplementedError("2-D images (xs3d/twod.py, needs cc3d) are out of scope of the B200 build")
+    # the reference's pure-Python 2-D path (xs3d/twod.py:73, via xs3d/__init__.py:79-80) on the device: xs_twod.cu
+    if pos.size != 2 or normal.size != 2 or anisotropy.size != 2:
+      raise ValueError("a 2-D image needs 2-D pos, normal and anisotropy")
+    a2 = np.asfortranarray(binimg).view(np.uint8)
+    pos, normal, anisotropy = (np.ascontiguousarray(v.reshape(-1)) for v in (pos, normal, anisotropy))
+    area2 = C.c_double(0.0)
+    contact2 = C.c_uint8(0)
+    rc = _abi.lib().xs3d_area_2d(a2.ctypes.data, a2.shape[0], a2.shape[1], _abi.fptr(pos), _abi.fptr(normal), _abi.fptr(anisotropy),
+                                 C.byref(area2), C.byref(contact2))
+    if rc == 2 and b"more than two distinct" in (_abi.lib().xs3d_last_error() or b""):
+      raise ValueError(_abi.lib().xs3d_last_error().decode())
+    _abi.check(rc)
+    return (area2.value, int(contact2.value)) if return_contact else area2.value
   elif binimg.ndim != 3:
     raise ValueError("dimensions not supported")
   L = _abi.lib()

@@ -147,6 +147,15 @@ int xs3d_volume_set_stream(xs3d_volume* vol, void* cuda_stream);
 int xs3d_area(const uint8_t* binimg, uint64_t sx, uint64_t sy, uint64_t sz,
               const float pos[3], const float normal[3], const float anisotropy[3],
               int slow_method, int use_persistent_data, float* area, uint8_t* contact);
+/* xs3d.cross_sectional_area on a 2-D image: the reference's pure-Python cross_sectional_area_2d (xs3d/twod.py:73-174,
+ * called at xs3d/__init__.py:79-80; its third-party dependency cc3d is only used to find the 8-connected component of
+ * the seed pixel among the marked pixels).  `binimg`: HOST, x fastest ([sx][sy] Fortran order), 1 byte per pixel.
+ * `vec` is the 2-D "normal" argument.  area is float64 like the reference's; contact bits: 0 x == 0, 1 x == sx-1,
+ * 2 y == 0, 3 y == sy-1; a vertex outside the image or on background gives (0.0, 0b00111111) (twod.py:83-90).
+ * XS3D_ERR_ARG with the message "more than two distinct intersection points..." where the reference raises ValueError
+ * (twod.py:163-164). */
+int xs3d_area_2d(const uint8_t* binimg, uint64_t sx, uint64_t sy, const float pos[2], const float vec[2],
+                 const float anisotropy[2], double* area, uint8_t* contact);
 /* fastxs3d.section (fastxs3d.cpp:13-80).  `out` is a HOST float32 F-order buffer of
  * sx*sy*sz elements (method 0/1) or ceil(sx/2)*ceil(sy/2)*ceil(sz/2) (method 2) that the caller has
  * zero-filled (the reference's std::fill, fastxs3d.cpp:42-44); non-zero contributions are scattered into it. */

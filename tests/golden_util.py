@@ -40,3 +40,15 @@ def same_bits(a, b):
   a = np.asarray(a)
   b = np.asarray(b)
   return a.shape == b.shape and a.dtype == b.dtype and a.tobytes(order="F") == b.tobytes(order="F")
+
+
+def twod_cases(path=None):
+  """Yield (i, image, pos, vec, anisotropy, area float64, contact, raises) from tests/golden/golden_2d_v1.npz
+  (outputs of the reference's own xs3d/twod.py, tests/golden/make_golden_2d.py)."""
+  import os
+  path = path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_2d_v1.npz")
+  g = np.load(path)
+  for i in range(len(g["area"])):
+    sx, sy = (int(v) for v in g["shapes"][i])
+    img = np.unpackbits(g["packed"][g["off"][i]:g["off"][i + 1]])[: sx * sy].astype(bool).reshape((sx, sy), order="F")
+    yield i, np.asfortranarray(img), g["pos"][i], g["vec"][i], g["ani"][i], float(g["area"][i]), int(g["contact"][i]), bool(g["err"][i])

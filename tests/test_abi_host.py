@@ -41,6 +41,8 @@ def test_no_cpu_fallback_without_gpu():
     xs3d.cross_section(vol, [1, 1, 1], [0, 0, 1])
   with pytest.raises(xs3d.XS3DError):
     xs3d.slice(vol.astype(np.uint8), [1, 1, 1], [0, 0, 1])
+  with pytest.raises(xs3d.XS3DError):
+    xs3d.cross_sectional_area(np.ones((3, 3), dtype=bool), [1, 1], [0, 1])      # the 2-D path is device code too
 
 
 def test_input_validation_matches_reference():

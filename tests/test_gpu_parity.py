@@ -786,3 +786,33 @@ def test_p2_pools_grow_and_rerun(xs, oracle):
   for env in ({"XS3D_P2_ORDER_CAP": "300"}, {"XS3D_P2_FACTOR": "1"}, {"XS3D_P2_ORDER_CAP": "256", "XS3D_P2_FACTOR": "1"}):
     r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "ok" in r.stdout, (env, (r.stdout + r.stderr)[-2000:])
+
+
+def test_twod_path_matches_reference(xs):
+  """2-D images (xs3d/twod.py:73-174 via xs3d/__init__.py:79-80) on the device: the 600 golden cases of the reference's
+  own twod.py — float64 areas bit for bit (the non-zero lengths are added in the reference's raster order), contacts —
+  and the known answers of automated_test.py:393-418."""
+  import golden_util as gu
+  n = 0
+  for i, img, p, v, w, area, contact, raises in gu.twod_cases():
+    if raises:
+      with pytest.raises(ValueError):
+        xs.cross_sectional_area(img, p, v, w, return_contact=True)
+    else:
+      a, c = xs.cross_sectional_area(img, p, v, w, return_contact=True)
+      assert a == area and c == contact, (i, img.shape, p, v, w, a, area, c, contact)
+      if i % 7 == 0:    # C-ordered input and the contact-less return
+        assert xs.cross_sectional_area(np.ascontiguousarray(img), p, v, w) == area
+    n += 1
+  assert n == 600
+  labels = np.ones([3, 3], dtype=bool)
+  assert xs.cross_sectional_area(labels, [1, 1], [0, 1]) == 3
+  assert xs.cross_sectional_area(labels, [1, 1], [0, 1], [3, 3]) == 9
+  assert xs.cross_sectional_area(labels, [1, 1], [1, 0], [5, 5]) == 15
+  assert np.isclose(xs.cross_sectional_area(labels, [0, 0], [-1, 1], [1, 1]), 3 * np.sqrt(2))
+  assert xs.cross_sectional_area(labels, [-1, 0], [-1, 1], [1, 1]) == 0
+  big = np.ones([1500, 1100], dtype=bool)                      # a larger image: many CTAs, long union-find chains
+  a, c = xs.cross_sectional_area(big, [700.25, 500.5], [0.3, 1.0], [4, 40], return_contact=True)
+  import twod_oracle
+  oa, oc = twod_oracle.cross_sectional_area_2d(big, [700.25, 500.5], [0.3, 1.0], [4, 40])
+  assert a == oa and c == oc

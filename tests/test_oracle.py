@@ -164,3 +164,40 @@ def test_is_26_connected_exhaustive(oracle, ref):
         for centre in range(0, 256, 3):
           for cand in range(0, 256, 5):
             assert bool(orc.oracle_is_26_connected(centre, cand, ox, oy, oz)) == ref.is_26_connected(centre, cand, (ox, oy, oz))
+
+
+def test_twod_oracle_matches_reference_golden():
+  """oracle/twod_oracle.py (restatement of xs3d/twod.py:73-174) against the outputs of the reference's own twod.py:
+  float64 areas equal bit for bit, contacts equal."""
+  import os
+  import sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+  import twod_oracle
+  n = 0
+  for i, img, p, v, w, area, contact, raises in gu.twod_cases():
+    if raises:
+      with pytest.raises(ValueError):
+        twod_oracle.cross_sectional_area_2d(img, p, v, w)
+    else:
+      a, c = twod_oracle.cross_sectional_area_2d(img, p, v, w)
+      assert a == area and c == contact, (i, a, area, c, contact)
+    n += 1
+  assert n == 600
+
+
+def test_twod_oracle_reference_known_answers():
+  """automated_test.py:393-418 (test_2d) on the restatement."""
+  import os
+  import sys
+  sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+  from twod_oracle import cross_sectional_area_2d as f
+  labels = np.ones([3, 3], dtype=bool)
+  assert f(labels, [1, 1], [0, 1])[0] == 3
+  assert f(labels, [1, 1], [0, 1], [3, 3])[0] == 9
+  assert f(labels, [1, 1], [1, 0], [1, 1])[0] == 3
+  assert f(labels, [1, 1], [1, 0], [5, 5])[0] == 15
+  assert np.isclose(f(labels, [0, 0], [-1, 1], [1, 1])[0], 3 * np.sqrt(2))
+  assert f(labels, [-1, 0], [-1, 1], [1, 1])[0] == 0
+  assert f(labels, [1, -1], [-1, 1], [1, 1])[0] == 0
+  labels[1, 1] = 0
+  assert f(labels, [1, 1], [0, 1], [1, 1])[0] == 0

@@ -6,8 +6,9 @@
   package : this repo's host layer (cross-section_b200/xs3d) as the drop-in `import xs3d`.
 
 The test file and the reference package are copied, as they are, into oracle/_ref/pytests by oracle/Makefile in the dev
-container (git-ignored, travels to the GPU box like the compiled reference); tests/shim/xs_refsuite_plugin.py deselects
-test_2d and sub-samples test_sphere's 500 k-normal loop."""
+container (git-ignored, travels to the GPU box like the compiled reference); tests/shim/xs_refsuite_plugin.py sub-samples
+test_sphere's 500 k-normal loop and deselects test_2d for the shim run only (there the reference's own pure-Python twod.py
+would run, on the CPU, and needs cc3d); through the package test_2d runs on the device (xs_twod.cu)."""
 import os
 import subprocess
 import sys
