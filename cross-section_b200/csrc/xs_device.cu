@@ -428,18 +428,18 @@ __global__ void __launch_bounds__(256) ingest_c_tma_kernel(const __grid_constant
     for (int k = 0; k < 8; k++) {
       const int idx = threadIdx.x + 256 * k, row = idx >> 4, seg = idx & 15;      // box layout: [x 64][y 2][z 256] = 128 rows of 256 bytes
       const uint4 q = src[idx];
-      const uint32_t w[4] = { q.x, q.y, q.z, q.w };
-      uint32_t m16 = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        // bit 7 of every byte <- byte != 0 (== want in EQ mode); then the four flags to bits 0..3 with one multiply
-        const uint32_t x = EQ ? (w[j] ^ want4) : w[j];
-        uint32_t nz = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
-        if (EQ) nz ^= 0x80808080u;
-        m16 |= (((nz >> 7) * 0x01020408u) >> 24) << (4 * j);
-      }
-      rows[row][2 * seg] = (uint8_t)m16;
-      rows[row][2 * seg + 1] = (uint8_t)(m16 >> 8);
+      // bit 7 of every byte <- byte != 0 (== want in EQ mode): three logic / add operations per four voxels; the flags are
+      // then gathered by the byte dot product (IDP.4A) with the weights 1 2 4 8 | 16 32 64 128: eight voxels -> 128 x their
+      // bit row, two instructions instead of a shift, a multiply, a shift and an OR per four voxels
+      auto flag4 = [&](uint32_t x) -> uint32_t {
+        if (EQ) x ^= want4;
+        const uint32_t t = (x & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+        return EQ ? (~(t | x) & 0x80808080u) : ((t | x) & 0x80808080u);
+      };
+      const uint32_t lo = __dp4a(flag4(q.y), 0x80402010u, __dp4a(flag4(q.x), 0x08040201u, 0u));
+      const uint32_t hi = __dp4a(flag4(q.w), 0x80402010u, __dp4a(flag4(q.z), 0x08040201u, 0u));
+      rows[row][2 * seg] = (uint8_t)(lo >> 7);
+      rows[row][2 * seg + 1] = (uint8_t)(hi >> 7);
     }
     __syncthreads();
     if (bx0 + bxl < hx) {
