@@ -41,6 +41,7 @@ ANISOTROPY = (32.0, 32.0, 40.0)
 METRIC = "cross-sections/sec (batched skeleton vertices, 512^3 vol)"
 WORKLOAD = "neurite512_sweep10k"
 SUSTAINED_SWEEPS = 200
+E2E_MIN_STEPS = 100          # steps of the pipelined end-to-end loop per timed region (>= --steps)
 # the same `config` object in both arms (the driver compares them key by key)
 CONFIG = {"workload": WORKLOAD, "volume": [VOLUME_N] * 3, "queries_per_step": QUERIES, "anisotropy": list(ANISOTROPY)}
 
@@ -114,16 +115,48 @@ def run_reference_arm(args):
 
 # ------------------------------------------------------------------------------------------------ GPU arm
 class ClockSampler:
-  """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+  """SM clock and throttle reasons sampled while the timed regions run.  In-process NVML (one nvmlInit, then three cheap
+  queries every 50 ms): a looping `nvidia-smi -lms 100` process took seconds per sample on the bench boxes and, hammering
+  the driver the whole time, slowed the host-bound end-to-end loop by 25 % (1.08 against 0.86 ms per step; it is the
+  fallback when the NVML binding is missing)."""
   Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+  REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
   def __init__(self, index):
     self.index, self.rows, self.proc = index, [], None
+    self.sm, self.mx, self.reasons, self.how = [], 0, set(), None
+    self._stop = threading.Event()
+    self._thread = None
 
   def start(self):
     try:
+      import pynvml
+      pynvml.nvmlInit()
+      h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+      self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+      get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+      def poll():
+        while not self._stop.is_set():
+          try:
+            self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+            mask = int(get_reasons(h))
+            for name, bit in self.REASONS:
+              if mask & bit:
+                self.reasons.add(name)
+          except Exception:
+            pass
+          self._stop.wait(0.05)
+      self.how = "nvml"
+      self._thread = threading.Thread(target=poll, daemon=True)
+      self._thread.start()
+      return
+    except Exception:
+      self.how = None
+    try:
       self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+      self.how = "nvidia-smi"
       threading.Thread(target=self._read, daemon=True).start()
     except Exception:
       self.proc = None
@@ -133,9 +166,12 @@ class ClockSampler:
       self.rows.append([x.strip() for x in line.split(",")])
 
   def stop(self):
+    self._stop.set()
+    if self._thread is not None:
+      self._thread.join(1.0)
     if self.proc:
       self.proc.terminate()
-    sm, mx, reasons = [], 0, set()
+    sm, mx, reasons = list(self.sm), self.mx, set(self.reasons)
     for r in self.rows:
       try:
         sm.append(float(r[1])); mx = max(mx, float(r[2]))
@@ -144,7 +180,7 @@ class ClockSampler:
             reasons.add(name)
       except Exception:
         pass
-    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm), "source": self.how}
 
 
 def slice_record(args, V0, world, rank, local, dev, barrier):
@@ -467,7 +503,9 @@ def run_own_arm(args):
   ms_e2e_res = time_steps(step_e2e_resident)
 
   import threading as _th
-  psteps = max(2, args.steps)
+  # the pipelined loop is timed over at least E2E_MIN_STEPS steps: its first step has no sweep to hide the packing of
+  # image 0 behind (one extra packing time per timed region: +5 % over 20 steps, +1 % over 100)
+  psteps = max(E2E_MIN_STEPS, args.steps)
   staged_mode = world > 1 or not os.environ.get("XS_BENCH_TWO_HANDLES")
   if not staged_mode:
     # ---- the same end-to-end step, pipelined across sweeps: two resident-volume handles on their own streams,
@@ -620,7 +658,7 @@ def run_own_arm(args):
     "rank_checks": rank_checks,
     "slices": slices,
     "e2e": {"value": e2e_value, "unit": "cross-sections/s", "h2d_bytes_per_step": int(h2d_volume + world * 2 * pos.nbytes),
-            "d2h_bytes_per_step": int(world * QUERIES * 5), "ms_per_step": ms_pipe / psteps,
+            "d2h_bytes_per_step": int(world * QUERIES * 5), "ms_per_step": ms_pipe / psteps, "steps": psteps,
             "host_input_bytes_per_step": int(vol.size + world * 2 * pos.nbytes),
             "upload": (f"bit-packed on {pack_threads} host threads{' of rank 0' if world > 1 else ''} (xs_hostpack.cpp): the 128 MiB boolean image is read once by the host cores, 16 MiB cross PCIe"
                        if (packed or staged_mode) else "plain bytes (too few host threads for the bit-packed upload)"),
