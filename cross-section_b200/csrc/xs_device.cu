@@ -2607,6 +2607,14 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(rec_t(v->evs[1], s2));
       CK(cudaEventRecord(v->evf[4], s2));
       CK(rec_t(v->evs[5], s2));
+      // (dev knob XS3D_P2_EARLY=1: a P2 chain right here, for the sections the first launch parked, beside the end of the warp
+      //  tier instead of behind the late hand-overs.  Measured on B200: no gain — the chain takes issue slots from the warp
+      //  tier's last queries, 0.435 instead of 0.418 ms, and the step stays at 0.69 ms: profiles/r2t_negative_results.txt)
+      static const bool p2_early = getenv("XS3D_P2_EARLY") != nullptr;
+      if (p2_early) {
+        a.out = out2; a.done_list = done2;
+        RET(launch_p2(s2));
+      }
       // profiling aid: under ncu every kernel runs alone, so the split of the warp tier into grids A and B would show
       // grid B (10 warps per SM) doing all the work; XS3D_SINGLE_GRID=1 launches the warp tier as one grid of 3 CTAs per SM
       const bool single_grid = getenv("XS3D_SINGLE_GRID") != nullptr;

@@ -53,7 +53,28 @@ def barrier():
   if world > 1:
     dist.barrier(); torch.cuda.synchronize()
 sweep(0); ref_a = harea.numpy().copy(); ref_c = hct.numpy().copy()
-feed = xdist.SharedVolumeFeed(V) if mode == "shared" else xdist.VolumeFeed(V)
+TRACE = os.environ.get("XS_TRACE")
+tlog = {"pack": [], "sweep": [], "gap": [], "bcast_enq": [], "status_wait": []}
+_last_end = [None]
+class TracedFeed(xdist.VolumeFeed):
+  """host-side timeline (XS_TRACE=1): how long the packing, the enqueue of a broadcast, the wait for a broadcast's
+  status and the sweeps take, and how long the main thread sits between two sweeps"""
+  def pack_and_stage(self, image, slot):
+    t0 = time.perf_counter(); super().pack_and_stage(image, slot); tlog["pack"].append(time.perf_counter() - t0)
+  def bcast_status(self, slot, value, src, group):
+    t0 = time.perf_counter(); super().bcast_status(slot, value, src, group); tlog["bcast_enq"].append(time.perf_counter() - t0)
+  def read_status(self, slot, wait=True):
+    t0 = time.perf_counter(); r = super().read_status(slot, wait)
+    if wait: tlog["status_wait"].append(time.perf_counter() - t0)
+    return r
+feed = xdist.SharedVolumeFeed(V) if mode == "shared" else (TracedFeed(V) if TRACE else xdist.VolumeFeed(V))
+if TRACE:
+  _sweep = sweep
+  def sweep(k):
+    t0 = time.perf_counter()
+    if _last_end[0] is not None: tlog["gap"].append(t0 - _last_end[0])
+    _sweep(k)
+    _last_end[0] = time.perf_counter(); tlog["sweep"].append(_last_end[0] - t0)
 def run(n):
   if mode == "shared":
     xdist.stream_shared_volumes(V, [img] * n, n, sweep, before_step=lambda k: flush.fill_(k & 255), feed=feed)
@@ -75,6 +96,12 @@ ok = np.array_equal(harea.numpy().view(np.uint32), ref_a.view(np.uint32)) and np
 oks = torch.tensor([int(ok)], device=dev)
 if world > 1:
   dist.all_reduce(oks, op=dist.ReduceOp.MIN)
+if TRACE:
+  tm = V.timing()
+  for r in range(world):
+    if world > 1: dist.barrier()
+    if r == rank:
+      print("rank %d host timeline (median / p90 ms): " % rank + " | ".join("%s %.3f / %.3f (n=%d)" % (k, np.median(v) * 1e3, np.percentile(v, 90) * 1e3, len(v)) for k, v in tlog.items() if v) + " || last sweep on the GPU: " + " ".join("%s %.3f" % (k.replace("_ms", ""), tm[k]) for k in ("prepass_ms", "warp_tier_ms", "mid_tier_ms", "mid_exposed_ms", "polygon_ms", "combine_ms", "p2_ms") if k in tm), flush=True)
 if rank == 0:
   print("mode %-6s N=%d threads/rank %s: e2e ms/step %s -> %.1f M xs/s ; results identical on every rank: %s" % (
       mode, world, os.environ.get("XS3D_HOST_THREADS"), " ".join("%.3f" % r for r in res), world * 10000 / min(res) / 1e3, bool(int(oks[0]))), flush=True)
