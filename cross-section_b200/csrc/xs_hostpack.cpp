@@ -22,6 +22,9 @@
 #if defined(__linux__)
 #include <sched.h>
 #include <pthread.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 #endif
 
 namespace {
@@ -172,6 +175,16 @@ class Pool {
     return true;
   }
   void loop() {
+#if defined(__linux__)
+    // The workers yield to the caller's other threads: the thread that launches and waits for the sweeps must not lose its
+    // core to a packer for a scheduler tick (on a 16-core host with 14 packers its sweep call took 0.81 ms at the median
+    // and 1.5 ms at the 90th percentile, 0.75 / 0.77 ms with 8 packers).  Per-thread nice value (Linux: setpriority on the
+    // thread id); XS3D_POOL_NICE overrides, 0 switches it off.
+    {
+      static const int nice_by = getenv("XS3D_POOL_NICE") ? atoi(getenv("XS3D_POOL_NICE")) : 10;
+      if (nice_by > 0) setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), nice_by);
+    }
+#endif
     uint64_t seen = 0;
     for (;;) {
       const uint8_t* in; uint8_t* out; size_t lo, hi;
