@@ -544,9 +544,25 @@ def run_own_arm(args):
     outs = None
 
     def run_e2e(nsteps):
-      xdist.stream_volumes(V, [vol] * nsteps if rank == 0 else None, nsteps, lambda k: step_e2e_resident(),
-                           before_step=lambda k: flush.fill_(k & 255),      # L2 eviction before every sweep (inside the timed region)
-                           feed=feed)
+      # L2 eviction before every sweep, on the sweep's stream, inside the timed region: the write for step 0 is enqueued by
+      # before_step, the write for step k+1 by the library's after-enqueue hook during step k's call — behind sweep k's
+      # kernels and result copies — so that the GPU runs it while the host is on its way back with the results of step k
+      # (the host waits for an event behind the result copies, not for the stream).  One write per sweep either way.
+      done = [0]
+
+      def evict_for_next_step():
+        done[0] += 1
+        if done[0] < nsteps:
+          flush.fill_(done[0] & 255)
+      hook = not os.environ.get("XS_BENCH_NO_HOOK")
+      if hook:
+        V.set_after_enqueue(evict_for_next_step)
+      try:
+        xdist.stream_volumes(V, [vol] * nsteps if rank == 0 else None, nsteps, lambda k: step_e2e_resident(),
+                             before_step=(lambda k: flush.fill_(0) if k == 0 else None) if hook else (lambda k: flush.fill_(k & 255)),
+                             feed=feed)
+      finally:
+        V.set_after_enqueue(None)
     e2e_mode = ("one volume in host memory, taken afresh every step: rank 0 bit-packs and uploads it (double-buffered: image k+1 is packed and copied beside the sweep of image k) and ingests it, "
                 + ("the 16 MiB occupancy bytes are NCCL-broadcast, " if world > 1 else "") + "every rank sweeps its own 10 000 host-resident queries and reads its results back")
 

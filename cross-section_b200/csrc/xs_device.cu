@@ -1769,6 +1769,9 @@ struct xs3d_volume {
   bool own_stream = true;
   cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_block = nullptr;    // blocking host wait (XS3D_BLOCKING_SYNC)
+  cudaEvent_t ev_done = nullptr;     // recorded behind a batch's result copies: the host waits for THIS, not for the stream
+  void (*after_enqueue)(void*) = nullptr;   // xs3d_volume_set_after_enqueue
+  void* after_enqueue_ctx = nullptr;
   float timing[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // ms, see xs3d_volume_timing
   int timing_pending = 0;   // 1: batch events not yet read, 2: same for a tiny (`single`) batch
 };
@@ -2757,7 +2760,17 @@ static int area_batch_device(xs3d_volume* v, uint64_t n, const float* d_pos, con
       CK(cudaGraphLaunch(hit->exec, s1));
     }
     trace(v, "launched");
-    CK(host_wait(v, s1));
+    if (v->after_enqueue && !use_graph) {
+      // the caller enqueues follow-up work on the launching stream now (e.g. the uploads — or, in bench.py, the L2-evicting
+      // write — of its NEXT step): it runs on the GPU right behind this batch, while the host is still on its way back with
+      // this batch's results.  The host therefore waits for an event behind the result copies, not for the whole stream.
+      if (!v->ev_done) CK(cudaEventCreateWithFlags(&v->ev_done, cudaEventDisableTiming));
+      CK(cudaEventRecord(v->ev_done, s1));
+      v->after_enqueue(v->after_enqueue_ctx);
+      CK(cudaEventSynchronize(v->ev_done));
+    } else {
+      CK(host_wait(v, s1));
+    }
     trace(v, "synced");
     v->timing_pending = single ? 2 : 1;   // event durations are read on demand (xs3d_volume_timing): ten driver calls off the hot path
     v->timing[3] = 0.0f;
@@ -2975,6 +2988,16 @@ extern "C" int xs3d_volume_timing(xs3d_volume* v, float ms[12]) {
     }
   }
   for (int i = 0; i < 12; i++) ms[i] = v->timing[i];
+  return XS3D_OK;
+}
+
+// `fn(ctx)` is called by xs3d_area_batch / xs3d_area_sweep_host on the calling thread once a batch — kernels and result
+// copies — is enqueued, before the host waits for it: work the callback enqueues on the volume's stream runs right behind
+// the batch, and does not delay the batch's results (the host waits for an event recorded before the callback).  null: off.
+extern "C" int xs3d_volume_set_after_enqueue(xs3d_volume* v, void (*fn)(void*), void* ctx) {
+  if (!v) return fail(XS3D_ERR_ARG, "null volume");
+  v->after_enqueue = fn;
+  v->after_enqueue_ctx = ctx;
   return XS3D_OK;
 }
 

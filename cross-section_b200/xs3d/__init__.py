@@ -272,6 +272,17 @@ class Volume:
     _abi.check(self._lib.xs3d_volume_mark_staged(self._h, int(slot), C.c_void_p(int(cuda_stream))))
 
   # -- one host image that every rank can read: each rank packs and uploads its part (xs3d.dist.stream_shared_volumes)
+  def set_after_enqueue(self, fn):
+    """`fn()` (or None) is called by every batched area call once the batch — kernels and result copies — is enqueued and
+    before the host waits for it: what it enqueues on the volume's stream (the next step's uploads, ...) runs right
+    behind the batch without delaying this batch's results."""
+    if fn is None:
+      self._after_cb = None
+      _abi.check(self._lib.xs3d_volume_set_after_enqueue(self._h, None, None))
+      return
+    self._after_cb = C.CFUNCTYPE(None, C.c_void_p)(lambda _ctx: fn())      # kept alive with the volume
+    _abi.check(self._lib.xs3d_volume_set_after_enqueue(self._h, C.cast(self._after_cb, C.c_void_p), None))
+
   def staged_bits(self, slot=0, min_bytes=0):
     """(device pointer, bytes of the image's bit stream) of the bit buffer of `slot`, at least `min_bytes` long."""
     p = C.c_void_p()

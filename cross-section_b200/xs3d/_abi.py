@@ -19,7 +19,7 @@ SYMBOLS = [
   "xs3d_last_error", "xs3d_version", "xs3d_device_count",
   "xs3d_volume_create", "xs3d_volume_destroy", "xs3d_volume_load", "xs3d_pack_bits", "xs3d_volume_load_packed", "xs3d_volume_stage_packed", "xs3d_volume_pack_and_stage", "xs3d_volume_commit_staged", "xs3d_volume_staged_cubes", "xs3d_volume_wait_staged", "xs3d_volume_mark_staged", "xs3d_volume_staged_bits", "xs3d_volume_pack_and_stage_part", "xs3d_volume_wait_staged_bits", "xs3d_volume_ingest_staged", "xs3d_volume_load_labels",
   "xs3d_volume_select_label", "xs3d_volume_cubes", "xs3d_volume_mark_loaded", "xs3d_volume_shape",
-  "xs3d_area_batch", "xs3d_area_sweep_host", "xs3d_volume_stats", "xs3d_volume_profile", "xs3d_volume_timing", "xs3d_volume_set_stream",
+  "xs3d_area_batch", "xs3d_area_sweep_host", "xs3d_volume_stats", "xs3d_volume_profile", "xs3d_volume_timing", "xs3d_volume_set_stream", "xs3d_volume_set_after_enqueue",
   "xs3d_area", "xs3d_area_2d", "xs3d_section", "xs3d_section_sparse", "xs3d_projection", "xs3d_projection_batch", "xs3d_projection_plan", "xs3d_projection_fill",
   "xs3d_volume_labels_buffer", "xs3d_skeleton_tangents",
   "xs3d_set_shape", "xs3d_set_shape_image", "xs3d_clear_shape",
@@ -75,6 +75,7 @@ def lib():
   L.xs3d_volume_profile.argtypes = [vp, C.POINTER(u64)]
   L.xs3d_volume_timing.argtypes = [vp, fp]
   L.xs3d_volume_set_stream.argtypes = [vp, vp]
+  L.xs3d_volume_set_after_enqueue.argtypes = [vp, vp, vp]
   L.xs3d_area.argtypes = [vp, u64, u64, u64, fp, fp, fp, C.c_int, C.c_int, fp, u8p]
   L.xs3d_section.argtypes = [vp, u64, u64, u64, fp, fp, fp, C.c_int, vp, u8p]
   L.xs3d_section_sparse.argtypes = [vp, fp, fp, fp, C.c_int, vp, vp, u64, C.POINTER(u64), u8p]

@@ -138,6 +138,11 @@ int xs3d_volume_timing(xs3d_volume* vol, float ms[12]);
 /* Launch on the caller's stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream) instead of the
  * volume's own, so the caller's CUDA events bracket the work.  The stream must outlive the volume. */
 int xs3d_volume_set_stream(xs3d_volume* vol, void* cuda_stream);
+/* Pipelining hook for callers that stream batches: `fn(ctx)` is called on the calling thread by xs3d_area_batch /
+ * xs3d_area_sweep_host once a batch (kernels + result copies) is enqueued, before the host waits for it.  Whatever the
+ * callback enqueues on the volume's stream (the uploads of the caller's next step, ...) runs right behind the batch and does
+ * not delay this batch's results: the host waits for an event recorded before the callback.  fn == NULL switches it off. */
+int xs3d_volume_set_after_enqueue(xs3d_volume* vol, void (*fn)(void*), void* ctx);
 
 /* ---- drop-in single-call entry points: one per fastxs3d export ------------------------------------- */
 /* fastxs3d.area (fastxs3d.cpp:82-117).  `binimg` is always the image that is evaluated (it is uploaded on every

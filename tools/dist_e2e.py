@@ -75,7 +75,20 @@ if TRACE:
     if _last_end[0] is not None: tlog["gap"].append(t0 - _last_end[0])
     _sweep(k)
     _last_end[0] = time.perf_counter(); tlog["sweep"].append(_last_end[0] - t0)
+HOOK = os.environ.get("HOOK")
 def run(n):
+  if HOOK and mode != "shared":
+    # the L2-evicting write of step k+1 enqueued by the library's after-enqueue hook during step k's call (as bench.py does)
+    done = [0]
+    def nxt():
+      done[0] += 1
+      if done[0] < n: flush.fill_(done[0] & 255)
+    V.set_after_enqueue(nxt)
+    try:
+      xdist.stream_volumes(V, [img] * n if rank == 0 else None, n, sweep, before_step=lambda k: flush.fill_(0) if k == 0 else None, feed=feed)
+    finally:
+      V.set_after_enqueue(None)
+    return
   if mode == "shared":
     xdist.stream_shared_volumes(V, [img] * n, n, sweep, before_step=lambda k: flush.fill_(k & 255), feed=feed)
   else:
