@@ -816,3 +816,34 @@ def test_twod_path_matches_reference(xs):
   import twod_oracle
   oa, oc = twod_oracle.cross_sectional_area_2d(big, [700.25, 500.5], [0.3, 1.0], [4, 40])
   assert a == oa and c == oc
+
+
+def test_after_enqueue_hook(xs, oracle):
+  """xs3d_volume_set_after_enqueue: the callback runs once per batch, behind the enqueue and before the host wait; work it
+  puts on the volume's stream (here: a write over a scratch tensor and a marker) does not change or delay the results."""
+  import torch
+  from xs3d import synthetic
+  vol, verts, tans = synthetic.make_neurite(96, seed=3, n_branches=3)
+  pos, nrm = synthetic.draw_queries(verts, tans, 500, seed=2)
+  w = [32, 32, 40]
+  oa, oc = oracle.area_batch(vol, pos, nrm, w)
+  st = torch.cuda.Stream()
+  scratch = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
+  calls = []
+  with torch.cuda.stream(st):
+    with xs.Volume(vol) as V:
+      V.set_stream(st.cuda_stream)
+
+      def hook():
+        calls.append(len(calls))
+        scratch.fill_(len(calls))            # enqueued on `st`, behind the batch
+      V.set_after_enqueue(hook)
+      a1, c1 = V.cross_sectional_area_batch(pos, nrm, w, return_contact=True)
+      a2, c2 = V.cross_sectional_area_batch(pos[:7], nrm[:7], w, return_contact=True)
+      V.set_after_enqueue(None)
+      a3, c3 = V.cross_sectional_area_batch(pos, nrm, w, return_contact=True)
+      st.synchronize()
+  assert calls == [0, 1] and int(scratch[0]) == 2
+  for a, c in ((a1, c1), (a3, c3)):
+    assert np.array_equal(bits(a), bits(oa)) and np.array_equal(c, oc)
+  assert np.array_equal(bits(a2), bits(oa[:7])) and np.array_equal(c2, oc[:7])
