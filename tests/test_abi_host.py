@@ -60,6 +60,16 @@ def test_input_validation_matches_reference():
         fn(ok, [0, 0, 0], [0, 0, 1], bad)
     with pytest.raises(ValueError):
       fn(np.ones([3, 3, 3, 3], dtype=bool, order="F"), [0, 0, 0], [0, 0, 1], [1, 1, 1])
+  # 2-D images (xs3d/__init__.py:59-80): same checks, before the device is touched
+  img2 = np.ones([3, 3], dtype=bool)
+  with pytest.raises(ValueError):
+    xs3d.cross_sectional_area(img2.astype(np.uint8), [1, 1], [0, 1])
+  with pytest.raises(ValueError):
+    xs3d.cross_sectional_area(img2, [1, 1], [0, 0])
+  with pytest.raises(ValueError):
+    xs3d.cross_sectional_area(img2, [1, 1], [0, 1], [1, -1])
+  with pytest.raises(ValueError):
+    xs3d.cross_sectional_area(img2, [1, 1, 1], [0, 1, 0], [1, 1, 1])
   with pytest.raises(ValueError):
     xs3d.slice(labels, [0, 0, 0], [0, 0, 0])
   with pytest.raises(ValueError):
