@@ -661,7 +661,7 @@ def run_own_arm(args):
                                     "frac": vol.size * (0.25 if packed else 1.125) / (ingest_e2e_ms / 1000.0) / 1e9 / peak if ingest_e2e_ms > 0 else None}}
 
   # ---- CPU baseline on this box's host cores (bounded: a few passes of the same sweep)
-  rate, cores, kind, times = cpu_sweep_rate(vol, pos, nrm, passes=3, warm=1)
+  rate, cores, kind, times = cpu_sweep_rate(vol, pos, nrm, passes=10, warm=2)    # ~15-25 core-seconds; the reference arm runs --steps passes
   line = {
     "metric": METRIC, "value": value, "unit": "cross-sections/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
     "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
