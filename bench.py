@@ -11,7 +11,10 @@ queries of the skeleton sweep against the 512^3 neurite volume.
           queries from pinned host memory (xs3d_pack_bits packs the volume on the host cores, 16 MiB cross PCIe;
           the packing + upload of step k+1 run beside the sweep of step k), ingests, sweeps, and reads areas +
           contact bits back.  N > 1: ONE host volume — rank 0 packs / uploads / ingests, the occupancy bytes are
-          NCCL-broadcast every step, every rank sweeps its own queries.
+          NCCL-broadcast every step, every rank sweeps its own queries.  Timed over >= 100 steps (pipeline fill
+          amortised); every sweep is preceded, on its stream and inside the timed region, by an L2-evicting write
+          (enqueued behind the previous sweep through xs3d_volume_set_after_enqueue).
+  clocks : SM clock / throttle reasons sampled by an in-process NVML thread while the timed regions run.
   roofline     : the dominant kernel (warp-tier query kernel), algorithmic bytes / CUDA-event duration vs the
                  measured HBM peak (MEASURED_PEAKS.json).  The mid / big tiers run beside it on a second stream.
   cpu_baseline : the compiled reference (oracle/_ref, else the C port) fanned out over all host cores.
